@@ -1,0 +1,268 @@
+// Host-side dictionary flattening (see builder.hpp).
+#include "builder.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "java_char_tables.h"
+
+namespace acgpu {
+
+namespace {
+
+uint16_t g_lower[65536];
+std::once_flag g_lower_once;
+
+// Growable (parent, class) -> child map used only while inserting keywords.
+struct EdgeMap {
+    std::vector<Edge> slots;
+    uint32_t mask = 0;
+    uint64_t count = 0;
+
+    EdgeMap() { resize(1u << 12); }
+
+    void resize(uint32_t n) {
+        std::vector<Edge> old;
+        old.swap(slots);
+        slots.assign(n, Edge{kNone, 0, 0, 0});
+        mask = n - 1;
+        for (const Edge &e : old) {
+            if (e.parent != kNone) put(e);
+        }
+    }
+    void put(const Edge &e) {
+        uint32_t i = edge_hash(e.parent, e.cls) & mask;
+        while (slots[i].parent != kNone) i = (i + 1) & mask;
+        slots[i] = e;
+    }
+    // returns child id, creating it (id = next_node++) when absent
+    uint32_t get_or_add(uint32_t parent, uint32_t c, uint32_t &next_node, bool &created) {
+        uint32_t i = edge_hash(parent, c) & mask;
+        while (slots[i].parent != kNone) {
+            if (slots[i].parent == parent && slots[i].cls == c) {
+                created = false;
+                return slots[i].child;
+            }
+            i = (i + 1) & mask;
+        }
+        if ((count + 1) * 2 > slots.size()) {
+            resize(static_cast<uint32_t>(slots.size() * 2));
+            i = edge_hash(parent, c) & mask;
+            while (slots[i].parent != kNone) i = (i + 1) & mask;
+        }
+        slots[i] = Edge{parent, c, next_node, 0};
+        ++count;
+        created = true;
+        return next_node++;
+    }
+};
+
+std::string utf8_of(const uint16_t *s, int32_t len) {
+    std::string out;
+    for (int32_t i = 0; i < len; i++) {
+        uint32_t c = s[i];
+        if (c < 0x80 && c != 0) {
+            out.push_back(static_cast<char>(c));
+        } else if (c < 0x800) {
+            out.push_back(static_cast<char>(0xC0 | (c >> 6)));
+            out.push_back(static_cast<char>(0x80 | (c & 0x3F)));
+        } else {
+            out.push_back(static_cast<char>(0xE0 | (c >> 12)));
+            out.push_back(static_cast<char>(0x80 | ((c >> 6) & 0x3F)));
+            out.push_back(static_cast<char>(0x80 | (c & 0x3F)));
+        }
+    }
+    return out;
+}
+
+}  // namespace
+
+const uint16_t *java_lower_table() {
+    std::call_once(g_lower_once, [] { java_fill_lower_table(g_lower); });
+    return g_lower;
+}
+
+void make_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, int32_t n, uint8_t *out) {
+    std::memset(out, 0, 65536);
+    if (mode == 0 || mode == 2) {
+        out['-'] = 1;
+        out['_'] = 1;
+        for (uint32_t c = 0; c < 65536; c++) {
+            if (java_is_letter_or_digit(static_cast<uint16_t>(c))) out[c] = 1;
+        }
+    }
+    if (mode == 1) {
+        for (int32_t i = 0; i < n; i++) out[chars[i]] = 1;
+    } else if (mode == 2) {
+        for (int32_t i = 0; i < n; i++) out[chars[i]] = toggles[i] ? 1 : 0;
+    }
+}
+
+HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *offsets, const uint8_t *is_null,
+                              int64_t n_keywords, int64_t n_values, bool case_sensitive,
+                              const uint8_t *word_chars) {
+    if (family < 0 || family > 3) throw std::invalid_argument("unknown matcher family");
+    const uint16_t *lower = java_lower_table();
+    HostAutomaton a;
+    a.family = family;
+    a.is_map = n_values >= 0;
+    a.case_sensitive = case_sensitive;
+    a.reversed = (family == 0);
+
+    // Maps zip keywords with values and stop at the shorter (AhoCorasickMap.java:32).
+    int64_t n = n_keywords;
+    if (a.is_map && n_values < n) n = n_values;
+
+    std::vector<uint8_t> wc;
+    if (family == 3) {
+        wc.resize(65536);
+        if (word_chars) {
+            std::memcpy(wc.data(), word_chars, 65536);
+        } else {
+            make_word_chars(0, nullptr, nullptr, 0, wc.data());
+        }
+        a.wordbits.assign(2048, 0);
+        for (uint32_t c = 0; c < 65536; c++) {
+            if (wc[c]) a.wordbits[c >> 5] |= 1u << (c & 31);
+        }
+        if (!case_sensitive) {
+            // Quirk Q7 (WholeWordMatchSet.java:96-101 vs :113,118): the reference tests the lower-cased
+            // char in the first word-char check but the raw char when scrolling.  The two views agree
+            // (and the "maximal run of word chars" formulation is exact) iff the table is closed under
+            // toLowerCase, which holds for the default table and every toggle of caseless chars.
+            for (uint32_t c = 0; c < 65536; c++) {
+                if (wc[c] != wc[lower[c]]) {
+                    throw std::domain_error(
+                        "case-insensitive WholeWord matcher with a word-character table that is not closed under "
+                        "Character.toLowerCase is not implemented on the GPU path (reference quirk Q7)");
+                }
+            }
+        }
+    }
+
+    // ---- effective keywords: (begin, len, entry index) into `chars`, after trim / skip rules
+    struct Kw {
+        int64_t begin;
+        int32_t len;
+        int64_t entry;
+    };
+    std::vector<Kw> kws;
+    kws.reserve(static_cast<size_t>(n));
+    int32_t longest = 0;
+    std::vector<uint8_t> used(65536, 0);
+    for (int64_t k = 0; k < n; k++) {
+        if (is_null && is_null[k]) continue;
+        int64_t b = offsets[k];
+        int32_t len = static_cast<int32_t>(offsets[k + 1] - offsets[k]);
+        if (family == 3) {
+            // WordCharacters.trim (WordCharacters.java:41-62) then validation (WholeWordMatchSet.java:147-153)
+            int32_t ws = 0, we = len;
+            for (int32_t i = 0; i < len; i++) {
+                if (wc[chars[b + i]]) {
+                    ws = i;
+                    break;
+                }
+            }
+            for (int32_t i = len - 1; i >= 0; i--) {
+                if (wc[chars[b + i]]) {
+                    we = i + 1;
+                    break;
+                }
+            }
+            b += ws;
+            len = we - ws;
+            for (int32_t i = 0; i < len; i++) {
+                if (!wc[chars[b + i]]) {
+                    throw IllegalArgument(utf8_of(chars + b, len) + " contains non-word characters.");
+                }
+            }
+        }
+        if (len > longest) longest = len;
+        if (len <= 0) continue;
+        kws.push_back(Kw{b, len, k});
+        for (int32_t i = 0; i < len; i++) {
+            uint16_t c = chars[b + i];
+            used[case_sensitive ? c : lower[c]] = 1;
+        }
+    }
+    a.max_len = longest;
+    a.char_buffer_size = longest > 2048 ? longest * 2 : 4096;
+    a.n_keywords_effective = static_cast<int64_t>(kws.size());
+
+    // ---- character classes
+    uint32_t distinct = 0;
+    for (uint32_t c = 0; c < 65536; c++) distinct += used[c];
+    a.has_other = distinct < 65536;
+    std::vector<uint16_t> class_of(65536, 0);
+    uint32_t next_class = a.has_other ? 1 : 0;
+    for (uint32_t c = 0; c < 65536; c++) {
+        if (used[c]) class_of[c] = static_cast<uint16_t>(next_class++);
+    }
+    a.n_classes = static_cast<int32_t>(next_class < 1 ? 1 : next_class);
+    a.cls.resize(65536);
+    for (uint32_t c = 0; c < 65536; c++) {
+        uint16_t f = case_sensitive ? static_cast<uint16_t>(c) : lower[c];
+        a.cls[c] = class_of[f];  // 0 ("other") when f is in no keyword and has_other
+    }
+
+    // ---- trie over class strings
+    EdgeMap map;
+    uint32_t next_node = 1;  // node 0 = root
+    std::vector<uint8_t> info(1, 0);
+    std::vector<uint32_t> value(1, kNone);
+    std::vector<uint32_t> depth_count(static_cast<size_t>(longest) + 1, 0);
+    depth_count[0] = 1;
+    const bool first_wins = (family == 2);  // ShortestMatchMap.java:44-54
+    for (const Kw &kw : kws) {
+        uint32_t node = 0;
+        for (int32_t i = 0; i < kw.len; i++) {
+            uint16_t raw = chars[kw.begin + (a.reversed ? (kw.len - 1 - i) : i)];
+            uint32_t c = a.cls[raw];
+            bool created = false;
+            uint32_t child = map.get_or_add(node, c, next_node, created);
+            if (created) {
+                info.push_back(0);
+                value.push_back(kNone);
+                info[node] |= kInfoHasChildren;
+                depth_count[static_cast<size_t>(i) + 1]++;
+                if (next_node == kNone) throw std::length_error("dictionary too large (node ids exceed 32 bits)");
+            }
+            node = child;
+        }
+        if (!(first_wins && (info[node] & kInfoTerminal))) {
+            value[node] = a.is_map ? static_cast<uint32_t>(kw.entry) : kNone;
+        }
+        info[node] |= kInfoTerminal;
+    }
+    a.n_nodes = next_node;
+    a.node_info.swap(info);
+    a.node_value.swap(value);
+    a.depth_count.swap(depth_count);
+
+    // ---- device tables: direct root table + hashed deeper edges
+    a.root.assign(static_cast<size_t>(a.n_classes), RootEdge{kNone, 0});
+    uint64_t deep_edges = 0;
+    for (const Edge &e : map.slots) {
+        if (e.parent == kNone) continue;
+        if (e.parent == 0) {
+            a.root[e.cls] = RootEdge{e.child, a.node_info[e.child]};
+        } else {
+            ++deep_edges;
+        }
+    }
+    uint64_t cap = 16;
+    while (cap < deep_edges * 2) cap <<= 1;
+    if (cap > (1ull << 31)) throw std::length_error("dictionary too large for the edge table");
+    a.edges.assign(static_cast<size_t>(cap), Edge{kNone, 0, 0, 0});
+    a.edge_mask = static_cast<uint32_t>(cap - 1);
+    for (const Edge &e : map.slots) {
+        if (e.parent == kNone || e.parent == 0) continue;
+        uint32_t i = edge_hash(e.parent, e.cls) & a.edge_mask;
+        while (a.edges[i].parent != kNone) i = (i + 1) & a.edge_mask;
+        a.edges[i] = Edge{e.parent, e.cls, e.child, a.node_info[e.child]};
+    }
+    return a;
+}
+
+}  // namespace acgpu

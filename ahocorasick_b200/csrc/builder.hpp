@@ -1,0 +1,81 @@
+// Host-side dictionary flattening for libacgpu.so.
+//
+// Replaces the reference's constructors (object-graph tries of HashmapNode/RangeNode with fail
+// links, e.g. AhoCorasickSet.java:16-191) by flat, upload-once tables:
+//   * cls[65536]   UTF-16 code unit -> character class, with Character.toLowerCase folded in
+//                  when case-insensitive (AhoCorasickSet.java:33,229); class 0 = "in no keyword"
+//   * an anchored trie over class strings, stored as a direct root table plus an open-addressing
+//     edge table  (parent, class) -> (child, flags)   in 16-byte slots
+//   * per-node value index (Q6 rules: last duplicate wins; first wins for ShortestMatchMap)
+//   * dense DFA / shared-memory tiers are derived from this trie by later stages.
+// The trie is built over REVERSED keywords for the AhoCorasick family (every end position walks
+// backwards and meets all keywords ending there, longest last) and over forward keywords for
+// Longest / Shortest / WholeWord (every start position walks forwards).
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace acgpu {
+
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr uint32_t kInfoTerminal = 1u;
+constexpr uint32_t kInfoHasChildren = 2u;
+
+struct Edge {  // one 16-byte slot of the device edge table
+    uint32_t parent;
+    uint32_t cls;
+    uint32_t child;
+    uint32_t info;
+};
+
+struct RootEdge {
+    uint32_t child;
+    uint32_t info;
+};
+
+inline uint32_t edge_hash(uint32_t parent, uint32_t c) {
+    uint32_t h = parent * 0x9E3779B1u ^ (c * 0x85EBCA6Bu + 0x7F4A7C15u);
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    return h;
+}
+
+struct IllegalArgument : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+struct HostAutomaton {
+    int family = 0;
+    bool is_map = false;
+    bool case_sensitive = true;
+    bool reversed = false;   // trie over reversed keywords (AhoCorasick family)
+    bool has_other = true;   // class 0 is "char occurs in no keyword"
+    int32_t max_len = 0;     // longest effective keyword (chars)
+    int32_t n_classes = 1;
+    int32_t char_buffer_size = 4096;  // AhoCorasickMap.java:53
+    int64_t n_nodes = 1;
+    int64_t n_keywords_effective = 0;
+    std::vector<uint16_t> cls;      // 65536
+    std::vector<uint32_t> wordbits; // 2048 words: raw word-char bitmap (WholeWord)
+    std::vector<RootEdge> root;     // n_classes
+    std::vector<Edge> edges;        // pow2 slots, empty = parent kNone
+    uint32_t edge_mask = 0;
+    std::vector<uint32_t> node_value;  // n_nodes, kNone when not terminal / Set
+    std::vector<uint8_t> node_info;    // n_nodes
+    std::vector<uint32_t> depth_count; // nodes per depth (diagnostics / tiering)
+};
+
+// Throws IllegalArgument with the reference's message for WholeWord keywords holding non-word chars.
+HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *offsets, const uint8_t *is_null,
+                              int64_t n_keywords, int64_t n_values, bool case_sensitive,
+                              const uint8_t *word_chars);
+
+// WordCharacters.generateWordCharsFlags (WordCharacters.java:6-39)
+void make_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, int32_t n, uint8_t *out65536);
+
+const uint16_t *java_lower_table();
+
+}  // namespace acgpu

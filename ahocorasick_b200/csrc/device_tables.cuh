@@ -1,0 +1,105 @@
+// Device-side view of a flattened dictionary + small shared helpers for the kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace acgpu {
+
+constexpr uint32_t kNoneD = 0xFFFFFFFFu;
+constexpr uint32_t kTerm = 1u;
+constexpr uint32_t kKids = 2u;
+
+struct DevAutomaton {
+    const uint16_t *cls;       // [65536] code unit -> class (case folding folded in)
+    const uint32_t *wordbits;  // [2048] raw word-char bitmap (WholeWord), else nullptr
+    const uint2 *root;         // [n_classes] {child, info}
+    const uint4 *edges;        // open addressing, {parent, cls, child, info}; empty: parent == kNoneD
+    const uint32_t *node_value;  // [n_nodes]
+    uint32_t edge_mask;
+    int32_t max_len;
+    int32_t n_classes;
+    int32_t has_other;
+    int32_t family;
+    int32_t is_map;
+};
+
+__host__ __device__ __forceinline__ uint32_t edge_hash_d(uint32_t parent, uint32_t c) {
+    uint32_t h = parent * 0x9E3779B1u ^ (c * 0x85EBCA6Bu + 0x7F4A7C15u);
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 12;
+    return h;
+}
+
+// One trie step: (node, class) -> child.  Root uses the direct table, deeper nodes the hashed edge table.
+__device__ __forceinline__ bool trie_step(const DevAutomaton &A, uint32_t &node, uint32_t c, uint32_t &info) {
+    if (node == 0) {
+        uint2 r = __ldg(&A.root[c]);
+        if (r.x == kNoneD) return false;
+        node = r.x;
+        info = r.y;
+        return true;
+    }
+    uint32_t i = edge_hash_d(node, c) & A.edge_mask;
+    while (true) {
+        uint4 e = __ldg(&A.edges[i]);
+        if (e.x == node && e.y == c) {
+            node = e.z;
+            info = e.w;
+            return true;
+        }
+        if (e.x == kNoneD) return false;
+        i = (i + 1) & A.edge_mask;
+    }
+}
+
+__device__ __forceinline__ bool is_word_char(const DevAutomaton &A, uint32_t raw) {
+    return (__ldg(&A.wordbits[raw >> 5]) >> (raw & 31)) & 1u;
+}
+
+// ---- decoupled look-back (single-pass ordered compaction across tiles) ------------------------------
+// status word: bits 63..62 = flag (0 invalid, 1 tile aggregate, 2 inclusive prefix), bits 61..0 = value
+constexpr unsigned long long kFlagAgg = 1ull << 62;
+constexpr unsigned long long kFlagInc = 2ull << 62;
+constexpr unsigned long long kValMask = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Called by ONE full warp (all 32 lanes).  Publishes this tile's aggregate, looks back over predecessor
+// tiles 32 at a time and returns the exclusive prefix (sum of aggregates of tiles < tile) to every lane.
+__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long *status, int64_t tile,
+                                                                 unsigned long long aggregate) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) st_status(&status[tile], (tile == 0 ? kFlagInc : kFlagAgg) | aggregate);
+    unsigned long long exclusive = 0;
+    int64_t base = tile - 1;
+    while (base >= 0) {
+        int64_t idx = base - lane;
+        unsigned long long w = kFlagInc;  // lanes before tile 0 behave like "inclusive prefix 0"
+        if (idx >= 0) {
+            do {
+                w = ld_status(&status[idx]);
+            } while ((w >> 62) == 0);
+        }
+        unsigned inc_mask = __ballot_sync(0xFFFFFFFFu, (w >> 62) == 2);
+        // nearest predecessor holding an inclusive prefix = lowest lane with the flag
+        int stop = inc_mask ? (__ffs(inc_mask) - 1) : 31;
+        unsigned long long contrib = (lane <= stop) ? (w & kValMask) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, o);
+        exclusive += contrib;
+        if (inc_mask) break;
+        base -= 32;
+    }
+    if (lane == 0 && tile != 0) st_status(&status[tile], kFlagInc | (exclusive + aggregate));
+    return exclusive;
+}
+
+}  // namespace acgpu

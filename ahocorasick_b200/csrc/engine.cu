@@ -1,0 +1,727 @@
+// libacgpu.so — C ABI (include/acgpu.h) over the sm_100a kernels.  No CPU matching path exists here:
+// every match entry point launches CUDA kernels or fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/acgpu.h"
+#include "builder.hpp"
+#include "kernels.cuh"
+
+using namespace acgpu;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            return fail(_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver ? ACGPU_ENODEVICE \
+                                                                                       : ACGPU_ECUDA,  \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                          \
+        }                                                                                              \
+    } while (0)
+
+constexpr uint64_t kMagic = 0xAC69B200AC69B200ull;
+
+struct Matcher {
+    uint64_t magic = kMagic;
+    int device = 0;
+    int sm_count = 148;
+    HostAutomaton host;  // tables kept for introspection; device copies below
+    DevAutomaton dev{};
+    void *d_blob = nullptr;  // one allocation holding every table
+    int64_t table_bytes = 0;
+    bool sel_attr_set = false;
+};
+
+Matcher *as_matcher(uint64_t h) {
+    Matcher *m = reinterpret_cast<Matcher *>(static_cast<uintptr_t>(h));
+    if (!m || m->magic != kMagic) return nullptr;
+    return m;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int upload(Matcher *m) {
+    const HostAutomaton &a = m->host;
+    size_t off = 0;
+    auto reserve = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    size_t o_cls = reserve(65536 * sizeof(uint16_t));
+    size_t o_word = reserve(a.wordbits.size() * sizeof(uint32_t));
+    size_t o_root = reserve(a.root.size() * sizeof(RootEdge));
+    size_t o_edges = reserve(a.edges.size() * sizeof(Edge));
+    size_t o_val = reserve(a.node_value.size() * sizeof(uint32_t));
+    CU_TRY(cudaMalloc(&m->d_blob, off));
+    m->table_bytes = static_cast<int64_t>(off);
+    char *b = static_cast<char *>(m->d_blob);
+    CU_TRY(cudaMemcpy(b + o_cls, a.cls.data(), 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    if (!a.wordbits.empty())
+        CU_TRY(cudaMemcpy(b + o_word, a.wordbits.data(), a.wordbits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(b + o_root, a.root.data(), a.root.size() * sizeof(RootEdge), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(b + o_edges, a.edges.data(), a.edges.size() * sizeof(Edge), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(b + o_val, a.node_value.data(), a.node_value.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    DevAutomaton &d = m->dev;
+    d.cls = reinterpret_cast<const uint16_t *>(b + o_cls);
+    d.wordbits = a.wordbits.empty() ? nullptr : reinterpret_cast<const uint32_t *>(b + o_word);
+    d.root = reinterpret_cast<const uint2 *>(b + o_root);
+    d.edges = reinterpret_cast<const uint4 *>(b + o_edges);
+    d.node_value = reinterpret_cast<const uint32_t *>(b + o_val);
+    d.edge_mask = a.edge_mask;
+    d.max_len = a.max_len;
+    d.n_classes = a.n_classes;
+    d.has_other = a.has_other ? 1 : 0;
+    d.family = a.family;
+    d.is_map = a.is_map ? 1 : 0;
+    return ACGPU_OK;
+}
+
+// Scratch for one match call, carved from one stream-ordered allocation.
+struct Scratch {
+    void *base = nullptr;
+    cudaStream_t st = nullptr;
+    size_t off = 0;
+    size_t reserve(size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    }
+};
+
+struct RunOpts {
+    int32_t pos_base = 0;  // stream offset added to positions
+    int64_t ctx = 0;       // leading window chars that are left context only (streaming)
+    int64_t entry0 = 0;    // chain position on entry (selection families)
+    int64_t chain_n = -1;  // chain domain [0, chain_n); -1 => n
+    int64_t *d_carry = nullptr;  // [2] int64 (selection families)
+};
+
+// Enqueue every kernel of one match on `st`.  d_total receives the total number of matches.
+int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from, int64_t emit_to, int2 *d_pos,
+                  uint32_t *d_val, int64_t cap, unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
+    const DevAutomaton &A = m->dev;
+    if (n < 0 || n > 0x7FFFFFFFll) return fail(ACGPU_EINVAL, "haystack length must fit a Java int");
+    if (A.is_map && !d_val && cap > 0) return fail(ACGPU_EINVAL, "Map matcher needs a value buffer");
+    const int persistent = m->sm_count * 8;
+
+    if (A.family == ACGPU_AHOCORASICK) {
+        emit_from = std::max<int64_t>(0, emit_from);
+        emit_to = std::min<int64_t>(n, emit_to);
+        const int64_t span = std::max<int64_t>(0, emit_to - emit_from);
+        const int64_t n_tiles = (span + kAcTile - 1) / kAcTile;
+        if (n_tiles == 0) {
+            CU_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
+            return ACGPU_OK;
+        }
+        size_t bytes = 256 + static_cast<size_t>(n_tiles) * 8;
+        void *ws = nullptr;
+        CU_TRY(cudaMallocAsync(&ws, bytes, st));
+        CU_TRY(cudaMemsetAsync(ws, 0, bytes, st));
+        AcArgs P{};
+        P.hay = d_hay;
+        P.n = n;
+        P.emit_from = emit_from;
+        P.emit_to = emit_to;
+        P.pos_base = opt.pos_base;
+        P.pos_out = d_pos;
+        P.val_out = d_val;
+        P.cap = cap;
+        P.total_out = d_total;
+        P.tile_counter = static_cast<unsigned int *>(ws);
+        P.status = reinterpret_cast<unsigned long long *>(static_cast<char *>(ws) + 256);
+        P.n_tiles = n_tiles;
+        const int grid = static_cast<int>(std::min<int64_t>(n_tiles, persistent));
+        if (A.is_map)
+            k_ac_scan<true><<<grid, kThreads, 0, st>>>(A, P);
+        else
+            k_ac_scan<false><<<grid, kThreads, 0, st>>>(A, P);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaFreeAsync(ws, st));
+        return ACGPU_OK;
+    }
+
+    // ---- start-anchored families
+    const int64_t chain_n = opt.chain_n < 0 ? n : opt.chain_n;
+    if (n == 0 || chain_n == 0) {
+        CU_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
+        return ACGPU_OK;
+    }
+    const bool chain = A.family != ACGPU_WHOLEWORD;
+    const int32_t M = A.max_len + 1;
+    const int64_t n_tiles = (chain_n + kSelTile - 1) / kSelTile;
+    const int64_t n_groups = (n_tiles + kSelGroup - 1) / kSelGroup;
+    Scratch S;
+    size_t o_ctr = S.reserve(256);
+    size_t o_status = S.reserve(static_cast<size_t>(n_tiles) * 8);
+    size_t o_zero_end = S.off;  // everything up to here is zero-initialised
+    size_t o_v = S.reserve(static_cast<size_t>(n) * sizeof(uint16_t));
+    size_t o_exit1 = 0, o_exit2 = 0, o_entry2 = 0, o_entry1 = 0;
+    if (chain) {
+        o_exit1 = S.reserve(static_cast<size_t>(n_tiles) * M * sizeof(uint16_t));
+        o_exit2 = S.reserve(static_cast<size_t>(n_groups) * M * sizeof(uint16_t));
+        o_entry2 = S.reserve(static_cast<size_t>(n_groups) * sizeof(int64_t));
+        o_entry1 = S.reserve(static_cast<size_t>(n_tiles) * sizeof(int32_t));
+    }
+    void *ws = nullptr;
+    CU_TRY(cudaMallocAsync(&ws, S.off, st));
+    char *b = static_cast<char *>(ws);
+    CU_TRY(cudaMemsetAsync(ws, 0, o_zero_end, st));
+
+    FwArgs F{};
+    F.hay = d_hay;
+    F.n = n;
+    F.p_lo = opt.ctx;
+    F.p_hi = n;
+    F.v = reinterpret_cast<uint16_t *>(b + o_v);
+    if (opt.ctx > 0) CU_TRY(cudaMemsetAsync(F.v, 0, static_cast<size_t>(opt.ctx) * sizeof(uint16_t), st));
+    {
+        const int64_t ft = (n + kFwTile - 1) / kFwTile;
+        const int grid = static_cast<int>(std::min<int64_t>(ft, persistent));
+        if (A.family == ACGPU_LONGEST)
+            k_fwd_v<1><<<grid, kThreads, 0, st>>>(A, F);
+        else if (A.family == ACGPU_SHORTEST)
+            k_fwd_v<2><<<grid, kThreads, 0, st>>>(A, F);
+        else
+            k_fwd_v<3><<<grid, kThreads, 0, st>>>(A, F);
+        CU_TRY(cudaGetLastError());
+    }
+
+    SelArgs P{};
+    P.v = F.v;
+    P.n_v = n;
+    P.n = chain_n;
+    P.M = M;
+    P.halo = std::max(0, A.max_len - 1);
+    P.dom_lo = opt.ctx;
+    P.mode = A.family == ACGPU_LONGEST ? kModeLongest : (A.family == ACGPU_SHORTEST ? kModeShortest : kModeWholeWord);
+    P.n_tiles = n_tiles;
+    P.n_groups = n_groups;
+    P.entry0 = opt.entry0;
+    P.carry_out = reinterpret_cast<long long *>(opt.d_carry);
+    if (opt.d_carry) CU_TRY(cudaMemsetAsync(opt.d_carry, 0xFF, 8, st));  // -1 = chain did not cross chain_n
+    P.hay = d_hay;
+    P.n_hay = n;
+    P.pos_base = opt.pos_base;
+    P.pos_out = d_pos;
+    P.val_out = d_val;
+    P.cap = cap;
+    P.total_out = d_total;
+    P.tile_counter = reinterpret_cast<unsigned int *>(b + o_ctr);
+    P.status = reinterpret_cast<unsigned long long *>(b + o_status);
+    if (chain) {
+        P.exit1 = reinterpret_cast<uint16_t *>(b + o_exit1);
+        P.exit2 = reinterpret_cast<uint16_t *>(b + o_exit2);
+        P.entry2 = reinterpret_cast<int64_t *>(b + o_entry2);
+        P.entry1 = reinterpret_cast<int32_t *>(b + o_entry1);
+        const int grid_map = static_cast<int>(std::min<int64_t>(n_tiles, m->sm_count * 4));
+        k_sel_map<<<grid_map, kThreads, 0, st>>>(P);
+        CU_TRY(cudaGetLastError());
+        k_sel_group<<<static_cast<unsigned>(n_groups), kThreads, 0, st>>>(P);
+        CU_TRY(cudaGetLastError());
+        k_sel_top<<<1, 32, 0, st>>>(P);
+        CU_TRY(cudaGetLastError());
+        k_sel_entries<<<static_cast<unsigned>((n_groups + 127) / 128), 128, 0, st>>>(P);
+        CU_TRY(cudaGetLastError());
+    }
+    {
+        const int grid = static_cast<int>(std::min<int64_t>(n_tiles, m->sm_count * 4));
+        if (A.is_map)
+            k_sel_emit<true><<<grid, kThreads, kSelEmitSmem, st>>>(A, P);
+        else
+            k_sel_emit<false><<<grid, kThreads, kSelEmitSmem, st>>>(A, P);
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaFreeAsync(ws, st));
+    return ACGPU_OK;
+}
+
+int ensure_device(Matcher *m) {
+    CU_TRY(cudaSetDevice(m->device));
+    if (!m->sel_attr_set) {
+        CU_TRY(cudaFuncSetAttribute(k_sel_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelEmitSmem));
+        CU_TRY(cudaFuncSetAttribute(k_sel_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelEmitSmem));
+        m->sel_attr_set = true;
+    }
+    return ACGPU_OK;
+}
+
+struct HostResult {  // owner block placed right before the arrays
+    int32_t *pos;
+    uint32_t *val;
+};
+
+void fill_empty(acgpu_result *out) {
+    out->n = 0;
+    out->pos = nullptr;
+    out->val = nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *acgpu_last_error(void) { return g_err.c_str(); }
+const char *acgpu_version(void) { return "acgpu 0.1 (sm_100a, anchored-trie generation 1)"; }
+
+int acgpu_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, int32_t n, uint8_t *out65536) {
+    if (!out65536 || mode < 0 || mode > 2 || n < 0) return fail(ACGPU_EINVAL, "bad arguments");
+    make_word_chars(mode, chars, toggles, n, out65536);
+    return ACGPU_OK;
+}
+
+int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t *offsets, const uint8_t *is_null,
+                               int64_t n_keywords, int64_t n_values, int case_sensitive, const uint8_t *word_chars,
+                               int device, uint64_t *handle) {
+    if (!handle || n_keywords < 0 || (n_keywords > 0 && (!chars || !offsets))) return fail(ACGPU_EINVAL, "bad arguments");
+    *handle = 0;
+    Matcher *m = new (std::nothrow) Matcher();
+    if (!m) return fail(ACGPU_ENOMEM, "out of memory");
+    try {
+        m->host = build_automaton(family, chars, offsets, is_null, n_keywords, n_values, case_sensitive != 0, word_chars);
+    } catch (const IllegalArgument &e) {
+        delete m;
+        return fail(ACGPU_EILLEGALARG, e.what());
+    } catch (const std::domain_error &e) {
+        delete m;
+        return fail(ACGPU_EUNSUPPORTED, e.what());
+    } catch (const std::bad_alloc &) {
+        delete m;
+        return fail(ACGPU_ENOMEM, "out of memory while flattening the dictionary");
+    } catch (const std::exception &e) {
+        delete m;
+        return fail(ACGPU_EINVAL, e.what());
+    }
+    if ((family == ACGPU_LONGEST || family == ACGPU_SHORTEST) && m->host.max_len + 1 > kSelMaxLen) {
+        delete m;
+        return fail(ACGPU_EUNSUPPORTED, "Longest/Shortest selection kernels support keywords up to 2047 chars");
+    }
+    if (m->host.max_len > 65535) {
+        delete m;
+        return fail(ACGPU_EUNSUPPORTED, "keywords longer than 65535 chars are not supported");
+    }
+    m->device = device;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        delete m;
+        return fail(ACGPU_ENODEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n_dev) {
+        delete m;
+        return fail(ACGPU_EINVAL, "device ordinal out of range");
+    }
+    int rc = ensure_device(m);
+    if (rc == ACGPU_OK) {
+        cudaDeviceProp prop{};
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) m->sm_count = prop.multiProcessorCount;
+        rc = upload(m);
+    }
+    if (rc != ACGPU_OK) {
+        if (m->d_blob) cudaFree(m->d_blob);
+        delete m;
+        return rc;
+    }
+    *handle = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(m));
+    return ACGPU_OK;
+}
+
+int acgpu_destroy(uint64_t handle) {
+    Matcher *m = as_matcher(handle);
+    if (!m) return fail(ACGPU_EINVAL, "bad handle");
+    cudaSetDevice(m->device);
+    if (m->d_blob) cudaFree(m->d_blob);
+    m->magic = 0;
+    delete m;
+    return ACGPU_OK;
+}
+
+int acgpu_info(uint64_t handle, int64_t *n_nodes, int32_t *n_classes, int32_t *max_len, int32_t *char_buffer_size,
+               int64_t *table_bytes) {
+    Matcher *m = as_matcher(handle);
+    if (!m) return fail(ACGPU_EINVAL, "bad handle");
+    if (n_nodes) *n_nodes = m->host.n_nodes;
+    if (n_classes) *n_classes = m->host.n_classes;
+    if (max_len) *max_len = m->host.max_len;
+    if (char_buffer_size) *char_buffer_size = m->host.char_buffer_size;
+    if (table_bytes) *table_bytes = m->table_bytes;
+    return ACGPU_OK;
+}
+
+int acgpu_launches_per_match(uint64_t handle) {
+    Matcher *m = as_matcher(handle);
+    if (!m) return fail(ACGPU_EINVAL, "bad handle");
+    switch (m->host.family) {
+    case ACGPU_AHOCORASICK: return 1;
+    case ACGPU_WHOLEWORD: return 2;
+    default: return 6;
+    }
+}
+
+int acgpu_match_device_async(uint64_t handle, const void *d_haystack, int64_t n, int64_t emit_from, int64_t emit_to,
+                             void *d_pos, void *d_val, int64_t cap, void *d_total, void *cuda_stream) {
+    Matcher *m = as_matcher(handle);
+    if (!m) return fail(ACGPU_EINVAL, "bad handle");
+    if (!d_total || (n > 0 && !d_haystack) || (cap > 0 && !d_pos) || cap < 0) return fail(ACGPU_EINVAL, "bad arguments");
+    int rc = ensure_device(m);
+    if (rc != ACGPU_OK) return rc;
+    RunOpts opt;
+    return enqueue_match(m, static_cast<const uint16_t *>(d_haystack), n, emit_from, emit_to, static_cast<int2 *>(d_pos),
+                         static_cast<uint32_t *>(d_val), cap, static_cast<unsigned long long *>(d_total),
+                         static_cast<cudaStream_t>(cuda_stream), opt);
+}
+
+int acgpu_match_device(uint64_t handle, const void *d_haystack, int64_t n, int64_t emit_from, int64_t emit_to,
+                       void *d_pos, void *d_val, int64_t cap, int64_t *n_out, void *cuda_stream) {
+    Matcher *m = as_matcher(handle);
+    if (!m) return fail(ACGPU_EINVAL, "bad handle");
+    if (!n_out) return fail(ACGPU_EINVAL, "bad arguments");
+    int rc = ensure_device(m);
+    if (rc != ACGPU_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    unsigned long long *d_total = nullptr;
+    CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_total), 8, st));
+    rc = acgpu_match_device_async(handle, d_haystack, n, emit_from, emit_to, d_pos, d_val, cap, d_total, cuda_stream);
+    unsigned long long total = 0;
+    if (rc == ACGPU_OK) {
+        CU_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    cudaFreeAsync(d_total, st);
+    if (rc == ACGPU_OK) *n_out = static_cast<int64_t>(total);
+    return rc;
+}
+
+int acgpu_match_utf16(uint64_t handle, const uint16_t *haystack, int32_t n, acgpu_result *out) {
+    Matcher *m = as_matcher(handle);
+    if (!m) return fail(ACGPU_EINVAL, "bad handle");
+    if (!out || n < 0 || (n > 0 && !haystack)) return fail(ACGPU_EINVAL, "bad arguments");
+    fill_empty(out);
+    int rc = ensure_device(m);
+    if (rc != ACGPU_OK) return rc;
+    if (n == 0) return ACGPU_OK;
+    cudaStream_t st;
+    CU_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    uint16_t *d_hay = nullptr;
+    int2 *d_pos = nullptr;
+    uint32_t *d_val = nullptr;
+    unsigned long long *d_total = nullptr;
+    int32_t *h_pos = nullptr;
+    uint32_t *h_val = nullptr;
+    auto cleanup = [&]() {
+        if (d_hay) cudaFreeAsync(d_hay, st);
+        if (d_pos) cudaFreeAsync(d_pos, st);
+        if (d_val) cudaFreeAsync(d_val, st);
+        if (d_total) cudaFreeAsync(d_total, st);
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+    };
+#define CU_TRY_C(expr)                 \
+    do {                               \
+        cudaError_t _e2 = (expr);      \
+        if (_e2 != cudaSuccess) {      \
+            cleanup();                 \
+            free(h_pos);               \
+            free(h_val);               \
+            CU_TRY(_e2);               \
+        }                              \
+    } while (0)
+    CU_TRY_C(cudaMallocAsync(reinterpret_cast<void **>(&d_hay), static_cast<size_t>(n) * 2, st));
+    CU_TRY_C(cudaMallocAsync(reinterpret_cast<void **>(&d_total), 8, st));
+    CU_TRY_C(cudaMemcpyAsync(d_hay, haystack, static_cast<size_t>(n) * 2, cudaMemcpyHostToDevice, st));
+    int64_t cap = std::max<int64_t>(1 << 16, n / 4);
+    unsigned long long total = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CU_TRY_C(cudaMallocAsync(reinterpret_cast<void **>(&d_pos), static_cast<size_t>(cap) * 8, st));
+        if (m->host.is_map) CU_TRY_C(cudaMallocAsync(reinterpret_cast<void **>(&d_val), static_cast<size_t>(cap) * 4, st));
+        RunOpts opt;
+        rc = enqueue_match(m, d_hay, n, 0, n, d_pos, d_val, cap, d_total, st, opt);
+        if (rc != ACGPU_OK) {
+            cleanup();
+            return rc;
+        }
+        CU_TRY_C(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY_C(cudaStreamSynchronize(st));
+        if (static_cast<int64_t>(total) <= cap) break;
+        // first guess too small: the kernel still counted everything; rerun with the exact size
+        cudaFreeAsync(d_pos, st);
+        d_pos = nullptr;
+        if (d_val) cudaFreeAsync(d_val, st);
+        d_val = nullptr;
+        cap = static_cast<int64_t>(total);
+    }
+    if (total > 0) {
+        h_pos = static_cast<int32_t *>(malloc(static_cast<size_t>(total) * 8));
+        if (m->host.is_map) h_val = static_cast<uint32_t *>(malloc(static_cast<size_t>(total) * 4));
+        if (!h_pos || (m->host.is_map && !h_val)) {
+            cleanup();
+            free(h_pos);
+            free(h_val);
+            return fail(ACGPU_ENOMEM, "out of host memory for the match records");
+        }
+        CU_TRY_C(cudaMemcpyAsync(h_pos, d_pos, static_cast<size_t>(total) * 8, cudaMemcpyDeviceToHost, st));
+        if (h_val) CU_TRY_C(cudaMemcpyAsync(h_val, d_val, static_cast<size_t>(total) * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY_C(cudaStreamSynchronize(st));
+    }
+    cleanup();
+    out->n = static_cast<int64_t>(total);
+    out->pos = h_pos;
+    out->val = h_val;
+    return ACGPU_OK;
+}
+
+void acgpu_free_result(acgpu_result *r) {
+    if (!r) return;
+    free(const_cast<int32_t *>(r->pos));
+    free(const_cast<uint32_t *>(r->val));
+    fill_empty(r);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// match(Readable, listener): block-wise scan with carried context.
+//
+// The device window holds [left context | new chars].  AhoCorasick (end-anchored) finalises every new
+// position at once and keeps the last max_len-1 chars as context.  The start-anchored families finalise the
+// chain domain [ctx, avail - D) where D = 2*max_len + 2 chars of look-ahead make v[] and the Shortest halo
+// exact; the unfinalised tail (plus one char of left context) is carried to the next window together with
+// the absolute chain position.  Host chars travel through two pinned staging buffers with cudaMemcpyAsync so
+// the CPU copy of chunk k+1 overlaps the DMA of chunk k.
+namespace {
+
+constexpr uint64_t kStreamMagic = 0x5712EA30AC69B200ull;
+constexpr size_t kPinChars = 1u << 21;  // 4 MiB per pinned staging buffer
+
+struct StreamCtx {
+    uint64_t magic = kStreamMagic;
+    Matcher *m = nullptr;
+    cudaStream_t st = nullptr;
+    uint16_t *h_pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    uint16_t *d_win[2] = {nullptr, nullptr};
+    int64_t win_cap[2] = {0, 0};
+    int cur = 0;          // active window
+    int64_t len = 0;      // chars in the active window (context + unprocessed tail)
+    int64_t ctx = 0;      // leading context chars of the active window
+    int64_t base = 0;     // absolute stream offset of window[0]
+    int64_t chain = 0;    // absolute chain position (selection families)
+    int64_t *d_carry = nullptr;
+    unsigned long long *d_total = nullptr;
+};
+
+StreamCtx *as_stream(uint64_t h) {
+    StreamCtx *s = reinterpret_cast<StreamCtx *>(static_cast<uintptr_t>(h));
+    if (!s || s->magic != kStreamMagic) return nullptr;
+    return s;
+}
+
+void stream_free(StreamCtx *s) {
+    cudaSetDevice(s->m->device);
+    if (s->st) cudaStreamSynchronize(s->st);
+    for (int i = 0; i < 2; i++) {
+        if (s->h_pin[i]) cudaFreeHost(s->h_pin[i]);
+        if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+        if (s->d_win[i]) cudaFree(s->d_win[i]);
+    }
+    if (s->d_carry) cudaFree(s->d_carry);
+    if (s->d_total) cudaFree(s->d_total);
+    if (s->st) cudaStreamDestroy(s->st);
+    s->magic = 0;
+    delete s;
+}
+
+int stream_reserve(StreamCtx *s, int which, int64_t chars) {
+    if (s->win_cap[which] >= chars) return ACGPU_OK;
+    int64_t cap = std::max<int64_t>(chars + chars / 4, 1 << 16);
+    uint16_t *nw = nullptr;
+    CU_TRY(cudaMalloc(reinterpret_cast<void **>(&nw), static_cast<size_t>(cap) * 2));
+    if (which == s->cur && s->len > 0)
+        CU_TRY(cudaMemcpyAsync(nw, s->d_win[which], static_cast<size_t>(s->len) * 2, cudaMemcpyDeviceToDevice, s->st));
+    CU_TRY(cudaStreamSynchronize(s->st));
+    if (s->d_win[which]) cudaFree(s->d_win[which]);
+    s->d_win[which] = nw;
+    s->win_cap[which] = cap;
+    return ACGPU_OK;
+}
+
+// append host chars to the active window through the pinned double buffer
+int stream_append(StreamCtx *s, const uint16_t *chars, int64_t n) {
+    int rc = stream_reserve(s, s->cur, s->len + n);
+    if (rc != ACGPU_OK) return rc;
+    int64_t done = 0;
+    int k = 0;
+    while (done < n) {
+        const int64_t c = std::min<int64_t>(static_cast<int64_t>(kPinChars), n - done);
+        CU_TRY(cudaEventSynchronize(s->ev[k]));  // staging buffer k free again
+        std::memcpy(s->h_pin[k], chars + done, static_cast<size_t>(c) * 2);
+        CU_TRY(cudaMemcpyAsync(s->d_win[s->cur] + s->len + done, s->h_pin[k], static_cast<size_t>(c) * 2,
+                               cudaMemcpyHostToDevice, s->st));
+        CU_TRY(cudaEventRecord(s->ev[k], s->st));
+        done += c;
+        k ^= 1;
+    }
+    s->len += n;
+    return ACGPU_OK;
+}
+
+// scan what can be finalised, copy the records out, slide the window
+int stream_process(StreamCtx *s, bool final, acgpu_result *out) {
+    Matcher *m = s->m;
+    const int family = m->host.family;
+    const int64_t L = m->host.max_len;
+    const int64_t avail = s->len;
+    int64_t limit;  // window positions [ctx, limit) are finalised by this call
+    if (family == ACGPU_AHOCORASICK) {
+        limit = avail;
+    } else {
+        const int64_t D = 2 * L + 2;
+        limit = final ? avail : std::max<int64_t>(s->ctx, avail - D);
+    }
+    fill_empty(out);
+    if (limit <= s->ctx) return ACGPU_OK;
+
+    int64_t cap = std::max<int64_t>(1 << 16, (limit - s->ctx) / 4);
+    unsigned long long total = 0;
+    int2 *d_pos = nullptr;
+    uint32_t *d_val = nullptr;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_pos), static_cast<size_t>(cap) * 8, s->st));
+        if (m->host.is_map) CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_val), static_cast<size_t>(cap) * 4, s->st));
+        RunOpts opt;
+        opt.pos_base = static_cast<int32_t>(static_cast<uint32_t>(s->base));
+        opt.ctx = s->ctx;
+        int rc;
+        if (family == ACGPU_AHOCORASICK) {
+            rc = enqueue_match(m, s->d_win[s->cur], avail, s->ctx, avail, d_pos, d_val, cap, s->d_total, s->st, opt);
+        } else {
+            opt.entry0 = s->chain - s->base;
+            opt.chain_n = limit;
+            opt.d_carry = s->d_carry;
+            rc = enqueue_match(m, s->d_win[s->cur], avail, 0, avail, d_pos, d_val, cap, s->d_total, s->st, opt);
+        }
+        if (rc != ACGPU_OK) return rc;
+        CU_TRY(cudaMemcpyAsync(&total, s->d_total, 8, cudaMemcpyDeviceToHost, s->st));
+        CU_TRY(cudaStreamSynchronize(s->st));
+        if (static_cast<int64_t>(total) <= cap) break;
+        cudaFreeAsync(d_pos, s->st);
+        if (d_val) cudaFreeAsync(d_val, s->st);
+        d_pos = nullptr;
+        d_val = nullptr;
+        cap = static_cast<int64_t>(total);
+    }
+    if (total > 0) {
+        int32_t *h_pos = static_cast<int32_t *>(malloc(static_cast<size_t>(total) * 8));
+        uint32_t *h_val = m->host.is_map ? static_cast<uint32_t *>(malloc(static_cast<size_t>(total) * 4)) : nullptr;
+        if (!h_pos || (m->host.is_map && !h_val)) {
+            free(h_pos);
+            free(h_val);
+            return fail(ACGPU_ENOMEM, "out of host memory for the match records");
+        }
+        CU_TRY(cudaMemcpyAsync(h_pos, d_pos, static_cast<size_t>(total) * 8, cudaMemcpyDeviceToHost, s->st));
+        if (h_val) CU_TRY(cudaMemcpyAsync(h_val, d_val, static_cast<size_t>(total) * 4, cudaMemcpyDeviceToHost, s->st));
+        CU_TRY(cudaStreamSynchronize(s->st));
+        out->n = static_cast<int64_t>(total);
+        out->pos = h_pos;
+        out->val = h_val;
+    }
+    cudaFreeAsync(d_pos, s->st);
+    if (d_val) cudaFreeAsync(d_val, s->st);
+
+    // chain position for the next block
+    if (family == ACGPU_LONGEST || family == ACGPU_SHORTEST) {
+        int64_t carry = -1;
+        CU_TRY(cudaMemcpyAsync(&carry, s->d_carry, sizeof(carry), cudaMemcpyDeviceToHost, s->st));
+        CU_TRY(cudaStreamSynchronize(s->st));
+        if (carry >= 0) s->chain = s->base + carry;  // else: the chain already stood beyond this block
+    } else {
+        s->chain = s->base + limit;
+    }
+
+    // slide: keep the context the next block needs at the front of the other window
+    int64_t keep_from;
+    if (family == ACGPU_AHOCORASICK) {
+        keep_from = std::max<int64_t>(0, avail - std::max<int64_t>(0, L - 1));
+    } else {
+        keep_from = std::max<int64_t>(0, limit - 1);
+    }
+    const int64_t keep = avail - keep_from;
+    const int other = s->cur ^ 1;
+    int rc = stream_reserve(s, other, std::max<int64_t>(keep, 1));
+    if (rc != ACGPU_OK) return rc;
+    if (keep > 0)
+        CU_TRY(cudaMemcpyAsync(s->d_win[other], s->d_win[s->cur] + keep_from, static_cast<size_t>(keep) * 2,
+                               cudaMemcpyDeviceToDevice, s->st));
+    s->cur = other;
+    s->base += keep_from;
+    s->len = keep;
+    s->ctx = (family == ACGPU_AHOCORASICK) ? keep : std::min<int64_t>(keep, limit - keep_from);
+    return ACGPU_OK;
+}
+
+}  // namespace
+
+int acgpu_stream_begin(uint64_t handle, uint64_t *stream_handle) {
+    Matcher *m = as_matcher(handle);
+    if (!m || !stream_handle) return fail(ACGPU_EINVAL, "bad arguments");
+    *stream_handle = 0;
+    int rc = ensure_device(m);
+    if (rc != ACGPU_OK) return rc;
+    StreamCtx *s = new (std::nothrow) StreamCtx();
+    if (!s) return fail(ACGPU_ENOMEM, "out of memory");
+    s->m = m;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaMallocHost(reinterpret_cast<void **>(&s->h_pin[i]), kPinChars * 2);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s->d_carry), 16);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s->d_total), 8);
+    if (e != cudaSuccess) {
+        stream_free(s);
+        return fail(ACGPU_ECUDA, std::string("stream setup: ") + cudaGetErrorString(e));
+    }
+    *stream_handle = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(s));
+    return ACGPU_OK;
+}
+
+int acgpu_stream_feed(uint64_t stream_handle, const uint16_t *chars, int32_t n, acgpu_result *out) {
+    StreamCtx *s = as_stream(stream_handle);
+    if (!s || !out || n < 0 || (n > 0 && !chars)) return fail(ACGPU_EINVAL, "bad arguments");
+    fill_empty(out);
+    CU_TRY(cudaSetDevice(s->m->device));
+    if (n == 0) return ACGPU_OK;
+    int rc = stream_append(s, chars, n);
+    if (rc != ACGPU_OK) return rc;
+    return stream_process(s, false, out);
+}
+
+int acgpu_stream_end(uint64_t stream_handle, acgpu_result *out) {
+    StreamCtx *s = as_stream(stream_handle);
+    if (!s) return fail(ACGPU_EINVAL, "bad stream handle");
+    int rc = ACGPU_OK;
+    if (out) {
+        fill_empty(out);
+        cudaSetDevice(s->m->device);
+        rc = stream_process(s, true, out);
+    }
+    stream_free(s);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+/*
+ * acgpu.h — C ABI of libacgpu.so, the B200-native (sm_100a) drop-in for the matching hot
+ * path of RokLenarcic/AhoCorasick.
+ *
+ * The reference is a pure-Java library with no FFI of its own; its boundary is the public
+ * Java API.  Every entry point below names the reference interface it stands in for
+ * (paths relative to src/main/java/com/roklenarcic/util/strings/ of the reference); the JNI
+ * veneer a maintainer adds on the Java side is shown in INTEGRATION.md and java/.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns 0 on
+ * success and a negative ACGPU_E* code on failure (text via acgpu_last_error()); handles are
+ * opaque; host buffers are caller-owned and only read during the call; haystacks are UTF-16
+ * code units (Java char), positions are int32 like Java's int; `end` is exclusive.
+ * There is no CPU fallback: every match entry point needs a CUDA device and fails loudly
+ * (ACGPU_ENODEVICE) without one.
+ */
+#ifndef ACGPU_H
+#define ACGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACGPU_OK 0
+#define ACGPU_EINVAL (-1)      /* bad argument / bad handle */
+#define ACGPU_EILLEGALARG (-2) /* the reference would throw IllegalArgumentException */
+#define ACGPU_ENODEVICE (-3)   /* no usable CUDA device */
+#define ACGPU_ECUDA (-4)       /* a CUDA call failed */
+#define ACGPU_ENOMEM (-5)
+#define ACGPU_EUNSUPPORTED (-6) /* input outside what the GPU path implements (documented in DESIGN.md) */
+
+#define ACGPU_NO_VALUE 0xFFFFFFFFu
+
+/* Matcher families: the four public class pairs named by BASELINE.json north_star. */
+enum acgpu_family {
+    ACGPU_AHOCORASICK = 0, /* AhoCorasickSet.java / AhoCorasickMap.java : all overlapping matches */
+    ACGPU_LONGEST = 1,     /* LongestMatchSet.java / LongestMatchMap.java : leftmost-longest, non-overlapping */
+    ACGPU_SHORTEST = 2,    /* ShortestMatchSet.java / ShortestMatchMap.java : earliest-end, non-overlapping */
+    ACGPU_WHOLEWORD = 3    /* WholeWordMatchSet.java / WholeWordMatchMap.java : whole word-character runs */
+};
+
+/* A match stream in the reference's listener order.
+ *   pos : 2*n int32, (start,end) pairs — the arguments of SetMatchListener.match(haystack,start,end)
+ *         (SetMatchListener.java:6) / MapMatchListener.match(haystack,start,end,value) (MapMatchListener.java:6)
+ *   val : n uint32 value indices (index into the values Iterable given to the Map constructor), NULL for Sets;
+ *         for the Readable overloads (ReadableMatchListener.java:7) only val is meaningful to the listener.
+ * Owned by the library; release with acgpu_free_result(). */
+typedef struct {
+    int64_t n;
+    const int32_t *pos;
+    const uint32_t *val;
+} acgpu_result;
+
+/*
+ * Constructors.  Replaces:
+ *   AhoCorasickSet(Iterable<String>, boolean[, Thresholder])            AhoCorasickSet.java:16-191
+ *   AhoCorasickMap(Iterable<String>, Iterable<T>, boolean[, Thresholder]) AhoCorasickMap.java:20-206
+ *   LongestMatchSet/Map   LongestMatchSet.java:15-140 / LongestMatchMap.java:19-201
+ *   ShortestMatchSet/Map  ShortestMatchSet.java:14-135 / ShortestMatchMap.java:19-197
+ *   WholeWordMatchSet/Map (all six overloads) WholeWordMatchSet.java:16-45,138-205 / WholeWordMatchMap.java:21-53,246-323
+ *
+ *  chars/offsets : keyword i = chars[offsets[i] .. offsets[i+1])   (UTF-16 code units)
+ *  is_null       : optional n_keywords flags; nonzero = Java null (skipped, but consumes a value)
+ *  n_values      : -1 => Set; >= 0 => Map whose values Iterable has n_values entries (zip stops at the shorter,
+ *                  AhoCorasickMap.java:32).  The value reported for a match is the index of the winning entry.
+ *  case_sensitive: as in the reference; folding is java.lang.Character.toLowerCase per UTF-16 unit (Unicode 15).
+ *  word_chars    : WholeWord only: 65536 flags = the boolean[] WordCharacters.generateWordCharsFlags(...)
+ *                  builds (WordCharacters.java:6-39); NULL = the default table.  acgpu_word_chars() builds all
+ *                  three variants.
+ *  device        : CUDA device ordinal the tables are uploaded to.
+ * The Thresholder argument of the reference only shapes its node objects (never results) and has no counterpart.
+ * ACGPU_EILLEGALARG + "<keyword> contains non-word characters." mirrors WholeWordMatchSet.java:149-153.
+ */
+int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t *offsets,
+                               const uint8_t *is_null, int64_t n_keywords, int64_t n_values,
+                               int case_sensitive, const uint8_t *word_chars, int device,
+                               uint64_t *handle);
+int acgpu_destroy(uint64_t handle);
+
+/* WordCharacters.generateWordCharsFlags (WordCharacters.java:6-16 mode 0, :18-24 mode 1, :26-39 mode 2). */
+int acgpu_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, int32_t n, uint8_t *out65536);
+
+/* Introspection (sizes in the flattened automaton; charBufferSize = AhoCorasickMap.java:53). */
+int acgpu_info(uint64_t handle, int64_t *n_nodes, int32_t *n_classes, int32_t *max_len,
+               int32_t *char_buffer_size, int64_t *table_bytes);
+
+/*
+ * match(String haystack, listener) — StringSet.java:4, StringMap.java:8; the scan loops
+ * AhoCorasickSet.java:193-252, LongestMatchSet.java:192-265, ShortestMatchSet.java:182-260,
+ * WholeWordMatchSet.java:47-132 and their Map twins.  Host buffer in, ordered records out
+ * (H2D copy, kernels, D2H copy all inside the call).  The caller replays the records to the listener and
+ * stops at the first `false` (family quirks: INTEGRATION.md).
+ */
+int acgpu_match_utf16(uint64_t handle, const uint16_t *haystack, int32_t n, acgpu_result *out);
+void acgpu_free_result(acgpu_result *r);
+
+/*
+ * Same scan with the haystack already resident in device memory (kernel-only measurements, multi-GPU
+ * shards).  d_pos (capacity cap records, 8 B each) and d_val (4 B each; may be NULL for Sets) are device
+ * buffers; *n_out receives the TOTAL number of matches, which may exceed cap (then only the first cap
+ * records were written — enlarge and rerun).  cuda_stream: a cudaStream_t, or NULL for the default stream.
+ * The call synchronises the stream before returning (it reads back *n_out).
+ *
+ * Sharding: emit_from/emit_to restrict reported matches; the scan itself may look outside:
+ *   AhoCorasick: matches with  emit_from <  end   <= emit_to
+ *   other families need the whole haystack (chain state) — pass emit_from = 0, emit_to = n.
+ */
+int acgpu_match_device(uint64_t handle, const void *d_haystack, int64_t n, int64_t emit_from, int64_t emit_to,
+                       void *d_pos, void *d_val, int64_t cap, int64_t *n_out, void *cuda_stream);
+
+/* Async flavour for benchmarking: enqueues the kernels only; the total lands in *d_total (device int64). */
+int acgpu_match_device_async(uint64_t handle, const void *d_haystack, int64_t n, int64_t emit_from,
+                             int64_t emit_to, void *d_pos, void *d_val, int64_t cap, void *d_total,
+                             void *cuda_stream);
+/* Number of kernel launches one acgpu_match_device_async enqueues for this matcher (for bench accounting). */
+int acgpu_launches_per_match(uint64_t handle);
+
+/*
+ * match(Readable haystack, ReadableMatchListener) — StringMap.java:6; loops AhoCorasickMap.java:208-275,
+ * LongestMatchMap.java:203-286, ShortestMatchMap.java:199-291, WholeWordMatchMap.java:55-153.
+ * begin -> feed* -> end.  Each feed copies the block through pinned double buffers (cudaMemcpyAsync),
+ * scans it with the automaton context carried over from previous blocks, and returns the records that
+ * are final so far, in order; positions are offsets in the whole stream.  end() flushes the rest.
+ */
+int acgpu_stream_begin(uint64_t handle, uint64_t *stream_handle);
+int acgpu_stream_feed(uint64_t stream_handle, const uint16_t *chars, int32_t n, acgpu_result *out);
+int acgpu_stream_end(uint64_t stream_handle, acgpu_result *out);
+
+const char *acgpu_last_error(void);
+const char *acgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

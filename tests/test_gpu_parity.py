@@ -1,0 +1,240 @@
+"""GPU parity: the CUDA path (through the C ABI, via the host-side API mirror) must deliver the same
+ordered listener calls as the CPU oracle (oracle/ac_oracle.c) on the same inputs.  Bit-exact: these are
+integer positions and value indices."""
+import io
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import ac_spec as spec  # noqa: E402
+from golden_cases import FAMILIES, ILLEGAL, LITERAL_CASES  # noqa: E402
+from oracle import oracle as ora  # noqa: E402
+
+import ahocorasick_b200 as ac  # noqa: E402
+import workloads as W  # noqa: E402
+
+SETS = {"ahocorasick": ac.AhoCorasickSet, "longest": ac.LongestMatchSet, "shortest": ac.ShortestMatchSet,
+        "wholeword": ac.WholeWordMatchSet}
+MAPS = {"ahocorasick": ac.AhoCorasickMap, "longest": ac.LongestMatchMap, "shortest": ac.ShortestMatchMap,
+        "wholeword": ac.WholeWordMatchMap}
+
+
+class Collect:
+    """Listener that records every call and answers False on its stop_after-th call."""
+
+    def __init__(self, stop_after=0):
+        self.calls = []
+        self.stop_after = stop_after
+
+    def match(self, *args):
+        self.calls.append(args[1:] if len(args) >= 3 else args)
+        return not (self.stop_after and len(self.calls) >= self.stop_after)
+
+
+def oracle_stream(m, hay, **kw):
+    return [(int(r["start"]), int(r["end"]), int(r["value"])) for r in m.match(hay, **kw)]
+
+
+def gpu_set_stream(s, hay, stop_after=0):
+    c = Collect(stop_after)
+    s.match(hay, c)
+    return [(a, b) for a, b in c.calls]
+
+
+def gpu_map_stream(m, hay, stop_after=0):
+    c = Collect(stop_after)
+    m.match(hay, c)
+    return [(a, b, v) for a, b, v in c.calls]
+
+
+@pytest.mark.parametrize("name", sorted(LITERAL_CASES))
+@pytest.mark.parametrize("family", FAMILIES)
+def test_literal_cases(name, family):
+    hay, kws, expect = LITERAL_CASES[name]
+    if expect.get(family) == ILLEGAL:
+        with pytest.raises(ac.IllegalArgumentException, match="contains non-word characters"):
+            SETS[family](kws, True)
+        with pytest.raises(ac.IllegalArgumentException):
+            MAPS[family](kws, kws, True)
+        return
+    if family == "wholeword" and family not in expect:
+        # keywords with inner non-word chars would throw; the reference test classes expect that too
+        try:
+            om = ora.Matcher(family, kws)
+        except ora.OracleError:
+            with pytest.raises(ac.IllegalArgumentException):
+                SETS[family](kws, True)
+            return
+    om = ora.Matcher(family, kws, n_values=len(kws))
+    want = oracle_stream(om, hay)
+    if isinstance(expect.get(family), list):
+        assert [(s, e) for s, e, _ in want] == expect[family]
+    assert gpu_set_stream(SETS[family](kws, True), hay) == [(s, e) for s, e, _ in want]
+    values = ["v%d" % i for i in range(len(kws))]
+    got = gpu_map_stream(MAPS[family](kws, values, True), hay)
+    assert got == [(s, e, values[v]) for s, e, v in want]
+    # Readable overload: values only, same order (MapTest.java:178-188 asserts equal counts)
+    c = Collect()
+    MAPS[family](kws, values, True).match(io.StringIO(hay), c)
+    assert [v[0] for v in c.calls] == [values[int(r["value"])] for r in om.match(hay, readable=True)]
+
+
+def _rand_word(rng, alphabet, lo, hi):
+    return "".join(rng.choice(alphabet) for _ in range(rng.randint(lo, hi)))
+
+
+@pytest.mark.parametrize("family", FAMILIES)
+@pytest.mark.parametrize("cs", [True, False])
+def test_fuzz_small(family, cs):
+    rng = random.Random(hash((family, cs, "gpu")) & 0xFFFF)
+    for it in range(60):
+        alphabet = rng.choice(["ab", "abc", "abAB", "abcdeXYZ", "aβΒbİi"])
+        nk = rng.randint(0, 8)
+        kws = [_rand_word(rng, alphabet, 1, rng.choice([2, 3, 5, 9])) for _ in range(nk)]
+        if rng.random() < 0.2:
+            kws.insert(rng.randint(0, len(kws)), rng.choice([None, ""]))
+        sep = " " if family == "wholeword" or rng.random() < 0.3 else ""
+        hay = "".join(rng.choice(alphabet + sep * 2) for _ in range(rng.randint(0, 200)))
+        nv = rng.choice([len(kws), max(0, len(kws) - 1)])
+        want = oracle_stream(ora.Matcher(family, kws, n_values=nv, case_sensitive=cs), hay)
+        got = gpu_map_stream(MAPS[family](kws, list(range(nv)), cs), hay)
+        assert got == want, (kws, hay, cs, nv)
+        want_set = oracle_stream(ora.Matcher(family, kws, case_sensitive=cs), hay)
+        assert gpu_set_stream(SETS[family](kws, cs), hay) == [(s, e) for s, e, _ in want_set]
+
+
+@pytest.mark.parametrize("family", FAMILIES)
+def test_fuzz_medium_dense(family):
+    """Longer haystacks that span many tiles, dense matches, repetitive text (chains that never resynchronise)."""
+    rng = random.Random(99)
+    for alphabet, nk, n in (("ab", 12, 30000), ("abc", 40, 50000), ("ab ", 6, 20000)):
+        kws = list({_rand_word(rng, alphabet.strip() or "ab", 1, 7) for _ in range(nk)})
+        hay = "".join(rng.choice(alphabet) for _ in range(n))
+        if family == "wholeword":
+            hay = hay.replace("b", " ", n // 7) if " " not in alphabet else hay
+        want = oracle_stream(ora.Matcher(family, kws, n_values=len(kws)), hay)
+        got = gpu_map_stream(MAPS[family](kws, list(range(len(kws))), True), hay)
+        assert got == want
+    # periodic text: two interleaved greedy chains that never merge
+    hay = "ab" * 20000
+    kws = ["ab", "ba", "aba", "bab"]
+    for cls_ in (SETS[family],):
+        want = [(s, e) for s, e, _ in oracle_stream(ora.Matcher(family, kws), hay)]
+        assert gpu_set_stream(cls_(kws, True), hay) == want
+
+
+def test_early_stop_quirks():
+    kws = ["ab", "b", "abc", "c"]
+    hay = "abcabcabc"
+    for family in FAMILIES:
+        om = ora.Matcher(family, kws)
+        full = oracle_stream(om, hay)
+        for k in range(1, len(full) + 2):
+            want = [(s, e) for s, e, _ in oracle_stream(om, hay, stop_after=k)]
+            assert gpu_set_stream(SETS[family](kws, True), hay, stop_after=k) == want, (family, k)
+
+
+def test_wide_alphabet_reference_style_dictionaries():
+    """Generator.randomStrings(n, 2, 3) (Generator.java:61-76) + testFullNode: whole-BMP alphabets."""
+    rng = random.Random(7)
+    kws = list({"".join(chr(rng.randrange(256) if rng.random() < 0.5 else rng.randrange(65536))
+                        for _ in range(2)) for _ in range(20000)})
+    kws = [k for k in kws if not any(0xD800 <= ord(c) <= 0xDFFF for c in k)]
+    hay = "The quick red fox, jumps over the lazy brown dog." + "".join(rng.choice(kws) for _ in range(500))
+    for family in ("ahocorasick", "longest", "shortest"):
+        want = [(s, e) for s, e, _ in oracle_stream(ora.Matcher(family, kws), hay)]
+        assert gpu_set_stream(SETS[family](kws, True), hay) == want
+        assert len(want) >= 250
+
+
+def test_wholeword_custom_word_chars_config3_style():
+    kws = ["a=b", "x-y", "_q_", "Hello"]
+    wc = ora.word_chars(2, ["_", "="], [False, True])
+    hay = "a=b_x-y q _q_ a=b= hello,Hello;HELLO"
+    for cs in (True, False):
+        want = [(s, e) for s, e, _ in oracle_stream(ora.Matcher("wholeword", kws, case_sensitive=cs, word_chars_table=wc), hay)]
+        got = gpu_set_stream(ac.WholeWordMatchSet(kws, cs, ["_", "="], [False, True]), hay)
+        assert got == want
+    with pytest.raises(ac.IllegalArgumentException):
+        ac.WholeWordMatchSet(["abc"], True, ["_", "="])
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
+def test_baseline_configs_scaled(cfg):
+    """The five BASELINE.json configs at a size the oracle finishes in seconds: identical ordered streams."""
+    c = W.config(cfg, scale=0.02 if cfg != 0 else 0.25)
+    n = min(c["n"], 2_000_000)
+    hay = W.make_haystack(c["spec"], n)
+    kws = c["keywords"]
+    wc_args = ()
+    wc_table = None
+    if "word_chars" in c:
+        wc_args = tuple(c["word_chars"])
+        wc_table = ora.word_chars(2, *c["word_chars"])
+    families = [c["family"]] if cfg != 2 else ["longest", "shortest"]
+    for family in families:
+        om = ora.Matcher(family, kws, n_values=len(kws), case_sensitive=c["cs"], word_chars_table=wc_table)
+        want = om.match(hay)
+        gm = MAPS[family](kws, list(range(len(kws))), c["cs"], *wc_args)
+        rec = gm.match_records(hay)
+        assert len(rec) == len(want) and len(want) > 1000
+        assert np.array_equal(rec.start, want["start"])
+        assert np.array_equal(rec.end, want["end"])
+        assert np.array_equal(rec.value.astype(np.int64), want["value"].astype(np.int64))
+
+
+class _NumpyReadable:
+    """A Readable over a uint16 array (like java.io.CharArrayReader): read(n) returns up to n chars."""
+
+    def __init__(self, arr):
+        self.arr, self.at = arr, 0
+
+    def read(self, n):
+        out = self.arr[self.at:self.at + n]
+        self.at += out.size
+        return out
+
+
+@pytest.mark.parametrize("family", FAMILIES)
+@pytest.mark.parametrize("block", [4096, 3 * 4096, 1 << 16])
+def test_readable_streaming_blocks(family, block):
+    """match(Readable): device blocks of several sizes (context / chain state carried across blocks) must give
+    the oracle's Readable value stream, including ShortestMatchMap's fill-boundary duplicates (Q4)."""
+    from ahocorasick_b200.streaming import match_readable
+    rng = random.Random(block)
+    kws = list({_rand_word(rng, "abc", 1, 9) for _ in range(60)}) + ["a" * 40, "cab" * 20]
+    n = 150_000
+    hay = "".join(rng.choice("abc  ") for _ in range(n))
+    if family == "wholeword":
+        kws = [k for k in kws]
+    values = list(range(len(kws)))
+    om = ora.Matcher(family, kws, n_values=len(kws))
+    want = [int(r["value"]) for r in om.match(hay, readable=True)]
+    gm = MAPS[family](kws, values, True)
+    got = []
+    match_readable(gm, io.StringIO(hay), lambda v: got.append(v) or True, block_chars=block)
+    assert got == want
+    # early stop through the Readable path
+    for stop in (1, 7, 500):
+        if stop > len(want):
+            continue
+        c = Collect(stop)
+        match_readable(gm, io.StringIO(hay), c.match, block_chars=block)
+        w = [int(r["value"]) for r in om.match(hay, readable=True, stop_after=stop)]
+        assert [x[0] for x in c.calls] == w
+
+
+def test_readable_config3_wholeword_map():
+    """configs[3]: WholeWordMatchMap with the toggle word-char constructor, streamed via Readable."""
+    c = W.config(3, scale=0.02)
+    hay = W.make_haystack(c["spec"], 1_000_000)
+    kws = c["keywords"]
+    om = ora.Matcher("wholeword", kws, n_values=len(kws), word_chars_table=ora.word_chars(2, *c["word_chars"]))
+    want = [int(r["value"]) for r in om.match(hay, readable=True)]
+    gm = ac.WholeWordMatchMap(kws, list(range(len(kws))), True, *c["word_chars"])
+    got = []
+    gm.match(_NumpyReadable(hay), lambda v: got.append(v) or True)
+    assert got == want and len(want) > 100
