@@ -1,0 +1,329 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the matching hot path (BASELINE.json metric).
+
+Workload (configs[4] of BASELINE.json): AhoCorasickSet, 1,000,000 synthetic a-z keywords (len 3-12),
+case-sensitive, all overlapping matches over a 64 GB corpus = 32 independent haystacks of 10^9 UTF-16 chars
+(a Java String holds < 2^31 chars, so the corpus is necessarily many match() calls), generated ON THE DEVICE
+from SplitMix64 seeds.  The corpus is sharded by haystack across the N ranks ("strong" scaling: total fixed);
+a step = one match() of every haystack of the corpus.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path
+  python bench.py --impl reference ...                           # the reference's algorithm on the host cores
+
+One JSON line on stdout (rank 0).  `value` = haystack GB/s with inputs resident in HBM (device-timed, CUDA
+events on the launch stream, max over ranks); `e2e` = the same metric through the host-buffer C-ABI call
+acgpu_match_utf16 (H2D copy, kernels, D2H of the match records inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import workloads as W  # noqa: E402
+
+METRIC = "haystack_GB_per_s"
+UNIT = "GB/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--haystacks", type=int, default=32, help="haystacks in the corpus (total over all ranks)")
+    ap.add_argument("--chars", type=int, default=1_000_000_000, help="UTF-16 chars per haystack")
+    ap.add_argument("--keywords", type=int, default=1_000_000)
+    ap.add_argument("--e2e-chars", type=int, default=250_000_000)
+    ap.add_argument("--cpu-sample-chars", type=int, default=2_000_000, help="chars per host thread per CPU pass")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    return {
+        "workload": "configs[4]: AhoCorasickSet, %d a-z keywords (len 3-12), case-sensitive, all overlapping "
+                    "matches, %d haystacks x %d UTF-16 chars (%.1f GB corpus), sharded by haystack"
+                    % (args.keywords, args.haystacks, args.chars, args.haystacks * args.chars * 2 / 1e9),
+        "keywords": args.keywords, "haystacks": args.haystacks, "chars_per_haystack": args.chars,
+        "l2": "inputs larger than L2 (each haystack is %.1f GB; no flush needed)" % (args.chars * 2 / 1e9),
+        "dict_seed": 1005, "haystack_seed": "2005+i",
+    }
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle on host cores)
+
+def cpu_pass(matcher, slices, results):
+    threads = []
+    for i, sl in enumerate(slices):
+        def run(i=i, sl=sl):
+            results[i] = matcher.count(sl)
+        t = threading.Thread(target=run)
+        threads.append(t)
+        t.start()
+    for t in threads:
+        t.join()
+
+
+def cpu_measure(args, keywords, spec, passes: int, warm: int):
+    """All host threads, one independent match() per thread over disjoint slices of haystack 0 (the only
+    parallelism the reference API allows).  ctypes releases the GIL inside the oracle call."""
+    from oracle import oracle as ora
+    cores = os.cpu_count() or 1
+    m = ora.Matcher("ahocorasick", keywords, case_sensitive=True)
+    n = args.cpu_sample_chars
+    slices = [W.make_haystack(spec, n, start=i * ((n + 63) // 64 * 64)) for i in range(cores)]
+    res = [0] * cores
+    for _ in range(warm):
+        cpu_pass(m, slices, res)
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        cpu_pass(m, slices, res)
+    dt = (time.perf_counter() - t0) / passes
+    gbps = cores * n * 2 / dt / 1e9
+    return dict(value=gbps, unit=UNIT, cores=cores, kind="port",
+                sample="%d threads x %d chars of haystack 0 per pass (AhoCorasickSet, same dictionary); "
+                       "literal C restatement of the reference (no JVM in this image), gcc -O2" % (cores, n),
+                matches_per_s=sum(res) / dt, ms_per_pass=dt * 1e3)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = W.config(4, scale=args.keywords / 1_000_000)
+    kws = cfg["keywords"]
+    spec = W.HaystackSpec("lower", 2005, kws)
+    r = cpu_measure(args, kws, spec, passes=args.steps, warm=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_pass"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": workload_config(args), "matches_per_s": r["matches_per_s"],
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- our arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ahocorasick_b200 as ac
+    from ahocorasick_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the matching path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    lib = _lib.lib()
+    cfg = W.config(4, scale=args.keywords / 1_000_000)
+    kws = cfg["keywords"]
+    t0 = time.perf_counter()
+    matcher = ac.AhoCorasickSet(kws, True, device=local_rank)
+    build_s = time.perf_counter() - t0
+    info = matcher.info()
+
+    # corpus shard of this rank: haystacks rank, rank+world, ... generated on the device
+    mine = list(range(rank, args.haystacks, world))
+    n = args.chars
+    hays = []
+    for i in mine:
+        spec = W.HaystackSpec("lower", 2005 + i, kws)
+        hays.append(W.make_haystack_torch(spec, n, device=dev))
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+    # size the record buffer from a counting run (cap = 0 writes nothing, the kernel still counts)
+    counts = []
+    for h in hays:
+        tot = C.c_int64(0)
+        _lib.check(lib.acgpu_match_device(matcher.handle, h.data_ptr(), n, 0, n, None, None, 0, C.byref(tot), sp))
+        counts.append(tot.value)
+    cap = max(counts) if counts else 0
+    d_pos = torch.empty((max(cap, 1), 2), dtype=torch.int32, device=dev)
+    d_tot = torch.zeros(max(len(hays), 1), dtype=torch.int64, device=dev)
+    launches = lib.acgpu_launches_per_match(matcher.handle)
+
+    def step():
+        for j, h in enumerate(hays):
+            _lib.check(lib.acgpu_match_device_async(matcher.handle, h.data_ptr(), n, 0, n, d_pos.data_ptr(), None, cap,
+                                                    d_tot[j:].data_ptr(), sp))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    got = d_tot[:len(hays)].tolist()
+    assert got == counts, "match counts changed between runs: %r vs %r" % (got, counts)
+
+    # per-shard match counts: the one exchange the path has — all_gather over NCCL
+    my_matches = torch.tensor([sum(counts)], dtype=torch.int64, device=dev)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        gathered = [torch.zeros_like(my_matches) for _ in range(world)]
+        dist.all_gather(gathered, my_matches)
+        total_matches = int(sum(int(g.item()) for g in gathered))
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    else:
+        total_matches = int(my_matches.item())
+    ms_max = float(t_ms.item())
+    ms_per_step = ms_max / args.steps
+    total_chars = args.haystacks * n
+    value = total_chars * 2 / (ms_per_step * 1e-3) / 1e9
+    matches_per_s = total_matches / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel (k_ac_scan): algorithmic bytes per launch / average launch duration
+    n_launch = max(len(hays), 1)
+    alg_bytes = 2 * n + 8 * (sum(counts) / n_launch)
+    launch_ms = ms / args.steps / n_launch
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_ac_scan", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
+                "haystack_only_frac": (2 * n / (launch_ms * 1e-3) / 1e9) / peak}
+
+    # end-to-end through the host-buffer C-ABI call (H2D + kernels + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        ne = min(n, args.e2e_chars)
+        spec0 = W.HaystackSpec("lower", 2005 + (mine[0] if mine else 0), kws)
+        host = torch.empty(ne, dtype=torch.int16, pin_memory=True)
+        host.copy_(W.make_haystack_torch(spec0, ne, device=dev).cpu())
+        res = _lib.Result()
+        times, n_rec = [], 0
+        for it in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            _lib.check(lib.acgpu_match_utf16(matcher.handle, host.data_ptr(), ne, C.byref(res)))
+            dt = time.perf_counter() - t0
+            n_rec = int(res.n)
+            lib.acgpu_free_result(C.byref(res))
+            if it > 0:
+                times.append(dt)
+        t_e = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * ne * 2 / float(t_e.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": ne * 2,
+               "d2h_bytes_per_step": n_rec * 8,
+               "note": "acgpu_match_utf16 on one %d-char haystack per rank from pinned host memory, "
+                       "records copied back to host; mean of 2 after 1 warm-up" % ne}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_measure(args, kws, W.HaystackSpec("lower", 2005, kws), passes=2, warm=1)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u16", "data": "synthetic", "config": workload_config(args),
+            "matches_per_s": matches_per_s, "matches_per_step": total_matches,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * len(hays) * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu,
+            "dictionary": dict(info, build_seconds=build_s),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
