@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libacgpu.so")
 SOURCES = ["engine.cu", "builder.cpp"]
-HEADERS = ["kernels.cuh", "device_tables.cuh", "builder.hpp", "java_char_tables.h",
+HEADERS = ["kernels.cuh", "kernel_tier.cuh", "device_tables.cuh", "builder.hpp", "java_char_tables.h",
            os.path.join("..", "..", "include", "acgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-cudart", "static"]

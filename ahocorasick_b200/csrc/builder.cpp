@@ -99,6 +99,97 @@ void make_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, in
     }
 }
 
+namespace {
+
+constexpr uint64_t kTierSmemBits = 150ull * 1024 * 8;  // budget for the direct-indexed level K table
+
+void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, const std::vector<uint16_t> &node_cls) {
+    TierTables &t = a.tier;
+    t.ok = false;
+    const int64_t C = a.n_classes;
+    if (!a.has_other || a.max_len < 1 || C < 2 || C > 256) return;  // classes travel as bytes
+    int b = 1;
+    while ((1 << b) < C) b++;
+    if (static_cast<int64_t>(b) * a.max_len > 60 || a.max_len - 1 > 16) return;
+    // K = deepest level whose 2-bit table fits the shared-memory budget
+    int K = 0;
+    uint64_t entries = 1;
+    while (K < a.max_len && K < 8) {
+        if (entries * C * 2 > kTierSmemBits) break;
+        entries *= C;
+        K++;
+    }
+    if (K < 1) return;
+    t.C = static_cast<int32_t>(C);
+    t.b = b;
+    t.K = K;
+    uint64_t pw = 1;
+    uint32_t off = 0;
+    for (int j = 1; j <= K; j++) {
+        t.pow_c[j] = static_cast<uint32_t>(pw);  // C^(j-1)
+        pw *= C;
+        t.lvl_off[j] = off;
+        const uint64_t bits = pw * (j == K ? 2 : 1);
+        off += static_cast<uint32_t>((bits + 31) / 32);
+    }
+    t.smem_words.assign(off, 0);
+    const int64_t n = a.n_nodes;
+    std::vector<uint8_t> depth(n, 0);
+    std::vector<uint64_t> packed(n, 0);
+    std::vector<uint32_t> radix(n, 0);
+    uint64_t n_deep = 0;
+    for (int64_t id = 1; id < n; id++) {
+        const uint32_t p = node_parent[id];
+        const int d = depth[p] + 1;
+        depth[id] = static_cast<uint8_t>(d);
+        packed[id] = packed[p] | (static_cast<uint64_t>(node_cls[id]) << (b * (d - 1)));
+        if (d <= K) {
+            radix[id] = radix[p] + node_cls[id] * t.pow_c[d];
+        } else {
+            n_deep++;
+        }
+    }
+    uint64_t cap = 16;
+    while (cap < n_deep * 2) cap <<= 1;
+    t.deep.assign(n_deep ? cap : 16, 0);
+    t.deep_mask = static_cast<uint32_t>(t.deep.size() - 1);
+    t.n_deep = n_deep;
+    if (a.is_map) {
+        t.deep_val.assign(t.deep.size(), kNone);
+        uint64_t voff = 0, e = 1;
+        for (int j = 1; j <= K; j++) {
+            e *= C;
+            t.val_off[j] = voff;
+            voff += e;
+        }
+        t.shallow_val.assign(voff, kNone);
+    }
+    for (int64_t id = 1; id < n; id++) {
+        const int d = depth[id];
+        const uint32_t inf = a.node_info[id];
+        if (d < K) {
+            if (inf & kInfoTerminal) {
+                t.smem_words[t.lvl_off[d] + (radix[id] >> 5)] |= 1u << (radix[id] & 31);
+                t.term_levels |= 1u << d;
+            }
+        } else if (d == K) {
+            const uint32_t two = (inf & kInfoTerminal ? 1u : 0u) | (inf & kInfoHasChildren ? 2u : 0u);
+            t.smem_words[t.lvl_off[K] + (radix[id] >> 4)] |= two << ((radix[id] & 15) * 2);
+            if (inf & kInfoTerminal) t.term_levels |= 1u << d;
+        } else {
+            const uint64_t slot = (packed[id] << 4) | (inf & kInfoTerminal ? 1u : 0u) | (inf & kInfoHasChildren ? 2u : 0u);
+            uint32_t i = deep_hash(packed[id]) & t.deep_mask;
+            while (t.deep[i] != 0) i = (i + 1) & t.deep_mask;
+            t.deep[i] = slot;
+            if (a.is_map) t.deep_val[i] = a.node_value[id];
+        }
+        if (a.is_map && d <= K && (inf & kInfoTerminal)) t.shallow_val[t.val_off[d] + radix[id]] = a.node_value[id];
+    }
+    t.ok = true;
+}
+
+}  // namespace
+
 HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *offsets, const uint8_t *is_null,
                               int64_t n_keywords, int64_t n_values, bool case_sensitive,
                               const uint8_t *word_chars) {
@@ -211,6 +302,8 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
     uint32_t next_node = 1;  // node 0 = root
     std::vector<uint8_t> info(1, 0);
     std::vector<uint32_t> value(1, kNone);
+    std::vector<uint32_t> node_parent(1, 0);
+    std::vector<uint16_t> node_cls(1, 0);
     std::vector<uint32_t> depth_count(static_cast<size_t>(longest) + 1, 0);
     depth_count[0] = 1;
     const bool first_wins = (family == 2);  // ShortestMatchMap.java:44-54
@@ -224,6 +317,8 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
             if (created) {
                 info.push_back(0);
                 value.push_back(kNone);
+                node_parent.push_back(node);
+                node_cls.push_back(static_cast<uint16_t>(c));
                 info[node] |= kInfoHasChildren;
                 depth_count[static_cast<size_t>(i) + 1]++;
                 if (next_node == kNone) throw std::length_error("dictionary too large (node ids exceed 32 bits)");
@@ -262,6 +357,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
         while (a.edges[i].parent != kNone) i = (i + 1) & a.edge_mask;
         a.edges[i] = Edge{e.parent, e.cls, e.child, a.node_info[e.child]};
     }
+    build_tiers(a, node_parent, node_cls);
     return a;
 }
 

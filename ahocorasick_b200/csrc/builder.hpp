@@ -47,6 +47,37 @@ struct IllegalArgument : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
+// Generation-2 tables for narrow alphabets (every context of max_len classes packs into 60 bits):
+//   * levels 1..K of the anchored trie are DIRECT-INDEXED by the mixed-radix number of the last j classes
+//     (most recent class = lowest digit): terminal bitmaps for j < K, 2 bits (terminal, has-children) for j = K;
+//     small enough to live in shared memory
+//   * deeper nodes sit in an open-addressing table of 8-byte slots  (packed context << 4 | flags), keyed by the
+//     context itself (b bits per class), so levels are probed independently of each other
+struct TierTables {
+    bool ok = false;
+    int32_t C = 0;        // radix = number of classes (including class 0 = other)
+    int32_t b = 0;        // bits per class in the packed context
+    int32_t K = 0;        // direct-indexed levels
+    uint32_t term_levels = 0;        // bit j: some keyword has length j (j <= K)
+    uint32_t lvl_off[10] = {0};      // word offset of level j's table inside smem_words (j = 1..K)
+    uint32_t pow_c[10] = {0};        // C^(j-1)
+    std::vector<uint32_t> smem_words;
+    std::vector<uint64_t> deep;      // empty slot = 0
+    uint32_t deep_mask = 0;
+    uint64_t n_deep = 0;
+    // Map values: shallow levels indexed like the bit tables, deep values parallel to `deep`
+    std::vector<uint32_t> shallow_val;
+    uint64_t val_off[10] = {0};
+    std::vector<uint32_t> deep_val;
+};
+
+inline uint32_t deep_hash(uint64_t key) {
+    key ^= key >> 29;
+    key *= 0xBF58476D1CE4E5B9ull;
+    key ^= key >> 32;
+    return static_cast<uint32_t>(key);
+}
+
 struct HostAutomaton {
     int family = 0;
     bool is_map = false;
@@ -66,6 +97,7 @@ struct HostAutomaton {
     std::vector<uint32_t> node_value;  // n_nodes, kNone when not terminal / Set
     std::vector<uint8_t> node_info;    // n_nodes
     std::vector<uint32_t> depth_count; // nodes per depth (diagnostics / tiering)
+    TierTables tier;                   // generation-2 tables (tier.ok == false: not applicable)
 };
 
 // Throws IllegalArgument with the reference's message for WholeWord keywords holding non-word chars.

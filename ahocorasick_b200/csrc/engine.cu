@@ -14,6 +14,7 @@
 #include "../../include/acgpu.h"
 #include "builder.hpp"
 #include "kernels.cuh"
+#include "kernel_tier.cuh"
 
 using namespace acgpu;
 
@@ -47,6 +48,12 @@ struct Matcher {
     void *d_blob = nullptr;  // one allocation holding every table
     int64_t table_bytes = 0;
     bool sel_attr_set = false;
+    // generation-2 (tiered) tables, AhoCorasick family on narrow alphabets
+    bool use_tier = false;
+    bool tier_attr_set = false;
+    DevTier tier{};
+    void *d_tier_blob = nullptr;
+    size_t tier_smem = 0;
 };
 
 Matcher *as_matcher(uint64_t h) {
@@ -94,6 +101,86 @@ int upload(Matcher *m) {
     return ACGPU_OK;
 }
 
+int upload_tier(Matcher *m) {
+    const TierTables &t = m->host.tier;
+    m->use_tier = false;
+    if (!t.ok || m->host.family != ACGPU_AHOCORASICK) return ACGPU_OK;
+    const char *force = getenv("ACGPU_FORCE_GEN1");
+    if (force && force[0] == '1') return ACGPU_OK;
+    const size_t smem = (64 + t.smem_words.size()) * sizeof(uint32_t);
+    if (smem > 200 * 1024) return ACGPU_OK;
+    size_t off = 0;
+    auto reserve = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + std::max<size_t>(bytes, 16), 256);
+        return o;
+    };
+    size_t o_words = reserve(t.smem_words.size() * 4);
+    size_t o_cls8 = reserve(256);
+    size_t o_deep = reserve(t.deep.size() * 8);
+    size_t o_sval = reserve(t.shallow_val.size() * 4);
+    size_t o_dval = reserve(t.deep_val.size() * 4);
+    CU_TRY(cudaMalloc(&m->d_tier_blob, off));
+    m->table_bytes += static_cast<int64_t>(off);
+    char *b = static_cast<char *>(m->d_tier_blob);
+    uint8_t cls8[256];
+    for (int c = 0; c < 256; c++) cls8[c] = static_cast<uint8_t>(m->host.cls[c]);
+    if (!t.smem_words.empty()) CU_TRY(cudaMemcpy(b + o_words, t.smem_words.data(), t.smem_words.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(b + o_cls8, cls8, 256, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(b + o_deep, t.deep.data(), t.deep.size() * 8, cudaMemcpyHostToDevice));
+    if (!t.shallow_val.empty()) CU_TRY(cudaMemcpy(b + o_sval, t.shallow_val.data(), t.shallow_val.size() * 4, cudaMemcpyHostToDevice));
+    if (!t.deep_val.empty()) CU_TRY(cudaMemcpy(b + o_dval, t.deep_val.data(), t.deep_val.size() * 4, cudaMemcpyHostToDevice));
+    DevTier &d = m->tier;
+    d.smem_words = reinterpret_cast<const uint32_t *>(b + o_words);
+    d.cls8 = reinterpret_cast<const uint32_t *>(b + o_cls8);
+    d.deep = reinterpret_cast<const unsigned long long *>(b + o_deep);
+    d.shallow_val = reinterpret_cast<const uint32_t *>(b + o_sval);
+    d.deep_val = reinterpret_cast<const uint32_t *>(b + o_dval);
+    d.n_words = static_cast<uint32_t>(t.smem_words.size());
+    d.deep_mask = t.deep_mask;
+    d.term_levels = t.term_levels;
+    d.b = t.b;
+    d.C = t.C;
+    d.K = t.K;
+    for (int j = 0; j < 10; j++) {
+        d.lvl_off[j] = t.lvl_off[j];
+        d.pow_c[j] = t.pow_c[j];
+        d.val_off[j] = t.val_off[j];
+    }
+    m->tier_smem = smem;
+    m->use_tier = true;
+    return ACGPU_OK;
+}
+
+template <int K>
+int launch_tier_k(Matcher *m, const AcArgs &P, int grid, cudaStream_t st) {
+    if (m->dev.is_map) {
+        if (!m->tier_attr_set)
+            CU_TRY(cudaFuncSetAttribute(k_ac_tier<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tier_smem));
+        k_ac_tier<K, true><<<grid, kTierThreads, m->tier_smem, st>>>(m->dev, m->tier, P);
+    } else {
+        if (!m->tier_attr_set)
+            CU_TRY(cudaFuncSetAttribute(k_ac_tier<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tier_smem));
+        k_ac_tier<K, false><<<grid, kTierThreads, m->tier_smem, st>>>(m->dev, m->tier, P);
+    }
+    m->tier_attr_set = true;
+    CU_TRY(cudaGetLastError());
+    return ACGPU_OK;
+}
+
+int launch_tier(Matcher *m, const AcArgs &P, int grid, cudaStream_t st) {
+    switch (m->tier.K) {
+    case 1: return launch_tier_k<1>(m, P, grid, st);
+    case 2: return launch_tier_k<2>(m, P, grid, st);
+    case 3: return launch_tier_k<3>(m, P, grid, st);
+    case 4: return launch_tier_k<4>(m, P, grid, st);
+    case 5: return launch_tier_k<5>(m, P, grid, st);
+    case 6: return launch_tier_k<6>(m, P, grid, st);
+    case 7: return launch_tier_k<7>(m, P, grid, st);
+    default: return launch_tier_k<8>(m, P, grid, st);
+    }
+}
+
 // Scratch for one match call, carved from one stream-ordered allocation.
 struct Scratch {
     void *base = nullptr;
@@ -126,7 +213,8 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
         emit_from = std::max<int64_t>(0, emit_from);
         emit_to = std::min<int64_t>(n, emit_to);
         const int64_t span = std::max<int64_t>(0, emit_to - emit_from);
-        const int64_t n_tiles = (span + kAcTile - 1) / kAcTile;
+        const int64_t tile_sz = m->use_tier ? kTierTile : kAcTile;
+        const int64_t n_tiles = (span + tile_sz - 1) / tile_sz;
         if (n_tiles == 0) {
             CU_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
             return ACGPU_OK;
@@ -148,12 +236,17 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
         P.tile_counter = static_cast<unsigned int *>(ws);
         P.status = reinterpret_cast<unsigned long long *>(static_cast<char *>(ws) + 256);
         P.n_tiles = n_tiles;
-        const int grid = static_cast<int>(std::min<int64_t>(n_tiles, persistent));
-        if (A.is_map)
-            k_ac_scan<true><<<grid, kThreads, 0, st>>>(A, P);
-        else
-            k_ac_scan<false><<<grid, kThreads, 0, st>>>(A, P);
-        CU_TRY(cudaGetLastError());
+        if (m->use_tier) {
+            int rc = launch_tier(m, P, static_cast<int>(std::min<int64_t>(n_tiles, m->sm_count)), st);
+            if (rc != ACGPU_OK) return rc;
+        } else {
+            const int grid = static_cast<int>(std::min<int64_t>(n_tiles, persistent));
+            if (A.is_map)
+                k_ac_scan<true><<<grid, kThreads, 0, st>>>(A, P);
+            else
+                k_ac_scan<false><<<grid, kThreads, 0, st>>>(A, P);
+            CU_TRY(cudaGetLastError());
+        }
         CU_TRY(cudaFreeAsync(ws, st));
         return ACGPU_OK;
     }
@@ -333,8 +426,10 @@ int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t 
         cudaDeviceProp prop{};
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) m->sm_count = prop.multiProcessorCount;
         rc = upload(m);
+        if (rc == ACGPU_OK) rc = upload_tier(m);
     }
     if (rc != ACGPU_OK) {
+        if (m->d_tier_blob) cudaFree(m->d_tier_blob);
         if (m->d_blob) cudaFree(m->d_blob);
         delete m;
         return rc;
@@ -348,6 +443,7 @@ int acgpu_destroy(uint64_t handle) {
     if (!m) return fail(ACGPU_EINVAL, "bad handle");
     cudaSetDevice(m->device);
     if (m->d_blob) cudaFree(m->d_blob);
+    if (m->d_tier_blob) cudaFree(m->d_tier_blob);
     m->magic = 0;
     delete m;
     return ACGPU_OK;

@@ -162,9 +162,15 @@ def test_wholeword_custom_word_chars_config3_style():
         ac.WholeWordMatchSet(["abc"], True, ["_", "="])
 
 
+@pytest.mark.parametrize("gen1", [False, True])
 @pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
-def test_baseline_configs_scaled(cfg):
-    """The five BASELINE.json configs at a size the oracle finishes in seconds: identical ordered streams."""
+def test_baseline_configs_scaled(cfg, gen1, monkeypatch):
+    """The five BASELINE.json configs at a size the oracle finishes in seconds: identical ordered streams.
+    gen1=True forces the general anchored-trie kernel where the tiered kernel would be chosen."""
+    if gen1:
+        if cfg in (2, 3):
+            pytest.skip("tiered kernel only exists for the AhoCorasick family")
+        monkeypatch.setenv("ACGPU_FORCE_GEN1", "1")
     c = W.config(cfg, scale=0.02 if cfg != 0 else 0.25)
     n = min(c["n"], 2_000_000)
     hay = W.make_haystack(c["spec"], n)
@@ -238,3 +244,18 @@ def test_readable_config3_wholeword_map():
     got = []
     gm.match(_NumpyReadable(hay), lambda v: got.append(v) or True)
     assert got == want and len(want) > 100
+
+
+def test_full_1m_dictionary_parity(monkeypatch):
+    """configs[4] dictionary at FULL size (10^6 keywords, ~4.4M trie nodes) on a 4M-char slice: both kernel
+    generations against the oracle (dictionary-size dependent bugs do not show at the scaled configs)."""
+    c = W.config(4)
+    kws = c["keywords"]
+    hay = W.make_haystack(c["spec"], 4_000_000)
+    want = ora.Matcher("ahocorasick", kws).match(hay)
+    for gen1 in (False, True):
+        if gen1:
+            monkeypatch.setenv("ACGPU_FORCE_GEN1", "1")
+        rec = ac.AhoCorasickSet(kws, True).match_records(hay)
+        assert len(rec) == len(want), (gen1, len(rec), len(want))
+        assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"])
