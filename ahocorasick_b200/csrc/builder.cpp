@@ -107,7 +107,7 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
     TierTables &t = a.tier;
     t.ok = false;
     const int64_t C = a.n_classes;
-    if (!a.has_other || a.max_len < 1 || C < 2 || C > 256) return;  // classes travel as bytes
+    if (!a.has_other || a.max_len < 1 || C < 2 || C > 32) return;  // child masks are 32-bit words
     int b = 1;
     while ((1 << b) < C) b++;
     if (static_cast<int64_t>(b) * a.max_len > 60 || a.max_len - 1 > 16) return;
@@ -137,25 +137,23 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
     std::vector<uint8_t> depth(n, 0);
     std::vector<uint64_t> packed(n, 0);
     std::vector<uint32_t> radix(n, 0);
+    std::vector<uint32_t> kids(n, 0);
     uint64_t n_deep = 0;
     for (int64_t id = 1; id < n; id++) {
         const uint32_t p = node_parent[id];
         const int d = depth[p] + 1;
         depth[id] = static_cast<uint8_t>(d);
         packed[id] = packed[p] | (static_cast<uint64_t>(node_cls[id]) << (b * (d - 1)));
+        kids[p] |= 1u << node_cls[id];
         if (d <= K) {
             radix[id] = radix[p] + node_cls[id] * t.pow_c[d];
         } else {
             n_deep++;
         }
     }
-    uint64_t cap = 16;
-    while (cap < n_deep * 2) cap <<= 1;
-    t.deep.assign(n_deep ? cap : 16, 0);
-    t.deep_mask = static_cast<uint32_t>(t.deep.size() - 1);
     t.n_deep = n_deep;
+    if (a.max_len > K) t.kidmask.assign(entries, 0);
     if (a.is_map) {
-        t.deep_val.assign(t.deep.size(), kNone);
         uint64_t voff = 0, e = 1;
         for (int j = 1; j <= K; j++) {
             e *= C;
@@ -176,16 +174,54 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
             const uint32_t two = (inf & kInfoTerminal ? 1u : 0u) | (inf & kInfoHasChildren ? 2u : 0u);
             t.smem_words[t.lvl_off[K] + (radix[id] >> 4)] |= two << ((radix[id] & 15) * 2);
             if (inf & kInfoTerminal) t.term_levels |= 1u << d;
-        } else {
-            const uint64_t slot = (packed[id] << 4) | (inf & kInfoTerminal ? 1u : 0u) | (inf & kInfoHasChildren ? 2u : 0u);
-            uint32_t i = deep_hash(packed[id]) & t.deep_mask;
-            while (t.deep[i] != 0) i = (i + 1) & t.deep_mask;
-            t.deep[i] = slot;
-            if (a.is_map) t.deep_val[i] = a.node_value[id];
+            if (!t.kidmask.empty()) t.kidmask[radix[id]] = kids[id];
         }
         if (a.is_map && d <= K && (inf & kInfoTerminal)) t.shallow_val[t.val_off[d] + radix[id]] = a.node_value[id];
     }
-    t.ok = true;
+    // bucketed deep table (4 entries per 32-byte bucket, load factor <= 0.5); retry with another seed if two
+    // entries on one probe path would share a tag
+    uint64_t n_buckets = 4;
+    while (n_buckets * 2 < n_deep) n_buckets <<= 1;
+    t.bucket_mask = static_cast<uint32_t>(n_buckets - 1);
+    for (int attempt = 0; attempt < 16; attempt++) {
+        t.hash_seed = 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(attempt + 1);
+        t.buckets.assign(n_buckets * 8, 0);
+        if (a.is_map) t.deep_val.assign(n_buckets * 4, kNone);
+        bool clash = false;
+        for (int64_t id = 1; id < n && !clash; id++) {
+            if (depth[id] <= K) continue;
+            const uint32_t inf = a.node_info[id];
+            const uint64_t h = deep_hash64(packed[id], t.hash_seed);
+            const uint32_t want = (static_cast<uint32_t>(h >> 36) << 4) | 8u;
+            uint32_t bk = static_cast<uint32_t>(h) & t.bucket_mask;
+            while (true) {
+                uint32_t *e = &t.buckets[static_cast<size_t>(bk) * 8];
+                int free_slot = -1;
+                for (int k = 0; k < 4; k++) {
+                    if (e[2 * k] == 0) {
+                        if (free_slot < 0) free_slot = k;
+                    } else if ((e[2 * k] & ~7u) == want) {
+                        clash = true;
+                    }
+                }
+                if (clash) break;
+                if (free_slot >= 0) {
+                    e[2 * free_slot] = want | (inf & kInfoTerminal ? 1u : 0u) | (inf & kInfoHasChildren ? 2u : 0u);
+                    e[2 * free_slot + 1] = kids[id];
+                    if (a.is_map) t.deep_val[static_cast<size_t>(bk) * 4 + free_slot] = a.node_value[id];
+                    break;
+                }
+                bk = (bk + 1) & t.bucket_mask;
+            }
+        }
+        // a later insertion may put an equal tag into a bucket that an earlier key's probe path crosses only if
+        // that bucket was full when the earlier key passed it - and full buckets never change, so checking at
+        // insertion time against every bucket passed (done above) is sufficient.
+        if (!clash) {
+            t.ok = true;
+            return;
+        }
+    }
 }
 
 }  // namespace

@@ -47,12 +47,17 @@ struct IllegalArgument : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
-// Generation-2 tables for narrow alphabets (every context of max_len classes packs into 60 bits):
+// Generation-2 tables for narrow alphabets (at most 32 classes, every context of max_len classes packs into
+// 60 bits):
 //   * levels 1..K of the anchored trie are DIRECT-INDEXED by the mixed-radix number of the last j classes
 //     (most recent class = lowest digit): terminal bitmaps for j < K, 2 bits (terminal, has-children) for j = K;
 //     small enough to live in shared memory
-//   * deeper nodes sit in an open-addressing table of 8-byte slots  (packed context << 4 | flags), keyed by the
-//     context itself (b bits per class), so levels are probed independently of each other
+//   * kidmask[level-K index] = set of classes that continue the context (exact), so level K+1 is only probed
+//     for contexts that exist
+//   * deeper nodes sit in a bucketed table keyed by the packed context itself (b bits per class): a bucket is one
+//     32-byte sector holding four 8-byte entries {28-bit tag | occupied | flags, child mask}.  Because child masks
+//     are exact, every probe is for a key that exists, and the builder guarantees that no bucket on a key's probe
+//     path holds another entry with the same tag - so a tag match is exact and one sector load resolves one level.
 struct TierTables {
     bool ok = false;
     int32_t C = 0;        // radix = number of classes (including class 0 = other)
@@ -62,20 +67,25 @@ struct TierTables {
     uint32_t lvl_off[10] = {0};      // word offset of level j's table inside smem_words (j = 1..K)
     uint32_t pow_c[10] = {0};        // C^(j-1)
     std::vector<uint32_t> smem_words;
-    std::vector<uint64_t> deep;      // empty slot = 0
-    uint32_t deep_mask = 0;
+    std::vector<uint32_t> kidmask;   // per level-K entry, bit c = the node has a child on class c
+    std::vector<uint32_t> buckets;   // 8 words per bucket: 4 x {tag << 4 | 8 | flags, child mask}
+    uint32_t bucket_mask = 0;
+    uint64_t hash_seed = 0;
     uint64_t n_deep = 0;
-    // Map values: shallow levels indexed like the bit tables, deep values parallel to `deep`
+    // Map values: shallow levels indexed like the bit tables, deep values indexed by bucket * 4 + entry
     std::vector<uint32_t> shallow_val;
     uint64_t val_off[10] = {0};
     std::vector<uint32_t> deep_val;
 };
 
-inline uint32_t deep_hash(uint64_t key) {
-    key ^= key >> 29;
-    key *= 0xBF58476D1CE4E5B9ull;
-    key ^= key >> 32;
-    return static_cast<uint32_t>(key);
+inline uint64_t deep_hash64(uint64_t key, uint64_t seed) {
+    uint64_t h = key ^ seed;
+    h ^= h >> 29;
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 32;
+    h *= 0x94D049BB133111EBull;
+    h ^= h >> 29;
+    return h;
 }
 
 struct HostAutomaton {

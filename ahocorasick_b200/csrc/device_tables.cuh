@@ -72,21 +72,28 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Called by ONE full warp (all 32 lanes).  Publishes this tile's aggregate, looks back over predecessor
-// tiles 32 at a time and returns the exclusive prefix (sum of aggregates of tiles < tile) to every lane.
-__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long *status, int64_t tile,
-                                                                 unsigned long long aggregate) {
+// Step 1 (one lane): make this tile's aggregate visible.  Tile 0 has no predecessors: its aggregate is its
+// inclusive prefix.
+__device__ __forceinline__ void lookback_publish(unsigned long long *status, int64_t tile, unsigned long long aggregate) {
+    st_status(&status[tile], (tile == 0 ? kFlagInc : kFlagAgg) | aggregate);
+}
+
+// Step 2, called by ONE full warp (all 32 lanes): looks back over predecessor tiles 32 at a time, returns the
+// exclusive prefix (sum of aggregates of tiles < tile) to every lane and publishes the inclusive prefix.
+__device__ __forceinline__ unsigned long long lookback_resolve(unsigned long long *status, int64_t tile,
+                                                               unsigned long long aggregate) {
     const int lane = threadIdx.x & 31;
-    if (lane == 0) st_status(&status[tile], (tile == 0 ? kFlagInc : kFlagAgg) | aggregate);
     unsigned long long exclusive = 0;
     int64_t base = tile - 1;
     while (base >= 0) {
         int64_t idx = base - lane;
         unsigned long long w = kFlagInc;  // lanes before tile 0 behave like "inclusive prefix 0"
         if (idx >= 0) {
-            do {
+            w = ld_status(&status[idx]);
+            while ((w >> 62) == 0) {
+                __nanosleep(64);
                 w = ld_status(&status[idx]);
-            } while ((w >> 62) == 0);
+            }
         }
         unsigned inc_mask = __ballot_sync(0xFFFFFFFFu, (w >> 62) == 2);
         // nearest predecessor holding an inclusive prefix = lowest lane with the flag
@@ -100,6 +107,13 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long l
     }
     if (lane == 0 && tile != 0) st_status(&status[tile], kFlagInc | (exclusive + aggregate));
     return exclusive;
+}
+
+// publish + resolve back to back (block-level tiles)
+__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long *status, int64_t tile,
+                                                                 unsigned long long aggregate) {
+    if ((threadIdx.x & 31) == 0) lookback_publish(status, tile, aggregate);
+    return lookback_resolve(status, tile, aggregate);
 }
 
 }  // namespace acgpu

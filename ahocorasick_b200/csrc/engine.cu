@@ -107,8 +107,8 @@ int upload_tier(Matcher *m) {
     if (!t.ok || m->host.family != ACGPU_AHOCORASICK) return ACGPU_OK;
     const char *force = getenv("ACGPU_FORCE_GEN1");
     if (force && force[0] == '1') return ACGPU_OK;
-    const size_t smem = (64 + t.smem_words.size()) * sizeof(uint32_t);
-    if (smem > 200 * 1024) return ACGPU_OK;
+    const size_t smem = (64 + ((t.smem_words.size() + 3) & ~size_t(3))) * sizeof(uint32_t) + tier_stage_bytes(m->host.is_map);
+    if (smem > 220 * 1024) return ACGPU_OK;
     size_t off = 0;
     auto reserve = [&](size_t bytes) {
         size_t o = off;
@@ -117,7 +117,8 @@ int upload_tier(Matcher *m) {
     };
     size_t o_words = reserve(t.smem_words.size() * 4);
     size_t o_cls8 = reserve(256);
-    size_t o_deep = reserve(t.deep.size() * 8);
+    size_t o_kid = reserve(t.kidmask.size() * 4);
+    size_t o_deep = reserve(t.buckets.size() * 4);
     size_t o_sval = reserve(t.shallow_val.size() * 4);
     size_t o_dval = reserve(t.deep_val.size() * 4);
     CU_TRY(cudaMalloc(&m->d_tier_blob, off));
@@ -127,17 +128,20 @@ int upload_tier(Matcher *m) {
     for (int c = 0; c < 256; c++) cls8[c] = static_cast<uint8_t>(m->host.cls[c]);
     if (!t.smem_words.empty()) CU_TRY(cudaMemcpy(b + o_words, t.smem_words.data(), t.smem_words.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(b + o_cls8, cls8, 256, cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(b + o_deep, t.deep.data(), t.deep.size() * 8, cudaMemcpyHostToDevice));
+    if (!t.kidmask.empty()) CU_TRY(cudaMemcpy(b + o_kid, t.kidmask.data(), t.kidmask.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(b + o_deep, t.buckets.data(), t.buckets.size() * 4, cudaMemcpyHostToDevice));
     if (!t.shallow_val.empty()) CU_TRY(cudaMemcpy(b + o_sval, t.shallow_val.data(), t.shallow_val.size() * 4, cudaMemcpyHostToDevice));
     if (!t.deep_val.empty()) CU_TRY(cudaMemcpy(b + o_dval, t.deep_val.data(), t.deep_val.size() * 4, cudaMemcpyHostToDevice));
     DevTier &d = m->tier;
     d.smem_words = reinterpret_cast<const uint32_t *>(b + o_words);
     d.cls8 = reinterpret_cast<const uint32_t *>(b + o_cls8);
-    d.deep = reinterpret_cast<const unsigned long long *>(b + o_deep);
+    d.kidmask = t.kidmask.empty() ? nullptr : reinterpret_cast<const uint32_t *>(b + o_kid);
+    d.buckets = reinterpret_cast<const uint4 *>(b + o_deep);
+    d.hash_seed = t.hash_seed;
     d.shallow_val = reinterpret_cast<const uint32_t *>(b + o_sval);
     d.deep_val = reinterpret_cast<const uint32_t *>(b + o_dval);
     d.n_words = static_cast<uint32_t>(t.smem_words.size());
-    d.deep_mask = t.deep_mask;
+    d.bucket_mask = t.bucket_mask;
     d.term_levels = t.term_levels;
     d.b = t.b;
     d.C = t.C;
@@ -152,19 +156,18 @@ int upload_tier(Matcher *m) {
     return ACGPU_OK;
 }
 
+// The tiered kernel assigns rows statically and lets a warp wait for rows of lower index, so every CTA of the
+// grid must be resident at once: launched cooperatively (fails loudly instead of dead-locking).
 template <int K>
 int launch_tier_k(Matcher *m, const AcArgs &P, int grid, cudaStream_t st) {
-    if (m->dev.is_map) {
-        if (!m->tier_attr_set)
-            CU_TRY(cudaFuncSetAttribute(k_ac_tier<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tier_smem));
-        k_ac_tier<K, true><<<grid, kTierThreads, m->tier_smem, st>>>(m->dev, m->tier, P);
-    } else {
-        if (!m->tier_attr_set)
-            CU_TRY(cudaFuncSetAttribute(k_ac_tier<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tier_smem));
-        k_ac_tier<K, false><<<grid, kTierThreads, m->tier_smem, st>>>(m->dev, m->tier, P);
+    void *args[3] = {const_cast<DevAutomaton *>(&m->dev), const_cast<DevTier *>(&m->tier), const_cast<AcArgs *>(&P)};
+    const void *fn = m->dev.is_map ? reinterpret_cast<const void *>(k_ac_tier<K, true>)
+                                   : reinterpret_cast<const void *>(k_ac_tier<K, false>);
+    if (!m->tier_attr_set) {
+        CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tier_smem));
+        m->tier_attr_set = true;
     }
-    m->tier_attr_set = true;
-    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kTierThreads), args, m->tier_smem, st));
     return ACGPU_OK;
 }
 
@@ -213,7 +216,7 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
         emit_from = std::max<int64_t>(0, emit_from);
         emit_to = std::min<int64_t>(n, emit_to);
         const int64_t span = std::max<int64_t>(0, emit_to - emit_from);
-        const int64_t tile_sz = m->use_tier ? kTierTile : kAcTile;
+        const int64_t tile_sz = m->use_tier ? kTierRow : kAcTile;
         const int64_t n_tiles = (span + tile_sz - 1) / tile_sz;
         if (n_tiles == 0) {
             CU_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
@@ -237,7 +240,8 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
         P.status = reinterpret_cast<unsigned long long *>(static_cast<char *>(ws) + 256);
         P.n_tiles = n_tiles;
         if (m->use_tier) {
-            int rc = launch_tier(m, P, static_cast<int>(std::min<int64_t>(n_tiles, m->sm_count)), st);
+            const int64_t ctas = (n_tiles + kTierWarps - 1) / kTierWarps;
+            int rc = launch_tier(m, P, static_cast<int>(std::min<int64_t>(ctas, m->sm_count)), st);
             if (rc != ACGPU_OK) return rc;
         } else {
             const int grid = static_cast<int>(std::min<int64_t>(n_tiles, persistent));
