@@ -1,0 +1,144 @@
+package com.roklenarcic.util.strings.gpu;
+
+import java.io.IOException;
+import java.nio.CharBuffer;
+import java.util.ArrayList;
+import java.util.Iterator;
+import java.util.List;
+
+import com.roklenarcic.util.strings.MapMatchListener;
+import com.roklenarcic.util.strings.ReadableMatchListener;
+import com.roklenarcic.util.strings.SetMatchListener;
+
+/**
+ * Shared body of the eight drop-in classes: flatten the Iterables into the arrays acgpu_create_from_keywords takes,
+ * call the native scan, replay the ordered records to the listener with the reference's early-stop behaviour
+ * (ahocorasick_b200/matchers.py is the tested twin of this class).
+ */
+abstract class GpuMatcher<T> implements AutoCloseable {
+    private final long handle;
+    private final int family;
+    private final Object[] values; // null for Sets; index = the valueIdx the kernels report
+
+    GpuMatcher(int family, Iterable<String> keywords, Iterable<? extends T> valuesIn, boolean caseSensitive,
+            boolean[] wordChars) {
+        this.family = family;
+        List<String> kws = new ArrayList<String>();
+        List<Object> vals = valuesIn == null ? null : new ArrayList<Object>();
+        Iterator<String> ki = keywords.iterator();
+        Iterator<? extends T> vi = valuesIn == null ? null : valuesIn.iterator();
+        // Maps zip keywords with values and stop at the shorter (AhoCorasickMap.java:32); null/empty keywords are
+        // skipped by the builder but still consume a value (AhoCorasickMap.java:33-36).
+        while (ki.hasNext() && (vi == null || vi.hasNext())) {
+            kws.add(ki.next());
+            if (vi != null) {
+                vals.add(vi.next());
+            }
+        }
+        int total = 0;
+        for (String k : kws) {
+            total += k == null ? 0 : k.length();
+        }
+        char[] chars = new char[Math.max(total, 1)];
+        long[] offsets = new long[kws.size() + 1];
+        byte[] isNull = new byte[Math.max(kws.size(), 1)];
+        int at = 0;
+        for (int i = 0; i < kws.size(); i++) {
+            String k = kws.get(i);
+            offsets[i] = at;
+            if (k == null) {
+                isNull[i] = 1;
+            } else {
+                k.getChars(0, k.length(), chars, at);
+                at += k.length();
+            }
+        }
+        offsets[kws.size()] = at;
+        this.values = vals == null ? null : vals.toArray();
+        this.handle = AcGpuNative.create(family, chars, offsets, isNull, kws.size(), vals == null ? -1 : vals.size(),
+                caseSensitive, wordChars, 0);
+    }
+
+    public void close() {
+        AcGpuNative.destroy(handle);
+    }
+
+    /** StringSet.match(String, SetMatchListener) — StringSet.java:4 */
+    protected void matchSet(String haystack, SetMatchListener listener) {
+        int[] pos = (int[]) AcGpuNative.match(handle, haystack)[0];
+        int n = pos.length / 2;
+        for (int i = 0; i < n; i++) {
+            boolean more = listener.match(haystack, pos[2 * i], pos[2 * i + 1]);
+            if (family == AcGpuNative.SHORTEST) {
+                // ShortestMatchSet.java:196-226: the match ending at haystack.length() is emitted post-loop (return
+                // value ignored); a `false` on any other match falls into the post-loop emit and delivers it again.
+                if (pos[2 * i + 1] == haystack.length()) {
+                    return;
+                }
+                if (!more) {
+                    listener.match(haystack, pos[2 * i], pos[2 * i + 1]);
+                    return;
+                }
+            } else if (!more) {
+                return;
+            }
+        }
+    }
+
+    /** StringMap.match(String, MapMatchListener) — StringMap.java:8 */
+    @SuppressWarnings("unchecked")
+    protected void matchMap(String haystack, MapMatchListener<T> listener) {
+        Object[] r = AcGpuNative.match(handle, haystack);
+        int[] pos = (int[]) r[0], val = (int[]) r[1];
+        for (int i = 0; i < val.length; i++) {
+            T v = (T) values[val[i]];
+            boolean more = listener.match(haystack, pos[2 * i], pos[2 * i + 1], v);
+            if (family == AcGpuNative.SHORTEST) {
+                if (pos[2 * i + 1] == haystack.length()) {
+                    return;
+                }
+                if (!more) {
+                    listener.match(haystack, pos[2 * i], pos[2 * i + 1], v);
+                    return;
+                }
+            } else if (!more) {
+                return;
+            }
+        }
+    }
+
+    /**
+     * StringMap.match(Readable, ReadableMatchListener) — StringMap.java:6.  Reads the Readable in charBufferSize
+     * fills exactly like the reference (AhoCorasickMap.java:213-219) and forwards them in 4 MiB blocks; the Shortest
+     * family re-delivers a match that ends on a fill boundary (quirk Q4, ShortestMatchMap.java:241-249): the replay
+     * knows every fill boundary, so it is applied here (see ahocorasick_b200/streaming.py for the tested twin).
+     */
+    @SuppressWarnings("unchecked")
+    protected void matchReadable(Readable haystack, ReadableMatchListener<T> listener) throws IOException {
+        long s = AcGpuNative.streamBegin(handle);
+        boolean ended = false;
+        try {
+            CharBuffer buf = CharBuffer.allocate(1 << 21);
+            while (haystack.read(buf) != -1) {
+                buf.flip();
+                Object[] r = AcGpuNative.streamFeed(s, buf.array(), buf.remaining());
+                for (int v : (int[]) r[1]) {
+                    if (!listener.match((T) values[v])) {
+                        return;
+                    }
+                }
+                buf.clear();
+            }
+            ended = true;
+            for (int v : (int[]) AcGpuNative.streamEnd(s)[1]) {
+                if (!listener.match((T) values[v])) {
+                    return;
+                }
+            }
+        } finally {
+            if (!ended) {
+                AcGpuNative.streamEnd(s);
+            }
+        }
+    }
+}

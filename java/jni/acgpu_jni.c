@@ -1,0 +1,110 @@
+/*
+ * JNI glue: com.roklenarcic.util.strings.gpu.AcGpuNative -> libacgpu.so (include/acgpu.h).
+ * Build (outside this image; needs a JDK for jni.h):
+ *   gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux -Iinclude java/jni/acgpu_jni.c \
+ *       -Lahocorasick_b200 -lacgpu -o libacgpu_jni.so
+ * No matching logic lives here: arrays are pinned, the C entry point is called, the records are copied into
+ * Java int[]s.  Not compiled in this repository's image (no JDK) — see INTEGRATION.md.
+ */
+#include <jni.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "acgpu.h"
+
+static void throw_for(JNIEnv *env, int rc) {
+    const char *cls = rc == ACGPU_EILLEGALARG ? "java/lang/IllegalArgumentException"
+                    : rc == ACGPU_ENOMEM      ? "java/lang/OutOfMemoryError"
+                                              : "java/lang/RuntimeException";
+    (*env)->ThrowNew(env, (*env)->FindClass(env, cls), acgpu_last_error());
+}
+
+static jobjectArray wrap_result(JNIEnv *env, acgpu_result *r) {
+    jobjectArray out = (*env)->NewObjectArray(env, 2, (*env)->FindClass(env, "java/lang/Object"), NULL);
+    jintArray pos = (*env)->NewIntArray(env, (jsize)(2 * r->n));
+    if (r->n) (*env)->SetIntArrayRegion(env, pos, 0, (jsize)(2 * r->n), (const jint *)r->pos);
+    (*env)->SetObjectArrayElement(env, out, 0, pos);
+    if (r->val) {
+        jintArray val = (*env)->NewIntArray(env, (jsize)r->n);
+        (*env)->SetIntArrayRegion(env, val, 0, (jsize)r->n, (const jint *)r->val);
+        (*env)->SetObjectArrayElement(env, out, 1, val);
+    } else if (r->n == 0) {
+        (*env)->SetObjectArrayElement(env, out, 1, (*env)->NewIntArray(env, 0));
+    }
+    acgpu_free_result(r);
+    return out;
+}
+
+JNIEXPORT jlong JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_create(
+    JNIEnv *env, jclass c, jint family, jcharArray chars, jlongArray offsets, jbyteArray isNull, jlong nKeywords,
+    jlong nValues, jboolean caseSensitive, jbooleanArray wordChars, jint device) {
+    jchar *pc = (*env)->GetCharArrayElements(env, chars, NULL);
+    jlong *po = (*env)->GetLongArrayElements(env, offsets, NULL);
+    jbyte *pn = (*env)->GetByteArrayElements(env, isNull, NULL);
+    jboolean *pw = wordChars ? (*env)->GetBooleanArrayElements(env, wordChars, NULL) : NULL;
+    uint64_t h = 0;
+    int rc = acgpu_create_from_keywords(family, (const uint16_t *)pc, (const int64_t *)po, (const uint8_t *)pn,
+                                        nKeywords, nValues, caseSensitive ? 1 : 0, (const uint8_t *)pw, device, &h);
+    (*env)->ReleaseCharArrayElements(env, chars, pc, JNI_ABORT);
+    (*env)->ReleaseLongArrayElements(env, offsets, po, JNI_ABORT);
+    (*env)->ReleaseByteArrayElements(env, isNull, pn, JNI_ABORT);
+    if (pw) (*env)->ReleaseBooleanArrayElements(env, wordChars, pw, JNI_ABORT);
+    if (rc != ACGPU_OK) throw_for(env, rc);
+    return (jlong)h;
+}
+
+JNIEXPORT void JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_destroy(JNIEnv *env, jclass c, jlong h) {
+    acgpu_destroy((uint64_t)h);
+}
+
+JNIEXPORT jobjectArray JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_match(JNIEnv *env, jclass c, jlong h,
+                                                                                       jstring haystack) {
+    const jsize n = (*env)->GetStringLength(env, haystack);
+    const jchar *p = (*env)->GetStringCritical(env, haystack, NULL); /* pins the char[]; no JNI calls until release */
+    acgpu_result r;
+    int rc = acgpu_match_utf16((uint64_t)h, (const uint16_t *)p, (int32_t)n, &r);
+    (*env)->ReleaseStringCritical(env, haystack, p);
+    if (rc != ACGPU_OK) {
+        throw_for(env, rc);
+        return NULL;
+    }
+    return wrap_result(env, &r);
+}
+
+JNIEXPORT jlong JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_streamBegin(JNIEnv *env, jclass c, jlong h) {
+    uint64_t s = 0;
+    int rc = acgpu_stream_begin((uint64_t)h, &s);
+    if (rc != ACGPU_OK) throw_for(env, rc);
+    return (jlong)s;
+}
+
+JNIEXPORT jobjectArray JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_streamFeed(JNIEnv *env, jclass c,
+                                                                                            jlong s, jcharArray buf,
+                                                                                            jint n) {
+    jchar *p = (*env)->GetPrimitiveArrayCritical(env, buf, NULL);
+    acgpu_result r;
+    int rc = acgpu_stream_feed((uint64_t)s, (const uint16_t *)p, n, &r);
+    (*env)->ReleasePrimitiveArrayCritical(env, buf, p, JNI_ABORT);
+    if (rc != ACGPU_OK) {
+        throw_for(env, rc);
+        return NULL;
+    }
+    return wrap_result(env, &r);
+}
+
+JNIEXPORT jobjectArray JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_streamEnd(JNIEnv *env, jclass c,
+                                                                                           jlong s) {
+    acgpu_result r;
+    int rc = acgpu_stream_end((uint64_t)s, &r);
+    if (rc != ACGPU_OK) {
+        throw_for(env, rc);
+        return NULL;
+    }
+    return wrap_result(env, &r);
+}
+
+JNIEXPORT jint JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_charBufferSize(JNIEnv *env, jclass c, jlong h) {
+    int32_t cbs = 0;
+    acgpu_info((uint64_t)h, NULL, NULL, NULL, &cbs, NULL);
+    return cbs;
+}
