@@ -101,7 +101,7 @@ void make_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, in
 
 namespace {
 
-constexpr uint64_t kTierSmemBits = 150ull * 1024 * 8;  // budget for the direct-indexed level K table
+constexpr uint64_t kTierSmemBits = 152ull * 1024 * 8;  // shared-memory budget for ALL direct-indexed level tables
 
 void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, const std::vector<uint16_t> &node_cls) {
     TierTables &t = a.tier;
@@ -113,9 +113,11 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
     if (static_cast<int64_t>(b) * a.max_len > 60 || a.max_len - 1 > 16) return;
     // K = deepest level whose 2-bit table fits the shared-memory budget
     int K = 0;
-    uint64_t entries = 1;
+    uint64_t entries = 1, lower_bits = 0;  // lower_bits: 1-bit tables of the levels below K (word-rounded)
     while (K < a.max_len && K < 8) {
-        if (entries * C * 2 > kTierSmemBits) break;
+        const uint64_t lower_next = lower_bits + (K >= 1 ? (entries + 31) / 32 * 32 : 0);
+        if (lower_next + entries * C * 2 + 32 > kTierSmemBits) break;
+        lower_bits = lower_next;
         entries *= C;
         K++;
     }

@@ -9,6 +9,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <initializer_list>
 #include <vector>
 
 #include "../../include/acgpu.h"
@@ -107,8 +108,8 @@ int upload_tier(Matcher *m) {
     if (!t.ok || m->host.family != ACGPU_AHOCORASICK) return ACGPU_OK;
     const char *force = getenv("ACGPU_FORCE_GEN1");
     if (force && force[0] == '1') return ACGPU_OK;
-    const size_t smem = (64 + ((t.smem_words.size() + 3) & ~size_t(3))) * sizeof(uint32_t) + tier_stage_bytes(m->host.is_map);
-    if (smem > 220 * 1024) return ACGPU_OK;
+    const size_t smem = tier_smem_bytes(t.smem_words.size(), m->host.is_map);
+    if (smem > 227 * 1024) return ACGPU_OK;
     size_t off = 0;
     auto reserve = [&](size_t bytes) {
         size_t o = off;
@@ -215,9 +216,12 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
     if (A.family == ACGPU_AHOCORASICK) {
         emit_from = std::max<int64_t>(0, emit_from);
         emit_to = std::min<int64_t>(n, emit_to);
-        const int64_t span = std::max<int64_t>(0, emit_to - emit_from);
-        const int64_t tile_sz = m->use_tier ? kTierRow : kAcTile;
-        const int64_t n_tiles = (span + tile_sz - 1) / tile_sz;
+        // k_ac_tier rows start at `origin` <= emit_from, placed so that every lane's 8-char load is 16-byte aligned
+        const int64_t mis = static_cast<int64_t>((reinterpret_cast<uintptr_t>(d_hay) >> 1) & 7);
+        const int64_t origin = m->use_tier ? ((emit_from + mis) & ~int64_t(7)) - mis : emit_from;
+        const int64_t span = std::max<int64_t>(0, emit_to - origin);
+        const int64_t tile_sz = m->use_tier ? kTierTile : kAcTile;
+        const int64_t n_tiles = emit_to > emit_from ? (span + tile_sz - 1) / tile_sz : 0;
         if (n_tiles == 0) {
             CU_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
             return ACGPU_OK;
@@ -231,6 +235,7 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
         P.n = n;
         P.emit_from = emit_from;
         P.emit_to = emit_to;
+        P.origin = origin;
         P.pos_base = opt.pos_base;
         P.pos_out = d_pos;
         P.val_out = d_val;
@@ -240,8 +245,7 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
         P.status = reinterpret_cast<unsigned long long *>(static_cast<char *>(ws) + 256);
         P.n_tiles = n_tiles;
         if (m->use_tier) {
-            const int64_t ctas = (n_tiles + kTierWarps - 1) / kTierWarps;
-            int rc = launch_tier(m, P, static_cast<int>(std::min<int64_t>(ctas, m->sm_count)), st);
+            int rc = launch_tier(m, P, static_cast<int>(std::min<int64_t>(n_tiles, m->sm_count)), st);
             if (rc != ACGPU_OK) return rc;
         } else {
             const int grid = static_cast<int>(std::min<int64_t>(n_tiles, persistent));
@@ -353,6 +357,12 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
 int ensure_device(Matcher *m) {
     CU_TRY(cudaSetDevice(m->device));
     if (!m->sel_attr_set) {
+        // keep stream-ordered scratch cached between calls instead of returning it to the driver at every sync
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, m->device) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
         CU_TRY(cudaFuncSetAttribute(k_sel_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelEmitSmem));
         CU_TRY(cudaFuncSetAttribute(k_sel_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelEmitSmem));
         m->sel_attr_set = true;
@@ -370,6 +380,275 @@ void fill_empty(acgpu_result *out) {
     out->pos = nullptr;
     out->val = nullptr;
 }
+
+
+// ---------------------------------------------------------------------------------------------------
+// Host-buffer calls: pinned result blocks + a three-stream chunk pipeline.
+//
+// Match records leave the device through page-locked host memory (a pageable D2H copy runs at a fraction of the
+// PCIe rate).  cudaHostAlloc is slow (hundreds of ms per GB), so released result blocks are parked in a small
+// process-wide cache and reused by later calls; acgpu_free_result() hands a block back.
+struct PinnedBlock {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+std::mutex g_pin_mu;
+std::vector<PinnedBlock> g_pin_free;
+std::vector<PinnedBlock> g_pin_live;
+constexpr size_t kPinCacheBlocks = 4;
+
+bool pin_take(size_t bytes, PinnedBlock *out) {
+    bytes = std::max<size_t>(bytes, 1 << 20);
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        int best = -1;
+        for (size_t i = 0; i < g_pin_free.size(); i++) {
+            if (g_pin_free[i].bytes >= bytes && (best < 0 || g_pin_free[i].bytes < g_pin_free[best].bytes)) best = (int)i;
+        }
+        if (best >= 0) {
+            *out = g_pin_free[best];
+            g_pin_free.erase(g_pin_free.begin() + best);
+            g_pin_live.push_back(*out);
+            return true;
+        }
+    }
+    PinnedBlock b;
+    b.bytes = align_up(bytes + bytes / 8, 1 << 20);
+    if (cudaHostAlloc(&b.p, b.bytes, cudaHostAllocDefault) != cudaSuccess) {
+        b.bytes = align_up(bytes, 1 << 20);
+        if (cudaHostAlloc(&b.p, b.bytes, cudaHostAllocDefault) != cudaSuccess) return false;
+    }
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pin_live.push_back(b);
+    *out = b;
+    return true;
+}
+
+// returns false when p is not a live pinned block
+bool pin_release(const void *p) {
+    PinnedBlock victim;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        size_t i = 0;
+        for (; i < g_pin_live.size(); i++) {
+            if (g_pin_live[i].p == p) break;
+        }
+        if (i == g_pin_live.size()) return false;
+        g_pin_free.push_back(g_pin_live[i]);
+        g_pin_live.erase(g_pin_live.begin() + i);
+        if (g_pin_free.size() <= kPinCacheBlocks) return true;
+        size_t small = 0;  // keep the larger blocks
+        for (size_t k = 1; k < g_pin_free.size(); k++) {
+            if (g_pin_free[k].bytes < g_pin_free[small].bytes) small = k;
+        }
+        victim = g_pin_free[small];
+        g_pin_free.erase(g_pin_free.begin() + small);
+    }
+    cudaFreeHost(victim.p);
+    return true;
+}
+
+// One acgpu_match_utf16 call.
+//   run_chunked (AhoCorasick family: every chunk is independent given max_len-1 chars of left context): the
+//     haystack goes up chunk by chunk on an upload stream, the kernels of chunk k run on a compute stream as soon
+//     as chunk k has landed, and the records of chunk k-1 come down on a third stream at the same time, so H2D,
+//     scan and D2H overlap and the call is bound by the slower PCIe direction.
+//   run_whole (Longest / Shortest / WholeWord: the selection chain runs over the whole haystack): upload, scan,
+//     download.
+struct HostCall {
+    static constexpr int64_t kChunk = int64_t(1) << 23;  // chars per pipeline chunk (16 MiB of UTF-16)
+    Matcher *m;
+    bool is_map;
+    cudaStream_t s_up = nullptr, s_k = nullptr, s_dn = nullptr;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_dn[2] = {nullptr, nullptr};
+    uint16_t *d_hay = nullptr;
+    int2 *d_pos[2] = {nullptr, nullptr};
+    uint32_t *d_val[2] = {nullptr, nullptr};
+    unsigned long long *d_total = nullptr;   // [2]
+    unsigned long long *h_total = nullptr;   // [2] pinned
+    PinnedBlock blk;                          // result block: pos[cap] then val[cap]
+    int64_t cap = 0, count = 0;               // records the block can hold / holds
+
+    explicit HostCall(Matcher *mm) : m(mm), is_map(mm->host.is_map) {}
+
+    int init() {
+        CU_TRY(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&s_dn, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU_TRY(cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&ev_dn[i], cudaEventDisableTiming));
+        }
+        CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_total), 16, s_k));
+        CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h_total), 16, cudaHostAllocDefault));
+        return ACGPU_OK;
+    }
+
+    int32_t *h_pos() const { return static_cast<int32_t *>(blk.p); }
+    uint32_t *h_val() const { return reinterpret_cast<uint32_t *>(static_cast<char *>(blk.p) + static_cast<size_t>(cap) * 8); }
+
+    // make room for `need` records in the pinned block, keeping the `count` records already there
+    int reserve(int64_t need) {
+        if (need <= cap) return ACGPU_OK;
+        const int64_t ncap = std::max<int64_t>(need, 1 << 16);
+        PinnedBlock nb;
+        if (!pin_take(static_cast<size_t>(ncap) * (is_map ? 12 : 8), &nb)) return fail(ACGPU_ENOMEM, "out of pinned host memory for the match records");
+        const int64_t real_cap = static_cast<int64_t>(nb.bytes / (is_map ? 12 : 8));
+        if (blk.p) {
+            CU_TRY(cudaStreamSynchronize(s_dn));  // copies into the old block have landed
+            std::memcpy(nb.p, blk.p, static_cast<size_t>(count) * 8);
+            if (is_map) std::memcpy(static_cast<char *>(nb.p) + static_cast<size_t>(real_cap) * 8, h_val(), static_cast<size_t>(count) * 4);
+            pin_release(blk.p);
+        }
+        blk = nb;
+        cap = real_cap;
+        return ACGPU_OK;
+    }
+
+    int download(const int2 *dp, const uint32_t *dv, int64_t k_records) {
+        if (k_records == 0) return ACGPU_OK;
+        CU_TRY(cudaMemcpyAsync(h_pos() + 2 * count, dp, static_cast<size_t>(k_records) * 8, cudaMemcpyDeviceToHost, s_dn));
+        if (is_map) CU_TRY(cudaMemcpyAsync(h_val() + count, dv, static_cast<size_t>(k_records) * 4, cudaMemcpyDeviceToHost, s_dn));
+        count += k_records;
+        return ACGPU_OK;
+    }
+
+    int run_chunked(const uint16_t *hay, int64_t n) {
+        const int64_t n_chunks = (n + kChunk - 1) / kChunk;
+        const int64_t span0 = std::min<int64_t>(n, kChunk);
+        const int64_t chunk_cap = std::max<int64_t>(1 << 16, span0 + span0 / 2);
+        CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_hay), static_cast<size_t>(n) * 2, s_k));
+        for (int i = 0; i < (n_chunks > 1 ? 2 : 1); i++) {
+            CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_pos[i]), static_cast<size_t>(chunk_cap) * 8, s_k));
+            if (is_map) CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_val[i]), static_cast<size_t>(chunk_cap) * 4, s_k));
+        }
+        CU_TRY(cudaEventRecord(ev_dn[0], s_k));  // the upload stream may touch d_hay once it exists
+        CU_TRY(cudaStreamWaitEvent(s_up, ev_dn[0], 0));
+        auto issue = [&](int64_t k) -> int {
+            const int bf = static_cast<int>(k & 1);
+            const int64_t lo = k * kChunk, hi = std::min<int64_t>(n, lo + kChunk);
+            CU_TRY(cudaMemcpyAsync(d_hay + lo, hay + lo, static_cast<size_t>(hi - lo) * 2, cudaMemcpyHostToDevice, s_up));
+            CU_TRY(cudaEventRecord(ev_up[bf], s_up));
+            CU_TRY(cudaStreamWaitEvent(s_k, ev_up[bf], 0));
+            if (k >= 2) CU_TRY(cudaStreamWaitEvent(s_k, ev_dn[bf], 0));  // records of chunk k-2 have left the buffer
+            RunOpts opt;
+            // chars beyond `hi` are not on the device yet: the window ends at hi (matches end inside [lo, hi))
+            int rc = enqueue_match(m, d_hay, hi, lo, hi, d_pos[bf], d_val[bf], chunk_cap, d_total + bf, s_k, opt);
+            if (rc != ACGPU_OK) return rc;
+            CU_TRY(cudaMemcpyAsync(h_total + bf, d_total + bf, 8, cudaMemcpyDeviceToHost, s_k));
+            CU_TRY(cudaEventRecord(ev_k[bf], s_k));
+            return ACGPU_OK;
+        };
+        int rc = issue(0);
+        if (rc != ACGPU_OK) return rc;
+        for (int64_t k = 0; k < n_chunks; k++) {
+            const int bf = static_cast<int>(k & 1);
+            if (k + 1 < n_chunks) {
+                rc = issue(k + 1);
+                if (rc != ACGPU_OK) return rc;
+            }
+            CU_TRY(cudaEventSynchronize(ev_k[bf]));
+            const int64_t got = static_cast<int64_t>(h_total[bf]);
+            if (count + got > cap) {
+                // size the block from the density seen so far (plus head-room); grows again if the text gets denser
+                const int64_t done_chars = std::min<int64_t>(n, (k + 1) * kChunk);
+                const double density = static_cast<double>(count + got) / static_cast<double>(done_chars);
+                const int64_t est = static_cast<int64_t>(density * 1.15 * static_cast<double>(n)) + (1 << 16);
+                rc = reserve(std::max<int64_t>(count + got, k + 1 == n_chunks ? count + got : est));
+                if (rc != ACGPU_OK) return rc;
+            }
+            if (got <= chunk_cap) {
+                CU_TRY(cudaStreamWaitEvent(s_dn, ev_k[bf], 0));
+                rc = download(d_pos[bf], d_val[bf], got);
+                if (rc != ACGPU_OK) return rc;
+            } else {
+                // denser than the chunk buffers: scan this chunk again into an exact-size buffer (the first run
+                // counted everything), after the pipeline has drained
+                const int64_t lo = k * kChunk, hi = std::min<int64_t>(n, lo + kChunk);
+                int2 *big_pos = nullptr;
+                uint32_t *big_val = nullptr;
+                CU_TRY(cudaStreamSynchronize(s_k));
+                CU_TRY(cudaStreamSynchronize(s_dn));
+                CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&big_pos), static_cast<size_t>(got) * 8, s_dn));
+                if (is_map) CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&big_val), static_cast<size_t>(got) * 4, s_dn));
+                RunOpts opt;
+                rc = enqueue_match(m, d_hay, hi, lo, hi, big_pos, big_val, got, d_total + bf, s_dn, opt);
+                if (rc == ACGPU_OK) rc = download(big_pos, big_val, got);
+                cudaFreeAsync(big_pos, s_dn);
+                if (big_val) cudaFreeAsync(big_val, s_dn);
+                if (rc != ACGPU_OK) return rc;
+
+            }
+            CU_TRY(cudaEventRecord(ev_dn[bf], s_dn));
+        }
+        CU_TRY(cudaStreamSynchronize(s_dn));
+        return ACGPU_OK;
+    }
+
+    int run_whole(const uint16_t *hay, int64_t n) {
+        CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_hay), static_cast<size_t>(n) * 2, s_k));
+        CU_TRY(cudaMemcpyAsync(d_hay, hay, static_cast<size_t>(n) * 2, cudaMemcpyHostToDevice, s_k));
+        int64_t dcap = std::max<int64_t>(1 << 16, n / 4);
+        for (int attempt = 0; attempt < 2; attempt++) {
+            CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_pos[0]), static_cast<size_t>(dcap) * 8, s_k));
+            if (is_map) CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_val[0]), static_cast<size_t>(dcap) * 4, s_k));
+            RunOpts opt;
+            int rc = enqueue_match(m, d_hay, n, 0, n, d_pos[0], d_val[0], dcap, d_total, s_k, opt);
+            if (rc != ACGPU_OK) return rc;
+            CU_TRY(cudaMemcpyAsync(h_total, d_total, 8, cudaMemcpyDeviceToHost, s_k));
+            CU_TRY(cudaStreamSynchronize(s_k));
+            if (static_cast<int64_t>(h_total[0]) <= dcap) break;
+            // first guess too small: the kernels still counted everything; rerun with the exact size
+            cudaFreeAsync(d_pos[0], s_k);
+            d_pos[0] = nullptr;
+            if (d_val[0]) cudaFreeAsync(d_val[0], s_k);
+            d_val[0] = nullptr;
+            dcap = static_cast<int64_t>(h_total[0]);
+        }
+        const int64_t got = static_cast<int64_t>(h_total[0]);
+        int rc = reserve(got);
+        if (rc != ACGPU_OK) return rc;
+        rc = download(d_pos[0], d_val[0], got);  // on s_dn; the scan on s_k has been synchronised above
+        if (rc != ACGPU_OK) return rc;
+        CU_TRY(cudaStreamSynchronize(s_dn));
+        return ACGPU_OK;
+    }
+
+    // release everything; on success hand the pinned block to the caller
+    int finish(int rc, acgpu_result *out) {
+        cudaError_t pending = cudaSuccess;
+        for (cudaStream_t st : {s_up, s_dn, s_k}) {
+            if (st) {
+                cudaError_t e = cudaStreamSynchronize(st);
+                if (e != cudaSuccess) pending = e;
+            }
+        }
+        if (rc == ACGPU_OK && pending != cudaSuccess) rc = fail(ACGPU_ECUDA, std::string("match: ") + cudaGetErrorString(pending));
+        if (d_hay) cudaFreeAsync(d_hay, s_k);
+        for (int i = 0; i < 2; i++) {
+            if (d_pos[i]) cudaFreeAsync(d_pos[i], s_k);
+            if (d_val[i]) cudaFreeAsync(d_val[i], s_k);
+            if (ev_up[i]) cudaEventDestroy(ev_up[i]);
+            if (ev_k[i]) cudaEventDestroy(ev_k[i]);
+            if (ev_dn[i]) cudaEventDestroy(ev_dn[i]);
+        }
+        if (d_total) cudaFreeAsync(d_total, s_k);
+        if (s_k) cudaStreamSynchronize(s_k);
+        if (h_total) cudaFreeHost(h_total);
+        if (s_up) cudaStreamDestroy(s_up);
+        if (s_k) cudaStreamDestroy(s_k);
+        if (s_dn) cudaStreamDestroy(s_dn);
+        if (rc == ACGPU_OK && count > 0) {
+            out->n = count;
+            out->pos = h_pos();
+            out->val = is_map ? h_val() : nullptr;
+        } else if (blk.p) {
+            pin_release(blk.p);
+        }
+        return rc;
+    }
+};
 
 }  // namespace
 
@@ -517,80 +796,19 @@ int acgpu_match_utf16(uint64_t handle, const uint16_t *haystack, int32_t n, acgp
     int rc = ensure_device(m);
     if (rc != ACGPU_OK) return rc;
     if (n == 0) return ACGPU_OK;
-    cudaStream_t st;
-    CU_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    uint16_t *d_hay = nullptr;
-    int2 *d_pos = nullptr;
-    uint32_t *d_val = nullptr;
-    unsigned long long *d_total = nullptr;
-    int32_t *h_pos = nullptr;
-    uint32_t *h_val = nullptr;
-    auto cleanup = [&]() {
-        if (d_hay) cudaFreeAsync(d_hay, st);
-        if (d_pos) cudaFreeAsync(d_pos, st);
-        if (d_val) cudaFreeAsync(d_val, st);
-        if (d_total) cudaFreeAsync(d_total, st);
-        cudaStreamSynchronize(st);
-        cudaStreamDestroy(st);
-    };
-#define CU_TRY_C(expr)                 \
-    do {                               \
-        cudaError_t _e2 = (expr);      \
-        if (_e2 != cudaSuccess) {      \
-            cleanup();                 \
-            free(h_pos);               \
-            free(h_val);               \
-            CU_TRY(_e2);               \
-        }                              \
-    } while (0)
-    CU_TRY_C(cudaMallocAsync(reinterpret_cast<void **>(&d_hay), static_cast<size_t>(n) * 2, st));
-    CU_TRY_C(cudaMallocAsync(reinterpret_cast<void **>(&d_total), 8, st));
-    CU_TRY_C(cudaMemcpyAsync(d_hay, haystack, static_cast<size_t>(n) * 2, cudaMemcpyHostToDevice, st));
-    int64_t cap = std::max<int64_t>(1 << 16, n / 4);
-    unsigned long long total = 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        CU_TRY_C(cudaMallocAsync(reinterpret_cast<void **>(&d_pos), static_cast<size_t>(cap) * 8, st));
-        if (m->host.is_map) CU_TRY_C(cudaMallocAsync(reinterpret_cast<void **>(&d_val), static_cast<size_t>(cap) * 4, st));
-        RunOpts opt;
-        rc = enqueue_match(m, d_hay, n, 0, n, d_pos, d_val, cap, d_total, st, opt);
-        if (rc != ACGPU_OK) {
-            cleanup();
-            return rc;
-        }
-        CU_TRY_C(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
-        CU_TRY_C(cudaStreamSynchronize(st));
-        if (static_cast<int64_t>(total) <= cap) break;
-        // first guess too small: the kernel still counted everything; rerun with the exact size
-        cudaFreeAsync(d_pos, st);
-        d_pos = nullptr;
-        if (d_val) cudaFreeAsync(d_val, st);
-        d_val = nullptr;
-        cap = static_cast<int64_t>(total);
-    }
-    if (total > 0) {
-        h_pos = static_cast<int32_t *>(malloc(static_cast<size_t>(total) * 8));
-        if (m->host.is_map) h_val = static_cast<uint32_t *>(malloc(static_cast<size_t>(total) * 4));
-        if (!h_pos || (m->host.is_map && !h_val)) {
-            cleanup();
-            free(h_pos);
-            free(h_val);
-            return fail(ACGPU_ENOMEM, "out of host memory for the match records");
-        }
-        CU_TRY_C(cudaMemcpyAsync(h_pos, d_pos, static_cast<size_t>(total) * 8, cudaMemcpyDeviceToHost, st));
-        if (h_val) CU_TRY_C(cudaMemcpyAsync(h_val, d_val, static_cast<size_t>(total) * 4, cudaMemcpyDeviceToHost, st));
-        CU_TRY_C(cudaStreamSynchronize(st));
-    }
-    cleanup();
-    out->n = static_cast<int64_t>(total);
-    out->pos = h_pos;
-    out->val = h_val;
-    return ACGPU_OK;
+    HostCall hc(m);
+    rc = hc.init();
+    if (rc == ACGPU_OK)
+        rc = m->host.family == ACGPU_AHOCORASICK ? hc.run_chunked(haystack, n) : hc.run_whole(haystack, n);
+    return hc.finish(rc, out);
 }
 
 void acgpu_free_result(acgpu_result *r) {
     if (!r) return;
-    free(const_cast<int32_t *>(r->pos));
-    free(const_cast<uint32_t *>(r->val));
+    if (r->pos && !pin_release(r->pos)) {  // streaming results are plain heap blocks
+        free(const_cast<int32_t *>(r->pos));
+        free(const_cast<uint32_t *>(r->val));
+    }
     fill_empty(r);
 }
 

@@ -12,10 +12,13 @@
 //   * levels > K are 8-byte slots (context << 4 | flags) in an open-addressing table keyed by the context itself;
 //   * loads of a lane's 8 positions are issued back to back (memory-level parallelism) before any is consumed;
 //   * the depths that hit are kept as a bitmask per position: one pass, count = popc.
-// Ordered emission without block barriers: one WARP row (256 positions) is one tile of the decoupled look-back;
-// rows are assigned statically to the persistent, fully resident grid, so a warp only ever waits for rows that
-// are running or finished.  Records are staged in a per-warp shared-memory window and flushed with coalesced
-// streaming stores.
+// Ordered emission: a CTA tile = 24 warp rows of 240 positions.  Worker warps count their row, hand the count to
+// a dedicated RESOLVER warp through shared memory + named barriers (bar.arrive / bar.sync, no __syncthreads in the
+// loop), and go on to count their next row; the resolver does ONE decoupled look-back per CTA tile and hands every
+// worker its global record offset, which the worker picks up one iteration later (software pipeline), stages its
+// records in a per-warp shared-memory window and flushes them with coalesced streaming stores.  Tiles are assigned
+// statically to the persistent, fully resident (cooperatively launched) grid, so a look-back only ever waits for
+// tiles that are running or finished.
 #pragma once
 #include "device_tables.cuh"
 
@@ -38,15 +41,25 @@ struct DevTier {
     unsigned long long val_off[10];
 };
 
-constexpr int kTierThreads = 768;
-constexpr int kTierWarps = kTierThreads / 32;
-constexpr int kTierPer = 8;                  // consecutive positions per lane
-constexpr int kTierRow = 30 * kTierPer;      // 240 emitting positions per warp row = one look-back tile
-constexpr int kTierStage = 256;              // records per warp staging window
+constexpr int kTierWorkers = 24;                         // worker warps per CTA
+constexpr int kTierWarps = kTierWorkers;                 // rows per CTA tile
+constexpr int kTierThreads = (kTierWorkers + 1) * 32;    // + the resolver warp
+constexpr int kTierPer = 8;                              // consecutive positions per lane
+constexpr int kTierRow = 30 * kTierPer;                  // 240 emitting positions per warp row
+constexpr int kTierTile = kTierWorkers * kTierRow;       // positions per CTA tile = one look-back tile
+constexpr int kTierCtrlWords = 256;                      // control block: counts + per-warp bases, double buffered
 
+__host__ __device__ constexpr int tier_stage_records(bool is_map) { return is_map ? 256 : 384; }
 __host__ __device__ constexpr size_t tier_stage_bytes(bool is_map) {
-    return (size_t)kTierWarps * kTierStage * (is_map ? 12 : 8);
+    return (size_t)kTierWorkers * tier_stage_records(is_map) * (is_map ? 12 : 8);
 }
+// dynamic shared memory of k_ac_tier for a table of n_words words
+__host__ __device__ constexpr size_t tier_smem_bytes(size_t n_words, bool is_map) {
+    return (64 + ((n_words + 3) & ~size_t(3)) + kTierCtrlWords) * sizeof(uint32_t) + tier_stage_bytes(is_map);
+}
+
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ unsigned long long deep_hash64_d(unsigned long long key, unsigned long long seed) {
     unsigned long long h = key ^ seed;
@@ -58,63 +71,67 @@ __device__ __forceinline__ unsigned long long deep_hash64_d(unsigned long long k
     return h;
 }
 
-// A deep probe in two halves so that several can be in flight: issue the sector load, consume it later.
-// Every probe is for a key that exists (child masks are exact) and the builder keeps tags unique along a probe
-// path, so the first entry whose tag matches is the node.
-struct DeepProbe {
-    uint4 a, b;
-    uint32_t bucket, want;
-};
-
-__device__ __forceinline__ void deep_issue(const DevTier &T, unsigned long long key, DeepProbe &p) {
+// One deep probe.  Every probe is for a key that exists (child masks are exact) and the builder keeps tags unique
+// along a probe path, so the first entry whose tag matches is the node.
+__device__ __forceinline__ void deep_probe(const DevTier &T, unsigned long long key, uint32_t &flags, uint32_t &kids,
+                                           uint32_t &slot) {
     const unsigned long long h = deep_hash64_d(key, T.hash_seed);
-    p.bucket = (uint32_t)h & T.bucket_mask;
-    p.want = ((uint32_t)(h >> 36) << 4) | 8u;
-    const uint4 *q = T.buckets + (size_t)p.bucket * 2;
-    p.a = __ldg(q);
-    p.b = __ldg(q + 1);
-}
-
-__device__ __forceinline__ void deep_consume(const DevTier &T, DeepProbe &p, uint32_t &flags, uint32_t &kids, uint32_t &slot) {
+    uint32_t bucket = (uint32_t)h & T.bucket_mask;
+    const uint32_t want = ((uint32_t)(h >> 36) << 4) | 8u;
     while (true) {
-        if ((p.a.x & ~7u) == p.want) { flags = p.a.x & 7u; kids = p.a.y; slot = p.bucket * 4u; return; }
-        if ((p.a.z & ~7u) == p.want) { flags = p.a.z & 7u; kids = p.a.w; slot = p.bucket * 4u + 1u; return; }
-        if ((p.b.x & ~7u) == p.want) { flags = p.b.x & 7u; kids = p.b.y; slot = p.bucket * 4u + 2u; return; }
-        if ((p.b.z & ~7u) == p.want) { flags = p.b.z & 7u; kids = p.b.w; slot = p.bucket * 4u + 3u; return; }
-        p.bucket = (p.bucket + 1u) & T.bucket_mask;  // overflowed bucket: the key sits further along
-        const uint4 *q = T.buckets + (size_t)p.bucket * 2;
-        p.a = __ldg(q);
-        p.b = __ldg(q + 1);
+        const uint4 *q = T.buckets + (size_t)bucket * 2;
+        const uint4 a = __ldg(q);
+        const uint4 b = __ldg(q + 1);
+        if ((a.x & ~7u) == want) { flags = a.x & 7u; kids = a.y; slot = bucket * 4u; return; }
+        if ((a.z & ~7u) == want) { flags = a.z & 7u; kids = a.w; slot = bucket * 4u + 1u; return; }
+        if ((b.x & ~7u) == want) { flags = b.x & 7u; kids = b.y; slot = bucket * 4u + 2u; return; }
+        if ((b.z & ~7u) == want) { flags = b.z & 7u; kids = b.w; slot = bucket * 4u + 3u; return; }
+        bucket = (bucket + 1u) & T.bucket_mask;  // overflowed bucket: the key sits further along
     }
 }
 
-// classes of the 8 chars at [p0, p0+8), first char in the HIGHEST field; positions outside [0, n) give class 0
-__device__ __forceinline__ unsigned long long pack8(const DevAutomaton &A, const uint16_t *hay, int64_t n, int64_t p0,
-                                                    const uint8_t *s_cls8, int b) {
-    uint32_t ch[8];
-    if (p0 >= 0 && p0 + 8 <= n && ((reinterpret_cast<uintptr_t>(hay + p0) & 15) == 0)) {
-        uint4 v = __ldcs(reinterpret_cast<const uint4 *>(hay + p0));  // streaming: read once
-        ch[0] = v.x & 0xFFFFu; ch[1] = v.x >> 16; ch[2] = v.y & 0xFFFFu; ch[3] = v.y >> 16;
-        ch[4] = v.z & 0xFFFFu; ch[5] = v.z >> 16; ch[6] = v.w & 0xFFFFu; ch[7] = v.w >> 16;
+// Levels K+1.. of a context whose level-(K+1) node exists: bit (d - K - 1) set = a keyword of length d ends here.
+template <int K>
+__device__ __forceinline__ uint32_t deep_bits(const DevTier &T, unsigned long long ctx, uint32_t cm, int max_len) {
+    uint32_t fl, kids, slot;
+    deep_probe(T, ctx & ((1ull << (T.b * (K + 1))) - 1ull), fl, kids, slot);
+    uint32_t bits = fl & 1u;
+    for (int d = K + 2; d <= max_len && (fl & 2u); d++) {
+        const uint32_t c = ((uint32_t)(ctx >> (T.b * (d - 1)))) & cm;
+        if (!((kids >> c) & 1u)) break;  // exact: no such child (class 0 never has one)
+        deep_probe(T, ctx & ((1ull << (T.b * d)) - 1ull), fl, kids, slot);
+        bits |= (fl & 1u) << (d - K - 1);
+    }
+    return bits;
+}
+
+// classes of the 8 chars at [p0, p0+8); positions outside [0, n) give class 0
+__device__ __forceinline__ void load_classes8(const DevAutomaton &A, const uint16_t *hay, int64_t n, int64_t p0,
+                                              const uint8_t *s_cls8, uint32_t (&c)[kTierPer]) {
+    if (p0 >= 0 && p0 + 8 <= n) {  // rows are laid out so that hay + p0 is 16-byte aligned
+        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(hay + p0));  // streaming: read once
+        if (((v.x | v.y | v.z | v.w) & 0xFF00FF00u) == 0u) {
+            c[0] = s_cls8[v.x & 0xFFu]; c[1] = s_cls8[v.x >> 16];
+            c[2] = s_cls8[v.y & 0xFFu]; c[3] = s_cls8[v.y >> 16];
+            c[4] = s_cls8[v.z & 0xFFu]; c[5] = s_cls8[v.z >> 16];
+            c[6] = s_cls8[v.w & 0xFFu]; c[7] = s_cls8[v.w >> 16];
+        } else {
+            const uint32_t ch[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16,
+                                    v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
+#pragma unroll
+            for (int j = 0; j < 8; j++) c[j] = ch[j] < 256u ? (uint32_t)s_cls8[ch[j]] : (uint32_t)__ldg(&A.cls[ch[j]]);
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            int64_t p = p0 + j;
-            ch[j] = (p >= 0 && p < n) ? (uint32_t)__ldg(&hay[p]) : 0x10000u;  // 0x10000 = outside
+            const int64_t p = p0 + j;
+            c[j] = (p >= 0 && p < n) ? (uint32_t)__ldg(&A.cls[__ldg(&hay[p])]) : 0u;
         }
     }
-    unsigned long long P = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        uint32_t c = ch[j] < 256u ? (uint32_t)s_cls8[ch[j]] : (ch[j] < 0x10000u ? (uint32_t)__ldg(&A.cls[ch[j]]) : 0u);
-        P = (P << b) | c;
-    }
-    return P;
 }
 
 template <int K>
-__device__ __forceinline__ uint32_t tier_value(const DevAutomaton &A, const DevTier &T, unsigned long long ctx,
-                                               uint32_t cm, int d) {
+__device__ __forceinline__ uint32_t tier_value(const DevTier &T, unsigned long long ctx, uint32_t cm, int d) {
     if (d <= K) {
         uint32_t idx = 0;
 #pragma unroll
@@ -123,211 +140,262 @@ __device__ __forceinline__ uint32_t tier_value(const DevAutomaton &A, const DevT
         }
         return __ldg(&T.shallow_val[T.val_off[d] + idx]);
     }
-    DeepProbe pr;
     uint32_t fl, kids, slot;
-    deep_issue(T, ctx & ((1ull << (T.b * d)) - 1ull), pr);
-    deep_consume(T, pr, fl, kids, slot);
+    deep_probe(T, ctx & ((1ull << (T.b * d)) - 1ull), fl, kids, slot);
     return __ldg(&T.deep_val[slot]);
 }
 
-// Levels d0.. for a context whose level (d0-1) node has flags `fl` and child mask `kids`; returns hit bits.
-__device__ __forceinline__ uint32_t deep_walk_from(const DevAutomaton &A, const DevTier &T, unsigned long long ctx,
-                                                   uint32_t cm, int d0, uint32_t fl, uint32_t kids) {
-    uint32_t m = 0;
-    for (int d = d0; d <= A.max_len && (fl & 2u); d++) {
-        const uint32_t c = ((uint32_t)(ctx >> (T.b * (d - 1)))) & cm;
-        if (!((kids >> c) & 1u)) break;  // exact: no such child (class 0 never has one)
-        DeepProbe pr;
-        uint32_t slot;
-        deep_issue(T, ctx & ((1ull << (T.b * d)) - 1ull), pr);
-        deep_consume(T, pr, fl, kids, slot);
-        m |= (fl & 1u) << d;
-    }
-    return m;
-}
-
-// AcArgs.n_tiles = number of rows; a row = 240 emitting positions (lanes 2..31) preceded by 16 context positions
-// (lanes 0,1), so one 128-bit load per lane covers the row and its left context.  tile_counter is unused.
+// AcArgs: n_tiles = number of CTA tiles; a row = 240 emitting positions (lanes 2..31) preceded by 16 context
+// positions (lanes 0,1), so one 128-bit load per lane covers the row and its left context.  Rows start at
+// P.origin (<= emit_from, chosen by the host so that every lane's load is 16-byte aligned).
 template <int K, bool kIsMap>
 __global__ void __launch_bounds__(kTierThreads, 1) k_ac_tier(const DevAutomaton A, const DevTier T, const AcArgs P) {
+    constexpr int kStage = tier_stage_records(kIsMap);
     extern __shared__ __align__(16) uint32_t s_mem[];
     const uint8_t *s_cls8 = reinterpret_cast<const uint8_t *>(s_mem);
     const uint32_t *s_tab = s_mem + 64;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = T.b;
     const uint32_t cm = (1u << b) - 1u;
-    // per-warp staging window behind the tables
-    int2 *s_stage = reinterpret_cast<int2 *>(s_mem + 64 + ((T.n_words + 3u) & ~3u)) + warp * kTierStage;
-    uint32_t *s_stage_val = reinterpret_cast<uint32_t *>(reinterpret_cast<int2 *>(s_mem + 64 + ((T.n_words + 3u) & ~3u)) +
-                                                         kTierWarps * kTierStage) + warp * kTierStage;
+    uint32_t *s_ctrl = s_mem + 64 + ((T.n_words + 3u) & ~3u);
+    uint32_t *s_cnt = s_ctrl;                                                             // [2][32]
+    unsigned long long *s_wbase = reinterpret_cast<unsigned long long *>(s_ctrl + 64);   // [2][32]
+    int2 *s_stage_all = reinterpret_cast<int2 *>(s_ctrl + kTierCtrlWords);
+    int2 *s_stage = s_stage_all + warp * kStage;
+    uint32_t *s_stage_val = reinterpret_cast<uint32_t *>(s_stage_all + kTierWorkers * kStage) + warp * kStage;
 
     for (uint32_t i = tid; i < 64; i += kTierThreads) s_mem[i] = __ldg(&T.cls8[i]);
     for (uint32_t i = tid; i < T.n_words; i += kTierThreads) s_mem[64 + i] = __ldg(&T.smem_words[i]);
     __syncthreads();
 
-    const int64_t n_rows = P.n_tiles;
-    // software pipeline: row i's records are resolved and written after row i+1 has been counted and its
-    // aggregate published, so the look-back of row i finds its predecessors ready
-    bool pv = false;
-    int64_t p_row = 0, p_p0 = 0;
-    unsigned long long p_Pk = 0, p_ctx0 = 0;
-    uint32_t p_masks[kTierPer], p_cnt = 0, p_inc = 0, p_total = 0;
+    const int64_t n_tiles = P.n_tiles;
+    const int n_iter = (int)((n_tiles - (int64_t)blockIdx.x + (int64_t)gridDim.x - 1) / (int64_t)gridDim.x);
+
+    // ================================================================= resolver warp
+    if (warp == kTierWorkers) {
+        for (int it = 0; it < n_iter; ++it) {
+            const int buf = it & 1;
+            named_sync(1 + buf, kTierThreads);  // the 24 row counts of this tile are in s_cnt[buf]
+            const uint32_t c = lane < kTierWorkers ? s_cnt[buf * 32 + lane] : 0u;
+            uint32_t inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc += y;
+            }
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
+            if (lane == 0) lookback_publish(P.status, tile, total);
+            const unsigned long long excl = lookback_resolve(P.status, tile, total);
+            if (lane < kTierWorkers) s_wbase[buf * 32 + lane] = excl + inc - c;
+            if (lane == 0 && tile == n_tiles - 1) *P.total_out = excl + total;
+            __threadfence_block();
+            named_arrive(3 + buf, kTierThreads);
+        }
+        return;
+    }
+
+    // ================================================================= worker warps
+    const uint32_t C = (uint32_t)T.C;
+    const uint32_t sh = 1u << b;
+    const bool deeper = T.kidmask != nullptr;  // some keyword is longer than K
+    // row state carried to the next iteration (emission is one iteration behind counting)
+    uint32_t p_masks[kTierPer], p_cnt = 0, p_inc = 0, p_total = 0, p_hi = 0, p_lo = 0;
+    int32_t p_e0 = 0;
 #pragma unroll
     for (int j = 0; j < kTierPer; j++) p_masks[j] = 0;
 
-    for (int64_t row = (int64_t)blockIdx.x * kTierWarps + warp;; row += (int64_t)gridDim.x * kTierWarps) {
-        const bool have = row < n_rows;
-        int64_t p0 = 0;
-        unsigned long long Pk = 0, ctx0 = 0;
-        uint32_t masks[kTierPer], my_cnt = 0, inc = 0, row_total = 0;
+    for (int it = 0; it <= n_iter; ++it) {
+        uint32_t masks[kTierPer], my_cnt = 0, inc = 0, row_total = 0, hi = 0, lo = 0;
+        int32_t e0 = 0;
 #pragma unroll
         for (int j = 0; j < kTierPer; j++) masks[j] = 0;
-        if (have) {
-            const int64_t q_lo = P.emit_from + row * kTierRow;
-            const int64_t q_hi = min(P.emit_to, q_lo + (int64_t)kTierRow);
-            p0 = q_lo - 16 + (int64_t)lane * kTierPer;
-            Pk = pack8(A, P.hay, P.n, p0, s_cls8, b);
-            const unsigned long long Q1 = __shfl_up_sync(0xFFFFFFFFu, Pk, 1);
-            const unsigned long long Q2 = __shfl_up_sync(0xFFFFFFFFu, Pk, 2);
-            ctx0 = (Q2 << (8 * b)) | Q1;  // lanes 0,1 hold garbage here and never emit
 
-            // ---- phase A: shared-memory levels for the 8 positions; remember which contexts may continue
-            uint32_t ki[kTierPer];
-            {
-                unsigned long long ctx = ctx0;
-#pragma unroll
-                for (int j = 0; j < kTierPer; j++) {
-                    ctx = (ctx << b) | ((Pk >> (b * (kTierPer - 1 - j))) & cm);
-                    uint32_t m = 0, idx = 0, f = 0;
-#pragma unroll
-                    for (int i = 1; i <= K; i++) {
-                        idx += ((uint32_t)(ctx >> (b * (i - 1))) & cm) * T.pow_c[i];
-                        if (i < K) {
-                            if ((T.term_levels >> i) & 1u) m |= ((s_tab[T.lvl_off[i] + (idx >> 5)] >> (idx & 31u)) & 1u) << i;
-                        } else {
-                            f = (s_tab[T.lvl_off[K] + (idx >> 4)] >> ((idx & 15u) * 2u)) & 3u;
-                            m |= (f & 1u) << K;
-                        }
-                    }
-                    const bool valid = lane >= 2 && (p0 + j) < q_hi;
-                    masks[j] = valid ? m : 0u;
-                    ki[j] = (valid && (f & 2u)) ? idx : 0xFFFFFFFFu;
-                }
+        if (it < n_iter) {
+            const int64_t row = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTierWorkers + warp;
+            const int64_t q_lo = P.origin + row * kTierRow;
+            const int64_t q_hi = min(P.emit_to, q_lo + (int64_t)kTierRow);
+            const int64_t p0 = q_lo - 16 + (int64_t)lane * kTierPer;
+            e0 = (int32_t)(p0 + 1) + P.pos_base;
+            // bit j set: position p0 + j reports matches
+            uint32_t vm = 0;
+            if (lane >= 2) {
+                const int64_t lo_j = max(P.emit_from, q_lo) - p0, hi_j = q_hi - p0;
+                const uint32_t a = lo_j <= 0 ? 0xFFu : (lo_j >= 8 ? 0u : (0xFFu << (int)lo_j) & 0xFFu);
+                const uint32_t z = hi_j >= 8 ? 0xFFu : (hi_j <= 0 ? 0u : (0xFFu >> (8 - (int)hi_j)));
+                vm = a & z;
             }
-            // ---- phase B: exact child masks of the level-K entries (all 8 loads in flight together) say which
-            //      contexts continue to level K+1
-            uint32_t probe_mask = 0;
-            if (T.kidmask) {
+            uint32_t c[kTierPer];
+            load_classes8(A, P.hay, P.n, p0, s_cls8, c);
+            hi = ((c[0] * sh + c[1]) * sh + c[2]) * sh + c[3];
+            lo = ((c[4] * sh + c[5]) * sh + c[6]) * sh + c[7];
+            const uint32_t lo1 = __shfl_up_sync(0xFFFFFFFFu, lo, 1);
+            const uint32_t hi1 = __shfl_up_sync(0xFFFFFFFFu, hi, 1);
+            // class i positions before this lane's first one (i = 1..8); lane 0 reads garbage and never reports
+            auto prev_class = [&](int i) -> uint32_t {
+                return i <= 4 ? (lo1 >> (b * (i - 1))) & cm : (hi1 >> (b * (i - 5))) & cm;
+            };
+
+            // ---- phase A: rolling mixed-radix indices of the last 1..K classes; shared-memory level tables
+            uint32_t r[K + 1];
+            {
+                uint32_t acc = 0;
+                r[0] = 0;
+#pragma unroll
+                for (int k = 1; k < K; k++) {
+                    acc += prev_class(k) * T.pow_c[k];
+                    r[k] = acc;
+                }
+                r[K] = 0;
+            }
+            uint32_t ki[kTierPer];
+#pragma unroll
+            for (int j = 0; j < kTierPer; j++) {
+#pragma unroll
+                for (int k = K; k >= 2; k--) r[k] = r[k - 1] * C + c[j];
+                r[1] = c[j];
+                uint32_t m = 0;
+#pragma unroll
+                for (int i = 1; i < K; i++) {
+                    const bool on = (T.term_levels >> i) & 1u;
+                    const uint32_t w = on ? s_tab[T.lvl_off[i] + (r[i] >> 5)] : 0u;
+                    m |= (__funnelshift_r(w, 0u, r[i]) & 1u) << i;
+                }
+                const uint32_t w = s_tab[T.lvl_off[K] + (r[K] >> 4)];
+                const uint32_t f = __funnelshift_r(w, 0u, (r[K] & 15u) * 2u) & 3u;
+                m |= (f & 1u) << K;
+                const bool valid = (vm >> j) & 1u;
+                masks[j] = valid ? m : 0u;
+                ki[j] = (valid && (f & 2u)) ? r[K] : 0xFFFFFFFFu;
+            }
+
+            if (deeper) {
+                // ---- phase B: exact child masks of the level-K entries (all 8 loads in flight together) say which
+                //      contexts continue to level K+1
+                uint32_t pm = 0;
 #pragma unroll
                 for (int j = 0; j < kTierPer; j++) ki[j] = ki[j] != 0xFFFFFFFFu ? __ldg(&T.kidmask[ki[j]]) : 0u;
 #pragma unroll
                 for (int j = 0; j < kTierPer; j++) {
-                    // context of position j in closed form: ctx0 shifted by j+1 classes | the first j+1 classes of Pk
-                    const unsigned long long ctx = (ctx0 << (b * (j + 1))) | (Pk >> (b * (kTierPer - 1 - j)));
-                    const uint32_t c = (uint32_t)(ctx >> (b * K)) & cm;
-                    probe_mask |= ((ki[j] >> c) & 1u) << j;
+                    const uint32_t ck = j >= K ? c[j >= K ? j - K : 0] : prev_class(K - j);
+                    pm |= ((ki[j] >> ck) & 1u) << j;
                 }
-            }
-            // ---- phase C: deep levels.  Converged loop: every lane takes up to two of its continuing positions per
-            //      round, both sector loads are issued before either is consumed.  Hit bits go to a packed word
-            //      (8 bits per position, bit = depth - K - 1; 16 levels in two words) to avoid indexed registers.
-            unsigned long long dlo = 0, dhi = 0;
-            while (__any_sync(0xFFFFFFFFu, probe_mask != 0)) {
-                int j1 = -1, j2 = -1;
-                if (probe_mask) {
-                    j1 = __ffs(probe_mask) - 1;
-                    probe_mask &= probe_mask - 1;
-                }
-                if (probe_mask) {
-                    j2 = __ffs(probe_mask) - 1;
-                    probe_mask &= probe_mask - 1;
-                }
-                DeepProbe pr1, pr2;
-                unsigned long long c1 = 0, c2 = 0;
-                if (j1 >= 0) {
-                    c1 = (ctx0 << (b * (j1 + 1))) | (Pk >> (b * (kTierPer - 1 - j1)));
-                    deep_issue(T, c1 & ((1ull << (b * (K + 1))) - 1ull), pr1);
-                }
-                if (j2 >= 0) {
-                    c2 = (ctx0 << (b * (j2 + 1))) | (Pk >> (b * (kTierPer - 1 - j2)));
-                    deep_issue(T, c2 & ((1ull << (b * (K + 1))) - 1ull), pr2);
-                }
-                if (j1 >= 0) {
-                    uint32_t fl, kids, slot;
-                    deep_consume(T, pr1, fl, kids, slot);
-                    uint32_t bits = (fl & 1u) | (deep_walk_from(A, T, c1, cm, K + 2, fl, kids) >> (K + 1));
-                    dlo |= (unsigned long long)(bits & 0xFFu) << (8 * j1);
-                    dhi |= (unsigned long long)((bits >> 8) & 0xFFu) << (8 * j1);
-                }
-                if (j2 >= 0) {
-                    uint32_t fl, kids, slot;
-                    deep_consume(T, pr2, fl, kids, slot);
-                    uint32_t bits = (fl & 1u) | (deep_walk_from(A, T, c2, cm, K + 2, fl, kids) >> (K + 1));
-                    dlo |= (unsigned long long)(bits & 0xFFu) << (8 * j2);
-                    dhi |= (unsigned long long)((bits >> 8) & 0xFFu) << (8 * j2);
-                }
-            }
+                // ---- phase C: the continuing contexts of the whole row are compacted into a queue (ids in the warp's
+                //      staging window, free at this point) and walked 32 at a time with all lanes busy
+                uint32_t n_mine = __popc(pm), q_inc = n_mine;
 #pragma unroll
-            for (int j = 0; j < kTierPer; j++) {
-                masks[j] |= ((uint32_t)(dlo >> (8 * j)) & 0xFFu) << (K + 1);
-                masks[j] |= ((uint32_t)(dhi >> (8 * j)) & 0xFFu) << (K + 9);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, q_inc, o);
+                    if (lane >= o) q_inc += y;
+                }
+                const uint32_t q_total = __shfl_sync(0xFFFFFFFFu, q_inc, 31);
+                if (q_total) {
+                    uint8_t *s_q = reinterpret_cast<uint8_t *>(s_stage);                 // [256] ids = lane * 8 + j
+                    uint16_t *s_r = reinterpret_cast<uint16_t *>(s_stage) + 128;         // [256] deep bits per id
+                    reinterpret_cast<uint4 *>(s_r)[lane] = make_uint4(0u, 0u, 0u, 0u);
+                    uint32_t o = q_inc - n_mine;
+                    for (uint32_t t = pm; t; t &= t - 1u) s_q[o++] = (uint8_t)(lane * 8 + (__ffs(t) - 1));
+                    __syncwarp();
+                    for (uint32_t base = 0; base < q_total; base += 32) {
+                        const bool act = base + lane < q_total;
+                        const uint32_t id = act ? (uint32_t)s_q[base + lane] : 64u;
+                        const int owner = (int)(id >> 3), j = (int)(id & 7u);
+                        const uint32_t h0 = __shfl_sync(0xFFFFFFFFu, hi, owner), l0 = __shfl_sync(0xFFFFFFFFu, lo, owner);
+                        const uint32_t h1 = __shfl_sync(0xFFFFFFFFu, hi, owner - 1), l1 = __shfl_sync(0xFFFFFFFFu, lo, owner - 1);
+                        const uint32_t h2 = __shfl_sync(0xFFFFFFFFu, hi, owner - 2), l2 = __shfl_sync(0xFFFFFFFFu, lo, owner - 2);
+                        if (act) {
+                            const unsigned long long P0 = ((unsigned long long)h0 << (4 * b)) | l0;
+                            const unsigned long long P1 = ((unsigned long long)h1 << (4 * b)) | l1;
+                            const unsigned long long P2 = ((unsigned long long)h2 << (4 * b)) | l2;
+                            const unsigned long long ctx = ((((P2 << (8 * b)) | P1) << (b * (j + 1)))) | (P0 >> (b * (7 - j)));
+                            s_r[id] = (uint16_t)deep_bits<K>(T, ctx, cm, A.max_len);
+                        }
+                    }
+                    __syncwarp();
+                    const uint4 rr = reinterpret_cast<const uint4 *>(s_r)[lane];
+                    masks[0] |= (rr.x & 0xFFFFu) << (K + 1); masks[1] |= (rr.x >> 16) << (K + 1);
+                    masks[2] |= (rr.y & 0xFFFFu) << (K + 1); masks[3] |= (rr.y >> 16) << (K + 1);
+                    masks[4] |= (rr.z & 0xFFFFu) << (K + 1); masks[5] |= (rr.z >> 16) << (K + 1);
+                    masks[6] |= (rr.w & 0xFFFFu) << (K + 1); masks[7] |= (rr.w >> 16) << (K + 1);
+                    __syncwarp();
+                }
             }
-            // ---- ordered offsets inside the row; publish the row aggregate right away
+            // ---- ordered offsets inside the row; hand the row total to the resolver
 #pragma unroll
             for (int j = 0; j < kTierPer; j++) my_cnt += __popc(masks[j]);
             inc = my_cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
                 if (lane >= o) inc += y;
             }
             row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-            if (lane == 0) lookback_publish(P.status, row, row_total);
+            if (lane == 0) s_cnt[(it & 1) * 32 + warp] = row_total;
+            __threadfence_block();
+            named_arrive(1 + (it & 1), kTierThreads);
         }
 
-        // ---- finish the previous row of this warp: look-back, stage, flush
-        if (pv) {
-            const unsigned long long base = lookback_resolve(P.status, p_row, p_total);
-            if (lane == 0 && p_row == n_rows - 1) *P.total_out = base + p_total;
+        // ---- finish the previous row of this warp: pick up its global offset, stage, flush
+        if (it > 0) {
+            const int pb = (it - 1) & 1;
+            named_sync(3 + pb, kTierThreads);
+            const unsigned long long base = s_wbase[pb * 32 + warp];
+            unsigned long long ctx0 = 0;
+            if (kIsMap) {
+                const uint32_t h1 = __shfl_up_sync(0xFFFFFFFFu, p_hi, 1), l1 = __shfl_up_sync(0xFFFFFFFFu, p_lo, 1);
+                const uint32_t h2 = __shfl_up_sync(0xFFFFFFFFu, p_hi, 2), l2 = __shfl_up_sync(0xFFFFFFFFu, p_lo, 2);
+                ctx0 = (((((unsigned long long)h2 << (4 * b)) | l2)) << (8 * b)) | (((unsigned long long)h1 << (4 * b)) | l1);
+            }
+            const unsigned long long Pk = ((unsigned long long)p_hi << (4 * b)) | p_lo;
             const uint32_t my_off = p_inc - p_cnt;
-            for (uint32_t win = 0; win < p_total; win += kTierStage) {
-                if (p_cnt && my_off < win + kTierStage && my_off + p_cnt > win) {
-                    unsigned long long ctx = p_ctx0;
-                    uint32_t o = my_off;
+            for (uint32_t win = 0; win < p_total; win += kStage) {
+                if (p_cnt && my_off < win + kStage && my_off + p_cnt > win) {
+                    uint32_t o = my_off - win;  // wraps below zero for records of an earlier window
 #pragma unroll
                     for (int j = 0; j < kTierPer; j++) {
-                        ctx = (ctx << b) | ((p_Pk >> (b * (kTierPer - 1 - j))) & cm);
                         uint32_t m = p_masks[j];
-                        const int32_t e = (int32_t)(p_p0 + j + 1);
-                        while (m) {
-                            const int d = 31 - __clz(m);
-                            m ^= 1u << d;
-                            if (o >= win && o < win + kTierStage) {
-                                s_stage[o - win] = make_int2(e - d + P.pos_base, e + P.pos_base);
-                                if (kIsMap) s_stage_val[o - win] = tier_value<K>(A, T, ctx, cm, d);
+                        const int32_t e = p_e0 + j;
+                        const unsigned long long ctx = kIsMap ? (ctx0 << (b * (j + 1))) | (Pk >> (b * (kTierPer - 1 - j))) : 0ull;
+                        auto put = [&](int d) {
+                            if (o < (uint32_t)kStage) {
+                                s_stage[o] = make_int2(e - d, e);
+                                if (kIsMap) s_stage_val[o] = tier_value<K>(T, ctx, cm, d);
                             }
                             ++o;
+                        };
+                        // longest first: deep levels (rare), then the two shared-memory levels that carry almost all
+                        // matches as straight-line code, then shallower levels (rare)
+                        for (uint32_t t = m >> (K + 1); t;) {
+                            const int d = 31 - __clz(t);
+                            t ^= 1u << d;
+                            put(d + K + 1);
+                        }
+                        if ((m >> K) & 1u) put(K);
+                        if (K >= 2 && ((m >> (K - 1)) & 1u)) put(K - 1);
+                        if (K >= 3) {
+                            for (uint32_t t = m & ((1u << (K - 1)) - 1u); t;) {
+                                const int d = 31 - __clz(t);
+                                t ^= 1u << d;
+                                put(d);
+                            }
                         }
                     }
                 }
                 __syncwarp();
-                const uint32_t cnt = min((uint32_t)kTierStage, p_total - win);
-                for (uint32_t r = lane; r < cnt; r += 32) {
-                    const unsigned long long g = base + win + r;
+                const uint32_t cnt = min((uint32_t)kStage, p_total - win);
+                for (uint32_t rr = lane; rr < cnt; rr += 32) {
+                    const unsigned long long g = base + win + rr;
                     if (g < (unsigned long long)P.cap) {
-                        __stcs(&P.pos_out[g], s_stage[r]);
-                        if (kIsMap) __stcs(&P.val_out[g], s_stage_val[r]);
+                        __stcs(&P.pos_out[g], s_stage[rr]);
+                        if (kIsMap) __stcs(&P.val_out[g], s_stage_val[rr]);
                     }
                 }
                 __syncwarp();
             }
         }
-        if (!have) break;
-        pv = true;
-        p_row = row;
-        p_p0 = p0;
-        p_Pk = Pk;
-        p_ctx0 = ctx0;
+        p_e0 = e0;
+        p_hi = hi;
+        p_lo = lo;
         p_cnt = my_cnt;
         p_inc = inc;
         p_total = row_total;

@@ -99,6 +99,7 @@ struct AcArgs {
     int64_t n;             // chars in the window
     int64_t emit_from;     // report matches whose last char index q is in [emit_from, emit_to)
     int64_t emit_to;
+    int64_t origin;        // k_ac_tier: position of row 0 (<= emit_from; makes every lane's 128-bit load aligned)
     int32_t pos_base;      // added to reported positions (stream offset; wraps like a Java int)
     int2 *pos_out;
     uint32_t *val_out;
