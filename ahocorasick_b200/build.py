@@ -10,10 +10,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libacgpu.so")
 SOURCES = ["engine.cu", "builder.cpp"]
-HEADERS = ["kernels.cuh", "kernel_tier.cuh", "device_tables.cuh", "builder.hpp", "java_char_tables.h",
-           os.path.join("..", "..", "include", "acgpu.h")]
+TIER_KS = range(1, 9)  # tier_inst.cu is compiled once per K (-DTIER_K=k), in parallel
+HEADERS = ["kernels.cuh", "kernel_tier.cuh", "tier_launch.hpp", "tier_inst.cu", "device_tables.cuh", "builder.hpp",
+           "java_char_tables.h", os.path.join("..", "..", "include", "acgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-cudart", "static"]
+              "-Xcompiler", "-fPIC,-O3,-Wall"]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def nvcc_path() -> str:
@@ -31,17 +33,35 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile(job):
+    src, obj, extra, verbose = job
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return r.returncode, r.stdout + r.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every translation unit for sm_100a (in parallel) and link libacgpu.so in-tree."""
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    jobs = [(os.path.join(CSRC, s), os.path.join(OBJ_DIR, os.path.splitext(s)[0] + ".o"), [], verbose) for s in SOURCES]
+    jobs += [(os.path.join(CSRC, "tier_inst.cu"), os.path.join(OBJ_DIR, "tier_k%d.o" % k), ["-DTIER_K=%d" % k], verbose)
+             for k in TIER_KS]
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(_compile, jobs))
+    log = "".join(out for _, out in results)
+    if any(rc != 0 for rc, _ in results):
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed building libacgpu.so")
+    cmd = [nvcc_path(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [j[1] for j in jobs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libacgpu.so")
+        sys.stderr.write(log + r.stdout + r.stderr)
+        raise RuntimeError("linking libacgpu.so failed")
     if verbose:
-        sys.stderr.write(r.stdout + r.stderr)
+        sys.stderr.write(log + r.stdout + r.stderr)
     return LIB
 
 

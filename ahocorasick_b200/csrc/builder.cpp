@@ -180,46 +180,105 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
         }
         if (a.is_map && d <= K && (inf & kInfoTerminal)) t.shallow_val[t.val_off[d] + radix[id]] = a.node_value[id];
     }
-    // bucketed deep table (4 entries per 32-byte bucket, load factor <= 0.5); retry with another seed if two
-    // entries on one probe path would share a tag
-    uint64_t n_buckets = 4;
-    while (n_buckets * 2 < n_deep) n_buckets <<= 1;
-    t.bucket_mask = static_cast<uint32_t>(n_buckets - 1);
+    // ---- path-compressed deep table
+    if (n_deep == 0) {
+        t.n_buckets = 1;
+        t.buckets.assign(8, 0);
+        if (a.is_map) {
+            t.deep_valbase.assign(2, 0);
+            t.deep_val.assign(1, kNone);
+        }
+        t.ok = true;
+        return;
+    }
+    std::vector<uint32_t> child_count(n, 0), only_child(n, 0);
+    for (int64_t id = 1; id < n; id++) {
+        child_count[node_parent[id]]++;
+        only_child[node_parent[id]] = static_cast<uint32_t>(id);
+    }
+    std::vector<uint8_t> is_head(n, 0);
+    for (int64_t id = 1; id < n; id++) {
+        if (depth[id] == K + 1 || (depth[id] > K + 1 && child_count[node_parent[id]] >= 2)) is_head[id] = 1;
+    }
+    struct Head {
+        uint64_t key;   // packed context of the head
+        uint64_t zw;    // chain | L << 40 | terminal flags << 44
+        uint32_t kids;  // child mask of the chain's last node
+        uint32_t val_begin, val_count;
+    };
+    std::vector<Head> heads;
+    std::vector<uint32_t> vals;
+    for (int64_t id = 1; id < n; id++) {  // ids ascend from parent to child, so continuation heads are marked in time
+        if (depth[id] <= K || !is_head[id]) continue;
+        Head h;
+        h.key = packed[id];
+        h.val_begin = static_cast<uint32_t>(vals.size());
+        uint64_t chain = 0, term = 0;
+        uint32_t cur = static_cast<uint32_t>(id);
+        int L = 0;
+        while (true) {
+            if (a.node_info[cur] & kInfoTerminal) {
+                term |= 1ull << L;
+                if (a.is_map) vals.push_back(a.node_value[cur]);
+            }
+            if (child_count[cur] != 1 || L == kTierChainMax) break;
+            const uint32_t nxt = only_child[cur];
+            chain |= static_cast<uint64_t>(node_cls[nxt]) << (b * L);
+            L++;
+            cur = nxt;
+        }
+        if (child_count[cur] == 1) is_head[only_child[cur]] = 1;  // chain outgrew the entry: continue in a new head
+        h.zw = chain | (static_cast<uint64_t>(L) << 40) | (term << 44);
+        h.kids = kids[cur];
+        h.val_count = static_cast<uint32_t>(vals.size()) - h.val_begin;
+        heads.push_back(h);
+    }
+    t.n_heads = heads.size();
+    // two entries per bucket, load factor about 0.55; retry with another seed if two entries on one probe path would
+    // share a tag
+    uint64_t n_buckets = std::max<uint64_t>(4, (heads.size() * 10 + 10) / 11);
+    if (n_buckets > 0x7FFFFFFFull) return;
+    t.n_buckets = static_cast<uint32_t>(n_buckets);
     for (int attempt = 0; attempt < 16; attempt++) {
         t.hash_seed = 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(attempt + 1);
         t.buckets.assign(n_buckets * 8, 0);
-        if (a.is_map) t.deep_val.assign(n_buckets * 4, kNone);
+        if (a.is_map) t.deep_valbase.assign(n_buckets * 2, 0);
         bool clash = false;
-        for (int64_t id = 1; id < n && !clash; id++) {
-            if (depth[id] <= K) continue;
-            const uint32_t inf = a.node_info[id];
-            const uint64_t h = deep_hash64(packed[id], t.hash_seed);
-            const uint32_t want = (static_cast<uint32_t>(h >> 36) << 4) | 8u;
-            uint32_t bk = static_cast<uint32_t>(h) & t.bucket_mask;
+        for (size_t i = 0; i < heads.size() && !clash; i++) {
+            const Head &h = heads[i];
+            const uint64_t hs = deep_hash64(h.key, t.hash_seed);
+            const uint32_t want = (static_cast<uint32_t>(hs >> 36) << 4) | 8u;
+            uint32_t bk = static_cast<uint32_t>(((hs & 0xFFFFFFFFull) * n_buckets) >> 32);
             while (true) {
                 uint32_t *e = &t.buckets[static_cast<size_t>(bk) * 8];
                 int free_slot = -1;
-                for (int k = 0; k < 4; k++) {
-                    if (e[2 * k] == 0) {
+                for (int k = 0; k < 2; k++) {
+                    if (e[4 * k] == 0) {
                         if (free_slot < 0) free_slot = k;
-                    } else if ((e[2 * k] & ~7u) == want) {
+                    } else if ((e[4 * k] & ~7u) == want) {
                         clash = true;
                     }
                 }
                 if (clash) break;
                 if (free_slot >= 0) {
-                    e[2 * free_slot] = want | (inf & kInfoTerminal ? 1u : 0u) | (inf & kInfoHasChildren ? 2u : 0u);
-                    e[2 * free_slot + 1] = kids[id];
-                    if (a.is_map) t.deep_val[static_cast<size_t>(bk) * 4 + free_slot] = a.node_value[id];
+                    e[4 * free_slot] = want;
+                    e[4 * free_slot + 1] = h.kids;
+                    e[4 * free_slot + 2] = static_cast<uint32_t>(h.zw);
+                    e[4 * free_slot + 3] = static_cast<uint32_t>(h.zw >> 32);
+                    if (a.is_map) t.deep_valbase[static_cast<size_t>(bk) * 2 + free_slot] = h.val_begin;
                     break;
                 }
-                bk = (bk + 1) & t.bucket_mask;
+                bk = bk + 1 == t.n_buckets ? 0 : bk + 1;
             }
         }
         // a later insertion may put an equal tag into a bucket that an earlier key's probe path crosses only if
         // that bucket was full when the earlier key passed it - and full buckets never change, so checking at
         // insertion time against every bucket passed (done above) is sufficient.
         if (!clash) {
+            if (a.is_map) {
+                t.deep_val.swap(vals);
+                if (t.deep_val.empty()) t.deep_val.push_back(kNone);
+            }
             t.ok = true;
             return;
         }

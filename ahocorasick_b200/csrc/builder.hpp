@@ -54,10 +54,19 @@ struct IllegalArgument : std::runtime_error {
 //     small enough to live in shared memory
 //   * kidmask[level-K index] = set of classes that continue the context (exact), so level K+1 is only probed
 //     for contexts that exist
-//   * deeper nodes sit in a bucketed table keyed by the packed context itself (b bits per class): a bucket is one
-//     32-byte sector holding four 8-byte entries {28-bit tag | occupied | flags, child mask}.  Because child masks
-//     are exact, every probe is for a key that exists, and the builder guarantees that no bucket on a key's probe
-//     path holds another entry with the same tag - so a tag match is exact and one sector load resolves one level.
+//   * deeper nodes are PATH-COMPRESSED: a "head" is a level-(K+1) node, a child of a branching deep node, or the
+//     continuation of a chain that outgrew one entry.  One 16-byte entry describes the head and the unbranched chain
+//     hanging below it:
+//         x = 28-bit tag << 4 | 8 (occupied)
+//         y = child mask of the chain's LAST node (exact)
+//         z,w (64 bits) = chain classes (b bits each, first step lowest) | chain length L << 40 | terminal flags of
+//                         the head and the L chain nodes << 44        (L <= 8, b <= 5)
+//     so a context that reaches a head resolves all of its deeper levels with ONE probe in the common case (keyword
+//     tails rarely branch).  Entries live in a bucketed open-addressing table keyed by the packed context of the
+//     head (two entries per 32-byte sector, bucket = fastrange(hash)).  Child masks are exact, so every probe is for
+//     a key that exists, and the builder guarantees that no bucket on a key's probe path holds another entry with
+//     the same tag - a tag match is exact.
+constexpr int kTierChainMax = 8;
 struct TierTables {
     bool ok = false;
     int32_t C = 0;        // radix = number of classes (including class 0 = other)
@@ -68,13 +77,16 @@ struct TierTables {
     uint32_t pow_c[10] = {0};        // C^(j-1)
     std::vector<uint32_t> smem_words;
     std::vector<uint32_t> kidmask;   // per level-K entry, bit c = the node has a child on class c
-    std::vector<uint32_t> buckets;   // 8 words per bucket: 4 x {tag << 4 | 8 | flags, child mask}
-    uint32_t bucket_mask = 0;
+    std::vector<uint32_t> buckets;   // 8 words per bucket: 2 entries x {x, y, z, w}
+    uint32_t n_buckets = 0;
     uint64_t hash_seed = 0;
-    uint64_t n_deep = 0;
-    // Map values: shallow levels indexed like the bit tables, deep values indexed by bucket * 4 + entry
+    uint64_t n_deep = 0;             // trie nodes deeper than K
+    uint64_t n_heads = 0;            // entries of the compressed table
+    // Map values: shallow levels indexed like the bit tables; deep values are stored per entry, consecutively in
+    // chain order (terminal nodes only), starting at deep_valbase[bucket * 2 + entry]
     std::vector<uint32_t> shallow_val;
     uint64_t val_off[10] = {0};
+    std::vector<uint32_t> deep_valbase;
     std::vector<uint32_t> deep_val;
 };
 

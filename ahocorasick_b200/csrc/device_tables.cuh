@@ -23,6 +23,23 @@ struct DevAutomaton {
     int32_t is_map;
 };
 
+// arguments of the AhoCorasick-family scan kernels (k_ac_scan, k_ac_tier)
+struct AcArgs {
+    const uint16_t *hay;   // haystack window (device)
+    int64_t n;             // chars in the window
+    int64_t emit_from;     // report matches whose last char index q is in [emit_from, emit_to)
+    int64_t emit_to;
+    int64_t origin;        // k_ac_tier: position of row 0 (<= emit_from; makes every lane's 128-bit load aligned)
+    int32_t pos_base;      // added to reported positions (stream offset; wraps like a Java int)
+    int2 *pos_out;
+    uint32_t *val_out;
+    int64_t cap;
+    unsigned long long *total_out;
+    unsigned int *tile_counter;
+    unsigned long long *status;
+    int64_t n_tiles;
+};
+
 __host__ __device__ __forceinline__ uint32_t edge_hash_d(uint32_t parent, uint32_t c) {
     uint32_t h = parent * 0x9E3779B1u ^ (c * 0x85EBCA6Bu + 0x7F4A7C15u);
     h ^= h >> 15;

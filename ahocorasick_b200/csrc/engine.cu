@@ -16,6 +16,7 @@
 #include "builder.hpp"
 #include "kernels.cuh"
 #include "kernel_tier.cuh"
+#include "tier_launch.hpp"
 
 using namespace acgpu;
 
@@ -51,7 +52,6 @@ struct Matcher {
     bool sel_attr_set = false;
     // generation-2 (tiered) tables, AhoCorasick family on narrow alphabets
     bool use_tier = false;
-    bool tier_attr_set = false;
     DevTier tier{};
     void *d_tier_blob = nullptr;
     size_t tier_smem = 0;
@@ -121,6 +121,7 @@ int upload_tier(Matcher *m) {
     size_t o_kid = reserve(t.kidmask.size() * 4);
     size_t o_deep = reserve(t.buckets.size() * 4);
     size_t o_sval = reserve(t.shallow_val.size() * 4);
+    size_t o_dvb = reserve(t.deep_valbase.size() * 4);
     size_t o_dval = reserve(t.deep_val.size() * 4);
     CU_TRY(cudaMalloc(&m->d_tier_blob, off));
     m->table_bytes += static_cast<int64_t>(off);
@@ -132,6 +133,7 @@ int upload_tier(Matcher *m) {
     if (!t.kidmask.empty()) CU_TRY(cudaMemcpy(b + o_kid, t.kidmask.data(), t.kidmask.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(b + o_deep, t.buckets.data(), t.buckets.size() * 4, cudaMemcpyHostToDevice));
     if (!t.shallow_val.empty()) CU_TRY(cudaMemcpy(b + o_sval, t.shallow_val.data(), t.shallow_val.size() * 4, cudaMemcpyHostToDevice));
+    if (!t.deep_valbase.empty()) CU_TRY(cudaMemcpy(b + o_dvb, t.deep_valbase.data(), t.deep_valbase.size() * 4, cudaMemcpyHostToDevice));
     if (!t.deep_val.empty()) CU_TRY(cudaMemcpy(b + o_dval, t.deep_val.data(), t.deep_val.size() * 4, cudaMemcpyHostToDevice));
     DevTier &d = m->tier;
     d.smem_words = reinterpret_cast<const uint32_t *>(b + o_words);
@@ -140,9 +142,11 @@ int upload_tier(Matcher *m) {
     d.buckets = reinterpret_cast<const uint4 *>(b + o_deep);
     d.hash_seed = t.hash_seed;
     d.shallow_val = reinterpret_cast<const uint32_t *>(b + o_sval);
+    d.deep_valbase = reinterpret_cast<const uint32_t *>(b + o_dvb);
     d.deep_val = reinterpret_cast<const uint32_t *>(b + o_dval);
     d.n_words = static_cast<uint32_t>(t.smem_words.size());
-    d.bucket_mask = t.bucket_mask;
+    d.n_buckets = t.n_buckets;
+    d.inv_b = (65536u + static_cast<uint32_t>(t.b) - 1u) / static_cast<uint32_t>(t.b);
     d.term_levels = t.term_levels;
     d.b = t.b;
     d.C = t.C;
@@ -157,32 +161,30 @@ int upload_tier(Matcher *m) {
     return ACGPU_OK;
 }
 
-// The tiered kernel assigns rows statically and lets a warp wait for rows of lower index, so every CTA of the
-// grid must be resident at once: launched cooperatively (fails loudly instead of dead-locking).
-template <int K>
-int launch_tier_k(Matcher *m, const AcArgs &P, int grid, cudaStream_t st) {
-    void *args[3] = {const_cast<DevAutomaton *>(&m->dev), const_cast<DevTier *>(&m->tier), const_cast<AcArgs *>(&P)};
-    const void *fn = m->dev.is_map ? reinterpret_cast<const void *>(k_ac_tier<K, true>)
-                                   : reinterpret_cast<const void *>(k_ac_tier<K, false>);
-    if (!m->tier_attr_set) {
-        CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->tier_smem));
-        m->tier_attr_set = true;
-    }
-    CU_TRY(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kTierThreads), args, m->tier_smem, st));
-    return ACGPU_OK;
+// k_ac_tier variant for this dictionary: which levels below K hold keywords (see kernel_tier.cuh)
+int tier_low_variant(const DevTier &t) {
+    const uint32_t below = t.term_levels & ((1u << t.K) - 1u) & ~1u;  // bits 1..K-1
+    if (below == 0) return 2;
+    if (below == (1u << (t.K - 1))) return 1;
+    return 0;
 }
 
 int launch_tier(Matcher *m, const AcArgs &P, int grid, cudaStream_t st) {
+    const int low = tier_low_variant(m->tier);
+    const bool is_map = m->dev.is_map != 0;
+    cudaError_t e;
     switch (m->tier.K) {
-    case 1: return launch_tier_k<1>(m, P, grid, st);
-    case 2: return launch_tier_k<2>(m, P, grid, st);
-    case 3: return launch_tier_k<3>(m, P, grid, st);
-    case 4: return launch_tier_k<4>(m, P, grid, st);
-    case 5: return launch_tier_k<5>(m, P, grid, st);
-    case 6: return launch_tier_k<6>(m, P, grid, st);
-    case 7: return launch_tier_k<7>(m, P, grid, st);
-    default: return launch_tier_k<8>(m, P, grid, st);
+    case 1: e = tier_launch_1(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
+    case 2: e = tier_launch_2(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
+    case 3: e = tier_launch_3(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
+    case 4: e = tier_launch_4(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
+    case 5: e = tier_launch_5(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
+    case 6: e = tier_launch_6(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
+    case 7: e = tier_launch_7(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
+    default: e = tier_launch_8(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
     }
+    CU_TRY(e);
+    return ACGPU_OK;
 }
 
 // Scratch for one match call, carved from one stream-ordered allocation.

@@ -9,8 +9,9 @@
 //   * levels 1..K are direct-indexed bit tables in SHARED memory (mixed-radix index of the last j classes);
 //   * level K+1 existence comes from a per-level-K-entry child mask (one L2-resident word), so the deep table is
 //     only probed for contexts that really continue;
-//   * levels > K are 8-byte slots (context << 4 | flags) in an open-addressing table keyed by the context itself;
-//   * loads of a lane's 8 positions are issued back to back (memory-level parallelism) before any is consumed;
+//   * levels > K are path-compressed: one 16-byte entry per chain head (keyed by the packed context of the head)
+//     holds the unbranched chain below it, so one sector load resolves a whole keyword tail;
+//   * the contexts of a warp row that continue past level K are compacted into a queue and walked 32 at a time;
 //   * the depths that hit are kept as a bitmask per position: one pass, count = popc.
 // Ordered emission: a CTA tile = 24 warp rows of 240 positions.  Worker warps count their row, hand the count to
 // a dedicated RESOLVER warp through shared memory + named barriers (bar.arrive / bar.sync, no __syncthreads in the
@@ -28,12 +29,14 @@ struct DevTier {
     const uint32_t *smem_words;  // direct-indexed level tables (copied to shared memory by every CTA)
     const uint32_t *cls8;        // 64 words: class of code units 0..255, one byte each
     const uint32_t *kidmask;     // [C^K] exact child masks of the level-K entries (nullptr: no deeper levels)
-    const uint4 *buckets;        // deep table: 2 x uint4 per 32-byte bucket = 4 entries {tag<<4 | 8 | flags, child mask}
+    const uint4 *buckets;        // deep table: 2 entries per 32-byte bucket, see TierTables in builder.hpp
     const uint32_t *shallow_val;
-    const uint32_t *deep_val;    // [bucket * 4 + entry]
+    const uint32_t *deep_valbase;  // [bucket * 2 + entry] -> first value of the entry's chain in deep_val
+    const uint32_t *deep_val;
     unsigned long long hash_seed;
     uint32_t n_words;
-    uint32_t bucket_mask;
+    uint32_t n_buckets;
+    uint32_t inv_b;              // ceil(65536 / b): (t * inv_b) >> 16 == t / b for t < 64
     uint32_t term_levels;
     int32_t b, C, K;
     uint32_t lvl_off[10];
@@ -71,36 +74,43 @@ __device__ __forceinline__ unsigned long long deep_hash64_d(unsigned long long k
     return h;
 }
 
-// One deep probe.  Every probe is for a key that exists (child masks are exact) and the builder keeps tags unique
-// along a probe path, so the first entry whose tag matches is the node.
-__device__ __forceinline__ void deep_probe(const DevTier &T, unsigned long long key, uint32_t &flags, uint32_t &kids,
-                                           uint32_t &slot) {
+// One deep probe: the entry of the chain head whose packed context is `key`.  Every probe is for a key that exists
+// (child masks are exact) and the builder keeps tags unique along a probe path, so the first entry whose tag
+// matches is the head.
+__device__ __forceinline__ uint4 deep_probe(const DevTier &T, unsigned long long key, uint32_t &slot) {
     const unsigned long long h = deep_hash64_d(key, T.hash_seed);
-    uint32_t bucket = (uint32_t)h & T.bucket_mask;
+    uint32_t bucket = __umulhi((uint32_t)h, T.n_buckets);
     const uint32_t want = ((uint32_t)(h >> 36) << 4) | 8u;
     while (true) {
         const uint4 *q = T.buckets + (size_t)bucket * 2;
-        const uint4 a = __ldg(q);
-        const uint4 b = __ldg(q + 1);
-        if ((a.x & ~7u) == want) { flags = a.x & 7u; kids = a.y; slot = bucket * 4u; return; }
-        if ((a.z & ~7u) == want) { flags = a.z & 7u; kids = a.w; slot = bucket * 4u + 1u; return; }
-        if ((b.x & ~7u) == want) { flags = b.x & 7u; kids = b.y; slot = bucket * 4u + 2u; return; }
-        if ((b.z & ~7u) == want) { flags = b.z & 7u; kids = b.w; slot = bucket * 4u + 3u; return; }
-        bucket = (bucket + 1u) & T.bucket_mask;  // overflowed bucket: the key sits further along
+        const uint4 e0 = __ldg(q);
+        const uint4 e1 = __ldg(q + 1);
+        if ((e0.x & ~7u) == want) { slot = bucket * 2u; return e0; }
+        if ((e1.x & ~7u) == want) { slot = bucket * 2u + 1u; return e1; }
+        bucket = bucket + 1u == T.n_buckets ? 0u : bucket + 1u;  // overflowed bucket: the key sits further along
     }
 }
 
 // Levels K+1.. of a context whose level-(K+1) node exists: bit (d - K - 1) set = a keyword of length d ends here.
+// One probe per chain head; the chain below a head is compared against the context in registers.
 template <int K>
 __device__ __forceinline__ uint32_t deep_bits(const DevTier &T, unsigned long long ctx, uint32_t cm, int max_len) {
-    uint32_t fl, kids, slot;
-    deep_probe(T, ctx & ((1ull << (T.b * (K + 1))) - 1ull), fl, kids, slot);
-    uint32_t bits = fl & 1u;
-    for (int d = K + 2; d <= max_len && (fl & 2u); d++) {
-        const uint32_t c = ((uint32_t)(ctx >> (T.b * (d - 1)))) & cm;
-        if (!((kids >> c) & 1u)) break;  // exact: no such child (class 0 never has one)
-        deep_probe(T, ctx & ((1ull << (T.b * d)) - 1ull), fl, kids, slot);
-        bits |= (fl & 1u) << (d - K - 1);
+    uint32_t bits = 0;
+    int d = K + 1;  // depth of the current head
+    while (true) {
+        uint32_t slot;
+        const uint4 e = deep_probe(T, ctx & ((1ull << (T.b * d)) - 1ull), slot);
+        const unsigned long long zw = ((unsigned long long)e.w << 32) | e.z;
+        const int L = (int)(e.w >> 8) & 15;
+        const uint32_t term = (e.w >> 12) & 0x1FFu;
+        const unsigned long long x = ((ctx >> (T.b * d)) ^ zw) & ((1ull << (T.b * L)) - 1ull);
+        const int m = x ? (int)(((uint32_t)(__ffsll((long long)x) - 1) * T.inv_b) >> 16) : L;  // chain steps that match
+        bits |= (term & ((2u << m) - 1u)) << (d - K - 1);
+        d += L;
+        if (m < L || d >= max_len) break;
+        const uint32_t c = ((uint32_t)(ctx >> (T.b * d))) & cm;
+        if (!((e.y >> c) & 1u)) break;  // exact: no such child (class 0 never has one)
+        d += 1;
     }
     return bits;
 }
@@ -130,6 +140,7 @@ __device__ __forceinline__ void load_classes8(const DevAutomaton &A, const uint1
     }
 }
 
+// value index of the keyword of length d that ends the context (Maps)
 template <int K>
 __device__ __forceinline__ uint32_t tier_value(const DevTier &T, unsigned long long ctx, uint32_t cm, int d) {
     if (d <= K) {
@@ -140,15 +151,25 @@ __device__ __forceinline__ uint32_t tier_value(const DevTier &T, unsigned long l
         }
         return __ldg(&T.shallow_val[T.val_off[d] + idx]);
     }
-    uint32_t fl, kids, slot;
-    deep_probe(T, ctx & ((1ull << (T.b * d)) - 1ull), fl, kids, slot);
-    return __ldg(&T.deep_val[slot]);
+    int hd = K + 1;  // walk the chain heads down to the one whose chain covers depth d
+    while (true) {
+        uint32_t slot;
+        const uint4 e = deep_probe(T, ctx & ((1ull << (T.b * hd)) - 1ull), slot);
+        const int L = (int)(e.w >> 8) & 15;
+        if (d <= hd + L) {
+            const uint32_t term = (e.w >> 12) & 0x1FFu;
+            return __ldg(&T.deep_val[__ldg(&T.deep_valbase[slot]) + __popc(term & ((1u << (d - hd)) - 1u))]);
+        }
+        hd += L + 1;
+    }
 }
 
 // AcArgs: n_tiles = number of CTA tiles; a row = 240 emitting positions (lanes 2..31) preceded by 16 context
 // positions (lanes 0,1), so one 128-bit load per lane covers the row and its left context.  Rows start at
 // P.origin (<= emit_from, chosen by the host so that every lane's load is 16-byte aligned).
-template <int K, bool kIsMap>
+// LOW selects how the levels below K are looked up: 0 = every level that has keywords (predicated), 1 = only level
+// K-1 has keywords, 2 = no keyword is shorter than K.
+template <int K, int LOW, bool kIsMap>
 __global__ void __launch_bounds__(kTierThreads, 1) k_ac_tier(const DevAutomaton A, const DevTier T, const AcArgs P) {
     constexpr int kStage = tier_stage_records(kIsMap);
     extern __shared__ __align__(16) uint32_t s_mem[];
@@ -257,7 +278,8 @@ __global__ void __launch_bounds__(kTierThreads, 1) k_ac_tier(const DevAutomaton 
                 uint32_t m = 0;
 #pragma unroll
                 for (int i = 1; i < K; i++) {
-                    const bool on = (T.term_levels >> i) & 1u;
+                    if (LOW == 2 || (LOW == 1 && i != K - 1)) continue;
+                    const bool on = LOW == 1 || ((T.term_levels >> i) & 1u);
                     const uint32_t w = on ? s_tab[T.lvl_off[i] + (r[i] >> 5)] : 0u;
                     m |= (__funnelshift_r(w, 0u, r[i]) & 1u) << i;
                 }
@@ -348,49 +370,79 @@ __global__ void __launch_bounds__(kTierThreads, 1) k_ac_tier(const DevAutomaton 
             }
             const unsigned long long Pk = ((unsigned long long)p_hi << (4 * b)) | p_lo;
             const uint32_t my_off = p_inc - p_cnt;
-            for (uint32_t win = 0; win < p_total; win += kStage) {
-                if (p_cnt && my_off < win + kStage && my_off + p_cnt > win) {
-                    uint32_t o = my_off - win;  // wraps below zero for records of an earlier window
+            if (!kIsMap && p_total <= (uint32_t)kStage) {
+                // ---- common case: the whole row fits the staging window.  Longest first: deep levels (rare, loop),
+                //      then the two shared-memory levels that carry almost all matches as predicated straight-line
+                //      stores, then shallower levels (rare, loop)
+                if (p_cnt) {
+                    int2 *dst = s_stage + my_off;
 #pragma unroll
                     for (int j = 0; j < kTierPer; j++) {
-                        uint32_t m = p_masks[j];
+                        const uint32_t m = p_masks[j];
                         const int32_t e = p_e0 + j;
-                        const unsigned long long ctx = kIsMap ? (ctx0 << (b * (j + 1))) | (Pk >> (b * (kTierPer - 1 - j))) : 0ull;
-                        auto put = [&](int d) {
-                            if (o < (uint32_t)kStage) {
-                                s_stage[o] = make_int2(e - d, e);
-                                if (kIsMap) s_stage_val[o] = tier_value<K>(T, ctx, cm, d);
+                        if (m >> (K + 1)) {
+                            for (uint32_t t = m >> (K + 1); t;) {
+                                const int d = 31 - __clz(t);
+                                t ^= 1u << d;
+                                *dst++ = make_int2(e - (d + K + 1), e);
                             }
-                            ++o;
-                        };
-                        // longest first: deep levels (rare), then the two shared-memory levels that carry almost all
-                        // matches as straight-line code, then shallower levels (rare)
-                        for (uint32_t t = m >> (K + 1); t;) {
-                            const int d = 31 - __clz(t);
-                            t ^= 1u << d;
-                            put(d + K + 1);
                         }
-                        if ((m >> K) & 1u) put(K);
-                        if (K >= 2 && ((m >> (K - 1)) & 1u)) put(K - 1);
-                        if (K >= 3) {
+                        const bool tk = (m >> K) & 1u;
+                        if (tk) *dst = make_int2(e - K, e);
+                        dst += tk;
+                        if (K >= 2 && LOW != 2) {
+                            const bool tk1 = (m >> (K - 1)) & 1u;
+                            if (tk1) *dst = make_int2(e - (K - 1), e);
+                            dst += tk1;
+                        }
+                        if (K >= 3 && LOW == 0) {
                             for (uint32_t t = m & ((1u << (K - 1)) - 1u); t;) {
                                 const int d = 31 - __clz(t);
                                 t ^= 1u << d;
-                                put(d);
+                                *dst++ = make_int2(e - d, e);
                             }
                         }
                     }
                 }
                 __syncwarp();
-                const uint32_t cnt = min((uint32_t)kStage, p_total - win);
-                for (uint32_t rr = lane; rr < cnt; rr += 32) {
-                    const unsigned long long g = base + win + rr;
-                    if (g < (unsigned long long)P.cap) {
-                        __stcs(&P.pos_out[g], s_stage[rr]);
-                        if (kIsMap) __stcs(&P.val_out[g], s_stage_val[rr]);
-                    }
+                for (uint32_t rr = lane; rr < p_total; rr += 32) {
+                    const unsigned long long g = base + rr;
+                    if (g < (unsigned long long)P.cap) __stcs(&P.pos_out[g], s_stage[rr]);
                 }
                 __syncwarp();
+            } else {
+                for (uint32_t win = 0; win < p_total; win += kStage) {
+                    if (p_cnt && my_off < win + kStage && my_off + p_cnt > win) {
+                        uint32_t o = my_off - win;  // wraps below zero for records of an earlier window
+#pragma unroll 1
+                        for (int j = 0; j < kTierPer; j++) {
+                            const int32_t e = p_e0 + j;
+                            const unsigned long long ctx = kIsMap ? (ctx0 << (b * (j + 1))) | (Pk >> (b * (kTierPer - 1 - j))) : 0ull;
+                            uint32_t m = 0;
+#pragma unroll
+                            for (int jj = 0; jj < kTierPer; jj++) m = jj == j ? p_masks[jj] : m;
+                            while (m) {  // longest first
+                                const int d = 31 - __clz(m);
+                                m ^= 1u << d;
+                                if (o < (uint32_t)kStage) {
+                                    s_stage[o] = make_int2(e - d, e);
+                                    if (kIsMap) s_stage_val[o] = tier_value<K>(T, ctx, cm, d);
+                                }
+                                ++o;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    const uint32_t cnt = min((uint32_t)kStage, p_total - win);
+                    for (uint32_t rr = lane; rr < cnt; rr += 32) {
+                        const unsigned long long g = base + win + rr;
+                        if (g < (unsigned long long)P.cap) {
+                            __stcs(&P.pos_out[g], s_stage[rr]);
+                            if (kIsMap) __stcs(&P.val_out[g], s_stage_val[rr]);
+                        }
+                    }
+                    __syncwarp();
+                }
             }
         }
         p_e0 = e0;

@@ -94,21 +94,6 @@ constexpr int kAcTile = 4096;                  // end positions per tile
 constexpr int kAcRows = kAcTile / kThreads;    // 16 rows of 32 per warp
 constexpr int kAcHaloMax = 2048;               // classes staged to the left of a tile
 
-struct AcArgs {
-    const uint16_t *hay;   // haystack window (device)
-    int64_t n;             // chars in the window
-    int64_t emit_from;     // report matches whose last char index q is in [emit_from, emit_to)
-    int64_t emit_to;
-    int64_t origin;        // k_ac_tier: position of row 0 (<= emit_from; makes every lane's 128-bit load aligned)
-    int32_t pos_base;      // added to reported positions (stream offset; wraps like a Java int)
-    int2 *pos_out;
-    uint32_t *val_out;
-    int64_t cap;
-    unsigned long long *total_out;
-    unsigned int *tile_counter;
-    unsigned long long *status;
-    int64_t n_tiles;
-};
 
 template <bool kIsMap>
 __global__ void __launch_bounds__(kThreads) k_ac_scan(const DevAutomaton A, const AcArgs P) {

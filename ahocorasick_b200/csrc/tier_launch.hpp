@@ -1,0 +1,27 @@
+// Launch entry points of the k_ac_tier instantiations.  Every K lives in its own translation unit (tier_inst.cu
+// compiled with -DTIER_K=k) so the 48 kernels build in parallel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device_tables.cuh"
+
+namespace acgpu {
+
+struct DevTier;
+
+// low: 0 = every level below K may hold keywords, 1 = only level K-1 does, 2 = none does.
+// Sets the dynamic shared-memory attribute once per kernel and launches cooperatively (the kernel waits for tiles of
+// lower index, so the whole grid must be resident: a launch that cannot be, fails instead of dead-locking).
+#define ACGPU_DECLARE_TIER(k) \
+    cudaError_t tier_launch_##k(int low, bool is_map, const DevAutomaton &A, const DevTier &T, const AcArgs &P, int grid, size_t smem, cudaStream_t st);
+ACGPU_DECLARE_TIER(1)
+ACGPU_DECLARE_TIER(2)
+ACGPU_DECLARE_TIER(3)
+ACGPU_DECLARE_TIER(4)
+ACGPU_DECLARE_TIER(5)
+ACGPU_DECLARE_TIER(6)
+ACGPU_DECLARE_TIER(7)
+ACGPU_DECLARE_TIER(8)
+#undef ACGPU_DECLARE_TIER
+
+}  // namespace acgpu

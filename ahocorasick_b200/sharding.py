@@ -1,0 +1,84 @@
+"""Multi-GPU sharding of the matching path — host-side plan + the one exchange the path has.
+
+The AhoCorasick family needs no automaton state across positions (every end position is matched from its own
+left context), so a corpus shards with NO data-path collective:
+
+* a corpus of independent haystacks (a Java String holds < 2^31 chars, so a 64 GB corpus is many match() calls,
+  AhoCorasickSet.java:193) is dealt round-robin: ``deal_haystacks``;
+* one large haystack is cut by END-position range: rank r reports the matches whose end lies in its range and reads
+  ``max_len - 1`` chars of left context: ``plan_range_shards``.  Concatenating the ranks' record streams in rank
+  order gives exactly the single-GPU stream (end ascending, longest first).
+
+The only exchange is an all-gather of per-rank match counts (8 bytes per rank) so that every rank knows its
+global record offset: ``exchange_counts`` (NCCL on device tensors, gloo on CPU tensors in the tests).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Sequence, Tuple
+
+
+@dataclass(frozen=True)
+class RangeShard:
+    rank: int
+    emit_from: int   # first end-anchor position (index of the match's last char) this rank reports
+    emit_to: int     # one past the last
+    read_from: int   # first haystack char this rank needs on its device (left context)
+
+    @property
+    def read_to(self) -> int:
+        return self.emit_to
+
+
+def plan_range_shards(n_chars: int, world: int, max_len: int, align: int = 8) -> List[RangeShard]:
+    """Cut [0, n_chars) into `world` contiguous end-position ranges (boundaries aligned to `align` chars so every
+    shard keeps the kernel's 16-byte aligned loads)."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    ctx = max(0, max_len - 1)
+    bounds = [0]
+    for r in range(1, world):
+        b = (n_chars * r // world) // align * align
+        bounds.append(max(bounds[-1], min(b, n_chars)))
+    bounds.append(n_chars)
+    return [RangeShard(r, bounds[r], bounds[r + 1], max(0, bounds[r] - ctx)) for r in range(world)]
+
+
+def deal_haystacks(n_haystacks: int, world: int, rank: int) -> List[int]:
+    """Indices of the haystacks rank `rank` scans (round-robin)."""
+    return list(range(rank, n_haystacks, world))
+
+
+def exchange_counts(my_count: int, device=None, group=None) -> Tuple[List[int], int, int]:
+    """All-gather the per-rank match counts.  Returns (counts per rank, my global record offset, total)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return [int(my_count)], 0, int(my_count)
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = torch.tensor([int(my_count)], dtype=torch.int64, device=device)
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    counts = [int(p.item()) for p in parts]
+    return counts, sum(counts[:rank]), sum(counts)
+
+
+def match_range_shard(matcher, d_haystack_ptr: int, n_chars: int, shard: RangeShard, d_pos_ptr: int, d_val_ptr,
+                      cap: int, stream_ptr=None) -> int:
+    """Scan one end-position range of a haystack that is resident on this rank's GPU (the pointer addresses char 0
+    of the WHOLE haystack; only [shard.read_from, shard.emit_to) is touched).  Returns the number of matches."""
+    import ctypes as C
+    from . import _lib
+    tot = C.c_int64(0)
+    _lib.check(_lib.lib().acgpu_match_device(matcher.handle, d_haystack_ptr, shard.emit_to, shard.emit_from, shard.emit_to,
+                                             d_pos_ptr, d_val_ptr, cap, C.byref(tot), stream_ptr))
+    return tot.value
+
+
+def merge_rank_streams(streams: Sequence[Sequence]) -> list:
+    """Rank-ordered concatenation = the reference's listener order."""
+    out: list = []
+    for s in streams:
+        out.extend(s)
+    return out
