@@ -101,7 +101,7 @@ void make_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, in
 
 namespace {
 
-constexpr uint64_t kTierSmemBits = 152ull * 1024 * 8;  // shared-memory budget for ALL direct-indexed level tables
+constexpr uint64_t kTierSmemBits = 135ull * 1024 * 8;  // shared-memory budget for ALL direct-indexed level tables
 
 void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, const std::vector<uint16_t> &node_cls) {
     TierTables &t = a.tier;
@@ -110,7 +110,7 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
     if (!a.has_other || a.max_len < 1 || C < 2 || C > 32) return;  // child masks are 32-bit words
     int b = 1;
     while ((1 << b) < C) b++;
-    if (static_cast<int64_t>(b) * a.max_len > 60 || a.max_len - 1 > 16) return;
+    if (static_cast<int64_t>(b) * a.max_len > 60 || a.max_len > 16) return;  // contexts pack into 60 bits, hit masks into 16
     // K = deepest level whose 2-bit table fits the shared-memory budget
     int K = 0;
     uint64_t entries = 1, lower_bits = 0;  // lower_bits: 1-bit tables of the levels below K (word-rounded)

@@ -41,8 +41,31 @@ int fail(int code, const std::string &msg) {
 
 constexpr uint64_t kMagic = 0xAC69B200AC69B200ull;
 
+// Streams, events and the pinned/device counters of one host-buffer call; parked in the matcher between calls
+// (creating them costs far more than a small scan).
+struct CallCtx {
+    cudaStream_t s_up = nullptr, s_k = nullptr, s_dn = nullptr;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_dn[2] = {nullptr, nullptr};
+    unsigned long long *d_total = nullptr;  // [2] device
+    unsigned long long *h_total = nullptr;  // [2] pinned
+    void destroy() {
+        for (int i = 0; i < 2; i++) {
+            if (ev_up[i]) cudaEventDestroy(ev_up[i]);
+            if (ev_k[i]) cudaEventDestroy(ev_k[i]);
+            if (ev_dn[i]) cudaEventDestroy(ev_dn[i]);
+        }
+        if (d_total) cudaFree(d_total);
+        if (h_total) cudaFreeHost(h_total);
+        if (s_up) cudaStreamDestroy(s_up);
+        if (s_k) cudaStreamDestroy(s_k);
+        if (s_dn) cudaStreamDestroy(s_dn);
+    }
+};
+
 struct Matcher {
     uint64_t magic = kMagic;
+    std::mutex ctx_mu;
+    std::vector<CallCtx *> ctx_free;
     int device = 0;
     int sm_count = 148;
     HostAutomaton host;  // tables kept for introspection; device copies below
@@ -461,6 +484,7 @@ struct HostCall {
     static constexpr int64_t kChunk = int64_t(1) << 23;  // chars per pipeline chunk (16 MiB of UTF-16)
     Matcher *m;
     bool is_map;
+    CallCtx *cx = nullptr;
     cudaStream_t s_up = nullptr, s_k = nullptr, s_dn = nullptr;
     cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_dn[2] = {nullptr, nullptr};
     uint16_t *d_hay = nullptr;
@@ -474,16 +498,37 @@ struct HostCall {
     explicit HostCall(Matcher *mm) : m(mm), is_map(mm->host.is_map) {}
 
     int init() {
-        CU_TRY(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
-        CU_TRY(cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking));
-        CU_TRY(cudaStreamCreateWithFlags(&s_dn, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
-            CU_TRY(cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
-            CU_TRY(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
-            CU_TRY(cudaEventCreateWithFlags(&ev_dn[i], cudaEventDisableTiming));
+        {
+            std::lock_guard<std::mutex> lk(m->ctx_mu);
+            if (!m->ctx_free.empty()) {
+                cx = m->ctx_free.back();
+                m->ctx_free.pop_back();
+            }
         }
-        CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_total), 16, s_k));
-        CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&h_total), 16, cudaHostAllocDefault));
+        if (!cx) {
+            cx = new (std::nothrow) CallCtx();
+            if (!cx) return fail(ACGPU_ENOMEM, "out of memory");
+            CU_TRY(cudaStreamCreateWithFlags(&cx->s_up, cudaStreamNonBlocking));
+            CU_TRY(cudaStreamCreateWithFlags(&cx->s_k, cudaStreamNonBlocking));
+            CU_TRY(cudaStreamCreateWithFlags(&cx->s_dn, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; i++) {
+                CU_TRY(cudaEventCreateWithFlags(&cx->ev_up[i], cudaEventDisableTiming));
+                CU_TRY(cudaEventCreateWithFlags(&cx->ev_k[i], cudaEventDisableTiming));
+                CU_TRY(cudaEventCreateWithFlags(&cx->ev_dn[i], cudaEventDisableTiming));
+            }
+            CU_TRY(cudaMalloc(reinterpret_cast<void **>(&cx->d_total), 16));
+            CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&cx->h_total), 16, cudaHostAllocDefault));
+        }
+        s_up = cx->s_up;
+        s_k = cx->s_k;
+        s_dn = cx->s_dn;
+        for (int i = 0; i < 2; i++) {
+            ev_up[i] = cx->ev_up[i];
+            ev_k[i] = cx->ev_k[i];
+            ev_dn[i] = cx->ev_dn[i];
+        }
+        d_total = cx->d_total;
+        h_total = cx->h_total;
         return ACGPU_OK;
     }
 
@@ -627,20 +672,23 @@ struct HostCall {
             }
         }
         if (rc == ACGPU_OK && pending != cudaSuccess) rc = fail(ACGPU_ECUDA, std::string("match: ") + cudaGetErrorString(pending));
-        if (d_hay) cudaFreeAsync(d_hay, s_k);
-        for (int i = 0; i < 2; i++) {
-            if (d_pos[i]) cudaFreeAsync(d_pos[i], s_k);
-            if (d_val[i]) cudaFreeAsync(d_val[i], s_k);
-            if (ev_up[i]) cudaEventDestroy(ev_up[i]);
-            if (ev_k[i]) cudaEventDestroy(ev_k[i]);
-            if (ev_dn[i]) cudaEventDestroy(ev_dn[i]);
+        if (s_k) {
+            if (d_hay) cudaFreeAsync(d_hay, s_k);
+            for (int i = 0; i < 2; i++) {
+                if (d_pos[i]) cudaFreeAsync(d_pos[i], s_k);
+                if (d_val[i]) cudaFreeAsync(d_val[i], s_k);
+            }
         }
-        if (d_total) cudaFreeAsync(d_total, s_k);
-        if (s_k) cudaStreamSynchronize(s_k);
-        if (h_total) cudaFreeHost(h_total);
-        if (s_up) cudaStreamDestroy(s_up);
-        if (s_k) cudaStreamDestroy(s_k);
-        if (s_dn) cudaStreamDestroy(s_dn);
+        if (cx) {
+            if (pending == cudaSuccess && cx->h_total) {
+                std::lock_guard<std::mutex> lk(m->ctx_mu);
+                m->ctx_free.push_back(cx);
+            } else {
+                cx->destroy();
+                delete cx;
+            }
+            cx = nullptr;
+        }
         if (rc == ACGPU_OK && count > 0) {
             out->n = count;
             out->pos = h_pos();
@@ -727,6 +775,11 @@ int acgpu_destroy(uint64_t handle) {
     Matcher *m = as_matcher(handle);
     if (!m) return fail(ACGPU_EINVAL, "bad handle");
     cudaSetDevice(m->device);
+    for (CallCtx *cx : m->ctx_free) {
+        cx->destroy();
+        delete cx;
+    }
+    m->ctx_free.clear();
     if (m->d_blob) cudaFree(m->d_blob);
     if (m->d_tier_blob) cudaFree(m->d_tier_blob);
     m->magic = 0;

@@ -17,9 +17,11 @@
 // a dedicated RESOLVER warp through shared memory + named barriers (bar.arrive / bar.sync, no __syncthreads in the
 // loop), and go on to count their next row; the resolver does ONE decoupled look-back per CTA tile and hands every
 // worker its global record offset, which the worker picks up one iteration later (software pipeline), stages its
-// records in a per-warp shared-memory window and flushes them with coalesced streaming stores.  Tiles are assigned
-// statically to the persistent, fully resident (cooperatively launched) grid, so a look-back only ever waits for
-// tiles that are running or finished.
+// records in a per-warp shared-memory window and flushes them with coalesced streaming stores.  Tiles are handed out
+// by a global ticket counter (SMs differ in speed; a static split leaves the fast ones waiting at the look-back):
+// warp 0 draws the CTA's tickets two iterations ahead and publishes them in shared memory.  The grid is persistent
+// and fully resident (cooperative launch) and tickets ascend, so a look-back only ever waits for tiles that are
+// running or finished.
 #pragma once
 #include "device_tables.cuh"
 
@@ -50,19 +52,51 @@ constexpr int kTierThreads = (kTierWorkers + 1) * 32;    // + the resolver warp
 constexpr int kTierPer = 8;                              // consecutive positions per lane
 constexpr int kTierRow = 30 * kTierPer;                  // 240 emitting positions per warp row
 constexpr int kTierTile = kTierWorkers * kTierRow;       // positions per CTA tile = one look-back tile
-constexpr int kTierCtrlWords = 256;                      // control block: counts + per-warp bases, double buffered
+constexpr int kTierCtrlWords = 416;                      // control block: row counts + per-warp bases (4 phases), 8 tile tickets, 4 mbarriers
 
-__host__ __device__ constexpr int tier_stage_records(bool is_map) { return is_map ? 256 : 384; }
-__host__ __device__ constexpr size_t tier_stage_bytes(bool is_map) {
-    return (size_t)kTierWorkers * tier_stage_records(is_map) * (is_map ? 12 : 8);
+// Emission runs tier_depth() iterations behind counting: a row's hit masks wait in a per-warp shared-memory ring
+// until the resolver has produced the row's global record offset.
+__host__ __device__ constexpr int tier_stage_records(bool is_map) { return is_map ? 160 : 256; }
+__host__ __device__ constexpr int tier_depth(bool is_map) { return is_map ? 2 : 3; }
+// ring slot: 32 x uint4 hit masks (8 positions x 16 depth bits), 32 x u16 inclusive record offsets, Maps: 32 x (hi, lo),
+// the tile index (16 bytes reserved)
+__host__ __device__ constexpr size_t tier_slot_bytes(bool is_map) { return 512 + 64 + (is_map ? 256 : 0) + 16; }
+__host__ __device__ constexpr size_t tier_warp_bytes(bool is_map) {
+    return tier_depth(is_map) * tier_slot_bytes(is_map) + (size_t)tier_stage_records(is_map) * (is_map ? 12 : 8);
 }
 // dynamic shared memory of k_ac_tier for a table of n_words words
 __host__ __device__ constexpr size_t tier_smem_bytes(size_t n_words, bool is_map) {
-    return (64 + ((n_words + 3) & ~size_t(3)) + kTierCtrlWords) * sizeof(uint32_t) + tier_stage_bytes(is_map);
+    return (64 + ((n_words + 3) & ~size_t(3)) + kTierCtrlWords) * sizeof(uint32_t) + kTierWorkers * tier_warp_bytes(is_map);
 }
 
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// mbarrier (one signaller, many waiters: unlike bar.sync the waiters do not wait for each other)
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE;\n bra LAB_WAIT;\n DONE:\n}"
+        ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Loads that must be ISSUED where they are written (their consumers sit behind barriers and other work): volatile asm
+// keeps the compiler from sinking them to the first use.
+__device__ __forceinline__ uint32_t ldg_u32_early(const uint32_t *p) {
+    uint32_t x;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(x) : "l"(p));
+    return x;
+}
+__device__ __forceinline__ uint4 ldcs_v4_if(const void *p, bool on) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %5, 0;\n @p ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];\n}"
+                 : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "l"(p), "r"((uint32_t)on));
+    return v;
+}
 
 __device__ __forceinline__ unsigned long long deep_hash64_d(unsigned long long key, unsigned long long seed) {
     unsigned long long h = key ^ seed;
@@ -115,11 +149,11 @@ __device__ __forceinline__ uint32_t deep_bits(const DevTier &T, unsigned long lo
     return bits;
 }
 
-// classes of the 8 chars at [p0, p0+8); positions outside [0, n) give class 0
-__device__ __forceinline__ void load_classes8(const DevAutomaton &A, const uint16_t *hay, int64_t n, int64_t p0,
-                                              const uint8_t *s_cls8, uint32_t (&c)[kTierPer]) {
-    if (p0 >= 0 && p0 + 8 <= n) {  // rows are laid out so that hay + p0 is 16-byte aligned
-        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(hay + p0));  // streaming: read once
+// classes of the 8 chars at [p0, p0+8) given the prefetched vector v (valid when the 8 chars lie inside [0, n));
+// positions outside [0, n) give class 0
+__device__ __forceinline__ void classify8(const DevAutomaton &A, const uint16_t *hay, int64_t n, int64_t p0, const uint4 v,
+                                          const uint8_t *s_cls8, uint32_t (&c)[kTierPer]) {
+    if (p0 >= 0 && p0 + 8 <= n) {
         if (((v.x | v.y | v.z | v.w) & 0xFF00FF00u) == 0u) {
             c[0] = s_cls8[v.x & 0xFFu]; c[1] = s_cls8[v.x >> 16];
             c[2] = s_cls8[v.y & 0xFFu]; c[3] = s_cls8[v.y >> 16];
@@ -172,6 +206,8 @@ __device__ __forceinline__ uint32_t tier_value(const DevTier &T, unsigned long l
 template <int K, int LOW, bool kIsMap>
 __global__ void __launch_bounds__(kTierThreads, 1) k_ac_tier(const DevAutomaton A, const DevTier T, const AcArgs P) {
     constexpr int kStage = tier_stage_records(kIsMap);
+    constexpr int kDepth = tier_depth(kIsMap);
+    constexpr int kSlot = (int)tier_slot_bytes(kIsMap);
     extern __shared__ __align__(16) uint32_t s_mem[];
     const uint8_t *s_cls8 = reinterpret_cast<const uint8_t *>(s_mem);
     const uint32_t *s_tab = s_mem + 64;
@@ -179,25 +215,42 @@ __global__ void __launch_bounds__(kTierThreads, 1) k_ac_tier(const DevAutomaton 
     const int b = T.b;
     const uint32_t cm = (1u << b) - 1u;
     uint32_t *s_ctrl = s_mem + 64 + ((T.n_words + 3u) & ~3u);
-    uint32_t *s_cnt = s_ctrl;                                                             // [2][32]
-    unsigned long long *s_wbase = reinterpret_cast<unsigned long long *>(s_ctrl + 64);   // [2][32]
-    int2 *s_stage_all = reinterpret_cast<int2 *>(s_ctrl + kTierCtrlWords);
-    int2 *s_stage = s_stage_all + warp * kStage;
-    uint32_t *s_stage_val = reinterpret_cast<uint32_t *>(s_stage_all + kTierWorkers * kStage) + warp * kStage;
+    uint32_t *s_cnt = s_ctrl;                                                              // [4][32]
+    unsigned long long *s_wbase = reinterpret_cast<unsigned long long *>(s_ctrl + 128);   // [4][32]
+    // tile tickets: slot (it & 7) = (it + 1) << 32 | tile of iteration it (tile >= n_tiles: the corpus is exhausted)
+    volatile unsigned long long *s_ticket = reinterpret_cast<volatile unsigned long long *>(s_ctrl + 384);
+    // mbarrier ph: "the record offsets of iteration it (it & 3 == ph) are in s_wbase[ph]"; phase parity (it >> 2) & 1
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_ctrl + 400);
+    const int64_t n_tiles = P.n_tiles;
 
     for (uint32_t i = tid; i < 64; i += kTierThreads) s_mem[i] = __ldg(&T.cls8[i]);
     for (uint32_t i = tid; i < T.n_words; i += kTierThreads) s_mem[64 + i] = __ldg(&T.smem_words[i]);
+    if (tid < 8) {
+        unsigned long long w = 0;
+        if (tid < 2) w = ((unsigned long long)(tid + 1) << 32) | (unsigned long long)atomicAdd(P.tile_counter, 1u);
+        s_ticket[tid] = w;
+    }
+    if (tid >= 32 && tid < 36) mbar_init(s_bar + (tid - 32), 1);
     __syncthreads();
-
-    const int64_t n_tiles = P.n_tiles;
-    const int n_iter = (int)((n_tiles - (int64_t)blockIdx.x + (int64_t)gridDim.x - 1) / (int64_t)gridDim.x);
+    auto wait_ticket = [&](int it) -> uint32_t {
+        unsigned long long w;
+        do {
+            w = s_ticket[it & 7];
+        } while ((uint32_t)(w >> 32) != (uint32_t)(it + 1));
+        return (uint32_t)w;
+    };
 
     // ================================================================= resolver warp
+    // named barriers 1..4: "row counts of iteration it are in s_cnt[it & 3]" (workers bar.arrive, the resolver
+    // bar.sync's); mbarriers 0..3: "offsets of iteration it are in s_wbase[it & 3]" (the resolver arrives, every worker
+    // waits on its own).  Four phases: a worker is at most kDepth + 1 <= 4 iterations ahead of the resolver.
     if (warp == kTierWorkers) {
-        for (int it = 0; it < n_iter; ++it) {
-            const int buf = it & 1;
-            named_sync(1 + buf, kTierThreads);  // the 24 row counts of this tile are in s_cnt[buf]
-            const uint32_t c = lane < kTierWorkers ? s_cnt[buf * 32 + lane] : 0u;
+        for (int it = 0;; ++it) {
+            const int64_t tile = wait_ticket(it);
+            if (tile >= n_tiles) break;
+            const int ph = it & 3;
+            named_sync(1 + ph, kTierThreads);
+            const uint32_t c = lane < kTierWorkers ? s_cnt[ph * 32 + lane] : 0u;
             uint32_t inc = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -205,39 +258,55 @@ __global__ void __launch_bounds__(kTierThreads, 1) k_ac_tier(const DevAutomaton 
                 if (lane >= o) inc += y;
             }
             const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-            const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
             if (lane == 0) lookback_publish(P.status, tile, total);
             const unsigned long long excl = lookback_resolve(P.status, tile, total);
-            if (lane < kTierWorkers) s_wbase[buf * 32 + lane] = excl + inc - c;
+            if (lane < kTierWorkers) s_wbase[ph * 32 + lane] = excl + inc - c;
             if (lane == 0 && tile == n_tiles - 1) *P.total_out = excl + total;
             __threadfence_block();
-            named_arrive(3 + buf, kTierThreads);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_bar + ph);
         }
         return;
     }
 
     // ================================================================= worker warps
+    unsigned char *s_warp = reinterpret_cast<unsigned char *>(s_ctrl + kTierCtrlWords) + (size_t)warp * tier_warp_bytes(kIsMap);
+    int2 *s_stage = reinterpret_cast<int2 *>(s_warp + kDepth * kSlot);
+    uint32_t *s_stage_val = reinterpret_cast<uint32_t *>(s_stage + kStage);
     const uint32_t C = (uint32_t)T.C;
     const uint32_t sh = 1u << b;
     const bool deeper = T.kidmask != nullptr;  // some keyword is longer than K
-    // row state carried to the next iteration (emission is one iteration behind counting)
-    uint32_t p_masks[kTierPer], p_cnt = 0, p_inc = 0, p_total = 0, p_hi = 0, p_lo = 0;
-    int32_t p_e0 = 0;
-#pragma unroll
-    for (int j = 0; j < kTierPer; j++) p_masks[j] = 0;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    auto row_p0 = [&](uint32_t tile) -> int64_t {  // first char of this lane in this warp's row of the tile
+        const int64_t row = (int64_t)tile * kTierWorkers + warp;
+        return P.origin + row * kTierRow - 16 + (int64_t)lane * kTierPer;
+    };
+    auto fetch = [&](uint32_t tile) -> uint4 {  // rows are laid out so that hay + p0 is 16-byte aligned
+        const int64_t p0 = row_p0(tile);
+        return ldcs_v4_if(P.hay + p0, (int64_t)tile < n_tiles && p0 >= 0 && p0 + 8 <= P.n);
+    };
 
-    for (int it = 0; it <= n_iter; ++it) {
-        uint32_t masks[kTierPer], my_cnt = 0, inc = 0, row_total = 0, hi = 0, lo = 0;
-        int32_t e0 = 0;
+    uint32_t tile_cur = wait_ticket(0);
+    uint4 v = fetch(tile_cur);
+    int slot_w = 0, slot_r = 0;  // ring slots written by counting / read by emission
+    int end_it = 0x7FFFFFFF;     // first iteration without a tile
+    for (int it = 0; it - kDepth < end_it; ++it) {
+        const bool counting = (int64_t)tile_cur < n_tiles;
+        if (!counting && end_it == 0x7FFFFFFF) end_it = it;
+        uint32_t tile_next = 0xFFFFFFFFu;
+        uint32_t c[kTierPer], masks[kTierPer], ki[kTierPer];
+        uint32_t hi = 0, lo = 0, lo1 = 0, hi1 = 0;
 #pragma unroll
-        for (int j = 0; j < kTierPer; j++) masks[j] = 0;
+        for (int j = 0; j < kTierPer; j++) c[j] = masks[j] = ki[j] = 0;
 
-        if (it < n_iter) {
-            const int64_t row = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kTierWorkers + warp;
-            const int64_t q_lo = P.origin + row * kTierRow;
+        if (counting) {
+            // warp 0 draws the ticket of iteration it + 2 (published further down, once the atomic has returned)
+            unsigned int drawn = 0;
+            if (warp == 0 && lane == 0) drawn = atomicAdd(P.tile_counter, 1u);
+            tile_next = wait_ticket(it + 1);
+            const int64_t p0 = row_p0(tile_cur);
+            const int64_t q_lo = p0 + 16 - (int64_t)lane * kTierPer;
             const int64_t q_hi = min(P.emit_to, q_lo + (int64_t)kTierRow);
-            const int64_t p0 = q_lo - 16 + (int64_t)lane * kTierPer;
-            e0 = (int32_t)(p0 + 1) + P.pos_base;
             // bit j set: position p0 + j reports matches
             uint32_t vm = 0;
             if (lane >= 2) {
@@ -246,12 +315,12 @@ __global__ void __launch_bounds__(kTierThreads, 1) k_ac_tier(const DevAutomaton 
                 const uint32_t z = hi_j >= 8 ? 0xFFu : (hi_j <= 0 ? 0u : (0xFFu >> (8 - (int)hi_j)));
                 vm = a & z;
             }
-            uint32_t c[kTierPer];
-            load_classes8(A, P.hay, P.n, p0, s_cls8, c);
+            classify8(A, P.hay, P.n, p0, v, s_cls8, c);
+            v = fetch(tile_next);  // next row's chars, in flight while this row is processed
             hi = ((c[0] * sh + c[1]) * sh + c[2]) * sh + c[3];
             lo = ((c[4] * sh + c[5]) * sh + c[6]) * sh + c[7];
-            const uint32_t lo1 = __shfl_up_sync(0xFFFFFFFFu, lo, 1);
-            const uint32_t hi1 = __shfl_up_sync(0xFFFFFFFFu, hi, 1);
+            lo1 = __shfl_up_sync(0xFFFFFFFFu, lo, 1);
+            hi1 = __shfl_up_sync(0xFFFFFFFFu, hi, 1);
             // class i positions before this lane's first one (i = 1..8); lane 0 reads garbage and never reports
             auto prev_class = [&](int i) -> uint32_t {
                 return i <= 4 ? (lo1 >> (b * (i - 1))) & cm : (hi1 >> (b * (i - 5))) & cm;
@@ -269,7 +338,6 @@ __global__ void __launch_bounds__(kTierThreads, 1) k_ac_tier(const DevAutomaton 
                 }
                 r[K] = 0;
             }
-            uint32_t ki[kTierPer];
 #pragma unroll
             for (int j = 0; j < kTierPer; j++) {
 #pragma unroll
@@ -288,87 +356,39 @@ __global__ void __launch_bounds__(kTierThreads, 1) k_ac_tier(const DevAutomaton 
                 m |= (f & 1u) << K;
                 const bool valid = (vm >> j) & 1u;
                 masks[j] = valid ? m : 0u;
-                ki[j] = (valid && (f & 2u)) ? r[K] : 0xFFFFFFFFu;
+                // ---- phase B, issue: exact child mask of the level-K entry.  The 8 loads stay in flight across the
+                //      emission block below and are consumed after it.
+                // (entry 0 = the all-"other" context has no children: positions that need no mask read it, an L1 hit)
+                if (deeper) ki[j] = ldg_u32_early(T.kidmask + ((valid && (f & 2u)) ? r[K] : 0u));
             }
-
-            if (deeper) {
-                // ---- phase B: exact child masks of the level-K entries (all 8 loads in flight together) say which
-                //      contexts continue to level K+1
-                uint32_t pm = 0;
-#pragma unroll
-                for (int j = 0; j < kTierPer; j++) ki[j] = ki[j] != 0xFFFFFFFFu ? __ldg(&T.kidmask[ki[j]]) : 0u;
-#pragma unroll
-                for (int j = 0; j < kTierPer; j++) {
-                    const uint32_t ck = j >= K ? c[j >= K ? j - K : 0] : prev_class(K - j);
-                    pm |= ((ki[j] >> ck) & 1u) << j;
-                }
-                // ---- phase C: the continuing contexts of the whole row are compacted into a queue (ids in the warp's
-                //      staging window, free at this point) and walked 32 at a time with all lanes busy
-                uint32_t n_mine = __popc(pm), q_inc = n_mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, q_inc, o);
-                    if (lane >= o) q_inc += y;
-                }
-                const uint32_t q_total = __shfl_sync(0xFFFFFFFFu, q_inc, 31);
-                if (q_total) {
-                    uint8_t *s_q = reinterpret_cast<uint8_t *>(s_stage);                 // [256] ids = lane * 8 + j
-                    uint16_t *s_r = reinterpret_cast<uint16_t *>(s_stage) + 128;         // [256] deep bits per id
-                    reinterpret_cast<uint4 *>(s_r)[lane] = make_uint4(0u, 0u, 0u, 0u);
-                    uint32_t o = q_inc - n_mine;
-                    for (uint32_t t = pm; t; t &= t - 1u) s_q[o++] = (uint8_t)(lane * 8 + (__ffs(t) - 1));
-                    __syncwarp();
-                    for (uint32_t base = 0; base < q_total; base += 32) {
-                        const bool act = base + lane < q_total;
-                        const uint32_t id = act ? (uint32_t)s_q[base + lane] : 64u;
-                        const int owner = (int)(id >> 3), j = (int)(id & 7u);
-                        const uint32_t h0 = __shfl_sync(0xFFFFFFFFu, hi, owner), l0 = __shfl_sync(0xFFFFFFFFu, lo, owner);
-                        const uint32_t h1 = __shfl_sync(0xFFFFFFFFu, hi, owner - 1), l1 = __shfl_sync(0xFFFFFFFFu, lo, owner - 1);
-                        const uint32_t h2 = __shfl_sync(0xFFFFFFFFu, hi, owner - 2), l2 = __shfl_sync(0xFFFFFFFFu, lo, owner - 2);
-                        if (act) {
-                            const unsigned long long P0 = ((unsigned long long)h0 << (4 * b)) | l0;
-                            const unsigned long long P1 = ((unsigned long long)h1 << (4 * b)) | l1;
-                            const unsigned long long P2 = ((unsigned long long)h2 << (4 * b)) | l2;
-                            const unsigned long long ctx = ((((P2 << (8 * b)) | P1) << (b * (j + 1)))) | (P0 >> (b * (7 - j)));
-                            s_r[id] = (uint16_t)deep_bits<K>(T, ctx, cm, A.max_len);
-                        }
-                    }
-                    __syncwarp();
-                    const uint4 rr = reinterpret_cast<const uint4 *>(s_r)[lane];
-                    masks[0] |= (rr.x & 0xFFFFu) << (K + 1); masks[1] |= (rr.x >> 16) << (K + 1);
-                    masks[2] |= (rr.y & 0xFFFFu) << (K + 1); masks[3] |= (rr.y >> 16) << (K + 1);
-                    masks[4] |= (rr.z & 0xFFFFu) << (K + 1); masks[5] |= (rr.z >> 16) << (K + 1);
-                    masks[6] |= (rr.w & 0xFFFFu) << (K + 1); masks[7] |= (rr.w >> 16) << (K + 1);
-                    __syncwarp();
-                }
-            }
-            // ---- ordered offsets inside the row; hand the row total to the resolver
-#pragma unroll
-            for (int j = 0; j < kTierPer; j++) my_cnt += __popc(masks[j]);
-            inc = my_cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                if (lane >= o) inc += y;
-            }
-            row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-            if (lane == 0) s_cnt[(it & 1) * 32 + warp] = row_total;
-            __threadfence_block();
-            named_arrive(1 + (it & 1), kTierThreads);
+            if (warp == 0 && lane == 0) s_ticket[(it + 2) & 7] = ((unsigned long long)(it + 3) << 32) | drawn;
         }
 
-        // ---- finish the previous row of this warp: pick up its global offset, stage, flush
-        if (it > 0) {
-            const int pb = (it - 1) & 1;
-            named_sync(3 + pb, kTierThreads);
-            const unsigned long long base = s_wbase[pb * 32 + warp];
-            unsigned long long ctx0 = 0;
+        // ---- emission of the row counted kDepth iterations ago: pick up its global offset, stage, flush
+        if (it >= kDepth) {  // it - kDepth < end_it: that iteration had a tile
+            const int eit = it - kDepth;
+            mbar_wait(s_bar + (eit & 3), (uint32_t)(eit >> 2) & 1u);
+            const unsigned long long base = s_wbase[(eit & 3) * 32 + warp];
+            const unsigned char *slot = s_warp + slot_r * kSlot;
+            slot_r = slot_r + 1 == kDepth ? 0 : slot_r + 1;
+            const uint4 mm = reinterpret_cast<const uint4 *>(slot)[lane];
+            const uint16_t *s_inc = reinterpret_cast<const uint16_t *>(slot + 512);
+            const uint32_t p_inc = s_inc[lane], p_total = s_inc[31];
+            uint32_t p_masks[kTierPer];  // bit d = a keyword of length d ends here (stored shifted down by one)
+            p_masks[0] = (mm.x & 0xFFFFu) << 1; p_masks[1] = (mm.x >> 16) << 1;
+            p_masks[2] = (mm.y & 0xFFFFu) << 1; p_masks[3] = (mm.y >> 16) << 1;
+            p_masks[4] = (mm.z & 0xFFFFu) << 1; p_masks[5] = (mm.z >> 16) << 1;
+            p_masks[6] = (mm.w & 0xFFFFu) << 1; p_masks[7] = (mm.w >> 16) << 1;
+            const uint32_t p_cnt = __popc(mm.x) + __popc(mm.y) + __popc(mm.z) + __popc(mm.w);
+            const int32_t p_e0 = (int32_t)(row_p0(*reinterpret_cast<const uint32_t *>(slot + kSlot - 16)) + 1) + P.pos_base;
+            unsigned long long ctx0 = 0, Pk = 0;
             if (kIsMap) {
-                const uint32_t h1 = __shfl_up_sync(0xFFFFFFFFu, p_hi, 1), l1 = __shfl_up_sync(0xFFFFFFFFu, p_lo, 1);
-                const uint32_t h2 = __shfl_up_sync(0xFFFFFFFFu, p_hi, 2), l2 = __shfl_up_sync(0xFFFFFFFFu, p_lo, 2);
+                const uint2 hl = reinterpret_cast<const uint2 *>(slot + 576)[lane];
+                const uint32_t h1 = __shfl_up_sync(0xFFFFFFFFu, hl.x, 1), l1 = __shfl_up_sync(0xFFFFFFFFu, hl.y, 1);
+                const uint32_t h2 = __shfl_up_sync(0xFFFFFFFFu, hl.x, 2), l2 = __shfl_up_sync(0xFFFFFFFFu, hl.y, 2);
                 ctx0 = (((((unsigned long long)h2 << (4 * b)) | l2)) << (8 * b)) | (((unsigned long long)h1 << (4 * b)) | l1);
+                Pk = ((unsigned long long)hl.x << (4 * b)) | hl.y;
             }
-            const unsigned long long Pk = ((unsigned long long)p_hi << (4 * b)) | p_lo;
             const uint32_t my_off = p_inc - p_cnt;
             if (!kIsMap && p_total <= (uint32_t)kStage) {
                 // ---- common case: the whole row fits the staging window.  Longest first: deep levels (rare, loop),
@@ -405,9 +425,13 @@ __global__ void __launch_bounds__(kTierThreads, 1) k_ac_tier(const DevAutomaton 
                     }
                 }
                 __syncwarp();
-                for (uint32_t rr = lane; rr < p_total; rr += 32) {
-                    const unsigned long long g = base + rr;
-                    if (g < (unsigned long long)P.cap) __stcs(&P.pos_out[g], s_stage[rr]);
+                {
+                    // records of this row that fit the caller's buffer (cap = 0: count only)
+                    const unsigned long long room = base < (unsigned long long)P.cap ? (unsigned long long)P.cap - base : 0ull;
+                    const uint32_t n_out = (uint32_t)min((unsigned long long)p_total, room);
+                    int2 *gp = P.pos_out + base + lane;
+                    const int2 *sp = s_stage + lane;
+                    for (uint32_t rr = lane; rr < n_out; rr += 32, gp += 32, sp += 32) __stcs(gp, *sp);
                 }
                 __syncwarp();
             } else {
@@ -445,14 +469,84 @@ __global__ void __launch_bounds__(kTierThreads, 1) k_ac_tier(const DevAutomaton 
                 }
             }
         }
-        p_e0 = e0;
-        p_hi = hi;
-        p_lo = lo;
-        p_cnt = my_cnt;
-        p_inc = inc;
-        p_total = row_total;
+
+        if (counting) {
+            if (deeper) {
+                // ---- phase B, consume: which contexts continue to level K+1
+                auto prev_class = [&](int i) -> uint32_t {
+                    return i <= 4 ? (lo1 >> (b * (i - 1))) & cm : (hi1 >> (b * (i - 5))) & cm;
+                };
+                uint32_t pm = 0;
 #pragma unroll
-        for (int j = 0; j < kTierPer; j++) p_masks[j] = masks[j];
+                for (int j = 0; j < kTierPer; j++) {
+                    const uint32_t ck = j >= K ? c[j >= K ? j - K : 0] : prev_class(K - j);
+                    pm |= ((ki[j] >> ck) & 1u) << j;
+                }
+                // ---- phase C: the continuing contexts of the whole row are compacted into a queue (ids in the warp's
+                //      staging window, free at this point) and walked 32 at a time with all lanes busy
+                uint8_t *s_q = reinterpret_cast<uint8_t *>(s_stage);                 // [256] ids = lane * 8 + j
+                uint16_t *s_r = reinterpret_cast<uint16_t *>(s_stage) + 128;         // [256] deep bits per id
+                uint32_t q_total = 0;
+#pragma unroll
+                for (int j = 0; j < kTierPer; j++) {
+                    const bool on = (pm >> j) & 1u;
+                    const uint32_t bj = __ballot_sync(0xFFFFFFFFu, on);
+                    if (on) s_q[q_total + __popc(bj & lt_mask)] = (uint8_t)(lane * 8 + j);
+                    q_total += __popc(bj);
+                }
+                if (q_total) {
+                    reinterpret_cast<uint4 *>(s_r)[lane] = make_uint4(0u, 0u, 0u, 0u);
+                    __syncwarp();
+                    for (uint32_t qb = 0; qb < q_total; qb += 32) {
+                        const bool act = qb + lane < q_total;
+                        const uint32_t id = act ? (uint32_t)s_q[qb + lane] : 64u;
+                        const int owner = (int)(id >> 3), j = (int)(id & 7u);
+                        const uint32_t h0 = __shfl_sync(0xFFFFFFFFu, hi, owner), l0 = __shfl_sync(0xFFFFFFFFu, lo, owner);
+                        const uint32_t h1 = __shfl_sync(0xFFFFFFFFu, hi, owner - 1), l1 = __shfl_sync(0xFFFFFFFFu, lo, owner - 1);
+                        const uint32_t h2 = __shfl_sync(0xFFFFFFFFu, hi, owner - 2), l2 = __shfl_sync(0xFFFFFFFFu, lo, owner - 2);
+                        if (act) {
+                            const unsigned long long P0 = ((unsigned long long)h0 << (4 * b)) | l0;
+                            const unsigned long long P1 = ((unsigned long long)h1 << (4 * b)) | l1;
+                            const unsigned long long P2 = ((unsigned long long)h2 << (4 * b)) | l2;
+                            const unsigned long long ctx = ((((P2 << (8 * b)) | P1) << (b * (j + 1)))) | (P0 >> (b * (7 - j)));
+                            s_r[id] = (uint16_t)deep_bits<K>(T, ctx, cm, A.max_len);
+                        }
+                    }
+                    __syncwarp();
+                    const uint4 rr = reinterpret_cast<const uint4 *>(s_r)[lane];
+                    masks[0] |= (rr.x & 0xFFFFu) << (K + 1); masks[1] |= (rr.x >> 16) << (K + 1);
+                    masks[2] |= (rr.y & 0xFFFFu) << (K + 1); masks[3] |= (rr.y >> 16) << (K + 1);
+                    masks[4] |= (rr.z & 0xFFFFu) << (K + 1); masks[5] |= (rr.z >> 16) << (K + 1);
+                    masks[6] |= (rr.w & 0xFFFFu) << (K + 1); masks[7] |= (rr.w >> 16) << (K + 1);
+                }
+            }
+            // ---- ordered offsets inside the row; park the row in the ring; hand the row total to the resolver
+            uint32_t my_cnt = 0;
+#pragma unroll
+            for (int j = 0; j < kTierPer; j++) my_cnt += __popc(masks[j]);
+            uint32_t inc = my_cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc += y;
+            }
+            const uint32_t row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            unsigned char *slot = s_warp + slot_w * kSlot;
+            slot_w = slot_w + 1 == kDepth ? 0 : slot_w + 1;
+            __syncwarp();
+            reinterpret_cast<uint4 *>(slot)[lane] =
+                make_uint4((masks[0] >> 1) | (masks[1] >> 1) << 16, (masks[2] >> 1) | (masks[3] >> 1) << 16,
+                           (masks[4] >> 1) | (masks[5] >> 1) << 16, (masks[6] >> 1) | (masks[7] >> 1) << 16);
+            reinterpret_cast<uint16_t *>(slot + 512)[lane] = (uint16_t)inc;
+            if (kIsMap) reinterpret_cast<uint2 *>(slot + 576)[lane] = make_uint2(hi, lo);
+            if (lane == 0) {
+                *reinterpret_cast<uint32_t *>(slot + kSlot - 16) = tile_cur;
+                s_cnt[(it & 3) * 32 + warp] = row_total;
+            }
+            __threadfence_block();
+            named_arrive(1 + (it & 3), kTierThreads);
+        }
+        tile_cur = tile_next;
     }
 }
 

@@ -1,0 +1,115 @@
+#!/usr/bin/env python3
+"""Kernel-resident and end-to-end throughput of BASELINE.json configs[0..3] on one B200 (the headline config[4] is
+bench.py).  One JSON line per (config, matcher).  Inputs are generated on the device; timing = CUDA events on the
+launch stream, haystacks larger than L2.
+
+  python tools/bench_configs.py [--scale S] [--configs 0,1,2,3]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import ahocorasick_b200 as ac  # noqa: E402
+import workloads as W  # noqa: E402
+from ahocorasick_b200 import _lib  # noqa: E402
+
+
+def matchers_for(idx, cfg):
+    kws = cfg["keywords"]
+    vals = list(range(len(kws)))
+    if idx == 0:
+        return [("AhoCorasickSet", ac.AhoCorasickSet(kws, True))]
+    if idx == 1:
+        return [("AhoCorasickMap(ci)", ac.AhoCorasickMap(kws, vals, False))]
+    if idx == 2:
+        return [("LongestMatchMap", ac.LongestMatchMap(kws, vals, True)), ("ShortestMatchSet", ac.ShortestMatchSet(kws, True))]
+    if idx == 3:
+        wc, tg = cfg["word_chars"]
+        return [("WholeWordMatchSet", ac.WholeWordMatchSet(kws, True, wc, tg)),
+                ("WholeWordMatchMap", ac.WholeWordMatchMap(kws, vals, True, wc, tg))]
+    raise ValueError(idx)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="0,1,2,3")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrinks the haystack (dictionary stays full size)")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--e2e-chars", type=int, default=100_000_000)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    lib = _lib.lib()
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    for idx in [int(x) for x in args.configs.split(",")]:
+        cfg = W.config(idx)
+        n = max(1 << 20, int(cfg["n"] * args.scale))
+        n = min(n, 2_000_000_000)
+        hay = W.make_haystack_torch(cfg["spec"], n, device=dev)
+        torch.cuda.synchronize()
+        for name, m in matchers_for(idx, cfg):
+            is_map = m._is_map
+            stream = torch.cuda.current_stream()
+            sp = C.c_void_p(stream.cuda_stream)
+            tot = C.c_int64(0)
+            _lib.check(lib.acgpu_match_device(m.handle, hay.data_ptr(), n, 0, n, None, None, 0, C.byref(tot), sp))
+            cap = max(tot.value, 1)
+            d_pos = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+            d_val = torch.empty(cap, dtype=torch.int32, device=dev) if is_map else None
+            d_tot = torch.zeros(1, dtype=torch.int64, device=dev)
+
+            def step():
+                _lib.check(lib.acgpu_match_device_async(m.handle, hay.data_ptr(), n, 0, n, d_pos.data_ptr(),
+                                                        d_val.data_ptr() if is_map else None, cap, d_tot.data_ptr(), sp))
+            for _ in range(args.warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.steps):
+                step()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.steps
+            assert int(d_tot.item()) == tot.value
+            rec = 12 if is_map else 8
+            alg = 2 * n + rec * tot.value
+            # end to end through the host-buffer call
+            ne = min(n, args.e2e_chars)
+            host = torch.empty(ne, dtype=torch.int16, pin_memory=True)
+            host.copy_(hay[:ne])
+            res = _lib.Result()
+            ts = []
+            for it in range(3):
+                t0 = time.perf_counter()
+                _lib.check(lib.acgpu_match_utf16(m.handle, host.data_ptr(), ne, C.byref(res)))
+                ts.append(time.perf_counter() - t0)
+                lib.acgpu_free_result(C.byref(res))
+            print(json.dumps({
+                "config": idx, "matcher": name, "chars": n, "keywords": len(cfg["keywords"]), "matches": tot.value,
+                "ms": ms, "haystack_GB_per_s": 2 * n / ms / 1e6, "matches_per_s": tot.value / ms * 1e3,
+                "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "frac": alg / ms / 1e6 / peak,
+                             "algorithmic_bytes": alg},
+                "e2e_GB_per_s": 2 * ne / min(ts[1:]) / 1e9, "e2e_chars": ne,
+                "launches_per_match": lib.acgpu_launches_per_match(m.handle), "info": m.info()}), flush=True)
+            del d_pos, d_val
+            m.close()
+        del hay
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()

@@ -207,7 +207,7 @@ def make_haystack_torch(spec: HaystackSpec, n: int, start: int = 0, device="cuda
     10^9-char haystack needs no large temporaries.  Returns an int16 tensor holding the uint16 code units."""
     import torch
     assert start % BLOCK == 0 and chunk % BLOCK == 0
-    assert spec.style in ("lower", "mixed")
+    assert spec.style in ("lower", "mixed", "words")
     if out is None:
         out = torch.empty(n, dtype=torch.int16, device=device)
     plant = spec.plant and spec.kw_lens.size > 0 and spec.max_len <= BLOCK - 4
@@ -216,6 +216,9 @@ def make_haystack_torch(spec: HaystackSpec, n: int, start: int = 0, device="cuda
         kw_offsets = torch.from_numpy(spec.kw_offsets.astype(np.int64)).to(device)
         kw_lens = torch.from_numpy(spec.kw_lens.astype(np.int64)).to(device)
     ex = torch.tensor([ord(c) for c in EXOTIC], dtype=torch.int64, device=device)
+    alpha_w = torch.tensor([ord(c) for c in "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789=-"],
+                           dtype=torch.int64, device=device)
+    pun = torch.tensor([ord(c) for c in PUNCT], dtype=torch.int64, device=device)
     for c0 in range(0, n, chunk):
         m = min(chunk, n - c0)
         idx = torch.arange(start + c0, start + c0 + m, dtype=torch.int64, device=device)
@@ -224,6 +227,9 @@ def make_haystack_torch(spec: HaystackSpec, n: int, start: int = 0, device="cuda
         if spec.style == "lower":
             ch = letter + ord("a")
             ch = torch.where((h & 7) == 0, torch.full_like(ch, ord(" ")), ch)
+        elif spec.style == "words":
+            ch = alpha_w[_lsr(h, 8) % alpha_w.numel()]
+            ch = torch.where((h & 7) < 2, pun[_lsr(h, 32) % pun.numel()], ch)
         else:
             upper = _lsr(h, 16) & 1
             ch = letter + ord("a") - upper * 32
@@ -241,8 +247,15 @@ def make_haystack_torch(spec: HaystackSpec, n: int, start: int = 0, device="cuda
             off = 1 + (_lsr(hb, 20) % BLOCK) % torch.clamp(room, min=1)
             pos0 = (b - (start + c0) // BLOCK) * BLOCK + off
             case_bits = _lsr(hb, 44)
+            if spec.style == "words":
+                mode = _lsr(hb, 40) % 10
+                planted = mode < 2
+                glue = mode == 1
+            else:
+                planted = torch.ones_like(ln, dtype=torch.bool)
+                glue = torch.zeros_like(planted)
             for j in range(spec.max_len):
-                msk = j < ln
+                msk = planted & (j < ln)
                 p = pos0[msk] + j
                 kc = kw_chars[kw_offsets[k[msk]] + j]
                 if spec.style == "mixed":
@@ -250,6 +263,15 @@ def make_haystack_torch(spec: HaystackSpec, n: int, start: int = 0, device="cuda
                     kc = torch.where(up, kc - 32, kc)
                 ok = p < m
                 ch[p[ok]] = kc[ok]
+            if spec.style == "words":
+                before = pos0[planted] - 1
+                after = pos0[planted] + ln[planted] + glue[planted].to(torch.int64)
+                for p in (before, after):
+                    ok = (p >= 0) & (p < m)
+                    ch[p[ok]] = ord(" ")
+                p = pos0[glue] + ln[glue]
+                ok = p < m
+                ch[p[ok]] = ord("x")
         out[c0:c0 + m] = ch.to(torch.int16)  # wraps values >= 0x8000 into the same 16 bits
         del ch
     return out
