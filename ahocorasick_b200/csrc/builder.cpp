@@ -102,6 +102,7 @@ void make_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, in
 namespace {
 
 constexpr uint64_t kTierSmemBits = 135ull * 1024 * 8;  // shared-memory budget for ALL direct-indexed level tables
+constexpr uint64_t kTierRowBytes = 176ull * 1024;      // ... and for the same levels in row layout (k_tier_mask)
 
 void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, const std::vector<uint16_t> &node_cls) {
     TierTables &t = a.tier;
@@ -117,6 +118,7 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
     while (K < a.max_len && K < 8) {
         const uint64_t lower_next = lower_bits + (K >= 1 ? (entries + 31) / 32 * 32 : 0);
         if (lower_next + entries * C * 2 + 32 > kTierSmemBits) break;
+        if (lower_next / 8 * 32 / C + entries * 8 + 64 > kTierRowBytes) break;  // lower levels: a word per C entries
         lower_bits = lower_next;
         entries *= C;
         K++;
@@ -135,6 +137,17 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
         off += static_cast<uint32_t>((bits + 31) / 32);
     }
     t.smem_words.assign(off, 0);
+    {
+        uint32_t roff = 0;
+        uint64_t rows = 1;  // C^(j-1)
+        for (int j = 1; j <= K; j++) {
+            if (j == K) roff = (roff + 1u) & ~1u;  // level-K rows are read as 8-byte pairs
+            t.row_off[j] = roff;
+            roff += static_cast<uint32_t>(rows * (j == K ? 2 : 1));
+            rows *= C;
+        }
+        t.row_words.assign(roff, 0);
+    }
     const int64_t n = a.n_nodes;
     std::vector<uint8_t> depth(n, 0);
     std::vector<uint64_t> packed(n, 0);
@@ -170,11 +183,15 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
         if (d < K) {
             if (inf & kInfoTerminal) {
                 t.smem_words[t.lvl_off[d] + (radix[id] >> 5)] |= 1u << (radix[id] & 31);
+                t.row_words[t.row_off[d] + radix[id] / C] |= 1u << ((radix[id] % C + 16 - d) & 31);
                 t.term_levels |= 1u << d;
             }
         } else if (d == K) {
             const uint32_t two = (inf & kInfoTerminal ? 1u : 0u) | (inf & kInfoHasChildren ? 2u : 0u);
             t.smem_words[t.lvl_off[K] + (radix[id] >> 4)] |= two << ((radix[id] & 15) * 2);
+            uint32_t *rw = &t.row_words[t.row_off[K] + 2 * (radix[id] / C)];
+            if (inf & kInfoTerminal) rw[0] |= 1u << ((radix[id] % C + 16 - K) & 31);
+            if (inf & kInfoHasChildren) rw[1] |= 1u << (radix[id] % C);
             if (inf & kInfoTerminal) t.term_levels |= 1u << d;
             if (!t.kidmask.empty()) t.kidmask[radix[id]] = kids[id];
         }

@@ -76,6 +76,13 @@ struct TierTables {
     uint32_t lvl_off[10] = {0};      // word offset of level j's table inside smem_words (j = 1..K)
     uint32_t pow_c[10] = {0};        // C^(j-1)
     std::vector<uint32_t> smem_words;
+    // the same levels laid out by ROW for k_tier_mask: the row of level j is the mixed-radix number of the j-1 classes
+    // BEFORE the current one, the current class selects a bit.  Level j < K: one word per row, the terminal bit of
+    // class c sits at bit (c + 16 - j) & 31, so rotating the word right by c drops it on bit 16 - j = where a keyword
+    // of length j lives in a hit mask.  Level K: two words per row, terminal bits (same rotation) and has-children bits
+    // (bit c).
+    uint32_t row_off[10] = {0};      // word offset of level j's rows inside row_words (j = 1..K)
+    std::vector<uint32_t> row_words;
     std::vector<uint32_t> kidmask;   // per level-K entry, bit c = the node has a child on class c
     std::vector<uint32_t> buckets;   // 8 words per bucket: 2 entries x {x, y, z, w}
     uint32_t n_buckets = 0;

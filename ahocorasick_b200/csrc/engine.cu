@@ -16,6 +16,8 @@
 #include "builder.hpp"
 #include "kernels.cuh"
 #include "kernel_tier.cuh"
+#include "kernel_mask.cuh"
+#include "kernel_emit.cuh"
 #include "tier_launch.hpp"
 
 using namespace acgpu;
@@ -78,6 +80,8 @@ struct Matcher {
     DevTier tier{};
     void *d_tier_blob = nullptr;
     size_t tier_smem = 0;
+    bool use_mask = false;  // generation 3: k_tier_mask + k_row_scan + k_tier_emit
+    size_t mask_smem = 0;
 };
 
 Matcher *as_matcher(uint64_t h) {
@@ -140,6 +144,7 @@ int upload_tier(Matcher *m) {
         return o;
     };
     size_t o_words = reserve(t.smem_words.size() * 4);
+    size_t o_rows = reserve(t.row_words.size() * 4);
     size_t o_cls8 = reserve(256);
     size_t o_kid = reserve(t.kidmask.size() * 4);
     size_t o_deep = reserve(t.buckets.size() * 4);
@@ -152,6 +157,7 @@ int upload_tier(Matcher *m) {
     uint8_t cls8[256];
     for (int c = 0; c < 256; c++) cls8[c] = static_cast<uint8_t>(m->host.cls[c]);
     if (!t.smem_words.empty()) CU_TRY(cudaMemcpy(b + o_words, t.smem_words.data(), t.smem_words.size() * 4, cudaMemcpyHostToDevice));
+    if (!t.row_words.empty()) CU_TRY(cudaMemcpy(b + o_rows, t.row_words.data(), t.row_words.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(b + o_cls8, cls8, 256, cudaMemcpyHostToDevice));
     if (!t.kidmask.empty()) CU_TRY(cudaMemcpy(b + o_kid, t.kidmask.data(), t.kidmask.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(b + o_deep, t.buckets.data(), t.buckets.size() * 4, cudaMemcpyHostToDevice));
@@ -168,6 +174,12 @@ int upload_tier(Matcher *m) {
     d.deep_valbase = reinterpret_cast<const uint32_t *>(b + o_dvb);
     d.deep_val = reinterpret_cast<const uint32_t *>(b + o_dval);
     d.n_words = static_cast<uint32_t>(t.smem_words.size());
+    d.row_words = reinterpret_cast<const uint32_t *>(b + o_rows);
+    d.n_row_words = static_cast<uint32_t>(t.row_words.size());
+    for (int j = 0; j < 10; j++) d.row_off[j] = t.row_off[j];
+    m->mask_smem = mask_smem_bytes(t.row_words.size());
+    const char *gen2 = getenv("ACGPU_FORCE_GEN2");
+    m->use_mask = m->mask_smem <= 227 * 1024 && !(gen2 && gen2[0] == '1');
     d.n_buckets = t.n_buckets;
     d.inv_b = (65536u + static_cast<uint32_t>(t.b) - 1u) / static_cast<uint32_t>(t.b);
     d.term_levels = t.term_levels;
@@ -230,6 +242,83 @@ struct RunOpts {
     int64_t *d_carry = nullptr;  // [2] int64 (selection families)
 };
 
+int launch_mask(Matcher *m, const MaskArgs &P, int grid, cudaStream_t st) {
+    const int low = tier_low_variant(m->tier);
+    cudaError_t e;
+    switch (m->tier.K) {
+    case 1: e = mask_launch_1(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
+    case 2: e = mask_launch_2(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
+    case 3: e = mask_launch_3(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
+    case 4: e = mask_launch_4(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
+    case 5: e = mask_launch_5(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
+    case 6: e = mask_launch_6(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
+    case 7: e = mask_launch_7(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
+    default: e = mask_launch_8(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
+    }
+    CU_TRY(e);
+    return ACGPU_OK;
+}
+
+// AhoCorasick family, narrow alphabets: hit masks -> row-count scan -> records (kernel_mask.cuh)
+int enqueue_mask(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from, int64_t emit_to, int64_t origin, int2 *d_pos,
+                 uint32_t *d_val, int64_t cap, unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
+    const int64_t n_rows = (emit_to - origin + kMaskRow - 1) / kMaskRow;
+    const int64_t n_blocks = (n_rows + kScanRows - 1) / kScanRows;
+    Scratch S;
+    const size_t o_ctr = S.reserve(256);
+    const size_t o_cnt = S.reserve(static_cast<size_t>(n_rows) * 4);
+    const size_t o_blk = S.reserve(static_cast<size_t>(n_blocks) * 8);
+    const size_t o_mask = S.reserve(static_cast<size_t>(n_rows) * kMaskRow * 2);
+    void *ws = nullptr;
+    CU_TRY(cudaMallocAsync(&ws, S.off, st));
+    char *w = static_cast<char *>(ws);
+    CU_TRY(cudaMemsetAsync(w + o_ctr, 0, 256, st));
+    MaskArgs P{};
+    P.hay = d_hay;
+    P.n = n;
+    P.emit_from = emit_from;
+    P.emit_to = emit_to;
+    P.origin = origin;
+    P.masks = reinterpret_cast<uint32_t *>(w + o_mask);
+    P.row_count = reinterpret_cast<uint32_t *>(w + o_cnt);
+    P.ticket = reinterpret_cast<unsigned int *>(w + o_ctr);
+    P.n_rows = n_rows;
+    const int64_t n_chunks = (n_rows + kMaskChunkRows - 1) / kMaskChunkRows;
+    const int grid = static_cast<int>(std::min<int64_t>((n_chunks + kMaskWarps - 1) / kMaskWarps, m->sm_count));
+    int rc = launch_mask(m, P, grid, st);
+    if (rc != ACGPU_OK) return rc;
+    ScanArgs SA{};
+    SA.row_count = P.row_count;
+    SA.block_excl = reinterpret_cast<unsigned long long *>(w + o_blk);
+    SA.done = reinterpret_cast<unsigned int *>(w + o_ctr + 64);
+    SA.total_out = d_total;
+    SA.n_rows = n_rows;
+    k_row_scan<<<static_cast<unsigned>(n_blocks), 1024, 0, st>>>(SA);
+    CU_TRY(cudaGetLastError());
+    if (cap > 0) {
+        EmitArgs E{};
+        E.hay = d_hay;
+        E.n = n;
+        E.masks = P.masks;
+        E.row_excl = P.row_count;
+        E.block_excl = SA.block_excl;
+        E.n_rows = n_rows;
+        E.origin = origin;
+        E.pos_base = opt.pos_base;
+        E.pos_out = d_pos;
+        E.val_out = d_val;
+        E.cap = cap;
+        const int egrid = static_cast<int>(std::min<int64_t>((n_rows + kEmitWarps - 1) / kEmitWarps, static_cast<int64_t>(m->sm_count) * 8));
+        if (m->dev.is_map)
+            k_tier_emit<true><<<egrid, kEmitWarps * 32, 0, st>>>(m->dev, m->tier, E);
+        else
+            k_tier_emit<false><<<egrid, kEmitWarps * 32, 0, st>>>(m->dev, m->tier, E);
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaFreeAsync(ws, st));
+    return ACGPU_OK;
+}
+
 // Enqueue every kernel of one match on `st`.  d_total receives the total number of matches.
 int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from, int64_t emit_to, int2 *d_pos,
                   uint32_t *d_val, int64_t cap, unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
@@ -251,6 +340,7 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
             CU_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
             return ACGPU_OK;
         }
+        if (m->use_tier && m->use_mask) return enqueue_mask(m, d_hay, n, emit_from, emit_to, origin, d_pos, d_val, cap, d_total, st, opt);
         size_t bytes = 256 + static_cast<size_t>(n_tiles) * 8;
         void *ws = nullptr;
         CU_TRY(cudaMallocAsync(&ws, bytes, st));
@@ -803,7 +893,7 @@ int acgpu_launches_per_match(uint64_t handle) {
     Matcher *m = as_matcher(handle);
     if (!m) return fail(ACGPU_EINVAL, "bad handle");
     switch (m->host.family) {
-    case ACGPU_AHOCORASICK: return 1;
+    case ACGPU_AHOCORASICK: return m->use_tier && m->use_mask ? 3 : 1;
     case ACGPU_WHOLEWORD: return 2;
     default: return 6;
     }

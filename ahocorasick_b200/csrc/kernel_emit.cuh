@@ -1,0 +1,197 @@
+// k_row_scan and k_tier_emit: the second and third launch of the generation-3 AhoCorasick path (see kernel_mask.cuh).
+#pragma once
+#include "kernel_mask.cuh"
+
+namespace acgpu {
+
+// Exclusive scan of the row counts: every block scans kScanRows rows in place; the last block to finish scans the
+// block totals.
+__global__ void __launch_bounds__(1024, 1) k_row_scan(const ScanArgs S) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t base = (int64_t)blockIdx.x * kScanRows + (int64_t)tid * 4;
+    uint32_t c[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) c[k] = base + k < S.n_rows ? S.row_count[base + k] : 0u;
+    const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+    uint32_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = (uint32_t)s_warp[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        s_warp[lane] = ((unsigned long long)wi << 32) | (wi - w);  // inclusive | exclusive
+    }
+    __syncthreads();
+    uint32_t ex = (uint32_t)s_warp[warp] + inc - mine;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k < S.n_rows) S.row_count[base + k] = ex;
+        ex += c[k];
+    }
+    if (tid == 0) {
+        S.block_excl[blockIdx.x] = s_warp[31] >> 32;  // block total for now
+        __threadfence();
+        s_last = atomicAdd(S.done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- block totals -> exclusive prefixes (one block; each thread takes a contiguous slice)
+    const int nb = (int)gridDim.x;
+    const int per = (nb + 1023) / 1024;
+    const int lo = min(nb, tid * per), hi = min(nb, lo + per);
+    unsigned long long sum = 0;
+    volatile unsigned long long *be = S.block_excl;
+    for (int i = lo; i < hi; i++) sum += be[i];
+    unsigned long long sinc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, sinc, o);
+        if (lane >= o) sinc += y;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = sinc;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned long long w = s_warp[lane];
+        unsigned long long wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) *S.total_out = wi;
+    }
+    __syncthreads();
+    unsigned long long run = s_warp[warp] + sinc - sum;
+    for (int i = lo; i < hi; i++) {
+        const unsigned long long t = be[i];
+        be[i] = run;
+        run += t;
+    }
+}
+
+// value index of the keyword of length d that ends the context (Maps); K is a run-time value here
+__device__ __forceinline__ uint32_t tier_value_rt(const DevTier &T, unsigned long long ctx, uint32_t cm, int d) {
+    const int K = T.K;
+    if (d <= K) {
+        uint32_t idx = 0;
+        for (int i = 1; i <= d; i++) idx += ((uint32_t)(ctx >> (T.b * (i - 1))) & cm) * T.pow_c[i];
+        return __ldg(&T.shallow_val[T.val_off[d] + idx]);
+    }
+    int hd = K + 1;  // walk the chain heads down to the one whose chain covers depth d
+    while (true) {
+        uint32_t slot;
+        const uint4 e = deep_probe(T, ctx & ((1ull << (T.b * hd)) - 1ull), slot);
+        const int L = (int)(e.w >> 8) & 15;
+        if (d <= hd + L) {
+            const uint32_t term = (e.w >> 12) & 0x1FFu;
+            return __ldg(&T.deep_val[__ldg(&T.deep_valbase[slot]) + __popc(term & ((1u << (d - hd)) - 1u))]);
+        }
+        hd += L + 1;
+    }
+}
+
+// Masks -> records.  A warp takes rows round-robin; a lane expands its 8 positions in order (ascending bit scan of the
+// four mask words: position-major, longest keyword first) into the warp's staging window, which is flushed with
+// coalesced streaming stores.  Maps re-read the row's chars to rebuild the contexts their value look-ups need.
+template <bool kIsMap>
+__global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomaton A, const DevTier T, const EmitArgs E) {
+    __shared__ __align__(16) int2 s_stage_all[kEmitWarps][kEmitStage];
+    __shared__ uint32_t s_val_all[kIsMap ? kEmitWarps : 1][kIsMap ? kEmitStage : 1];
+    __shared__ __align__(16) uint32_t s_cls[64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int2 *s_stage = s_stage_all[warp];
+    uint32_t *s_val = s_val_all[kIsMap ? warp : 0];
+    uint8_t *s_cls4 = reinterpret_cast<uint8_t *>(s_cls);
+    if (kIsMap) {
+        for (uint32_t i = tid; i < 256; i += kEmitWarps * 32) s_cls4[i] = (uint8_t)(((__ldg(&T.cls8[i >> 2]) >> ((i & 3) * 8)) & 0xFFu) * 4u);
+        __syncthreads();
+    }
+    const int b = T.b;
+    const uint32_t cm = (1u << b) - 1u, sh = 1u << b;
+    const int64_t stride = (int64_t)gridDim.x * kEmitWarps;
+    for (int64_t row = (int64_t)blockIdx.x * kEmitWarps + warp; row < E.n_rows; row += stride) {
+        const uint4 mm = __ldcs(reinterpret_cast<const uint4 *>(E.masks + ((size_t)row * 32 + lane) * 4));
+        const unsigned long long base = E.block_excl[row / kScanRows] + E.row_excl[row];
+        const uint32_t cnt = __popc(mm.x) + __popc(mm.y) + __popc(mm.z) + __popc(mm.w);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        if (total == 0) continue;
+        const uint32_t my_off = inc - cnt;
+        const int64_t p0 = E.origin + row * kMaskRow + (int64_t)lane * 8;
+        const int32_t e0 = (int32_t)(p0 + 1) + E.pos_base;  // end (exclusive) of a keyword whose last char is position p0
+        Pack8 P0{0u, 0u}, P1{0u, 0u}, P2{0u, 0u};
+        if (kIsMap) {
+            uint32_t c4[8];
+            const uint4 v = ldcs_v4_if(E.hay + p0, p0 >= 0 && p0 + 8 <= E.n);
+            classify8x4(A, E.hay, E.n, p0, v, s_cls4, c4);
+            P0 = pack8(c4, sh);
+            Pack8 h{0u, 0u};
+            if (lane < 2) {
+                const int64_t q0 = E.origin + row * kMaskRow - 16 + (int64_t)lane * 8;
+                const uint4 hv = ldcs_v4_if(E.hay + q0, q0 >= 0 && q0 + 8 <= E.n);
+                uint32_t h4[8];
+                classify8x4(A, E.hay, E.n, q0, hv, s_cls4, h4);
+                h = pack8(h4, sh);
+            }
+            Pack8 car0, car1;
+            car0.hi = __shfl_sync(0xFFFFFFFFu, h.hi, 0); car0.lo = __shfl_sync(0xFFFFFFFFu, h.lo, 0);
+            car1.hi = __shfl_sync(0xFFFFFFFFu, h.hi, 1); car1.lo = __shfl_sync(0xFFFFFFFFu, h.lo, 1);
+            P1.hi = __shfl_up_sync(0xFFFFFFFFu, P0.hi, 1); P1.lo = __shfl_up_sync(0xFFFFFFFFu, P0.lo, 1);
+            P2.hi = __shfl_up_sync(0xFFFFFFFFu, P0.hi, 2); P2.lo = __shfl_up_sync(0xFFFFFFFFu, P0.lo, 2);
+            if (lane == 0) { P1 = car1; P2 = car0; }
+            if (lane == 1) P2 = car1;
+        }
+        const uint32_t words[4] = {mm.x, mm.y, mm.z, mm.w};
+        for (uint32_t win = 0; win < total; win += kEmitStage) {
+            if (cnt && my_off < win + kEmitStage && my_off + cnt > win) {
+                uint32_t o = my_off - win;  // wraps below zero for records of an earlier window
+#pragma unroll
+                for (int wi = 0; wi < 4; wi++) {
+                    uint32_t w = words[wi];
+                    while (w) {
+                        const int t = __ffs(w) - 1;
+                        w &= w - 1u;
+                        const int j = 2 * wi + (t >> 4), d = 16 - (t & 15);
+                        if (o < (uint32_t)kEmitStage) {
+                            const int32_t e = e0 + j;
+                            s_stage[o] = make_int2(e - d, e);
+                            if (kIsMap) s_val[o] = tier_value_rt(T, context_of(P0, P1, P2, j, b), cm, d);
+                        }
+                        ++o;
+                    }
+                }
+            }
+            __syncwarp();
+            const uint32_t n_win = min((uint32_t)kEmitStage, total - win);
+            const unsigned long long g0 = base + win;
+            const unsigned long long room = g0 < (unsigned long long)E.cap ? (unsigned long long)E.cap - g0 : 0ull;
+            const uint32_t n_out = (uint32_t)min((unsigned long long)n_win, room);
+            for (uint32_t rr = lane; rr < n_out; rr += 32) {
+                __stcs(&E.pos_out[g0 + rr], s_stage[rr]);
+                if (kIsMap) __stcs(&E.val_out[g0 + rr], s_val[rr]);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace acgpu

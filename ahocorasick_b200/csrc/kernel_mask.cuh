@@ -1,0 +1,289 @@
+// Generation-3 AhoCorasick path for narrow alphabets: three launches per match, no ordered coupling inside a kernel.
+//
+//   k_tier_mask<K, LOW>  every haystack position q is an END anchor (all keywords ending at q, longest first —
+//                        AhoCorasickSet.java:522-535).  The kernel writes one 16-bit HIT MASK per position (bit 16 - d
+//                        set = a keyword of length d ends here) and one record count per 256-position row.
+//   k_row_scan           exclusive scan of the row counts (the reference's output order is position-major, so a row's
+//                        records start at the sum of the counts of all rows before it).
+//   k_tier_emit<isMap>   expands the masks into (start, end[, value]) records at their final offsets — the same ordered
+//                        stream the reference's listener sees (end ascending, longest first).
+//
+// k_tier_mask: a warp owns a CHUNK of 32 consecutive rows (dynamic tickets); a lane owns 8 consecutive positions of a row
+// (one streaming 128-bit load, prefetched two rows ahead) and the classes of the 16 positions before them arrive by warp
+// shuffle — from the previous row of the same warp for lanes 0 and 1, so nothing is loaded twice.  Levels 1..K come from
+// row-layout bit tables in shared memory (row = mixed-radix number of the previous classes, kept pre-scaled and
+// rolling in registers; bit = current class; one rotate drops the bit onto its place in the hit mask).  Contexts
+// that continue past level K (exact child mask, one L2-resident word) are queued with their packed context and probed
+// in full batches of 32 against the path-compressed deep table; their hits are OR-ed into the already stored masks.
+#pragma once
+#include "kernel_tier.cuh"
+
+namespace acgpu {
+
+constexpr int kMaskWarps = 24;
+constexpr int kMaskThreads = kMaskWarps * 32;
+constexpr int kMaskRow = 256;          // positions per warp row
+constexpr int kMaskChunkRows = 32;     // rows per ticket
+constexpr int kMaskQueue = 64;         // deep-probe queue entries per warp (a round adds at most 32 to at most 31)
+constexpr int kScanRows = 4096;        // rows per k_row_scan block
+constexpr int kEmitWarps = 8;
+constexpr int kEmitStage = 384;        // records staged per warp before a coalesced flush
+
+struct MaskArgs {
+    const uint16_t *hay;
+    int64_t n;
+    int64_t emit_from;      // positions (index of a keyword's last char) in [emit_from, emit_to) report
+    int64_t emit_to;
+    int64_t origin;         // first position of row 0: <= emit_from and hay + origin is 16-byte aligned
+    uint32_t *masks;        // [n_rows * 128] words, two positions per word
+    uint32_t *row_count;    // [n_rows]
+    unsigned int *ticket;
+    int64_t n_rows;
+};
+
+struct ScanArgs {
+    uint32_t *row_count;              // in: counts, out: exclusive prefix inside the row's block of kScanRows rows
+    unsigned long long *block_excl;   // [n_blocks] exclusive prefix of the block
+    unsigned int *done;               // blocks finished
+    unsigned long long *total_out;
+    int64_t n_rows;
+};
+
+struct EmitArgs {
+    const uint16_t *hay;
+    int64_t n;
+    const uint32_t *masks;
+    const uint32_t *row_excl;
+    const unsigned long long *block_excl;
+    int64_t n_rows;
+    int64_t origin;
+    int32_t pos_base;
+    int2 *pos_out;
+    uint32_t *val_out;
+    int64_t cap;
+};
+
+__host__ __device__ constexpr size_t mask_smem_bytes(size_t n_row_words) {
+    return (64 + ((n_row_words + 3) & ~size_t(3))) * sizeof(uint32_t) + (size_t)kMaskWarps * kMaskQueue * 12;
+}
+
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, uint32_t s) { return __funnelshift_r(x, x, s); }
+
+__device__ __forceinline__ uint32_t ldg_u32_if(const void *p, bool on) {
+    uint32_t x = 0;
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p ld.global.nc.u32 %0, [%1];\n}" : "+r"(x) : "l"(p), "r"((uint32_t)on));
+    return x;
+}
+
+// scaled classes (class * 4) of the 8 chars at [p0, p0 + 8); v is the prefetched vector (valid when the 8 chars lie
+// inside [0, n)); positions outside [0, n) give class 0
+__device__ __forceinline__ void classify8x4(const DevAutomaton &A, const uint16_t *hay, int64_t n, int64_t p0, const uint4 v,
+                                            const uint8_t *s_cls4, uint32_t (&c4)[8]) {
+    if (p0 >= 0 && p0 + 8 <= n) {
+        if (((v.x | v.y | v.z | v.w) & 0xFF00FF00u) == 0u) {
+            c4[0] = s_cls4[v.x & 0xFFu]; c4[1] = s_cls4[v.x >> 16];
+            c4[2] = s_cls4[v.y & 0xFFu]; c4[3] = s_cls4[v.y >> 16];
+            c4[4] = s_cls4[v.z & 0xFFu]; c4[5] = s_cls4[v.z >> 16];
+            c4[6] = s_cls4[v.w & 0xFFu]; c4[7] = s_cls4[v.w >> 16];
+        } else {
+            const uint32_t ch[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16,
+                                    v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
+#pragma unroll
+            for (int j = 0; j < 8; j++) c4[j] = ch[j] < 256u ? (uint32_t)s_cls4[ch[j]] : (uint32_t)__ldg(&A.cls[ch[j]]) * 4u;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int64_t p = p0 + j;
+            c4[j] = (p >= 0 && p < n) ? (uint32_t)__ldg(&A.cls[__ldg(&hay[p])]) * 4u : 0u;
+        }
+    }
+}
+
+// The classes of 8 consecutive positions packed b bits each, most recent lowest, as two words of 4 classes.
+struct Pack8 {
+    uint32_t hi, lo;  // hi: positions 0..3, lo: positions 4..7 (position 7 = most recent = lowest bits of lo)
+};
+__device__ __forceinline__ Pack8 pack8(const uint32_t (&c4)[8], uint32_t sh) {
+    Pack8 p;
+    p.hi = (((c4[0] >> 2) * sh + (c4[1] >> 2)) * sh + (c4[2] >> 2)) * sh + (c4[3] >> 2);
+    p.lo = (((c4[4] >> 2) * sh + (c4[5] >> 2)) * sh + (c4[6] >> 2)) * sh + (c4[7] >> 2);
+    return p;
+}
+__device__ __forceinline__ unsigned long long pack64(const Pack8 &p, int b) { return ((unsigned long long)p.hi << (4 * b)) | p.lo; }
+
+// Context (the last classes, most recent lowest) of the lane's position j given the lane's own 8 classes P0 and the 16
+// before them (P1 most recent).  Only the low b * max_len bits matter to the callers.
+__device__ __forceinline__ unsigned long long context_of(const Pack8 &P0, const Pack8 &P1, const Pack8 &P2, int j, int b) {
+    const unsigned long long q = (pack64(P2, b) << (8 * b)) | pack64(P1, b);
+    return (q << (b * (j + 1))) | (pack64(P0, b) >> (b * (7 - j)));
+}
+
+template <int K, int LOW>
+__global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomaton A, const DevTier T, const MaskArgs P) {
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    uint8_t *s_cls4 = reinterpret_cast<uint8_t *>(s_mem);
+    const unsigned char *s_tab = reinterpret_cast<const unsigned char *>(s_mem + 64);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = T.b;
+    const uint32_t cm = (1u << b) - 1u, sh = 1u << b, C = (uint32_t)T.C;
+    unsigned char *s_q = reinterpret_cast<unsigned char *>(s_mem + 64 + ((T.n_row_words + 3u) & ~3u)) + (size_t)warp * kMaskQueue * 12;
+    unsigned long long *s_qctx = reinterpret_cast<unsigned long long *>(s_q);
+    uint32_t *s_qpos = reinterpret_cast<uint32_t *>(s_q + kMaskQueue * 8);
+
+    for (uint32_t i = tid; i < 256; i += kMaskThreads) s_cls4[i] = (uint8_t)(((__ldg(&T.cls8[i >> 2]) >> ((i & 3) * 8)) & 0xFFu) * 4u);
+    for (uint32_t i = tid; i < T.n_row_words; i += kMaskThreads) s_mem[64 + i] = __ldg(&T.row_words[i]);
+    __syncthreads();
+
+    const bool deeper = T.kidmask != nullptr;  // some keyword is longer than K
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t roff[K + 1];
+#pragma unroll
+    for (int i = 1; i <= K; i++) roff[i] = T.row_off[i] * 4u;
+    const unsigned char *kid_bytes = reinterpret_cast<const unsigned char *>(T.kidmask);
+    uint32_t q_cnt = 0;
+
+    auto probe = [&](uint32_t first, uint32_t count) {  // entries [first, first + count) of the queue, count <= 32
+        if ((uint32_t)lane < count) {
+            const unsigned long long ctx = s_qctx[first + lane];
+            const uint32_t pos = s_qpos[first + lane];
+            const uint32_t bits = deep_bits<K>(T, ctx, cm, A.max_len);
+            if (bits) {
+                atomicOr(P.masks + (pos >> 1), (__brev(bits) >> (16 + K)) << ((pos & 1u) * 16u));
+                atomicAdd(P.row_count + (pos >> 8), (uint32_t)__popc(bits));
+            }
+        }
+    };
+    auto fetch = [&](int64_t row, int64_t row_end) -> uint4 {
+        const int64_t p0 = P.origin + row * kMaskRow + (int64_t)lane * 8;
+        return ldcs_v4_if(P.hay + p0, row < row_end && p0 >= 0 && p0 + 8 <= P.n);
+    };
+
+    while (true) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(P.ticket, 1u);
+        chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
+        const int64_t row0 = (int64_t)chunk * kMaskChunkRows;
+        if (row0 >= P.n_rows) break;
+        const int64_t row_end = min(row0 + (int64_t)kMaskChunkRows, P.n_rows);
+        uint4 v = fetch(row0, row_end), vn = fetch(row0 + 1, row_end);
+        // left context of the chunk: lanes 0, 1 classify the 16 chars before it
+        Pack8 car0, car1;  // the 8 classes ending 8 positions before the row / right before the row
+        {
+            Pack8 h{0u, 0u};
+            if (lane < 2) {
+                const int64_t p0 = P.origin + row0 * kMaskRow - 16 + (int64_t)lane * 8;
+                const uint4 hv = ldcs_v4_if(P.hay + p0, p0 >= 0 && p0 + 8 <= P.n);
+                uint32_t h4[8];
+                classify8x4(A, P.hay, P.n, p0, hv, s_cls4, h4);
+                h = pack8(h4, sh);
+            }
+            car0.hi = __shfl_sync(0xFFFFFFFFu, h.hi, 0); car0.lo = __shfl_sync(0xFFFFFFFFu, h.lo, 0);
+            car1.hi = __shfl_sync(0xFFFFFFFFu, h.hi, 1); car1.lo = __shfl_sync(0xFFFFFFFFu, h.lo, 1);
+        }
+        for (int64_t row = row0; row < row_end; ++row) {
+            const uint4 vnn = fetch(row + 2, row_end);
+            const int64_t r_lo = P.origin + row * kMaskRow;  // first position of the row
+            const int64_t p0 = r_lo + (int64_t)lane * 8;
+            uint32_t c4[8];
+            classify8x4(A, P.hay, P.n, p0, v, s_cls4, c4);
+            v = vn;
+            vn = vnn;
+            const Pack8 P0 = pack8(c4, sh);
+            Pack8 P1, P2;
+            P1.hi = __shfl_up_sync(0xFFFFFFFFu, P0.hi, 1); P1.lo = __shfl_up_sync(0xFFFFFFFFu, P0.lo, 1);
+            P2.hi = __shfl_up_sync(0xFFFFFFFFu, P0.hi, 2); P2.lo = __shfl_up_sync(0xFFFFFFFFu, P0.lo, 2);
+            if (lane == 0) { P1 = car1; P2 = car0; }
+            if (lane == 1) P2 = car1;
+            car0.hi = __shfl_sync(0xFFFFFFFFu, P0.hi, 30); car0.lo = __shfl_sync(0xFFFFFFFFu, P0.lo, 30);
+            car1.hi = __shfl_sync(0xFFFFFFFFu, P0.hi, 31); car1.lo = __shfl_sync(0xFFFFFFFFu, P0.lo, 31);
+            // class i positions before this lane's first one (i = 1..8)
+            auto prev_class = [&](int i) -> uint32_t {
+                return i <= 4 ? (P1.lo >> (b * (i - 1))) & cm : (P1.hi >> (b * (i - 5))) & cm;
+            };
+
+            // ---- levels 1..K.  rs[k] = 4 * (mixed-radix number of the k classes before the current position)
+            uint32_t rs[K + 1];
+            rs[0] = 0;
+            {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int k = 1; k < K; k++) {
+                    acc += prev_class(k) * (T.pow_c[k] * 4u);
+                    rs[k] = acc;
+                }
+            }
+            uint32_t m[8], ki[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t cj = c4[j] >> 2;
+                uint32_t mj = 0;
+#pragma unroll
+                for (int i = 1; i < K; i++) {
+                    if (LOW == 2 || (LOW == 1 && i != K - 1)) continue;
+                    if (LOW == 1 || ((T.term_levels >> i) & 1u)) {
+                        const uint32_t w = *reinterpret_cast<const uint32_t *>(s_tab + roff[i] + rs[i - 1]);
+                        mj |= rotr32(w, cj) & (1u << (16 - i));
+                    }
+                }
+                const uint2 wk = *reinterpret_cast<const uint2 *>(s_tab + roff[K] + rs[K - 1] * 2u);
+                mj |= rotr32(wk.x, cj) & (1u << (16 - K));
+                const bool kids = (wk.y >> cj) & 1u;
+                const uint32_t rk = rs[K - 1] * C + c4[j];  // byte offset of the level-K entry's child mask
+#pragma unroll
+                for (int k = K - 1; k >= 2; k--) rs[k] = rs[k - 1] * C + c4[j];
+                if (K >= 2) rs[1] = c4[j];
+                m[j] = mj;
+                ki[j] = deeper ? ldg_u32_if(kid_bytes + rk, kids) : 0u;
+            }
+            // ---- positions outside [emit_from, emit_to) report nothing (edge rows only)
+            uint32_t vm = 0xFFu;
+            if (r_lo < P.emit_from || r_lo + kMaskRow > P.emit_to) {
+                const int64_t lo_j = P.emit_from - p0, hi_j = P.emit_to - p0;
+                const uint32_t a = lo_j <= 0 ? 0xFFu : (lo_j >= 8 ? 0u : (0xFFu << (int)lo_j) & 0xFFu);
+                const uint32_t z = hi_j >= 8 ? 0xFFu : (hi_j <= 0 ? 0u : (0xFFu >> (8 - (int)hi_j)));
+                vm = a & z;
+#pragma unroll
+                for (int j = 0; j < 8; j++) m[j] = (vm >> j) & 1u ? m[j] : 0u;
+            }
+            // ---- which contexts continue to level K + 1
+            uint32_t pm = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t ck = j >= K ? c4[j >= K ? j - K : 0] >> 2 : prev_class(K - j);
+                pm |= ((ki[j] >> ck) & 1u) << j;
+            }
+            pm &= vm;
+            // ---- store the shallow masks and the row count; deep hits are OR-ed in later by this same warp
+            const uint4 mw = make_uint4(m[0] | m[1] << 16, m[2] | m[3] << 16, m[4] | m[5] << 16, m[6] | m[7] << 16);
+            *reinterpret_cast<uint4 *>(P.masks + ((size_t)row * 32 + lane) * 4) = mw;
+            const uint32_t cnt = __popc(mw.x) + __popc(mw.y) + __popc(mw.z) + __popc(mw.w);
+            const uint32_t row_total = __reduce_add_sync(0xFFFFFFFFu, cnt);
+            if (lane == 0) P.row_count[row] = row_total;
+            __syncwarp();
+            // ---- queue the continuing contexts; probe whenever 32 are waiting
+            while (true) {
+                const bool has = pm != 0u;
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, has);
+                if (!bal) break;
+                if (has) {
+                    const int j = __ffs(pm) - 1;
+                    pm &= pm - 1u;
+                    const uint32_t slot = q_cnt + __popc(bal & lt_mask);
+                    s_qctx[slot] = context_of(P0, P1, P2, j, b);
+                    s_qpos[slot] = (uint32_t)(row * kMaskRow) + lane * 8 + j;
+                }
+                q_cnt += __popc(bal);
+                __syncwarp();
+                if (q_cnt >= 32u) {
+                    q_cnt -= 32u;
+                    probe(q_cnt, 32u);
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    if (q_cnt) probe(0u, q_cnt);
+}
+
+}  // namespace acgpu

@@ -29,6 +29,7 @@ namespace acgpu {
 
 struct DevTier {
     const uint32_t *smem_words;  // direct-indexed level tables (copied to shared memory by every CTA)
+    const uint32_t *row_words;   // the same levels in row layout (k_tier_mask), see TierTables in builder.hpp
     const uint32_t *cls8;        // 64 words: class of code units 0..255, one byte each
     const uint32_t *kidmask;     // [C^K] exact child masks of the level-K entries (nullptr: no deeper levels)
     const uint4 *buckets;        // deep table: 2 entries per 32-byte bucket, see TierTables in builder.hpp
@@ -37,6 +38,8 @@ struct DevTier {
     const uint32_t *deep_val;
     unsigned long long hash_seed;
     uint32_t n_words;
+    uint32_t n_row_words;
+    uint32_t row_off[10];
     uint32_t n_buckets;
     uint32_t inv_b;              // ceil(65536 / b): (t * inv_b) >> 16 == t / b for t < 64
     uint32_t term_levels;

@@ -1,5 +1,6 @@
 // One translation unit per K: nvcc ... -DTIER_K=k tier_inst.cu
 #include "kernel_tier.cuh"
+#include "kernel_mask.cuh"
 #include "tier_launch.hpp"
 
 #ifndef TIER_K
@@ -26,6 +27,22 @@ cudaError_t launch_variant(const DevAutomaton &A, const DevTier &T, const AcArgs
     return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kTierThreads), args, smem, st);
 }
 
+template <int LOW>
+cudaError_t launch_mask_variant(const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, cudaStream_t st) {
+    static size_t attr_smem[64] = {0};
+    const void *fn = reinterpret_cast<const void *>(k_tier_mask<TIER_K, LOW>);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || attr_smem[dev] < smem) {
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_smem[dev] = smem;
+    }
+    k_tier_mask<TIER_K, LOW><<<grid, kMaskThreads, smem, st>>>(A, T, P);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 #define ACGPU_CAT2(a, b) a##b
@@ -41,6 +58,16 @@ cudaError_t ACGPU_CAT(tier_launch_, TIER_K)(int low, bool is_map, const DevAutom
     case 3: return launch_variant<1, true>(A, T, P, grid, smem, st);
     case 4: return launch_variant<2, false>(A, T, P, grid, smem, st);
     default: return launch_variant<2, true>(A, T, P, grid, smem, st);
+    }
+}
+
+cudaError_t ACGPU_CAT(mask_launch_, TIER_K)(int low, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid,
+                                            size_t smem, cudaStream_t st) {
+    if (TIER_K == 1) low = 2;
+    switch (low) {
+    case 0: return launch_mask_variant<0>(A, T, P, grid, smem, st);
+    case 1: return launch_mask_variant<1>(A, T, P, grid, smem, st);
+    default: return launch_mask_variant<2>(A, T, P, grid, smem, st);
     }
 }
 

@@ -8,6 +8,7 @@
 namespace acgpu {
 
 struct DevTier;
+struct MaskArgs;
 
 // low: 0 = every level below K may hold keywords, 1 = only level K-1 does, 2 = none does.
 // Sets the dynamic shared-memory attribute once per kernel and launches cooperatively (the kernel waits for tiles of
@@ -23,5 +24,18 @@ ACGPU_DECLARE_TIER(6)
 ACGPU_DECLARE_TIER(7)
 ACGPU_DECLARE_TIER(8)
 #undef ACGPU_DECLARE_TIER
+
+// k_tier_mask<K, LOW> (kernel_mask.cuh): persistent, one CTA per SM; no inter-CTA waiting, plain launch.
+#define ACGPU_DECLARE_MASK(k) \
+    cudaError_t mask_launch_##k(int low, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, cudaStream_t st);
+ACGPU_DECLARE_MASK(1)
+ACGPU_DECLARE_MASK(2)
+ACGPU_DECLARE_MASK(3)
+ACGPU_DECLARE_MASK(4)
+ACGPU_DECLARE_MASK(5)
+ACGPU_DECLARE_MASK(6)
+ACGPU_DECLARE_MASK(7)
+ACGPU_DECLARE_MASK(8)
+#undef ACGPU_DECLARE_MASK
 
 }  // namespace acgpu
