@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libacgpu.so")
+LIB_PATH = os.environ.get("ACGPU_LIB") or os.path.join(_HERE, "libacgpu.so")  # ACGPU_LIB: A/B experiment builds only
 
 OK, EINVAL, EILLEGALARG, ENODEVICE, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 NO_VALUE = 0xFFFFFFFF

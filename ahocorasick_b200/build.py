@@ -8,14 +8,16 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libacgpu.so")
+# experiment knobs (tools/gpu_quick.sh A/B runs): extra nvcc flags and another output file; the product build uses neither
+EXTRA = os.environ.get("ACGPU_NVCC_EXTRA", "").split()
+LIB = os.environ.get("ACGPU_LIB_OUT") or os.path.join(HERE, "libacgpu.so")
 SOURCES = ["engine.cu", "builder.cpp"]
 TIER_KS = range(1, 9)  # tier_inst.cu is compiled once per K (-DTIER_K=k), in parallel
 HEADERS = ["kernels.cuh", "kernel_tier.cuh", "kernel_mask.cuh", "kernel_emit.cuh", "tier_launch.hpp", "tier_inst.cu", "device_tables.cuh", "builder.hpp",
            "java_char_tables.h", os.path.join("..", "..", "include", "acgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall"]
-OBJ_DIR = os.path.join(HERE, "build")
+OBJ_DIR = os.path.join(HERE, "build" + ("_" + os.path.basename(LIB) if os.environ.get("ACGPU_LIB_OUT") else ""))
 
 
 def nvcc_path() -> str:
@@ -35,7 +37,7 @@ def is_stale() -> bool:
 
 def _compile(job):
     src, obj, extra, verbose = job
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    cmd = [nvcc_path()] + NVCC_FLAGS + EXTRA + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return r.returncode, r.stdout + r.stderr
 

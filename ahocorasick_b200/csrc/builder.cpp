@@ -184,6 +184,8 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
             if (inf & kInfoTerminal) {
                 t.smem_words[t.lvl_off[d] + (radix[id] >> 5)] |= 1u << (radix[id] & 31);
                 t.row_words[t.row_off[d] + radix[id] / C] |= 1u << ((radix[id] % C + 16 - d) & 31);
+                // a keyword of length K-1 is also flagged in the level-K row it names (spare bit 31 of the kids word)
+                if (d == K - 1 && C <= 31) t.row_words[t.row_off[K] + 2 * radix[id] + 1] |= 1u << 31;
                 t.term_levels |= 1u << d;
             }
         } else if (d == K) {

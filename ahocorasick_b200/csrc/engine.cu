@@ -81,6 +81,7 @@ struct Matcher {
     void *d_tier_blob = nullptr;
     size_t tier_smem = 0;
     bool use_mask = false;  // generation 3: k_tier_mask + k_row_scan + k_tier_emit
+    L2Window l2win;         // child masks + deep table, kept L2-resident across the streaming traffic
     size_t mask_smem = 0;
 };
 
@@ -140,7 +141,7 @@ int upload_tier(Matcher *m) {
     size_t off = 0;
     auto reserve = [&](size_t bytes) {
         size_t o = off;
-        off = align_up(off + std::max<size_t>(bytes, 16), 256);
+        off = align_up(off + std::max<size_t>(bytes, 16), 512);  // linear textures want 512-byte aligned bases
         return o;
     };
     size_t o_words = reserve(t.smem_words.size() * 4);
@@ -168,6 +169,20 @@ int upload_tier(Matcher *m) {
     d.smem_words = reinterpret_cast<const uint32_t *>(b + o_words);
     d.cls8 = reinterpret_cast<const uint32_t *>(b + o_cls8);
     d.kidmask = t.kidmask.empty() ? nullptr : reinterpret_cast<const uint32_t *>(b + o_kid);
+    d.kid_tex = 0;
+    if (!t.kidmask.empty()) {
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = b + o_kid;
+        rd.res.linear.desc = cudaCreateChannelDesc<unsigned int>();
+        rd.res.linear.sizeInBytes = t.kidmask.size() * 4;
+        cudaTextureDesc td{};
+        td.readMode = cudaReadModeElementType;
+        td.filterMode = cudaFilterModePoint;
+        td.addressMode[0] = cudaAddressModeClamp;
+        td.normalizedCoords = 0;
+        CU_TRY(cudaCreateTextureObject(&d.kid_tex, &rd, &td, nullptr));
+    }
     d.buckets = reinterpret_cast<const uint4 *>(b + o_deep);
     d.hash_seed = t.hash_seed;
     d.shallow_val = reinterpret_cast<const uint32_t *>(b + o_sval);
@@ -178,6 +193,24 @@ int upload_tier(Matcher *m) {
     d.n_row_words = static_cast<uint32_t>(t.row_words.size());
     for (int j = 0; j < 10; j++) d.row_off[j] = t.row_off[j];
     m->mask_smem = mask_smem_bytes(t.row_words.size());
+    {
+        // L2 residency window over [child masks | deep table] (adjacent in the blob)
+        int max_win = 0, max_persist = 0;
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, m->device);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, m->device);
+        const size_t want = (o_deep + t.buckets.size() * 4) - o_kid;
+        const char *win = getenv("ACGPU_L2_WINDOW");  // measured slower than plain L2 on B200 (profiles/): opt-in only
+        if (max_win > 0 && max_persist > 0 && !t.kidmask.empty() && (win && win[0] == '1')) {
+            const size_t persist = std::min<size_t>(static_cast<size_t>(max_persist), want);
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) == cudaSuccess) {
+                m->l2win.base = b + o_kid;
+                m->l2win.bytes = std::min<size_t>(want, static_cast<size_t>(max_win));
+                m->l2win.hit_ratio = want <= persist ? 1.0f : static_cast<float>(persist) / static_cast<float>(want);
+            } else {
+                cudaGetLastError();
+            }
+        }
+    }
     const char *gen2 = getenv("ACGPU_FORCE_GEN2");
     m->use_mask = m->mask_smem <= 227 * 1024 && !(gen2 && gen2[0] == '1');
     d.n_buckets = t.n_buckets;
@@ -201,6 +234,14 @@ int tier_low_variant(const DevTier &t) {
     const uint32_t below = t.term_levels & ((1u << t.K) - 1u) & ~1u;  // bits 1..K-1
     if (below == 0) return 2;
     if (below == (1u << (t.K - 1))) return 1;
+    return 0;
+}
+
+// k_tier_mask: variant 1 reads level K-1 from the spare bit of the level-K rows, which exists for at most 31 classes
+int mask_low_variant(const DevTier &t) {
+    const uint32_t below = t.term_levels & ((1u << t.K) - 1u);  // bits 1..K-1 (bit 0 is never set)
+    if (below == 0) return 2;
+    if (below == (1u << (t.K - 1)) && t.C <= 31) return 1;
     return 0;
 }
 
@@ -243,17 +284,30 @@ struct RunOpts {
 };
 
 int launch_mask(Matcher *m, const MaskArgs &P, int grid, cudaStream_t st) {
-    const int low = tier_low_variant(m->tier);
+    const int low = mask_low_variant(m->tier);
     cudaError_t e;
     switch (m->tier.K) {
-    case 1: e = mask_launch_1(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
-    case 2: e = mask_launch_2(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
-    case 3: e = mask_launch_3(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
-    case 4: e = mask_launch_4(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
-    case 5: e = mask_launch_5(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
-    case 6: e = mask_launch_6(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
-    case 7: e = mask_launch_7(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
-    default: e = mask_launch_8(low, m->dev, m->tier, P, grid, m->mask_smem, st); break;
+    case 1: e = mask_launch_1(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 2: e = mask_launch_2(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 3: e = mask_launch_3(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 4: e = mask_launch_4(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 5: e = mask_launch_5(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 6: e = mask_launch_6(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 7: e = mask_launch_7(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    default: e = mask_launch_8(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    }
+    CU_TRY(e);
+    if (m->tier.kidmask == nullptr) return ACGPU_OK;  // no keyword longer than K: nothing is ever queued
+    const int dgrid = m->sm_count * 8;
+    switch (m->tier.K) {
+    case 1: e = deep_launch_1(m->dev, m->tier, P, dgrid, m->l2win, st); break;
+    case 2: e = deep_launch_2(m->dev, m->tier, P, dgrid, m->l2win, st); break;
+    case 3: e = deep_launch_3(m->dev, m->tier, P, dgrid, m->l2win, st); break;
+    case 4: e = deep_launch_4(m->dev, m->tier, P, dgrid, m->l2win, st); break;
+    case 5: e = deep_launch_5(m->dev, m->tier, P, dgrid, m->l2win, st); break;
+    case 6: e = deep_launch_6(m->dev, m->tier, P, dgrid, m->l2win, st); break;
+    case 7: e = deep_launch_7(m->dev, m->tier, P, dgrid, m->l2win, st); break;
+    default: e = deep_launch_8(m->dev, m->tier, P, dgrid, m->l2win, st); break;
     }
     CU_TRY(e);
     return ACGPU_OK;
@@ -269,6 +323,11 @@ int enqueue_mask(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from
     const size_t o_cnt = S.reserve(static_cast<size_t>(n_rows) * 4);
     const size_t o_blk = S.reserve(static_cast<size_t>(n_blocks) * 8);
     const size_t o_mask = S.reserve(static_cast<size_t>(n_rows) * kMaskRow * 2);
+    // candidate list for k_tier_deep: one position in eight continues past level K on ordinary text; denser input
+    // overflows into in-place probing
+    const uint32_t cand_cap = static_cast<uint32_t>(std::min<int64_t>(n_rows * (kMaskRow / 8) + 4096, 0x7FFFFFFF));
+    const size_t o_cctx = S.reserve(static_cast<size_t>(cand_cap) * 8);
+    const size_t o_cpos = S.reserve(static_cast<size_t>(cand_cap) * 4);
     void *ws = nullptr;
     CU_TRY(cudaMallocAsync(&ws, S.off, st));
     char *w = static_cast<char *>(ws);
@@ -283,6 +342,10 @@ int enqueue_mask(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from
     P.row_count = reinterpret_cast<uint32_t *>(w + o_cnt);
     P.ticket = reinterpret_cast<unsigned int *>(w + o_ctr);
     P.n_rows = n_rows;
+    P.cand_ctx = reinterpret_cast<unsigned long long *>(w + o_cctx);
+    P.cand_pos = reinterpret_cast<uint32_t *>(w + o_cpos);
+    P.cand_count = reinterpret_cast<unsigned int *>(w + o_ctr + 128);
+    P.cand_cap = cand_cap;
     const int64_t n_chunks = (n_rows + kMaskChunkRows - 1) / kMaskChunkRows;
     const int grid = static_cast<int>(std::min<int64_t>((n_chunks + kMaskWarps - 1) / kMaskWarps, m->sm_count));
     int rc = launch_mask(m, P, grid, st);
@@ -852,6 +915,7 @@ int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t 
         if (rc == ACGPU_OK) rc = upload_tier(m);
     }
     if (rc != ACGPU_OK) {
+        if (m->tier.kid_tex) cudaDestroyTextureObject(m->tier.kid_tex);
         if (m->d_tier_blob) cudaFree(m->d_tier_blob);
         if (m->d_blob) cudaFree(m->d_blob);
         delete m;
@@ -871,6 +935,7 @@ int acgpu_destroy(uint64_t handle) {
     }
     m->ctx_free.clear();
     if (m->d_blob) cudaFree(m->d_blob);
+    if (m->tier.kid_tex) cudaDestroyTextureObject(m->tier.kid_tex);
     if (m->d_tier_blob) cudaFree(m->d_tier_blob);
     m->magic = 0;
     delete m;
@@ -893,7 +958,7 @@ int acgpu_launches_per_match(uint64_t handle) {
     Matcher *m = as_matcher(handle);
     if (!m) return fail(ACGPU_EINVAL, "bad handle");
     switch (m->host.family) {
-    case ACGPU_AHOCORASICK: return m->use_tier && m->use_mask ? 3 : 1;
+    case ACGPU_AHOCORASICK: return m->use_tier && m->use_mask ? (m->tier.kidmask ? 4 : 3) : 1;
     case ACGPU_WHOLEWORD: return 2;
     default: return 6;
     }

@@ -104,12 +104,17 @@ __device__ __forceinline__ uint32_t tier_value_rt(const DevTier &T, unsigned lon
     }
 }
 
-// Masks -> records.  A warp takes rows round-robin; a lane expands its 8 positions in order (ascending bit scan of the
-// four mask words: position-major, longest keyword first) into the warp's staging window, which is flushed with
-// coalesced streaming stores.  Maps re-read the row's chars to rebuild the contexts their value look-ups need.
+// Masks -> records.  A warp takes rows round-robin (the next row's masks and offsets are prefetched while the current
+// row is expanded); a lane expands its 8 positions in order (ascending bit scan of the four mask words: position-major,
+// longest keyword first) into the warp's staging window, which is flushed with coalesced 128-bit streaming stores.
+// Maps re-read the row's chars to rebuild the contexts their value look-ups need.
+__device__ __forceinline__ void sts_v2(uint32_t saddr, int32_t x, int32_t y) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(x), "r"(y) : "memory");
+}
+
 template <bool kIsMap>
 __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomaton A, const DevTier T, const EmitArgs E) {
-    __shared__ __align__(16) int2 s_stage_all[kEmitWarps][kEmitStage];
+    __shared__ __align__(16) int2 s_stage_all[kEmitWarps][kEmitStage + 2];
     __shared__ uint32_t s_val_all[kIsMap ? kEmitWarps : 1][kIsMap ? kEmitStage : 1];
     __shared__ __align__(16) uint32_t s_cls[64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -123,9 +128,24 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
     const int b = T.b;
     const uint32_t cm = (1u << b) - 1u, sh = 1u << b;
     const int64_t stride = (int64_t)gridDim.x * kEmitWarps;
-    for (int64_t row = (int64_t)blockIdx.x * kEmitWarps + warp; row < E.n_rows; row += stride) {
-        const uint4 mm = __ldcs(reinterpret_cast<const uint4 *>(E.masks + ((size_t)row * 32 + lane) * 4));
-        const unsigned long long base = E.block_excl[row / kScanRows] + E.row_excl[row];
+    const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(s_stage);
+    // parity of the output buffer in 8-byte units: record g is 16-byte aligned iff (g + out_par) is even
+    const uint32_t out_par = (uint32_t)(reinterpret_cast<uintptr_t>(E.pos_out) >> 3) & 1u;
+
+    int64_t row = (int64_t)blockIdx.x * kEmitWarps + warp;
+    uint4 mm_n = make_uint4(0u, 0u, 0u, 0u);
+    unsigned long long base_n = 0;
+    if (row < E.n_rows) {
+        mm_n = __ldcs(reinterpret_cast<const uint4 *>(E.masks + ((size_t)row * 32 + lane) * 4));
+        base_n = __ldg(E.block_excl + row / kScanRows) + __ldg(E.row_excl + row);
+    }
+    for (; row < E.n_rows; row += stride) {
+        const uint4 mm = mm_n;
+        const unsigned long long base = base_n;
+        if (row + stride < E.n_rows) {
+            mm_n = __ldcs(reinterpret_cast<const uint4 *>(E.masks + ((size_t)(row + stride) * 32 + lane) * 4));
+            base_n = __ldg(E.block_excl + (row + stride) / kScanRows) + __ldg(E.row_excl + row + stride);
+        }
         const uint32_t cnt = __popc(mm.x) + __popc(mm.y) + __popc(mm.z) + __popc(mm.w);
         uint32_t inc = cnt;
 #pragma unroll
@@ -138,6 +158,43 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
         const uint32_t my_off = inc - cnt;
         const int64_t p0 = E.origin + row * kMaskRow + (int64_t)lane * 8;
         const int32_t e0 = (int32_t)(p0 + 1) + E.pos_base;  // end (exclusive) of a keyword whose last char is position p0
+        const uint32_t words[4] = {mm.x, mm.y, mm.z, mm.w};
+
+        if (!kIsMap && total <= (uint32_t)kEmitStage && base + total <= (unsigned long long)E.cap) {
+            // ---- common case: the whole row fits the staging window and the caller's buffer.  Records are staged at
+            //      the parity of their final address so that both sides of the flush are 16-byte aligned.
+            const uint32_t par = ((uint32_t)base + out_par) & 1u;
+            uint32_t sa = stage_sa + (my_off + par) * 8u;
+#pragma unroll
+            for (int wi = 0; wi < 4; wi++) {
+                uint32_t w = words[wi];
+                const int32_t eb = e0 + 2 * wi;
+                while (w) {
+                    const uint32_t t = (uint32_t)__clz((int)__brev(w));
+                    w &= w - 1u;
+                    const int32_t e = eb + (int32_t)(t >> 4);
+                    sts_v2(sa, e - 16 + (int32_t)(t & 15u), e);
+                    sa += 8u;
+                }
+            }
+            __syncwarp();
+            int2 *g = E.pos_out + (base - par);  // 16-byte aligned
+            const uint32_t n_pair = (par + total + 1u) >> 1;
+            for (uint32_t k = lane; k < n_pair; k += 32) {
+                const int4 v = *reinterpret_cast<const int4 *>(s_stage + 2 * k);
+                const bool lo_ok = 2 * k >= par, hi_ok = 2 * k + 1 < par + total;
+                if (lo_ok && hi_ok) {
+                    __stcs(reinterpret_cast<int4 *>(g + 2 * k), v);
+                } else if (lo_ok) {
+                    __stcs(g + 2 * k, make_int2(v.x, v.y));
+                } else if (hi_ok) {
+                    __stcs(g + 2 * k + 1, make_int2(v.z, v.w));
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+
         Pack8 P0{0u, 0u}, P1{0u, 0u}, P2{0u, 0u};
         if (kIsMap) {
             uint32_t c4[8];
@@ -160,7 +217,6 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
             if (lane == 0) { P1 = car1; P2 = car0; }
             if (lane == 1) P2 = car1;
         }
-        const uint32_t words[4] = {mm.x, mm.y, mm.z, mm.w};
         for (uint32_t win = 0; win < total; win += kEmitStage) {
             if (cnt && my_off < win + kEmitStage && my_off + cnt > win) {
                 uint32_t o = my_off - win;  // wraps below zero for records of an earlier window

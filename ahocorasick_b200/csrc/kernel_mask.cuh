@@ -20,7 +20,13 @@
 
 namespace acgpu {
 
-constexpr int kMaskWarps = 24;
+#ifndef ACGPU_MASK_WARPS
+#define ACGPU_MASK_WARPS 24
+#endif
+constexpr int kMaskWarps = ACGPU_MASK_WARPS;
+#ifndef ACGPU_KID_TEX
+#define ACGPU_KID_TEX 1   // child masks are gathered through the texture pipe (the LSU data pipe is the kernel's bottleneck)
+#endif
 constexpr int kMaskThreads = kMaskWarps * 32;
 constexpr int kMaskRow = 256;          // positions per warp row
 constexpr int kMaskChunkRows = 32;     // rows per ticket
@@ -39,7 +45,13 @@ struct MaskArgs {
     uint32_t *row_count;    // [n_rows]
     unsigned int *ticket;
     int64_t n_rows;
+    // contexts that continue past level K: probed against the deep table by k_tier_deep
+    unsigned long long *cand_ctx;
+    uint32_t *cand_pos;       // position relative to origin; kCandNone = hole
+    unsigned int *cand_count; // entries reserved so far (may exceed cand_cap: batches that did not fit were probed in place)
+    uint32_t cand_cap;
 };
+constexpr uint32_t kCandNone = 0xFFFFFFFFu;
 
 struct ScanArgs {
     uint32_t *row_count;              // in: counts, out: exclusive prefix inside the row's block of kScanRows rows
@@ -119,6 +131,41 @@ __device__ __forceinline__ unsigned long long context_of(const Pack8 &P0, const 
     return (q << (b * (j + 1))) | (pack64(P0, b) >> (b * (7 - j)));
 }
 
+// One queued context: levels K+1.. against the deep table; hits are OR-ed into the stored mask of the position and
+// added to its row's count.
+template <int K>
+__device__ __noinline__ void deep_resolve(const uint4 *buckets, unsigned long long hash_seed, uint32_t n_buckets, int b,
+                                          uint32_t inv_b, unsigned long long ctx, uint32_t pos, int max_len, uint32_t *masks,
+                                          uint32_t *row_count) {
+    DevTier T;  // only the fields deep_bits reads
+    T.buckets = buckets;
+    T.hash_seed = hash_seed;
+    T.n_buckets = n_buckets;
+    T.b = b;
+    T.inv_b = inv_b;
+    const uint32_t bits = deep_bits<K>(T, ctx, (1u << b) - 1u, max_len);
+    if (bits) {
+        atomicOr(masks + (pos >> 1), (__brev(bits) >> (16 + K)) << ((pos & 1u) * 16u));
+        atomicAdd(row_count + (pos >> 8), (uint32_t)__popc(bits));
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) k_tier_deep(const DevAutomaton A, const DevTier T, const MaskArgs P) {
+    const uint32_t n = min(*P.cand_count, P.cand_cap);
+    const uint32_t cm = (1u << T.b) - 1u;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+        const uint32_t pos = __ldcs(P.cand_pos + i);
+        if (pos == kCandNone) continue;
+        const unsigned long long ctx = __ldcs(P.cand_ctx + i);
+        const uint32_t bits = deep_bits<K>(T, ctx, cm, A.max_len);
+        if (bits) {
+            atomicOr(P.masks + (pos >> 1), (__brev(bits) >> (16 + K)) << ((pos & 1u) * 16u));
+            atomicAdd(P.row_count + (pos >> 8), (uint32_t)__popc(bits));
+        }
+    }
+}
+
 template <int K, int LOW>
 __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomaton A, const DevTier T, const MaskArgs P) {
     extern __shared__ __align__(16) uint32_t s_mem[];
@@ -143,14 +190,23 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
     const unsigned char *kid_bytes = reinterpret_cast<const unsigned char *>(T.kidmask);
     uint32_t q_cnt = 0;
 
-    auto probe = [&](uint32_t first, uint32_t count) {  // entries [first, first + count) of the queue, count <= 32
-        if ((uint32_t)lane < count) {
-            const unsigned long long ctx = s_qctx[first + lane];
-            const uint32_t pos = s_qpos[first + lane];
-            const uint32_t bits = deep_bits<K>(T, ctx, cm, A.max_len);
-            if (bits) {
-                atomicOr(P.masks + (pos >> 1), (__brev(bits) >> (16 + K)) << ((pos & 1u) * 16u));
-                atomicAdd(P.row_count + (pos >> 8), (uint32_t)__popc(bits));
+    // hand entries [first, first + count) of the queue (count <= 32) to k_tier_deep; a batch that does not fit the
+    // candidate list is probed right here (dense-continuation texts; slow but exact)
+    auto probe = [&](uint32_t first, uint32_t count) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(P.cand_count, count);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        const bool mine = (uint32_t)lane < count;
+        if (base + count <= P.cand_cap && base + count >= base) {
+            if (mine) {
+                P.cand_ctx[base + lane] = s_qctx[first + lane];
+                P.cand_pos[base + lane] = s_qpos[first + lane];
+            }
+        } else {
+            if (mine) {
+                if (base < P.cand_cap && base + (uint32_t)lane < P.cand_cap) P.cand_pos[base + lane] = kCandNone;
+                deep_resolve<K>(T.buckets, T.hash_seed, T.n_buckets, T.b, T.inv_b, s_qctx[first + lane], s_qpos[first + lane], A.max_len,
+                                    P.masks, P.row_count);
             }
         }
     };
@@ -220,21 +276,33 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
                 uint32_t mj = 0;
 #pragma unroll
                 for (int i = 1; i < K; i++) {
-                    if (LOW == 2 || (LOW == 1 && i != K - 1)) continue;
-                    if (LOW == 1 || ((T.term_levels >> i) & 1u)) {
+                    if (LOW != 0) continue;  // LOW 1: level K-1 rides in the level-K rows (below); LOW 2: nothing there
+                    if ((T.term_levels >> i) & 1u) {
                         const uint32_t w = *reinterpret_cast<const uint32_t *>(s_tab + roff[i] + rs[i - 1]);
                         mj |= rotr32(w, cj) & (1u << (16 - i));
                     }
                 }
                 const uint2 wk = *reinterpret_cast<const uint2 *>(s_tab + roff[K] + rs[K - 1] * 2u);
                 mj |= rotr32(wk.x, cj) & (1u << (16 - K));
-                const bool kids = (wk.y >> cj) & 1u;
+                // bit 31 of the second word: the K-1 classes that name this row are a keyword (it ends one position back)
+                if (LOW == 1 && j >= 1) m[j - 1] |= (wk.y >> (14 + K)) & (1u << (17 - K));
+                // class K positions back: the child the context needs (class 0 = "in no keyword" never has one)
+                const uint32_t ck = j >= K ? c4[j >= K ? j - K : 0] >> 2 : prev_class(K - j);
+                const bool kids = ((wk.y >> cj) & 1u) && ck != 0u;
                 const uint32_t rk = rs[K - 1] * C + c4[j];  // byte offset of the level-K entry's child mask
 #pragma unroll
                 for (int k = K - 1; k >= 2; k--) rs[k] = rs[k - 1] * C + c4[j];
                 if (K >= 2) rs[1] = c4[j];
                 m[j] = mj;
+#if ACGPU_KID_TEX
+                ki[j] = (deeper && kids) ? tex1Dfetch<unsigned int>(T.kid_tex, (int)(rk >> 2)) : 0u;
+#else
                 ki[j] = deeper ? ldg_u32_if(kid_bytes + rk, kids) : 0u;
+#endif
+            }
+            if (LOW == 1) {  // position 7's level K-1 bit sits in the row the NEXT position would read
+                const uint32_t y = *reinterpret_cast<const uint32_t *>(s_tab + roff[K] + rs[K - 1] * 2u + 4u);
+                m[7] |= (y >> (14 + K)) & (1u << (17 - K));
             }
             // ---- positions outside [emit_from, emit_to) report nothing (edge rows only)
             uint32_t vm = 0xFFu;

@@ -32,6 +32,7 @@ struct DevTier {
     const uint32_t *row_words;   // the same levels in row layout (k_tier_mask), see TierTables in builder.hpp
     const uint32_t *cls8;        // 64 words: class of code units 0..255, one byte each
     const uint32_t *kidmask;     // [C^K] exact child masks of the level-K entries (nullptr: no deeper levels)
+    cudaTextureObject_t kid_tex; // the same table as a linear texture (k_tier_mask gathers it through the TEX pipe)
     const uint4 *buckets;        // deep table: 2 entries per 32-byte bucket, see TierTables in builder.hpp
     const uint32_t *shallow_val;
     const uint32_t *deep_valbase;  // [bucket * 2 + entry] -> first value of the entry's chain in deep_val

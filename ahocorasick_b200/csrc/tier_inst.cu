@@ -27,8 +27,31 @@ cudaError_t launch_variant(const DevAutomaton &A, const DevTier &T, const AcArgs
     return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kTierThreads), args, smem, st);
 }
 
+template <typename Kern>
+cudaError_t launch_windowed(Kern kern, int grid, int block, size_t smem, const L2Window &W, cudaStream_t st, const DevAutomaton &A,
+                            const DevTier &T, const MaskArgs &P) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (W.bytes) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<void *>(W.base);
+        attr[0].val.accessPolicyWindow.num_bytes = W.bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = W.hit_ratio;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, A, T, P);
+}
+
 template <int LOW>
-cudaError_t launch_mask_variant(const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, cudaStream_t st) {
+cudaError_t launch_mask_variant(const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, const L2Window &W,
+                                cudaStream_t st) {
     static size_t attr_smem[64] = {0};
     const void *fn = reinterpret_cast<const void *>(k_tier_mask<TIER_K, LOW>);
     int dev = 0;
@@ -39,8 +62,7 @@ cudaError_t launch_mask_variant(const DevAutomaton &A, const DevTier &T, const M
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_smem[dev] = smem;
     }
-    k_tier_mask<TIER_K, LOW><<<grid, kMaskThreads, smem, st>>>(A, T, P);
-    return cudaGetLastError();
+    return launch_windowed(k_tier_mask<TIER_K, LOW>, grid, kMaskThreads, smem, W, st, A, T, P);
 }
 
 }  // namespace
@@ -61,13 +83,18 @@ cudaError_t ACGPU_CAT(tier_launch_, TIER_K)(int low, bool is_map, const DevAutom
     }
 }
 
+cudaError_t ACGPU_CAT(deep_launch_, TIER_K)(const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, const L2Window &W,
+                                            cudaStream_t st) {
+    return launch_windowed(k_tier_deep<TIER_K>, grid, 256, 0, W, st, A, T, P);
+}
+
 cudaError_t ACGPU_CAT(mask_launch_, TIER_K)(int low, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid,
-                                            size_t smem, cudaStream_t st) {
+                                            size_t smem, const L2Window &W, cudaStream_t st) {
     if (TIER_K == 1) low = 2;
     switch (low) {
-    case 0: return launch_mask_variant<0>(A, T, P, grid, smem, st);
-    case 1: return launch_mask_variant<1>(A, T, P, grid, smem, st);
-    default: return launch_mask_variant<2>(A, T, P, grid, smem, st);
+    case 0: return launch_mask_variant<0>(A, T, P, grid, smem, W, st);
+    case 1: return launch_mask_variant<1>(A, T, P, grid, smem, W, st);
+    default: return launch_mask_variant<2>(A, T, P, grid, smem, W, st);
     }
 }
 

@@ -10,6 +10,14 @@ namespace acgpu {
 struct DevTier;
 struct MaskArgs;
 
+// Tables that every probe gathers from (child masks + deep table): the launches ask L2 to keep them resident while the
+// haystack, mask and record streams pass through (cudaLaunchAttributeAccessPolicyWindow; bytes == 0: no window).
+struct L2Window {
+    const void *base = nullptr;
+    size_t bytes = 0;
+    float hit_ratio = 1.0f;
+};
+
 // low: 0 = every level below K may hold keywords, 1 = only level K-1 does, 2 = none does.
 // Sets the dynamic shared-memory attribute once per kernel and launches cooperatively (the kernel waits for tiles of
 // lower index, so the whole grid must be resident: a launch that cannot be, fails instead of dead-locking).
@@ -27,7 +35,8 @@ ACGPU_DECLARE_TIER(8)
 
 // k_tier_mask<K, LOW> (kernel_mask.cuh): persistent, one CTA per SM; no inter-CTA waiting, plain launch.
 #define ACGPU_DECLARE_MASK(k) \
-    cudaError_t mask_launch_##k(int low, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, cudaStream_t st);
+    cudaError_t deep_launch_##k(const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, const L2Window &W, cudaStream_t st); \
+    cudaError_t mask_launch_##k(int low, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, const L2Window &W, cudaStream_t st);
 ACGPU_DECLARE_MASK(1)
 ACGPU_DECLARE_MASK(2)
 ACGPU_DECLARE_MASK(3)
