@@ -178,19 +178,14 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
                 }
             }
             __syncwarp();
+            // pairs [k_lo, k_hi) are whole; a lone head record (par == 1) and a lone tail record go out as 8-byte stores
             int2 *g = E.pos_out + (base - par);  // 16-byte aligned
-            const uint32_t n_pair = (par + total + 1u) >> 1;
-            for (uint32_t k = lane; k < n_pair; k += 32) {
-                const int4 v = *reinterpret_cast<const int4 *>(s_stage + 2 * k);
-                const bool lo_ok = 2 * k >= par, hi_ok = 2 * k + 1 < par + total;
-                if (lo_ok && hi_ok) {
-                    __stcs(reinterpret_cast<int4 *>(g + 2 * k), v);
-                } else if (lo_ok) {
-                    __stcs(g + 2 * k, make_int2(v.x, v.y));
-                } else if (hi_ok) {
-                    __stcs(g + 2 * k + 1, make_int2(v.z, v.w));
-                }
-            }
+            const uint32_t end = par + total, k_hi = end >> 1;
+            if (lane == 0 && par) __stcs(g + 1, s_stage[1]);
+            if (lane == 1 && (end & 1u)) __stcs(g + (end - 1u), s_stage[end - 1u]);
+            int4 *gp = reinterpret_cast<int4 *>(g) + par + lane;
+            const int4 *sp = reinterpret_cast<const int4 *>(s_stage) + par + lane;
+            for (uint32_t k = par + lane; k < k_hi; k += 32, gp += 32, sp += 32) __stcs(gp, *sp);
             __syncwarp();
             continue;
         }

@@ -21,7 +21,7 @@
 namespace acgpu {
 
 #ifndef ACGPU_MASK_WARPS
-#define ACGPU_MASK_WARPS 24
+#define ACGPU_MASK_WARPS 32
 #endif
 constexpr int kMaskWarps = ACGPU_MASK_WARPS;
 #ifndef ACGPU_KID_TEX
@@ -45,13 +45,7 @@ struct MaskArgs {
     uint32_t *row_count;    // [n_rows]
     unsigned int *ticket;
     int64_t n_rows;
-    // contexts that continue past level K: probed against the deep table by k_tier_deep
-    unsigned long long *cand_ctx;
-    uint32_t *cand_pos;       // position relative to origin; kCandNone = hole
-    unsigned int *cand_count; // entries reserved so far (may exceed cand_cap: batches that did not fit were probed in place)
-    uint32_t cand_cap;
 };
-constexpr uint32_t kCandNone = 0xFFFFFFFFu;
 
 struct ScanArgs {
     uint32_t *row_count;              // in: counts, out: exclusive prefix inside the row's block of kScanRows rows
@@ -150,22 +144,6 @@ __device__ __noinline__ void deep_resolve(const uint4 *buckets, unsigned long lo
     }
 }
 
-template <int K>
-__global__ void __launch_bounds__(256) k_tier_deep(const DevAutomaton A, const DevTier T, const MaskArgs P) {
-    const uint32_t n = min(*P.cand_count, P.cand_cap);
-    const uint32_t cm = (1u << T.b) - 1u;
-    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
-        const uint32_t pos = __ldcs(P.cand_pos + i);
-        if (pos == kCandNone) continue;
-        const unsigned long long ctx = __ldcs(P.cand_ctx + i);
-        const uint32_t bits = deep_bits<K>(T, ctx, cm, A.max_len);
-        if (bits) {
-            atomicOr(P.masks + (pos >> 1), (__brev(bits) >> (16 + K)) << ((pos & 1u) * 16u));
-            atomicAdd(P.row_count + (pos >> 8), (uint32_t)__popc(bits));
-        }
-    }
-}
-
 template <int K, int LOW>
 __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomaton A, const DevTier T, const MaskArgs P) {
     extern __shared__ __align__(16) uint32_t s_mem[];
@@ -179,7 +157,14 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
     uint32_t *s_qpos = reinterpret_cast<uint32_t *>(s_q + kMaskQueue * 8);
 
     for (uint32_t i = tid; i < 256; i += kMaskThreads) s_cls4[i] = (uint8_t)(((__ldg(&T.cls8[i >> 2]) >> ((i & 3) * 8)) & 0xFFu) * 4u);
-    for (uint32_t i = tid; i < T.n_row_words; i += kMaskThreads) s_mem[64 + i] = __ldg(&T.row_words[i]);
+    {
+        const uint32_t n4 = T.n_row_words >> 2;  // the table is 16-byte aligned on both sides
+        const uint4 *src = reinterpret_cast<const uint4 *>(T.row_words);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_mem + 64);
+#pragma unroll 4
+        for (uint32_t i = tid; i < n4; i += kMaskThreads) dst[i] = __ldg(src + i);
+        for (uint32_t i = (n4 << 2) + tid; i < T.n_row_words; i += kMaskThreads) s_mem[64 + i] = __ldg(&T.row_words[i]);
+    }
     __syncthreads();
 
     const bool deeper = T.kidmask != nullptr;  // some keyword is longer than K
@@ -187,28 +172,17 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
     uint32_t roff[K + 1];
 #pragma unroll
     for (int i = 1; i <= K; i++) roff[i] = T.row_off[i] * 4u;
+#if !ACGPU_KID_TEX
     const unsigned char *kid_bytes = reinterpret_cast<const unsigned char *>(T.kidmask);
+#endif
     uint32_t q_cnt = 0;
 
-    // hand entries [first, first + count) of the queue (count <= 32) to k_tier_deep; a batch that does not fit the
-    // candidate list is probed right here (dense-continuation texts; slow but exact)
+    // entries [first, first + count) of the queue (count <= 32) against the deep table.  (A separate gather kernel fed
+    // from a candidate list measured 3% slower end to end and costs 1.5 GB of scratch per 10^9 chars.)
     auto probe = [&](uint32_t first, uint32_t count) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(P.cand_count, count);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        const bool mine = (uint32_t)lane < count;
-        if (base + count <= P.cand_cap && base + count >= base) {
-            if (mine) {
-                P.cand_ctx[base + lane] = s_qctx[first + lane];
-                P.cand_pos[base + lane] = s_qpos[first + lane];
-            }
-        } else {
-            if (mine) {
-                if (base < P.cand_cap && base + (uint32_t)lane < P.cand_cap) P.cand_pos[base + lane] = kCandNone;
-                deep_resolve<K>(T.buckets, T.hash_seed, T.n_buckets, T.b, T.inv_b, s_qctx[first + lane], s_qpos[first + lane], A.max_len,
-                                    P.masks, P.row_count);
-            }
-        }
+        if ((uint32_t)lane < count)
+            deep_resolve<K>(T.buckets, T.hash_seed, T.n_buckets, T.b, T.inv_b, s_qctx[first + lane], s_qpos[first + lane], A.max_len,
+                            P.masks, P.row_count);
     };
     auto fetch = [&](int64_t row, int64_t row_end) -> uint4 {
         const int64_t p0 = P.origin + row * kMaskRow + (int64_t)lane * 8;

@@ -83,11 +83,6 @@ cudaError_t ACGPU_CAT(tier_launch_, TIER_K)(int low, bool is_map, const DevAutom
     }
 }
 
-cudaError_t ACGPU_CAT(deep_launch_, TIER_K)(const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, const L2Window &W,
-                                            cudaStream_t st) {
-    return launch_windowed(k_tier_deep<TIER_K>, grid, 256, 0, W, st, A, T, P);
-}
-
 cudaError_t ACGPU_CAT(mask_launch_, TIER_K)(int low, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid,
                                             size_t smem, const L2Window &W, cudaStream_t st) {
     if (TIER_K == 1) low = 2;

@@ -35,7 +35,6 @@ ACGPU_DECLARE_TIER(8)
 
 // k_tier_mask<K, LOW> (kernel_mask.cuh): persistent, one CTA per SM; no inter-CTA waiting, plain launch.
 #define ACGPU_DECLARE_MASK(k) \
-    cudaError_t deep_launch_##k(const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, const L2Window &W, cudaStream_t st); \
     cudaError_t mask_launch_##k(int low, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, const L2Window &W, cudaStream_t st);
 ACGPU_DECLARE_MASK(1)
 ACGPU_DECLARE_MASK(2)

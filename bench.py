@@ -256,7 +256,9 @@ def run_ours(args):
     value = total_chars * 2 / (ms_per_step * 1e-3) / 1e9
     matches_per_s = total_matches / (ms_per_step * 1e-3)
 
-    # roofline of the dominant kernel (k_ac_scan): algorithmic bytes per launch / average launch duration
+    # roofline of one match = k_tier_mask + k_row_scan + k_tier_emit back to back (the scan is 0.4 % of it):
+    # algorithmic bytes per match (2 B per char read once + 8 B per record written once) / average duration of the
+    # three launches, timed by the CUDA events above on the launch stream
     n_launch = max(len(hays), 1)
     alg_bytes = 2 * n + 8 * (sum(counts) / n_launch)
     launch_ms = ms / args.steps / n_launch
@@ -266,8 +268,16 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+    # DRAM bytes of the same three launches from the committed ncu --set full captures (profiles/traffic.json), scaled
+    # to this haystack length; null when the captures are for another workload
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath))
+        if t.get("keywords") == args.keywords:
+            traffic = t["dram_bytes_per_char"] * n
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_ac_scan", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "k_tier_mask + k_row_scan + k_tier_emit (one match)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
                 "haystack_only_frac": (2 * n / (launch_ms * 1e-3) / 1e9) / peak}
 
