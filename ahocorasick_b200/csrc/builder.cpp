@@ -101,8 +101,7 @@ void make_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, in
 
 namespace {
 
-constexpr uint64_t kTierSmemBits = 135ull * 1024 * 8;  // shared-memory budget for ALL direct-indexed level tables
-constexpr uint64_t kTierRowBytes = 176ull * 1024;      // ... and for the same levels in row layout (k_tier_mask)
+constexpr uint64_t kTierRowBytes = 176ull * 1024;  // shared-memory budget for ALL direct-indexed level tables (row layout)
 
 void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, const std::vector<uint16_t> &node_cls) {
     TierTables &t = a.tier;
@@ -112,14 +111,14 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
     int b = 1;
     while ((1 << b) < C) b++;
     if (static_cast<int64_t>(b) * a.max_len > 60 || a.max_len > 16) return;  // contexts pack into 60 bits, hit masks into 16
-    // K = deepest level whose 2-bit table fits the shared-memory budget
+    // K = deepest level whose rows (two words per row) fit the shared-memory budget next to the one-word rows of the
+    // levels below it
     int K = 0;
-    uint64_t entries = 1, lower_bits = 0;  // lower_bits: 1-bit tables of the levels below K (word-rounded)
+    uint64_t entries = 1, lower_bytes = 0;  // entries = C^K = rows of level K+1
     while (K < a.max_len && K < 8) {
-        const uint64_t lower_next = lower_bits + (K >= 1 ? (entries + 31) / 32 * 32 : 0);
-        if (lower_next + entries * C * 2 + 32 > kTierSmemBits) break;
-        if (lower_next / 8 * 32 / C + entries * 8 + 64 > kTierRowBytes) break;  // lower levels: a word per C entries
-        lower_bits = lower_next;
+        const uint64_t lower_next = lower_bytes + (K >= 1 ? entries / C * 4 : 0);  // level K becomes a lower level
+        if (lower_next + entries * 8 + 64 > kTierRowBytes) break;
+        lower_bytes = lower_next;
         entries *= C;
         K++;
     }
@@ -128,15 +127,10 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
     t.b = b;
     t.K = K;
     uint64_t pw = 1;
-    uint32_t off = 0;
     for (int j = 1; j <= K; j++) {
         t.pow_c[j] = static_cast<uint32_t>(pw);  // C^(j-1)
         pw *= C;
-        t.lvl_off[j] = off;
-        const uint64_t bits = pw * (j == K ? 2 : 1);
-        off += static_cast<uint32_t>((bits + 31) / 32);
     }
-    t.smem_words.assign(off, 0);
     {
         uint32_t roff = 0;
         uint64_t rows = 1;  // C^(j-1)
@@ -182,15 +176,12 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
         const uint32_t inf = a.node_info[id];
         if (d < K) {
             if (inf & kInfoTerminal) {
-                t.smem_words[t.lvl_off[d] + (radix[id] >> 5)] |= 1u << (radix[id] & 31);
                 t.row_words[t.row_off[d] + radix[id] / C] |= 1u << ((radix[id] % C + 16 - d) & 31);
                 // a keyword of length K-1 is also flagged in the level-K row it names (spare bit 31 of the kids word)
                 if (d == K - 1 && C <= 31) t.row_words[t.row_off[K] + 2 * radix[id] + 1] |= 1u << 31;
                 t.term_levels |= 1u << d;
             }
         } else if (d == K) {
-            const uint32_t two = (inf & kInfoTerminal ? 1u : 0u) | (inf & kInfoHasChildren ? 2u : 0u);
-            t.smem_words[t.lvl_off[K] + (radix[id] >> 4)] |= two << ((radix[id] & 15) * 2);
             uint32_t *rw = &t.row_words[t.row_off[K] + 2 * (radix[id] / C)];
             if (inf & kInfoTerminal) rw[0] |= 1u << ((radix[id] % C + 16 - K) & 31);
             if (inf & kInfoHasChildren) rw[1] |= 1u << (radix[id] % C);

@@ -73,10 +73,8 @@ struct TierTables {
     int32_t b = 0;        // bits per class in the packed context
     int32_t K = 0;        // direct-indexed levels
     uint32_t term_levels = 0;        // bit j: some keyword has length j (j <= K)
-    uint32_t lvl_off[10] = {0};      // word offset of level j's table inside smem_words (j = 1..K)
     uint32_t pow_c[10] = {0};        // C^(j-1)
-    std::vector<uint32_t> smem_words;
-    // the same levels laid out by ROW for k_tier_mask: the row of level j is the mixed-radix number of the j-1 classes
+    // levels 1..K laid out by ROW for k_tier_mask: the row of level j is the mixed-radix number of the j-1 classes
     // BEFORE the current one, the current class selects a bit.  Level j < K: one word per row, the terminal bit of
     // class c sits at bit (c + 16 - j) & 31, so rotating the word right by c drops it on bit 16 - j = where a keyword
     // of length j lives in a hit mask.  Level K: two words per row, terminal bits (same rotation) and has-children bits

@@ -79,8 +79,6 @@ struct Matcher {
     bool use_tier = false;
     DevTier tier{};
     void *d_tier_blob = nullptr;
-    size_t tier_smem = 0;
-    bool use_mask = false;  // generation 3: k_tier_mask + k_row_scan + k_tier_emit
     L2Window l2win;         // child masks + deep table, kept L2-resident across the streaming traffic
     size_t mask_smem = 0;
 };
@@ -136,15 +134,14 @@ int upload_tier(Matcher *m) {
     if (!t.ok || m->host.family != ACGPU_AHOCORASICK) return ACGPU_OK;
     const char *force = getenv("ACGPU_FORCE_GEN1");
     if (force && force[0] == '1') return ACGPU_OK;
-    const size_t smem = tier_smem_bytes(t.smem_words.size(), m->host.is_map);
-    if (smem > 227 * 1024) return ACGPU_OK;
+    m->mask_smem = mask_smem_bytes(t.row_words.size());
+    if (m->mask_smem > 227 * 1024) return ACGPU_OK;
     size_t off = 0;
     auto reserve = [&](size_t bytes) {
         size_t o = off;
         off = align_up(off + std::max<size_t>(bytes, 16), 512);  // linear textures want 512-byte aligned bases
         return o;
     };
-    size_t o_words = reserve(t.smem_words.size() * 4);
     size_t o_rows = reserve(t.row_words.size() * 4);
     size_t o_cls8 = reserve(256);
     size_t o_kid = reserve(t.kidmask.size() * 4);
@@ -157,7 +154,6 @@ int upload_tier(Matcher *m) {
     char *b = static_cast<char *>(m->d_tier_blob);
     uint8_t cls8[256];
     for (int c = 0; c < 256; c++) cls8[c] = static_cast<uint8_t>(m->host.cls[c]);
-    if (!t.smem_words.empty()) CU_TRY(cudaMemcpy(b + o_words, t.smem_words.data(), t.smem_words.size() * 4, cudaMemcpyHostToDevice));
     if (!t.row_words.empty()) CU_TRY(cudaMemcpy(b + o_rows, t.row_words.data(), t.row_words.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(b + o_cls8, cls8, 256, cudaMemcpyHostToDevice));
     if (!t.kidmask.empty()) CU_TRY(cudaMemcpy(b + o_kid, t.kidmask.data(), t.kidmask.size() * 4, cudaMemcpyHostToDevice));
@@ -166,7 +162,6 @@ int upload_tier(Matcher *m) {
     if (!t.deep_valbase.empty()) CU_TRY(cudaMemcpy(b + o_dvb, t.deep_valbase.data(), t.deep_valbase.size() * 4, cudaMemcpyHostToDevice));
     if (!t.deep_val.empty()) CU_TRY(cudaMemcpy(b + o_dval, t.deep_val.data(), t.deep_val.size() * 4, cudaMemcpyHostToDevice));
     DevTier &d = m->tier;
-    d.smem_words = reinterpret_cast<const uint32_t *>(b + o_words);
     d.cls8 = reinterpret_cast<const uint32_t *>(b + o_cls8);
     d.kidmask = t.kidmask.empty() ? nullptr : reinterpret_cast<const uint32_t *>(b + o_kid);
     d.kid_tex = 0;
@@ -188,11 +183,9 @@ int upload_tier(Matcher *m) {
     d.shallow_val = reinterpret_cast<const uint32_t *>(b + o_sval);
     d.deep_valbase = reinterpret_cast<const uint32_t *>(b + o_dvb);
     d.deep_val = reinterpret_cast<const uint32_t *>(b + o_dval);
-    d.n_words = static_cast<uint32_t>(t.smem_words.size());
     d.row_words = reinterpret_cast<const uint32_t *>(b + o_rows);
     d.n_row_words = static_cast<uint32_t>(t.row_words.size());
     for (int j = 0; j < 10; j++) d.row_off[j] = t.row_off[j];
-    m->mask_smem = mask_smem_bytes(t.row_words.size());
     {
         // L2 residency window over [child masks | deep table] (adjacent in the blob)
         int max_win = 0, max_persist = 0;
@@ -211,8 +204,6 @@ int upload_tier(Matcher *m) {
             }
         }
     }
-    const char *gen2 = getenv("ACGPU_FORCE_GEN2");
-    m->use_mask = m->mask_smem <= 227 * 1024 && !(gen2 && gen2[0] == '1');
     d.n_buckets = t.n_buckets;
     d.inv_b = (65536u + static_cast<uint32_t>(t.b) - 1u) / static_cast<uint32_t>(t.b);
     d.term_levels = t.term_levels;
@@ -220,21 +211,11 @@ int upload_tier(Matcher *m) {
     d.C = t.C;
     d.K = t.K;
     for (int j = 0; j < 10; j++) {
-        d.lvl_off[j] = t.lvl_off[j];
         d.pow_c[j] = t.pow_c[j];
         d.val_off[j] = t.val_off[j];
     }
-    m->tier_smem = smem;
     m->use_tier = true;
     return ACGPU_OK;
-}
-
-// k_ac_tier variant for this dictionary: which levels below K hold keywords (see kernel_tier.cuh)
-int tier_low_variant(const DevTier &t) {
-    const uint32_t below = t.term_levels & ((1u << t.K) - 1u) & ~1u;  // bits 1..K-1
-    if (below == 0) return 2;
-    if (below == (1u << (t.K - 1))) return 1;
-    return 0;
 }
 
 // k_tier_mask: variant 1 reads level K-1 from the spare bit of the level-K rows, which exists for at most 31 classes
@@ -243,24 +224,6 @@ int mask_low_variant(const DevTier &t) {
     if (below == 0) return 2;
     if (below == (1u << (t.K - 1)) && t.C <= 31) return 1;
     return 0;
-}
-
-int launch_tier(Matcher *m, const AcArgs &P, int grid, cudaStream_t st) {
-    const int low = tier_low_variant(m->tier);
-    const bool is_map = m->dev.is_map != 0;
-    cudaError_t e;
-    switch (m->tier.K) {
-    case 1: e = tier_launch_1(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
-    case 2: e = tier_launch_2(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
-    case 3: e = tier_launch_3(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
-    case 4: e = tier_launch_4(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
-    case 5: e = tier_launch_5(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
-    case 6: e = tier_launch_6(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
-    case 7: e = tier_launch_7(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
-    default: e = tier_launch_8(low, is_map, m->dev, m->tier, P, grid, m->tier_smem, st); break;
-    }
-    CU_TRY(e);
-    return ACGPU_OK;
 }
 
 // Scratch for one match call, carved from one stream-ordered allocation.
@@ -378,13 +341,13 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
         const int64_t mis = static_cast<int64_t>((reinterpret_cast<uintptr_t>(d_hay) >> 1) & 7);
         const int64_t origin = m->use_tier ? ((emit_from + mis) & ~int64_t(7)) - mis : emit_from;
         const int64_t span = std::max<int64_t>(0, emit_to - origin);
-        const int64_t tile_sz = m->use_tier ? kTierTile : kAcTile;
+        const int64_t tile_sz = kAcTile;
         const int64_t n_tiles = emit_to > emit_from ? (span + tile_sz - 1) / tile_sz : 0;
         if (n_tiles == 0) {
             CU_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
             return ACGPU_OK;
         }
-        if (m->use_tier && m->use_mask) return enqueue_mask(m, d_hay, n, emit_from, emit_to, origin, d_pos, d_val, cap, d_total, st, opt);
+        if (m->use_tier) return enqueue_mask(m, d_hay, n, emit_from, emit_to, origin, d_pos, d_val, cap, d_total, st, opt);
         size_t bytes = 256 + static_cast<size_t>(n_tiles) * 8;
         void *ws = nullptr;
         CU_TRY(cudaMallocAsync(&ws, bytes, st));
@@ -403,17 +366,12 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
         P.tile_counter = static_cast<unsigned int *>(ws);
         P.status = reinterpret_cast<unsigned long long *>(static_cast<char *>(ws) + 256);
         P.n_tiles = n_tiles;
-        if (m->use_tier) {
-            int rc = launch_tier(m, P, static_cast<int>(std::min<int64_t>(n_tiles, m->sm_count)), st);
-            if (rc != ACGPU_OK) return rc;
-        } else {
-            const int grid = static_cast<int>(std::min<int64_t>(n_tiles, persistent));
-            if (A.is_map)
-                k_ac_scan<true><<<grid, kThreads, 0, st>>>(A, P);
-            else
-                k_ac_scan<false><<<grid, kThreads, 0, st>>>(A, P);
-            CU_TRY(cudaGetLastError());
-        }
+        const int grid = static_cast<int>(std::min<int64_t>(n_tiles, persistent));
+        if (A.is_map)
+            k_ac_scan<true><<<grid, kThreads, 0, st>>>(A, P);
+        else
+            k_ac_scan<false><<<grid, kThreads, 0, st>>>(A, P);
+        CU_TRY(cudaGetLastError());
         CU_TRY(cudaFreeAsync(ws, st));
         return ACGPU_OK;
     }
@@ -939,7 +897,7 @@ int acgpu_launches_per_match(uint64_t handle) {
     Matcher *m = as_matcher(handle);
     if (!m) return fail(ACGPU_EINVAL, "bad handle");
     switch (m->host.family) {
-    case ACGPU_AHOCORASICK: return m->use_tier && m->use_mask ? 3 : 1;
+    case ACGPU_AHOCORASICK: return m->use_tier ? 3 : 1;
     case ACGPU_WHOLEWORD: return 2;
     default: return 6;
     }

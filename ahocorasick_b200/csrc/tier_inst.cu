@@ -11,22 +11,6 @@ namespace acgpu {
 
 namespace {
 
-template <int LOW, bool kIsMap>
-cudaError_t launch_variant(const DevAutomaton &A, const DevTier &T, const AcArgs &P, int grid, size_t smem, cudaStream_t st) {
-    static size_t attr_smem[64] = {0};  // per device: dynamic shared memory already granted to this kernel
-    const void *fn = reinterpret_cast<const void *>(k_ac_tier<TIER_K, LOW, kIsMap>);
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev < 0 || dev >= 64 || attr_smem[dev] < smem) {
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) attr_smem[dev] = smem;
-    }
-    void *args[3] = {const_cast<DevAutomaton *>(&A), const_cast<DevTier *>(&T), const_cast<AcArgs *>(&P)};
-    return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kTierThreads), args, smem, st);
-}
-
 template <typename Kern>
 cudaError_t launch_windowed(Kern kern, int grid, int block, size_t smem, const L2Window &W, cudaStream_t st, const DevAutomaton &A,
                             const DevTier &T, const MaskArgs &P) {
@@ -69,19 +53,6 @@ cudaError_t launch_mask_variant(const DevAutomaton &A, const DevTier &T, const M
 
 #define ACGPU_CAT2(a, b) a##b
 #define ACGPU_CAT(a, b) ACGPU_CAT2(a, b)
-
-cudaError_t ACGPU_CAT(tier_launch_, TIER_K)(int low, bool is_map, const DevAutomaton &A, const DevTier &T, const AcArgs &P,
-                                            int grid, size_t smem, cudaStream_t st) {
-    if (TIER_K == 1) low = 2;  // there is no level below 1
-    switch (low * 2 + (is_map ? 1 : 0)) {
-    case 0: return launch_variant<0, false>(A, T, P, grid, smem, st);
-    case 1: return launch_variant<0, true>(A, T, P, grid, smem, st);
-    case 2: return launch_variant<1, false>(A, T, P, grid, smem, st);
-    case 3: return launch_variant<1, true>(A, T, P, grid, smem, st);
-    case 4: return launch_variant<2, false>(A, T, P, grid, smem, st);
-    default: return launch_variant<2, true>(A, T, P, grid, smem, st);
-    }
-}
 
 cudaError_t ACGPU_CAT(mask_launch_, TIER_K)(int low, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid,
                                             size_t smem, const L2Window &W, cudaStream_t st) {

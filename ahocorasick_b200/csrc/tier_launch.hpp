@@ -1,5 +1,5 @@
-// Launch entry points of the k_ac_tier instantiations.  Every K lives in its own translation unit (tier_inst.cu
-// compiled with -DTIER_K=k) so the 48 kernels build in parallel.
+// Launch entry points of the k_tier_mask instantiations.  Every K lives in its own translation unit (tier_inst.cu
+// compiled with -DTIER_K=k) so the kernels build in parallel.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -18,21 +18,7 @@ struct L2Window {
     float hit_ratio = 1.0f;
 };
 
-// low: 0 = every level below K may hold keywords, 1 = only level K-1 does, 2 = none does.
-// Sets the dynamic shared-memory attribute once per kernel and launches cooperatively (the kernel waits for tiles of
-// lower index, so the whole grid must be resident: a launch that cannot be, fails instead of dead-locking).
-#define ACGPU_DECLARE_TIER(k) \
-    cudaError_t tier_launch_##k(int low, bool is_map, const DevAutomaton &A, const DevTier &T, const AcArgs &P, int grid, size_t smem, cudaStream_t st);
-ACGPU_DECLARE_TIER(1)
-ACGPU_DECLARE_TIER(2)
-ACGPU_DECLARE_TIER(3)
-ACGPU_DECLARE_TIER(4)
-ACGPU_DECLARE_TIER(5)
-ACGPU_DECLARE_TIER(6)
-ACGPU_DECLARE_TIER(7)
-ACGPU_DECLARE_TIER(8)
-#undef ACGPU_DECLARE_TIER
-
+// low: 0 = every level below K may hold keywords, 1 = only level K-1 does (and rides in the level-K rows), 2 = none does.
 // k_tier_mask<K, LOW> (kernel_mask.cuh): persistent, one CTA per SM; no inter-CTA waiting, plain launch.
 #define ACGPU_DECLARE_MASK(k) \
     cudaError_t mask_launch_##k(int low, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, const L2Window &W, cudaStream_t st);

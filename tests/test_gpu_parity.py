@@ -259,3 +259,33 @@ def test_full_1m_dictionary_parity(monkeypatch):
         rec = ac.AhoCorasickSet(kws, True).match_records(hay)
         assert len(rec) == len(want), (gen1, len(rec), len(want))
         assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"])
+
+
+# ---------------------------------------------------------------- committed fixtures (tests/golden/oracle_streams.json)
+
+def _golden_cases():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_streams.json")))
+
+
+@pytest.mark.parametrize("case", _golden_cases(), ids=lambda c: c["name"])
+def test_committed_fixture_streams(case):
+    """The CUDA path against the committed ordered streams — no oracle call in this test."""
+    kws, hay, cs = case["keywords"], case["haystack"], case["case_sensitive"]
+    values = list(range(len(kws)))
+    for fam in FAMILIES:
+        want = case["streams"][fam]
+        extra = ()
+        if case.get("word_chars") and fam == "wholeword":
+            w = case["word_chars"]
+            extra = (w["chars"], w["toggles"])
+        if "error" in want:
+            with pytest.raises(ac.IllegalArgumentException):
+                SETS[fam](kws, cs, *extra)
+            continue
+        assert gpu_set_stream(SETS[fam](kws, cs, *extra), hay) == [(s, e) for s, e, _ in want["string"]]
+        assert gpu_map_stream(MAPS[fam](kws, values, cs, *extra), hay) == [tuple(t) for t in want["string"]]
+        c = Collect()
+        MAPS[fam](kws, values, cs, *extra).match(io.StringIO(hay), c)
+        assert [v[0] for v in c.calls] == want["readable_values"]

@@ -181,3 +181,47 @@ def test_reference_random_unicode_dictionary():
         want = [(s, e) for s, e, _ in spec.MODELS[fam](kws, hay)]
         assert got == want
         assert len(got) >= 25
+
+
+# ---------------------------------------------------------------- committed fixtures (tests/golden/)
+
+def _golden(name):
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)))
+
+
+def test_reference_kats_fixture_in_sync():
+    """tests/golden/reference_kats.json is the committed form of golden_cases.py (MatchQueueTest.java:8-57,
+    SetTest.java:67-130, README examples); tests/golden/make_golden.py regenerates it."""
+    kats = _golden("reference_kats.json")
+    assert set(kats["match_queue"]) == set(MATCH_QUEUE_KATS)
+    for name, kat in MATCH_QUEUE_KATS.items():
+        assert [tuple(x) for x in kats["match_queue"][name]["expect"]] == kat["expect"]
+        assert [tuple(x) for x in kats["match_queue"][name]["steps"]] == kat["steps"]
+    assert set(kats["literal"]) == set(LITERAL_CASES)
+    for name, (hay, kws, expect) in LITERAL_CASES.items():
+        got = kats["literal"][name]["expect"]
+        assert set(got) == set(expect)
+        for fam, exp in expect.items():
+            assert got[fam] == ([list(x) for x in exp] if isinstance(exp, list) else exp)
+
+
+@pytest.mark.parametrize("case", _golden("oracle_streams.json"), ids=lambda c: c["name"])
+def test_oracle_reproduces_committed_streams(case):
+    """The seeded fixtures freeze the oracle's ordered (start, end, value) streams (String and Readable overloads)."""
+    for fam in FAMILIES:
+        want = case["streams"][fam]
+        wc = None
+        if case.get("word_chars") and fam == "wholeword":
+            w = case["word_chars"]
+            wc = ora.word_chars(w["mode"], w["chars"], w["toggles"])
+        if "error" in want:
+            with pytest.raises(ora.OracleError):
+                ora.Matcher(fam, case["keywords"], n_values=len(case["keywords"]), case_sensitive=case["case_sensitive"],
+                            word_chars_table=wc)
+            continue
+        m = ora.Matcher(fam, case["keywords"], n_values=len(case["keywords"]), case_sensitive=case["case_sensitive"],
+                        word_chars_table=wc)
+        assert [list(t) for t in stream_v(m.match(case["haystack"]))] == want["string"]
+        assert [int(r["value"]) for r in m.match(case["haystack"], readable=True)] == want["readable_values"]
