@@ -117,7 +117,9 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
     __shared__ __align__(16) int2 s_stage_all[kEmitWarps][kEmitStage + 2];
     __shared__ uint32_t s_val_all[kIsMap ? kEmitWarps : 1][kIsMap ? kEmitStage : 1];
     __shared__ __align__(16) uint32_t s_cls[64];
+    __shared__ uint2 s_pack_all[kIsMap ? kEmitWarps : 1][kIsMap ? 34 : 1];  // packed classes of the row: [0,1] = the 16 chars before it
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint2 *s_pack = s_pack_all[kIsMap ? warp : 0];
     int2 *s_stage = s_stage_all[warp];
     uint32_t *s_val = s_val_all[kIsMap ? warp : 0];
     uint8_t *s_cls4 = reinterpret_cast<uint8_t *>(s_cls);
@@ -160,36 +162,6 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
         const int32_t e0 = (int32_t)(p0 + 1) + E.pos_base;  // end (exclusive) of a keyword whose last char is position p0
         const uint32_t words[4] = {mm.x, mm.y, mm.z, mm.w};
 
-        if (!kIsMap && total <= (uint32_t)kEmitStage && base + total <= (unsigned long long)E.cap) {
-            // ---- common case: the whole row fits the staging window and the caller's buffer.  Records are staged at
-            //      the parity of their final address so that both sides of the flush are 16-byte aligned.
-            const uint32_t par = ((uint32_t)base + out_par) & 1u;
-            uint32_t sa = stage_sa + (my_off + par) * 8u;
-#pragma unroll
-            for (int wi = 0; wi < 4; wi++) {
-                uint32_t w = words[wi];
-                const int32_t eb = e0 + 2 * wi;
-                while (w) {
-                    const uint32_t t = (uint32_t)__clz((int)__brev(w));
-                    w &= w - 1u;
-                    const int32_t e = eb + (int32_t)(t >> 4);
-                    sts_v2(sa, e - 16 + (int32_t)(t & 15u), e);
-                    sa += 8u;
-                }
-            }
-            __syncwarp();
-            // pairs [k_lo, k_hi) are whole; a lone head record (par == 1) and a lone tail record go out as 8-byte stores
-            int2 *g = E.pos_out + (base - par);  // 16-byte aligned
-            const uint32_t end = par + total, k_hi = end >> 1;
-            if (lane == 0 && par) __stcs(g + 1, s_stage[1]);
-            if (lane == 1 && (end & 1u)) __stcs(g + (end - 1u), s_stage[end - 1u]);
-            int4 *gp = reinterpret_cast<int4 *>(g) + par + lane;
-            const int4 *sp = reinterpret_cast<const int4 *>(s_stage) + par + lane;
-            for (uint32_t k = par + lane; k < k_hi; k += 32, gp += 32, sp += 32) __stcs(gp, *sp);
-            __syncwarp();
-            continue;
-        }
-
         Pack8 P0{0u, 0u}, P1{0u, 0u}, P2{0u, 0u};
         if (kIsMap) {
             uint32_t c4[8];
@@ -211,7 +183,54 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
             P2.hi = __shfl_up_sync(0xFFFFFFFFu, P0.hi, 2); P2.lo = __shfl_up_sync(0xFFFFFFFFu, P0.lo, 2);
             if (lane == 0) { P1 = car1; P2 = car0; }
             if (lane == 1) P2 = car1;
+            __syncwarp();  // the previous row's readers are done with s_pack
+            s_pack[lane + 2] = make_uint2(P0.hi, P0.lo);
+            if (lane < 2) s_pack[lane] = make_uint2(h.hi, h.lo);
+            __syncwarp();
         }
+        if (total <= (uint32_t)kEmitStage && base + total <= (unsigned long long)E.cap) {
+            // ---- common case: the whole row fits the staging window and the caller's buffer.  Records are staged at
+            //      the parity of their final address so that both sides of the flush are 16-byte aligned.
+            const uint32_t par = ((uint32_t)base + out_par) & 1u;
+            uint32_t sa = stage_sa + (my_off + par) * 8u;
+#pragma unroll
+            for (int wi = 0; wi < 4; wi++) {
+                uint32_t w = words[wi];
+                const int32_t eb = e0 + 2 * wi;
+                while (w) {
+                    const uint32_t t = (uint32_t)__clz((int)__brev(w));
+                    w &= w - 1u;
+                    const int32_t e = eb + (int32_t)(t >> 4);
+                    sts_v2(sa, e - 16 + (int32_t)(t & 15u), e);
+                    sa += 8u;
+                }
+            }
+            __syncwarp();
+            if (kIsMap) {
+                // ---- values, one RECORD per lane (balanced, unlike the per-position bit loops): the record itself says
+                //      which position and length it is; the contexts come from the row's packed classes in shared memory
+                const int32_t e_row = (int32_t)(E.origin + row * kMaskRow) + E.pos_base;  // end of a keyword ending at row position -1
+                for (uint32_t r = lane; r < total; r += 32) {
+                    const int2 rec = s_stage[r + par];
+                    const uint32_t pos = (uint32_t)(rec.y - e_row) - 1u;  // 0..255
+                    const uint32_t own = pos >> 3;
+                    const uint2 a0 = s_pack[own + 2], a1 = s_pack[own + 1], a2 = s_pack[own];
+                    const Pack8 Q0{a0.x, a0.y}, Q1{a1.x, a1.y}, Q2{a2.x, a2.y};
+                    __stcs(E.val_out + base + r, tier_value_rt(T, context_of(Q0, Q1, Q2, (int)(pos & 7u), b), cm, rec.y - rec.x));
+                }
+            }
+            // pairs [k_lo, k_hi) are whole; a lone head record (par == 1) and a lone tail record go out as 8-byte stores
+            int2 *g = E.pos_out + (base - par);  // 16-byte aligned
+            const uint32_t end = par + total, k_hi = end >> 1;
+            if (lane == 0 && par) __stcs(g + 1, s_stage[1]);
+            if (lane == 1 && (end & 1u)) __stcs(g + (end - 1u), s_stage[end - 1u]);
+            int4 *gp = reinterpret_cast<int4 *>(g) + par + lane;
+            const int4 *sp = reinterpret_cast<const int4 *>(s_stage) + par + lane;
+            for (uint32_t k = par + lane; k < k_hi; k += 32, gp += 32, sp += 32) __stcs(gp, *sp);
+            __syncwarp();
+            continue;
+        }
+
         for (uint32_t win = 0; win < total; win += kEmitStage) {
             if (cnt && my_off < win + kEmitStage && my_off + cnt > win) {
                 uint32_t o = my_off - win;  // wraps below zero for records of an earlier window
