@@ -289,3 +289,80 @@ def test_committed_fixture_streams(case):
         c = Collect()
         MAPS[fam](kws, values, cs, *extra).match(io.StringIO(hay), c)
         assert [v[0] for v in c.calls] == want["readable_values"]
+
+
+# ---------------------------------------------------------------- mask / scan / emit path: shapes the fuzz tests miss
+
+def _records(m, hay):
+    rec = m.match_records(hay)
+    return list(zip(rec.start.tolist(), rec.end.tolist())), (rec.value.tolist() if rec.value is not None else None)
+
+
+@pytest.mark.parametrize("alphabet,max_kw", [("ab", 16), ("acgt", 16), ("0123456789", 12), ("abcdefghijklmnopqrstuvwxyz", 12),
+                                              ("abcdefghijklmnopqrstuvwxyzABCDE", 9)])
+def test_tier_path_alphabets_and_boundary_lengths(alphabet, max_kw):
+    """Class counts 3..32 pick different K (direct-indexed levels 8..3) and LOW variants of k_tier_mask; haystack
+    lengths straddle the 8-char lane, 256-char row and 8 192-char chunk boundaries; Set and Map streams must equal
+    the oracle's, including the empty haystack."""
+    rng = random.Random(len(alphabet) * 100 + max_kw)
+    kws = sorted({_rand_word(rng, alphabet, 1 if len(alphabet) < 8 else 2, max_kw) for _ in range(400)})
+    values = list(range(len(kws)))
+    om = ora.Matcher("ahocorasick", kws, n_values=len(kws))
+    gs, gm = ac.AhoCorasickSet(kws, True), ac.AhoCorasickMap(kws, values, True)
+    sep = " " if len(alphabet) > 4 else ""
+    base = "".join(rng.choice(alphabet + sep) for _ in range(70_001))
+    for n in (0, 1, 7, 8, 9, 255, 256, 257, 511, 8191, 8192, 8193, 70_001):
+        hay = base[:n]
+        want = oracle_stream(om, hay)
+        pos, _ = _records(gs, hay)
+        assert pos == [(s, e) for s, e, _ in want], (alphabet, n)
+        pos, val = _records(gm, hay)
+        assert pos == [(s, e) for s, e, _ in want] and [int(v) for v in val] == [v for _, _, v in want], (alphabet, n)
+
+
+def test_tier_path_dense_rows_and_long_chains():
+    """'aaaa…' with nested keywords a^1..a^16 emits 16 records per position: rows overflow the staging window of
+    k_tier_emit (windowed path) and every context continues past level K (deep-probe queue runs full)."""
+    kws = ["a" * i for i in range(1, 17)] + ["ab", "ba" * 4, "b" * 11]
+    hay = "a" * 3000 + "b" * 40 + ("ab" * 700) + "a" * 513
+    want = oracle_stream(ora.Matcher("ahocorasick", kws, n_values=len(kws)), hay)
+    pos, _ = _records(ac.AhoCorasickSet(kws, True), hay)
+    assert pos == [(s, e) for s, e, _ in want] and len(pos) > 50_000
+    pos, val = _records(ac.AhoCorasickMap(kws, list(range(len(kws))), True), hay)
+    assert pos == [(s, e) for s, e, _ in want] and [int(v) for v in val] == [v for _, _, v in want]
+
+
+def test_device_range_shards_and_cap():
+    """acgpu_match_device on end-position ranges of a resident haystack (the multi-GPU shard entry): shards at odd
+    boundaries concatenate to the single stream; a capacity below the total truncates the stream, not the count."""
+    import ctypes as C
+    import torch
+    from ahocorasick_b200 import _lib
+    from ahocorasick_b200.sharding import plan_range_shards
+    c = W.config(0, scale=0.25)
+    kws = c["keywords"]
+    hay = W.make_haystack(c["spec"], 300_000)
+    want = ora.Matcher("ahocorasick", kws).match(hay)
+    want_pos = np.stack([want["start"], want["end"]], axis=1).astype(np.int32)
+    m = ac.AhoCorasickSet(kws, True)
+    lib = _lib.lib()
+    d_hay = torch.from_numpy(hay.astype(np.int16)).cuda()
+    d_pos = torch.empty((len(want) + 16, 2), dtype=torch.int32, device="cuda")
+
+    def run(lo, hi, cap):
+        tot = C.c_int64(0)
+        _lib.check(lib.acgpu_match_device(m.handle, d_hay.data_ptr(), hay.size, lo, hi, d_pos.data_ptr(), None, cap, C.byref(tot), None))
+        torch.cuda.synchronize()
+        return tot.value, d_pos[:min(tot.value, cap)].cpu().numpy()
+
+    for world in (2, 3, 8):
+        parts = []
+        for sh in plan_range_shards(hay.size, world, max_len=12, align=1 if world == 3 else 8):
+            n_sh, rec = run(sh.emit_from, sh.emit_to, len(want) + 16)
+            parts.append(rec.copy())
+        got = np.concatenate(parts, axis=0)
+        assert got.shape == want_pos.shape and np.array_equal(got, want_pos), world
+    total, rec = run(0, hay.size, 1000)
+    assert total == len(want) and np.array_equal(rec, want_pos[:1000])
+    total, rec = run(0, hay.size, 0)
+    assert total == len(want)
