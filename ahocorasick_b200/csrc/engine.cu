@@ -18,6 +18,7 @@
 #include "kernel_tier.cuh"
 #include "kernel_mask.cuh"
 #include "kernel_emit.cuh"
+#include "kernel_sel2.cuh"
 #include "tier_launch.hpp"
 
 using namespace acgpu;
@@ -131,7 +132,8 @@ int upload(Matcher *m) {
 int upload_tier(Matcher *m) {
     const TierTables &t = m->host.tier;
     m->use_tier = false;
-    if (!t.ok || m->host.family != ACGPU_AHOCORASICK) return ACGPU_OK;
+    // AhoCorasick: end masks over the reversed-keyword trie; Longest / Shortest: start masks over the forward trie
+    if (!t.ok || m->host.family == ACGPU_WHOLEWORD) return ACGPU_OK;
     const char *force = getenv("ACGPU_FORCE_GEN1");
     if (force && force[0] == '1') return ACGPU_OK;
     m->mask_smem = mask_smem_bytes(t.row_words.size());
@@ -246,20 +248,100 @@ struct RunOpts {
     int64_t *d_carry = nullptr;  // [2] int64 (selection families)
 };
 
-int launch_mask(Matcher *m, const MaskArgs &P, int grid, cudaStream_t st) {
+int launch_mask(Matcher *m, const MaskArgs &P, int grid, cudaStream_t st, bool mir = false) {
     const int low = mask_low_variant(m->tier);
     cudaError_t e;
     switch (m->tier.K) {
-    case 1: e = mask_launch_1(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
-    case 2: e = mask_launch_2(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
-    case 3: e = mask_launch_3(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
-    case 4: e = mask_launch_4(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
-    case 5: e = mask_launch_5(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
-    case 6: e = mask_launch_6(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
-    case 7: e = mask_launch_7(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
-    default: e = mask_launch_8(low, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 1: e = mask_launch_1(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 2: e = mask_launch_2(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 3: e = mask_launch_3(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 4: e = mask_launch_4(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 5: e = mask_launch_5(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 6: e = mask_launch_6(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 7: e = mask_launch_7(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    default: e = mask_launch_8(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
     }
     CU_TRY(e);
+    return ACGPU_OK;
+}
+
+// Longest / Shortest, narrow alphabets, one-shot match: start masks (mirrored k_tier_mask) -> exit maps -> scan ->
+// records (kernel_sel2.cuh)
+int enqueue_sel2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint32_t *d_val, int64_t cap,
+                 unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
+    // the mirrored kernel loads hay[n - 8 - p0, n - p0): rows start at origin <= 0 with origin = mis + n (mod 8)
+    const int64_t mis = static_cast<int64_t>((reinterpret_cast<uintptr_t>(d_hay) >> 1) & 7);
+    const int64_t r = (mis + n) & 7;
+    const int64_t origin = r ? r - 8 : 0;
+    const int64_t n_rows = (n - origin + kMaskRow - 1) / kMaskRow;
+    const int64_t n_idx = n_rows * kMaskRow;
+    const int64_t moff = n_idx - n + origin;
+    const int64_t n_tiles = (n_idx + kS2Tile - 1) / kS2Tile;
+    Scratch S;
+    const size_t o_ctr = S.reserve(256);
+    const size_t o_cnt = S.reserve(static_cast<size_t>(n_rows) * 4);
+    const size_t o_mask = S.reserve(static_cast<size_t>(n_idx) * 2);
+    const size_t o_map = S.reserve(static_cast<size_t>(n_tiles) * kS2Ent * 4);
+    const size_t o_ent = S.reserve(static_cast<size_t>(n_tiles));
+    const size_t o_base = S.reserve(static_cast<size_t>(n_tiles) * 8);
+    void *ws = nullptr;
+    CU_TRY(cudaMallocAsync(&ws, S.off, st));
+    char *w = static_cast<char *>(ws);
+    CU_TRY(cudaMemsetAsync(w + o_ctr, 0, 256, st));
+    MaskArgs P{};
+    P.hay = d_hay;
+    P.n = n;
+    P.emit_from = 0;
+    P.emit_to = n;
+    P.origin = origin;
+    P.masks = reinterpret_cast<uint32_t *>(w + o_mask);
+    P.row_count = reinterpret_cast<uint32_t *>(w + o_cnt);
+    P.ticket = reinterpret_cast<unsigned int *>(w + o_ctr);
+    P.n_rows = n_rows;
+    const int64_t n_chunks = (n_rows + kMaskChunkRows - 1) / kMaskChunkRows;
+    const int grid = static_cast<int>(std::min<int64_t>((n_chunks + kMaskWarps - 1) / kMaskWarps, m->sm_count));
+    int rc = launch_mask(m, P, grid, st, true);
+    if (rc != ACGPU_OK) return rc;
+    Sel2Args Q{};
+    Q.masks = P.masks;
+    Q.n_idx = n_idx;
+    Q.moff = moff;
+    Q.n_tiles = n_tiles;
+    Q.tile_map = reinterpret_cast<uint32_t *>(w + o_map);
+    Q.tile_entry = reinterpret_cast<uint8_t *>(w + o_ent);
+    Q.tile_base = reinterpret_cast<unsigned long long *>(w + o_base);
+    Q.total_out = d_total;
+    Q.hay = d_hay;
+    Q.n = n;
+    Q.pos_base = opt.pos_base;
+    Q.pos_out = d_pos;
+    Q.val_out = d_val;
+    Q.cap = cap;
+    const bool longest = m->dev.family == ACGPU_LONGEST;
+    const size_t smem = static_cast<size_t>(kS2SmemWords) * 4;
+    const int sgrid = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(m->sm_count) * 16));
+    if (longest)
+        k_sel2_map<kModeLongest><<<sgrid, kS2Threads, smem, st>>>(Q);
+    else
+        k_sel2_map<kModeShortest><<<sgrid, kS2Threads, smem, st>>>(Q);
+    CU_TRY(cudaGetLastError());
+    k_sel2_scan<<<1, kS2ScanThreads, 0, st>>>(Q);
+    CU_TRY(cudaGetLastError());
+    if (cap > 0) {
+        if (longest) {
+            if (m->dev.is_map)
+                k_sel2_emit<kModeLongest, true><<<sgrid, kS2Threads, smem, st>>>(m->dev, m->tier, Q);
+            else
+                k_sel2_emit<kModeLongest, false><<<sgrid, kS2Threads, smem, st>>>(m->dev, m->tier, Q);
+        } else {
+            if (m->dev.is_map)
+                k_sel2_emit<kModeShortest, true><<<sgrid, kS2Threads, smem, st>>>(m->dev, m->tier, Q);
+            else
+                k_sel2_emit<kModeShortest, false><<<sgrid, kS2Threads, smem, st>>>(m->dev, m->tier, Q);
+        }
+        CU_TRY(cudaGetLastError());
+    }
+    CU_TRY(cudaFreeAsync(ws, st));
     return ACGPU_OK;
 }
 
@@ -383,6 +465,8 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
         return ACGPU_OK;
     }
     const bool chain = A.family != ACGPU_WHOLEWORD;
+    if (chain && m->use_tier && opt.ctx == 0 && chain_n == n && opt.entry0 == 0 && !opt.d_carry)
+        return enqueue_sel2(m, d_hay, n, d_pos, d_val, cap, d_total, st, opt);
     const int32_t M = A.max_len + 1;
     const int64_t n_tiles = (chain_n + kSelTile - 1) / kSelTile;
     const int64_t n_groups = (n_tiles + kSelGroup - 1) / kSelGroup;
@@ -899,7 +983,7 @@ int acgpu_launches_per_match(uint64_t handle) {
     switch (m->host.family) {
     case ACGPU_AHOCORASICK: return m->use_tier ? 3 : 1;
     case ACGPU_WHOLEWORD: return 2;
-    default: return 6;
+    default: return m->use_tier ? 4 : 6;  // one-shot matches; the streaming path always takes the 6-launch route
     }
 }
 

@@ -83,6 +83,7 @@ __device__ __forceinline__ uint32_t ldg_u32_if(const void *p, bool on) {
 
 // scaled classes (class * 4) of the 8 chars at [p0, p0 + 8); v is the prefetched vector (valid when the 8 chars lie
 // inside [0, n)); positions outside [0, n) give class 0
+template <bool MIR = false>
 __device__ __forceinline__ void classify8x4(const DevAutomaton &A, const uint16_t *hay, int64_t n, int64_t p0, const uint4 v,
                                             const uint8_t *s_cls4, uint32_t (&c4)[8]) {
     if (p0 >= 0 && p0 + 8 <= n) {
@@ -101,9 +102,22 @@ __device__ __forceinline__ void classify8x4(const DevAutomaton &A, const uint16_
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int64_t p = p0 + j;
-            c4[j] = (p >= 0 && p < n) ? (uint32_t)__ldg(&A.cls[__ldg(&hay[p])]) * 4u : 0u;
+            c4[j] = (p >= 0 && p < n) ? (uint32_t)__ldg(&A.cls[__ldg(&hay[MIR ? n - 1 - p : p])]) * 4u : 0u;
         }
     }
+}
+
+// The 8 chars of kernel positions [p0, p0 + 8).  MIR: kernel position q' is haystack position n - 1 - q' (the haystack is
+// read right to left, so an END anchor of the kernel is a START anchor of the haystack and the tables are those of the
+// forward trie): one aligned 128-bit load of hay[n - 8 - p0, n - p0), chars reversed in registers.
+__device__ __forceinline__ uint32_t swap16(uint32_t x) { return __byte_perm(x, 0u, 0x1032u); }
+template <bool MIR>
+__device__ __forceinline__ uint4 load8(const uint16_t *hay, int64_t n, int64_t p0, bool on) {
+    if (MIR) {
+        const uint4 v = ldcs_v4_if(hay + (n - 8 - p0), on);
+        return make_uint4(swap16(v.w), swap16(v.z), swap16(v.y), swap16(v.x));
+    }
+    return ldcs_v4_if(hay + p0, on);
 }
 
 // The classes of 8 consecutive positions packed b bits each, most recent lowest, as two words of 4 classes.
@@ -144,7 +158,7 @@ __device__ __noinline__ void deep_resolve(const uint4 *buckets, unsigned long lo
     }
 }
 
-template <int K, int LOW>
+template <int K, int LOW, bool MIR>
 __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomaton A, const DevTier T, const MaskArgs P) {
     extern __shared__ __align__(16) uint32_t s_mem[];
     uint8_t *s_cls4 = reinterpret_cast<uint8_t *>(s_mem);
@@ -186,7 +200,7 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
     };
     auto fetch = [&](int64_t row, int64_t row_end) -> uint4 {
         const int64_t p0 = P.origin + row * kMaskRow + (int64_t)lane * 8;
-        return ldcs_v4_if(P.hay + p0, row < row_end && p0 >= 0 && p0 + 8 <= P.n);
+        return load8<MIR>(P.hay, P.n, p0, row < row_end && p0 >= 0 && p0 + 8 <= P.n);
     };
 
     while (true) {
@@ -203,9 +217,9 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
             Pack8 h{0u, 0u};
             if (lane < 2) {
                 const int64_t p0 = P.origin + row0 * kMaskRow - 16 + (int64_t)lane * 8;
-                const uint4 hv = ldcs_v4_if(P.hay + p0, p0 >= 0 && p0 + 8 <= P.n);
+                const uint4 hv = load8<MIR>(P.hay, P.n, p0, p0 >= 0 && p0 + 8 <= P.n);
                 uint32_t h4[8];
-                classify8x4(A, P.hay, P.n, p0, hv, s_cls4, h4);
+                classify8x4<MIR>(A, P.hay, P.n, p0, hv, s_cls4, h4);
                 h = pack8(h4, sh);
             }
             car0.hi = __shfl_sync(0xFFFFFFFFu, h.hi, 0); car0.lo = __shfl_sync(0xFFFFFFFFu, h.lo, 0);
@@ -216,7 +230,7 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
             const int64_t r_lo = P.origin + row * kMaskRow;  // first position of the row
             const int64_t p0 = r_lo + (int64_t)lane * 8;
             uint32_t c4[8];
-            classify8x4(A, P.hay, P.n, p0, v, s_cls4, c4);
+            classify8x4<MIR>(A, P.hay, P.n, p0, v, s_cls4, c4);
             v = vn;
             vn = vnn;
             const Pack8 P0 = pack8(c4, sh);
@@ -298,10 +312,14 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
             pm &= vm;
             // ---- store the shallow masks and the row count; deep hits are OR-ed in later by this same warp
             const uint4 mw = make_uint4(m[0] | m[1] << 16, m[2] | m[3] << 16, m[4] | m[5] << 16, m[6] | m[7] << 16);
-            *reinterpret_cast<uint4 *>(P.masks + ((size_t)row * 32 + lane) * 4) = mw;
+            if (MIR)  // masks are stored in haystack order: the array is the kernel's, reversed
+                *reinterpret_cast<uint4 *>(P.masks + ((size_t)(P.n_rows - 1 - row) * 32 + (31 - lane)) * 4) =
+                    make_uint4(swap16(mw.w), swap16(mw.z), swap16(mw.y), swap16(mw.x));
+            else
+                *reinterpret_cast<uint4 *>(P.masks + ((size_t)row * 32 + lane) * 4) = mw;
             const uint32_t cnt = __popc(mw.x) + __popc(mw.y) + __popc(mw.z) + __popc(mw.w);
             const uint32_t row_total = __reduce_add_sync(0xFFFFFFFFu, cnt);
-            if (lane == 0) P.row_count[row] = row_total;
+            if (lane == 0) P.row_count[MIR ? P.n_rows - 1 - row : row] = row_total;
             __syncwarp();
             // ---- queue the continuing contexts; probe whenever 32 are waiting
             while (true) {
@@ -313,7 +331,8 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
                     pm &= pm - 1u;
                     const uint32_t slot = q_cnt + __popc(bal & lt_mask);
                     s_qctx[slot] = context_of(P0, P1, P2, j, b);
-                    s_qpos[slot] = (uint32_t)(row * kMaskRow) + lane * 8 + j;
+                    const uint32_t qp = (uint32_t)(row * kMaskRow) + lane * 8 + j;
+                    s_qpos[slot] = MIR ? (uint32_t)(P.n_rows * kMaskRow) - 1u - qp : qp;
                 }
                 q_cnt += __popc(bal);
                 __syncwarp();

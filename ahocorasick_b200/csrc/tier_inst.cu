@@ -33,11 +33,11 @@ cudaError_t launch_windowed(Kern kern, int grid, int block, size_t smem, const L
     return cudaLaunchKernelEx(&cfg, kern, A, T, P);
 }
 
-template <int LOW>
+template <int LOW, bool MIR>
 cudaError_t launch_mask_variant(const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, const L2Window &W,
                                 cudaStream_t st) {
     static size_t attr_smem[64] = {0};
-    const void *fn = reinterpret_cast<const void *>(k_tier_mask<TIER_K, LOW>);
+    const void *fn = reinterpret_cast<const void *>(k_tier_mask<TIER_K, LOW, MIR>);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -46,7 +46,7 @@ cudaError_t launch_mask_variant(const DevAutomaton &A, const DevTier &T, const M
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_smem[dev] = smem;
     }
-    return launch_windowed(k_tier_mask<TIER_K, LOW>, grid, kMaskThreads, smem, W, st, A, T, P);
+    return launch_windowed(k_tier_mask<TIER_K, LOW, MIR>, grid, kMaskThreads, smem, W, st, A, T, P);
 }
 
 }  // namespace
@@ -54,13 +54,20 @@ cudaError_t launch_mask_variant(const DevAutomaton &A, const DevTier &T, const M
 #define ACGPU_CAT2(a, b) a##b
 #define ACGPU_CAT(a, b) ACGPU_CAT2(a, b)
 
-cudaError_t ACGPU_CAT(mask_launch_, TIER_K)(int low, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid,
+cudaError_t ACGPU_CAT(mask_launch_, TIER_K)(int low, bool mir, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid,
                                             size_t smem, const L2Window &W, cudaStream_t st) {
     if (TIER_K == 1) low = 2;
+    if (mir) {
+        switch (low) {
+        case 0: return launch_mask_variant<0, true>(A, T, P, grid, smem, W, st);
+        case 1: return launch_mask_variant<1, true>(A, T, P, grid, smem, W, st);
+        default: return launch_mask_variant<2, true>(A, T, P, grid, smem, W, st);
+        }
+    }
     switch (low) {
-    case 0: return launch_mask_variant<0>(A, T, P, grid, smem, W, st);
-    case 1: return launch_mask_variant<1>(A, T, P, grid, smem, W, st);
-    default: return launch_mask_variant<2>(A, T, P, grid, smem, W, st);
+    case 0: return launch_mask_variant<0, false>(A, T, P, grid, smem, W, st);
+    case 1: return launch_mask_variant<1, false>(A, T, P, grid, smem, W, st);
+    default: return launch_mask_variant<2, false>(A, T, P, grid, smem, W, st);
     }
 }
 

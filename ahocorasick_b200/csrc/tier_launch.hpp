@@ -18,10 +18,11 @@ struct L2Window {
     float hit_ratio = 1.0f;
 };
 
+// mir: the kernel reads the haystack right to left (start anchors over the forward trie: Longest / Shortest).
 // low: 0 = every level below K may hold keywords, 1 = only level K-1 does (and rides in the level-K rows), 2 = none does.
 // k_tier_mask<K, LOW> (kernel_mask.cuh): persistent, one CTA per SM; no inter-CTA waiting, plain launch.
 #define ACGPU_DECLARE_MASK(k) \
-    cudaError_t mask_launch_##k(int low, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, const L2Window &W, cudaStream_t st);
+    cudaError_t mask_launch_##k(int low, bool mir, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, const L2Window &W, cudaStream_t st);
 ACGPU_DECLARE_MASK(1)
 ACGPU_DECLARE_MASK(2)
 ACGPU_DECLARE_MASK(3)

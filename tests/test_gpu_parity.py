@@ -168,8 +168,8 @@ def test_baseline_configs_scaled(cfg, gen1, monkeypatch):
     """The five BASELINE.json configs at a size the oracle finishes in seconds: identical ordered streams.
     gen1=True forces the general anchored-trie kernel where the tiered kernel would be chosen."""
     if gen1:
-        if cfg in (2, 3):
-            pytest.skip("tiered kernel only exists for the AhoCorasick family")
+        if cfg == 3:
+            pytest.skip("the tiered kernels do not serve WholeWord")
         monkeypatch.setenv("ACGPU_FORCE_GEN1", "1")
     c = W.config(cfg, scale=0.02 if cfg != 0 else 0.25)
     n = min(c["n"], 2_000_000)
@@ -366,3 +366,92 @@ def test_device_range_shards_and_cap():
     assert total == len(want) and np.array_equal(rec, want_pos[:1000])
     total, rec = run(0, hay.size, 0)
     assert total == len(want)
+
+
+# ---------------------------------------------------------------- Longest / Shortest on the start-mask path (kernel_sel2.cuh)
+
+@pytest.mark.parametrize("family", ["longest", "shortest"])
+@pytest.mark.parametrize("alphabet,max_kw", [("ab", 16), ("acgt", 13), ("abcdefghijklmnopqrstuvwxyz", 12)])
+def test_sel2_alphabets_and_boundary_lengths(family, alphabet, max_kw):
+    """Mirrored k_tier_mask + exit maps: haystack lengths straddle the 8-char lane group, the 32-position lane
+    sub-tile, the 256-position row, the 1 024-position warp and the 8 192-position tile; Set and Map streams must
+    equal the oracle's.  gen-1 (k_fwd_v + k_sel_*) is checked on the same inputs."""
+    rng = random.Random(len(alphabet) * 1000 + max_kw + len(family))
+    kws = sorted({_rand_word(rng, alphabet, 1 if len(alphabet) < 8 else 2, max_kw) for _ in range(300)})
+    values = list(range(len(kws)))
+    om = ora.Matcher(family, kws, n_values=len(kws))
+    gs, gm = SETS[family](kws, True), MAPS[family](kws, values, True)
+    sep = " " if len(alphabet) > 4 else ""
+    base = "".join(rng.choice(alphabet + sep) for _ in range(70_001))
+    for n in (0, 1, 7, 8, 9, 31, 32, 33, 255, 256, 257, 1023, 1024, 1025, 8191, 8192, 8193, 8207, 16385, 70_001):
+        hay = base[:n]
+        want = oracle_stream(om, hay)
+        pos, _ = _records(gs, hay)
+        assert pos == [(s, e) for s, e, _ in want], (alphabet, n)
+        pos, val = _records(gm, hay)
+        assert pos == [(s, e) for s, e, _ in want] and [int(v) for v in val] == [v for _, _, v in want], (alphabet, n)
+
+
+@pytest.mark.parametrize("family", ["longest", "shortest"])
+def test_sel2_dense_periodic_and_sparse(family):
+    """Chains that never resynchronise (periodic text), one match per position (nested a^k), sparse text where whole
+    lanes / warps / tiles are skipped, and keywords of the maximum length 16 ending at the very end."""
+    cases = [
+        (["a" * i for i in range(1, 17)] + ["ab", "ba" * 4, "b" * 11], "a" * 3000 + "b" * 40 + ("ab" * 700) + "a" * 513),
+        (["ab", "ba", "aba", "bab", "abab" * 4], "ab" * 40000),
+        (["needle", "nee", "dle", "edl"], ("x" * 20011 + "needle") * 9 + "x" * 7 + "nee"),
+        (["abcdefghijklmnop", "p", "op", "ponm"], ("abcdefghijklmnop" * 2100)),
+        (["aab", "ab", "b", "aaaaaaaaab"], ("a" * 9 + "b") * 5000 + "aaaa"),
+    ]
+    for kws, hay in cases:
+        want = oracle_stream(ora.Matcher(family, kws, n_values=len(kws)), hay)
+        pos, val = _records(MAPS[family](kws, list(range(len(kws))), True), hay)
+        assert pos == [(s, e) for s, e, _ in want], (family, kws)
+        assert [int(v) for v in val] == [v for _, _, v in want], (family, kws)
+        assert len(pos) >= 10
+
+
+@pytest.mark.parametrize("family", ["longest", "shortest"])
+def test_sel2_many_tiles_scan_slices(family):
+    """10^7 chars = 1 221 tiles: every k_sel2_scan thread composes a slice of several tiles."""
+    c = W.config(2, scale=0.02)
+    hay = W.make_haystack(c["spec"], 10_000_000)
+    kws = c["keywords"]
+    want = ora.Matcher(family, kws).match(hay)
+    rec = SETS[family](kws, True).match_records(hay)
+    assert len(rec) == len(want) and len(want) > 100_000
+    assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"])
+
+
+@pytest.mark.parametrize("family", ["longest", "shortest"])
+def test_sel2_device_unaligned_and_cap(family):
+    """acgpu_match_device on a resident haystack whose first char sits at every 16-byte misalignment (the mirrored
+    kernel derives its row origin from the pointer and the length), and with a record capacity below the total."""
+    import ctypes as C
+    import torch
+    from ahocorasick_b200 import _lib
+    c = W.config(2, scale=0.01)
+    kws = c["keywords"]
+    full = W.make_haystack(c["spec"], 100_000 + 16)
+    m = SETS[family](kws, True)
+    om = ora.Matcher(family, kws)
+    lib = _lib.lib()
+    d_full = torch.from_numpy(full.astype(np.int16)).cuda()
+    d_pos = torch.empty((60_000, 2), dtype=torch.int32, device="cuda")
+    for off in range(8):
+        for n in (100_000, 99_997):
+            hay = full[off:off + n]
+            want = om.match(hay)
+            want_pos = np.stack([want["start"], want["end"]], axis=1).astype(np.int32)
+            tot = C.c_int64(0)
+            _lib.check(lib.acgpu_match_device(m.handle, d_full.data_ptr() + 2 * off, n, 0, n, d_pos.data_ptr(), None, 60_000,
+                                              C.byref(tot), None))
+            torch.cuda.synchronize()
+            assert tot.value == len(want), (off, n)
+            assert np.array_equal(d_pos[:tot.value].cpu().numpy(), want_pos), (off, n)
+    tot = C.c_int64(0)
+    _lib.check(lib.acgpu_match_device(m.handle, d_full.data_ptr(), 100_000, 0, 100_000, d_pos.data_ptr(), None, 777, C.byref(tot), None))
+    torch.cuda.synchronize()
+    want = om.match(full[:100_000])
+    assert tot.value == len(want)
+    assert np.array_equal(d_pos[:777].cpu().numpy(), np.stack([want["start"], want["end"]], axis=1).astype(np.int32)[:777])
