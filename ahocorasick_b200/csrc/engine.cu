@@ -284,6 +284,10 @@ int enqueue_sel2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint
     const size_t o_map = S.reserve(static_cast<size_t>(n_tiles) * kS2Ent * 4);
     const size_t o_ent = S.reserve(static_cast<size_t>(n_tiles));
     const size_t o_base = S.reserve(static_cast<size_t>(n_tiles) * 8);
+    const int64_t n_groups = (n_tiles + kS2Group - 1) / kS2Group;
+    const size_t o_gmap = S.reserve(static_cast<size_t>(n_groups) * kS2Ent * 4);
+    const size_t o_gent = S.reserve(static_cast<size_t>(n_groups));
+    const size_t o_gbase = S.reserve(static_cast<size_t>(n_groups) * 8);
     void *ws = nullptr;
     CU_TRY(cudaMallocAsync(&ws, S.off, st));
     char *w = static_cast<char *>(ws);
@@ -310,6 +314,10 @@ int enqueue_sel2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint
     Q.tile_map = reinterpret_cast<uint32_t *>(w + o_map);
     Q.tile_entry = reinterpret_cast<uint8_t *>(w + o_ent);
     Q.tile_base = reinterpret_cast<unsigned long long *>(w + o_base);
+    Q.n_groups = n_groups;
+    Q.group_map = reinterpret_cast<uint32_t *>(w + o_gmap);
+    Q.group_entry = reinterpret_cast<uint8_t *>(w + o_gent);
+    Q.group_base = reinterpret_cast<unsigned long long *>(w + o_gbase);
     Q.total_out = d_total;
     Q.hay = d_hay;
     Q.n = n;
@@ -325,21 +333,22 @@ int enqueue_sel2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint
     else
         k_sel2_map<kModeShortest><<<sgrid, kS2Threads, smem, st>>>(Q);
     CU_TRY(cudaGetLastError());
-    k_sel2_scan<<<1, kS2ScanThreads, 0, st>>>(Q);
+    k_sel2_group<<<static_cast<unsigned>(n_groups), 32, 0, st>>>(Q);
+    CU_TRY(cudaGetLastError());
+    k_sel2_top<<<1, 1024, static_cast<size_t>(n_groups) * kS2Ent * 4, st>>>(Q);
+    CU_TRY(cudaGetLastError());
+    k_sel2_tiles<<<static_cast<unsigned>(n_groups), 32, 0, st>>>(Q);
     CU_TRY(cudaGetLastError());
     if (cap > 0) {
-        if (longest) {
-            if (m->dev.is_map)
-                k_sel2_emit<kModeLongest, true><<<sgrid, kS2Threads, smem, st>>>(m->dev, m->tier, Q);
-            else
-                k_sel2_emit<kModeLongest, false><<<sgrid, kS2Threads, smem, st>>>(m->dev, m->tier, Q);
-        } else {
-            if (m->dev.is_map)
-                k_sel2_emit<kModeShortest, true><<<sgrid, kS2Threads, smem, st>>>(m->dev, m->tier, Q);
-            else
-                k_sel2_emit<kModeShortest, false><<<sgrid, kS2Threads, smem, st>>>(m->dev, m->tier, Q);
-        }
+        if (longest)
+            k_sel2_emit<kModeLongest><<<sgrid, kS2Threads, smem, st>>>(Q);
+        else
+            k_sel2_emit<kModeShortest><<<sgrid, kS2Threads, smem, st>>>(Q);
         CU_TRY(cudaGetLastError());
+        if (m->dev.is_map) {
+            k_sel2_values<<<m->sm_count * 16, 256, 0, st>>>(m->dev, m->tier, Q, d_total);
+            CU_TRY(cudaGetLastError());
+        }
     }
     CU_TRY(cudaFreeAsync(ws, st));
     return ACGPU_OK;
@@ -566,6 +575,7 @@ int ensure_device(Matcher *m) {
         }
         CU_TRY(cudaFuncSetAttribute(k_sel_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelEmitSmem));
         CU_TRY(cudaFuncSetAttribute(k_sel_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelEmitSmem));
+        CU_TRY(cudaFuncSetAttribute(k_sel2_top, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         m->sel_attr_set = true;
     }
     return ACGPU_OK;
@@ -983,7 +993,7 @@ int acgpu_launches_per_match(uint64_t handle) {
     switch (m->host.family) {
     case ACGPU_AHOCORASICK: return m->use_tier ? 3 : 1;
     case ACGPU_WHOLEWORD: return 2;
-    default: return m->use_tier ? 4 : 6;  // one-shot matches; the streaming path always takes the 6-launch route
+    default: return 6;  // one-shot matches; the streaming path always takes the 6-launch route
     }
 }
 

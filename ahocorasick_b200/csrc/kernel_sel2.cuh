@@ -4,10 +4,12 @@
 //                                     at s (forward-trie tier tables; the kernel reads the haystack right to left).
 //   k_sel2_map                        per tile of 8 192 positions: for every possible chain entry offset, where the chain
 //                                     leaves the tile and how many matches it emits on the way (an "exit map").
-//   k_sel2_scan                       composes the tile maps left to right: every tile learns its true entry offset and the
-//                                     index of its first record; also the total.
-//   k_sel2_emit<isMap>                rebuilds the tile's maps, walks the true chain and writes the records at their final
+//   k_sel2_group / _top / _tiles      compose the tile maps left to right (groups of 256 tiles, one thread over the group
+//                                     maps, back down): every tile learns its true entry offset and the index of its
+//                                     first record; also the total.
+//   k_sel2_emit                       rebuilds the tile's maps, walks the true chain and writes the records at their final
 //                                     offsets (ascending start = the reference's listener order).
+//   k_sel2_values (Maps)              one record per thread: the value index of every record.
 //
 // The sequential selection of the reference (LongestMatchSet.java:192-265 + SetMatchQueue.java:45-95;
 // ShortestMatchSet.java:182-260) is a chain  pos -> J(pos):
@@ -31,7 +33,7 @@ constexpr int kS2Sub = 32;                       // positions per lane
 constexpr int kS2Tile = kS2Threads * kS2Sub;     // positions per CTA tile
 constexpr int kS2Ent = 16;                       // entry offsets of a map (exit offsets are < max_len <= 16)
 constexpr int kS2LmapStride = 17;                // words per lane in the entry-window array (conflict-free both ways)
-constexpr int kS2ScanThreads = 512;
+constexpr int kS2Group = 256;                    // tiles per composition group
 // shared words: [lane entry windows: positions 0..15 of every lane][positions 16..31, position-major]
 constexpr int kS2LmapWords = kS2Threads * kS2LmapStride;
 constexpr int kS2SmemWords = kS2LmapWords + 16 * kS2Threads;
@@ -44,6 +46,10 @@ struct Sel2Args {
     uint32_t *tile_map;             // [n_tiles][16]  exit offset | matches << 8, per entry offset
     uint8_t *tile_entry;            // [n_tiles]
     unsigned long long *tile_base;  // [n_tiles] index of the tile's first record
+    int64_t n_groups;
+    uint32_t *group_map;            // [n_groups][16]
+    uint8_t *group_entry;           // [n_groups]
+    unsigned long long *group_base; // [n_groups]
     unsigned long long *total_out;
     const uint16_t *hay;
     int64_t n;
@@ -84,7 +90,8 @@ __device__ __forceinline__ void s2_load(const Sel2Args &P, int64_t tile, uint32_
     }
 }
 
-// Right-to-left resolution of the lane's 32 positions into s_w (see the word layout above).
+// Right-to-left resolution of the lane's 32 positions into s_w (see the word layout above).  Branch-free: every position
+// costs the same ~20 instructions in every lane (the divergent version ran at 17 of 32 lanes).
 template <int MODE>
 __device__ __forceinline__ void s2_resolve(const uint32_t (&mw)[16], const uint32_t (&hw)[8], uint32_t *s_w) {
     const int tid = threadIdx.x;
@@ -93,41 +100,41 @@ __device__ __forceinline__ void s2_resolve(const uint32_t (&mw)[16], const uint3
 #pragma unroll
         for (int k = 15; k >= 0; k--) {
             const uint32_t m = (hw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
-            if (m) {
-                const uint32_t e = (uint32_t)(32 + k) + (uint32_t)__clz((int)m) - 15u;  // + 16 - (highest set bit)
-                if (e <= h_end) { h_end = e; h_start = 32 + k; }                        // ties: leftmost start
-            }
+            const uint32_t e = (uint32_t)(32 + k) + (uint32_t)__clz((int)m) - 15u;  // + 16 - (highest set bit)
+            const bool better = m != 0u && e <= h_end;                              // ties: leftmost start
+            h_end = better ? e : h_end;
+            h_start = better ? (uint32_t)(32 + k) : h_start;
         }
     }
-    uint32_t word = 32u << 10;  // nothing to the right: skip to the end of the sub-tile, no match
-    uint32_t b_end = 0xFFFFu, b_start = 0;
+    // state: the chain standing here jumps to nx (32 = leaves the sub-tile without a match) emitting (st, nx) if em
+    uint32_t nx = 32u, st = 0u, em = 0u;
+    uint32_t b_end = 0xFFFFu, b_start = 0u;
+    const uint32_t base_lo = (uint32_t)tid * kS2LmapStride, base_hi = (uint32_t)kS2LmapWords - 16u * kS2Threads + (uint32_t)tid;
 #pragma unroll
     for (int k = 31; k >= 0; k--) {
         const uint32_t m = (mw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
-        if (m) {
-            uint32_t nx, st;
-            if (MODE == kModeLongest) {
-                nx = (uint32_t)k + 17u - (uint32_t)__ffs((int)m);  // + 16 - (lowest set bit)
-                st = k;
-            } else {
-                const uint32_t e = (uint32_t)k + (uint32_t)__clz((int)m) - 15u;
-                if (e <= b_end) { b_end = e; b_start = k; }
-                const bool halo = h_end < b_end;
-                nx = halo ? h_end : b_end;
-                st = halo ? h_start : b_start;
-            }
-            uint32_t x, c;
-            if (nx >= 32u) {
-                x = nx - 32u;
-                c = 1u;
-            } else {
-                const uint32_t t = s_w[s2_idx((int)nx, tid)];
-                x = t & 15u;
-                c = ((t >> 4) & 63u) + 1u;
-            }
-            word = x | (c << 4) | (nx << 10) | (st << 16) | (1u << 22);
+        const bool has = m != 0u;
+        if (MODE == kModeLongest) {
+            const uint32_t e = (uint32_t)k + 17u - (uint32_t)__ffs((int)m);  // + 16 - (lowest set bit)
+            nx = has ? e : nx;
+            st = has ? (uint32_t)k : st;
+        } else {
+            const uint32_t e = (uint32_t)k + (uint32_t)__clz((int)m) - 15u;
+            const bool better = has && e <= b_end;
+            b_end = better ? e : b_end;
+            b_start = better ? (uint32_t)k : b_start;
+            const bool halo = h_end < b_end;
+            nx = halo ? h_end : b_end;
+            st = halo ? h_start : b_start;
+            nx = b_end == 0xFFFFu ? 32u : nx;  // no candidate inside the sub-tile: skip to its end (the halo is the next lane's)
         }
-        s_w[s2_idx(k, tid)] = word;
+        em |= has ? 1u : 0u;
+        const uint32_t nc = min(nx, 31u);
+        const uint32_t t = s_w[nc < 16u ? base_lo + nc : base_hi + nc * kS2Threads];
+        const bool out = nx >= 32u;
+        const uint32_t x = out ? nx - 32u : (t & 15u);
+        const uint32_t c = out ? em : ((t >> 4) & 63u) + 1u;
+        s_w[s2_idx(k, tid)] = x | (c << 4) | (nx << 10) | (st << 16) | (em << 22);
     }
 }
 
@@ -137,13 +144,17 @@ __device__ __forceinline__ uint32_t s2_idx_rt(uint32_t k, int tid) {
 }
 
 // Warp maps: s_wmap[warp * 16 + o] = exit offset | matches << 8 of the warp's 1 024 positions entered at offset o.
-__device__ __forceinline__ void s2_warp_maps(const uint32_t *s_w, uint32_t *s_wmap) {
+// TRAJ: also records, for every entry offset o, where the chain enters each lane and how many matches it has emitted by
+// then (s_traj[(warp * 32 + l) * 16 + o] = entry | matches << 4), so the emit kernel needs no second walk.
+template <bool TRAJ>
+__device__ __forceinline__ void s2_warp_maps(const uint32_t *s_w, uint32_t *s_wmap, uint16_t *s_traj) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __syncwarp();
     if (lane < kS2Ent) {
         uint32_t cur = lane, cnt = 0;
 #pragma unroll 4
         for (int l = 0; l < 32; l++) {
+            if (TRAJ) s_traj[(warp * 32 + l) * kS2Ent + lane] = (uint16_t)(cur | (cnt << 4));
             const uint32_t t = s_w[(warp * 32 + l) * kS2LmapStride + cur];
             cur = t & 15u;
             cnt += (t >> 4) & 63u;
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(kS2Threads, 4) k_sel2_map(const Sel2Args P) {
         s2_load(P, tile, mw, hw);
         __syncthreads();  // the previous tile's readers are done
         s2_resolve<MODE>(mw, hw, s_w);
-        s2_warp_maps(s_w, s_wmap);
+        s2_warp_maps<false>(s_w, s_wmap, nullptr);
         __syncthreads();
         if (tid < kS2Ent) {
             uint32_t cur = tid, cnt = 0;
@@ -177,71 +188,107 @@ __global__ void __launch_bounds__(kS2Threads, 4) k_sel2_map(const Sel2Args P) {
     }
 }
 
-// One block: thread j composes the maps of a contiguous slice of tiles for all 16 entry offsets, thread 0 then follows
-// the one true chain over the 512 slice maps, and every thread hands its tiles their entry offset and record base.
-__global__ void __launch_bounds__(kS2ScanThreads, 1) k_sel2_scan(const Sel2Args P) {
-    __shared__ uint8_t s_exit[kS2ScanThreads][kS2Ent];
-    __shared__ uint32_t s_cnt[kS2ScanThreads][kS2Ent + 1];
-    __shared__ uint8_t s_in[kS2ScanThreads];
-    __shared__ unsigned long long s_base[kS2ScanThreads];
-    const int tid = threadIdx.x;
-    const int64_t per = (P.n_tiles + kS2ScanThreads - 1) / kS2ScanThreads;
-    const int64_t lo = min(P.n_tiles, (int64_t)tid * per), hi = min(P.n_tiles, lo + per);
-    {
-        uint32_t cur[kS2Ent], cnt[kS2Ent];
+// ---- composing the tile maps: groups of 256 tiles (one warp each), then the group maps (one thread), then back down.
+// A map row is 16 words: exit offset | matches << 8 for entry offsets 0..15.
+
+// one warp: the rows of 32 consecutive maps staged in shared memory
+__device__ __forceinline__ void s2_stage_rows(const uint32_t *rows, int64_t first, int64_t n_rows, uint32_t *s_rows) {
+    const int lane = threadIdx.x & 31;
 #pragma unroll
-        for (int o = 0; o < kS2Ent; o++) { cur[o] = o; cnt[o] = 0; }
-        for (int64_t t = lo; t < hi; t++) {
-            const uint32_t *row = P.tile_map + t * kS2Ent;
-#pragma unroll
-            for (int o = 0; o < kS2Ent; o++) {
-                const uint32_t w = __ldg(row + cur[o]);
-                cur[o] = w & 0xFFu;
-                cnt[o] += w >> 8;
-            }
-        }
-#pragma unroll
-        for (int o = 0; o < kS2Ent; o++) { s_exit[tid][o] = (uint8_t)cur[o]; s_cnt[tid][o] = cnt[o]; }
+    for (int k = 0; k < 16; k++) {
+        const int64_t w = first * kS2Ent + k * 32 + lane;
+        s_rows[k * 32 + lane] = w < n_rows * kS2Ent ? __ldg(rows + w) : ((uint32_t)lane & 15u);  // past the end: identity, no matches
     }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(32) k_sel2_group(const Sel2Args P) {
+    __shared__ uint32_t s_rows[32 * kS2Ent];
+    const int lane = threadIdx.x;
+    const int64_t g = blockIdx.x;
+    uint32_t cur = lane & 15u, cnt = 0;
+    for (int c = 0; c < kS2Group / 32; c++) {
+        const int64_t first = g * kS2Group + c * 32;
+        if (first >= P.n_tiles) break;
+        __syncwarp();
+        s2_stage_rows(P.tile_map, first, P.n_tiles, s_rows);
+#pragma unroll 8
+        for (int l = 0; l < 32; l++) {
+            const uint32_t t = s_rows[l * kS2Ent + cur];
+            cur = t & 0xFFu;
+            cnt += t >> 8;
+        }
+    }
+    if (lane < kS2Ent) P.group_map[g * kS2Ent + lane] = cur | (cnt << 8);
+}
+
+// one thread follows the true chain over the group maps (at most 1 024 groups for a 2^31-char haystack)
+__global__ void __launch_bounds__(1024, 1) k_sel2_top(const Sel2Args P) {
+    extern __shared__ __align__(16) uint32_t s_gm[];
+    for (int64_t i = threadIdx.x; i < P.n_groups * kS2Ent; i += blockDim.x) s_gm[i] = P.group_map[i];
     __syncthreads();
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         uint32_t cur = 0;  // the chain starts at index 0 (entries before haystack position 0 are empty)
         unsigned long long acc = 0;
-        for (int j = 0; j < kS2ScanThreads; j++) {
-            s_in[j] = (uint8_t)cur;
-            s_base[j] = acc;
-            acc += s_cnt[j][cur];
-            cur = s_exit[j][cur];
+        for (int64_t g = 0; g < P.n_groups; g++) {
+            P.group_entry[g] = (uint8_t)cur;
+            P.group_base[g] = acc;
+            const uint32_t t = s_gm[g * kS2Ent + cur];
+            cur = t & 0xFFu;
+            acc += t >> 8;
         }
         *P.total_out = acc;
     }
-    __syncthreads();
-    uint32_t cur = s_in[tid];
-    unsigned long long acc = s_base[tid];
-    for (int64_t t = lo; t < hi; t++) {
-        P.tile_entry[t] = (uint8_t)cur;
-        P.tile_base[t] = acc;
-        const uint32_t w = __ldg(P.tile_map + t * kS2Ent + cur);
-        cur = w & 0xFFu;
-        acc += w >> 8;
+}
+
+// one warp per group: every tile learns its entry offset and the index of its first record
+__global__ void __launch_bounds__(32) k_sel2_tiles(const Sel2Args P) {
+    __shared__ uint32_t s_rows[32 * kS2Ent];
+    __shared__ uint8_t s_ent[32];
+    __shared__ unsigned long long s_bas[32];
+    const int lane = threadIdx.x;
+    const int64_t g = blockIdx.x;
+    uint32_t cur = P.group_entry[g];
+    unsigned long long acc = P.group_base[g];
+    for (int c = 0; c < kS2Group / 32; c++) {
+        const int64_t first = g * kS2Group + c * 32;
+        if (first >= P.n_tiles) break;
+        __syncwarp();
+        s2_stage_rows(P.tile_map, first, P.n_tiles, s_rows);
+        if (lane == 0) {
+            for (int l = 0; l < 32; l++) {
+                s_ent[l] = (uint8_t)cur;
+                s_bas[l] = acc;
+                const uint32_t t = s_rows[l * kS2Ent + cur];
+                cur = t & 0xFFu;
+                acc += t >> 8;
+            }
+        }
+        cur = __shfl_sync(0xFFFFFFFFu, cur, 0);
+        acc = __shfl_sync(0xFFFFFFFFu, acc, 0);
+        __syncwarp();
+        if (first + lane < P.n_tiles) {
+            P.tile_entry[first + lane] = s_ent[lane];
+            P.tile_base[first + lane] = s_bas[lane];
+        }
     }
 }
 
-template <int MODE, bool kIsMap>
-__global__ void __launch_bounds__(kS2Threads, 4) k_sel2_emit(const DevAutomaton A, const DevTier T, const Sel2Args P) {
+template <int MODE>
+__global__ void __launch_bounds__(kS2Threads, 4) k_sel2_emit(const Sel2Args P) {
     extern __shared__ __align__(16) uint32_t s_w[];
     __shared__ uint32_t s_wmap[(kS2Threads / 32) * kS2Ent];
     __shared__ uint32_t s_wentry[kS2Threads / 32];
     __shared__ unsigned long long s_wbase[kS2Threads / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = T.b;
-    const uint32_t cm = (1u << b) - 1u;
+    __shared__ uint16_t s_traj[kS2Threads * kS2Ent];
+    const int tid = threadIdx.x, warp = tid >> 5;
     for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         uint32_t mw[16], hw[8];
         s2_load(P, tile, mw, hw);
+        const int64_t a = tile * kS2Tile + (int64_t)tid * kS2Sub - P.moff;  // haystack position of the lane's first index
         __syncthreads();  // the previous tile's readers are done
         s2_resolve<MODE>(mw, hw, s_w);
-        s2_warp_maps(s_w, s_wmap);
+        s2_warp_maps<true>(s_w, s_wmap, s_traj);
         __syncthreads();
         if (tid == 0) {
             uint32_t cur = P.tile_entry[tile];
@@ -256,45 +303,43 @@ __global__ void __launch_bounds__(kS2Threads, 4) k_sel2_emit(const DevAutomaton 
             }
         }
         __syncthreads();
-        // lane entries: lane 0 follows the warp's chain through the 32 lane maps
-        uint32_t my_entry = 0, my_off = 0;
-        {
-            uint32_t cur = s_wentry[warp], acc = 0;
-            if (lane == 0) {
-                for (int l = 0; l < 32; l++) {
-                    const uint32_t t = s_w[(warp * 32 + l) * kS2LmapStride + cur];
-                    // park (entry, offset) of lane l in the unused 17th word of its entry window
-                    s_w[(warp * 32 + l) * kS2LmapStride + 16] = cur | (acc << 8);
-                    cur = t & 15u;
-                    acc += (t >> 4) & 63u;
-                }
-            }
-            __syncwarp();
-            const uint32_t eo = s_w[tid * kS2LmapStride + 16];
-            my_entry = eo & 0xFFu;
-            my_off = eo >> 8;
-        }
-        unsigned long long idx = s_wbase[warp] + my_off;
-        const int64_t a = tile * kS2Tile + (int64_t)tid * kS2Sub - P.moff;  // haystack position of the lane's first index
-        uint32_t p = my_entry;
+        const uint32_t eo = s_traj[tid * kS2Ent + s_wentry[warp]];
+        unsigned long long idx = s_wbase[warp] + (eo >> 4);
+        uint32_t p = eo & 15u;
+        const int32_t a32 = (int32_t)a + P.pos_base;
         while (p < 32u) {
             const uint32_t w = s_w[s2_idx_rt(p, tid)];
             if ((w >> 22) & 1u) {
-                if (idx < (unsigned long long)P.cap) {
-                    const int64_t st = a + ((w >> 16) & 63u), en = a + ((w >> 10) & 63u);
-                    __stcs(&P.pos_out[idx], make_int2((int32_t)st + P.pos_base, (int32_t)en + P.pos_base));
-                    if (kIsMap) {
-                        unsigned long long ctx = 0;
-                        const int d = (int)(en - st);
-                        for (int i = 0; i < d; i++)
-                            ctx |= (unsigned long long)__ldg(&A.cls[__ldg(&P.hay[st + i])]) << (b * i);
-                        __stcs(&P.val_out[idx], tier_value_rt(T, ctx, cm, d));
-                    }
-                }
+                if (idx < (unsigned long long)P.cap)
+                    __stcs(&P.pos_out[idx], make_int2(a32 + (int32_t)((w >> 16) & 63u), a32 + (int32_t)((w >> 10) & 63u)));
                 ++idx;
             }
             p = (w >> 10) & 63u;
         }
+    }
+}
+
+// Maps: one record per thread (balanced; every look-up of the warp is in flight at once, unlike inside the chain walk):
+// the keyword's classes are packed from the haystack (first char lowest, the order the forward-trie tables use) and
+// resolved through the tier tables.
+__global__ void __launch_bounds__(256) k_sel2_values(const DevAutomaton A, const DevTier T, const Sel2Args P, const unsigned long long *total) {
+    __shared__ uint8_t s_cls[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = (uint8_t)((__ldg(&T.cls8[i >> 2]) >> ((i & 3) * 8)) & 0xFFu);
+    __syncthreads();
+    const int b = T.b;
+    const uint32_t cm = (1u << b) - 1u;
+    const unsigned long long n_rec = min(*total, (unsigned long long)P.cap);
+    for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (unsigned long long)gridDim.x * blockDim.x) {
+        const int2 rec = __ldcs(&P.pos_out[r]);
+        const int64_t st = (int64_t)(rec.x - P.pos_base);
+        const int d = rec.y - rec.x;
+        unsigned long long ctx = 0;
+        for (int i = 0; i < d; i++) {
+            const uint32_t ch = __ldg(&P.hay[st + i]);
+            const uint32_t c = ch < 256u ? (uint32_t)s_cls[ch] : (uint32_t)__ldg(&A.cls[ch]);
+            ctx |= (unsigned long long)c << (b * i);
+        }
+        __stcs(&P.val_out[r], tier_value_rt(T, ctx, cm, d));
     }
 }
 
