@@ -191,13 +191,39 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
         if (a.is_map && d <= K && (inf & kInfoTerminal)) t.shallow_val[t.val_off[d] + radix[id]] = a.node_value[id];
     }
     // ---- path-compressed deep table
+    // ---- Map values of the keywords longer than K
+    t.n_vbuckets = 1;
+    t.vbuckets.assign(8, 0xFFFFFFFFu);
+    if (a.is_map && n_deep > 0) {
+        uint64_t n_keys = 0;
+        for (int64_t id = 1; id < n; id++) n_keys += depth[id] > K && (a.node_info[id] & kInfoTerminal);
+        const uint64_t nvb = std::max<uint64_t>(4, (n_keys * 10 + 10) / 11);
+        if (nvb > 0x7FFFFFFFull) return;
+        t.n_vbuckets = static_cast<uint32_t>(nvb);
+        t.vseed = 0xD6E8FEB86659FD93ull;
+        t.vbuckets.assign(nvb * 8, 0xFFFFFFFFu);  // empty: key = all ones (no key has length bits 1111 and all classes set: b * max_len <= 60 leaves them apart)
+        for (int64_t id = 1; id < n; id++) {
+            if (depth[id] <= K || !(a.node_info[id] & kInfoTerminal)) continue;
+            const uint64_t key = packed[id] | (static_cast<uint64_t>(depth[id] - 1) << 60);
+            const uint64_t hs = deep_hash64(key, t.vseed);
+            uint32_t bk = static_cast<uint32_t>(((hs & 0xFFFFFFFFull) * nvb) >> 32);
+            while (true) {
+                uint32_t *e = &t.vbuckets[static_cast<size_t>(bk) * 8];
+                int k = (e[0] == 0xFFFFFFFFu && e[1] == 0xFFFFFFFFu) ? 0 : ((e[4] == 0xFFFFFFFFu && e[5] == 0xFFFFFFFFu) ? 1 : -1);
+                if (k >= 0) {
+                    e[4 * k] = static_cast<uint32_t>(key);
+                    e[4 * k + 1] = static_cast<uint32_t>(key >> 32);
+                    e[4 * k + 2] = a.node_value[id];
+                    e[4 * k + 3] = 0;
+                    break;
+                }
+                bk = bk + 1 == t.n_vbuckets ? 0 : bk + 1;
+            }
+        }
+    }
     if (n_deep == 0) {
         t.n_buckets = 1;
         t.buckets.assign(8, 0);
-        if (a.is_map) {
-            t.deep_valbase.assign(2, 0);
-            t.deep_val.assign(1, kNone);
-        }
         t.ok = true;
         return;
     }
@@ -214,23 +240,17 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
         uint64_t key;   // packed context of the head
         uint64_t zw;    // chain | L << 40 | terminal flags << 44
         uint32_t kids;  // child mask of the chain's last node
-        uint32_t val_begin, val_count;
     };
     std::vector<Head> heads;
-    std::vector<uint32_t> vals;
     for (int64_t id = 1; id < n; id++) {  // ids ascend from parent to child, so continuation heads are marked in time
         if (depth[id] <= K || !is_head[id]) continue;
         Head h;
         h.key = packed[id];
-        h.val_begin = static_cast<uint32_t>(vals.size());
         uint64_t chain = 0, term = 0;
         uint32_t cur = static_cast<uint32_t>(id);
         int L = 0;
         while (true) {
-            if (a.node_info[cur] & kInfoTerminal) {
-                term |= 1ull << L;
-                if (a.is_map) vals.push_back(a.node_value[cur]);
-            }
+            if (a.node_info[cur] & kInfoTerminal) term |= 1ull << L;
             if (child_count[cur] != 1 || L == kTierChainMax) break;
             const uint32_t nxt = only_child[cur];
             chain |= static_cast<uint64_t>(node_cls[nxt]) << (b * L);
@@ -240,7 +260,6 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
         if (child_count[cur] == 1) is_head[only_child[cur]] = 1;  // chain outgrew the entry: continue in a new head
         h.zw = chain | (static_cast<uint64_t>(L) << 40) | (term << 44);
         h.kids = kids[cur];
-        h.val_count = static_cast<uint32_t>(vals.size()) - h.val_begin;
         heads.push_back(h);
     }
     t.n_heads = heads.size();
@@ -252,7 +271,6 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
     for (int attempt = 0; attempt < 16; attempt++) {
         t.hash_seed = 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(attempt + 1);
         t.buckets.assign(n_buckets * 8, 0);
-        if (a.is_map) t.deep_valbase.assign(n_buckets * 2, 0);
         bool clash = false;
         for (size_t i = 0; i < heads.size() && !clash; i++) {
             const Head &h = heads[i];
@@ -275,7 +293,6 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
                     e[4 * free_slot + 1] = h.kids;
                     e[4 * free_slot + 2] = static_cast<uint32_t>(h.zw);
                     e[4 * free_slot + 3] = static_cast<uint32_t>(h.zw >> 32);
-                    if (a.is_map) t.deep_valbase[static_cast<size_t>(bk) * 2 + free_slot] = h.val_begin;
                     break;
                 }
                 bk = bk + 1 == t.n_buckets ? 0 : bk + 1;
@@ -285,14 +302,54 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
         // that bucket was full when the earlier key passed it - and full buckets never change, so checking at
         // insertion time against every bucket passed (done above) is sufficient.
         if (!clash) {
-            if (a.is_map) {
-                t.deep_val.swap(vals);
-                if (t.deep_val.empty()) t.deep_val.push_back(kNone);
-            }
             t.ok = true;
             return;
         }
     }
+}
+
+// WholeWord hash tables: one entry per distinct (trimmed, folded) keyword = per terminal node of the forward trie
+void build_ww(HostAutomaton &a, const std::vector<uint8_t> &wc, const std::vector<uint32_t> &node_parent,
+              const std::vector<uint16_t> &node_cls) {
+    WwTables &w = a.ww;
+    w.ok = false;
+    if (!a.has_other || a.n_classes >= 32768 || a.max_len > kWwMaxLen) return;
+    w.wcls.resize(65536);
+    for (uint32_t c = 0; c < 65536; c++) w.wcls[c] = static_cast<uint16_t>(a.cls[c] | (wc[c] ? 0x8000u : 0u));
+    uint64_t n_keys = 0;
+    for (int64_t id = 1; id < a.n_nodes; id++) n_keys += a.node_info[id] & kInfoTerminal;
+    const uint64_t nb = std::max<uint64_t>(4, n_keys * 2);  // two entries per bucket: load factor 0.25 (most probes are misses)
+    if (nb > 0x7FFFFFFFull) return;
+    w.n_buckets = static_cast<uint32_t>(nb);
+    w.buckets.assign(nb * 8, 0xFFFFFFFFu);
+    std::vector<uint16_t> tmp;
+    for (int64_t id = 1; id < a.n_nodes; id++) {
+        if (!(a.node_info[id] & kInfoTerminal)) continue;
+        tmp.clear();
+        for (uint32_t cur = static_cast<uint32_t>(id); cur != 0; cur = node_parent[cur]) tmp.push_back(node_cls[cur]);
+        std::reverse(tmp.begin(), tmp.end());
+        WwHash h;
+        for (uint16_t c : tmp) h.add(c);
+        h.finish(static_cast<uint32_t>(tmp.size()));
+        if (w.pool.size() + tmp.size() > 0xFFFFFFF0ull) return;
+        const uint32_t off = static_cast<uint32_t>(w.pool.size());
+        w.pool.insert(w.pool.end(), tmp.begin(), tmp.end());
+        uint32_t bk = static_cast<uint32_t>((static_cast<uint64_t>(h.spread()) * nb) >> 32);
+        while (true) {
+            uint32_t *e = &w.buckets[static_cast<size_t>(bk) * 8];
+            const int k = e[2] == 0xFFFFFFFFu ? 0 : (e[6] == 0xFFFFFFFFu ? 1 : -1);
+            if (k >= 0) {
+                e[4 * k] = h.h1;
+                e[4 * k + 1] = static_cast<uint32_t>(tmp.size());
+                e[4 * k + 2] = off;
+                e[4 * k + 3] = a.node_value[id];
+                break;
+            }
+            bk = bk + 1 == w.n_buckets ? 0 : bk + 1;
+        }
+    }
+    if (w.pool.empty()) w.pool.push_back(0);
+    w.ok = true;
 }
 
 }  // namespace
@@ -465,6 +522,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
         a.edges[i] = Edge{e.parent, e.cls, e.child, a.node_info[e.child]};
     }
     build_tiers(a, node_parent, node_cls);
+    if (family == 3) build_ww(a, wc, node_parent, node_cls);
     return a;
 }
 

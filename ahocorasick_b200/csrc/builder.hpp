@@ -87,12 +87,52 @@ struct TierTables {
     uint64_t hash_seed = 0;
     uint64_t n_deep = 0;             // trie nodes deeper than K
     uint64_t n_heads = 0;            // entries of the compressed table
-    // Map values: shallow levels indexed like the bit tables; deep values are stored per entry, consecutively in
-    // chain order (terminal nodes only), starting at deep_valbase[bucket * 2 + entry]
+    // Map values: shallow levels indexed like the bit tables; a keyword longer than K is looked up by its whole packed
+    // context in a bucketed hash table (two 16-byte entries {key lo, key hi, value, 0} per 32-byte bucket; key = packed
+    // classes | (length - 1) << 60, compared exactly) - one gather per record
     std::vector<uint32_t> shallow_val;
     uint64_t val_off[10] = {0};
-    std::vector<uint32_t> deep_valbase;
-    std::vector<uint32_t> deep_val;
+    std::vector<uint32_t> vbuckets;  // 8 words per bucket
+    uint32_t n_vbuckets = 0;
+    uint64_t vseed = 0;
+};
+
+// WholeWord (generation 2): a word is a keyword iff its class string is in a hash table - no trie walk.
+//   wcls[65536]  code unit -> class (15 bits, case folding folded in) | word-char flag << 15
+//   buckets      two 16-byte entries {h1, length, pool offset, value} per 32-byte bucket, empty: pool offset = 0xFFFFFFFF
+//   pool         the keywords' classes (u16 each) - compared exactly after a hash and length match
+constexpr int kWwMaxLen = 255;
+struct WwTables {
+    bool ok = false;
+    std::vector<uint16_t> wcls;
+    std::vector<uint32_t> buckets;
+    uint32_t n_buckets = 0;
+    std::vector<uint16_t> pool;
+};
+
+// hash of a class string, shared by the builder and k_ww_scan (FNV-1a over the classes, murmur-style finish)
+struct WwHash {
+    uint32_t h1 = 0x811C9DC5u;
+#ifdef __CUDACC__
+    __host__ __device__
+#endif
+    inline void add(uint32_t c) { h1 = (h1 ^ c) * 0x01000193u; }
+#ifdef __CUDACC__
+    __host__ __device__
+#endif
+    inline void finish(uint32_t len) {
+        h1 ^= len * 0x27D4EB2Fu;
+        h1 ^= h1 >> 16;
+        h1 *= 0x85EBCA6Bu;
+        h1 ^= h1 >> 13;
+    }
+#ifdef __CUDACC__
+    __host__ __device__
+#endif
+    inline uint32_t spread() const {
+        uint32_t x = h1 * 0xC2B2AE35u;
+        return x ^ (x >> 16);
+    }
 };
 
 inline uint64_t deep_hash64(uint64_t key, uint64_t seed) {
@@ -125,6 +165,7 @@ struct HostAutomaton {
     std::vector<uint8_t> node_info;    // n_nodes
     std::vector<uint32_t> depth_count; // nodes per depth (diagnostics / tiering)
     TierTables tier;                   // generation-2 tables (tier.ok == false: not applicable)
+    WwTables ww;                       // WholeWord hash tables (ww.ok == false: not applicable)
 };
 
 // Throws IllegalArgument with the reference's message for WholeWord keywords holding non-word chars.

@@ -19,6 +19,7 @@
 #include "kernel_mask.cuh"
 #include "kernel_emit.cuh"
 #include "kernel_sel2.cuh"
+#include "kernel_ww.cuh"
 #include "tier_launch.hpp"
 
 using namespace acgpu;
@@ -82,6 +83,10 @@ struct Matcher {
     void *d_tier_blob = nullptr;
     L2Window l2win;         // child masks + deep table, kept L2-resident across the streaming traffic
     size_t mask_smem = 0;
+    // WholeWord hash tables (kernel_ww.cuh)
+    bool use_ww = false;
+    DevWw ww{};
+    void *d_ww_blob = nullptr;
 };
 
 Matcher *as_matcher(uint64_t h) {
@@ -149,8 +154,7 @@ int upload_tier(Matcher *m) {
     size_t o_kid = reserve(t.kidmask.size() * 4);
     size_t o_deep = reserve(t.buckets.size() * 4);
     size_t o_sval = reserve(t.shallow_val.size() * 4);
-    size_t o_dvb = reserve(t.deep_valbase.size() * 4);
-    size_t o_dval = reserve(t.deep_val.size() * 4);
+    size_t o_vb = reserve(t.vbuckets.size() * 4);
     CU_TRY(cudaMalloc(&m->d_tier_blob, off));
     m->table_bytes += static_cast<int64_t>(off);
     char *b = static_cast<char *>(m->d_tier_blob);
@@ -161,8 +165,7 @@ int upload_tier(Matcher *m) {
     if (!t.kidmask.empty()) CU_TRY(cudaMemcpy(b + o_kid, t.kidmask.data(), t.kidmask.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(b + o_deep, t.buckets.data(), t.buckets.size() * 4, cudaMemcpyHostToDevice));
     if (!t.shallow_val.empty()) CU_TRY(cudaMemcpy(b + o_sval, t.shallow_val.data(), t.shallow_val.size() * 4, cudaMemcpyHostToDevice));
-    if (!t.deep_valbase.empty()) CU_TRY(cudaMemcpy(b + o_dvb, t.deep_valbase.data(), t.deep_valbase.size() * 4, cudaMemcpyHostToDevice));
-    if (!t.deep_val.empty()) CU_TRY(cudaMemcpy(b + o_dval, t.deep_val.data(), t.deep_val.size() * 4, cudaMemcpyHostToDevice));
+    if (!t.vbuckets.empty()) CU_TRY(cudaMemcpy(b + o_vb, t.vbuckets.data(), t.vbuckets.size() * 4, cudaMemcpyHostToDevice));
     DevTier &d = m->tier;
     d.cls8 = reinterpret_cast<const uint32_t *>(b + o_cls8);
     d.kidmask = t.kidmask.empty() ? nullptr : reinterpret_cast<const uint32_t *>(b + o_kid);
@@ -183,8 +186,9 @@ int upload_tier(Matcher *m) {
     d.buckets = reinterpret_cast<const uint4 *>(b + o_deep);
     d.hash_seed = t.hash_seed;
     d.shallow_val = reinterpret_cast<const uint32_t *>(b + o_sval);
-    d.deep_valbase = reinterpret_cast<const uint32_t *>(b + o_dvb);
-    d.deep_val = reinterpret_cast<const uint32_t *>(b + o_dval);
+    d.vbuckets = reinterpret_cast<const uint4 *>(b + o_vb);
+    d.vseed = t.vseed;
+    d.n_vbuckets = t.n_vbuckets;
     d.row_words = reinterpret_cast<const uint32_t *>(b + o_rows);
     d.n_row_words = static_cast<uint32_t>(t.row_words.size());
     for (int j = 0; j < 10; j++) d.row_off[j] = t.row_off[j];
@@ -217,6 +221,36 @@ int upload_tier(Matcher *m) {
         d.val_off[j] = t.val_off[j];
     }
     m->use_tier = true;
+    return ACGPU_OK;
+}
+
+int upload_ww(Matcher *m) {
+    const WwTables &t = m->host.ww;
+    m->use_ww = false;
+    if (!t.ok || m->host.family != ACGPU_WHOLEWORD) return ACGPU_OK;
+    const char *force = getenv("ACGPU_FORCE_GEN1");
+    if (force && force[0] == '1') return ACGPU_OK;
+    size_t off = 0;
+    auto reserve = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + std::max<size_t>(bytes, 16), 256);
+        return o;
+    };
+    const size_t o_wcls = reserve(65536 * 2);
+    const size_t o_bk = reserve(t.buckets.size() * 4);
+    const size_t o_pool = reserve(t.pool.size() * 2);
+    CU_TRY(cudaMalloc(&m->d_ww_blob, off));
+    m->table_bytes += static_cast<int64_t>(off);
+    char *b = static_cast<char *>(m->d_ww_blob);
+    CU_TRY(cudaMemcpy(b + o_wcls, t.wcls.data(), 65536 * 2, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(b + o_bk, t.buckets.data(), t.buckets.size() * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(b + o_pool, t.pool.data(), t.pool.size() * 2, cudaMemcpyHostToDevice));
+    m->ww.wcls = reinterpret_cast<const uint16_t *>(b + o_wcls);
+    m->ww.buckets = reinterpret_cast<const uint4 *>(b + o_bk);
+    m->ww.pool = reinterpret_cast<const uint16_t *>(b + o_pool);
+    m->ww.n_buckets = t.n_buckets;
+    m->ww.max_len = m->host.max_len;
+    m->use_ww = true;
     return ACGPU_OK;
 }
 
@@ -346,7 +380,7 @@ int enqueue_sel2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint
             k_sel2_emit<kModeShortest><<<sgrid, kS2Threads, smem, st>>>(Q);
         CU_TRY(cudaGetLastError());
         if (m->dev.is_map) {
-            k_sel2_values<<<m->sm_count * 16, 256, 0, st>>>(m->dev, m->tier, Q, d_total);
+            k_sel2_values<<<sgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q);
             CU_TRY(cudaGetLastError());
         }
     }
@@ -474,6 +508,44 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
         return ACGPU_OK;
     }
     const bool chain = A.family != ACGPU_WHOLEWORD;
+    if (!chain && m->use_ww) {
+        // WholeWord: one launch (kernel_ww.cuh); words starting in [ctx, chain_n) are reported
+        const int64_t dom_lo = opt.ctx, dom_hi = chain_n;
+        const int64_t mis = static_cast<int64_t>((reinterpret_cast<uintptr_t>(d_hay) >> 1) & 7);
+        const int64_t origin = ((dom_lo + mis) & ~int64_t(7)) - mis;  // <= dom_lo, hay + origin 16-byte aligned
+        const int64_t n_tiles = dom_hi > dom_lo ? (dom_hi - origin + kWwTile - 1) / kWwTile : 0;
+        if (n_tiles == 0) {
+            CU_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
+            return ACGPU_OK;
+        }
+        const size_t bytes = 256 + static_cast<size_t>(n_tiles) * 8;
+        void *ws = nullptr;
+        CU_TRY(cudaMallocAsync(&ws, bytes, st));
+        CU_TRY(cudaMemsetAsync(ws, 0, bytes, st));
+        WwArgs W{};
+        W.hay = d_hay;
+        W.n = n;
+        W.dom_lo = dom_lo;
+        W.dom_hi = dom_hi;
+        W.origin = origin;
+        W.n_tiles = n_tiles;
+        W.pos_base = opt.pos_base;
+        W.pos_out = d_pos;
+        W.val_out = d_val;
+        W.cap = cap;
+        W.total_out = d_total;
+        W.tile_counter = static_cast<unsigned int *>(ws);
+        W.status = reinterpret_cast<unsigned long long *>(static_cast<char *>(ws) + 256);
+        const size_t smem = static_cast<size_t>(kWwTile + 16 * ((m->ww.max_len + 1 + 15) / 16)) * 2;
+        const int grid = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(m->sm_count) * 6));
+        if (A.is_map)
+            k_ww_scan<true><<<grid, kWwThreads, smem, st>>>(m->ww, W);
+        else
+            k_ww_scan<false><<<grid, kWwThreads, smem, st>>>(m->ww, W);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaFreeAsync(ws, st));
+        return ACGPU_OK;
+    }
     if (chain && m->use_tier && opt.ctx == 0 && chain_n == n && opt.entry0 == 0 && !opt.d_carry)
         return enqueue_sel2(m, d_hay, n, d_pos, d_val, cap, d_total, st, opt);
     const int32_t M = A.max_len + 1;
@@ -946,10 +1018,12 @@ int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t 
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) m->sm_count = prop.multiProcessorCount;
         rc = upload(m);
         if (rc == ACGPU_OK) rc = upload_tier(m);
+        if (rc == ACGPU_OK) rc = upload_ww(m);
     }
     if (rc != ACGPU_OK) {
         if (m->tier.kid_tex) cudaDestroyTextureObject(m->tier.kid_tex);
         if (m->d_tier_blob) cudaFree(m->d_tier_blob);
+        if (m->d_ww_blob) cudaFree(m->d_ww_blob);
         if (m->d_blob) cudaFree(m->d_blob);
         delete m;
         return rc;
@@ -970,6 +1044,7 @@ int acgpu_destroy(uint64_t handle) {
     if (m->d_blob) cudaFree(m->d_blob);
     if (m->tier.kid_tex) cudaDestroyTextureObject(m->tier.kid_tex);
     if (m->d_tier_blob) cudaFree(m->d_tier_blob);
+    if (m->d_ww_blob) cudaFree(m->d_ww_blob);
     m->magic = 0;
     delete m;
     return ACGPU_OK;
@@ -992,7 +1067,7 @@ int acgpu_launches_per_match(uint64_t handle) {
     if (!m) return fail(ACGPU_EINVAL, "bad handle");
     switch (m->host.family) {
     case ACGPU_AHOCORASICK: return m->use_tier ? 3 : 1;
-    case ACGPU_WHOLEWORD: return 2;
+    case ACGPU_WHOLEWORD: return m->use_ww ? 1 : 2;
     default: return 6;  // one-shot matches; the streaming path always takes the 6-launch route
     }
 }

@@ -91,17 +91,20 @@ __device__ __forceinline__ uint32_t tier_value_rt(const DevTier &T, unsigned lon
         for (int i = 1; i <= d; i++) idx += ((uint32_t)(ctx >> (T.b * (i - 1))) & cm) * T.pow_c[i];
         return __ldg(&T.shallow_val[T.val_off[d] + idx]);
     }
-    int hd = K + 1;  // walk the chain heads down to the one whose chain covers depth d
-    while (true) {
-        uint32_t slot;
-        const uint4 e = deep_probe(T, ctx & ((1ull << (T.b * hd)) - 1ull), slot);
-        const int L = (int)(e.w >> 8) & 15;
-        if (d <= hd + L) {
-            const uint32_t term = (e.w >> 12) & 0x1FFu;
-            return __ldg(&T.deep_val[__ldg(&T.deep_valbase[slot]) + __popc(term & ((1u << (d - hd)) - 1u))]);
-        }
-        hd += L + 1;
+    // longer keywords: one probe of the keyword -> value table (the record is a real match, so the key exists)
+    const unsigned long long key = (ctx & ((1ull << (T.b * d)) - 1ull)) | ((unsigned long long)(d - 1) << 60);
+    const unsigned long long h = deep_hash64_d(key, T.vseed);
+    uint32_t bucket = __umulhi((uint32_t)h, T.n_vbuckets);
+    const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
+    for (uint32_t tries = 0; tries < T.n_vbuckets; tries++) {
+        const uint4 *q = T.vbuckets + (size_t)bucket * 2;
+        const uint4 e0 = __ldg(q);
+        if (e0.x == klo && e0.y == khi) return e0.z;
+        const uint4 e1 = __ldg(q + 1);
+        if (e1.x == klo && e1.y == khi) return e1.z;
+        bucket = bucket + 1u == T.n_vbuckets ? 0u : bucket + 1u;
     }
+    return kNoneD;
 }
 
 // Masks -> records.  A warp takes rows round-robin (the next row's masks and offsets are prefetched while the current

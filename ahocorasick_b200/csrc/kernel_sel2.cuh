@@ -319,27 +319,69 @@ __global__ void __launch_bounds__(kS2Threads, 4) k_sel2_emit(const Sel2Args P) {
     }
 }
 
-// Maps: one record per thread (balanced; every look-up of the warp is in flight at once, unlike inside the chain walk):
-// the keyword's classes are packed from the haystack (first char lowest, the order the forward-trie tables use) and
-// resolved through the tier tables.
-__global__ void __launch_bounds__(256) k_sel2_values(const DevAutomaton A, const DevTier T, const Sel2Args P, const unsigned long long *total) {
+// ---- Maps.  The records of a tile are consecutive (tile_base), so one CTA per tile packs the classes of the tile's
+// 8 192 + 32 positions into a bit stream in shared memory (b bits per position, every position classified once) and then
+// takes one record per thread: the keyword's context (its packed classes, first char lowest - the order the forward-trie
+// tables use) is three word loads and two funnel shifts, the value one probe of the tier tables.
+__device__ __forceinline__ void s2_pack_classes(const DevAutomaton &A, const uint16_t *hay, int64_t n, int64_t a, int b,
+                                                const uint8_t *s_cls, uint32_t *dst) {
+    // 32 positions starting at haystack position a (a 16-byte aligned address when inside the haystack) -> b words at dst
+    unsigned long long acc = 0;
+    int fill = 0, o = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int64_t p0 = a + q * 8;
+        uint32_t ch[8];
+        if (p0 >= 0 && p0 + 8 <= n) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(hay + p0));
+            ch[0] = v.x & 0xFFFFu; ch[1] = v.x >> 16; ch[2] = v.y & 0xFFFFu; ch[3] = v.y >> 16;
+            ch[4] = v.z & 0xFFFFu; ch[5] = v.z >> 16; ch[6] = v.w & 0xFFFFu; ch[7] = v.w >> 16;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) ch[j] = (p0 + j >= 0 && p0 + j < n) ? (uint32_t)__ldg(&hay[p0 + j]) : 0x10000u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t c = ch[j] < 256u ? (uint32_t)s_cls[ch[j]] : (ch[j] < 0x10000u ? (uint32_t)__ldg(&A.cls[ch[j]]) : 0u);
+            acc |= (unsigned long long)c << fill;
+            fill += b;
+            if (fill >= 32) {
+                dst[o++] = (uint32_t)acc;
+                acc >>= 32;
+                fill -= 32;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kS2Threads) k_sel2_values(const DevAutomaton A, const DevTier T, const Sel2Args P) {
+    __shared__ uint32_t s_bits[(kS2Threads + 1) * 5 + 3];
     __shared__ uint8_t s_cls[256];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = (uint8_t)((__ldg(&T.cls8[i >> 2]) >> ((i & 3) * 8)) & 0xFFu);
-    __syncthreads();
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += kS2Threads) s_cls[i] = (uint8_t)((__ldg(&T.cls8[i >> 2]) >> ((i & 3) * 8)) & 0xFFu);
     const int b = T.b;
     const uint32_t cm = (1u << b) - 1u;
-    const unsigned long long n_rec = min(*total, (unsigned long long)P.cap);
-    for (unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += (unsigned long long)gridDim.x * blockDim.x) {
-        const int2 rec = __ldcs(&P.pos_out[r]);
-        const int64_t st = (int64_t)(rec.x - P.pos_base);
-        const int d = rec.y - rec.x;
-        unsigned long long ctx = 0;
-        for (int i = 0; i < d; i++) {
-            const uint32_t ch = __ldg(&P.hay[st + i]);
-            const uint32_t c = ch < 256u ? (uint32_t)s_cls[ch] : (uint32_t)__ldg(&A.cls[ch]);
-            ctx |= (unsigned long long)c << (b * i);
+    const unsigned long long n_rec = min(*P.total_out, (unsigned long long)P.cap);
+    for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        const unsigned long long r0 = min(P.tile_base[tile], n_rec);
+        const unsigned long long r1 = tile + 1 < P.n_tiles ? min(P.tile_base[tile + 1], n_rec) : n_rec;
+        if (r0 >= r1) continue;  // uniform over the block
+        const int64_t a0 = tile * kS2Tile - P.moff;  // haystack position of the tile's first index
+        __syncthreads();  // the previous tile's readers are done (and s_cls is written)
+        s2_pack_classes(A, P.hay, P.n, a0 + (int64_t)tid * kS2Sub, b, s_cls, s_bits + tid * b);
+        if (tid == 0) s2_pack_classes(A, P.hay, P.n, a0 + kS2Tile, b, s_cls, s_bits + kS2Threads * b);
+        __syncthreads();
+        const int32_t a32 = (int32_t)a0 + P.pos_base;
+        for (unsigned long long r = r0 + tid; r < r1; r += kS2Threads) {
+            const int2 rec = __ldcs(&P.pos_out[r]);
+            const uint32_t d = (uint32_t)(rec.y - rec.x);
+            const uint32_t bit = (uint32_t)(rec.x - a32) * (uint32_t)b;
+            const uint32_t *q = s_bits + (bit >> 5);
+            const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+            const uint32_t lo = __funnelshift_r(w0, w1, bit & 31u), hi = __funnelshift_r(w1, w2, bit & 31u);
+            const unsigned long long ctx = (((unsigned long long)hi << 32) | lo) & ((1ull << (d * (uint32_t)b)) - 1ull);
+            __stcs(&P.val_out[r], tier_value_rt(T, ctx, cm, (int)d));
         }
-        __stcs(&P.val_out[r], tier_value_rt(T, ctx, cm, d));
     }
 }
 

@@ -19,8 +19,9 @@ struct DevTier {
     cudaTextureObject_t kid_tex; // the same table as a linear texture (k_tier_mask gathers it through the TEX pipe)
     const uint4 *buckets;        // deep table: 2 entries per 32-byte bucket, see TierTables in builder.hpp
     const uint32_t *shallow_val;
-    const uint32_t *deep_valbase;  // [bucket * 2 + entry] -> first value of the entry's chain in deep_val
-    const uint32_t *deep_val;
+    const uint4 *vbuckets;       // Map values of keywords longer than K: {key lo, key hi, value, 0}, 2 per bucket
+    unsigned long long vseed;
+    uint32_t n_vbuckets;
     unsigned long long hash_seed;
     uint32_t n_row_words;
     uint32_t row_off[10];

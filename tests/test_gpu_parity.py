@@ -168,8 +168,6 @@ def test_baseline_configs_scaled(cfg, gen1, monkeypatch):
     """The five BASELINE.json configs at a size the oracle finishes in seconds: identical ordered streams.
     gen1=True forces the general anchored-trie kernel where the tiered kernel would be chosen."""
     if gen1:
-        if cfg == 3:
-            pytest.skip("the tiered kernels do not serve WholeWord")
         monkeypatch.setenv("ACGPU_FORCE_GEN1", "1")
     c = W.config(cfg, scale=0.02 if cfg != 0 else 0.25)
     n = min(c["n"], 2_000_000)
@@ -455,3 +453,38 @@ def test_sel2_device_unaligned_and_cap(family):
     want = om.match(full[:100_000])
     assert tot.value == len(want)
     assert np.array_equal(d_pos[:777].cpu().numpy(), np.stack([want["start"], want["end"]], axis=1).astype(np.int32)[:777])
+
+
+# ---------------------------------------------------------------- WholeWord on the hash path (kernel_ww.cuh)
+
+@pytest.mark.parametrize("cs", [True, False])
+def test_ww_hash_path_shapes(cs):
+    """Words that straddle the 4 096-position tiles, words longer than every keyword, keywords up to 200 chars (the
+    right context staged per tile grows with max_len), words at both ends of the haystack, non-ASCII letters, words
+    that share a hash bucket's probe path, and a dictionary where every word of the text is a keyword (dense output)."""
+    rng = random.Random(4242 + cs)
+    alphabet = "abcdefgXYZ0123456789-_" + "βΒжЖé"
+    kws = sorted({_rand_word(rng, alphabet, 1, 9) for _ in range(3000)})
+    kws += ["q" * 200, "Ab" * 60, "z" * 17]
+    words = kws + [_rand_word(rng, alphabet, 1, 12) for _ in range(2000)] + ["q" * 201, "q" * 199, "Z" * 17, "z" * 18]
+    seps = [" ", ", ", ".", "\n", " ; ", "(", ")", "  "]
+    parts, total = [], 0
+    while total < 120_000:
+        w = rng.choice(words)
+        sp = rng.choice(seps)
+        parts.append(w + sp)
+        total += len(w) + len(sp)
+    body = "".join(parts)
+    for hay in (body, body.rstrip(" ,.;()\n") , "q" * 200, "", " ", "ab", body[:4096], body[:4097], body[1:8193]):
+        om = ora.Matcher("wholeword", kws, n_values=len(kws), case_sensitive=cs)
+        want = oracle_stream(om, hay)
+        pos, val = _records(ac.WholeWordMatchMap(kws, list(range(len(kws))), cs), hay)
+        assert pos == [(s, e) for s, e, _ in want], (cs, len(hay))
+        assert [int(v) for v in val] == [v for _, _, v in want], (cs, len(hay))
+        pos, _ = _records(ac.WholeWordMatchSet(kws, cs), hay)
+        assert pos == [(s, e) for s, e, _ in want], (cs, len(hay))
+    # every word a keyword
+    dense = " ".join(rng.choice(kws[:500]) for _ in range(30_000))
+    want = oracle_stream(ora.Matcher("wholeword", kws[:500]), dense)
+    pos, _ = _records(ac.WholeWordMatchSet(kws[:500], True), dense)
+    assert pos == [(s, e) for s, e, _ in want] and len(pos) == 30_000

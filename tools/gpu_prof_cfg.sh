@@ -7,7 +7,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'
 grep -E "k_tier|k_sel|k_row|k_fwd|k_ac|k_ww" gpurun_out/${TAG}_launches.csv | awk -F'","' '{print substr($5,1,60), $NF}' | tail -40
 if [ -n "$3" ]; then
   for KR in $(echo $3 | tr ',' ' '); do
-    timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KR -s 2 -c 1 -f -o gpurun_out/${TAG}_prof_$KR $CMD > gpurun_out/${TAG}_prof_$KR.log 2>&1
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:$KR -s ${SKIP:-0} -c 1 -f -o gpurun_out/${TAG}_prof_$KR $CMD > gpurun_out/${TAG}_prof_$KR.log 2>&1
     ls -la gpurun_out/${TAG}_prof_$KR.ncu-rep
   done
 fi
