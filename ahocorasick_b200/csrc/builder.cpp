@@ -162,15 +162,6 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
     }
     t.n_deep = n_deep;
     if (a.max_len > K) t.kidmask.assign(entries, 0);
-    if (a.is_map) {
-        uint64_t voff = 0, e = 1;
-        for (int j = 1; j <= K; j++) {
-            e *= C;
-            t.val_off[j] = voff;
-            voff += e;
-        }
-        t.shallow_val.assign(voff, kNone);
-    }
     for (int64_t id = 1; id < n; id++) {
         const int d = depth[id];
         const uint32_t inf = a.node_info[id];
@@ -188,25 +179,24 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
             if (inf & kInfoTerminal) t.term_levels |= 1u << d;
             if (!t.kidmask.empty()) t.kidmask[radix[id]] = kids[id];
         }
-        if (a.is_map && d <= K && (inf & kInfoTerminal)) t.shallow_val[t.val_off[d] + radix[id]] = a.node_value[id];
     }
     // ---- path-compressed deep table
-    // ---- Map values of the keywords longer than K
+    // ---- Map values: every keyword, keyed by its packed classes and length
     t.n_vbuckets = 1;
     t.vbuckets.assign(8, 0xFFFFFFFFu);
-    if (a.is_map && n_deep > 0) {
+    if (a.is_map) {
         uint64_t n_keys = 0;
-        for (int64_t id = 1; id < n; id++) n_keys += depth[id] > K && (a.node_info[id] & kInfoTerminal);
+        for (int64_t id = 1; id < n; id++) n_keys += (a.node_info[id] & kInfoTerminal) ? 1 : 0;
         const uint64_t nvb = std::max<uint64_t>(4, (n_keys * 10 + 10) / 11);
         if (nvb > 0x7FFFFFFFull) return;
         t.n_vbuckets = static_cast<uint32_t>(nvb);
         t.vseed = 0xD6E8FEB86659FD93ull;
         t.vbuckets.assign(nvb * 8, 0xFFFFFFFFu);  // empty: key = all ones (no key has length bits 1111 and all classes set: b * max_len <= 60 leaves them apart)
         for (int64_t id = 1; id < n; id++) {
-            if (depth[id] <= K || !(a.node_info[id] & kInfoTerminal)) continue;
+            if (!(a.node_info[id] & kInfoTerminal)) continue;
             const uint64_t key = packed[id] | (static_cast<uint64_t>(depth[id] - 1) << 60);
-            const uint64_t hs = deep_hash64(key, t.vseed);
-            uint32_t bk = static_cast<uint32_t>(((hs & 0xFFFFFFFFull) * nvb) >> 32);
+            const uint32_t hs = value_hash32(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32));
+            uint32_t bk = static_cast<uint32_t>((static_cast<uint64_t>(hs) * nvb) >> 32);
             while (true) {
                 uint32_t *e = &t.vbuckets[static_cast<size_t>(bk) * 8];
                 int k = (e[0] == 0xFFFFFFFFu && e[1] == 0xFFFFFFFFu) ? 0 : ((e[4] == 0xFFFFFFFFu && e[5] == 0xFFFFFFFFu) ? 1 : -1);

@@ -87,11 +87,9 @@ struct TierTables {
     uint64_t hash_seed = 0;
     uint64_t n_deep = 0;             // trie nodes deeper than K
     uint64_t n_heads = 0;            // entries of the compressed table
-    // Map values: shallow levels indexed like the bit tables; a keyword longer than K is looked up by its whole packed
-    // context in a bucketed hash table (two 16-byte entries {key lo, key hi, value, 0} per 32-byte bucket; key = packed
-    // classes | (length - 1) << 60, compared exactly) - one gather per record
-    std::vector<uint32_t> shallow_val;
-    uint64_t val_off[10] = {0};
+    // Map values: a keyword is looked up by its whole packed context in a bucketed hash table (two 16-byte entries
+    // {key lo, key hi, value, 0} per 32-byte bucket; key = packed classes | (length - 1) << 60, compared exactly) - one
+    // gather per record
     std::vector<uint32_t> vbuckets;  // 8 words per bucket
     uint32_t n_vbuckets = 0;
     uint64_t vseed = 0;
@@ -134,6 +132,18 @@ struct WwHash {
         return x ^ (x >> 16);
     }
 };
+
+// bucket hash of the keyword -> value table (32-bit arithmetic only: it runs once per Map record on the device)
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t value_hash32(uint32_t lo, uint32_t hi) {
+    uint32_t h = (lo * 0x9E3779B1u) ^ (hi * 0x85EBCA6Bu);
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 13;
+    return h;
+}
 
 inline uint64_t deep_hash64(uint64_t key, uint64_t seed) {
     uint64_t h = key ^ seed;

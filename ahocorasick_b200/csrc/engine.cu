@@ -153,7 +153,6 @@ int upload_tier(Matcher *m) {
     size_t o_cls8 = reserve(256);
     size_t o_kid = reserve(t.kidmask.size() * 4);
     size_t o_deep = reserve(t.buckets.size() * 4);
-    size_t o_sval = reserve(t.shallow_val.size() * 4);
     size_t o_vb = reserve(t.vbuckets.size() * 4);
     CU_TRY(cudaMalloc(&m->d_tier_blob, off));
     m->table_bytes += static_cast<int64_t>(off);
@@ -164,7 +163,6 @@ int upload_tier(Matcher *m) {
     CU_TRY(cudaMemcpy(b + o_cls8, cls8, 256, cudaMemcpyHostToDevice));
     if (!t.kidmask.empty()) CU_TRY(cudaMemcpy(b + o_kid, t.kidmask.data(), t.kidmask.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(b + o_deep, t.buckets.data(), t.buckets.size() * 4, cudaMemcpyHostToDevice));
-    if (!t.shallow_val.empty()) CU_TRY(cudaMemcpy(b + o_sval, t.shallow_val.data(), t.shallow_val.size() * 4, cudaMemcpyHostToDevice));
     if (!t.vbuckets.empty()) CU_TRY(cudaMemcpy(b + o_vb, t.vbuckets.data(), t.vbuckets.size() * 4, cudaMemcpyHostToDevice));
     DevTier &d = m->tier;
     d.cls8 = reinterpret_cast<const uint32_t *>(b + o_cls8);
@@ -185,7 +183,6 @@ int upload_tier(Matcher *m) {
     }
     d.buckets = reinterpret_cast<const uint4 *>(b + o_deep);
     d.hash_seed = t.hash_seed;
-    d.shallow_val = reinterpret_cast<const uint32_t *>(b + o_sval);
     d.vbuckets = reinterpret_cast<const uint4 *>(b + o_vb);
     d.vseed = t.vseed;
     d.n_vbuckets = t.n_vbuckets;
@@ -218,7 +215,6 @@ int upload_tier(Matcher *m) {
     d.K = t.K;
     for (int j = 0; j < 10; j++) {
         d.pow_c[j] = t.pow_c[j];
-        d.val_off[j] = t.val_off[j];
     }
     m->use_tier = true;
     return ACGPU_OK;
@@ -322,6 +318,7 @@ int enqueue_sel2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint
     const size_t o_gmap = S.reserve(static_cast<size_t>(n_groups) * kS2Ent * 4);
     const size_t o_gent = S.reserve(static_cast<size_t>(n_groups));
     const size_t o_gbase = S.reserve(static_cast<size_t>(n_groups) * 8);
+    const size_t o_status = S.reserve(static_cast<size_t>(n_tiles) * sizeof(S2Status));
     void *ws = nullptr;
     CU_TRY(cudaMallocAsync(&ws, S.off, st));
     char *w = static_cast<char *>(ws);
@@ -361,28 +358,52 @@ int enqueue_sel2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint
     Q.cap = cap;
     const bool longest = m->dev.family == ACGPU_LONGEST;
     const size_t smem = static_cast<size_t>(kS2SmemWords) * 4;
-    const int sgrid = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(m->sm_count) * 16));
-    if (longest)
-        k_sel2_map<kModeLongest><<<sgrid, kS2Threads, smem, st>>>(Q);
-    else
-        k_sel2_map<kModeShortest><<<sgrid, kS2Threads, smem, st>>>(Q);
-    CU_TRY(cudaGetLastError());
-    k_sel2_group<<<static_cast<unsigned>(n_groups), 32, 0, st>>>(Q);
-    CU_TRY(cudaGetLastError());
-    k_sel2_top<<<1, 1024, static_cast<size_t>(n_groups) * kS2Ent * 4, st>>>(Q);
-    CU_TRY(cudaGetLastError());
-    k_sel2_tiles<<<static_cast<unsigned>(n_groups), 32, 0, st>>>(Q);
-    CU_TRY(cudaGetLastError());
-    if (cap > 0) {
+    // Measured (profiles/r01_s5_summary.md): the look-back over MAPS costs ~12 us per tile (following the chain through
+    // the published maps is latency-bound), more than the second resolution pass it saves - opt-in only.
+    const char *fused = getenv("ACGPU_SEL2_FUSED");
+    if (fused && fused[0] == '1') {
+        // single pass: maps, look-back over the maps, emission (k_sel2_fused)
+        CU_TRY(cudaMemsetAsync(w + o_status, 0, static_cast<size_t>(n_tiles) * sizeof(S2Status), st));
+        Q.status = reinterpret_cast<S2Status *>(w + o_status);
+        Q.tile_counter = reinterpret_cast<unsigned int *>(w + o_ctr + 64);
+        Q.err = reinterpret_cast<unsigned int *>(w + o_ctr + 128);
+        const int fgrid = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(m->sm_count) * 4));
         if (longest)
-            k_sel2_emit<kModeLongest><<<sgrid, kS2Threads, smem, st>>>(Q);
+            k_sel2_fused<kModeLongest><<<fgrid, kS2Threads, smem, st>>>(Q);
         else
-            k_sel2_emit<kModeShortest><<<sgrid, kS2Threads, smem, st>>>(Q);
+            k_sel2_fused<kModeShortest><<<fgrid, kS2Threads, smem, st>>>(Q);
         CU_TRY(cudaGetLastError());
-        if (m->dev.is_map) {
-            k_sel2_values<<<sgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q);
+    } else {
+        const int sgrid = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(m->sm_count) * 16));
+        if (longest)
+            k_sel2_map<kModeLongest><<<sgrid, kS2Threads, smem, st>>>(Q);
+        else
+            k_sel2_map<kModeShortest><<<sgrid, kS2Threads, smem, st>>>(Q);
+        CU_TRY(cudaGetLastError());
+        k_sel2_group<<<static_cast<unsigned>(n_groups), 32, 0, st>>>(Q);
+        CU_TRY(cudaGetLastError());
+        k_sel2_top<<<1, 1024, static_cast<size_t>(n_groups) * kS2Ent * 4, st>>>(Q);
+        CU_TRY(cudaGetLastError());
+        k_sel2_tiles<<<static_cast<unsigned>(n_groups), 32, 0, st>>>(Q);
+        CU_TRY(cudaGetLastError());
+        if (cap > 0) {
+            if (longest)
+                k_sel2_emit<kModeLongest><<<sgrid, kS2Threads, smem, st>>>(Q);
+            else
+                k_sel2_emit<kModeShortest><<<sgrid, kS2Threads, smem, st>>>(Q);
             CU_TRY(cudaGetLastError());
         }
+    }
+    if (cap > 0 && m->dev.is_map) {
+        const int vgrid = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(m->sm_count) * 16));
+        switch (m->tier.b) {
+        case 1: k_sel2_values<1><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
+        case 2: k_sel2_values<2><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
+        case 3: k_sel2_values<3><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
+        case 4: k_sel2_values<4><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
+        default: k_sel2_values<5><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
+        }
+        CU_TRY(cudaGetLastError());
     }
     CU_TRY(cudaFreeAsync(ws, st));
     return ACGPU_OK;
@@ -1068,7 +1089,7 @@ int acgpu_launches_per_match(uint64_t handle) {
     switch (m->host.family) {
     case ACGPU_AHOCORASICK: return m->use_tier ? 3 : 1;
     case ACGPU_WHOLEWORD: return m->use_ww ? 1 : 2;
-    default: return 6;  // one-shot matches; the streaming path always takes the 6-launch route
+    default: return m->use_tier && m->host.is_map ? 7 : 6;  // one-shot tier path: mask, map, group, top, tiles, emit (+ values)  // one-shot matches; the streaming path always takes the 6-launch route
     }
 }
 

@@ -83,19 +83,12 @@ __global__ void __launch_bounds__(1024, 1) k_row_scan(const ScanArgs S) {
     }
 }
 
-// value index of the keyword of length d that ends the context (Maps); K is a run-time value here
+// value index of the keyword of length d that ends the context (Maps): one probe of the keyword -> value table (the
+// record is a real match, so the key exists)
 __device__ __forceinline__ uint32_t tier_value_rt(const DevTier &T, unsigned long long ctx, uint32_t cm, int d) {
-    const int K = T.K;
-    if (d <= K) {
-        uint32_t idx = 0;
-        for (int i = 1; i <= d; i++) idx += ((uint32_t)(ctx >> (T.b * (i - 1))) & cm) * T.pow_c[i];
-        return __ldg(&T.shallow_val[T.val_off[d] + idx]);
-    }
-    // longer keywords: one probe of the keyword -> value table (the record is a real match, so the key exists)
     const unsigned long long key = (ctx & ((1ull << (T.b * d)) - 1ull)) | ((unsigned long long)(d - 1) << 60);
-    const unsigned long long h = deep_hash64_d(key, T.vseed);
-    uint32_t bucket = __umulhi((uint32_t)h, T.n_vbuckets);
     const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
+    uint32_t bucket = __umulhi(value_hash32(klo, khi), T.n_vbuckets);
     for (uint32_t tries = 0; tries < T.n_vbuckets; tries++) {
         const uint4 *q = T.vbuckets + (size_t)bucket * 2;
         const uint4 e0 = __ldg(q);

@@ -46,6 +46,9 @@ struct Sel2Args {
     uint32_t *tile_map;             // [n_tiles][16]  exit offset | matches << 8, per entry offset
     uint8_t *tile_entry;            // [n_tiles]
     unsigned long long *tile_base;  // [n_tiles] index of the tile's first record
+    struct S2Status *status;        // [n_tiles] look-back records of k_sel2_fused (zeroed)
+    unsigned int *tile_counter;     // ticket counter (zeroed)
+    unsigned int *err;              // set when a look-back wait gave up
     int64_t n_groups;
     uint32_t *group_map;            // [n_groups][16]
     uint8_t *group_entry;           // [n_groups]
@@ -319,15 +322,185 @@ __global__ void __launch_bounds__(kS2Threads, 4) k_sel2_emit(const Sel2Args P) {
     }
 }
 
+// ---- single pass: exit maps, decoupled look-back over the MAPS of the preceding tiles, emission.
+//
+// Tiles are taken in ticket order.  A tile publishes its 16-entry map (flag 1) as soon as it has it, then looks back for the
+// nearest predecessor whose chain state is resolved (flag 2 = "the chain enters the NEXT tile at offset e with r records
+// before it"), follows the chain through the maps of the tiles in between, publishes its own resolved state and emits.
+// Nothing is speculative; a tile only ever waits for tiles that were started before it.
+struct __align__(16) S2Status {   // 64 bytes per tile
+    uint32_t flag;                // 0 = nothing yet, 1 = map published, 2 = map and resolved state published
+    uint32_t next_entry;          // chain offset on entry to the next tile
+    unsigned long long next_base; // records emitted before the next tile
+    unsigned long long exits;     // the map: exit offset (4 bits) per entry offset
+    uint32_t pad[2];
+    uint16_t counts[16];          //          matches per entry offset (16-byte aligned: read as two uint4)
+};
+static_assert(sizeof(S2Status) == 64, "one look-back record per 64-byte line");
+
+__device__ __forceinline__ uint32_t s2_ld_flag(const S2Status *st) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->flag) : "memory");
+    return v;
+}
+__device__ __forceinline__ void s2_st_flag(S2Status *st, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->flag), "r"(v) : "memory");
+}
+
+constexpr uint32_t kS2SpinLimit = 1u << 26;  // a tile that waits this long reports an error instead of hanging the device
+
+// Called by warp 0 after the tile map is in s_tmap[16] (exit | matches << 8).  Returns the tile's entry offset and record
+// base to every lane of the warp.
+__device__ __forceinline__ void s2_lookback(S2Status *status, int64_t tile, const uint32_t *s_tmap, unsigned long long *s_ex,
+                                            uint16_t *s_cn, unsigned int *err, uint32_t &entry_out, unsigned long long &base_out) {
+    const int lane = threadIdx.x & 31;
+    S2Status *mine = status + tile;
+    // ---- publish the map
+    {
+        const uint32_t t = lane < kS2Ent ? s_tmap[lane] : 0u;
+        const uint32_t lo = __reduce_or_sync(0xFFFFFFFFu, lane < 8 ? (t & 15u) << (4 * lane) : 0u);
+        const uint32_t hi = __reduce_or_sync(0xFFFFFFFFu, (lane >= 8 && lane < 16) ? (t & 15u) << (4 * (lane - 8)) : 0u);
+        if (lane < kS2Ent) mine->counts[lane] = (uint16_t)(t >> 8);
+        if (lane == 0) mine->exits = ((unsigned long long)hi << 32) | lo;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0 && tile != 0) s2_st_flag(mine, 1u);
+    }
+    uint32_t cur = 0;
+    unsigned long long base = 0;
+    if (tile != 0) {
+        // ---- find the nearest resolved predecessor J (every tile between J and this one has published its map by then)
+        int64_t J = -1;
+        for (int64_t look = tile - 1; look >= 0 && J < 0; look -= 32) {
+            const int64_t idx = look - lane;
+            uint32_t f = 2u;  // lanes before tile 0 never stop the search on their own (masked below)
+            if (idx >= 0) {
+                uint32_t spins = 0;
+                while ((f = s2_ld_flag(status + idx)) == 0u) {
+                    __nanosleep(40);
+                    if (++spins > kS2SpinLimit) { atomicExch(err, 1u); f = 2u; break; }
+                }
+            }
+            const uint32_t res = __ballot_sync(0xFFFFFFFFu, idx >= 0 && f == 2u);
+            if (res) J = look - (__ffs(res) - 1);
+        }
+        __threadfence();
+        // ---- the chain state after tile J (tile -1 = the start of the haystack: offset 0, no records)
+        if (J >= 0) {
+            cur = __ldcg(&status[J].next_entry);
+            base = __ldcg(&status[J].next_base);
+        }
+        // ---- follow the chain through the maps of tiles J+1 .. tile-1, 32 at a time
+        for (int64_t first = J + 1; first < tile; first += 32) {
+            const int64_t idx = first + lane;
+            __syncwarp();
+            if (idx < tile) {
+                s_ex[lane] = __ldcg(&status[idx].exits);
+                const uint4 c0 = __ldcg(reinterpret_cast<const uint4 *>(status[idx].counts));
+                const uint4 c1 = __ldcg(reinterpret_cast<const uint4 *>(status[idx].counts) + 1);
+                reinterpret_cast<uint4 *>(s_cn + lane * 16)[0] = c0;
+                reinterpret_cast<uint4 *>(s_cn + lane * 16)[1] = c1;
+            }
+            __syncwarp();
+            const int cnt = (int)min((int64_t)32, tile - first);
+            for (int i = 0; i < cnt; i++) {
+                base += s_cn[i * 16 + cur];
+                cur = (uint32_t)(s_ex[i] >> (4 * cur)) & 15u;
+            }
+        }
+    }
+    entry_out = cur;
+    base_out = base;
+    // ---- publish the resolved state
+    if (lane == 0) {
+        const uint32_t t = s_tmap[cur];
+        mine->next_entry = t & 0xFFu;
+        mine->next_base = base + (t >> 8);
+        __threadfence();
+        s2_st_flag(mine, 2u);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kS2Threads, 4) k_sel2_fused(const Sel2Args P) {
+    extern __shared__ __align__(16) uint32_t s_w[];
+    __shared__ uint32_t s_wmap[(kS2Threads / 32) * kS2Ent];
+    __shared__ uint32_t s_tmap[kS2Ent];
+    __shared__ uint32_t s_wentry[kS2Threads / 32];
+    __shared__ unsigned long long s_wbase[kS2Threads / 32];
+    __shared__ uint16_t s_traj[kS2Threads * kS2Ent];
+    __shared__ __align__(16) unsigned long long s_ex[32];
+    __shared__ __align__(16) uint16_t s_cn[32 * 16];
+    __shared__ long long s_tile;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    while (true) {
+        __syncthreads();  // the previous tile's readers are done
+        if (tid == 0) s_tile = (long long)atomicAdd(P.tile_counter, 1u);
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= P.n_tiles) break;
+        uint32_t mw[16], hw[8];
+        s2_load(P, tile, mw, hw);
+        const int64_t a = tile * kS2Tile + (int64_t)tid * kS2Sub - P.moff;  // haystack position of the lane's first index
+        s2_resolve<MODE>(mw, hw, s_w);
+        s2_warp_maps<true>(s_w, s_wmap, s_traj);
+        __syncthreads();
+        if (tid < kS2Ent) {
+            uint32_t cur = tid, cnt = 0;
+#pragma unroll
+            for (int w = 0; w < kS2Threads / 32; w++) {
+                const uint32_t t = s_wmap[w * kS2Ent + cur];
+                cur = t & 0xFFu;
+                cnt += t >> 8;
+            }
+            s_tmap[tid] = cur | (cnt << 8);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t cur;
+            unsigned long long acc;
+            s2_lookback(P.status, tile, s_tmap, s_ex, s_cn, P.err, cur, acc);
+            if (tid == 0) {
+                if (tile == P.n_tiles - 1) *P.total_out = acc + (s_tmap[cur] >> 8);
+#pragma unroll
+                for (int w = 0; w < kS2Threads / 32; w++) {
+                    s_wentry[w] = cur;
+                    s_wbase[w] = acc;
+                    const uint32_t t = s_wmap[w * kS2Ent + cur];
+                    cur = t & 0xFFu;
+                    acc += t >> 8;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t eo = s_traj[tid * kS2Ent + s_wentry[warp]];
+        unsigned long long idx = s_wbase[warp] + (eo >> 4);
+        uint32_t p = eo & 15u;
+        const int32_t a32 = (int32_t)a + P.pos_base;
+        while (p < 32u) {
+            const uint32_t w = s_w[s2_idx_rt(p, tid)];
+            if ((w >> 22) & 1u) {
+                if (idx < (unsigned long long)P.cap)
+                    __stcs(&P.pos_out[idx], make_int2(a32 + (int32_t)((w >> 16) & 63u), a32 + (int32_t)((w >> 10) & 63u)));
+                ++idx;
+            }
+            p = (w >> 10) & 63u;
+        }
+    }
+}
+
 // ---- Maps.  The records of a tile are consecutive (tile_base), so one CTA per tile packs the classes of the tile's
 // 8 192 + 32 positions into a bit stream in shared memory (b bits per position, every position classified once) and then
 // takes one record per thread: the keyword's context (its packed classes, first char lowest - the order the forward-trie
 // tables use) is three word loads and two funnel shifts, the value one probe of the tier tables.
-__device__ __forceinline__ void s2_pack_classes(const DevAutomaton &A, const uint16_t *hay, int64_t n, int64_t a, int b,
+template <int B>
+__device__ __forceinline__ void s2_pack_classes(const DevAutomaton &A, const uint16_t *hay, int64_t n, int64_t a,
                                                 const uint8_t *s_cls, uint32_t *dst) {
-    // 32 positions starting at haystack position a (a 16-byte aligned address when inside the haystack) -> b words at dst
-    unsigned long long acc = 0;
-    int fill = 0, o = 0;
+    // 32 positions starting at haystack position a (a 16-byte aligned address when inside the haystack) -> B words at dst;
+    // B is a compile-time constant so every class lands with one shift-or at a fixed place
+    uint32_t out[B];
+#pragma unroll
+    for (int k = 0; k < B; k++) out[k] = 0u;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int64_t p0 = a + q * 8;
@@ -343,33 +516,39 @@ __device__ __forceinline__ void s2_pack_classes(const DevAutomaton &A, const uin
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const uint32_t c = ch[j] < 256u ? (uint32_t)s_cls[ch[j]] : (ch[j] < 0x10000u ? (uint32_t)__ldg(&A.cls[ch[j]]) : 0u);
-            acc |= (unsigned long long)c << fill;
-            fill += b;
-            if (fill >= 32) {
-                dst[o++] = (uint32_t)acc;
-                acc >>= 32;
-                fill -= 32;
-            }
+            const int bit = (q * 8 + j) * B;
+            out[bit >> 5] |= c << (bit & 31);
+            if ((bit & 31) + B > 32) out[(bit >> 5) + 1] |= c >> (32 - (bit & 31));
         }
     }
+#pragma unroll
+    for (int k = 0; k < B; k++) dst[k] = out[k];
 }
 
+template <int B>
 __global__ void __launch_bounds__(kS2Threads) k_sel2_values(const DevAutomaton A, const DevTier T, const Sel2Args P) {
-    __shared__ uint32_t s_bits[(kS2Threads + 1) * 5 + 3];
+    __shared__ uint32_t s_bits[(kS2Threads + 1) * B + 3];
     __shared__ uint8_t s_cls[256];
     const int tid = threadIdx.x;
     for (int i = tid; i < 256; i += kS2Threads) s_cls[i] = (uint8_t)((__ldg(&T.cls8[i >> 2]) >> ((i & 3) * 8)) & 0xFFu);
-    const int b = T.b;
+    constexpr int b = B;
     const uint32_t cm = (1u << b) - 1u;
     const unsigned long long n_rec = min(*P.total_out, (unsigned long long)P.cap);
     for (int64_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
-        const unsigned long long r0 = min(P.tile_base[tile], n_rec);
-        const unsigned long long r1 = tile + 1 < P.n_tiles ? min(P.tile_base[tile + 1], n_rec) : n_rec;
+        // records of tile t: [base after tile t-1, base after tile t)
+        unsigned long long r0, r1;
+        if (P.status) {
+            r0 = tile ? min(P.status[tile - 1].next_base, n_rec) : 0ull;
+            r1 = min(P.status[tile].next_base, n_rec);
+        } else {
+            r0 = min(P.tile_base[tile], n_rec);
+            r1 = tile + 1 < P.n_tiles ? min(P.tile_base[tile + 1], n_rec) : n_rec;
+        }
         if (r0 >= r1) continue;  // uniform over the block
         const int64_t a0 = tile * kS2Tile - P.moff;  // haystack position of the tile's first index
         __syncthreads();  // the previous tile's readers are done (and s_cls is written)
-        s2_pack_classes(A, P.hay, P.n, a0 + (int64_t)tid * kS2Sub, b, s_cls, s_bits + tid * b);
-        if (tid == 0) s2_pack_classes(A, P.hay, P.n, a0 + kS2Tile, b, s_cls, s_bits + kS2Threads * b);
+        s2_pack_classes<B>(A, P.hay, P.n, a0 + (int64_t)tid * kS2Sub, s_cls, s_bits + tid * b);
+        if (tid == 0) s2_pack_classes<B>(A, P.hay, P.n, a0 + kS2Tile, s_cls, s_bits + kS2Threads * b);
         __syncthreads();
         const int32_t a32 = (int32_t)a0 + P.pos_base;
         for (unsigned long long r = r0 + tid; r < r1; r += kS2Threads) {

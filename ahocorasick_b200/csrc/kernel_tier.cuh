@@ -8,6 +8,7 @@
 //   * levels > K are path-compressed: one 16-byte entry per chain head (keyed by the packed context of the head)
 //     holds the unbranched chain below it, so one sector load resolves a whole keyword tail.
 #pragma once
+#include "builder.hpp"
 #include "device_tables.cuh"
 
 namespace acgpu {
@@ -18,8 +19,7 @@ struct DevTier {
     const uint32_t *kidmask;     // [C^K] exact child masks of the level-K entries (nullptr: no deeper levels)
     cudaTextureObject_t kid_tex; // the same table as a linear texture (k_tier_mask gathers it through the TEX pipe)
     const uint4 *buckets;        // deep table: 2 entries per 32-byte bucket, see TierTables in builder.hpp
-    const uint32_t *shallow_val;
-    const uint4 *vbuckets;       // Map values of keywords longer than K: {key lo, key hi, value, 0}, 2 per bucket
+    const uint4 *vbuckets;       // Map values: {key lo, key hi, value, 0}, 2 per bucket, key = packed classes | (length - 1) << 60
     unsigned long long vseed;
     uint32_t n_vbuckets;
     unsigned long long hash_seed;
@@ -30,7 +30,6 @@ struct DevTier {
     uint32_t term_levels;
     int32_t b, C, K;
     uint32_t pow_c[10];
-    unsigned long long val_off[10];
 };
 
 // streaming 128-bit haystack load, predicated (rows at the edges of the haystack)

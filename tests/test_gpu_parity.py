@@ -409,9 +409,13 @@ def test_sel2_dense_periodic_and_sparse(family):
         assert len(pos) >= 10
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("family", ["longest", "shortest"])
-def test_sel2_many_tiles_scan_slices(family):
-    """10^7 chars = 1 221 tiles: every k_sel2_scan thread composes a slice of several tiles."""
+def test_sel2_many_tiles_scan_slices(family, fused, monkeypatch):
+    """10^7 chars = 1 221 tiles = 5 composition groups (k_sel2_group / _top / _tiles); fused=True runs the opt-in
+    single-pass kernel instead (k_sel2_fused: decoupled look-back over the tile maps)."""
+    if fused:
+        monkeypatch.setenv("ACGPU_SEL2_FUSED", "1")
     c = W.config(2, scale=0.02)
     hay = W.make_haystack(c["spec"], 10_000_000)
     kws = c["keywords"]
