@@ -60,7 +60,21 @@ __device__ __forceinline__ uint32_t ww_classify16(const DevWw &W, const uint16_t
 #pragma unroll
         for (int j = 0; j < 16; j++) ch[j] = (p0 + j >= 0 && p0 + j < n) ? (uint32_t)__ldg(&hay[p0 + j]) : 0x10000u;  // outside: no word char
     }
+    uint32_t any = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) any |= ch[j];
     uint32_t wc = 0, kc = 0;
+    if (any < 256u) {  // the common case: 16 Latin-1 chars, classes straight from the shared-memory table
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint32_t x0 = s_tab[ch[2 * k]], x1 = s_tab[ch[2 * k + 1]];
+            const uint32_t pair = x0 | (x1 << 16);
+            reinterpret_cast<uint32_t *>(s_c)[k] = pair & 0x7FFF7FFFu;
+            wc |= ((pair >> 15) & 1u) << (2 * k) | (pair >> 31) << (2 * k + 1);
+            kc |= ((pair & 0x7FFFu) ? 1u : 0u) << (2 * k) | ((pair & 0x7FFF0000u) ? 1u : 0u) << (2 * k + 1);
+        }
+        return wc | (kc << 16);
+    }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         uint32_t x[2];
