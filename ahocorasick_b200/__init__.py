@@ -7,12 +7,12 @@ itself runs in libacgpu.so (CUDA).  There is no CPU fallback.
 from ._lib import AcgpuError, IllegalArgumentException
 from .matchers import (AhoCorasickMap, AhoCorasickSet, LongestMatchMap, LongestMatchSet, MapMatchListener,
                        RangeNodeThreshold, ReadableMatchListener, SetMatchListener, ShortestMatchMap,
-                       ShortestMatchSet, StringMap, StringSet, Thresholder, WholeWordMatchMap,
-                       WholeWordMatchSet, WordCharacters)
+                       ShortestMatchSet, StringMap, StringSet, Thresholder, WholeWordLongestMatchMap,
+                       WholeWordLongestMatchSet, WholeWordMatchMap, WholeWordMatchSet, WordCharacters)
 
 __all__ = [
     "AcgpuError", "IllegalArgumentException", "AhoCorasickMap", "AhoCorasickSet", "LongestMatchMap",
     "LongestMatchSet", "MapMatchListener", "RangeNodeThreshold", "ReadableMatchListener", "SetMatchListener",
-    "ShortestMatchMap", "ShortestMatchSet", "StringMap", "StringSet", "Thresholder", "WholeWordMatchMap",
-    "WholeWordMatchSet", "WordCharacters",
+    "ShortestMatchMap", "ShortestMatchSet", "StringMap", "StringSet", "Thresholder", "WholeWordLongestMatchMap",
+    "WholeWordLongestMatchSet", "WholeWordMatchMap", "WholeWordMatchSet", "WordCharacters",
 ]

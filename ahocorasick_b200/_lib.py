@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("ACGPU_LIB") or os.path.join(_HERE, "libacgpu.so")  # 
 OK, EINVAL, EILLEGALARG, ENODEVICE, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 NO_VALUE = 0xFFFFFFFF
 
-AHOCORASICK, LONGEST, SHORTEST, WHOLEWORD = 0, 1, 2, 3
+AHOCORASICK, LONGEST, SHORTEST, WHOLEWORD, WHOLEWORDLONGEST = 0, 1, 2, 3, 4
 
 # every symbol include/acgpu.h declares (tests check the .so exports all of them)
 EXPORTS = [

@@ -347,7 +347,8 @@ void build_ww(HostAutomaton &a, const std::vector<uint8_t> &wc, const std::vecto
 HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *offsets, const uint8_t *is_null,
                               int64_t n_keywords, int64_t n_values, bool case_sensitive,
                               const uint8_t *word_chars) {
-    if (family < 0 || family > 3) throw std::invalid_argument("unknown matcher family");
+    if (family < 0 || family > 4) throw std::invalid_argument("unknown matcher family");
+    const bool word_family = family == 3 || family == 4;  // WholeWord, WholeWordLongest
     const uint16_t *lower = java_lower_table();
     HostAutomaton a;
     a.family = family;
@@ -360,7 +361,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
     if (a.is_map && n_values < n) n = n_values;
 
     std::vector<uint8_t> wc;
-    if (family == 3) {
+    if (word_family) {
         wc.resize(65536);
         if (word_chars) {
             std::memcpy(wc.data(), word_chars, 65536);
@@ -400,8 +401,9 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
         if (is_null && is_null[k]) continue;
         int64_t b = offsets[k];
         int32_t len = static_cast<int32_t>(offsets[k + 1] - offsets[k]);
-        if (family == 3) {
-            // WordCharacters.trim (WordCharacters.java:41-62) then validation (WholeWordMatchSet.java:147-153)
+        if (word_family) {
+            // WordCharacters.trim (WordCharacters.java:41-62) then validation (WholeWordMatchSet.java:147-153);
+            // WholeWordLongest trims but accepts inner non-word chars (WholeWordLongestMatchSet.java:190-206)
             int32_t ws = 0, we = len;
             for (int32_t i = 0; i < len; i++) {
                 if (wc[chars[b + i]]) {
@@ -418,7 +420,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
             b += ws;
             len = we - ws;
             for (int32_t i = 0; i < len; i++) {
-                if (!wc[chars[b + i]]) {
+                if (family == 3 && !wc[chars[b + i]]) {
                     throw IllegalArgument(utf8_of(chars + b, len) + " contains non-word characters.");
                 }
             }
@@ -511,7 +513,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
         while (a.edges[i].parent != kNone) i = (i + 1) & a.edge_mask;
         a.edges[i] = Edge{e.parent, e.cls, e.child, a.node_info[e.child]};
     }
-    build_tiers(a, node_parent, node_cls);
+    if (family != 4) build_tiers(a, node_parent, node_cls);
     if (family == 3) build_ww(a, wc, node_parent, node_cls);
     return a;
 }

@@ -138,7 +138,7 @@ int upload_tier(Matcher *m) {
     const TierTables &t = m->host.tier;
     m->use_tier = false;
     // AhoCorasick: end masks over the reversed-keyword trie; Longest / Shortest: start masks over the forward trie
-    if (!t.ok || m->host.family == ACGPU_WHOLEWORD) return ACGPU_OK;
+    if (!t.ok || m->host.family == ACGPU_WHOLEWORD || m->host.family == ACGPU_WHOLEWORDLONGEST) return ACGPU_OK;
     const char *force = getenv("ACGPU_FORCE_GEN1");
     if (force && force[0] == '1') return ACGPU_OK;
     m->mask_smem = mask_smem_bytes(t.row_words.size());
@@ -276,6 +276,7 @@ struct RunOpts {
     int64_t entry0 = 0;    // chain position on entry (selection families)
     int64_t chain_n = -1;  // chain domain [0, chain_n); -1 => n
     int64_t *d_carry = nullptr;  // [2] int64 (selection families)
+    int64_t abs0 = 0;      // window position of the first char of the input, -1 = before this window (WholeWordLongest)
 };
 
 int launch_mask(Matcher *m, const MaskArgs &P, int grid, cudaStream_t st, bool mir = false) {
@@ -569,7 +570,7 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
     }
     if (chain && m->use_tier && opt.ctx == 0 && chain_n == n && opt.entry0 == 0 && !opt.d_carry)
         return enqueue_sel2(m, d_hay, n, d_pos, d_val, cap, d_total, st, opt);
-    const int32_t M = A.max_len + 1;
+    const int32_t M = A.max_len + (A.family == ACGPU_WHOLEWORDLONGEST ? 2 : 1);  // exit offsets are < M
     const int64_t n_tiles = (chain_n + kSelTile - 1) / kSelTile;
     const int64_t n_groups = (n_tiles + kSelGroup - 1) / kSelGroup;
     Scratch S;
@@ -595,6 +596,7 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
     F.p_lo = opt.ctx;
     F.p_hi = n;
     F.v = reinterpret_cast<uint16_t *>(b + o_v);
+    F.abs0 = opt.abs0;
     if (opt.ctx > 0) CU_TRY(cudaMemsetAsync(F.v, 0, static_cast<size_t>(opt.ctx) * sizeof(uint16_t), st));
     {
         const int64_t ft = (n + kFwTile - 1) / kFwTile;
@@ -603,6 +605,8 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
             k_fwd_v<1><<<grid, kThreads, 0, st>>>(A, F);
         else if (A.family == ACGPU_SHORTEST)
             k_fwd_v<2><<<grid, kThreads, 0, st>>>(A, F);
+        else if (A.family == ACGPU_WHOLEWORDLONGEST)
+            k_fwd_v<4><<<grid, kThreads, 0, st>>>(A, F);
         else
             k_fwd_v<3><<<grid, kThreads, 0, st>>>(A, F);
         CU_TRY(cudaGetLastError());
@@ -615,7 +619,9 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
     P.M = M;
     P.halo = std::max(0, A.max_len - 1);
     P.dom_lo = opt.ctx;
-    P.mode = A.family == ACGPU_LONGEST ? kModeLongest : (A.family == ACGPU_SHORTEST ? kModeShortest : kModeWholeWord);
+    P.mode = A.family == ACGPU_LONGEST ? kModeLongest
+             : (A.family == ACGPU_SHORTEST ? kModeShortest
+                                           : (A.family == ACGPU_WHOLEWORDLONGEST ? kModeWholeWordLongest : kModeWholeWord));
     P.n_tiles = n_tiles;
     P.n_groups = n_groups;
     P.entry0 = opt.entry0;
@@ -1018,6 +1024,10 @@ int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t 
         delete m;
         return fail(ACGPU_EUNSUPPORTED, "Longest/Shortest selection kernels support keywords up to 2047 chars");
     }
+    if (family == ACGPU_WHOLEWORDLONGEST && m->host.max_len > 254) {
+        delete m;
+        return fail(ACGPU_EUNSUPPORTED, "WholeWordLongest keywords longer than 254 chars are not supported");
+    }
     if (m->host.max_len > 65535) {
         delete m;
         return fail(ACGPU_EUNSUPPORTED, "keywords longer than 65535 chars are not supported");
@@ -1270,6 +1280,7 @@ int stream_process(StreamCtx *s, bool final, acgpu_result *out) {
             opt.entry0 = s->chain - s->base;
             opt.chain_n = limit;
             opt.d_carry = s->d_carry;
+            opt.abs0 = s->base == 0 ? 0 : -1;
             rc = enqueue_match(m, s->d_win[s->cur], avail, 0, avail, d_pos, d_val, cap, s->d_total, s->st, opt);
         }
         if (rc != ACGPU_OK) return rc;
@@ -1301,7 +1312,7 @@ int stream_process(StreamCtx *s, bool final, acgpu_result *out) {
     if (d_val) cudaFreeAsync(d_val, s->st);
 
     // chain position for the next block
-    if (family == ACGPU_LONGEST || family == ACGPU_SHORTEST) {
+    if (family == ACGPU_LONGEST || family == ACGPU_SHORTEST || family == ACGPU_WHOLEWORDLONGEST) {
         int64_t carry = -1;
         CU_TRY(cudaMemcpyAsync(&carry, s->d_carry, sizeof(carry), cudaMemcpyDeviceToHost, s->st));
         CU_TRY(cudaStreamSynchronize(s->st));

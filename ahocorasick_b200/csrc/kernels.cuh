@@ -199,6 +199,7 @@ struct FwArgs {
     int64_t p_lo;     // compute v for start positions [p_lo, p_hi)
     int64_t p_hi;
     uint16_t *v;      // v[s], indexed by window position
+    int64_t abs0;     // WholeWordLongest: window position of the first char of the input (always a walk start), -1 = not here
 };
 
 template <int kFamily>
@@ -235,6 +236,27 @@ __global__ void __launch_bounds__(kThreads) k_fwd_v(const DevAutomaton A, const 
                         ++i;
                     }
                 }
+            } else if (kFamily == 4) {
+                // WholeWordLongest (WholeWordLongestMatchSet.java:47-182): a walk starts at the first char of the input
+                // and at every word start; it follows the trie over word AND non-word chars until there is no
+                // transition (position idx).  Reported: the longest keyword on the path that is followed by a non-word
+                // char or the end of the input (the node's own match or its carried "fail match", :224-240).  The next
+                // walk starts at the first word start after idx.  v = length | (idx + 1 - s) << 8.
+                const bool start = s == P.abs0 ||
+                                   (is_word_char(A, __ldg(&P.hay[s])) && s > 0 && !is_word_char(A, __ldg(&P.hay[s - 1])));
+                if (start) {
+                    uint32_t node = 0, info = 0, len = 0;
+                    int64_t i = s;
+                    while (i < P.n) {
+                        const uint32_t c = cls_at(i);
+                        if ((A.has_other && c == 0) || !trie_step(A, node, c, info)) break;
+                        ++i;
+                        if ((info & kTerm) && (i == P.n || !is_word_char(A, __ldg(&P.hay[i])))) len = (uint32_t)(i - s);
+                        if (!(info & kKids)) break;
+                    }
+                    // i = first position without a transition (a leaf has none for any char)
+                    best = len | ((uint32_t)(i - s + 1) << 8);
+                }
             } else {
                 uint32_t node = 0, info = 0;
                 const int64_t lim = min(P.n, s + A.max_len);
@@ -264,7 +286,7 @@ constexpr int kSelGroup = 256;                 // tiles per composition group
 constexpr int kSelMaxLen = 2048;               // longest keyword the selection kernels accept
 constexpr uint32_t kSkip = 0xFFFFu;
 
-enum { kModeLongest = 1, kModeShortest = 2, kModeWholeWord = 3 };
+enum { kModeLongest = 1, kModeShortest = 2, kModeWholeWord = 3, kModeWholeWordLongest = 4 };
 
 struct SelArgs {
     const uint16_t *v;   // per-start values, window positions [0, n_v)
@@ -308,8 +330,10 @@ __device__ __forceinline__ void sel_build_nxt(const SelArgs &P, int64_t tile_sta
         vloc[k] = (g < P.n_v) ? (uint32_t)__ldg(&P.v[g]) : 0u;
         s_v[p0 + k] = (uint16_t)vloc[k];
     }
-    if (P.mode == kModeLongest) {
-        // first start >= p with a keyword (suffix "min position with v > 0")
+    if (P.mode == kModeLongest || P.mode == kModeWholeWordLongest) {
+        // first start >= p with a keyword (suffix "min position with v > 0"); WholeWordLongest: first walk start >= p,
+        // v = reported length | jump << 8 (the chain moves by the jump, the record ends at start + length)
+        const bool wwl = P.mode == kModeWholeWordLongest;
         uint32_t mine = 0xFFFFFFFFu;
 #pragma unroll
         for (int k = kSelPer - 1; k >= 0; k--) {
@@ -324,7 +348,7 @@ __device__ __forceinline__ void sel_build_nxt(const SelArgs &P, int64_t tile_sta
                 s_nxt[p0 + k] = kSelTile;
                 s_st[p0 + k] = kSkip;
             } else {
-                s_nxt[p0 + k] = (uint16_t)(fs + s_v[fs]);
+                s_nxt[p0 + k] = (uint16_t)(fs + (wwl ? (uint32_t)s_v[fs] >> 8 : (uint32_t)s_v[fs]));
                 s_st[p0 + k] = (uint16_t)fs;
             }
         }
@@ -522,6 +546,8 @@ __global__ void __launch_bounds__(kThreads) k_sel_emit(const DevAutomaton A, con
                 if (on && tile_start + (int64_t)s_nxt[p] >= P.n && P.carry_out) {
                     P.carry_out[0] = emits ? tile_start + (int64_t)s_nxt[p] : (long long)P.n;
                 }
+                // WholeWordLongest: a walk moves the chain even when it reports nothing
+                if (P.mode == kModeWholeWordLongest && emits) emits = (s_v[s_st[p]] & 0xFFu) != 0u;
                 mk[k] = emits;
                 my_cnt += mk[k];
             }
@@ -545,7 +571,8 @@ __global__ void __launch_bounds__(kThreads) k_sel_emit(const DevAutomaton A, con
             if (!mk[k]) continue;
             const int p = p0 + k;
             const int64_t st = tile_start + s_st[p];
-            const int64_t en = (P.mode == kModeWholeWord) ? st + s_v[p] : tile_start + s_nxt[p];
+            const int64_t en = (P.mode == kModeWholeWord) ? st + s_v[p]
+                               : (P.mode == kModeWholeWordLongest ? st + (s_v[s_st[p]] & 0xFFu) : tile_start + s_nxt[p]);
             if (idx < (unsigned long long)P.cap) {
                 P.pos_out[idx] = make_int2((int32_t)st + P.pos_base, (int32_t)en + P.pos_base);
                 if (kIsMap) {

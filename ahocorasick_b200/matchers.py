@@ -383,3 +383,29 @@ class WholeWordMatchMap(StringMap):
     def getWordChars(self) -> np.ndarray:
         """WholeWordMatchMap.java:242."""
         return self._wordChars
+
+
+class WholeWordLongestMatchSet(StringSet):
+    """WholeWordLongestMatchSet.java:9-260.  Same constructor overloads as WholeWordMatchSet; keywords are trimmed
+    but may hold non-word chars inside ("as if"), so no IllegalArgumentException."""
+    _family = _lib.WHOLEWORDLONGEST
+
+    def __init__(self, keywords, caseSensitive: bool, *rest, device: int = 0):
+        self._wordChars = _word_flags(rest)
+        self._create(keywords, None, caseSensitive, self._wordChars, device)
+
+    def getWordChars(self) -> np.ndarray:
+        """WholeWordLongestMatchSet.java:180."""
+        return self._wordChars
+
+
+class WholeWordLongestMatchMap(StringMap):
+    """WholeWordLongestMatchMap.java:13-420."""
+    _family = _lib.WHOLEWORDLONGEST
+
+    def __init__(self, keywords, values, caseSensitive: bool, *rest, device: int = 0):
+        self._wordChars = _word_flags(rest)
+        self._create(keywords, values, caseSensitive, self._wordChars, device)
+
+    def getWordChars(self) -> np.ndarray:
+        return self._wordChars

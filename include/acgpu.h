@@ -32,12 +32,15 @@ extern "C" {
 
 #define ACGPU_NO_VALUE 0xFFFFFFFFu
 
-/* Matcher families: the four public class pairs named by BASELINE.json north_star. */
+/* Matcher families: the four public class pairs named by BASELINE.json north_star, plus the fifth public pair of the
+ * reference ("next" row 1). */
 enum acgpu_family {
     ACGPU_AHOCORASICK = 0, /* AhoCorasickSet.java / AhoCorasickMap.java : all overlapping matches */
     ACGPU_LONGEST = 1,     /* LongestMatchSet.java / LongestMatchMap.java : leftmost-longest, non-overlapping */
     ACGPU_SHORTEST = 2,    /* ShortestMatchSet.java / ShortestMatchMap.java : earliest-end, non-overlapping */
-    ACGPU_WHOLEWORD = 3    /* WholeWordMatchSet.java / WholeWordMatchMap.java : whole word-character runs */
+    ACGPU_WHOLEWORD = 3,   /* WholeWordMatchSet.java / WholeWordMatchMap.java : whole word-character runs */
+    ACGPU_WHOLEWORDLONGEST = 4 /* WholeWordLongestMatchSet.java / WholeWordLongestMatchMap.java : longest whole-word keyword
+                                * from every walk start; keywords may hold non-word chars ("as if") */
 };
 
 /* A match stream in the reference's listener order.

@@ -63,6 +63,9 @@ struct Node {
     int32_t matchLength;
     int32_t level; /* LongestMatchSet.java:513 */
     int32_t value; /* index of the dictionary entry whose value object is stored; -1 = null/none */
+    int32_t failMatchLength; /* WholeWordLongestMatchSet.java:TrieNode — last whole-word match up the tree */
+    int32_t failMatchOffset;
+    int32_t failValue;       /* WholeWordLongestMatchMap.java: value of that match */
     int32_t cap;   /* keys.length */
     int32_t modulusMask;
     int32_t numEntries;
@@ -133,6 +136,7 @@ static Node *new_hashmap_node(ora_matcher *m, int root, int32_t level) {
     n->defaultTransition = root ? n : NULL;
     n->level = level;
     n->value = -1;
+    n->failValue = -1;
     m->nodes++;
     return n;
 }
@@ -409,6 +413,24 @@ static void visit_wholeword(ora_matcher *m, NQueue *q, Node *parent, uint16_t ke
     optimize_node(m, value, level);
 }
 
+/* optimizeNodesAndFailTransitions of WholeWordLongestMatchSet.java:224-247 / WholeWordLongestMatchMap.java:362-386:
+ * the fail match of a node is the deepest keyword on its path that is followed (on the path) by a non-word char. */
+static void visit_wwlongest(ora_matcher *m, NQueue *q, Node *parent, uint16_t key, Node *value, int32_t level) {
+    optimize_node(m, value, level);
+    if (parent->matchLength != 0 && !m->wordChars[key]) {
+        value->failMatchLength = parent->matchLength;
+        value->failMatchOffset = 1;
+        value->failValue = parent->value;
+    } else {
+        value->failMatchLength = parent->failMatchLength;
+        value->failMatchOffset = parent->failMatchOffset + 1;
+        value->failValue = parent->failValue;
+    }
+    if (!is_empty(value)) {
+        q_push(q, value);
+    }
+}
+
 /* enqueueNodesVisitor — AhoCorasickSet.java:147-155 */
 static void visit_enqueue(ora_matcher *m, NQueue *q, Node *parent, uint16_t key, Node *value, int32_t level) {
     (void)m;
@@ -531,7 +553,7 @@ ora_matcher *ora_create(int family, const uint16_t *chars, const int64_t *offset
     int64_t n = n_keywords;
     if (m->is_map && n_values < n) n = n_values;
 
-    if (family == ORA_WHOLEWORD) {
+    if (family == ORA_WHOLEWORD || family == ORA_WHOLEWORDLONGEST) {
         m->wordChars = (uint8_t *)malloc(65536);
         if (word_chars) {
             memcpy(m->wordChars, word_chars, 65536);
@@ -549,7 +571,22 @@ ora_matcher *ora_create(int family, const uint16_t *chars, const int64_t *offset
         if (is_null && is_null[k]) continue;
         const uint16_t *kw = chars + offsets[k];
         int32_t len = (int32_t)(offsets[k + 1] - offsets[k]);
-        if (family == ORA_WHOLEWORD) {
+        if (family == ORA_WHOLEWORDLONGEST) {
+            /* WholeWordLongestMatchSet.java:190-206 / WholeWordLongestMatchMap.java:322-344: trim, no validation */
+            int32_t ws, we;
+            trim_keyword(kw, len, m->wordChars, &ws, &we);
+            kw += ws;
+            len = we - ws;
+            if (len > 0) {
+                if (len > longestKeyword) longestKeyword = len;
+                Node *currentNode = m->root;
+                for (int32_t idx = 0; idx < len; idx++) {
+                    currentNode = get_or_add_child(m, currentNode, cs ? kw[idx] : g_lower[kw[idx]]);
+                }
+                currentNode->matchLength = len;
+                currentNode->value = m->is_map ? (int32_t)k : -1;
+            }
+        } else if (family == ORA_WHOLEWORD) {
             /* WholeWordMatchSet.java:145-166 / WholeWordMatchMap.java:262-285 */
             int32_t ws, we;
             trim_keyword(kw, len, m->wordChars, &ws, &we);
@@ -606,6 +643,9 @@ ora_matcher *ora_create(int family, const uint16_t *chars, const int64_t *offset
         break;
     case ORA_WHOLEWORD:
         bfs(m, &q, visit_wholeword);
+        break;
+    case ORA_WHOLEWORDLONGEST:
+        bfs(m, &q, visit_wwlongest);
         break;
     default:
         free(q.a);
@@ -1128,6 +1168,119 @@ main_loop_end:
     free(buf.a);
 }
 
+/* ------------------------------------------------------------------ WholeWordLongest */
+
+/* WholeWordLongestMatchSet.match — WholeWordLongestMatchSet.java:47-182 / WholeWordLongestMatchMap.java:183-310 */
+static inline __attribute__((always_inline)) void wwlongest_match_string(const ora_matcher *m, const uint16_t *haystack,
+                                                                        int32_t len, Sink *s, const int cs) {
+    const uint8_t *wordChars = m->wordChars;
+    const Node *root = m->root;
+    const Node *currentNode = root;
+    int32_t idx = 0;
+    while (idx < len) {
+        uint16_t c = cs ? haystack[idx] : g_lower[haystack[idx]];
+        const Node *nextNode = get_transition(currentNode, c);
+        if (nextNode == NULL) {
+            if (!wordChars[c]) {
+                if (currentNode->matchLength != 0) {
+                    if (!emit(s, idx - currentNode->matchLength, idx, currentNode->value)) {
+                        return;
+                    }
+                } else if (currentNode->failMatchLength != 0) {
+                    int32_t failMatchEnd = idx - currentNode->failMatchOffset;
+                    if (!emit(s, failMatchEnd - currentNode->failMatchLength, failMatchEnd, currentNode->failValue)) {
+                        return;
+                    }
+                }
+            } else {
+                if (currentNode->failMatchLength != 0) {
+                    int32_t failMatchEnd = idx - currentNode->failMatchOffset;
+                    if (!emit(s, failMatchEnd - currentNode->failMatchLength, failMatchEnd, currentNode->failValue)) {
+                        return;
+                    }
+                }
+                while (++idx < len && wordChars[haystack[idx]]) {
+                    ;
+                }
+            }
+            while (++idx < len && !wordChars[haystack[idx]]) {
+                ;
+            }
+            currentNode = root;
+        } else {
+            ++idx;
+            currentNode = nextNode;
+        }
+    }
+    if (currentNode->matchLength != 0) {
+        if (!emit(s, idx - currentNode->matchLength, idx, currentNode->value)) {
+            return;
+        }
+    } else if (currentNode->failMatchLength != 0) {
+        int32_t failMatchEnd = idx - currentNode->failMatchOffset;
+        if (!emit(s, failMatchEnd - currentNode->failMatchLength, failMatchEnd, currentNode->failValue)) {
+            return;
+        }
+    }
+}
+
+/* WholeWordLongestMatchMap.match(Readable) — WholeWordLongestMatchMap.java:54-181 (scroll: :401-414, same as the
+ * WholeWordMatchMap one) */
+static void wwlongest_match_readable(const ora_matcher *m, Reader *haystack, Sink *s, const int cs) {
+    const uint8_t *wordChars = m->wordChars;
+    const Node *root = m->root;
+    const Node *currentNode = root;
+    CharBuf buf = {(uint16_t *)malloc((size_t)m->charBufferSize * 2), m->charBufferSize, 0, m->charBufferSize};
+    while (reader_read(haystack, &buf) != -1) {
+        buf_flip(&buf);
+        while (buf_has_remaining(&buf)) {
+            uint16_t c = buf_get(&buf);
+            if (!cs) c = g_lower[c];
+            const Node *nextNode = get_transition(currentNode, c);
+            if (nextNode == NULL) {
+                if (!wordChars[c]) {
+                    if (currentNode->matchLength != 0) {
+                        if (!emit(s, -1, -1, currentNode->value)) {
+                            free(buf.a);
+                            return;
+                        }
+                    } else if (currentNode->failMatchLength != 0) {
+                        if (!emit(s, -1, -1, currentNode->failValue)) {
+                            free(buf.a);
+                            return;
+                        }
+                    }
+                } else {
+                    if (currentNode->failMatchLength != 0) {
+                        if (!emit(s, -1, -1, currentNode->failValue)) {
+                            free(buf.a);
+                            return;
+                        }
+                    }
+                    if (ww_scroll(m, haystack, &buf, 1, cs)) {
+                        currentNode = root;
+                        goto main_loop_end;
+                    }
+                }
+                currentNode = root;
+                if (ww_scroll(m, haystack, &buf, 0, cs)) {
+                    goto main_loop_end;
+                }
+            } else {
+                currentNode = nextNode;
+            }
+        }
+        buf_clear(&buf);
+    }
+main_loop_end:
+    if (currentNode->matchLength != 0) {
+        emit(s, -1, -1, currentNode->value);
+    } else if (currentNode->failMatchLength != 0) {
+        emit(s, -1, -1, currentNode->failValue);
+    }
+    free(buf.a);
+}
+
 /* ------------------------------------------------------------------ public entry points */
 
 int64_t ora_match_string(const ora_matcher *m, const uint16_t *hay, int32_t n, ora_listener cb, void *ctx) {
@@ -1149,6 +1302,10 @@ int64_t ora_match_string(const ora_matcher *m, const uint16_t *hay, int32_t n, o
         if (m->caseSensitive) wholeword_match_string(m, hay, n, &s, 1);
         else wholeword_match_string(m, hay, n, &s, 0);
         break;
+    case ORA_WHOLEWORDLONGEST:
+        if (m->caseSensitive) wwlongest_match_string(m, hay, n, &s, 1);
+        else wwlongest_match_string(m, hay, n, &s, 0);
+        break;
     }
     return s.calls;
 }
@@ -1169,6 +1326,9 @@ int64_t ora_match_readable(const ora_matcher *m, const uint16_t *hay, int64_t n,
         break;
     case ORA_WHOLEWORD:
         wholeword_match_readable(m, &r, &s, m->caseSensitive);
+        break;
+    case ORA_WHOLEWORDLONGEST:
+        wwlongest_match_readable(m, &r, &s, m->caseSensitive);
         break;
     }
     return s.calls;

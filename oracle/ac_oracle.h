@@ -31,7 +31,8 @@ enum {
     ORA_AHOCORASICK = 0, /* AhoCorasickSet.java / AhoCorasickMap.java */
     ORA_LONGEST = 1,     /* LongestMatchSet.java / LongestMatchMap.java */
     ORA_SHORTEST = 2,    /* ShortestMatchSet.java / ShortestMatchMap.java */
-    ORA_WHOLEWORD = 3    /* WholeWordMatchSet.java / WholeWordMatchMap.java */
+    ORA_WHOLEWORD = 3,   /* WholeWordMatchSet.java / WholeWordMatchMap.java */
+    ORA_WHOLEWORDLONGEST = 4 /* WholeWordLongestMatchSet.java / WholeWordLongestMatchMap.java */
 };
 
 typedef struct ora_matcher ora_matcher;

@@ -16,8 +16,9 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
-AHOCORASICK, LONGEST, SHORTEST, WHOLEWORD = 0, 1, 2, 3
-FAMILIES = {"ahocorasick": AHOCORASICK, "longest": LONGEST, "shortest": SHORTEST, "wholeword": WHOLEWORD}
+AHOCORASICK, LONGEST, SHORTEST, WHOLEWORD, WHOLEWORDLONGEST = 0, 1, 2, 3, 4
+FAMILIES = {"ahocorasick": AHOCORASICK, "longest": LONGEST, "shortest": SHORTEST, "wholeword": WHOLEWORD,
+            "wholewordlongest": WHOLEWORDLONGEST}
 
 
 def build(force: bool = False) -> str:

@@ -147,4 +147,71 @@ def wholeword(keywords, hay, cs=True, n_values=-1, is_word=default_word_char):
     return out
 
 
-MODELS = {"ahocorasick": ahocorasick, "longest": longest, "shortest": shortest, "wholeword": wholeword}
+def wholewordlongest(keywords, hay, cs=True, n_values=-1, is_word=default_word_char):
+    """WholeWordLongestMatchSet/Map (WholeWordLongestMatchSet.java:47-182), from the definition: a walk starts at
+    position 0 and then at word starts; from a start s it reports the LONGEST keyword that is a prefix of hay[s:] and is
+    followed by a non-word char or the end of the input; the walk consumes hay[s:idx] where idx is the first position at
+    which hay[s:idx+1] is no longer a prefix of any keyword, and the next walk starts at the first word start after idx
+    (words inside the consumed stretch are never rescanned).  Keywords are trimmed, not validated; last duplicate wins.
+    Valid when is_word(fold(c)) == is_word(c) for every haystack char."""
+    n = len(keywords) if n_values < 0 else min(len(keywords), n_values)
+    d: Dict[str, int] = {}
+    for i in range(n):
+        k = keywords[i]
+        if k is None:
+            continue
+        idx = [j for j, c in enumerate(k) if is_word(c)]
+        if idx:
+            k = k[idx[0]:idx[-1] + 1]
+        if len(k) == 0:
+            continue
+        d[fold(k, cs)] = i if n_values >= 0 else -1
+    prefixes = {k[:j] for k in d for j in range(1, len(k) + 1)}
+    h = fold(hay, cs)
+    nh = len(hay)
+    out = []
+    s = 0
+    while s < nh:
+        L = 0
+        while s + L < nh and h[s:s + L + 1] in prefixes:
+            L += 1
+        for dlen in range(L, 0, -1):
+            if h[s:s + dlen] in d and (s + dlen == nh or not is_word(h[s + dlen])):
+                out.append((s, s + dlen, d[h[s:s + dlen]]))
+                break
+        p = s + L + 1
+        while p < nh and not (is_word(hay[p]) and not is_word(hay[p - 1])):
+            p += 1
+        s = p
+    return out
+
+
+def reference_count_wholewordlongest(keywords, hay, is_word=default_word_char):
+    """The brute-force count the reference's own test asserts against (WholeWordLongestMatchTest.java:48-66):
+    keywords trimmed and sorted longest first, boundaries tested with Character.isLetterOrDigit."""
+    kws = []
+    for k in keywords:
+        idx = [j for j, c in enumerate(k) if is_word(c)]
+        kws.append(k[idx[0]:idx[-1] + 1] if idx else k)
+    kws.sort(key=lambda k: -len(k))
+    count = 0
+    i = 0
+    nh = len(hay)
+    while i < nh:
+        for needle in kws:
+            e = i + len(needle)
+            if (len(needle) > 0 and e <= nh and hay[i:e] == needle and (e == nh or not is_letter_or_digit(hay[e]))
+                    and (i == 0 or not is_letter_or_digit(hay[i - 1]))):
+                count += 1
+                i += len(needle) - 1
+                i += 1
+                while i < nh and not is_word(hay[i]):
+                    i += 1
+                i -= 1
+                break
+        i += 1
+    return count
+
+
+MODELS = {"ahocorasick": ahocorasick, "longest": longest, "shortest": shortest, "wholeword": wholeword,
+          "wholewordlongest": wholewordlongest}

@@ -25,9 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.dirname(HERE))
 
-from golden_cases import ILLEGAL, LITERAL_CASES, MATCH_QUEUE_KATS  # noqa: E402
-
-FAMILIES = ("ahocorasick", "longest", "shortest", "wholeword")
+from golden_cases import FAMILIES, ILLEGAL, LITERAL_CASES, MATCH_QUEUE_KATS  # noqa: E402
 
 
 def reference_kats():
@@ -75,6 +73,12 @@ def seeded_cases():
     # 6: long nested keywords up to 16 chars
     kws = ["a" * i for i in range(1, 17)] + ["ab" * i for i in range(1, 9)]
     cases.append(dict(name="nested16", keywords=kws, haystack="a" * 20 + "b" + "ab" * 9 + "aab", case_sensitive=True))
+    # 7: multi-word keywords (WholeWordLongest: carried fail matches, consumed words are not rescanned; the plain
+    #    WholeWord constructor rejects them)
+    kws = ["new york", "new", "york city", "new york city hall", "city", "hall of fame", "of", "  padded  ", "x-ray", "x"]
+    hay = ("new york city hall, new york city halls new yorker; york city new-york hall of fame of fames "
+           "padded x-ray x ray new york city hall")
+    cases.append(dict(name="multi_word", keywords=kws, haystack=hay, case_sensitive=False))
     return cases
 
 
@@ -88,7 +92,7 @@ def main():
         entry["streams"] = {}
         for fam in FAMILIES:
             wc = None
-            if c.get("word_chars") and fam == "wholeword":
+            if c.get("word_chars") and fam.startswith("wholeword"):
                 w = c["word_chars"]
                 wc = ora.word_chars(w["mode"], w["chars"], w["toggles"])
             try:

@@ -44,7 +44,8 @@ LITERAL_CASES = {
         "shortest": [(2, 4), (5, 6), (6, 7)],
         "wholeword": []}),
     "testLiteral": (FOX, FOX_WORDS, {
-        "ahocorasick": FOX_STREAM, "longest": FOX_STREAM, "shortest": FOX_STREAM, "wholeword": FOX_STREAM}),
+        "ahocorasick": FOX_STREAM, "longest": FOX_STREAM, "shortest": FOX_STREAM, "wholeword": FOX_STREAM,
+        "wholewordlongest": FOX_STREAM}),
     "testLongestMatch": ("XXXYYZZ", ["XXX", "YY", "XXXYYZZZ"], {
         "ahocorasick": [(0, 3), (3, 5)], "longest": [(0, 3), (3, 5)], "shortest": [(0, 3), (3, 5)],
         "wholeword": []}),
@@ -52,7 +53,7 @@ LITERAL_CASES = {
         "ahocorasick": [(0, 1), (0, 2), (1, 2), (0, 3), (1, 3), (2, 3), (0, 4), (1, 4), (2, 4), (3, 4)],
         "longest": [(0, 4)],
         "shortest": [(0, 1), (1, 2), (2, 3), (3, 4)],
-        "wholeword": [(0, 4)]}),
+        "wholeword": [(0, 4)], "wholewordlongest": [(0, 4)]}),
     "testOverlap2": (" aaaaaaa aaababababaabaa ", A4, {
         "ahocorasick": 37,
         "longest": [(1, 5), (5, 8), (9, 12), (13, 14), (15, 16), (17, 18), (19, 21), (22, 24)],
@@ -62,18 +63,26 @@ LITERAL_CASES = {
         "ahocorasick": [(2, 7)], "longest": [(2, 7)], "shortest": [(2, 7)]}),
     "testLongKeywords": ("a" * 100, A100, {
         "ahocorasick": 5050, "longest": [(0, 100)],
-        "shortest": [(i, i + 1) for i in range(100)], "wholeword": [(0, 100)]}),
+        "shortest": [(i, i + 1) for i in range(100)], "wholeword": [(0, 100)], "wholewordlongest": [(0, 100)]}),
     "readmeLongest": ("a1b2c3d4", ["b", "b2", "2c3d4"], {"longest": [(2, 4)]}),
     "readmeShortest1": ("a1b2c3d4", ["2", "b2", "2c3d4"], {"shortest": [(2, 4)]}),
     "readmeShortest2": ("a1b2c3d4", ["b", "2", "b2"], {"shortest": [(2, 3), (3, 4)]}),
     "readmeWholeWord": ("late evening", ["la", "late", "eve", "evening"], {"wholeword": [(0, 4), (5, 12)]}),
     "testWholeWordLongest1": ("as if", ["as", "if", "as if"], {
         "ahocorasick": [(0, 2), (0, 5), (3, 5)], "longest": [(0, 5)], "shortest": [(0, 2), (3, 5)],
-        "wholeword": ILLEGAL}),
+        "wholeword": ILLEGAL, "wholewordlongest": [(0, 5)]}),
+    # SetTest.java:124-130 (testWholeWordLongest) and README.md:124; the reference asserts the counts
+    "testWholeWordLongest2": ("ax if", ["as", "if", "as if"], {"wholewordlongest": [(3, 5)]}),
+    "testWholeWordLongest3": ("as in", ["as", "if", "as if"], {"wholewordlongest": [(0, 2)]}),
+    "testWholeWordLongest4": ("123 4x 1234 5x 1234 56 123 45 1x 345 12 34x 12 345x 123xb 1234 56s",
+                              ["123", "123 45", "1234 56", "12 345"], {
+        "wholewordlongest": [(0, 3), (15, 22), (23, 29)]}),
+    "testWholeWordLongest5": ("abc 12", ["abc", "abc 123"], {"wholewordlongest": [(0, 3)]}),
+    "readmeWholeWordLongest": ("as of", ["as", "if", "as if"], {"wholewordlongest": [(0, 2)]}),
     "divergenceProbe": ("abcd", ["abcd", "bc", "d"], {"shortest": [(1, 3), (3, 4)], "longest": [(0, 4)]}),
     "testFullNode": ("\u0000\uffff\ufffe", [chr(i) for i in range(65536)], {
         "ahocorasick": [(0, 1), (1, 2), (2, 3)], "longest": [(0, 1), (1, 2), (2, 3)],
         "shortest": [(0, 1), (1, 2), (2, 3)], "wholeword": ILLEGAL}),
 }
 
-FAMILIES = ("ahocorasick", "longest", "shortest", "wholeword")
+FAMILIES = ("ahocorasick", "longest", "shortest", "wholeword", "wholewordlongest")

@@ -17,9 +17,9 @@ import ahocorasick_b200 as ac  # noqa: E402
 import workloads as W  # noqa: E402
 
 SETS = {"ahocorasick": ac.AhoCorasickSet, "longest": ac.LongestMatchSet, "shortest": ac.ShortestMatchSet,
-        "wholeword": ac.WholeWordMatchSet}
+        "wholeword": ac.WholeWordMatchSet, "wholewordlongest": ac.WholeWordLongestMatchSet}
 MAPS = {"ahocorasick": ac.AhoCorasickMap, "longest": ac.LongestMatchMap, "shortest": ac.ShortestMatchMap,
-        "wholeword": ac.WholeWordMatchMap}
+        "wholeword": ac.WholeWordMatchMap, "wholewordlongest": ac.WholeWordLongestMatchMap}
 
 
 class Collect:
@@ -275,7 +275,7 @@ def test_committed_fixture_streams(case):
     for fam in FAMILIES:
         want = case["streams"][fam]
         extra = ()
-        if case.get("word_chars") and fam == "wholeword":
+        if case.get("word_chars") and fam.startswith("wholeword"):
             w = case["word_chars"]
             extra = (w["chars"], w["toggles"])
         if "error" in want:
@@ -492,3 +492,51 @@ def test_ww_hash_path_shapes(cs):
     want = oracle_stream(ora.Matcher("wholeword", kws[:500]), dense)
     pos, _ = _records(ac.WholeWordMatchSet(kws[:500], True), dense)
     assert pos == [(s, e) for s, e, _ in want] and len(pos) == 30_000
+
+
+# ---------------------------------------------------------------- WholeWordLongest (the fifth public family)
+
+@pytest.mark.parametrize("cs", [True, False])
+def test_wholewordlongest_multiword_fuzz(cs):
+    """Keywords with inner / outer non-word chars, walks that consume several words, carried fail matches, walk start
+    at position 0 on a non-word char: ordered Set and Map streams equal the oracle's."""
+    from test_oracle_golden import _wwl_case
+    rng = random.Random(9001 + cs)
+    for it in range(120):
+        kws, hay = _wwl_case(rng)
+        hay = hay * rng.choice([1, 1, 7])
+        nv = rng.choice([len(kws), max(0, len(kws) - 1)])
+        want = oracle_stream(ora.Matcher("wholewordlongest", kws, n_values=nv, case_sensitive=cs), hay)
+        got = gpu_map_stream(ac.WholeWordLongestMatchMap(kws, list(range(nv)), cs), hay)
+        assert got == want, (kws, hay, cs, nv)
+        want_set = oracle_stream(ora.Matcher("wholewordlongest", kws, case_sensitive=cs), hay)
+        assert gpu_set_stream(ac.WholeWordLongestMatchSet(kws, cs), hay) == [(s, e) for s, e, _ in want_set]
+
+
+def test_wholewordlongest_phrases_large():
+    """A phrase dictionary over a 300 000-char text (many selection tiles; walks cross tile boundaries), String and
+    Readable overloads, early stop."""
+    rng = random.Random(31337)
+    vocab = ["new", "york", "city", "hall", "of", "fame", "san", "jose", "los", "angeles", "x-ray", "st", "louis", "a", "b"]
+    kws = sorted({" ".join(rng.choice(vocab) for _ in range(rng.randint(1, 4))) for _ in range(400)}) + ["  padded  ", "st. louis"]
+    seps = [" ", " ", " ", ", ", ". ", "  ", "; ", "-", "_"]
+    parts, total = [], 0
+    while total < 300_000:
+        w = rng.choice(vocab + ["yorker", "halls", "zz"])
+        sp = rng.choice(seps)
+        parts.append(w + sp)
+        total += len(w) + len(sp)
+    hay = "".join(parts)
+    values = list(range(len(kws)))
+    om = ora.Matcher("wholewordlongest", kws, n_values=len(kws), case_sensitive=False)
+    want = oracle_stream(om, hay)
+    gm = ac.WholeWordLongestMatchMap(kws, values, False)
+    assert gpu_map_stream(gm, hay) == want and len(want) > 20_000
+    for block in (4096, 1 << 16):
+        from ahocorasick_b200.streaming import match_readable
+        got = []
+        match_readable(gm, io.StringIO(hay), lambda v: got.append(v) or True, block_chars=block)
+        assert got == [int(r["value"]) for r in om.match(hay, readable=True)]
+    for stop in (1, 5, 1000):
+        want_s = [(s, e) for s, e, _ in oracle_stream(om, hay, stop_after=stop)]
+        assert gpu_set_stream(ac.WholeWordLongestMatchSet(kws, False), hay, stop_after=stop) == want_s

@@ -167,6 +167,50 @@ def test_fuzz_against_spec(family, cs):
             assert [int(r["value"]) for r in rv] == [v for _, _, v in want]
 
 
+def _wwl_case(rng):
+    """Dictionaries whose keywords hold non-word chars inside / around them, haystacks of words and punctuation."""
+    letters = rng.choice(["ab", "abc", "abAB", "aβΒb"])
+    seps = rng.choice([" ", " ,", " -_"])
+    kws = []
+    for _ in range(rng.randint(0, 8)):
+        words = [_rand_word(rng, letters, 1, 3) for _ in range(rng.randint(1, 3))]
+        kw = rng.choice(seps).join(words)
+        if rng.random() < 0.25:
+            kw = rng.choice([" ", ",", ""]) + kw + rng.choice([" ", ", ", ""])
+        kws.append(kw)
+    if rng.random() < 0.2:
+        kws.insert(rng.randint(0, len(kws)), rng.choice([None, "", " ", ","]))
+    hay = "".join(rng.choice(letters * 2 + seps) for _ in range(rng.randint(0, 80)))
+    return kws, hay
+
+
+@pytest.mark.parametrize("cs", [True, False])
+def test_wholewordlongest_fuzz_against_spec(cs):
+    """WholeWordLongest with multi-word keywords: literal oracle == the definition-level model (ordered, with
+    values, String and Readable overloads), and the count equals the reference's own brute force
+    (WholeWordLongestMatchTest.java:48-66) whenever that brute force applies (case-sensitive, no '-'/'_')."""
+    rng = random.Random(7117 + cs)
+    for it in range(1500):
+        kws, hay = _wwl_case(rng)
+        nv = rng.choice([-1, len(kws), max(0, len(kws) - 1)])
+        m = ora.Matcher("wholewordlongest", kws, n_values=nv, case_sensitive=cs)
+        got = stream_v(m.match(hay))
+        want = spec.wholewordlongest(kws, hay, cs, nv)
+        assert got == want, (kws, hay, cs, nv)
+        if nv >= 0:
+            rv = m.match(hay, readable=True)
+            assert [int(r["value"]) for r in rv] == [v for _, _, v in want]
+
+
+def test_wholewordlongest_reference_bruteforce_counts():
+    """The reference's test asserts count == its brute force on its literal inputs (SetTest.java:124-130)."""
+    for name, (hay, kws, expect) in LITERAL_CASES.items():
+        if "wholewordlongest" not in expect or len(kws) > 1000:
+            continue
+        got = ora.Matcher("wholewordlongest", kws).match(hay)
+        assert len(got) == spec.reference_count_wholewordlongest(kws, hay), name
+
+
 def test_reference_random_unicode_dictionary():
     """Generator.randomStrings(n, 2, 3) style (Generator.java:61-76): length-2 keywords, 50% Latin-1,
     50% anywhere in the BMP — exercises wide alphabets (testFullRandom, SetTest.java:81-89)."""
@@ -213,7 +257,7 @@ def test_oracle_reproduces_committed_streams(case):
     for fam in FAMILIES:
         want = case["streams"][fam]
         wc = None
-        if case.get("word_chars") and fam == "wholeword":
+        if case.get("word_chars") and fam.startswith("wholeword"):
             w = case["word_chars"]
             wc = ora.word_chars(w["mode"], w["chars"], w["toggles"])
         if "error" in want:
