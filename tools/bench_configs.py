@@ -36,8 +36,11 @@ def matchers_for(idx, cfg):
         return [("LongestMatchMap", ac.LongestMatchMap(kws, vals, True)), ("ShortestMatchSet", ac.ShortestMatchSet(kws, True))]
     if idx == 3:
         wc, tg = cfg["word_chars"]
+        # the same text with a phrase dictionary (every tenth entry is a two-word keyword)
+        phrases = kws + [kws[i] + " " + kws[i + 1] for i in range(0, len(kws) - 1, 10)]
         return [("WholeWordMatchSet", ac.WholeWordMatchSet(kws, True, wc, tg)),
-                ("WholeWordMatchMap", ac.WholeWordMatchMap(kws, vals, True, wc, tg))]
+                ("WholeWordMatchMap", ac.WholeWordMatchMap(kws, vals, True, wc, tg)),
+                ("WholeWordLongestMatchSet(+phrases)", ac.WholeWordLongestMatchSet(phrases, True, wc, tg))]
     raise ValueError(idx)
 
 
