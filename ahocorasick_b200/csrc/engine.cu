@@ -675,6 +675,14 @@ int ensure_device(Matcher *m) {
         CU_TRY(cudaFuncSetAttribute(k_sel_emit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelEmitSmem));
         CU_TRY(cudaFuncSetAttribute(k_sel_emit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSelEmitSmem));
         CU_TRY(cudaFuncSetAttribute(k_sel2_top, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        // static + dynamic shared memory of the selection kernels passes 48 KB
+        const int s2_smem = kS2SmemWords * 4;
+        CU_TRY(cudaFuncSetAttribute(k_sel2_map<kModeLongest>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2_smem));
+        CU_TRY(cudaFuncSetAttribute(k_sel2_map<kModeShortest>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2_smem));
+        CU_TRY(cudaFuncSetAttribute(k_sel2_emit<kModeLongest>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2_smem));
+        CU_TRY(cudaFuncSetAttribute(k_sel2_emit<kModeShortest>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2_smem));
+        CU_TRY(cudaFuncSetAttribute(k_sel2_fused<kModeLongest>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2_smem));
+        CU_TRY(cudaFuncSetAttribute(k_sel2_fused<kModeShortest>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2_smem));
         m->sel_attr_set = true;
     }
     return ACGPU_OK;

@@ -32,11 +32,12 @@ constexpr int kS2Threads = 256;
 constexpr int kS2Sub = 32;                       // positions per lane
 constexpr int kS2Tile = kS2Threads * kS2Sub;     // positions per CTA tile
 constexpr int kS2Ent = 16;                       // entry offsets of a map (exit offsets are < max_len <= 16)
-constexpr int kS2LmapStride = 17;                // words per lane in the entry-window array (conflict-free both ways)
+constexpr int kS2LmapStride = 17;                // halfwords per lane in the entry-window array (odd: conflict-light both ways)
 constexpr int kS2Group = 256;                    // tiles per composition group
-// shared words: [lane entry windows: positions 0..15 of every lane][positions 16..31, position-major]
-constexpr int kS2LmapWords = kS2Threads * kS2LmapStride;
-constexpr int kS2SmemWords = kS2LmapWords + 16 * kS2Threads;
+// shared words: [32 positions x 256 threads, position-major (bank = lane: conflict-free for the resolution)] followed by
+// the lane entry windows: (exit, matches) of positions 0..15 of every lane as halfwords, lane-major, for the map walks
+constexpr int kS2LmapWords = (kS2Threads * kS2LmapStride + 1) / 2;
+constexpr int kS2SmemWords = kS2Sub * kS2Threads + kS2LmapWords;
 
 struct Sel2Args {
     const uint32_t *masks;          // start masks, two positions per word, index space [0, n_idx)
@@ -65,9 +66,7 @@ struct Sel2Args {
 // word of one position p of a lane's sub-tile (all relative to the sub-tile start a):
 //   bits 0..3 exit offset of the chain standing at p | 4..9 matches emitted from p to the exit | 10..15 J(p) - a
 //   | 16..21 start of the match emitted at p - a | 22 a match is emitted at p
-__device__ __forceinline__ uint32_t s2_idx(int k, int tid) {
-    return k < 16 ? (uint32_t)(tid * kS2LmapStride + k) : (uint32_t)(kS2LmapWords + (k - 16) * kS2Threads + tid);
-}
+__device__ __forceinline__ uint16_t *s2_lmap(uint32_t *s_w) { return reinterpret_cast<uint16_t *>(s_w + kS2Sub * kS2Threads); }
 
 // masks of the lane's 32 positions (mw) and of the 16 positions right of them (hw)
 __device__ __forceinline__ void s2_load(const Sel2Args &P, int64_t tile, uint32_t (&mw)[16], uint32_t (&hw)[8]) {
@@ -93,8 +92,8 @@ __device__ __forceinline__ void s2_load(const Sel2Args &P, int64_t tile, uint32_
     }
 }
 
-// Right-to-left resolution of the lane's 32 positions into s_w (see the word layout above).  Branch-free: every position
-// costs the same ~20 instructions in every lane (the divergent version ran at 17 of 32 lanes).
+// Right-to-left resolution of the lane's 32 positions into s_w (see the word layout above).  Branch-free; the fields
+// are kept in place (no re-packing), addresses are position * 256 + thread.
 template <int MODE>
 __device__ __forceinline__ void s2_resolve(const uint32_t (&mw)[16], const uint32_t (&hw)[8], uint32_t *s_w) {
     const int tid = threadIdx.x;
@@ -109,10 +108,12 @@ __device__ __forceinline__ void s2_resolve(const uint32_t (&mw)[16], const uint3
             h_start = better ? (uint32_t)(32 + k) : h_start;
         }
     }
-    // state: the chain standing here jumps to nx (32 = leaves the sub-tile without a match) emitting (st, nx) if em
-    uint32_t nx = 32u, st = 0u, em = 0u;
+    // state: the chain standing here jumps to nx (32 = leaves the sub-tile without a match); hi = nx << 10 | start << 16 |
+    // emits << 22 (the upper fields of the word), emf = 16 once a match is emitted (the "1 match" of the count field)
+    uint32_t nx = 32u, hi = 32u << 10, emf = 0u;
     uint32_t b_end = 0xFFFFu, b_start = 0u;
-    const uint32_t base_lo = (uint32_t)tid * kS2LmapStride, base_hi = (uint32_t)kS2LmapWords - 16u * kS2Threads + (uint32_t)tid;
+    uint32_t *col = s_w + tid;
+    uint16_t *lm = s2_lmap(s_w) + tid * kS2LmapStride;
 #pragma unroll
     for (int k = 31; k >= 0; k--) {
         const uint32_t m = (mw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
@@ -120,30 +121,26 @@ __device__ __forceinline__ void s2_resolve(const uint32_t (&mw)[16], const uint3
         if (MODE == kModeLongest) {
             const uint32_t e = (uint32_t)k + 17u - (uint32_t)__ffs((int)m);  // + 16 - (lowest set bit)
             nx = has ? e : nx;
-            st = has ? (uint32_t)k : st;
+            hi = has ? (e << 10) + (((uint32_t)k << 16) | (1u << 22)) : hi;
         } else {
             const uint32_t e = (uint32_t)k + (uint32_t)__clz((int)m) - 15u;
             const bool better = has && e <= b_end;
             b_end = better ? e : b_end;
             b_start = better ? (uint32_t)k : b_start;
             const bool halo = h_end < b_end;
-            nx = halo ? h_end : b_end;
-            st = halo ? h_start : b_start;
-            nx = b_end == 0xFFFFu ? 32u : nx;  // no candidate inside the sub-tile: skip to its end (the halo is the next lane's)
+            const uint32_t cand = halo ? h_end : b_end, st = halo ? h_start : b_start;
+            const bool any = b_end != 0xFFFFu;  // no candidate inside the sub-tile: skip to its end (the halo is the next lane's)
+            nx = any ? cand : 32u;
+            hi = any ? (cand << 10) | (st << 16) | (1u << 22) : (32u << 10);
         }
-        em |= has ? 1u : 0u;
-        const uint32_t nc = min(nx, 31u);
-        const uint32_t t = s_w[nc < 16u ? base_lo + nc : base_hi + nc * kS2Threads];
+        emf = has ? 16u : emf;
+        const uint32_t t = col[min(nx, 31u) * kS2Threads];
         const bool out = nx >= 32u;
-        const uint32_t x = out ? nx - 32u : (t & 15u);
-        const uint32_t c = out ? em : ((t >> 4) & 63u) + 1u;
-        s_w[s2_idx(k, tid)] = x | (c << 4) | (nx << 10) | (st << 16) | (em << 22);
+        const uint32_t lo = out ? (nx - 32u) | emf : (t & 0x3FFu) + 16u;  // exit offset | matches << 4
+        const uint32_t word = hi | lo;
+        col[k * kS2Threads] = word;
+        if (k < 16) lm[k] = (uint16_t)lo;
     }
-}
-
-// s2_idx with a run-time position
-__device__ __forceinline__ uint32_t s2_idx_rt(uint32_t k, int tid) {
-    return k < 16u ? (uint32_t)tid * kS2LmapStride + k : (uint32_t)kS2LmapWords + (k - 16u) * kS2Threads + (uint32_t)tid;
 }
 
 // Warp maps: s_wmap[warp * 16 + o] = exit offset | matches << 8 of the warp's 1 024 positions entered at offset o.
@@ -152,15 +149,16 @@ __device__ __forceinline__ uint32_t s2_idx_rt(uint32_t k, int tid) {
 template <bool TRAJ>
 __device__ __forceinline__ void s2_warp_maps(const uint32_t *s_w, uint32_t *s_wmap, uint16_t *s_traj) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint16_t *lmap = s2_lmap(const_cast<uint32_t *>(s_w));
     __syncwarp();
     if (lane < kS2Ent) {
         uint32_t cur = lane, cnt = 0;
 #pragma unroll 4
         for (int l = 0; l < 32; l++) {
             if (TRAJ) s_traj[(warp * 32 + l) * kS2Ent + lane] = (uint16_t)(cur | (cnt << 4));
-            const uint32_t t = s_w[(warp * 32 + l) * kS2LmapStride + cur];
+            const uint32_t t = lmap[(warp * 32 + l) * kS2LmapStride + cur];
             cur = t & 15u;
-            cnt += (t >> 4) & 63u;
+            cnt += t >> 4;
         }
         s_wmap[warp * kS2Ent + lane] = cur | (cnt << 8);
     }
@@ -311,7 +309,7 @@ __global__ void __launch_bounds__(kS2Threads, 4) k_sel2_emit(const Sel2Args P) {
         uint32_t p = eo & 15u;
         const int32_t a32 = (int32_t)a + P.pos_base;
         while (p < 32u) {
-            const uint32_t w = s_w[s2_idx_rt(p, tid)];
+            const uint32_t w = s_w[p * kS2Threads + tid];
             if ((w >> 22) & 1u) {
                 if (idx < (unsigned long long)P.cap)
                     __stcs(&P.pos_out[idx], make_int2(a32 + (int32_t)((w >> 16) & 63u), a32 + (int32_t)((w >> 10) & 63u)));
@@ -478,7 +476,7 @@ __global__ void __launch_bounds__(kS2Threads, 4) k_sel2_fused(const Sel2Args P) 
         uint32_t p = eo & 15u;
         const int32_t a32 = (int32_t)a + P.pos_base;
         while (p < 32u) {
-            const uint32_t w = s_w[s2_idx_rt(p, tid)];
+            const uint32_t w = s_w[p * kS2Threads + tid];
             if ((w >> 22) & 1u) {
                 if (idx < (unsigned long long)P.cap)
                     __stcs(&P.pos_out[idx], make_int2(a32 + (int32_t)((w >> 16) & 63u), a32 + (int32_t)((w >> 10) & 63u)));

@@ -522,15 +522,20 @@ __global__ void __launch_bounds__(kThreads) k_sel_emit(const DevAutomaton A, con
             if (entry >= 0 && tid == 0) s_mark[entry] = 1;
             __syncthreads();
             // positions reachable from the entry: apply jump tables from the largest stride down
+            // (reads and writes of a round are separated by a barrier: a mark set in round r is only looked at from
+            // round r - 1 on, so the set of marks after every round is deterministic)
             for (int r = kSelLevels - 1; r >= 0; r--) {
                 const uint16_t *lv = s_lvl + r * kSelTile;
+                uint32_t tgt[kSelPer];
 #pragma unroll
                 for (int k = 0; k < kSelPer; k++) {
                     int p = tid + k * kThreads;
-                    if (s_mark[p]) {
-                        uint32_t a = lv[p];
-                        if (a < kSelTile) s_mark[a] = 1;
-                    }
+                    tgt[k] = s_mark[p] ? (uint32_t)lv[p] : (uint32_t)kSelTile;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < kSelPer; k++) {
+                    if (tgt[k] < kSelTile) s_mark[tgt[k]] = 1;
                 }
                 __syncthreads();
             }
