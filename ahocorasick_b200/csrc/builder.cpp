@@ -420,6 +420,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
             b += ws;
             len = we - ws;
             for (int32_t i = 0; i < len; i++) {
+                if (family == 4 && !wc[chars[b + i]]) a.ww_plain = false;
                 if (family == 3 && !wc[chars[b + i]]) {
                     throw IllegalArgument(utf8_of(chars + b, len) + " contains non-word characters.");
                 }
@@ -514,7 +515,10 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
         a.edges[i] = Edge{e.parent, e.cls, e.child, a.node_info[e.child]};
     }
     if (family != 4) build_tiers(a, node_parent, node_cls);
-    if (family == 3) build_ww(a, wc, node_parent, node_cls);
+    // WholeWordLongest with a dictionary whose (trimmed) keywords hold no non-word char: a walk can never leave its word
+    // (there is no transition on a non-word char) and a keyword followed by a non-word char is the whole word, so the
+    // family coincides with WholeWord and takes its hash path.
+    if (family == 3 || (family == 4 && a.ww_plain)) build_ww(a, wc, node_parent, node_cls);
     return a;
 }
 

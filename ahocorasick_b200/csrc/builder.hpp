@@ -176,6 +176,7 @@ struct HostAutomaton {
     std::vector<uint32_t> depth_count; // nodes per depth (diagnostics / tiering)
     TierTables tier;                   // generation-2 tables (tier.ok == false: not applicable)
     WwTables ww;                       // WholeWord hash tables (ww.ok == false: not applicable)
+    bool ww_plain = true;              // WholeWordLongest: no keyword holds a non-word char (then it equals WholeWord)
 };
 
 // Throws IllegalArgument with the reference's message for WholeWord keywords holding non-word chars.

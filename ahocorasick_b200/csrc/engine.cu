@@ -223,7 +223,7 @@ int upload_tier(Matcher *m) {
 int upload_ww(Matcher *m) {
     const WwTables &t = m->host.ww;
     m->use_ww = false;
-    if (!t.ok || m->host.family != ACGPU_WHOLEWORD) return ACGPU_OK;
+    if (!t.ok || (m->host.family != ACGPU_WHOLEWORD && m->host.family != ACGPU_WHOLEWORDLONGEST)) return ACGPU_OK;
     const char *force = getenv("ACGPU_FORCE_GEN1");
     if (force && force[0] == '1') return ACGPU_OK;
     size_t off = 0;
@@ -529,8 +529,8 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
         CU_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
         return ACGPU_OK;
     }
-    const bool chain = A.family != ACGPU_WHOLEWORD;
-    if (!chain && m->use_ww) {
+    const bool chain = A.family != ACGPU_WHOLEWORD && !(A.family == ACGPU_WHOLEWORDLONGEST && m->use_ww);
+    if (m->use_ww) {
         // WholeWord: one launch (kernel_ww.cuh); words starting in [ctx, chain_n) are reported
         const int64_t dom_lo = opt.ctx, dom_hi = chain_n;
         const int64_t mis = static_cast<int64_t>((reinterpret_cast<uintptr_t>(d_hay) >> 1) & 7);
@@ -1268,6 +1268,7 @@ int stream_process(StreamCtx *s, bool final, acgpu_result *out) {
         const int64_t D = 2 * L + 2;
         limit = final ? avail : std::max<int64_t>(s->ctx, avail - D);
     }
+    const bool plain_words = family == ACGPU_WHOLEWORD || (family == ACGPU_WHOLEWORDLONGEST && m->use_ww);
     fill_empty(out);
     if (limit <= s->ctx) return ACGPU_OK;
 
@@ -1320,7 +1321,7 @@ int stream_process(StreamCtx *s, bool final, acgpu_result *out) {
     if (d_val) cudaFreeAsync(d_val, s->st);
 
     // chain position for the next block
-    if (family == ACGPU_LONGEST || family == ACGPU_SHORTEST || family == ACGPU_WHOLEWORDLONGEST) {
+    if (!plain_words && family != ACGPU_AHOCORASICK) {
         int64_t carry = -1;
         CU_TRY(cudaMemcpyAsync(&carry, s->d_carry, sizeof(carry), cudaMemcpyDeviceToHost, s->st));
         CU_TRY(cudaStreamSynchronize(s->st));
