@@ -540,3 +540,40 @@ def test_wholewordlongest_phrases_large():
     for stop in (1, 5, 1000):
         want_s = [(s, e) for s, e, _ in oracle_stream(om, hay, stop_after=stop)]
         assert gpu_set_stream(ac.WholeWordLongestMatchSet(kws, False), hay, stop_after=stop) == want_s
+
+
+# ---------------------------------------------------------------- full-size dictionaries, large haystacks: properties
+
+@pytest.mark.parametrize("cfg,family", [(2, "longest"), (2, "shortest"), (3, "wholeword")])
+def test_large_haystack_two_generations_agree(cfg, family, monkeypatch):
+    """BASELINE configs[2] / configs[3] with their FULL dictionaries over 3*10^8 device-generated chars (too long for the
+    CPU oracle): the start-mask / hash kernels and the generation-1 anchored-trie kernels are independent
+    implementations, so identical record streams pin both; plus the stream properties that hold at any size
+    (ascending, non-overlapping, lengths within the dictionary's range)."""
+    import ctypes as C
+    import torch
+    from ahocorasick_b200 import _lib
+    c = W.config(cfg)
+    kws = c["keywords"]
+    extra = tuple(c["word_chars"]) if "word_chars" in c else ()
+    n = 300_000_000
+    hay = W.make_haystack_torch(c["spec"], n, device=torch.device("cuda", 0))
+    lib = _lib.lib()
+
+    def run(m):
+        tot = C.c_int64(0)
+        _lib.check(lib.acgpu_match_device(m.handle, hay.data_ptr(), n, 0, n, None, None, 0, C.byref(tot), None))
+        d_pos = torch.empty((tot.value, 2), dtype=torch.int32, device="cuda")
+        _lib.check(lib.acgpu_match_device(m.handle, hay.data_ptr(), n, 0, n, d_pos.data_ptr(), None, tot.value, C.byref(tot), None))
+        torch.cuda.synchronize()
+        return d_pos
+
+    fast = run(SETS[family](kws, c["cs"], *extra))
+    monkeypatch.setenv("ACGPU_FORCE_GEN1", "1")
+    slow = run(SETS[family](kws, c["cs"], *extra))
+    assert fast.shape == slow.shape and fast.shape[0] > 100_000
+    assert torch.equal(fast, slow)
+    start, end = fast[:, 0].long(), fast[:, 1].long()
+    assert bool((end > start).all()) and bool((end - start <= 12).all())
+    assert bool((start[1:] >= end[:-1]).all())          # ascending and non-overlapping
+    assert int(start[0]) >= 0 and int(end[-1]) <= n
