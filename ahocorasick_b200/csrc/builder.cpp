@@ -319,7 +319,8 @@ void build_ww(HostAutomaton &a, const std::vector<uint8_t> &wc, const std::vecto
         for (uint32_t cur = static_cast<uint32_t>(id); cur != 0; cur = node_parent[cur]) tmp.push_back(node_cls[cur]);
         std::reverse(tmp.begin(), tmp.end());
         WwHash h;
-        for (uint16_t c : tmp) h.add(c);
+        for (size_t i = 0; i < tmp.size(); i += 2)
+            h.add_pair(static_cast<uint32_t>(tmp[i]) | (i + 1 < tmp.size() ? static_cast<uint32_t>(tmp[i + 1]) << 16 : 0u));
         h.finish(static_cast<uint32_t>(tmp.size()));
         if (w.pool.size() + tmp.size() > 0xFFFFFFF0ull) return;
         const uint32_t off = static_cast<uint32_t>(w.pool.size());

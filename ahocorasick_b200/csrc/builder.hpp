@@ -108,13 +108,14 @@ struct WwTables {
     std::vector<uint16_t> pool;
 };
 
-// hash of a class string, shared by the builder and k_ww_scan (FNV-1a over the classes, murmur-style finish)
+// hash of a class string, shared by the builder and k_ww_scan: FNV-1a over PAIRS of classes (c[2i] | c[2i+1] << 16, a
+// lone last class with a zero upper half), murmur-style finish
 struct WwHash {
     uint32_t h1 = 0x811C9DC5u;
 #ifdef __CUDACC__
     __host__ __device__
 #endif
-    inline void add(uint32_t c) { h1 = (h1 ^ c) * 0x01000193u; }
+    inline void add_pair(uint32_t pair) { h1 = (h1 ^ pair) * 0x01000193u; }
 #ifdef __CUDACC__
     __host__ __device__
 #endif

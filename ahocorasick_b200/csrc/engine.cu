@@ -558,7 +558,7 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
         W.total_out = d_total;
         W.tile_counter = static_cast<unsigned int *>(ws);
         W.status = reinterpret_cast<unsigned long long *>(static_cast<char *>(ws) + 256);
-        const size_t smem = static_cast<size_t>(kWwTile + 16 * ((m->ww.max_len + 1 + 15) / 16)) * 2;
+        const size_t smem = static_cast<size_t>(kWwTile + 16 * ((m->ww.max_len + 1 + 15) / 16) + 2) * 2;  // + one word read ahead by the pair hash
         const int grid = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(m->sm_count) * 6));
         if (A.is_map)
             k_ww_scan<true><<<grid, kWwThreads, smem, st>>>(m->ww, W);

@@ -190,7 +190,19 @@ __global__ void __launch_bounds__(kWwThreads) k_ww_scan(const DevWw W, const WwA
             if (ok && L <= (uint32_t)W.max_len) {
                 const uint16_t *run = s_c + p;
                 WwHash h;
-                for (uint32_t i = 0; i < L; i++) h.add(run[i]);
+                {
+                    // two classes per step: aligned words of the class array, shifted into place when the word starts odd
+                    const uint32_t *cw = reinterpret_cast<const uint32_t *>(s_c) + (p >> 1);
+                    const uint32_t sh = (p & 1u) * 16u;
+                    uint32_t w0 = cw[0];
+                    for (uint32_t i = 0; i < L; i += 2) {
+                        const uint32_t w1 = cw[(i >> 1) + 1];
+                        uint32_t pair = __funnelshift_r(w0, w1, sh);
+                        if (i + 1 >= L) pair &= 0xFFFFu;  // a lone last class
+                        h.add_pair(pair);
+                        w0 = w1;
+                    }
+                }
                 h.finish(L);
                 uint32_t bk = __umulhi(h.spread(), W.n_buckets);
                 for (uint32_t tries = 0; tries < W.n_buckets && !hit_len; tries++) {
