@@ -1235,10 +1235,18 @@ int stream_reserve(StreamCtx *s, int which, int64_t chars) {
     return ACGPU_OK;
 }
 
-// append host chars to the active window through the pinned double buffer
+// append host chars to the active window: straight DMA when the caller's buffer is page-locked (a pinned direct buffer
+// on the Java side), else through the pinned double buffer
 int stream_append(StreamCtx *s, const uint16_t *chars, int64_t n) {
     int rc = stream_reserve(s, s->cur, s->len + n);
     if (rc != ACGPU_OK) return rc;
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, chars) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+        CU_TRY(cudaMemcpyAsync(s->d_win[s->cur] + s->len, chars, static_cast<size_t>(n) * 2, cudaMemcpyHostToDevice, s->st));
+        s->len += n;
+        return ACGPU_OK;
+    }
+    cudaGetLastError();  // unregistered host memory reports an error on some drivers
     int64_t done = 0;
     int k = 0;
     while (done < n) {
@@ -1303,16 +1311,20 @@ int stream_process(StreamCtx *s, bool final, acgpu_result *out) {
         cap = static_cast<int64_t>(total);
     }
     if (total > 0) {
-        int32_t *h_pos = static_cast<int32_t *>(malloc(static_cast<size_t>(total) * 8));
-        uint32_t *h_val = m->host.is_map ? static_cast<uint32_t *>(malloc(static_cast<size_t>(total) * 4)) : nullptr;
-        if (!h_pos || (m->host.is_map && !h_val)) {
-            free(h_pos);
-            free(h_val);
-            return fail(ACGPU_ENOMEM, "out of host memory for the match records");
+        // one page-locked block from the process-wide cache: positions, then values (acgpu_free_result hands it back)
+        PinnedBlock blk;
+        const size_t pos_bytes = align_up(static_cast<size_t>(total) * 8, 16);
+        if (!pin_take(pos_bytes + (m->host.is_map ? static_cast<size_t>(total) * 4 : 0), &blk))
+            return fail(ACGPU_ENOMEM, "out of pinned host memory for the match records");
+        int32_t *h_pos = static_cast<int32_t *>(blk.p);
+        uint32_t *h_val = m->host.is_map ? reinterpret_cast<uint32_t *>(static_cast<char *>(blk.p) + pos_bytes) : nullptr;
+        cudaError_t e = cudaMemcpyAsync(h_pos, d_pos, static_cast<size_t>(total) * 8, cudaMemcpyDeviceToHost, s->st);
+        if (e == cudaSuccess && h_val) e = cudaMemcpyAsync(h_val, d_val, static_cast<size_t>(total) * 4, cudaMemcpyDeviceToHost, s->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+        if (e != cudaSuccess) {
+            pin_release(blk.p);
+            return fail(ACGPU_ECUDA, std::string("stream download: ") + cudaGetErrorString(e));
         }
-        CU_TRY(cudaMemcpyAsync(h_pos, d_pos, static_cast<size_t>(total) * 8, cudaMemcpyDeviceToHost, s->st));
-        if (h_val) CU_TRY(cudaMemcpyAsync(h_val, d_val, static_cast<size_t>(total) * 4, cudaMemcpyDeviceToHost, s->st));
-        CU_TRY(cudaStreamSynchronize(s->st));
         out->n = static_cast<int64_t>(total);
         out->pos = h_pos;
         out->val = h_val;

@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--chars", type=int, default=1_000_000_000, help="UTF-16 chars per haystack")
     ap.add_argument("--keywords", type=int, default=1_000_000)
     ap.add_argument("--e2e-chars", type=int, default=250_000_000)
-    ap.add_argument("--cpu-sample-chars", type=int, default=2_000_000, help="chars per host thread per CPU pass")
+    ap.add_argument("--cpu-sample-chars", type=int, default=16_000_000, help="chars per host thread per CPU pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
