@@ -161,15 +161,17 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
         Pack8 P0{0u, 0u}, P1{0u, 0u}, P2{0u, 0u};
         if (kIsMap) {
             uint32_t c4[8];
-            const uint4 v = ldcs_v4_if(E.hay + p0, p0 >= 0 && p0 + 8 <= E.n);
-            classify8x4(A, E.hay, E.n, p0, v, s_cls4, c4);
+            const bool in0 = p0 >= 0 && p0 + 8 <= E.n;
+            const uint4 v = ldcs_v4_if(E.hay + p0, in0);
+            classify8x4(A, E.hay, E.n, p0, in0, v, s_cls4, c4);
             P0 = pack8(c4, sh);
             Pack8 h{0u, 0u};
             if (lane < 2) {
                 const int64_t q0 = E.origin + row * kMaskRow - 16 + (int64_t)lane * 8;
-                const uint4 hv = ldcs_v4_if(E.hay + q0, q0 >= 0 && q0 + 8 <= E.n);
+                const bool inq = q0 >= 0 && q0 + 8 <= E.n;
+                const uint4 hv = ldcs_v4_if(E.hay + q0, inq);
                 uint32_t h4[8];
-                classify8x4(A, E.hay, E.n, q0, hv, s_cls4, h4);
+                classify8x4(A, E.hay, E.n, q0, inq, hv, s_cls4, h4);
                 h = pack8(h4, sh);
             }
             Pack8 car0, car1;

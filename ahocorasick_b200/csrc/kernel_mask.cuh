@@ -27,6 +27,10 @@ constexpr int kMaskWarps = ACGPU_MASK_WARPS;
 #ifndef ACGPU_KID_TEX
 #define ACGPU_KID_TEX 1   // child masks are gathered through the texture pipe (the LSU data pipe is the kernel's bottleneck)
 #endif
+// bytes per queue entry: the 64-bit context and the position.  (Keeping the packed classes instead and shifting the
+// context together at probe time - 20-byte entries, 201 KB of shared memory - pushed the carve-out to 228 KB and the
+// kernel from 2.80 to 4.79 ms: the 28 KB of L1 left do not hold the gathers' working set.  Measured, session 5.)
+constexpr int kMaskQueueEntry = 12;
 constexpr int kMaskThreads = kMaskWarps * 32;
 constexpr int kMaskRow = 256;          // positions per warp row
 constexpr int kMaskChunkRows = 32;     // rows per ticket
@@ -70,7 +74,7 @@ struct EmitArgs {
 };
 
 __host__ __device__ constexpr size_t mask_smem_bytes(size_t n_row_words) {
-    return (64 + ((n_row_words + 3) & ~size_t(3))) * sizeof(uint32_t) + (size_t)kMaskWarps * kMaskQueue * 12;
+    return (64 + ((n_row_words + 3) & ~size_t(3))) * sizeof(uint32_t) + (size_t)kMaskWarps * kMaskQueue * kMaskQueueEntry;
 }
 
 __device__ __forceinline__ uint32_t rotr32(uint32_t x, uint32_t s) { return __funnelshift_r(x, x, s); }
@@ -81,12 +85,12 @@ __device__ __forceinline__ uint32_t ldg_u32_if(const void *p, bool on) {
     return x;
 }
 
-// scaled classes (class * 4) of the 8 chars at [p0, p0 + 8); v is the prefetched vector (valid when the 8 chars lie
-// inside [0, n)); positions outside [0, n) give class 0
+// scaled classes (class * 4) of the 8 chars at kernel positions [p0, p0 + 8); v is the prefetched vector, valid when
+// `inside` (the 8 chars lie inside [0, n)); positions outside [0, n) give class 0
 template <bool MIR = false>
-__device__ __forceinline__ void classify8x4(const DevAutomaton &A, const uint16_t *hay, int64_t n, int64_t p0, const uint4 v,
+__device__ __forceinline__ void classify8x4(const DevAutomaton &A, const uint16_t *hay, int64_t n, int64_t p0, bool inside, const uint4 v,
                                             const uint8_t *s_cls4, uint32_t (&c4)[8]) {
-    if (p0 >= 0 && p0 + 8 <= n) {
+    if (inside) {
         if (((v.x | v.y | v.z | v.w) & 0xFF00FF00u) == 0u) {
             c4[0] = s_cls4[v.x & 0xFFu]; c4[1] = s_cls4[v.x >> 16];
             c4[2] = s_cls4[v.y & 0xFFu]; c4[3] = s_cls4[v.y >> 16];
@@ -126,8 +130,9 @@ struct Pack8 {
 };
 __device__ __forceinline__ Pack8 pack8(const uint32_t (&c4)[8], uint32_t sh) {
     Pack8 p;
-    p.hi = (((c4[0] >> 2) * sh + (c4[1] >> 2)) * sh + (c4[2] >> 2)) * sh + (c4[3] >> 2);
-    p.lo = (((c4[4] >> 2) * sh + (c4[5] >> 2)) * sh + (c4[6] >> 2)) * sh + (c4[7] >> 2);
+    // every c4 is a multiple of 4, so the scaled sum is 4 x the packed classes
+    p.hi = (((c4[0] * sh + c4[1]) * sh + c4[2]) * sh + c4[3]) >> 2;
+    p.lo = (((c4[4] * sh + c4[5]) * sh + c4[6]) * sh + c4[7]) >> 2;
     return p;
 }
 __device__ __forceinline__ unsigned long long pack64(const Pack8 &p, int b) { return ((unsigned long long)p.hi << (4 * b)) | p.lo; }
@@ -166,7 +171,8 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = T.b;
     const uint32_t cm = (1u << b) - 1u, sh = 1u << b, C = (uint32_t)T.C;
-    unsigned char *s_q = reinterpret_cast<unsigned char *>(s_mem + 64 + ((T.n_row_words + 3u) & ~3u)) + (size_t)warp * kMaskQueue * 12;
+    // per-warp queue of contexts that continue past level K
+    unsigned char *s_q = reinterpret_cast<unsigned char *>(s_mem + 64 + ((T.n_row_words + 3u) & ~3u)) + (size_t)warp * kMaskQueue * kMaskQueueEntry;
     unsigned long long *s_qctx = reinterpret_cast<unsigned long long *>(s_q);
     uint32_t *s_qpos = reinterpret_cast<uint32_t *>(s_q + kMaskQueue * 8);
 
@@ -198,39 +204,56 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
             deep_resolve<K>(T.buckets, T.hash_seed, T.n_buckets, T.b, T.inv_b, s_qctx[first + lane], s_qpos[first + lane], A.max_len,
                             P.masks, P.row_count);
     };
-    auto fetch = [&](int64_t row, int64_t row_end) -> uint4 {
-        const int64_t p0 = P.origin + row * kMaskRow + (int64_t)lane * 8;
-        return load8<MIR>(P.hay, P.n, p0, row < row_end && p0 >= 0 && p0 + 8 <= P.n);
-    };
-
     while (true) {
         uint32_t chunk = 0;
         if (lane == 0) chunk = atomicAdd(P.ticket, 1u);
         chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
         const int64_t row0 = (int64_t)chunk * kMaskChunkRows;
         if (row0 >= P.n_rows) break;
-        const int64_t row_end = min(row0 + (int64_t)kMaskChunkRows, P.n_rows);
-        uint4 v = fetch(row0, row_end), vn = fetch(row0 + 1, row_end);
+        const int n_cr = (int)min((int64_t)kMaskChunkRows, P.n_rows - row0);  // rows of this chunk
+        // 64-bit position arithmetic once per chunk; rows use 32-bit offsets from here
+        const int64_t c_lo = P.origin + row0 * kMaskRow, c_hi = c_lo + (int64_t)n_cr * kMaskRow;
+        const bool chunk_in = c_lo - 16 >= 0 && c_hi <= P.n;                    // every load of the chunk is inside the haystack
+        const bool chunk_full = c_lo >= P.emit_from && c_hi <= P.emit_to;        // no row is cut by the emit range
+        const int64_t l_lo = c_lo + (int64_t)lane * 8;                           // the lane's first position in row 0 of the chunk
+        const uint16_t *lp = MIR ? P.hay + (P.n - 8 - l_lo) : P.hay + l_lo;
+        auto fetch = [&](int r) -> uint4 {
+            const bool live = r < n_cr;
+            if (chunk_in) {
+                const uint4 x = ldcs_v4_if(MIR ? lp - r * kMaskRow : lp + r * kMaskRow, live);
+                return MIR ? make_uint4(swap16(x.w), swap16(x.z), swap16(x.y), swap16(x.x)) : x;
+            }
+            const int64_t p0 = P.origin + (row0 + r) * kMaskRow + (int64_t)lane * 8;
+            return load8<MIR>(P.hay, P.n, p0, live && p0 >= 0 && p0 + 8 <= P.n);
+        };
+        uint4 v = fetch(0), vn = fetch(1);
         // left context of the chunk: lanes 0, 1 classify the 16 chars before it
         Pack8 car0, car1;  // the 8 classes ending 8 positions before the row / right before the row
         {
             Pack8 h{0u, 0u};
             if (lane < 2) {
-                const int64_t p0 = P.origin + row0 * kMaskRow - 16 + (int64_t)lane * 8;
-                const uint4 hv = load8<MIR>(P.hay, P.n, p0, p0 >= 0 && p0 + 8 <= P.n);
+                const int64_t p0 = c_lo - 16 + (int64_t)lane * 8;
+                const bool in = p0 >= 0 && p0 + 8 <= P.n;
+                const uint4 hv = load8<MIR>(P.hay, P.n, p0, in);
                 uint32_t h4[8];
-                classify8x4<MIR>(A, P.hay, P.n, p0, hv, s_cls4, h4);
+                classify8x4<MIR>(A, P.hay, P.n, p0, in, hv, s_cls4, h4);
                 h = pack8(h4, sh);
             }
             car0.hi = __shfl_sync(0xFFFFFFFFu, h.hi, 0); car0.lo = __shfl_sync(0xFFFFFFFFu, h.lo, 0);
             car1.hi = __shfl_sync(0xFFFFFFFFu, h.hi, 1); car1.lo = __shfl_sync(0xFFFFFFFFu, h.lo, 1);
         }
-        for (int64_t row = row0; row < row_end; ++row) {
-            const uint4 vnn = fetch(row + 2, row_end);
-            const int64_t r_lo = P.origin + row * kMaskRow;  // first position of the row
-            const int64_t p0 = r_lo + (int64_t)lane * 8;
+        // per-chunk bases of the outputs
+        uint4 *mp = reinterpret_cast<uint4 *>(P.masks) + (MIR ? (size_t)(P.n_rows - 1 - row0) * 32 + (31 - lane) : (size_t)row0 * 32 + lane);
+        const uint32_t q0 = (uint32_t)(row0 * kMaskRow) + lane * 8;
+        for (int r = 0; r < n_cr; ++r) {
+            const uint4 vnn = fetch(r + 2);
             uint32_t c4[8];
-            classify8x4<MIR>(A, P.hay, P.n, p0, v, s_cls4, c4);
+            if (chunk_in) {
+                classify8x4<MIR>(A, P.hay, P.n, 0, true, v, s_cls4, c4);
+            } else {
+                const int64_t p0 = P.origin + (row0 + r) * kMaskRow + (int64_t)lane * 8;
+                classify8x4<MIR>(A, P.hay, P.n, p0, p0 >= 0 && p0 + 8 <= P.n, v, s_cls4, c4);
+            }
             v = vn;
             vn = vnn;
             const Pack8 P0 = pack8(c4, sh);
@@ -241,10 +264,11 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
             if (lane == 1) P2 = car1;
             car0.hi = __shfl_sync(0xFFFFFFFFu, P0.hi, 30); car0.lo = __shfl_sync(0xFFFFFFFFu, P0.lo, 30);
             car1.hi = __shfl_sync(0xFFFFFFFFu, P0.hi, 31); car1.lo = __shfl_sync(0xFFFFFFFFu, P0.lo, 31);
-            // class i positions before this lane's first one (i = 1..8)
-            auto prev_class = [&](int i) -> uint32_t {
-                return i <= 4 ? (P1.lo >> (b * (i - 1))) & cm : (P1.hi >> (b * (i - 5))) & cm;
-            };
+            // pc[i] = class i positions before this lane's first one (i = 1..K)
+            uint32_t pc[K + 1];
+            pc[0] = 0;
+#pragma unroll
+            for (int i = 1; i <= K; i++) pc[i] = i <= 4 ? (P1.lo >> (b * (i - 1))) & cm : (P1.hi >> (b * (i - 5))) & cm;
 
             // ---- levels 1..K.  rs[k] = 4 * (mixed-radix number of the k classes before the current position)
             uint32_t rs[K + 1];
@@ -253,7 +277,7 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
                 uint32_t acc = 0;
 #pragma unroll
                 for (int k = 1; k < K; k++) {
-                    acc += prev_class(k) * (T.pow_c[k] * 4u);
+                    acc += pc[k] * (T.pow_c[k] * 4u);
                     rs[k] = acc;
                 }
             }
@@ -275,7 +299,7 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
                 // bit 31 of the second word: the K-1 classes that name this row are a keyword (it ends one position back)
                 if (LOW == 1 && j >= 1) m[j - 1] |= (wk.y >> (14 + K)) & (1u << (17 - K));
                 // class K positions back: the child the context needs (class 0 = "in no keyword" never has one)
-                const uint32_t ck = j >= K ? c4[j >= K ? j - K : 0] >> 2 : prev_class(K - j);
+                const uint32_t ck = j >= K ? c4[j >= K ? j - K : 0] >> 2 : pc[j >= K ? 0 : K - j];
                 const bool kids = ((wk.y >> cj) & 1u) && ck != 0u;
                 const uint32_t rk = rs[K - 1] * C + c4[j];  // byte offset of the level-K entry's child mask
 #pragma unroll
@@ -294,7 +318,8 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
             }
             // ---- positions outside [emit_from, emit_to) report nothing (edge rows only)
             uint32_t vm = 0xFFu;
-            if (r_lo < P.emit_from || r_lo + kMaskRow > P.emit_to) {
+            if (!chunk_full) {
+                const int64_t p0 = P.origin + (row0 + r) * kMaskRow + (int64_t)lane * 8;
                 const int64_t lo_j = P.emit_from - p0, hi_j = P.emit_to - p0;
                 const uint32_t a = lo_j <= 0 ? 0xFFu : (lo_j >= 8 ? 0u : (0xFFu << (int)lo_j) & 0xFFu);
                 const uint32_t z = hi_j >= 8 ? 0xFFu : (hi_j <= 0 ? 0u : (0xFFu >> (8 - (int)hi_j)));
@@ -306,20 +331,20 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
             uint32_t pm = 0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const uint32_t ck = j >= K ? c4[j >= K ? j - K : 0] >> 2 : prev_class(K - j);
+                const uint32_t ck = j >= K ? c4[j >= K ? j - K : 0] >> 2 : pc[j >= K ? 0 : K - j];
                 pm |= ((ki[j] >> ck) & 1u) << j;
             }
             pm &= vm;
+            const unsigned long long own8 = pack64(P0, b), prev16 = (pack64(P2, b) << (8 * b)) | pack64(P1, b);
             // ---- store the shallow masks and the row count; deep hits are OR-ed in later by this same warp
             const uint4 mw = make_uint4(m[0] | m[1] << 16, m[2] | m[3] << 16, m[4] | m[5] << 16, m[6] | m[7] << 16);
             if (MIR)  // masks are stored in haystack order: the array is the kernel's, reversed
-                *reinterpret_cast<uint4 *>(P.masks + ((size_t)(P.n_rows - 1 - row) * 32 + (31 - lane)) * 4) =
-                    make_uint4(swap16(mw.w), swap16(mw.z), swap16(mw.y), swap16(mw.x));
+                *(mp - r * 32) = make_uint4(swap16(mw.w), swap16(mw.z), swap16(mw.y), swap16(mw.x));
             else
-                *reinterpret_cast<uint4 *>(P.masks + ((size_t)row * 32 + lane) * 4) = mw;
+                *(mp + r * 32) = mw;
             const uint32_t cnt = __popc(mw.x) + __popc(mw.y) + __popc(mw.z) + __popc(mw.w);
             const uint32_t row_total = __reduce_add_sync(0xFFFFFFFFu, cnt);
-            if (lane == 0) P.row_count[MIR ? P.n_rows - 1 - row : row] = row_total;
+            if (lane == 0) P.row_count[MIR ? P.n_rows - 1 - (row0 + r) : row0 + r] = row_total;
             __syncwarp();
             // ---- queue the continuing contexts; probe whenever 32 are waiting
             while (true) {
@@ -330,8 +355,8 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
                     const int j = __ffs(pm) - 1;
                     pm &= pm - 1u;
                     const uint32_t slot = q_cnt + __popc(bal & lt_mask);
-                    s_qctx[slot] = context_of(P0, P1, P2, j, b);
-                    const uint32_t qp = (uint32_t)(row * kMaskRow) + lane * 8 + j;
+                    s_qctx[slot] = (prev16 << (b * (j + 1))) | (own8 >> (b * (7 - j)));
+                    const uint32_t qp = q0 + (uint32_t)(r * kMaskRow) + j;
                     s_qpos[slot] = MIR ? (uint32_t)(P.n_rows * kMaskRow) - 1u - qp : qp;
                 }
                 q_cnt += __popc(bal);
