@@ -577,3 +577,49 @@ def test_large_haystack_two_generations_agree(cfg, family, monkeypatch):
     assert bool((end > start).all()) and bool((end - start <= 12).all())
     assert bool((start[1:] >= end[:-1]).all())          # ascending and non-overlapping
     assert int(start[0]) >= 0 and int(end[-1]) <= n
+
+
+# ---------------------------------------------------------------- randomised medium-size stress over every family
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_dictionaries_medium_haystacks(seed):
+    """Random alphabets (2..30 symbols, sometimes beyond ASCII), keyword lengths up to 16, separator densities from none to
+    one in three, case folding on and off, 40 000..120 000 chars: all five families, Set and Map, against the oracle."""
+    rng = random.Random(1000 + seed)
+    pool = "abcdefghijklmnopqrstuvwxyzABCD0123456789" + "βγδжзиé"
+    alphabet = "".join(rng.sample(pool, rng.randint(2, 30)))
+    max_kw = rng.choice([3, 6, 12, 16])
+    nk = rng.choice([5, 40, 400, 3000])
+    kws = sorted({_rand_word(rng, alphabet, 1, max_kw) for _ in range(nk)})
+    if rng.random() < 0.5:  # phrases for WholeWordLongest (the other families treat the space as a keyword char)
+        kws += [rng.choice(kws) + " " + rng.choice(kws) for _ in range(max(1, nk // 10))]
+        kws = [k for k in kws if len(k) <= 16]
+    sep_rate = rng.choice([0.0, 0.05, 0.15, 0.33])
+    n = rng.randint(40_000, 120_000)
+    seps = " ,.-"
+    hay = "".join(rng.choice(seps) if rng.random() < sep_rate else rng.choice(alphabet) for _ in range(n))
+    # plant keywords so that long ones occur too
+    hay_l = list(hay)
+    for _ in range(n // 50):
+        k = rng.choice(kws)
+        at = rng.randrange(0, n - len(k))
+        hay_l[at:at + len(k)] = k
+    hay = "".join(hay_l)
+    cs = rng.random() < 0.5
+    if not cs:
+        hay = "".join(c.upper() if rng.random() < 0.3 else c for c in hay)
+    values = list(range(len(kws)))
+    for family in FAMILIES:
+        try:
+            om = ora.Matcher(family, kws, n_values=len(kws), case_sensitive=cs)
+        except ora.OracleError:
+            with pytest.raises(ac.IllegalArgumentException):
+                MAPS[family](kws, values, cs)
+            continue
+        want = om.match(hay)
+        rec = MAPS[family](kws, values, cs).match_records(hay)
+        assert len(rec) == len(want), (seed, family, len(rec), len(want))
+        assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"]), (seed, family)
+        assert np.array_equal(rec.value.astype(np.int64), want["value"].astype(np.int64)), (seed, family)
+        rec = SETS[family](kws, cs).match_records(hay)
+        assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"]), (seed, family, "set")
