@@ -2,6 +2,9 @@
 #include "builder.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -55,6 +58,18 @@ struct EdgeMap {
         ++count;
         created = true;
         return next_node++;
+    }
+};
+
+// ACGPU_BUILD_TIMING=1: phase times of build_automaton on stderr (dictionary-construction throughput)
+struct PhaseTimer {
+    const bool on = std::getenv("ACGPU_BUILD_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[acgpu build] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
     }
 };
 
@@ -352,6 +367,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
     const bool word_family = family == 3 || family == 4;  // WholeWord, WholeWordLongest
     const uint16_t *lower = java_lower_table();
     HostAutomaton a;
+    PhaseTimer timer;
     a.family = family;
     a.is_map = n_values >= 0;
     a.case_sensitive = case_sensitive;
@@ -439,6 +455,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
     a.char_buffer_size = longest > 2048 ? longest * 2 : 4096;
     a.n_keywords_effective = static_cast<int64_t>(kws.size());
 
+    timer.lap("keywords: trim, validate");
     // ---- character classes
     uint32_t distinct = 0;
     for (uint32_t c = 0; c < 65536; c++) distinct += used[c];
@@ -488,6 +505,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
         }
         info[node] |= kInfoTerminal;
     }
+    timer.lap("trie insert");
     a.n_nodes = next_node;
     a.node_info.swap(info);
     a.node_value.swap(value);
@@ -515,11 +533,14 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
         while (a.edges[i].parent != kNone) i = (i + 1) & a.edge_mask;
         a.edges[i] = Edge{e.parent, e.cls, e.child, a.node_info[e.child]};
     }
+    timer.lap("edge table");
     if (family != 4) build_tiers(a, node_parent, node_cls);
+    timer.lap("tier tables");
     // WholeWordLongest with a dictionary whose (trimmed) keywords hold no non-word char: a walk can never leave its word
     // (there is no transition on a non-word char) and a keyword followed by a non-word char is the whole word, so the
     // family coincides with WholeWord and takes its hash path.
     if (family == 3 || (family == 4 && a.ww_plain)) build_ww(a, wc, node_parent, node_cls);
+    timer.lap("whole-word hash");
     return a;
 }
 

@@ -75,3 +75,22 @@ def test_no_device_fails_loudly():
         with pytest.raises(ac.AcgpuError) as e:
             cls(*args)
         assert e.value.code == _lib.ENODEVICE
+
+
+def test_keyword_packing_fast_path_equals_per_keyword_path():
+    """_pack_keywords joins all-str dictionaries and encodes once; the layout must equal the per-keyword path (which a
+    None keyword forces), including empty keywords, non-BMP characters (UTF-16 length != len(str)) and lone surrogates."""
+    from ahocorasick_b200.matchers import _pack_keywords
+    rng = np.random.default_rng(7)
+    cases = [["he", "she", "hers"], ["", "", ""], ["a\U0001F600b", "", "xy"], ["é", "日本語", "\ud800x"], [],
+             ["".join(chr(int(c)) for c in rng.integers(1, 0xD7FF, size=int(rng.integers(0, 9)))) for _ in range(500)]]
+    for kws in cases:
+        chars, offsets, is_null, n = _pack_keywords(kws)
+        chars2, offsets2, is_null2, n2 = _pack_keywords(list(kws) + [None])
+        assert n == len(kws) and n2 == n + 1 and is_null2[-1] == 1 and not is_null[:n].any()
+        assert np.array_equal(offsets, offsets2[:-1])
+        assert np.array_equal(chars[:offsets[-1]], chars2[:offsets[-1]])
+        for i, k in enumerate(kws):
+            assert chars[offsets[i]:offsets[i + 1]].tobytes() == k.encode("utf-16-le", "surrogatepass")
+    it = _pack_keywords(k for k in ["ab", "c"])  # any Iterable, like the Java constructors
+    assert it[3] == 2 and it[1].tolist() == [0, 2, 3]
