@@ -21,6 +21,16 @@ def exe():
     return build_cpp_tests.build()
 
 
+@pytest.fixture(scope="module")
+def mock_exe():
+    """The same program linked against libacgpu_mock_oracle.so (tests/cpp/mock_acgpu_oracle.cpp: the C ABI answered by
+    the oracle) - exercises the C++ host logic and the test expectations without a GPU.  Test infrastructure only."""
+    from oracle import oracle as ora
+    from ahocorasick_b200 import build_cpp_tests
+    ora.build()
+    return build_cpp_tests.build_mock()
+
+
 def _run(cmd, timeout=600):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
     assert r.returncode == 0, "exit %d\n%s\n%s" % (r.returncode, r.stdout[-2000:], r.stderr[-4000:])
@@ -46,6 +56,13 @@ def test_cpp_mirror_declares_every_reference_class():
     assert "oracle" not in text.lower()
 
 
+def test_cpp_host_logic_against_mocked_abi(mock_exe):
+    """Every reference-style C++ test with the C ABI mocked by the oracle: checks include/acgpu.hpp's packing, zipping,
+    replay and quirk logic and the expectations of the test program itself; the GPU run below checks the kernels."""
+    out = _run([mock_exe], timeout=600)
+    assert " 0 failures" in out, out
+
+
 @pytest.mark.gpu
 def test_cpp_reference_style_suite(exe):
     out = _run([exe], timeout=1200)
@@ -68,12 +85,21 @@ def _random_case(seed, fam):
     return list(kws), hay
 
 
+def test_cpp_dump_plumbing_against_mocked_abi(mock_exe, tmp_path):
+    for fam in range(5):
+        _check_streams(mock_exe, tmp_path, fam, fam % 2, seeds=(0,))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("fam", range(5), ids=FAMILIES)
 @pytest.mark.parametrize("cs", [1, 0], ids=["cs", "ci"])
 def test_cpp_streams_equal_oracle(exe, tmp_path, fam, cs):
+    _check_streams(exe, tmp_path, fam, cs, seeds=range(3))
+
+
+def _check_streams(exe, tmp_path, fam, cs, seeds):
     from oracle import oracle as ora
-    for seed in range(3):
+    for seed in seeds:
         kws, hay = _random_case(1000 * fam + 10 * seed + cs, fam)
         kp, hp = str(tmp_path / "kw.u16"), str(tmp_path / "hay.u16")
         open(kp, "wb").write("\n".join(kws).encode("utf-16-le"))
