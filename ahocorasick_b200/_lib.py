@@ -17,7 +17,7 @@ AHOCORASICK, LONGEST, SHORTEST, WHOLEWORD, WHOLEWORDLONGEST = 0, 1, 2, 3, 4
 
 # every symbol include/acgpu.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "acgpu_create_from_keywords", "acgpu_destroy", "acgpu_word_chars", "acgpu_info",
+    "acgpu_create_from_keywords", "acgpu_build_fingerprint", "acgpu_destroy", "acgpu_word_chars", "acgpu_info",
     "acgpu_match_utf16", "acgpu_free_result", "acgpu_match_device", "acgpu_match_device_async",
     "acgpu_launches_per_match", "acgpu_stream_begin", "acgpu_stream_feed", "acgpu_stream_end",
     "acgpu_last_error", "acgpu_version",
@@ -51,6 +51,8 @@ def lib():
     vp, i64, i32, u64 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64
     L.acgpu_create_from_keywords.restype = C.c_int
     L.acgpu_create_from_keywords.argtypes = [C.c_int, vp, vp, vp, i64, i64, C.c_int, vp, C.c_int, C.POINTER(u64)]
+    L.acgpu_build_fingerprint.restype = C.c_int
+    L.acgpu_build_fingerprint.argtypes = [C.c_int, vp, vp, vp, i64, i64, C.c_int, vp, C.POINTER(u64)]
     L.acgpu_destroy.restype = C.c_int
     L.acgpu_destroy.argtypes = [u64]
     L.acgpu_word_chars.restype = C.c_int

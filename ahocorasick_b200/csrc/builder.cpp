@@ -9,6 +9,7 @@
 #include <mutex>
 
 #include "java_char_tables.h"
+#include "trie_insert.hpp"
 
 namespace acgpu {
 
@@ -16,50 +17,6 @@ namespace {
 
 uint16_t g_lower[65536];
 std::once_flag g_lower_once;
-
-// Growable (parent, class) -> child map used only while inserting keywords.
-struct EdgeMap {
-    std::vector<Edge> slots;
-    uint32_t mask = 0;
-    uint64_t count = 0;
-
-    EdgeMap() { resize(1u << 12); }
-
-    void resize(uint32_t n) {
-        std::vector<Edge> old;
-        old.swap(slots);
-        slots.assign(n, Edge{kNone, 0, 0, 0});
-        mask = n - 1;
-        for (const Edge &e : old) {
-            if (e.parent != kNone) put(e);
-        }
-    }
-    void put(const Edge &e) {
-        uint32_t i = edge_hash(e.parent, e.cls) & mask;
-        while (slots[i].parent != kNone) i = (i + 1) & mask;
-        slots[i] = e;
-    }
-    // returns child id, creating it (id = next_node++) when absent
-    uint32_t get_or_add(uint32_t parent, uint32_t c, uint32_t &next_node, bool &created) {
-        uint32_t i = edge_hash(parent, c) & mask;
-        while (slots[i].parent != kNone) {
-            if (slots[i].parent == parent && slots[i].cls == c) {
-                created = false;
-                return slots[i].child;
-            }
-            i = (i + 1) & mask;
-        }
-        if ((count + 1) * 2 > slots.size()) {
-            resize(static_cast<uint32_t>(slots.size() * 2));
-            i = edge_hash(parent, c) & mask;
-            while (slots[i].parent != kNone) i = (i + 1) & mask;
-        }
-        slots[i] = Edge{parent, c, next_node, 0};
-        ++count;
-        created = true;
-        return next_node++;
-    }
-};
 
 // ACGPU_BUILD_TIMING=1: phase times of build_automaton on stderr (dictionary-construction throughput)
 struct PhaseTimer {
@@ -405,12 +362,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
     }
 
     // ---- effective keywords: (begin, len, entry index) into `chars`, after trim / skip rules
-    struct Kw {
-        int64_t begin;
-        int32_t len;
-        int64_t entry;
-    };
-    std::vector<Kw> kws;
+    std::vector<KwRef> kws;
     kws.reserve(static_cast<size_t>(n));
     int32_t longest = 0;
     std::vector<uint8_t> used(65536, 0);
@@ -445,7 +397,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
         }
         if (len > longest) longest = len;
         if (len <= 0) continue;
-        kws.push_back(Kw{b, len, k});
+        kws.push_back(KwRef{b, len, k});
         for (int32_t i = 0; i < len; i++) {
             uint16_t c = chars[b + i];
             used[case_sensitive ? c : lower[c]] = 1;
@@ -472,52 +424,28 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
         a.cls[c] = class_of[f];  // 0 ("other") when f is in no keyword and has_other
     }
 
-    // ---- trie over class strings
-    EdgeMap map;
-    uint32_t next_node = 1;  // node 0 = root
-    std::vector<uint8_t> info(1, 0);
-    std::vector<uint32_t> value(1, kNone);
-    std::vector<uint32_t> node_parent(1, 0);
-    std::vector<uint16_t> node_cls(1, 0);
-    std::vector<uint32_t> depth_count(static_cast<size_t>(longest) + 1, 0);
-    depth_count[0] = 1;
+    // ---- trie over class strings (trie_insert.hpp).  Dictionaries of 50 000+ keywords are inserted concurrently, one
+    // shard per first class; both ways give the same arrays.  ACGPU_BUILDER=serial|sharded forces one (tests).
     const bool first_wins = (family == 2);  // ShortestMatchMap.java:44-54
-    for (const Kw &kw : kws) {
-        uint32_t node = 0;
-        for (int32_t i = 0; i < kw.len; i++) {
-            uint16_t raw = chars[kw.begin + (a.reversed ? (kw.len - 1 - i) : i)];
-            uint32_t c = a.cls[raw];
-            bool created = false;
-            uint32_t child = map.get_or_add(node, c, next_node, created);
-            if (created) {
-                info.push_back(0);
-                value.push_back(kNone);
-                node_parent.push_back(node);
-                node_cls.push_back(static_cast<uint16_t>(c));
-                info[node] |= kInfoHasChildren;
-                depth_count[static_cast<size_t>(i) + 1]++;
-                if (next_node == kNone) throw std::length_error("dictionary too large (node ids exceed 32 bits)");
-            }
-            node = child;
-        }
-        if (!(first_wins && (info[node] & kInfoTerminal))) {
-            value[node] = a.is_map ? static_cast<uint32_t>(kw.entry) : kNone;
-        }
-        info[node] |= kInfoTerminal;
-    }
-    timer.lap("trie insert");
-    a.n_nodes = next_node;
-    a.node_info.swap(info);
-    a.node_value.swap(value);
-    a.depth_count.swap(depth_count);
+    const TrieInsertParams tp{chars, a.cls.data(), a.reversed, a.is_map, first_wins, longest};
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const char *mode = std::getenv("ACGPU_BUILDER");
+    const bool sharded = mode ? std::strcmp(mode, "sharded") == 0 : (kws.size() >= 50000 && hw > 1);
+    TrieArrays trie = sharded ? insert_sharded(kws, tp, a.n_classes, mode ? std::max(hw, 4u) : hw) : insert_serial(kws, tp);
+    timer.lap(sharded ? "trie insert (sharded)" : "trie insert (serial)");
+    a.n_nodes = static_cast<int64_t>(trie.info.size());
+    a.node_info.swap(trie.info);
+    a.node_value.swap(trie.value);
+    a.depth_count.swap(trie.depth_count);
+    const std::vector<uint32_t> &node_parent = trie.parent;
+    const std::vector<uint16_t> &node_cls = trie.cls;
 
-    // ---- device tables: direct root table + hashed deeper edges
+    // ---- device tables: direct root table + hashed deeper edges, inserted in child-id order (canonical layout)
     a.root.assign(static_cast<size_t>(a.n_classes), RootEdge{kNone, 0});
     uint64_t deep_edges = 0;
-    for (const Edge &e : map.slots) {
-        if (e.parent == kNone) continue;
-        if (e.parent == 0) {
-            a.root[e.cls] = RootEdge{e.child, a.node_info[e.child]};
+    for (int64_t id = 1; id < a.n_nodes; id++) {
+        if (node_parent[id] == 0) {
+            a.root[node_cls[id]] = RootEdge{static_cast<uint32_t>(id), a.node_info[id]};
         } else {
             ++deep_edges;
         }
@@ -527,11 +455,12 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
     if (cap > (1ull << 31)) throw std::length_error("dictionary too large for the edge table");
     a.edges.assign(static_cast<size_t>(cap), Edge{kNone, 0, 0, 0});
     a.edge_mask = static_cast<uint32_t>(cap - 1);
-    for (const Edge &e : map.slots) {
-        if (e.parent == kNone || e.parent == 0) continue;
-        uint32_t i = edge_hash(e.parent, e.cls) & a.edge_mask;
+    for (int64_t id = 1; id < a.n_nodes; id++) {
+        const uint32_t parent = node_parent[id];
+        if (parent == 0) continue;
+        uint32_t i = edge_hash(parent, node_cls[id]) & a.edge_mask;
         while (a.edges[i].parent != kNone) i = (i + 1) & a.edge_mask;
-        a.edges[i] = Edge{e.parent, e.cls, e.child, a.node_info[e.child]};
+        a.edges[i] = Edge{parent, node_cls[id], static_cast<uint32_t>(id), a.node_info[id]};
     }
     timer.lap("edge table");
     if (family != 4) build_tiers(a, node_parent, node_cls);
@@ -542,6 +471,34 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
     if (family == 3 || (family == 4 && a.ww_plain)) build_ww(a, wc, node_parent, node_cls);
     timer.lap("whole-word hash");
     return a;
+}
+
+uint64_t automaton_fingerprint(const HostAutomaton &a) {
+    uint64_t h = 0xCBF29CE484222325ull;
+    auto bytes = [&](const void *p, size_t n) {
+        const unsigned char *b = static_cast<const unsigned char *>(p);
+        for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 0x100000001B3ull;
+    };
+    auto num = [&](uint64_t v) { bytes(&v, sizeof v); };
+    auto vec = [&](const auto &v) {
+        num(v.size());
+        if (!v.empty()) bytes(v.data(), v.size() * sizeof(v[0]));
+    };
+    num((uint64_t)a.family); num(a.is_map); num(a.case_sensitive); num(a.reversed); num(a.has_other);
+    num((uint64_t)a.max_len); num((uint64_t)a.n_classes); num((uint64_t)a.char_buffer_size); num((uint64_t)a.n_nodes);
+    num((uint64_t)a.n_keywords_effective); num(a.edge_mask); num(a.ww_plain);
+    vec(a.cls); vec(a.wordbits); vec(a.node_value); vec(a.node_info); vec(a.depth_count);
+    num(a.root.size());
+    for (const RootEdge &e : a.root) { num(e.child); num(e.info); }
+    num(a.edges.size());
+    for (const Edge &e : a.edges) { num(e.parent); num(e.cls); num(e.child); num(e.info); }
+    const TierTables &t = a.tier;
+    num(t.ok); num((uint64_t)t.C); num((uint64_t)t.b); num((uint64_t)t.K); num(t.term_levels);
+    bytes(t.pow_c, sizeof t.pow_c); bytes(t.row_off, sizeof t.row_off);
+    vec(t.row_words); vec(t.kidmask); vec(t.buckets); num(t.n_buckets); num(t.hash_seed); num(t.n_deep); num(t.n_heads);
+    vec(t.vbuckets); num(t.n_vbuckets); num(t.vseed);
+    num(a.ww.ok); vec(a.ww.wcls); vec(a.ww.buckets); num(a.ww.n_buckets); vec(a.ww.pool);
+    return h;
 }
 
 }  // namespace acgpu

@@ -185,6 +185,10 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
                               int64_t n_keywords, int64_t n_values, bool case_sensitive,
                               const uint8_t *word_chars);
 
+// 64-bit FNV-1a over every table of the flattened automaton (tests: the serial and the sharded builder must agree, and
+// a build must be deterministic)
+uint64_t automaton_fingerprint(const HostAutomaton &a);
+
 // WordCharacters.generateWordCharsFlags (WordCharacters.java:6-39)
 void make_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, int32_t n, uint8_t *out65536);
 

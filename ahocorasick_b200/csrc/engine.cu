@@ -1071,6 +1071,25 @@ int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t 
     return ACGPU_OK;
 }
 
+int acgpu_build_fingerprint(int family, const uint16_t *chars, const int64_t *offsets, const uint8_t *is_null,
+                            int64_t n_keywords, int64_t n_values, int case_sensitive, const uint8_t *word_chars,
+                            uint64_t *fingerprint) {
+    if (!fingerprint || n_keywords < 0 || (n_keywords > 0 && (!chars || !offsets))) return fail(ACGPU_EINVAL, "bad arguments");
+    try {
+        *fingerprint = automaton_fingerprint(
+            build_automaton(family, chars, offsets, is_null, n_keywords, n_values, case_sensitive != 0, word_chars));
+    } catch (const IllegalArgument &e) {
+        return fail(ACGPU_EILLEGALARG, e.what());
+    } catch (const std::domain_error &e) {
+        return fail(ACGPU_EUNSUPPORTED, e.what());
+    } catch (const std::bad_alloc &) {
+        return fail(ACGPU_ENOMEM, "out of memory while flattening the dictionary");
+    } catch (const std::exception &e) {
+        return fail(ACGPU_EINVAL, e.what());
+    }
+    return ACGPU_OK;
+}
+
 int acgpu_destroy(uint64_t handle) {
     Matcher *m = as_matcher(handle);
     if (!m) return fail(ACGPU_EINVAL, "bad handle");

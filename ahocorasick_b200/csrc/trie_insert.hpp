@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdint>
+#include <exception>
+#include <mutex>
 #include <numeric>
 #include <thread>
 #include <vector>
@@ -54,11 +56,23 @@ struct FixedEdgeMap {
     };
     std::vector<Slot> slots;
     uint32_t mask = 0;
-    explicit FixedEdgeMap(uint64_t max_edges) {
+    static uint64_t capacity_for(uint64_t max_edges) {
         uint64_t cap = 4;
         while (cap < max_edges * 2) cap <<= 1;
         if (cap > (1ull << 31)) throw std::length_error("dictionary too large for the edge table");
-        slots.assign((size_t)cap, Slot{kNone, 0, 0});
+        return cap;
+    }
+    FixedEdgeMap() = default;
+    explicit FixedEdgeMap(uint64_t max_edges) { reset(max_edges); }
+    // empty table for up to max_edges edges; keeps (and re-uses) the memory of earlier, larger tables - first-touch page
+    // faults, not hashing, dominate a cold build
+    void reset(uint64_t max_edges) {
+        const uint64_t cap = capacity_for(max_edges);
+        if (slots.size() < cap) {
+            slots.assign((size_t)cap, Slot{kNone, 0, 0});
+        } else {
+            std::fill(slots.begin(), slots.begin() + (size_t)cap, Slot{kNone, 0, 0});
+        }
         mask = (uint32_t)(cap - 1);
     }
     uint32_t get_or_add(uint32_t parent, uint32_t c, uint32_t next, bool &created) {
@@ -120,11 +134,11 @@ inline TrieArrays insert_sharded(const std::vector<KwRef> &kws, const TrieInsert
 
     // ---- deal keywords into shards (counting sort by first class keeps the caller's order inside a shard)
     std::vector<uint64_t> shard_begin((size_t)n_classes + 1, 0);
-    std::vector<uint64_t> shard_chars((size_t)n_classes, 0);
+    std::vector<uint64_t> shard_chars((size_t)n_classes, 0);  // upper bound of the shard's edges below its depth-1 node
     for (const KwRef &k : kws) {
         const uint32_t c = first_class(k);
         shard_begin[c + 1]++;
-        shard_chars[c] += (uint64_t)k.len;
+        shard_chars[c] += (uint64_t)k.len - 1;
     }
     for (int c = 0; c < n_classes; c++) shard_begin[c + 1] += shard_begin[c];
     std::vector<uint32_t> order(n);  // indices into kws, grouped by shard
@@ -150,11 +164,15 @@ inline TrieArrays insert_sharded(const std::vector<KwRef> &kws, const TrieInsert
     std::vector<Shard> shards(work.size());
     std::vector<uint32_t> created_by(n, 0);  // nodes created per keyword (each keyword belongs to one shard)
     std::atomic<size_t> next_work{0};
-    std::atomic<bool> failed{false};
-    auto build_shard = [&](size_t w) {
+    std::exception_ptr error;  // first exception of any worker, rethrown on the calling thread
+    std::mutex error_mutex;
+    auto build_shard = [&](size_t w, trie_detail::FixedEdgeMap &map) {
         const uint32_t c0 = work[w];
         Shard &S = shards[w];
-        trie_detail::FixedEdgeMap map(shard_chars[c0]);
+        map.reset(shard_chars[c0]);
+        const size_t guess = (size_t)(shard_chars[c0] / 2 + 16);  // nodes: usually about half the shard's chars
+        S.parent.reserve(guess); S.cls.reserve(guess); S.info.reserve(guess);
+        S.value.reserve(guess); S.creator.reserve(guess); S.rank.reserve(guess);
         S.depth_count.assign((size_t)P.longest + 1, 0);
         S.parent.push_back(kNone);
         S.cls.push_back((uint16_t)c0);
@@ -192,9 +210,12 @@ inline TrieArrays insert_sharded(const std::vector<KwRef> &kws, const TrieInsert
     };
     auto worker = [&](auto &&job) {
         try {
-            for (size_t w; (w = next_work.fetch_add(1)) < work.size();) job(w);
+            trie_detail::FixedEdgeMap map;  // one per thread, re-used from shard to shard (largest shard first)
+            for (size_t w; (w = next_work.fetch_add(1)) < work.size();) job(w, map);
         } catch (...) {
-            failed = true;
+            std::lock_guard<std::mutex> lock(error_mutex);
+            if (!error) error = std::current_exception();
+            next_work = work.size();
         }
     };
     auto run_parallel = [&](auto &&job) {
@@ -204,7 +225,7 @@ inline TrieArrays insert_sharded(const std::vector<KwRef> &kws, const TrieInsert
         for (unsigned t = 1; t < nt; t++) pool.emplace_back([&] { worker(job); });
         worker(job);
         for (std::thread &th : pool) th.join();
-        if (failed) throw std::bad_alloc();
+        if (error) std::rethrow_exception(error);
     };
     run_parallel(build_shard);
 
@@ -222,7 +243,7 @@ inline TrieArrays insert_sharded(const std::vector<KwRef> &kws, const TrieInsert
     t.depth_count.assign((size_t)P.longest + 1, 0);
     t.depth_count[0] = 1;
     if (n) t.info[0] = kInfoHasChildren;
-    auto scatter = [&](size_t w) {
+    auto scatter = [&](size_t w, trie_detail::FixedEdgeMap &) {
         const Shard &S = shards[w];
         const size_t m = S.parent.size();
         std::vector<uint32_t> gid(m);

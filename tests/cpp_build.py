@@ -1,12 +1,13 @@
-"""Build tests/cpp/reference_style_test (g++, C++17) against include/acgpu.hpp and the in-tree libacgpu.so."""
+"""Test infrastructure: build tests/cpp/reference_style_test (g++, C++17) against include/acgpu.hpp and the in-tree
+libacgpu.so, and its oracle-mocked twin for CPU-only runs."""
 from __future__ import annotations
 
 import os
 import subprocess
 import sys
 
-HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.join(ROOT, "ahocorasick_b200")  # where libacgpu.so is built
 SRC = os.path.join(ROOT, "tests", "cpp", "reference_style_test.cpp")
 OUT_DIR = os.path.join(ROOT, "tests", "cpp", "build")
 EXE = os.path.join(OUT_DIR, "reference_style_test")

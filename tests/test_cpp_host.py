@@ -16,9 +16,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def exe():
-    from ahocorasick_b200 import build as acbuild, build_cpp_tests
+    from ahocorasick_b200 import build as acbuild
+    import cpp_build
     acbuild.build()
-    return build_cpp_tests.build()
+    return cpp_build.build()
 
 
 @pytest.fixture(scope="module")
@@ -26,9 +27,9 @@ def mock_exe():
     """The same program linked against libacgpu_mock_oracle.so (tests/cpp/mock_acgpu_oracle.cpp: the C ABI answered by
     the oracle) - exercises the C++ host logic and the test expectations without a GPU.  Test infrastructure only."""
     from oracle import oracle as ora
-    from ahocorasick_b200 import build_cpp_tests
+    import cpp_build
     ora.build()
-    return build_cpp_tests.build_mock()
+    return cpp_build.build_mock()
 
 
 def _run(cmd, timeout=600):

@@ -94,3 +94,73 @@ def test_keyword_packing_fast_path_equals_per_keyword_path():
             assert chars[offsets[i]:offsets[i + 1]].tobytes() == k.encode("utf-16-le", "surrogatepass")
     it = _pack_keywords(k for k in ["ab", "c"])  # any Iterable, like the Java constructors
     assert it[3] == 2 and it[1].tolist() == [0, 2, 3]
+
+
+def _fingerprint(family, kws, n_values=-1, cs=True, wc=None):
+    from ahocorasick_b200 import _lib
+    from ahocorasick_b200.matchers import _pack_keywords
+    chars, offsets, is_null, n = _pack_keywords(kws)
+    fp = C.c_uint64(0)
+    _lib.check(_lib.lib().acgpu_build_fingerprint(family, chars.ctypes.data, offsets.ctypes.data, is_null.ctypes.data, n, n_values,
+                                                  1 if cs else 0, wc.ctypes.data if wc is not None else None, C.byref(fp)))
+    return fp.value
+
+
+def test_sharded_builder_equals_serial_builder(monkeypatch):
+    """Dictionary flattening: the concurrent per-first-class insert (csrc/trie_insert.hpp, used for
+    50 000+ keywords) must give bit-identical tables to the serial insert - every family, Set and Map, both trie
+    directions, duplicates (last wins / first wins for Shortest), None keywords, case folding, wide alphabets."""
+    rng = np.random.default_rng(11)
+
+    def words(n, alpha, lo, hi):
+        return ["".join(rng.choice(list(alpha), size=int(rng.integers(lo, hi + 1)))) for _ in range(n)]
+
+    dicts = [
+        words(3000, "abcdefghijklmnopqrstuvwxyz", 3, 12),
+        words(2000, "ab", 1, 16) + words(50, "ab", 1, 3) * 3,          # heavy sharing and duplicates
+        words(1500, "ABCdef0123=-", 1, 9) + [None, "", "Zz"],           # case folding, nulls
+        [chr(c) for c in range(0x20, 0x2000)] + words(200, "αβγЖж", 2, 5),  # wide alphabet
+        [],
+    ]
+    seen = set()
+    for kws in dicts:
+        for family in range(5):
+            for n_values in (-1, len(kws)):
+                for cs in (True, False):
+                    try:
+                        monkeypatch.setenv("ACGPU_BUILDER", "serial")
+                        a = _fingerprint(family, kws, n_values, cs)
+                    except Exception as e:   # WholeWord refuses keywords with inner non-word chars: both must refuse
+                        monkeypatch.setenv("ACGPU_BUILDER", "sharded")
+                        with pytest.raises(type(e)):
+                            _fingerprint(family, kws, n_values, cs)
+                        continue
+                    monkeypatch.setenv("ACGPU_BUILDER", "sharded")
+                    b = _fingerprint(family, kws, n_values, cs)
+                    assert a == b, (family, n_values, cs, len(kws))
+                    seen.add(a)
+    assert len(seen) > 40   # the fingerprint does depend on the dictionary, the family and the flags
+
+
+def test_builder_default_mode_is_deterministic_at_scale(monkeypatch):
+    """100 000 keywords take the sharded path by default; two builds and the forced serial build agree."""
+    import workloads as W
+    kws = W.config(1)["keywords"]
+    monkeypatch.delenv("ACGPU_BUILDER", raising=False)
+    a = _fingerprint(0, kws, len(kws), False)
+    b = _fingerprint(0, kws, len(kws), False)
+    monkeypatch.setenv("ACGPU_BUILDER", "serial")
+    c = _fingerprint(0, kws, len(kws), False)
+    assert a == b == c
+
+
+def test_trie_insert_unit_program():
+    """tests/cpp/trie_insert_test.cpp: 720 random cases, sharded (1, 4 and 13 threads) == serial on the raw arrays."""
+    import subprocess
+    out_dir = os.path.join(ROOT, "tests", "cpp", "build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "trie_insert_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-pthread", os.path.join(ROOT, "tests", "cpp", "trie_insert_test.cpp"),
+                           "-o", exe])
+    out = subprocess.run([exe, "4"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and " 0 failures" in out.stdout, out.stdout + out.stderr
