@@ -52,7 +52,7 @@ def lib():
     L.acgpu_create_from_keywords.restype = C.c_int
     L.acgpu_create_from_keywords.argtypes = [C.c_int, vp, vp, vp, i64, i64, C.c_int, vp, C.c_int, C.POINTER(u64)]
     L.acgpu_build_fingerprint.restype = C.c_int
-    L.acgpu_build_fingerprint.argtypes = [C.c_int, vp, vp, vp, i64, i64, C.c_int, vp, C.POINTER(u64)]
+    L.acgpu_build_fingerprint.argtypes = [C.c_int, vp, vp, vp, i64, i64, C.c_int, vp, C.POINTER(u64), C.POINTER(C.c_double)]
     L.acgpu_destroy.restype = C.c_int
     L.acgpu_destroy.argtypes = [u64]
     L.acgpu_word_chars.restype = C.c_int

@@ -475,9 +475,16 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
 
 uint64_t automaton_fingerprint(const HostAutomaton &a) {
     uint64_t h = 0xCBF29CE484222325ull;
-    auto bytes = [&](const void *p, size_t n) {
+    auto bytes = [&](const void *p, size_t n) {  // 8 bytes per step (FNV-1a style over words), then the tail
         const unsigned char *b = static_cast<const unsigned char *>(p);
-        for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 0x100000001B3ull;
+        size_t i = 0;
+        for (; i + 8 <= n; i += 8) {
+            uint64_t w;
+            std::memcpy(&w, b + i, 8);
+            h = (h ^ w) * 0x100000001B3ull;
+            h ^= h >> 29;
+        }
+        for (; i < n; i++) h = (h ^ b[i]) * 0x100000001B3ull;
     };
     auto num = [&](uint64_t v) { bytes(&v, sizeof v); };
     auto vec = [&](const auto &v) {

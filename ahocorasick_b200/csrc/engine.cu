@@ -1,5 +1,6 @@
 // libacgpu.so — C ABI (include/acgpu.h) over the sm_100a kernels.  No CPU matching path exists here:
 // every match entry point launches CUDA kernels or fails.
+#include <chrono>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -1073,11 +1074,13 @@ int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t 
 
 int acgpu_build_fingerprint(int family, const uint16_t *chars, const int64_t *offsets, const uint8_t *is_null,
                             int64_t n_keywords, int64_t n_values, int case_sensitive, const uint8_t *word_chars,
-                            uint64_t *fingerprint) {
+                            uint64_t *fingerprint, double *build_seconds) {
     if (!fingerprint || n_keywords < 0 || (n_keywords > 0 && (!chars || !offsets))) return fail(ACGPU_EINVAL, "bad arguments");
     try {
-        *fingerprint = automaton_fingerprint(
-            build_automaton(family, chars, offsets, is_null, n_keywords, n_values, case_sensitive != 0, word_chars));
+        const auto t0 = std::chrono::steady_clock::now();
+        const HostAutomaton a = build_automaton(family, chars, offsets, is_null, n_keywords, n_values, case_sensitive != 0, word_chars);
+        if (build_seconds) *build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        *fingerprint = automaton_fingerprint(a);
     } catch (const IllegalArgument &e) {
         return fail(ACGPU_EILLEGALARG, e.what());
     } catch (const std::domain_error &e) {

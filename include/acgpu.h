@@ -87,7 +87,7 @@ int acgpu_destroy(uint64_t handle);
  * (environment ACGPU_BUILDER=serial|sharded forces either; ACGPU_BUILD_TIMING=1 prints phase times). */
 int acgpu_build_fingerprint(int family, const uint16_t *chars, const int64_t *offsets, const uint8_t *is_null,
                             int64_t n_keywords, int64_t n_values, int case_sensitive, const uint8_t *word_chars,
-                            uint64_t *fingerprint);
+                            uint64_t *fingerprint, double *build_seconds /* optional: time of the flattening alone */);
 
 /* WordCharacters.generateWordCharsFlags (WordCharacters.java:6-16 mode 0, :18-24 mode 1, :26-39 mode 2). */
 int acgpu_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, int32_t n, uint8_t *out65536);

@@ -102,7 +102,7 @@ def _fingerprint(family, kws, n_values=-1, cs=True, wc=None):
     chars, offsets, is_null, n = _pack_keywords(kws)
     fp = C.c_uint64(0)
     _lib.check(_lib.lib().acgpu_build_fingerprint(family, chars.ctypes.data, offsets.ctypes.data, is_null.ctypes.data, n, n_values,
-                                                  1 if cs else 0, wc.ctypes.data if wc is not None else None, C.byref(fp)))
+                                                  1 if cs else 0, wc.ctypes.data if wc is not None else None, C.byref(fp), None))
     return fp.value
 
 
