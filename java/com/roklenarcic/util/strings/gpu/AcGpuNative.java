@@ -11,7 +11,7 @@ final class AcGpuNative {
         System.loadLibrary("acgpu_jni"); // links against libacgpu.so
     }
 
-    static final int AHOCORASICK = 0, LONGEST = 1, SHORTEST = 2, WHOLEWORD = 3;
+    static final int AHOCORASICK = 0, LONGEST = 1, SHORTEST = 2, WHOLEWORD = 3, WHOLEWORDLONGEST = 4;
 
     private AcGpuNative() {
     }
@@ -19,6 +19,12 @@ final class AcGpuNative {
     /** acgpu_create_from_keywords; nValues = -1 for a Set.  Throws IllegalArgumentException on ACGPU_EILLEGALARG. */
     static native long create(int family, char[] chars, long[] offsets, byte[] isNull, long nKeywords, long nValues,
             boolean caseSensitive, boolean[] wordChars, int device);
+
+    /**
+     * acgpu_word_chars: the boolean[65536] of WordCharacters.generateWordCharsFlags (WordCharacters.java:6-39; that class
+     * is package-private in the reference, so the facade cannot call it).  mode 0 default, 1 only chars, 2 default + toggles.
+     */
+    static native boolean[] wordChars(int mode, char[] chars, boolean[] toggles);
 
     /** acgpu_destroy */
     static native void destroy(long handle);

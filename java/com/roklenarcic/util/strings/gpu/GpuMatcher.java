@@ -108,37 +108,70 @@ abstract class GpuMatcher<T> implements AutoCloseable {
     }
 
     /**
-     * StringMap.match(Readable, ReadableMatchListener) — StringMap.java:6.  Reads the Readable in charBufferSize
-     * fills exactly like the reference (AhoCorasickMap.java:213-219) and forwards them in 4 MiB blocks; the Shortest
-     * family re-delivers a match that ends on a fill boundary (quirk Q4, ShortestMatchMap.java:241-249): the replay
-     * knows every fill boundary, so it is applied here (see ahocorasick_b200/streaming.py for the tested twin).
+     * StringMap.match(Readable, ReadableMatchListener) — StringMap.java:6.  Reads the Readable in charBufferSize fills
+     * exactly like the reference (AhoCorasickMap.java:213-219), batches the fills into 4 Mi-char device blocks and replays
+     * the ordered value indices of every block.  ShortestMatchMap re-delivers a match that ends exactly on a fill boundary
+     * and is followed by more input (quirk Q4, ShortestMatchMap.java:241-249); the replay knows every fill boundary.
+     * Tested twins of this method: include/acgpu.hpp (detail::Handle::matchReadable) and ahocorasick_b200/streaming.py.
      */
     @SuppressWarnings("unchecked")
     protected void matchReadable(Readable haystack, ReadableMatchListener<T> listener) throws IOException {
+        final int cbs = AcGpuNative.charBufferSize(handle);
+        final int blockChars = 1 << 22;
+        final boolean shortest = family == AcGpuNative.SHORTEST;
+        final java.util.HashSet<Long> boundaries = new java.util.HashSet<Long>();
         long s = AcGpuNative.streamBegin(handle);
         boolean ended = false;
         try {
-            CharBuffer buf = CharBuffer.allocate(1 << 21);
-            while (haystack.read(buf) != -1) {
-                buf.flip();
-                Object[] r = AcGpuNative.streamFeed(s, buf.array(), buf.remaining());
-                for (int v : (int[]) r[1]) {
-                    if (!listener.match((T) values[v])) {
-                        return;
+            char[] block = new char[blockChars + cbs];
+            long nRead = 0;
+            boolean eof = false;
+            while (!eof) {
+                int got = 0;
+                while (got < blockChars) {
+                    int k = haystack.read(CharBuffer.wrap(block, got, cbs));
+                    if (k < 0) {
+                        eof = true;
+                        break;
+                    }
+                    got += k;
+                    nRead += k;
+                    if (shortest && k > 0) {
+                        boundaries.add(nRead);
+                    }
+                    if (k == 0) {
+                        break;
                     }
                 }
-                buf.clear();
-            }
-            ended = true;
-            for (int v : (int[]) AcGpuNative.streamEnd(s)[1]) {
-                if (!listener.match((T) values[v])) {
+                if (got > 0 && !replayValues(AcGpuNative.streamFeed(s, block, got), listener, shortest, boundaries, nRead)) {
                     return;
                 }
             }
+            ended = true;
+            replayValues(AcGpuNative.streamEnd(s), listener, shortest, boundaries, nRead);
         } finally {
             if (!ended) {
                 AcGpuNative.streamEnd(s);
             }
         }
+    }
+
+    @SuppressWarnings("unchecked")
+    private boolean replayValues(Object[] r, ReadableMatchListener<T> listener, boolean shortest,
+            java.util.HashSet<Long> boundaries, long nRead) {
+        int[] pos = (int[]) r[0], val = (int[]) r[1];
+        for (int i = 0; i < val.length; i++) {
+            T v = (T) values[val[i]];
+            if (!listener.match(v)) {
+                return false;
+            }
+            if (shortest) {
+                long e = pos[2 * i + 1];
+                if (e < nRead && boundaries.contains(e) && !listener.match(v)) {
+                    return false;
+                }
+            }
+        }
+        return true;
     }
 }

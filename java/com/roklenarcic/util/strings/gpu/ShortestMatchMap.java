@@ -1,0 +1,28 @@
+package com.roklenarcic.util.strings.gpu;
+
+import java.io.IOException;
+
+import com.roklenarcic.util.strings.MapMatchListener;
+import com.roklenarcic.util.strings.ReadableMatchListener;
+import com.roklenarcic.util.strings.StringMap;
+import com.roklenarcic.util.strings.threshold.Thresholder;
+
+/** Drop-in for com.roklenarcic.util.strings.ShortestMatchMap (ShortestMatchMap.java:19,23,199,293). */
+public class ShortestMatchMap<T> extends GpuMatcher<T> implements StringMap<T> {
+    public ShortestMatchMap(final Iterable<String> keywords, final Iterable<? extends T> values, boolean caseSensitive) {
+        super(AcGpuNative.SHORTEST, keywords, values, caseSensitive, null);
+    }
+
+    public ShortestMatchMap(final Iterable<String> keywords, final Iterable<? extends T> values, boolean caseSensitive,
+            final Thresholder thresholdStrategy) {
+        this(keywords, values, caseSensitive);
+    }
+
+    public void match(final Readable haystack, final ReadableMatchListener<T> listener) throws IOException {
+        matchReadable(haystack, listener);
+    }
+
+    public void match(final String haystack, final MapMatchListener<T> listener) {
+        matchMap(haystack, listener);
+    }
+}

@@ -1,0 +1,21 @@
+package com.roklenarcic.util.strings.gpu;
+
+import com.roklenarcic.util.strings.SetMatchListener;
+import com.roklenarcic.util.strings.StringSet;
+import com.roklenarcic.util.strings.threshold.Thresholder;
+
+/** Drop-in for com.roklenarcic.util.strings.ShortestMatchSet (ShortestMatchSet.java:14,18,182). */
+public class ShortestMatchSet extends GpuMatcher<Void> implements StringSet {
+    public ShortestMatchSet(final Iterable<String> keywords, boolean caseSensitive) {
+        super(AcGpuNative.SHORTEST, keywords, null, caseSensitive, null);
+    }
+
+    /** The Thresholder only shapes the reference's node objects; it never changes results and is ignored. */
+    public ShortestMatchSet(final Iterable<String> keywords, boolean caseSensitive, final Thresholder thresholdStrategy) {
+        this(keywords, caseSensitive);
+    }
+
+    public void match(final String haystack, final SetMatchListener listener) {
+        matchSet(haystack, listener);
+    }
+}

@@ -1,0 +1,54 @@
+package com.roklenarcic.util.strings.gpu;
+
+import com.roklenarcic.util.strings.SetMatchListener;
+import com.roklenarcic.util.strings.StringSet;
+import com.roklenarcic.util.strings.threshold.Thresholder;
+
+/**
+ * Drop-in for com.roklenarcic.util.strings.WholeWordLongestMatchSet (WholeWordLongestMatchSet.java:16-45,47): the six constructor overloads; the word
+ * character table comes from acgpu_word_chars (the reference's WordCharacters is package-private).
+ */
+public class WholeWordLongestMatchSet extends GpuMatcher<Void> implements StringSet {
+    private final boolean[] wordChars;
+
+    public WholeWordLongestMatchSet(final Iterable<String> keywords, boolean caseSensitive) {
+        this(keywords, caseSensitive, AcGpuNative.wordChars(0, null, null), 0);
+    }
+
+    public WholeWordLongestMatchSet(final Iterable<String> keywords, boolean caseSensitive, char[] wordCharacters) {
+        this(keywords, caseSensitive, AcGpuNative.wordChars(1, wordCharacters, null), 0);
+    }
+
+    public WholeWordLongestMatchSet(final Iterable<String> keywords, boolean caseSensitive, char[] wordCharacters, boolean[] toggleFlags) {
+        this(keywords, caseSensitive, AcGpuNative.wordChars(2, wordCharacters, toggleFlags), 0);
+    }
+
+    /** The Thresholder overloads: it only shapes the reference's node objects and is ignored. */
+    public WholeWordLongestMatchSet(final Iterable<String> keywords, boolean caseSensitive, final Thresholder thresholdStrategy) {
+        this(keywords, caseSensitive);
+    }
+
+    public WholeWordLongestMatchSet(final Iterable<String> keywords, boolean caseSensitive, char[] wordCharacters,
+            final Thresholder thresholdStrategy) {
+        this(keywords, caseSensitive, wordCharacters);
+    }
+
+    public WholeWordLongestMatchSet(final Iterable<String> keywords, boolean caseSensitive, char[] wordCharacters, boolean[] toggleFlags,
+            final Thresholder thresholdStrategy) {
+        this(keywords, caseSensitive, wordCharacters, toggleFlags);
+    }
+
+    private WholeWordLongestMatchSet(final Iterable<String> keywords, boolean caseSensitive, boolean[] wordChars, int unused) {
+        super(AcGpuNative.WHOLEWORDLONGEST, keywords, null, caseSensitive, wordChars);
+        this.wordChars = wordChars;
+    }
+
+    public void match(final String haystack, final SetMatchListener listener) {
+        matchSet(haystack, listener);
+    }
+
+    /** getWordChars() - WholeWordLongestMatchSet.java:180 / WholeWordLongestMatchMap.java:308 (package-private in the reference; public here because the facade lives in its own package) */
+    public boolean[] getWordChars() {
+        return wordChars;
+    }
+}

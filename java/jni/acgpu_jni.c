@@ -53,6 +53,29 @@ JNIEXPORT jlong JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_create
     return (jlong)h;
 }
 
+JNIEXPORT jbooleanArray JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_wordChars(JNIEnv *env, jclass c, jint mode,
+                                                                                            jcharArray chars,
+                                                                                            jbooleanArray toggles) {
+    uint8_t local[65536];
+    const jsize n = chars ? (*env)->GetArrayLength(env, chars) : 0;
+    if (mode == 2 && (!toggles || (*env)->GetArrayLength(env, toggles) < n)) {
+        (*env)->ThrowNew(env, (*env)->FindClass(env, "java/lang/ArrayIndexOutOfBoundsException"), "toggleFlags shorter than wordCharacters");
+        return NULL;
+    }
+    jchar *pc = n ? (*env)->GetCharArrayElements(env, chars, NULL) : NULL;
+    jboolean *pt = (mode == 2 && n) ? (*env)->GetBooleanArrayElements(env, toggles, NULL) : NULL;
+    int rc = acgpu_word_chars(mode, (const uint16_t *)pc, (const uint8_t *)pt, (int32_t)n, local);
+    if (pc) (*env)->ReleaseCharArrayElements(env, chars, pc, JNI_ABORT);
+    if (pt) (*env)->ReleaseBooleanArrayElements(env, toggles, pt, JNI_ABORT);
+    if (rc != ACGPU_OK) {
+        throw_for(env, rc);
+        return NULL;
+    }
+    jbooleanArray out = (*env)->NewBooleanArray(env, 65536);
+    (*env)->SetBooleanArrayRegion(env, out, 0, 65536, (const jboolean *)local);
+    return out;
+}
+
 JNIEXPORT void JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_destroy(JNIEnv *env, jclass c, jlong h) {
     acgpu_destroy((uint64_t)h);
 }
