@@ -288,9 +288,14 @@ class Handle {
      * acgpu_stream_*; the ordered value indices of every block go to emit(valueIdx).  ShortestMatchMap re-delivers a
      * match that ends exactly on a fill boundary and is followed by more input (quirk Q4, ShortestMatchMap.java:241-249).
      * Observable difference from the reference: the reader is consumed up to one block ahead of the listener calls.
+     * blockChars = 0: blocks start at 64 Ki chars (an early-stopping caller over-reads little) and double up to 16 Mi
+     * chars (the fixed cost of a feed is amortised); > 0: fixed block size.
      */
     template <class Emit>
-    void matchReadable(Readable &in, Emit emit, size_t blockChars = size_t(1) << 22) const {
+    void matchReadable(Readable &in, Emit emit, size_t blockChars = 0) const {
+        const bool adaptive = blockChars == 0;
+        const size_t maxBlock = size_t(1) << 24;
+        if (adaptive) blockChars = size_t(1) << 16;
         const int cbs = charBufferSize();
         struct Stream {
             uint64_t s = 0;
@@ -316,6 +321,7 @@ class Handle {
         bool eof = false;
         while (!eof) {
             size_t got = 0;
+            if (block.size() < blockChars + (size_t)cbs) block.resize(blockChars + (size_t)cbs);
             while (got < blockChars) {
                 int k = in.read(block.data() + got, cbs);
                 if (k < 0) {
@@ -332,6 +338,7 @@ class Handle {
                 check(acgpu_stream_feed(st.s, reinterpret_cast<const uint16_t *>(block.data()), (int32_t)got, &rec.r));
                 if (!deliver(rec)) return;
             }
+            if (adaptive) blockChars = std::min(2 * blockChars, maxBlock);
         }
         Result rec;
         uint64_t s = st.s;

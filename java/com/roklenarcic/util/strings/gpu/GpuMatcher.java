@@ -109,7 +109,7 @@ abstract class GpuMatcher<T> implements AutoCloseable {
 
     /**
      * StringMap.match(Readable, ReadableMatchListener) — StringMap.java:6.  Reads the Readable in charBufferSize fills
-     * exactly like the reference (AhoCorasickMap.java:213-219), batches the fills into 4 Mi-char device blocks and replays
+     * exactly like the reference (AhoCorasickMap.java:213-219), batches the fills into device blocks (64 Ki chars doubling to 16 Mi) and replays
      * the ordered value indices of every block.  ShortestMatchMap re-delivers a match that ends exactly on a fill boundary
      * and is followed by more input (quirk Q4, ShortestMatchMap.java:241-249); the replay knows every fill boundary.
      * Tested twins of this method: include/acgpu.hpp (detail::Handle::matchReadable) and ahocorasick_b200/streaming.py.
@@ -117,7 +117,8 @@ abstract class GpuMatcher<T> implements AutoCloseable {
     @SuppressWarnings("unchecked")
     protected void matchReadable(Readable haystack, ReadableMatchListener<T> listener) throws IOException {
         final int cbs = AcGpuNative.charBufferSize(handle);
-        final int blockChars = 1 << 22;
+        int blockChars = 1 << 16;            // device blocks start small (early stop over-reads little) ...
+        final int maxBlockChars = 1 << 24;   // ... and double up to 16 Mi chars (the fixed cost of a feed is amortised)
         final boolean shortest = family == AcGpuNative.SHORTEST;
         final java.util.HashSet<Long> boundaries = new java.util.HashSet<Long>();
         long s = AcGpuNative.streamBegin(handle);
@@ -128,6 +129,9 @@ abstract class GpuMatcher<T> implements AutoCloseable {
             boolean eof = false;
             while (!eof) {
                 int got = 0;
+                if (block.length < blockChars + cbs) {
+                    block = new char[blockChars + cbs];
+                }
                 while (got < blockChars) {
                     int k = haystack.read(CharBuffer.wrap(block, got, cbs));
                     if (k < 0) {
@@ -146,6 +150,7 @@ abstract class GpuMatcher<T> implements AutoCloseable {
                 if (got > 0 && !replayValues(AcGpuNative.streamFeed(s, block, got), listener, shortest, boundaries, nRead)) {
                     return;
                 }
+                blockChars = Math.min(2 * blockChars, maxBlockChars);
             }
             ended = true;
             replayValues(AcGpuNative.streamEnd(s), listener, shortest, boundaries, nRead);

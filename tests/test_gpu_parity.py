@@ -623,3 +623,54 @@ def test_random_dictionaries_medium_haystacks(seed):
         assert np.array_equal(rec.value.astype(np.int64), want["value"].astype(np.int64)), (seed, family)
         rec = SETS[family](kws, cs).match_records(hay)
         assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"]), (seed, family, "set")
+
+
+@pytest.mark.parametrize("family", FAMILIES)
+def test_concurrent_match_on_one_instance(family):
+    """Threading contract of the reference: the automaton is immutable after the constructor and every
+    match() keeps its state in locals, so concurrent match() calls on ONE instance are safe.  Here: 6 threads share one
+    Map, each runs String matches over its own haystacks plus one Readable match, all against oracle streams computed
+    up front (ctypes releases the GIL during the native call, so the calls really overlap)."""
+    import threading
+    word = family.startswith("wholeword")
+    c = W.config(3 if word else 2, scale=0.02)
+    kws = list(c["keywords"])
+    if family == "wholewordlongest":
+        kws = kws + [a + " " + b for a, b in zip(kws[::9], kws[4::9])]
+    if word:
+        m = MAPS[family](kws, list(range(len(kws))), True, *c["word_chars"])
+        o = ora.Matcher(family, kws, n_values=len(kws), word_chars_table=ora.word_chars(2, *c["word_chars"]))
+    else:
+        m = MAPS[family](kws, list(range(len(kws))), True)
+        o = ora.Matcher(family, kws, n_values=len(kws))
+    n_threads, per_thread = 6, 3
+    hays = [W.make_haystack(c["spec"], 150_000 + 37_000 * i, start=i * W.BLOCK * 8192) for i in range(n_threads * per_thread)]
+    want = [o.match(h) for h in hays]
+    want_readable = [o.match(hays[t * per_thread], readable=True)["value"].astype(np.int64) for t in range(n_threads)]
+    errors = []
+    barrier = threading.Barrier(n_threads)
+
+    def work(t):
+        try:
+            barrier.wait()
+            for rep in range(2):
+                for i in range(t * per_thread, (t + 1) * per_thread):
+                    rec = m.match_records(hays[i])
+                    w = want[i]
+                    assert len(rec) == len(w), (t, i, len(rec), len(w))
+                    assert np.array_equal(rec.start, w["start"]) and np.array_equal(rec.end, w["end"]), (t, i)
+                    assert np.array_equal(rec.value.astype(np.int64), w["value"].astype(np.int64)), (t, i)
+            got = []
+            m.match(_NumpyReadable(hays[t * per_thread]), lambda v: got.append(v) or True)
+            assert np.array_equal(np.array(got, dtype=np.int64), want_readable[t]), (t, "readable")
+        except BaseException as e:  # noqa: BLE001 - collected and re-raised on the main thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    if errors:
+        raise errors[0]
+    assert sum(len(w) for w in want) > 1000
