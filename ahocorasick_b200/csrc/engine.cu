@@ -1141,6 +1141,13 @@ int acgpu_match_device_async(uint64_t handle, const void *d_haystack, int64_t n,
     int rc = ensure_device(m);
     if (rc != ACGPU_OK) return rc;
     RunOpts opt;
+    if (m->host.family == ACGPU_WHOLEWORD || (m->host.family == ACGPU_WHOLEWORDLONGEST && m->use_ww)) {
+        // word-start range shards: a word is matched from its own start, so a shard reports the words that
+        // START in [emit_from, emit_to); it reads one char of look-behind and up to max_len + 1 chars past emit_to
+        if (emit_from < 0 || emit_to > n || emit_from > emit_to) return fail(ACGPU_EINVAL, "emit range outside the haystack");
+        opt.ctx = emit_from;
+        opt.chain_n = emit_to;
+    }
     return enqueue_match(m, static_cast<const uint16_t *>(d_haystack), n, emit_from, emit_to, static_cast<int2 *>(d_pos),
                          static_cast<uint32_t *>(d_val), cap, static_cast<unsigned long long *>(d_total),
                          static_cast<cudaStream_t>(cuda_stream), opt);

@@ -9,6 +9,9 @@ left context), so a corpus shards with NO data-path collective:
   ``max_len - 1`` chars of left context: ``plan_range_shards``.  Concatenating the ranks' record streams in rank
   order gives exactly the single-GPU stream (end ascending, longest first).
 
+The WholeWord family shards the same way by word-START range (``plan_word_shards``); Longest / Shortest /
+WholeWordLongest carry a selection chain across positions and shard by haystack only.
+
 The only exchange is an all-gather of per-rank match counts (8 bytes per rank) so that every rank knows its
 global record offset: ``exchange_counts`` (NCCL on device tensors, gloo on CPU tensors in the tests).
 """
@@ -42,6 +45,37 @@ def plan_range_shards(n_chars: int, world: int, max_len: int, align: int = 8) ->
         bounds.append(max(bounds[-1], min(b, n_chars)))
     bounds.append(n_chars)
     return [RangeShard(r, bounds[r], bounds[r + 1], max(0, bounds[r] - ctx)) for r in range(world)]
+
+
+@dataclass(frozen=True)
+class WordShard:
+    rank: int
+    emit_from: int   # first word-START position this rank reports
+    emit_to: int     # one past the last
+    read_from: int   # one char of look-behind (is emit_from a word start?)
+    read_to: int     # emit_to + max_len + 1, clipped: a word starting before emit_to is decided by then
+
+
+def plan_word_shards(n_chars: int, world: int, max_len: int) -> List[WordShard]:
+    """WholeWord family: a word is a keyword or not by itself, so one large haystack is cut by word-START
+    range with no state across shards; boundaries may fall anywhere, also inside a word (the word belongs to the
+    shard holding its first char).  Rank-ordered concatenation of the shards' streams is the single-GPU stream."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    bounds = [n_chars * r // world for r in range(world)] + [n_chars]
+    return [WordShard(r, bounds[r], bounds[r + 1], max(0, bounds[r] - 1), min(n_chars, bounds[r + 1] + max_len + 1))
+            for r in range(world)]
+
+
+def match_word_shard(matcher, d_haystack_ptr: int, shard: WordShard, d_pos_ptr: int, d_val_ptr, cap: int, stream_ptr=None) -> int:
+    """Scan one word-start range (WholeWordMatchSet/Map) of a haystack resident on this rank's GPU; the pointer addresses
+    char 0 of the WHOLE haystack, only [shard.read_from, shard.read_to) is touched.  Returns the number of matches."""
+    import ctypes as C
+    from . import _lib
+    tot = C.c_int64(0)
+    _lib.check(_lib.lib().acgpu_match_device(matcher.handle, d_haystack_ptr, shard.read_to, shard.emit_from, shard.emit_to,
+                                             d_pos_ptr, d_val_ptr, cap, C.byref(tot), stream_ptr))
+    return tot.value
 
 
 def deal_haystacks(n_haystacks: int, world: int, rank: int) -> List[int]:

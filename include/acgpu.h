@@ -114,8 +114,11 @@ void acgpu_free_result(acgpu_result *r);
  * The call synchronises the stream before returning (it reads back *n_out).
  *
  * Sharding: emit_from/emit_to restrict reported matches; the scan itself may look outside:
- *   AhoCorasick: matches with  emit_from <  end   <= emit_to
- *   other families need the whole haystack (chain state) — pass emit_from = 0, emit_to = n.
+ *   AhoCorasick: matches with  emit_from <  end   <= emit_to   (reads max_len - 1 chars before emit_from)
+ *   WholeWord:   matches with  emit_from <= start <  emit_to   (reads 1 char before emit_from and needs
+ *                n >= min(length of the haystack, emit_to + max_len + 1): a word is a keyword or not by itself)
+ *   Longest / Shortest / WholeWordLongest carry a selection chain across positions and need the whole
+ *   haystack — pass emit_from = 0, emit_to = n (corpora of independent haystacks shard by haystack).
  */
 int acgpu_match_device(uint64_t handle, const void *d_haystack, int64_t n, int64_t emit_from, int64_t emit_to,
                        void *d_pos, void *d_val, int64_t cap, int64_t *n_out, void *cuda_stream);

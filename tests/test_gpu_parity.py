@@ -366,6 +366,45 @@ def test_device_range_shards_and_cap():
     assert total == len(want)
 
 
+@pytest.mark.parametrize("is_map", [False, True])
+def test_wholeword_word_start_range_shards(is_map):
+    """SURVEY 8e, WholeWord: a haystack cut by word-START range at arbitrary boundaries (also inside words) - every shard
+    sees only [read_from, read_to) semantics-wise (n = read_to) and the rank-ordered concatenation is the single stream."""
+    import ctypes as C
+    import torch
+    from ahocorasick_b200 import _lib
+    from ahocorasick_b200.sharding import plan_word_shards
+    c = W.config(3, scale=0.05)
+    kws = c["keywords"]
+    hay = W.make_haystack(c["spec"], 400_003)
+    want = ora.Matcher("wholeword", kws, n_values=len(kws), word_chars_table=ora.word_chars(2, *c["word_chars"])).match(hay)
+    want_pos = np.stack([want["start"], want["end"]], axis=1).astype(np.int32)
+    assert len(want) > 500
+    m = (ac.WholeWordMatchMap(kws, list(range(len(kws))), True, *c["word_chars"]) if is_map
+         else ac.WholeWordMatchSet(kws, True, *c["word_chars"]))
+    max_len = m.info()["max_len"]
+    lib = _lib.lib()
+    d_hay = torch.from_numpy(hay.astype(np.int16)).cuda()
+    d_pos = torch.empty((len(want) + 16, 2), dtype=torch.int32, device="cuda")
+    d_val = torch.empty(len(want) + 16, dtype=torch.int32, device="cuda")
+    for world in (1, 2, 3, 7, 64):
+        pos_parts, val_parts = [], []
+        for sh in plan_word_shards(hay.size, world, max_len):
+            tot = C.c_int64(0)
+            _lib.check(lib.acgpu_match_device(m.handle, d_hay.data_ptr(), sh.read_to, sh.emit_from, sh.emit_to, d_pos.data_ptr(),
+                                              d_val.data_ptr() if is_map else None, len(want) + 16, C.byref(tot), None))
+            torch.cuda.synchronize()
+            pos_parts.append(d_pos[:tot.value].cpu().numpy().copy())
+            val_parts.append(d_val[:tot.value].cpu().numpy().copy())
+        got = np.concatenate(pos_parts, axis=0)
+        assert got.shape == want_pos.shape and np.array_equal(got, want_pos), world
+        if is_map:
+            assert np.array_equal(np.concatenate(val_parts).astype(np.int64), want["value"].astype(np.int64)), world
+    tot = C.c_int64(0)
+    rc = lib.acgpu_match_device(m.handle, d_hay.data_ptr(), hay.size, 10, hay.size + 1, d_pos.data_ptr(), None, 16, C.byref(tot), None)
+    assert rc == _lib.EINVAL
+
+
 # ---------------------------------------------------------------- Longest / Shortest on the start-mask path (kernel_sel2.cuh)
 
 @pytest.mark.parametrize("family", ["longest", "shortest"])
