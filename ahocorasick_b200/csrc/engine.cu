@@ -1227,6 +1227,7 @@ struct StreamCtx {
     int64_t chain = 0;    // absolute chain position (selection families)
     int64_t *d_carry = nullptr;
     unsigned long long *d_total = nullptr;
+    double density = 0.0;  // records per finalised char seen so far (max over feeds): sizes the next feed's record buffer
 };
 
 StreamCtx *as_stream(uint64_t h) {
@@ -1309,7 +1310,9 @@ int stream_process(StreamCtx *s, bool final, acgpu_result *out) {
     fill_empty(out);
     if (limit <= s->ctx) return ACGPU_OK;
 
-    int64_t cap = std::max<int64_t>(1 << 16, (limit - s->ctx) / 4);
+    // record buffer: a quarter record per char, or 1.25 x the densest feed so far - a feed that overflows is scanned twice
+    const int64_t span = limit - s->ctx;
+    int64_t cap = std::max<int64_t>(1 << 16, std::max<int64_t>(span / 4, static_cast<int64_t>(1.25 * s->density * static_cast<double>(span)) + 1024));
     unsigned long long total = 0;
     int2 *d_pos = nullptr;
     uint32_t *d_val = nullptr;
@@ -1339,6 +1342,7 @@ int stream_process(StreamCtx *s, bool final, acgpu_result *out) {
         d_val = nullptr;
         cap = static_cast<int64_t>(total);
     }
+    s->density = std::max(s->density, static_cast<double>(total) / static_cast<double>(std::max<int64_t>(span, 1)));
     if (total > 0) {
         // one page-locked block from the process-wide cache: positions, then values (acgpu_free_result hands it back)
         PinnedBlock blk;
