@@ -89,3 +89,83 @@ def test_plan_properties():
             assert s.emit_from % 8 == 0 or s.emit_from == n
     assert sharding.deal_haystacks(32, 8, 3) == [3, 11, 19, 27]
     assert sorted(sum((sharding.deal_haystacks(10, 4, r) for r in range(4)), [])) == list(range(10))
+
+
+# ---------------------------------------------------------------- WholeWord: word-START range shards
+
+def _word_case():
+    rng = random.Random(777)
+    # sorted: set order depends on the per-process string hash seed, and value indices must agree across ranks
+    kws = sorted({"".join(rng.choice("abcd") for _ in range(rng.randint(1, 7))) for _ in range(60)})
+    hay = "".join(rng.choice("abcd" * 3 + " ,._") for _ in range(6000))
+    return kws, hay
+
+
+def _word_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as ora
+        kws, hay = _word_case()
+        m = ora.Matcher("wholeword", kws, n_values=len(kws))
+        max_len = max(len(k) for k in kws)
+        shard = sharding.plan_word_shards(len(hay), world, max_len)[rank]
+        # the rank only sees [read_from, read_to): one char of look-behind, max_len + 1 chars of look-ahead;
+        # it reports the words that START in [emit_from, emit_to)
+        piece = hay[shard.read_from:shard.read_to]
+        mine = [(int(r["start"]) + shard.read_from, int(r["end"]) + shard.read_from, int(r["value"])) for r in m.match(piece)]
+        mine = [t for t in mine if shard.emit_from <= t[0] < shard.emit_to]
+        counts, offset, total = sharding.exchange_counts(len(mine))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        q.put((counts, offset, total, sharding.merge_rank_streams(gathered) if rank == 0 else None))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_word_shards_world2_gloo():
+    from oracle import oracle as ora
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_word_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    kws, hay = _word_case()
+    want = [(int(r["start"]), int(r["end"]), int(r["value"])) for r in ora.Matcher("wholeword", kws, n_values=len(kws)).match(hay)]
+    merged = [r[3] for r in results if r[3] is not None][0]
+    assert merged == want and len(want) > 50
+    for counts, offset, total, _ in results:
+        assert total == len(want) and sum(counts) == total
+
+
+def test_word_shard_plan_and_semantics_many_worlds():
+    """plan_word_shards covers [0, n) without gaps or overlaps for any world size, and the shard semantics (one char of
+    look-behind, max_len + 1 of look-ahead, filter by word start) reproduce the single stream even when boundaries cut
+    words - checked with the oracle in-process for world sizes up to more shards than words."""
+    from oracle import oracle as ora
+    kws, hay = _word_case()
+    m = ora.Matcher("wholeword", kws)
+    max_len = max(len(k) for k in kws)
+    want = [(int(r["start"]), int(r["end"])) for r in m.match(hay)]
+    for world in (1, 2, 3, 5, 16, 257, 3000):
+        shards = sharding.plan_word_shards(len(hay), world, max_len)
+        assert len(shards) == world and shards[0].emit_from == 0 and shards[-1].emit_to == len(hay)
+        got = []
+        for a, b in zip(shards, shards[1:]):
+            assert a.emit_to == b.emit_from
+        for s in shards:
+            assert s.read_from == max(0, s.emit_from - 1) and s.read_to == min(len(hay), s.emit_to + max_len + 1)
+            if s.emit_to == s.emit_from:
+                continue
+            piece = hay[s.read_from:s.read_to]
+            got += [(int(r["start"]) + s.read_from, int(r["end"]) + s.read_from) for r in m.match(piece)
+                    if s.emit_from <= int(r["start"]) + s.read_from < s.emit_to]
+        assert got == want, world
