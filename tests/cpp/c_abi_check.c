@@ -1,0 +1,45 @@
+/* include/acgpu.h must be a plain C header (C99, no C++/torch types) and every declared entry point must link from C.
+ * Host-only calls are exercised; the matching entry points are only referenced (they need a CUDA device).
+ * Built and run by tests/test_host_cpu.py::test_header_is_plain_c_and_links_from_c. */
+#include <stdio.h>
+#include <string.h>
+
+#include "acgpu.h"
+
+int main(void) {
+    /* every entry point, by address: a missing export fails at link time */
+    typedef void (*fn)(void);
+    const fn syms[] = {(fn)acgpu_create_from_keywords, (fn)acgpu_build_fingerprint, (fn)acgpu_destroy, (fn)acgpu_word_chars,
+                       (fn)acgpu_info, (fn)acgpu_match_utf16, (fn)acgpu_free_result, (fn)acgpu_match_device,
+                       (fn)acgpu_match_device_async, (fn)acgpu_launches_per_match, (fn)acgpu_stream_begin, (fn)acgpu_stream_feed,
+                       (fn)acgpu_stream_end, (fn)acgpu_last_error, (fn)acgpu_version};
+    unsigned i, n_syms = (unsigned)(sizeof syms / sizeof syms[0]);
+    for (i = 0; i < n_syms; i++)
+        if (!syms[i]) return 10;
+
+    static uint8_t flags[65536];
+    const uint16_t toggled[2] = {'_', '='};
+    const uint8_t toggles[2] = {0, 1};
+    if (acgpu_word_chars(2, toggled, toggles, 2, flags) != ACGPU_OK) return 11;
+    if (flags['_'] || !flags['='] || !flags['a'] || flags[' ']) return 12;
+
+    /* "he", "she", "hers" + a null entry; WholeWord refuses "as if" with the reference's message */
+    const uint16_t chars[] = {'h', 'e', 's', 'h', 'e', 'h', 'e', 'r', 's', 'a', 's', ' ', 'i', 'f'};
+    const int64_t offsets[] = {0, 2, 5, 9, 9, 14};
+    const uint8_t is_null[] = {0, 0, 0, 1, 0};
+    uint64_t fp1 = 0, fp2 = 0, fp3 = 0;
+    double secs = -1.0;
+    if (acgpu_build_fingerprint(ACGPU_AHOCORASICK, chars, offsets, is_null, 4, 4, 0, NULL, &fp1, &secs) != ACGPU_OK) return 13;
+    if (acgpu_build_fingerprint(ACGPU_AHOCORASICK, chars, offsets, is_null, 4, 4, 0, NULL, &fp2, NULL) != ACGPU_OK) return 14;
+    if (acgpu_build_fingerprint(ACGPU_LONGEST, chars, offsets, is_null, 4, 4, 0, NULL, &fp3, NULL) != ACGPU_OK) return 15;
+    if (fp1 != fp2 || fp1 == fp3 || secs < 0.0) return 16;
+    if (acgpu_build_fingerprint(ACGPU_WHOLEWORD, chars, offsets, is_null, 5, -1, 1, NULL, &fp3, NULL) != ACGPU_EILLEGALARG) return 17;
+    if (strcmp(acgpu_last_error(), "as if contains non-word characters.") != 0) return 18;
+    if (acgpu_build_fingerprint(ACGPU_WHOLEWORDLONGEST, chars, offsets, is_null, 5, -1, 1, NULL, &fp3, NULL) != ACGPU_OK) return 19;
+    if (acgpu_destroy(0) != ACGPU_EINVAL) return 20;
+    if (!acgpu_version() || !*acgpu_version()) return 21;
+    acgpu_result empty = {0, NULL, NULL};
+    acgpu_free_result(&empty); /* releasing an empty result is a no-op */
+    printf("c abi ok: %u entry points, version %s\n", n_syms, acgpu_version());
+    return 0;
+}

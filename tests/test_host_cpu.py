@@ -164,3 +164,17 @@ def test_trie_insert_unit_program():
                            "-o", exe])
     out = subprocess.run([exe, "4"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and " 0 failures" in out.stdout, out.stdout + out.stderr
+
+
+def test_header_is_plain_c_and_links_from_c():
+    """The drop-in boundary is a C ABI: include/acgpu.h compiles as strict C99 (no C++ or torch types in the signatures),
+    every declared entry point links from a C program, and the host-only calls behave (tests/cpp/c_abi_check.c)."""
+    import subprocess
+    out_dir = os.path.join(ROOT, "tests", "cpp", "build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "c_abi_check")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "c_abi_check.c"), "-L" + os.path.join(ROOT, "ahocorasick_b200"),
+                           "-lacgpu", "-Wl,-rpath," + os.path.join(ROOT, "ahocorasick_b200"), "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "c abi ok: %d entry points" % len(_header_symbols()) in r.stdout, (r.returncode, r.stdout, r.stderr)
