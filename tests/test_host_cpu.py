@@ -178,3 +178,19 @@ def test_header_is_plain_c_and_links_from_c():
                            "-lacgpu", "-Wl,-rpath," + os.path.join(ROOT, "ahocorasick_b200"), "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "c abi ok: %d entry points" % len(_header_symbols()) in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_builder_tables_match_committed_fingerprints(monkeypatch):
+    """The CUDA kernels read the flattened tables, and only a GPU run can prove a new layout right.  This guard fails when
+    a change alters the tables of seeded dictionaries (tests/golden/builder_fingerprints.json, generated by
+    tests/golden/make_builder_fingerprints.py): re-run the GPU parity suite, then regenerate the file."""
+    import json
+    import sys
+    monkeypatch.delenv("ACGPU_BUILDER", raising=False)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_builder_fingerprints as g
+    want = json.load(open(g.OUT))
+    got = g.compute()
+    assert sorted(got) == sorted(want)
+    diff = [k for k in want if got[k] != want[k]]
+    assert not diff, "flattened tables changed for %d dictionaries, e.g. %s" % (len(diff), diff[:3])
