@@ -17,7 +17,7 @@ AHOCORASICK, LONGEST, SHORTEST, WHOLEWORD, WHOLEWORDLONGEST = 0, 1, 2, 3, 4
 
 # every symbol include/acgpu.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "acgpu_create_from_keywords", "acgpu_build_fingerprint", "acgpu_destroy", "acgpu_word_chars", "acgpu_info",
+    "acgpu_create_from_keywords", "acgpu_build_fingerprint", "acgpu_destroy", "acgpu_word_chars", "acgpu_info", "acgpu_char_classes",
     "acgpu_match_utf16", "acgpu_free_result", "acgpu_match_device", "acgpu_match_device_async",
     "acgpu_launches_per_match", "acgpu_stream_begin", "acgpu_stream_feed", "acgpu_stream_end",
     "acgpu_last_error", "acgpu_version",
@@ -59,6 +59,8 @@ def lib():
     L.acgpu_word_chars.argtypes = [C.c_int, vp, vp, i32, vp]
     L.acgpu_info.restype = C.c_int
     L.acgpu_info.argtypes = [u64, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]
+    L.acgpu_char_classes.restype = C.c_int
+    L.acgpu_char_classes.argtypes = [u64, vp, C.POINTER(i32)]
     L.acgpu_match_utf16.restype = C.c_int
     L.acgpu_match_utf16.argtypes = [u64, vp, i32, C.POINTER(Result)]
     L.acgpu_free_result.restype = None

@@ -1123,6 +1123,14 @@ int acgpu_info(uint64_t handle, int64_t *n_nodes, int32_t *n_classes, int32_t *m
     return ACGPU_OK;
 }
 
+int acgpu_char_classes(uint64_t handle, uint16_t *out65536, int32_t *has_other) {
+    Matcher *m = as_matcher(handle);
+    if (!m || !out65536) return fail(ACGPU_EINVAL, "bad arguments");
+    std::memcpy(out65536, m->host.cls.data(), 65536 * sizeof(uint16_t));
+    if (has_other) *has_other = m->host.has_other ? 1 : 0;
+    return ACGPU_OK;
+}
+
 int acgpu_launches_per_match(uint64_t handle) {
     Matcher *m = as_matcher(handle);
     if (!m) return fail(ACGPU_EINVAL, "bad handle");

@@ -226,6 +226,14 @@ class _Matcher:
     def handle(self) -> int:
         return self._h
 
+    def char_classes(self) -> Tuple[np.ndarray, bool]:
+        """(classes[65536], has_other): class of every UTF-16 code unit under this matcher's case folding; with has_other,
+        class 0 = "occurs in no keyword" (not part of the reference API; used by sharding.plan_sync_shards)."""
+        out = np.zeros(65536, np.uint16)
+        ho = C.c_int32(0)
+        check(_lib.lib().acgpu_char_classes(self._h, out.ctypes.data, C.byref(ho)))
+        return out, bool(ho.value)
+
     def match_records(self, haystack) -> _Records:
         """The ordered (start, end[, valueIdx]) stream of one match(String) call, without replay."""
         hay = _utf16(haystack)

@@ -9,8 +9,10 @@ left context), so a corpus shards with NO data-path collective:
   ``max_len - 1`` chars of left context: ``plan_range_shards``.  Concatenating the ranks' record streams in rank
   order gives exactly the single-GPU stream (end ascending, longest first).
 
-The WholeWord family shards the same way by word-START range (``plan_word_shards``); Longest / Shortest /
-WholeWordLongest carry a selection chain across positions and shard by haystack only.
+The WholeWord family shards the same way by word-START range (``plan_word_shards``).  Longest / Shortest carry a
+selection chain across positions; one haystack is cut at SYNCHRONISATION points - chars that occur in no keyword reset
+every reference automaton - into independent pieces (``plan_sync_shards``; exact, but needs such chars near the even
+split, else the haystack stays whole).  WholeWordLongest shards by haystack only.
 
 The only exchange is an all-gather of per-rank match counts (8 bytes per rank) so that every rank knows its
 global record offset: ``exchange_counts`` (NCCL on device tensors, gloo on CPU tensors in the tests).
@@ -75,6 +77,62 @@ def match_word_shard(matcher, d_haystack_ptr: int, shard: WordShard, d_pos_ptr: 
     tot = C.c_int64(0)
     _lib.check(_lib.lib().acgpu_match_device(matcher.handle, d_haystack_ptr, shard.read_to, shard.emit_from, shard.emit_to,
                                              d_pos_ptr, d_val_ptr, cap, C.byref(tot), stream_ptr))
+    return tot.value
+
+
+@dataclass(frozen=True)
+class SyncShard:
+    rank: int
+    lo: int   # the shard is the independent haystack [lo, hi); positions it reports are relative to lo
+    hi: int
+
+
+def plan_sync_shards(haystack, world: int, classes, has_other: bool, window: int = 1 << 20):
+    """Longest / Shortest (and AhoCorasick): cut ONE haystack into `world` independent pieces at SYNCHRONISATION points.
+
+    A char that occurs in no keyword (class 0 of ``matcher.char_classes()``) sends every reference automaton back to its
+    root (all transitions fail), flushes the Longest match queue (LongestMatchSet.java:227) and ends any pending Shortest
+    match, so the scan of what follows does not depend on what came before: the rank-ordered concatenation of the pieces'
+    streams (positions shifted by ``lo``) is exactly the single stream.  Boundaries are the first such position at or
+    after the even split, searched over at most `window` chars; returns None when one boundary has no synchronisation
+    point in its window (e.g. every char of the text occurs in some keyword) - the caller then keeps the haystack whole.
+    `haystack` is a uint16 numpy array or an int16 / uint16 torch tensor (device tensors copy only the windows).
+    Not valid for the WholeWord families (use plan_word_shards / keep WholeWordLongest whole)."""
+    import numpy as np
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    n = int(haystack.shape[0])
+    if world == 1:
+        return [SyncShard(0, 0, n)]
+    if not has_other:
+        return None
+    is_other = np.asarray(classes) == 0
+    bounds = [0]
+    for r in range(1, world):
+        b = max(n * r // world, bounds[-1], 1)
+        if b >= n:
+            bounds.append(n)
+            continue
+        w = haystack[b - 1:min(n, b - 1 + window)]      # char p - 1 decides whether p is a synchronisation point
+        if hasattr(w, "cpu"):
+            w = w.cpu().numpy()
+        hit = np.flatnonzero(is_other[np.asarray(w).view(np.uint16)])
+        if hit.size == 0:
+            return None
+        bounds.append(b + int(hit[0]))
+    bounds.append(n)
+    return [SyncShard(r, bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def match_sync_shard(matcher, d_haystack_ptr: int, shard: SyncShard, d_pos_ptr: int, d_val_ptr, cap: int, stream_ptr=None) -> int:
+    """Scan one piece of plan_sync_shards as a haystack of its own (the pointer addresses char 0 of the WHOLE haystack).
+    The records written are relative to shard.lo: add shard.lo to both columns when merging.  Returns the match count."""
+    import ctypes as C
+    from . import _lib
+    tot = C.c_int64(0)
+    n = shard.hi - shard.lo
+    _lib.check(_lib.lib().acgpu_match_device(matcher.handle, d_haystack_ptr + 2 * shard.lo, n, 0, n, d_pos_ptr, d_val_ptr, cap,
+                                             C.byref(tot), stream_ptr))
     return tot.value
 
 

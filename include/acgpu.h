@@ -96,6 +96,12 @@ int acgpu_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, in
 int acgpu_info(uint64_t handle, int64_t *n_nodes, int32_t *n_classes, int32_t *max_len,
                int32_t *char_buffer_size, int64_t *table_bytes);
 
+/* The character-class table of the flattened dictionary: out65536[c] = class of UTF-16 code unit c with the matcher's
+ * case folding (Character.toLowerCase, AhoCorasickSet.java:33,229) folded in.  When *has_other is 1, class 0 means
+ * "c occurs in no keyword": right after such a char every reference automaton is back in its root state, so the
+ * haystack can be cut there into independent pieces (ahocorasick_b200/sharding.py::plan_sync_shards). */
+int acgpu_char_classes(uint64_t handle, uint16_t *out65536, int32_t *has_other);
+
 /*
  * match(String haystack, listener) — StringSet.java:4, StringMap.java:8; the scan loops
  * AhoCorasickSet.java:193-252, LongestMatchSet.java:192-265, ShortestMatchSet.java:182-260,

@@ -10,7 +10,7 @@ int main(void) {
     /* every entry point, by address: a missing export fails at link time */
     typedef void (*fn)(void);
     const fn syms[] = {(fn)acgpu_create_from_keywords, (fn)acgpu_build_fingerprint, (fn)acgpu_destroy, (fn)acgpu_word_chars,
-                       (fn)acgpu_info, (fn)acgpu_match_utf16, (fn)acgpu_free_result, (fn)acgpu_match_device,
+                       (fn)acgpu_info, (fn)acgpu_char_classes, (fn)acgpu_match_utf16, (fn)acgpu_free_result, (fn)acgpu_match_device,
                        (fn)acgpu_match_device_async, (fn)acgpu_launches_per_match, (fn)acgpu_stream_begin, (fn)acgpu_stream_feed,
                        (fn)acgpu_stream_end, (fn)acgpu_last_error, (fn)acgpu_version};
     unsigned i, n_syms = (unsigned)(sizeof syms / sizeof syms[0]);

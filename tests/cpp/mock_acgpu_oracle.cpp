@@ -80,6 +80,7 @@ int acgpu_info(uint64_t h, int64_t *n_nodes, int32_t *n_classes, int32_t *max_le
     if (bytes) *bytes = 0;
     return ACGPU_OK;
 }
+int acgpu_char_classes(uint64_t, uint16_t *, int32_t *) { return fail(ACGPU_EUNSUPPORTED, "mock: no class table"); }
 int acgpu_match_utf16(uint64_t h, const uint16_t *hay, int32_t n, acgpu_result *out) { return fill((Mock *)(uintptr_t)h, hay, n, out); }
 void acgpu_free_result(acgpu_result *r) {
     if (!r) return;

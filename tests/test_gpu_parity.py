@@ -405,6 +405,42 @@ def test_wholeword_word_start_range_shards(is_map):
     assert rc == _lib.EINVAL
 
 
+@pytest.mark.parametrize("family,is_map", [("longest", True), ("shortest", False), ("ahocorasick", True)])
+def test_sync_point_shards_on_device(family, is_map):
+    """SURVEY 8e for the chain families: one resident haystack cut at synchronisation points (chars that occur in no
+    keyword, matcher.char_classes()) into independent pieces; every piece is scanned as a haystack of its own
+    (unaligned device pointers included) and the shifted, rank-ordered concatenation is the oracle's single stream."""
+    import torch
+    from ahocorasick_b200.sharding import match_sync_shard, plan_sync_shards
+    c = W.config(2, scale=0.02)
+    kws = c["keywords"]
+    hay = W.make_haystack(c["spec"], 500_000)
+    want = ora.Matcher(family, kws, n_values=len(kws) if is_map else -1).match(hay)
+    want_pos = np.stack([want["start"], want["end"]], axis=1).astype(np.int64)
+    m = (MAPS if is_map else SETS)[family](*((kws, list(range(len(kws))), True) if is_map else (kws, True)))
+    classes, has_other = m.char_classes()
+    assert has_other and classes[ord(" ")] == 0 and classes[ord("a")] != 0 and classes[ord("A")] == 0
+    d_hay = torch.from_numpy(hay.astype(np.int16)).cuda()
+    cap = len(want) + 16
+    d_pos = torch.empty((cap, 2), dtype=torch.int32, device="cuda")
+    d_val = torch.empty(cap, dtype=torch.int32, device="cuda")
+    for world in (2, 3, 8):
+        shards = plan_sync_shards(d_hay, world, classes, has_other)
+        assert shards is not None and len(shards) == world
+        assert any(s.lo % 8 for s in shards[1:])          # pieces start at arbitrary (unaligned) chars
+        pos_parts, val_parts = [], []
+        for sh in shards:
+            k = match_sync_shard(m, d_hay.data_ptr(), sh, d_pos.data_ptr(), d_val.data_ptr() if is_map else None, cap)
+            torch.cuda.synchronize()
+            pos_parts.append(d_pos[:k].cpu().numpy().astype(np.int64) + sh.lo)
+            val_parts.append(d_val[:k].cpu().numpy().astype(np.int64))
+        got = np.concatenate(pos_parts, axis=0)
+        assert got.shape == want_pos.shape and np.array_equal(got, want_pos), (family, world)
+        if is_map:
+            assert np.array_equal(np.concatenate(val_parts), want["value"].astype(np.int64)), (family, world)
+    assert len(want) > 1000
+
+
 # ---------------------------------------------------------------- Longest / Shortest on the start-mask path (kernel_sel2.cuh)
 
 @pytest.mark.parametrize("family", ["longest", "shortest"])

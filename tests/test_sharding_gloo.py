@@ -169,3 +169,60 @@ def test_word_shard_plan_and_semantics_many_worlds():
             got += [(int(r["start"]) + s.read_from, int(r["end"]) + s.read_from) for r in m.match(piece)
                     if s.emit_from <= int(r["start"]) + s.read_from < s.emit_to]
         assert got == want, world
+
+
+# ---------------------------------------------------------------- Longest / Shortest: synchronisation-point shards
+
+def _classes_for(kws, cs):
+    """classes[c] == 0 iff code unit c (after the matcher's case folding) occurs in no keyword - what
+    matcher.char_classes() returns on the GPU side, restated with the spec's Java folding."""
+    import numpy as np
+    import ac_spec as spec
+    used = set()
+    for k in kws:
+        if k:
+            used.update(spec.fold(k, cs))
+    out = np.zeros(65536, np.uint16)
+    for c in range(65536):
+        ch = chr(c)
+        f = ch if cs or 0xD800 <= c < 0xE000 else spec.fold(ch, False)
+        out[c] = 1 if f in used else 0
+    return out
+
+
+@pytest.mark.parametrize("family", ["longest", "shortest", "ahocorasick"])
+@pytest.mark.parametrize("cs", [True, False])
+def test_sync_point_shards_reproduce_the_single_stream(family, cs):
+    """plan_sync_shards cuts a haystack right after chars that occur in no keyword; the reference automata are in their
+    root state there, so the pieces are independent haystacks.  Checked against the literal oracle: the concatenation of
+    the pieces' streams (shifted by lo) is the stream of the whole haystack - Set positions and Map values, dense and
+    sparse separators, any world size; and the plan declines (None) when a window holds no such char."""
+    import numpy as np
+    from oracle import oracle as ora
+    rng = random.Random(31337 + cs)
+    for it in range(40):
+        alpha = rng.choice(["ab", "abc", "abAB", "abcdeXY"])
+        kws = sorted({"".join(rng.choice(alpha) for _ in range(rng.randint(1, 7))) for _ in range(rng.randint(1, 30))})
+        seps = rng.choice([" ", " ,.", "z"])                      # never in a keyword (also not after folding)
+        p_sep = rng.choice([0.02, 0.15, 0.5])
+        hay = "".join(rng.choice(seps) if rng.random() < p_sep else rng.choice(alpha) for _ in range(rng.randint(50, 3000)))
+        arr = np.frombuffer(hay.encode("utf-16-le"), dtype=np.uint16)
+        classes = _classes_for(kws, cs)
+        m = ora.Matcher(family, kws, n_values=len(kws), case_sensitive=cs)
+        want = [(int(r["start"]), int(r["end"]), int(r["value"])) for r in m.match(hay)]
+        for world in (1, 2, 3, 8, 50):
+            shards = sharding.plan_sync_shards(arr, world, classes, True, window=4096)
+            if shards is None:
+                continue
+            assert shards[0].lo == 0 and shards[-1].hi == len(hay) and all(a.hi == b.lo for a, b in zip(shards, shards[1:]))
+            for s in shards[1:]:
+                assert s.lo == len(hay) or classes[arr[s.lo - 1]] == 0
+            got = []
+            for s in shards:
+                got += [(int(r["start"]) + s.lo, int(r["end"]) + s.lo, int(r["value"])) for r in m.match(hay[s.lo:s.hi])]
+            assert got == want, (family, cs, kws, hay, world)
+    # no synchronisation point in the window / every char is a keyword char -> the plan declines
+    arr = np.frombuffer(("ab" * 500).encode("utf-16-le"), dtype=np.uint16)
+    assert sharding.plan_sync_shards(arr, 2, _classes_for(["a", "b"], True), True) is None
+    assert sharding.plan_sync_shards(arr, 2, np.ones(65536, np.uint16), False) is None
+    assert [(s.lo, s.hi) for s in sharding.plan_sync_shards(arr, 1, np.ones(65536, np.uint16), False)] == [(0, 1000)]
