@@ -87,7 +87,7 @@ class SyncShard:
     hi: int
 
 
-def plan_sync_shards(haystack, world: int, classes, has_other: bool, window: int = 1 << 20):
+def plan_sync_shards(haystack, world: int, classes, has_other: bool, window: int = 1 << 20, word_chars=None):
     """Longest / Shortest (and AhoCorasick): cut ONE haystack into `world` independent pieces at SYNCHRONISATION points.
 
     A char that occurs in no keyword (class 0 of ``matcher.char_classes()``) sends every reference automaton back to its
@@ -97,7 +97,10 @@ def plan_sync_shards(haystack, world: int, classes, has_other: bool, window: int
     after the even split, searched over at most `window` chars; returns None when one boundary has no synchronisation
     point in its window (e.g. every char of the text occurs in some keyword) - the caller then keeps the haystack whole.
     `haystack` is a uint16 numpy array or an int16 / uint16 torch tensor (device tensors copy only the windows).
-    Not valid for the WholeWord families (use plan_word_shards / keep WholeWordLongest whole)."""
+
+    WholeWordLongest: pass the matcher's word-character table (``getWordChars()``) as `word_chars`; a synchronisation
+    point then also needs the char to be a NON-word char (after a keyword-free letter the rest of its word is no walk
+    start in the reference, but it would be one at the start of a piece).  WholeWord itself shards by plan_word_shards."""
     import numpy as np
     if world < 1:
         raise ValueError("world must be >= 1")
@@ -107,6 +110,8 @@ def plan_sync_shards(haystack, world: int, classes, has_other: bool, window: int
     if not has_other:
         return None
     is_other = np.asarray(classes) == 0
+    if word_chars is not None:
+        is_other &= ~np.asarray(word_chars).astype(bool)
     bounds = [0]
     for r in range(1, world):
         b = max(n * r // world, bounds[-1], 1)

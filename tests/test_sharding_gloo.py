@@ -226,3 +226,40 @@ def test_sync_point_shards_reproduce_the_single_stream(family, cs):
     assert sharding.plan_sync_shards(arr, 2, _classes_for(["a", "b"], True), True) is None
     assert sharding.plan_sync_shards(arr, 2, np.ones(65536, np.uint16), False) is None
     assert [(s.lo, s.hi) for s in sharding.plan_sync_shards(arr, 1, np.ones(65536, np.uint16), False)] == [(0, 1000)]
+
+
+@pytest.mark.parametrize("cs", [True, False])
+def test_sync_point_shards_wholewordlongest(cs):
+    """WholeWordLongest (keywords may hold non-word chars, "as if"): synchronisation points are chars that are in no
+    keyword AND are non-word chars; pieces cut there reproduce the oracle's single stream.  A keyword-free LETTER is not
+    a synchronisation point (the rest of its word would become a walk start) - the plan must skip it."""
+    import numpy as np
+    import ac_spec as spec
+    from oracle import oracle as ora
+    rng = random.Random(4711 + cs)
+    word_chars = ora.word_chars(0).astype(bool)
+    n_cut = 0
+    for it in range(60):
+        alpha = rng.choice(["ab", "abc", "abAB"])
+        words = sorted({"".join(rng.choice(alpha) for _ in range(rng.randint(1, 4))) for _ in range(rng.randint(1, 12))})
+        kws = words + [a + " " + b for a, b in zip(words[::2], words[1::2])]         # phrases: ' ' IS a keyword char
+        fill = alpha * 3 + "  " + ",;" + "z"                                            # ',' ';' sync points, 'z' a keyword-free letter
+        hay = "".join(rng.choice(fill) for _ in range(rng.randint(50, 2500)))
+        arr = np.frombuffer(hay.encode("utf-16-le"), dtype=np.uint16)
+        classes = _classes_for(kws, cs)
+        assert classes[ord("z")] == 0 and classes[ord(",")] == 0
+        ok_cut = ",;" + (" " if classes[ord(" ")] == 0 else "")   # ' ' only when no phrase made it a keyword char
+        m = ora.Matcher("wholewordlongest", kws, n_values=len(kws), case_sensitive=cs)
+        want = [(int(r["start"]), int(r["end"]), int(r["value"])) for r in m.match(hay)]
+        for world in (2, 3, 8, 40):
+            shards = sharding.plan_sync_shards(arr, world, classes, True, window=4096, word_chars=word_chars)
+            if shards is None:
+                continue
+            for s in shards[1:]:
+                assert s.lo == len(hay) or hay[s.lo - 1] in ok_cut
+            got = []
+            for s in shards:
+                got += [(int(r["start"]) + s.lo, int(r["end"]) + s.lo, int(r["value"])) for r in m.match(hay[s.lo:s.hi])]
+            assert got == want, (cs, kws, hay, world)
+            n_cut += 1
+    assert n_cut > 100
