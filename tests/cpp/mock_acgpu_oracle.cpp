@@ -60,6 +60,10 @@ int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t 
     *handle = (uint64_t)(uintptr_t) new Mock{m, n_values >= 0};
     return ACGPU_OK;
 }
+int acgpu_build_fingerprint(int, const uint16_t *, const int64_t *, const uint8_t *, int64_t, int64_t, int, const uint8_t *, uint64_t *,
+                            double *) {
+    return fail(ACGPU_EUNSUPPORTED, "mock: no builder");
+}
 int acgpu_destroy(uint64_t h) {
     Mock *mk = (Mock *)(uintptr_t)h;
     if (!mk) return fail(ACGPU_EINVAL, "bad handle");
