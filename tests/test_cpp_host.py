@@ -87,6 +87,16 @@ def _random_case(seed, fam):
     return list(kws), hay
 
 
+def test_cpp_usage_example_compiles_and_runs_against_mocked_abi(mock_exe):
+    """examples/cpp_usage.cpp = the snippet of INTEGRATION.md section 5; documentation that does not compile is a bug."""
+    build_dir = os.path.dirname(mock_exe)
+    exe = os.path.join(build_dir, "cpp_usage_mock")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "cpp_usage.cpp"), "-L" + build_dir, "-lacgpu_mock_oracle",
+                           "-Wl,-rpath," + build_dir, "-o", exe])
+    assert _run([exe]).split("\n")[:7] == ["1 4 2", "2 4 1", "2 6 3", "v 2", "v 1", "v 3", "ww 1"]
+
+
 def test_cpp_dump_plumbing_against_mocked_abi(mock_exe, tmp_path):
     for fam in range(5):
         _check_streams(mock_exe, tmp_path, fam, fam % 2, seeds=(0,))
