@@ -380,6 +380,8 @@ Packed zip(const KRange &keywords, const VRange &values, std::vector<T> &kept) {
 class StringSet {
    public:
     virtual ~StringSet() = default;
+    StringSet(StringSet &&) = default;  // matchers own their device automaton: movable, not copyable
+    StringSet &operator=(StringSet &&) = default;
 
     /** match(String haystack, SetMatchListener listener) — StringSet.java:4. */
     void match(const String &haystack, SetMatchListener &listener) const {
@@ -405,6 +407,8 @@ template <class T>
 class StringMap {
    public:
     virtual ~StringMap() = default;
+    StringMap(StringMap &&) = default;  // movable, not copyable
+    StringMap &operator=(StringMap &&) = default;
 
     /** match(String haystack, MapMatchListener<T> listener) — StringMap.java:8. */
     void match(const String &haystack, MapMatchListener<T> &listener) const {

@@ -444,6 +444,25 @@ static void deviceTests() {
         EXPECT(got == Spans({{0, 3}}), show(got));
     }
 
+    // Matchers own their device automaton: movable (containers, factories), not copyable
+    g_test = "moveSemantics";
+    {
+        static_assert(std::is_move_constructible<AhoCorasickSet>::value && !std::is_copy_constructible<AhoCorasickSet>::value, "Set");
+        static_assert(std::is_move_constructible<WholeWordMatchMap<int>>::value && !std::is_copy_constructible<WholeWordMatchMap<int>>::value, "Map");
+        std::vector<LongestMatchSet> sets;
+        sets.push_back(LongestMatchSet(Keywords{u"ab", u"abc"}, true));
+        sets.push_back(LongestMatchSet(Keywords{u"x"}, true));
+        LongestMatchSet moved = std::move(sets[0]);
+        Spans got;
+        moved.match(u"abcab", [&](const String &, int a, int b) { return got.emplace_back(a, b), true; });
+        EXPECT(got == Spans({{0, 3}, {3, 5}}), show(got));
+        WholeWordMatchMap<int> a(Keywords{u"key"}, std::vector<int>{7}, true), b(Keywords{u"other"}, std::vector<int>{9}, true);
+        b = std::move(a);
+        int v = 0;
+        b.match(u"a key", [&](const String &, int, int, const int &x) { return v = x, true; });
+        EXPECT(v == 7 && b.getWordChars()[u'k'], "moved-into Map delivers " << v);
+    }
+
     // Readable in many fills: a 300 000-char stream crosses charBufferSize fills and one device block boundary
     g_test = "readableLong";
     {
