@@ -194,3 +194,14 @@ def test_builder_tables_match_committed_fingerprints(monkeypatch):
     assert sorted(got) == sorted(want)
     diff = [k for k in want if got[k] != want[k]]
     assert not diff, "flattened tables changed for %d dictionaries, e.g. %s" % (len(diff), diff[:3])
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md maps every C entry point to the reference interface it replaces; a symbol added to include/acgpu.h
+    must be documented there (and in the Java native class when the facade needs it)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [s for s in _header_symbols() if s not in doc and s not in ("acgpu_last_error", "acgpu_version", "acgpu_free_result",
+                                                                          "acgpu_destroy")]
+    assert not missing, missing
+    for s in ("acgpu_last_error", "acgpu_free_result"):
+        assert s in doc
