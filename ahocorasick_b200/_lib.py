@@ -20,12 +20,21 @@ EXPORTS = [
     "acgpu_create_from_keywords", "acgpu_build_fingerprint", "acgpu_destroy", "acgpu_word_chars", "acgpu_info", "acgpu_char_classes",
     "acgpu_match_utf16", "acgpu_free_result", "acgpu_match_device", "acgpu_match_device_async",
     "acgpu_launches_per_match", "acgpu_stream_begin", "acgpu_stream_feed", "acgpu_stream_end",
-    "acgpu_last_error", "acgpu_version",
+    "acgpu_last_error", "acgpu_version", "acgpu_match_utf16_compact", "acgpu_free_matches", "acgpu_masks_to_records",
 ]
 
 
 class Result(C.Structure):
     _fields_ = [("n", C.c_int64), ("pos", C.POINTER(C.c_int32)), ("val", C.POINTER(C.c_uint32))]
+
+
+class Matches(C.Structure):
+    """acgpu_matches: records, or per-char hit masks for dense AhoCorasickSet streams (include/acgpu.h)."""
+    _fields_ = [("n", C.c_int64), ("kind", C.c_int32), ("reserved", C.c_int32), ("pos", C.POINTER(C.c_int32)),
+                ("val", C.POINTER(C.c_uint32)), ("masks", C.POINTER(C.c_uint16)), ("n_chars", C.c_int64)]
+
+
+MATCHES_RECORDS, MATCHES_MASKS = 0, 1
 
 
 class AcgpuError(RuntimeError):
@@ -77,6 +86,12 @@ def lib():
     L.acgpu_stream_feed.argtypes = [u64, vp, i32, C.POINTER(Result)]
     L.acgpu_stream_end.restype = C.c_int
     L.acgpu_stream_end.argtypes = [u64, C.POINTER(Result)]
+    L.acgpu_match_utf16_compact.restype = C.c_int
+    L.acgpu_match_utf16_compact.argtypes = [u64, vp, i32, C.POINTER(Matches)]
+    L.acgpu_free_matches.restype = None
+    L.acgpu_free_matches.argtypes = [C.POINTER(Matches)]
+    L.acgpu_masks_to_records.restype = i64
+    L.acgpu_masks_to_records.argtypes = [vp, i64, i64, vp, i64]
     L.acgpu_last_error.restype = C.c_char_p
     L.acgpu_version.restype = C.c_char_p
     _lib = L

@@ -412,49 +412,69 @@ int enqueue_sel2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint
 }
 
 // AhoCorasick family, narrow alphabets: hit masks -> row-count scan -> records (kernel_mask.cuh)
-int enqueue_mask(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from, int64_t emit_to, int64_t origin, int2 *d_pos,
-                 uint32_t *d_val, int64_t cap, unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
-    const int64_t n_rows = (emit_to - origin + kMaskRow - 1) / kMaskRow;
-    const int64_t n_blocks = (n_rows + kScanRows - 1) / kScanRows;
+struct MaskWs {  // one scratch block of a mask / scan (/ emit) run over n_rows rows
+    int64_t n_rows = 0, n_blocks = 0;
+    size_t o_ctr = 0, o_cnt = 0, o_blk = 0, o_mask = 0, bytes = 0;
+};
+
+MaskWs mask_ws_layout(int64_t emit_to, int64_t origin) {
+    MaskWs L;
+    L.n_rows = (emit_to - origin + kMaskRow - 1) / kMaskRow;
+    L.n_blocks = (L.n_rows + kScanRows - 1) / kScanRows;
     Scratch S;
-    const size_t o_ctr = S.reserve(256);
-    const size_t o_cnt = S.reserve(static_cast<size_t>(n_rows) * 4);
-    const size_t o_blk = S.reserve(static_cast<size_t>(n_blocks) * 8);
-    const size_t o_mask = S.reserve(static_cast<size_t>(n_rows) * kMaskRow * 2);
-    void *ws = nullptr;
-    CU_TRY(cudaMallocAsync(&ws, S.off, st));
-    char *w = static_cast<char *>(ws);
-    CU_TRY(cudaMemsetAsync(w + o_ctr, 0, 256, st));
+    L.o_ctr = S.reserve(256);
+    L.o_cnt = S.reserve(static_cast<size_t>(L.n_rows) * 4);
+    L.o_blk = S.reserve(static_cast<size_t>(L.n_blocks) * 8);
+    L.o_mask = S.reserve(static_cast<size_t>(L.n_rows) * kMaskRow * 2);
+    L.bytes = S.off;
+    return L;
+}
+
+// k_tier_mask + k_row_scan into the scratch block w: hit masks of positions [origin, origin + n_rows * 256) at
+// w + o_mask (16 bits each, zero outside [emit_from, emit_to)), the match count in *d_total
+int enqueue_mask_scan(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from, int64_t emit_to, int64_t origin, char *w,
+                      const MaskWs &L, unsigned long long *d_total, cudaStream_t st) {
+    CU_TRY(cudaMemsetAsync(w + L.o_ctr, 0, 256, st));
     MaskArgs P{};
     P.hay = d_hay;
     P.n = n;
     P.emit_from = emit_from;
     P.emit_to = emit_to;
     P.origin = origin;
-    P.masks = reinterpret_cast<uint32_t *>(w + o_mask);
-    P.row_count = reinterpret_cast<uint32_t *>(w + o_cnt);
-    P.ticket = reinterpret_cast<unsigned int *>(w + o_ctr);
-    P.n_rows = n_rows;
-    const int64_t n_chunks = (n_rows + kMaskChunkRows - 1) / kMaskChunkRows;
+    P.masks = reinterpret_cast<uint32_t *>(w + L.o_mask);
+    P.row_count = reinterpret_cast<uint32_t *>(w + L.o_cnt);
+    P.ticket = reinterpret_cast<unsigned int *>(w + L.o_ctr);
+    P.n_rows = L.n_rows;
+    const int64_t n_chunks = (L.n_rows + kMaskChunkRows - 1) / kMaskChunkRows;
     const int grid = static_cast<int>(std::min<int64_t>((n_chunks + kMaskWarps - 1) / kMaskWarps, m->sm_count));
     int rc = launch_mask(m, P, grid, st);
     if (rc != ACGPU_OK) return rc;
     ScanArgs SA{};
     SA.row_count = P.row_count;
-    SA.block_excl = reinterpret_cast<unsigned long long *>(w + o_blk);
-    SA.done = reinterpret_cast<unsigned int *>(w + o_ctr + 64);
+    SA.block_excl = reinterpret_cast<unsigned long long *>(w + L.o_blk);
+    SA.done = reinterpret_cast<unsigned int *>(w + L.o_ctr + 64);
     SA.total_out = d_total;
-    SA.n_rows = n_rows;
-    k_row_scan<<<static_cast<unsigned>(n_blocks), 1024, 0, st>>>(SA);
+    SA.n_rows = L.n_rows;
+    k_row_scan<<<static_cast<unsigned>(L.n_blocks), 1024, 0, st>>>(SA);
     CU_TRY(cudaGetLastError());
-    if (cap > 0) {
+    return ACGPU_OK;
+}
+
+int enqueue_mask(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from, int64_t emit_to, int64_t origin, int2 *d_pos,
+                 uint32_t *d_val, int64_t cap, unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
+    const MaskWs L = mask_ws_layout(emit_to, origin);
+    void *ws = nullptr;
+    CU_TRY(cudaMallocAsync(&ws, L.bytes, st));
+    char *w = static_cast<char *>(ws);
+    int rc = enqueue_mask_scan(m, d_hay, n, emit_from, emit_to, origin, w, L, d_total, st);
+    if (rc == ACGPU_OK && cap > 0) {
         EmitArgs E{};
         E.hay = d_hay;
         E.n = n;
-        E.masks = P.masks;
-        E.row_excl = P.row_count;
-        E.block_excl = SA.block_excl;
-        E.n_rows = n_rows;
+        E.masks = reinterpret_cast<uint32_t *>(w + L.o_mask);
+        E.row_excl = reinterpret_cast<uint32_t *>(w + L.o_cnt);
+        E.block_excl = reinterpret_cast<unsigned long long *>(w + L.o_blk);
+        E.n_rows = L.n_rows;
         E.origin = origin;
         E.pos_base = opt.pos_base;
         E.pos_out = d_pos;
@@ -463,15 +483,16 @@ int enqueue_mask(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from
         // many small CTAs: the hardware scheduler evens out SMs that run at different speeds (measured: 128 per SM beats 8 by 12%)
         const char *gm = getenv("ACGPU_EMIT_GRID");
         const int per_sm = gm ? std::max(1, atoi(gm)) : 128;
-        const int egrid = static_cast<int>(std::min<int64_t>((n_rows + kEmitWarps - 1) / kEmitWarps, static_cast<int64_t>(m->sm_count) * per_sm));
+        const int egrid = static_cast<int>(std::min<int64_t>((L.n_rows + kEmitWarps - 1) / kEmitWarps, static_cast<int64_t>(m->sm_count) * per_sm));
         if (m->dev.is_map)
             k_tier_emit<true><<<egrid, kEmitWarps * 32, 0, st>>>(m->dev, m->tier, E);
         else
             k_tier_emit<false><<<egrid, kEmitWarps * 32, 0, st>>>(m->dev, m->tier, E);
-        CU_TRY(cudaGetLastError());
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(ACGPU_ECUDA, std::string("k_tier_emit: ") + cudaGetErrorString(e));
     }
-    CU_TRY(cudaFreeAsync(ws, st));
-    return ACGPU_OK;
+    cudaFreeAsync(ws, st);  // on every path (no scratch leak when a launch fails)
+    return rc;
 }
 
 // Enqueue every kernel of one match on `st`.  d_total receives the total number of matches.
@@ -784,6 +805,7 @@ struct HostCall {
     uint16_t *d_hay = nullptr;
     int2 *d_pos[2] = {nullptr, nullptr};
     uint32_t *d_val[2] = {nullptr, nullptr};
+    char *d_ws[2] = {nullptr, nullptr};      // mask workspaces of the compact path
     unsigned long long *d_total = nullptr;   // [2]
     unsigned long long *h_total = nullptr;   // [2] pinned
     PinnedBlock blk;                          // result block: pos[cap] then val[cap]
@@ -927,6 +949,88 @@ struct HostCall {
         return ACGPU_OK;
     }
 
+    // Dense AhoCorasickSet streams in the compact wire format (acgpu_match_utf16_compact): the 16-bit hit masks of
+    // k_tier_mask ARE the ordered stream (position-major, ascending bit = longest first), 2 bytes per char whatever the
+    // density, so the call moves 2 B/char up and 2 B/char down and k_tier_emit never runs.  Chunk 0 decides: when it
+    // holds fewer than kMaskModeDensity records per char the caller falls back to records (*use_records = true).
+    static constexpr double kMaskModeDensity = 0.25;  // 8-byte records cost as much as 2-byte masks at 0.25 records per char
+    int64_t mask_total = 0;
+    uint16_t *h_masks() const { return static_cast<uint16_t *>(blk.p); }
+
+    int run_masks(const uint16_t *hay, int64_t n, bool *use_records) {
+        *use_records = false;
+        const int64_t n_chunks = (n + kChunk - 1) / kChunk;
+        const int64_t mis_max = 8;
+        const MaskWs LW = mask_ws_layout(std::min<int64_t>(n, kChunk) + mis_max, 0);  // workspace of the largest chunk
+        char **ws = d_ws;  // freed by finish(), after every stream has drained
+        CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_hay), static_cast<size_t>(n) * 2, s_k));
+        for (int i = 0; i < (n_chunks > 1 ? 2 : 1); i++) CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&ws[i]), LW.bytes, s_k));
+        CU_TRY(cudaEventRecord(ev_dn[0], s_k));
+        CU_TRY(cudaStreamWaitEvent(s_up, ev_dn[0], 0));
+        const int64_t mis = static_cast<int64_t>((reinterpret_cast<uintptr_t>(d_hay) >> 1) & 7);
+        unsigned long long *h_tot = nullptr;  // per-chunk totals, pinned, behind the masks in the result block
+        auto origin_of = [&](int64_t lo) { return ((lo + mis) & ~int64_t(7)) - mis; };
+        auto issue = [&](int64_t k) -> int {
+            const int bf = static_cast<int>(k & 1);
+            const int64_t lo = k * kChunk, hi = std::min<int64_t>(n, lo + kChunk);
+            CU_TRY(cudaMemcpyAsync(d_hay + lo, hay + lo, static_cast<size_t>(hi - lo) * 2, cudaMemcpyHostToDevice, s_up));
+            CU_TRY(cudaEventRecord(ev_up[bf], s_up));
+            CU_TRY(cudaStreamWaitEvent(s_k, ev_up[bf], 0));
+            if (k >= 2) CU_TRY(cudaStreamWaitEvent(s_k, ev_dn[bf], 0));  // the masks of chunk k-2 have left the workspace
+            const int64_t origin = origin_of(lo);
+            const MaskWs L = mask_ws_layout(hi, origin);
+            int rc = enqueue_mask_scan(m, d_hay, hi, lo, hi, origin, ws[bf], L, d_total + bf, s_k);
+            if (rc != ACGPU_OK) return rc;
+            if (k == 0)
+                CU_TRY(cudaMemcpyAsync(h_total, d_total, 8, cudaMemcpyDeviceToHost, s_k));
+            else
+                CU_TRY(cudaMemcpyAsync(h_tot + k, d_total + bf, 8, cudaMemcpyDeviceToHost, s_k));
+            CU_TRY(cudaEventRecord(ev_k[bf], s_k));
+            return ACGPU_OK;
+        };
+        auto download_masks = [&](int64_t k) -> int {
+            const int bf = static_cast<int>(k & 1);
+            const int64_t lo = k * kChunk, hi = std::min<int64_t>(n, lo + kChunk);
+            const MaskWs L = mask_ws_layout(hi, origin_of(lo));
+            CU_TRY(cudaStreamWaitEvent(s_dn, ev_k[bf], 0));
+            CU_TRY(cudaMemcpyAsync(h_masks() + lo, ws[bf] + L.o_mask + static_cast<size_t>(lo - origin_of(lo)) * 2,
+                                   static_cast<size_t>(hi - lo) * 2, cudaMemcpyDeviceToHost, s_dn));
+            CU_TRY(cudaEventRecord(ev_dn[bf], s_dn));
+            return ACGPU_OK;
+        };
+        int rc = issue(0);
+        if (rc == ACGPU_OK) {
+            const cudaError_t e = cudaEventSynchronize(ev_k[0]);
+            if (e != cudaSuccess) rc = fail(ACGPU_ECUDA, std::string("match: ") + cudaGetErrorString(e));
+        }
+        if (rc == ACGPU_OK && static_cast<double>(h_total[0]) < kMaskModeDensity * static_cast<double>(std::min<int64_t>(n, kChunk))) {
+            *use_records = true;
+            return ACGPU_OK;
+        }
+        if (rc == ACGPU_OK) {
+            const size_t mask_bytes = align_up(static_cast<size_t>(n) * 2, 64);
+            if (!pin_take(mask_bytes + static_cast<size_t>(n_chunks) * 8, &blk)) rc = fail(ACGPU_ENOMEM, "out of pinned host memory for the hit masks");
+            if (rc == ACGPU_OK) {
+                h_tot = reinterpret_cast<unsigned long long *>(static_cast<char *>(blk.p) + mask_bytes);
+                h_tot[0] = h_total[0];
+            }
+        }
+        for (int64_t k = 0; rc == ACGPU_OK && k < n_chunks; k++) {
+            if (k + 1 < n_chunks) rc = issue(k + 1);
+            if (rc == ACGPU_OK) rc = download_masks(k);
+        }
+        if (rc == ACGPU_OK) {
+            cudaError_t e = cudaStreamSynchronize(s_k);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s_dn);
+            if (e != cudaSuccess) rc = fail(ACGPU_ECUDA, std::string("match: ") + cudaGetErrorString(e));
+        }
+        if (rc == ACGPU_OK) {
+            mask_total = 0;
+            for (int64_t k = 0; k < n_chunks; k++) mask_total += static_cast<int64_t>(h_tot[k]);
+        }
+        return rc;
+    }
+
     int run_whole(const uint16_t *hay, int64_t n) {
         CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_hay), static_cast<size_t>(n) * 2, s_k));
         CU_TRY(cudaMemcpyAsync(d_hay, hay, static_cast<size_t>(n) * 2, cudaMemcpyHostToDevice, s_k));
@@ -957,6 +1061,24 @@ struct HostCall {
     }
 
     // release everything; on success hand the pinned block to the caller
+    int finish_masks(int rc, acgpu_matches *out, int64_t n_chars) {
+        acgpu_result none;
+        fill_empty(&none);
+        PinnedBlock keep = blk;
+        blk = PinnedBlock();
+        count = 0;
+        rc = finish(rc, &none);
+        if (rc == ACGPU_OK) {
+            out->kind = ACGPU_MATCHES_MASKS;
+            out->n = mask_total;
+            out->masks = static_cast<const uint16_t *>(keep.p);
+            out->n_chars = n_chars;
+        } else if (keep.p) {
+            pin_release(keep.p);
+        }
+        return rc;
+    }
+
     int finish(int rc, acgpu_result *out) {
         cudaError_t pending = cudaSuccess;
         for (cudaStream_t st : {s_up, s_dn, s_k}) {
@@ -971,6 +1093,7 @@ struct HostCall {
             for (int i = 0; i < 2; i++) {
                 if (d_pos[i]) cudaFreeAsync(d_pos[i], s_k);
                 if (d_val[i]) cudaFreeAsync(d_val[i], s_k);
+                if (d_ws[i]) cudaFreeAsync(d_ws[i], s_k);
             }
         }
         if (cx) {
@@ -999,7 +1122,7 @@ struct HostCall {
 extern "C" {
 
 const char *acgpu_last_error(void) { return g_err.c_str(); }
-const char *acgpu_version(void) { return "acgpu 0.1 (sm_100a, anchored-trie generation 1)"; }
+const char *acgpu_version(void) { return "acgpu 0.2 (sm_100a; tiered hit-mask kernels, generation 3)"; }
 
 int acgpu_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, int32_t n, uint8_t *out65536) {
     if (!out65536 || mode < 0 || mode > 2 || n < 0) return fail(ACGPU_EINVAL, "bad arguments");
@@ -1197,6 +1320,69 @@ int acgpu_match_utf16(uint64_t handle, const uint16_t *haystack, int32_t n, acgp
     return hc.finish(rc, out);
 }
 
+int acgpu_match_utf16_compact(uint64_t handle, const uint16_t *haystack, int32_t n, acgpu_matches *out) {
+    Matcher *m = as_matcher(handle);
+    if (!m) return fail(ACGPU_EINVAL, "bad handle");
+    if (!out || n < 0 || (n > 0 && !haystack)) return fail(ACGPU_EINVAL, "bad arguments");
+    std::memset(out, 0, sizeof(*out));
+    out->kind = ACGPU_MATCHES_RECORDS;
+    int rc = ensure_device(m);
+    if (rc != ACGPU_OK) return rc;
+    if (n == 0) return ACGPU_OK;
+    const char *off = getenv("ACGPU_NO_MASK_RESULTS");
+    if (m->host.family == ACGPU_AHOCORASICK && m->use_tier && !m->host.is_map && !(off && off[0] == '1')) {
+        HostCall hc(m);
+        bool use_records = false;
+        rc = hc.init();
+        if (rc == ACGPU_OK) rc = hc.run_masks(haystack, n, &use_records);
+        if (rc != ACGPU_OK || !use_records) return hc.finish_masks(rc, out, n);
+        acgpu_result none;
+        fill_empty(&none);
+        hc.finish(ACGPU_OK, &none);
+    }
+    acgpu_result r;
+    rc = acgpu_match_utf16(handle, haystack, n, &r);
+    if (rc != ACGPU_OK) return rc;
+    out->n = r.n;
+    out->pos = r.pos;
+    out->val = r.val;
+    return ACGPU_OK;
+}
+
+void acgpu_free_matches(acgpu_matches *r) {
+    if (!r) return;
+    if (r->kind == ACGPU_MATCHES_MASKS) {
+        if (r->masks) pin_release(r->masks);
+    } else {
+        acgpu_result q;
+        q.n = r->n;
+        q.pos = r->pos;
+        q.val = r->val;
+        acgpu_free_result(&q);
+    }
+    std::memset(r, 0, sizeof(*r));
+}
+
+int64_t acgpu_masks_to_records(const uint16_t *masks, int64_t n_chars, int64_t first_char, int32_t *pos_out, int64_t cap) {
+    // host-side expansion of the compact stream, the loop every mirror's lazy replay runs: position ascending, then
+    // bit index ascending = longest keyword first (AhoCorasickSet.java:522-535)
+    if (!masks || n_chars < 0 || first_char < 0 || cap < 0 || (cap > 0 && !pos_out)) return -1;
+    int64_t k = 0;
+    for (int64_t q = first_char; q < n_chars; q++) {
+        uint32_t mk = masks[q];
+        while (mk) {
+            const int t = __builtin_ctz(mk);
+            mk &= mk - 1u;
+            if (k < cap) {
+                pos_out[2 * k] = static_cast<int32_t>(q + 1 - (16 - t));
+                pos_out[2 * k + 1] = static_cast<int32_t>(q + 1);
+            }
+            k++;
+        }
+    }
+    return k;
+}
+
 void acgpu_free_result(acgpu_result *r) {
     if (!r) return;
     if (r->pos && !pin_release(r->pos)) {  // streaming results are plain heap blocks
@@ -1236,6 +1422,7 @@ struct StreamCtx {
     int64_t *d_carry = nullptr;
     unsigned long long *d_total = nullptr;
     double density = 0.0;  // records per finalised char seen so far (max over feeds): sizes the next feed's record buffer
+    bool dma_pending = false;  // a DMA straight from the caller's page-locked buffer is in flight (acgpu.h: host buffers are only read during the call)
 };
 
 StreamCtx *as_stream(uint64_t h) {
@@ -1281,6 +1468,7 @@ int stream_append(StreamCtx *s, const uint16_t *chars, int64_t n) {
     cudaPointerAttributes attr{};
     if (cudaPointerGetAttributes(&attr, chars) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
         CU_TRY(cudaMemcpyAsync(s->d_win[s->cur] + s->len, chars, static_cast<size_t>(n) * 2, cudaMemcpyHostToDevice, s->st));
+        s->dma_pending = true;
         s->len += n;
         return ACGPU_OK;
     }
@@ -1343,6 +1531,7 @@ int stream_process(StreamCtx *s, bool final, acgpu_result *out) {
         if (rc != ACGPU_OK) return rc;
         CU_TRY(cudaMemcpyAsync(&total, s->d_total, 8, cudaMemcpyDeviceToHost, s->st));
         CU_TRY(cudaStreamSynchronize(s->st));
+        s->dma_pending = false;
         if (static_cast<int64_t>(total) <= cap) break;
         cudaFreeAsync(d_pos, s->st);
         if (d_val) cudaFreeAsync(d_val, s->st);
@@ -1437,8 +1626,15 @@ int acgpu_stream_feed(uint64_t stream_handle, const uint16_t *chars, int32_t n, 
     CU_TRY(cudaSetDevice(s->m->device));
     if (n == 0) return ACGPU_OK;
     int rc = stream_append(s, chars, n);
-    if (rc != ACGPU_OK) return rc;
-    return stream_process(s, false, out);
+    if (rc == ACGPU_OK) rc = stream_process(s, false, out);
+    if (s->dma_pending) {
+        // nothing was finalised (a feed shorter than the look-ahead) or an error cut the call short: the upload still
+        // reads the caller's buffer - wait for it, the caller may refill the buffer as soon as we return
+        s->dma_pending = false;
+        const cudaError_t e = cudaStreamSynchronize(s->st);
+        if (e != cudaSuccess && rc == ACGPU_OK) rc = fail(ACGPU_ECUDA, std::string("stream upload: ") + cudaGetErrorString(e));
+    }
+    return rc;
 }
 
 int acgpu_stream_end(uint64_t stream_handle, acgpu_result *out) {

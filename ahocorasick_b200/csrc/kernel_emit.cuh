@@ -108,6 +108,15 @@ __device__ __forceinline__ void sts_v2(uint32_t saddr, int32_t x, int32_t y) {
     asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(x), "r"(y) : "memory");
 }
 
+__device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t x) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"((unsigned short)x) : "memory");
+}
+// code = row position << 4 | 16 - length  ->  (start, end); e_row = end of a keyword whose last char is row position 0
+__device__ __forceinline__ int2 decode_rec(uint32_t code, int32_t e_row) {
+    const int32_t e = e_row + (int32_t)(code >> 4);
+    return make_int2(e - 16 + (int32_t)(code & 15u), e);
+}
+
 template <bool kIsMap>
 __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomaton A, const DevTier T, const EmitArgs E) {
     __shared__ __align__(16) int2 s_stage_all[kEmitWarps][kEmitStage + 2];
@@ -117,6 +126,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint2 *s_pack = s_pack_all[kIsMap ? warp : 0];
     int2 *s_stage = s_stage_all[warp];
+    const unsigned short *s_code = reinterpret_cast<const unsigned short *>(s_stage);  // the common path stages 16-bit codes here
     uint32_t *s_val = s_val_all[kIsMap ? warp : 0];
     uint8_t *s_cls4 = reinterpret_cast<uint8_t *>(s_cls);
     if (kIsMap) {
@@ -187,44 +197,51 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
             __syncwarp();
         }
         if (total <= (uint32_t)kEmitStage && base + total <= (unsigned long long)E.cap) {
-            // ---- common case: the whole row fits the staging window and the caller's buffer.  Records are staged at
-            //      the parity of their final address so that both sides of the flush are 16-byte aligned.
+            // ---- common case: the whole row fits the staging window and the caller's buffer.  Phase 1: every lane
+            //      expands its own bits into 16-bit CODES (code = index of the bit in the row's 4096-bit mask =
+            //      row position << 4 | 16 - length) - 2-byte shared stores instead of 8-byte records, a third of the
+            //      shared-memory wavefronts.  Phase 2 is balanced: a lane decodes TWO consecutive codes into the two
+            //      records of one 16-byte streaming store.  Codes are staged at the parity of their final address so that
+            //      both sides of the flush are aligned.
             const uint32_t par = ((uint32_t)base + out_par) & 1u;
-            uint32_t sa = stage_sa + (my_off + par) * 8u;
+            uint32_t sa = stage_sa + (my_off + par) * 2u;
 #pragma unroll
             for (int wi = 0; wi < 4; wi++) {
                 uint32_t w = words[wi];
-                const int32_t eb = e0 + 2 * wi;
+                const uint32_t cb = (uint32_t)lane * 128u + (uint32_t)wi * 32u;
                 while (w) {
                     const uint32_t t = (uint32_t)__clz((int)__brev(w));
                     w &= w - 1u;
-                    const int32_t e = eb + (int32_t)(t >> 4);
-                    sts_v2(sa, e - 16 + (int32_t)(t & 15u), e);
-                    sa += 8u;
+                    sts_u16(sa, cb + t);
+                    sa += 2u;
                 }
             }
             __syncwarp();
+            const int32_t e_row = (int32_t)(E.origin + row * kMaskRow) + 1 + E.pos_base;  // end of a keyword whose last char is row position 0
             if (kIsMap) {
-                // ---- values, one RECORD per lane (balanced, unlike the per-position bit loops): the record itself says
-                //      which position and length it is; the contexts come from the row's packed classes in shared memory
-                const int32_t e_row = (int32_t)(E.origin + row * kMaskRow) + E.pos_base;  // end of a keyword ending at row position -1
+                // ---- values, one RECORD per lane: the code says which position and length it is; the contexts come from
+                //      the row's packed classes in shared memory
                 for (uint32_t r = lane; r < total; r += 32) {
-                    const int2 rec = s_stage[r + par];
-                    const uint32_t pos = (uint32_t)(rec.y - e_row) - 1u;  // 0..255
+                    const uint32_t code = s_code[r + par];
+                    const uint32_t pos = code >> 4;  // 0..255
                     const uint32_t own = pos >> 3;
                     const uint2 a0 = s_pack[own + 2], a1 = s_pack[own + 1], a2 = s_pack[own];
                     const Pack8 Q0{a0.x, a0.y}, Q1{a1.x, a1.y}, Q2{a2.x, a2.y};
-                    __stcs(E.val_out + base + r, tier_value_rt(T, context_of(Q0, Q1, Q2, (int)(pos & 7u), b), cm, rec.y - rec.x));
+                    __stcs(E.val_out + base + r, tier_value_rt(T, context_of(Q0, Q1, Q2, (int)(pos & 7u), b), cm, 16 - (int)(code & 15u)));
                 }
             }
             // pairs [k_lo, k_hi) are whole; a lone head record (par == 1) and a lone tail record go out as 8-byte stores
             int2 *g = E.pos_out + (base - par);  // 16-byte aligned
             const uint32_t end = par + total, k_hi = end >> 1;
-            if (lane == 0 && par) __stcs(g + 1, s_stage[1]);
-            if (lane == 1 && (end & 1u)) __stcs(g + (end - 1u), s_stage[end - 1u]);
+            if (lane == 0 && par) __stcs(g + 1, decode_rec(s_code[1], e_row));
+            if (lane == 1 && (end & 1u)) __stcs(g + (end - 1u), decode_rec(s_code[end - 1u], e_row));
             int4 *gp = reinterpret_cast<int4 *>(g) + par + lane;
-            const int4 *sp = reinterpret_cast<const int4 *>(s_stage) + par + lane;
-            for (uint32_t k = par + lane; k < k_hi; k += 32, gp += 32, sp += 32) __stcs(gp, *sp);
+            const uint32_t *sp = reinterpret_cast<const uint32_t *>(s_code) + par + lane;
+            for (uint32_t k = par + lane; k < k_hi; k += 32, gp += 32, sp += 32) {
+                const uint32_t cc = *sp;
+                const int2 r0 = decode_rec(cc & 0xFFFFu, e_row), r1 = decode_rec(cc >> 16, e_row);
+                __stcs(gp, make_int4(r0.x, r0.y, r1.x, r1.y));
+            }
             __syncwarp();
             continue;
         }

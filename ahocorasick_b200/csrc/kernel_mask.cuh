@@ -24,6 +24,9 @@ namespace acgpu {
 #define ACGPU_MASK_WARPS 32
 #endif
 constexpr int kMaskWarps = ACGPU_MASK_WARPS;
+#ifndef ACGPU_ABL
+#define ACGPU_ABL 0       // ablation builds (tools/gpu_quick.sh VARIANTS): 1 no child-mask gather, 2 no deep probes, 8 gathers split TEX/LSU
+#endif
 #ifndef ACGPU_KID_TEX
 #define ACGPU_KID_TEX 1   // child masks are gathered through the texture pipe (the LSU data pipe is the kernel's bottleneck)
 #endif
@@ -306,7 +309,12 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
                 for (int k = K - 1; k >= 2; k--) rs[k] = rs[k - 1] * C + c4[j];
                 if (K >= 2) rs[1] = c4[j];
                 m[j] = mj;
-#if ACGPU_KID_TEX
+#if ACGPU_ABL & 1
+                ki[j] = 0u;
+#elif ACGPU_ABL & 8
+                ki[j] = (j & 1) ? ((deeper && kids) ? tex1Dfetch<unsigned int>(T.kid_tex, (int)(rk >> 2)) : 0u)
+                                : (deeper ? ldg_u32_if(reinterpret_cast<const unsigned char *>(T.kidmask) + rk, kids) : 0u);
+#elif ACGPU_KID_TEX
                 ki[j] = (deeper && kids) ? tex1Dfetch<unsigned int>(T.kid_tex, (int)(rk >> 2)) : 0u;
 #else
                 ki[j] = deeper ? ldg_u32_if(kid_bytes + rk, kids) : 0u;
@@ -335,6 +343,10 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
                 pm |= ((ki[j] >> ck) & 1u) << j;
             }
             pm &= vm;
+#if ACGPU_ABL & 2
+            m[0] |= (pm * 0x01010101u) >> 31;  // keep the gathers alive, never queue
+            pm = 0u;
+#endif
             const unsigned long long own8 = pack64(P0, b), prev16 = (pack64(P2, b) << (8 * b)) | pack64(P1, b);
             // ---- store the shallow masks and the row count; deep hits are OR-ed in later by this same warp
             const uint4 mw = make_uint4(m[0] | m[1] << 16, m[2] | m[3] << 16, m[4] | m[5] << 16, m[6] | m[7] << 16);

@@ -156,9 +156,16 @@ class _Records:
 
     __slots__ = ("start", "end", "value")
 
-    def __init__(self, res: _lib.Result, is_map: bool):
+    def __init__(self, res, is_map: bool):
         n = int(res.n)
-        if n:
+        if n and getattr(res, "kind", _lib.MATCHES_RECORDS) == _lib.MATCHES_MASKS:
+            # compact wire format (dense AhoCorasickSet streams): expand the per-char hit masks on the host
+            pos = np.empty((n, 2), np.int32)
+            k = _lib.lib().acgpu_masks_to_records(res.masks, res.n_chars, 0, pos.ctypes.data, n)
+            if k != n:
+                raise _lib.AcgpuError(_lib.ECUDA, "hit masks hold %d matches, the call reported %d" % (k, n))
+            self.start, self.end, self.value = pos[:, 0], pos[:, 1], None
+        elif n:
             pos = np.ctypeslib.as_array(res.pos, shape=(n, 2)).copy()
             self.start, self.end = pos[:, 0], pos[:, 1]
             self.value = np.ctypeslib.as_array(res.val, shape=(n,)).copy() if (is_map and res.val) else None
@@ -234,9 +241,20 @@ class _Matcher:
         check(_lib.lib().acgpu_char_classes(self._h, out.ctypes.data, C.byref(ho)))
         return out, bool(ho.value)
 
-    def match_records(self, haystack) -> _Records:
-        """The ordered (start, end[, valueIdx]) stream of one match(String) call, without replay."""
+    def match_records(self, haystack, compact: bool = True) -> _Records:
+        """The ordered (start, end[, valueIdx]) stream of one match(String) call, without replay.  compact (default): through
+        acgpu_match_utf16_compact - dense AhoCorasickSet streams cross PCIe as 2-byte hit masks and are expanded here;
+        compact=False: through acgpu_match_utf16 (records on the wire)."""
         hay = _utf16(haystack)
+        if hay.size > 0x7FFFFFFF:
+            raise ValueError("haystack longer than a Java String (2^31 - 1 chars)")
+        if compact:
+            res = _lib.Matches()
+            check(_lib.lib().acgpu_match_utf16_compact(self._h, hay.ctypes.data if hay.size else None, hay.size, C.byref(res)))
+            try:
+                return _Records(res, self._is_map)
+            finally:
+                _lib.lib().acgpu_free_matches(C.byref(res))
         res = _lib.Result()
         check(_lib.lib().acgpu_match_utf16(self._h, hay.ctypes.data if hay.size else None, hay.size, C.byref(res)))
         try:

@@ -77,7 +77,7 @@ def cpu_pass(matcher, slices, results):
         t.join()
 
 
-def cpu_measure(args, keywords, spec, passes: int, warm: int):
+def cpu_measure(args, keywords, spec, passes: int, warm: int, gpu_matcher=None):
     """All host threads, one independent match() per thread over disjoint slices of haystack 0 (the only
     parallelism the reference API allows).  ctypes releases the GIL inside the oracle call."""
     from oracle import oracle as ora
@@ -93,7 +93,20 @@ def cpu_measure(args, keywords, spec, passes: int, warm: int):
         cpu_pass(m, slices, res)
     dt = (time.perf_counter() - t0) / passes
     gbps = cores * n * 2 / dt / 1e9
-    return dict(value=gbps, unit=UNIT, cores=cores, kind="port",
+    parity = None
+    if gpu_matcher is not None:
+        # post-timing parity spot check (the oracle as the CHECKER): the CUDA path through the host-buffer C-ABI call on
+        # the very slices the CPU arm just scanned - match counts of every slice, the full ordered record stream of slice 0
+        got = [len(gpu_matcher.match_records(sl)) for sl in slices]
+        want0 = m.match(slices[0], cap=n)
+        rec0 = gpu_matcher.match_records(slices[0])
+        ok = got == [int(r) for r in res] and len(rec0) == len(want0) and \
+            bool(np.array_equal(rec0.start, want0["start"])) and bool(np.array_equal(rec0.end, want0["end"]))
+        parity = {"checked": True, "ok": ok, "slices": cores, "chars_per_slice": n, "records_compared": int(len(want0)),
+                  "counts_compared": int(sum(res))}
+        if not ok:
+            raise SystemExit("bench.py: parity spot check FAILED (CUDA path != oracle): counts %r vs %r" % (got, res))
+    return dict(value=gbps, unit=UNIT, cores=cores, kind="port", parity=parity,
                 sample="%d threads x %d chars of haystack 0 per pass (AhoCorasickSet, same dictionary); "
                        "literal C restatement of the reference (no JVM in this image), gcc -O2" % (cores, n),
                 matches_per_s=sum(res) / dt, ms_per_pass=dt * 1e3)
@@ -308,10 +321,11 @@ def run_ours(args):
                "note": "acgpu_match_utf16 on one %d-char haystack per rank from pinned host memory, "
                        "records copied back to host; mean of 2 after 1 warm-up" % ne}
 
-    cpu = None
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_measure(args, kws, W.HaystackSpec("lower", 2005, kws), passes=2, warm=1)
+        r = cpu_measure(args, kws, W.HaystackSpec("lower", 2005, kws), passes=2, warm=1, gpu_matcher=matcher)
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        parity = r["parity"]
 
     if rank == 0:
         line = {
@@ -321,6 +335,7 @@ def run_ours(args):
             "matches_per_s": matches_per_s, "matches_per_step": total_matches,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * len(hays) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
+            "parity_checked": bool(parity and parity["ok"]), "parity": parity,
             "dictionary": dict(info, build_seconds=build_s),
         }
         print(json.dumps(line), flush=True)

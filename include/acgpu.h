@@ -113,6 +113,33 @@ int acgpu_match_utf16(uint64_t handle, const uint16_t *haystack, int32_t n, acgp
 void acgpu_free_result(acgpu_result *r);
 
 /*
+ * The same call with a COMPACT wire format for dense match streams (at 0.87 matches per char the 8-byte
+ * records are 3.5 x the haystack and the call is bound by their D2H copy).  For an AhoCorasickSet whose first chunk holds
+ * more than 0.25 matches per char the result is the per-char HIT MASKS the scan kernel produces - 2 bytes per char
+ * whatever the density - and the record expansion moves into the caller's replay loop:
+ *     for q in [0, n_chars): for every set bit t of masks[q], ascending:   match(haystack, q + 1 - (16 - t), q + 1)
+ * which is exactly the reference's order (end ascending, longest first - AhoCorasickSet.java:522-535; a keyword of
+ * length d that ends with char q sets bit 16 - d).  Everything else (Maps, sparse streams, the other families, wide
+ * alphabets) comes back as records, kind ACGPU_MATCHES_RECORDS.  `n` is the number of matches in both kinds.
+ */
+#define ACGPU_MATCHES_RECORDS 0
+#define ACGPU_MATCHES_MASKS 1
+typedef struct {
+    int64_t n;             /* matches in the stream */
+    int32_t kind;          /* ACGPU_MATCHES_RECORDS: pos/val as in acgpu_result; ACGPU_MATCHES_MASKS: masks */
+    int32_t reserved;
+    const int32_t *pos;
+    const uint32_t *val;
+    const uint16_t *masks; /* n_chars hit masks */
+    int64_t n_chars;
+} acgpu_matches;
+int acgpu_match_utf16_compact(uint64_t handle, const uint16_t *haystack, int32_t n, acgpu_matches *out);
+void acgpu_free_matches(acgpu_matches *r);
+/* Host-only helper: expands masks[first_char, n_chars) into (start,end) pairs, at most `cap` of them; returns the number
+ * of matches from first_char on (which may exceed cap), -1 on bad arguments. */
+int64_t acgpu_masks_to_records(const uint16_t *masks, int64_t n_chars, int64_t first_char, int32_t *pos_out, int64_t cap);
+
+/*
  * Same scan with the haystack already resident in device memory (kernel-only measurements, multi-GPU
  * shards).  d_pos (capacity cap records, 8 B each) and d_val (4 B each; may be NULL for Sets) are device
  * buffers; *n_out receives the TOTAL number of matches, which may exceed cap (then only the first cap

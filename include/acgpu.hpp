@@ -226,6 +226,17 @@ struct Result {
     uint32_t value(int64_t i) const { return r.val[i]; }
 };
 
+/** RAII acgpu_matches: the match stream of a Set in either wire format (records, or per-char hit masks when dense). */
+struct Matches {
+    acgpu_matches r{};
+    Matches() = default;
+    Matches(const Matches &) = delete;
+    Matches &operator=(const Matches &) = delete;
+    ~Matches() { acgpu_free_matches(&r); }
+    int64_t size() const { return r.n; }
+    bool masks() const { return r.kind == ACGPU_MATCHES_MASKS; }
+};
+
 /** Owns the device automaton; shared by the Set and Map façades. */
 class Handle {
    public:
@@ -254,6 +265,50 @@ class Handle {
     void match(const String &hay, Result &out) const {
         if (hay.size() > 0x7fffffffu) throw Error(ACGPU_EINVAL, "haystack longer than a Java String");
         check(acgpu_match_utf16(h_, reinterpret_cast<const uint16_t *>(hay.data()), (int32_t)hay.size(), &out.r));
+    }
+
+    void match(const String &hay, Matches &out) const {
+        if (hay.size() > 0x7fffffffu) throw Error(ACGPU_EINVAL, "haystack longer than a Java String");
+        check(acgpu_match_utf16_compact(h_, reinterpret_cast<const uint16_t *>(hay.data()), (int32_t)hay.size(), &out.r));
+    }
+
+    /**
+     * Replay of a Set stream in either wire format; emit(start, end) returns the listener's answer.  Hit masks are
+     * expanded lazily, in the reference's order (end ascending, longest first - AhoCorasickSet.java:522-535): bit t of
+     * masks[q] = a keyword of length 16 - t ends with char q.  Only the AhoCorasick family produces masks, so the
+     * Shortest quirks never meet them.
+     */
+    template <class Emit>
+    void replay(const Matches &m, size_t n_chars, Emit emit) const {
+        if (!m.masks()) {
+            const int32_t *pos = m.r.pos;
+            const int64_t n = m.r.n;
+            if (family_ == ACGPU_SHORTEST) {
+                for (int64_t i = 0; i < n; i++) {
+                    if ((size_t)pos[2 * i + 1] == n_chars) {
+                        emit(pos[2 * i], pos[2 * i + 1]);
+                        return;
+                    }
+                    if (!emit(pos[2 * i], pos[2 * i + 1])) {
+                        emit(pos[2 * i], pos[2 * i + 1]);
+                        return;
+                    }
+                }
+                return;
+            }
+            for (int64_t i = 0; i < n; i++)
+                if (!emit(pos[2 * i], pos[2 * i + 1])) return;
+            return;
+        }
+        const uint16_t *mk = m.r.masks;
+        for (int64_t q = 0; q < m.r.n_chars; q++) {
+            uint32_t w = mk[q];
+            while (w) {
+                const int t = __builtin_ctz(w);
+                w &= w - 1u;
+                if (!emit((int)(q + 1 - (16 - t)), (int)(q + 1))) return;
+            }
+        }
     }
 
     /**
@@ -390,9 +445,9 @@ class StringSet {
     /** Same, with any callable bool(const String&, int start, int end). */
     template <class F, class = std::enable_if_t<std::is_invocable_r_v<bool, F, const String &, int, int>>>
     void match(const String &haystack, F &&listener) const {
-        detail::Result rec;
+        detail::Matches rec;
         h_->match(haystack, rec);
-        h_->replay(rec, haystack.size(), [&](int64_t i) { return (bool)listener(haystack, rec.start(i), rec.end(i)); });
+        h_->replay(rec, haystack.size(), [&](int s, int e) { return (bool)listener(haystack, s, e); });
     }
 
    protected:

@@ -34,6 +34,8 @@ final class AcGpuNative {
      * (start,end) pairs in listener order, val = int[n] value indices (null for Sets).
      */
     static native Object[] match(long handle, String haystack);
+    /** acgpu_match_utf16_compact: {int[] pos, int[] valueIdx, char[] masks} - masks != null for dense AhoCorasickSet streams. */
+    static native Object[] matchCompact(long handle, String haystack);
 
     /** acgpu_stream_begin / feed / end; feed and end return {pos, val} like match (only val is used). */
     static native long streamBegin(long handle);

@@ -16,7 +16,7 @@ import com.roklenarcic.util.strings.SetMatchListener;
  * (ahocorasick_b200/matchers.py is the tested twin of this class).
  */
 abstract class GpuMatcher<T> implements AutoCloseable {
-    private final long handle;
+    private long handle; // 0 after close()
     private final int family;
     private final Object[] values; // null for Sets; index = the valueIdx the kernels report
 
@@ -59,13 +59,42 @@ abstract class GpuMatcher<T> implements AutoCloseable {
                 caseSensitive, wordChars, 0);
     }
 
-    public void close() {
-        AcGpuNative.destroy(handle);
+    /** Releases the device tables; idempotent.  Matching after close() throws IllegalStateException. */
+    public synchronized void close() {
+        long h = handle;
+        handle = 0;
+        if (h != 0) {
+            AcGpuNative.destroy(h);
+        }
+    }
+
+    private long live() {
+        long h = handle;
+        if (h == 0) {
+            throw new IllegalStateException("matcher is closed");
+        }
+        return h;
     }
 
     /** StringSet.match(String, SetMatchListener) — StringSet.java:4 */
     protected void matchSet(String haystack, SetMatchListener listener) {
-        int[] pos = (int[]) AcGpuNative.match(handle, haystack)[0];
+        // acgpu_match_utf16_compact: {int[] pos, int[] valueIdx, char[] masks}; dense AhoCorasickSet streams arrive as
+        // per-char hit masks (2 B/char) and are expanded lazily here, in the reference's order (end ascending, longest
+        // first - AhoCorasickSet.java:522-535): bit t of masks[q] = a keyword of length 16 - t ends with char q
+        Object[] r = AcGpuNative.matchCompact(live(), haystack);
+        if (r[2] != null) {
+            char[] masks = (char[]) r[2];
+            for (int q = 0; q < masks.length; q++) {
+                for (int w = masks[q]; w != 0; w &= w - 1) {
+                    int t = Integer.numberOfTrailingZeros(w);
+                    if (!listener.match(haystack, q + 1 - (16 - t), q + 1)) {
+                        return;
+                    }
+                }
+            }
+            return;
+        }
+        int[] pos = (int[]) r[0];
         int n = pos.length / 2;
         for (int i = 0; i < n; i++) {
             boolean more = listener.match(haystack, pos[2 * i], pos[2 * i + 1]);
@@ -88,7 +117,7 @@ abstract class GpuMatcher<T> implements AutoCloseable {
     /** StringMap.match(String, MapMatchListener) — StringMap.java:8 */
     @SuppressWarnings("unchecked")
     protected void matchMap(String haystack, MapMatchListener<T> listener) {
-        Object[] r = AcGpuNative.match(handle, haystack);
+        Object[] r = AcGpuNative.match(live(), haystack);
         int[] pos = (int[]) r[0], val = (int[]) r[1];
         for (int i = 0; i < val.length; i++) {
             T v = (T) values[val[i]];
@@ -116,12 +145,12 @@ abstract class GpuMatcher<T> implements AutoCloseable {
      */
     @SuppressWarnings("unchecked")
     protected void matchReadable(Readable haystack, ReadableMatchListener<T> listener) throws IOException {
-        final int cbs = AcGpuNative.charBufferSize(handle);
+        final int cbs = AcGpuNative.charBufferSize(live());
         int blockChars = 1 << 16;            // device blocks start small (early stop over-reads little) ...
         final int maxBlockChars = 1 << 24;   // ... and double up to 16 Mi chars (the fixed cost of a feed is amortised)
         final boolean shortest = family == AcGpuNative.SHORTEST;
         final java.util.HashSet<Long> boundaries = new java.util.HashSet<Long>();
-        long s = AcGpuNative.streamBegin(handle);
+        long s = AcGpuNative.streamBegin(live());
         boolean ended = false;
         try {
             char[] block = new char[blockChars + cbs];

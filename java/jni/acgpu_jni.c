@@ -20,8 +20,18 @@ static void throw_for(JNIEnv *env, int rc) {
 }
 
 static jobjectArray wrap_result(JNIEnv *env, acgpu_result *r) {
-    jobjectArray out = (*env)->NewObjectArray(env, 2, (*env)->FindClass(env, "java/lang/Object"), NULL);
-    jintArray pos = (*env)->NewIntArray(env, (jsize)(2 * r->n));
+    if (r->n > 0x3FFFFFFF) { /* 2 * n must fit a Java array length */
+        acgpu_free_result(r);
+        (*env)->ThrowNew(env, (*env)->FindClass(env, "java/lang/OutOfMemoryError"), "more than 2^30 matches in one call");
+        return NULL;
+    }
+    jclass obj = (*env)->FindClass(env, "java/lang/Object");
+    jobjectArray out = obj ? (*env)->NewObjectArray(env, 3, obj, NULL) : NULL;
+    jintArray pos = out ? (*env)->NewIntArray(env, (jsize)(2 * r->n)) : NULL;
+    if (!pos) { /* OutOfMemoryError is pending */
+        acgpu_free_result(r);
+        return NULL;
+    }
     if (r->n) (*env)->SetIntArrayRegion(env, pos, 0, (jsize)(2 * r->n), (const jint *)r->pos);
     (*env)->SetObjectArrayElement(env, out, 0, pos);
     if (r->val) {
@@ -80,13 +90,43 @@ JNIEXPORT void JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_destroy
     acgpu_destroy((uint64_t)h);
 }
 
+/* GetStringChars, not GetStringCritical: the call blocks on H2D copies, kernels and D2H copies for up to seconds, which a
+ * JNI critical region must not do (it can stall the collector for every Java thread). */
+JNIEXPORT jobjectArray JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_matchCompact(JNIEnv *env, jclass c, jlong h,
+                                                                                              jstring haystack) {
+    const jsize n = (*env)->GetStringLength(env, haystack);
+    const jchar *p = (*env)->GetStringChars(env, haystack, NULL);
+    if (!p) return NULL;
+    acgpu_matches m;
+    int rc = acgpu_match_utf16_compact((uint64_t)h, (const uint16_t *)p, (int32_t)n, &m);
+    (*env)->ReleaseStringChars(env, haystack, p);
+    if (rc != ACGPU_OK) {
+        throw_for(env, rc);
+        return NULL;
+    }
+    if (m.kind == ACGPU_MATCHES_RECORDS) {
+        acgpu_result r = {m.n, m.pos, m.val};
+        return wrap_result(env, &r);
+    }
+    jclass obj = (*env)->FindClass(env, "java/lang/Object");
+    jobjectArray out = obj ? (*env)->NewObjectArray(env, 3, obj, NULL) : NULL;
+    jcharArray masks = out ? (*env)->NewCharArray(env, (jsize)m.n_chars) : NULL;
+    if (masks) {
+        (*env)->SetCharArrayRegion(env, masks, 0, (jsize)m.n_chars, (const jchar *)m.masks);
+        (*env)->SetObjectArrayElement(env, out, 2, masks);
+    }
+    acgpu_free_matches(&m);
+    return masks ? out : NULL;
+}
+
 JNIEXPORT jobjectArray JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_match(JNIEnv *env, jclass c, jlong h,
                                                                                        jstring haystack) {
     const jsize n = (*env)->GetStringLength(env, haystack);
-    const jchar *p = (*env)->GetStringCritical(env, haystack, NULL); /* pins the char[]; no JNI calls until release */
+    const jchar *p = (*env)->GetStringChars(env, haystack, NULL);
+    if (!p) return NULL;
     acgpu_result r;
     int rc = acgpu_match_utf16((uint64_t)h, (const uint16_t *)p, (int32_t)n, &r);
-    (*env)->ReleaseStringCritical(env, haystack, p);
+    (*env)->ReleaseStringChars(env, haystack, p);
     if (rc != ACGPU_OK) {
         throw_for(env, rc);
         return NULL;
@@ -104,10 +144,11 @@ JNIEXPORT jlong JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_stream
 JNIEXPORT jobjectArray JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_streamFeed(JNIEnv *env, jclass c,
                                                                                             jlong s, jcharArray buf,
                                                                                             jint n) {
-    jchar *p = (*env)->GetPrimitiveArrayCritical(env, buf, NULL);
+    jchar *p = (*env)->GetCharArrayElements(env, buf, NULL); /* not a critical region: the feed blocks on the device */
+    if (!p) return NULL;
     acgpu_result r;
     int rc = acgpu_stream_feed((uint64_t)s, (const uint16_t *)p, n, &r);
-    (*env)->ReleasePrimitiveArrayCritical(env, buf, p, JNI_ABORT);
+    (*env)->ReleaseCharArrayElements(env, buf, p, JNI_ABORT);
     if (rc != ACGPU_OK) {
         throw_for(env, rc);
         return NULL;

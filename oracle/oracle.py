@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and
 bench.py's cpu_baseline / --impl reference legs — never from the product package
-``ahocorasick_b200`` (tests/test_no_oracle_in_product.py enforces that).
+``ahocorasick_b200`` (tests/test_host_cpu.py::test_product_does_not_import_oracle enforces that).
 """
 from __future__ import annotations
 
@@ -141,13 +141,14 @@ class Matcher:
     def node_count(self) -> int:
         return lib().ora_node_count(self._h)
 
-    def match(self, haystack, readable: bool = False, stop_after: int = 0) -> np.ndarray:
-        """All listener calls, in order, as a (start, end, value) record array."""
+    def match(self, haystack, readable: bool = False, stop_after: int = 0, cap: int = 1 << 16) -> np.ndarray:
+        """All listener calls, in order, as a (start, end, value) record array.  `cap`: first guess of the record
+        count (a too small guess costs a second pass)."""
         hay = utf16(haystack)
         n = hay.size
         if n == 0:
             hay = np.zeros(1, np.uint16)
-        cap = 1 << 16
+        cap = max(1, int(cap))
         while True:
             out = np.zeros(cap, MATCH_DTYPE)
             total = lib().ora_match_collect(self._h, hay.ctypes.data, n, 1 if readable else 0,

@@ -12,7 +12,8 @@ int main(void) {
     const fn syms[] = {(fn)acgpu_create_from_keywords, (fn)acgpu_build_fingerprint, (fn)acgpu_destroy, (fn)acgpu_word_chars,
                        (fn)acgpu_info, (fn)acgpu_char_classes, (fn)acgpu_match_utf16, (fn)acgpu_free_result, (fn)acgpu_match_device,
                        (fn)acgpu_match_device_async, (fn)acgpu_launches_per_match, (fn)acgpu_stream_begin, (fn)acgpu_stream_feed,
-                       (fn)acgpu_stream_end, (fn)acgpu_last_error, (fn)acgpu_version};
+                       (fn)acgpu_stream_end, (fn)acgpu_last_error, (fn)acgpu_version, (fn)acgpu_match_utf16_compact, (fn)acgpu_free_matches,
+                       (fn)acgpu_masks_to_records};
     unsigned i, n_syms = (unsigned)(sizeof syms / sizeof syms[0]);
     for (i = 0; i < n_syms; i++)
         if (!syms[i]) return 10;
@@ -40,6 +41,17 @@ int main(void) {
     if (!acgpu_version() || !*acgpu_version()) return 21;
     acgpu_result empty = {0, NULL, NULL};
     acgpu_free_result(&empty); /* releasing an empty result is a no-op */
+    {
+        /* compact wire format, host-side expansion: "abcd" with keywords ending at char 1 (length 2) and char 3 (lengths 4, 1) */
+        const uint16_t masks[4] = {0, 1u << 14, 0, (1u << 12) | (1u << 15)};
+        int32_t pos[6];
+        if (acgpu_masks_to_records(masks, 4, 0, pos, 3) != 3) return 22;
+        if (pos[0] != 0 || pos[1] != 2 || pos[2] != 0 || pos[3] != 4 || pos[4] != 3 || pos[5] != 4) return 23;
+        if (acgpu_masks_to_records(masks, 4, 2, pos, 0) != 2) return 24;
+        acgpu_matches none;
+        memset(&none, 0, sizeof none);
+        acgpu_free_matches(&none);
+    }
     printf("c abi ok: %u entry points, version %s\n", n_syms, acgpu_version());
     return 0;
 }

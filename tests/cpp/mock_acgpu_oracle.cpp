@@ -21,6 +21,7 @@ int fail(int rc, const std::string &m) {
 struct Mock {
     ora_matcher *m;
     bool is_map;
+    int family;
 };
 struct MockStream {
     Mock *owner;
@@ -57,7 +58,7 @@ int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t 
     char err[4096] = {0};
     ora_matcher *m = ora_create(family, chars, offsets, is_null, n_keywords, n_values, case_sensitive, word_chars, err, sizeof err);
     if (!m) return fail(ACGPU_EILLEGALARG, err);
-    *handle = (uint64_t)(uintptr_t) new Mock{m, n_values >= 0};
+    *handle = (uint64_t)(uintptr_t) new Mock{m, n_values >= 0, family};
     return ACGPU_OK;
 }
 int acgpu_build_fingerprint(int, const uint16_t *, const int64_t *, const uint8_t *, int64_t, int64_t, int, const uint8_t *, uint64_t *,
@@ -93,6 +94,48 @@ void acgpu_free_result(acgpu_result *r) {
     r->pos = nullptr;
     r->val = nullptr;
     r->n = 0;
+}
+// compact call: an AhoCorasickSet whose matches all fit 16-bit hit masks answers with MASKS (the wire format libacgpu.so
+// picks for dense streams), so the CPU suite drives the mirrors' lazy mask replay; everything else answers with records
+int acgpu_match_utf16_compact(uint64_t h, const uint16_t *hay, int32_t n, acgpu_matches *out) {
+    Mock *mk = (Mock *)(uintptr_t)h;
+    std::memset(out, 0, sizeof *out);
+    acgpu_result r{0, nullptr, nullptr};
+    int rc = fill(mk, hay, n, &r);
+    if (rc != ACGPU_OK) return rc;
+    bool fits = mk->family == ACGPU_AHOCORASICK && !mk->is_map && r.n > 0;
+    for (int64_t i = 0; fits && i < r.n; i++) fits = r.pos[2 * i + 1] - r.pos[2 * i] <= 16;
+    out->n = r.n;
+    if (!fits) {
+        out->kind = ACGPU_MATCHES_RECORDS;
+        out->pos = r.pos;
+        out->val = r.val;
+        return ACGPU_OK;
+    }
+    uint16_t *masks = new uint16_t[n]();
+    for (int64_t i = 0; i < r.n; i++) masks[r.pos[2 * i + 1] - 1] |= (uint16_t)(1u << (16 - (r.pos[2 * i + 1] - r.pos[2 * i])));
+    acgpu_free_result(&r);
+    out->kind = ACGPU_MATCHES_MASKS;
+    out->masks = masks;
+    out->n_chars = n;
+    return ACGPU_OK;
+}
+void acgpu_free_matches(acgpu_matches *r) {
+    if (!r) return;
+    delete[] r->pos;
+    delete[] r->val;
+    delete[] r->masks;
+    std::memset(r, 0, sizeof *r);
+}
+int64_t acgpu_masks_to_records(const uint16_t *masks, int64_t n_chars, int64_t first_char, int32_t *pos_out, int64_t cap) {
+    int64_t k = 0;
+    for (int64_t q = first_char; q < n_chars; q++)
+        for (uint32_t w = masks[q]; w; w &= w - 1u, k++)
+            if (k < cap) {
+                pos_out[2 * k] = (int32_t)(q + 1 - (16 - __builtin_ctz(w)));
+                pos_out[2 * k + 1] = (int32_t)(q + 1);
+            }
+    return k;
 }
 int acgpu_match_device(uint64_t, const void *, int64_t, int64_t, int64_t, void *, void *, int64_t, int64_t *, void *) {
     return fail(ACGPU_ENODEVICE, "mock: no device entry points");
