@@ -21,6 +21,7 @@ EXPORTS = [
     "acgpu_match_utf16", "acgpu_free_result", "acgpu_match_device", "acgpu_match_device_async",
     "acgpu_launches_per_match", "acgpu_stream_begin", "acgpu_stream_feed", "acgpu_stream_end",
     "acgpu_last_error", "acgpu_version", "acgpu_match_utf16_compact", "acgpu_free_matches", "acgpu_masks_to_records",
+    "acgpu_chain_shard_layout", "acgpu_chain_shard_begin", "acgpu_chain_shard_finish",
 ]
 
 
@@ -92,6 +93,12 @@ def lib():
     L.acgpu_free_matches.argtypes = [C.POINTER(Matches)]
     L.acgpu_masks_to_records.restype = i64
     L.acgpu_masks_to_records.argtypes = [vp, i64, i64, vp, i64]
+    L.acgpu_chain_shard_layout.restype = C.c_int
+    L.acgpu_chain_shard_layout.argtypes = [u64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
+    L.acgpu_chain_shard_begin.restype = C.c_int
+    L.acgpu_chain_shard_begin.argtypes = [u64, vp, i64, i64, vp, C.POINTER(u64), vp]
+    L.acgpu_chain_shard_finish.restype = C.c_int
+    L.acgpu_chain_shard_finish.argtypes = [u64, i32, i32, vp, vp, i64, vp, vp]
     L.acgpu_last_error.restype = C.c_char_p
     L.acgpu_version.restype = C.c_char_p
     _lib = L

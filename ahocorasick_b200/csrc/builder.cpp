@@ -270,6 +270,33 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
     }
 }
 
+// AhoCorasick family outside the tier envelope: class-pair table for levels 1 and 2 of the anchored walk (kernel_wide.cuh)
+constexpr int kWideMaxLenHost = 32, kWidePairMaxHost = 64;
+void build_wide(HostAutomaton &a, const std::vector<uint32_t> &node_parent, const std::vector<uint16_t> &node_cls) {
+    a.wide_ok = false;
+    a.wide_pair.clear();
+    if (!a.has_other || a.max_len < 1 || a.max_len > kWideMaxLenHost) return;
+    a.wide_ok = true;
+    const int64_t C = a.n_classes;
+    if (C > kWidePairMaxHost) return;  // the walk starts at the root table instead
+    a.wide_pair.assign(static_cast<size_t>(C * C * 2), 0);
+    for (int64_t c0 = 0; c0 < C; c0++) {
+        const RootEdge &r = a.root[c0];
+        for (int64_t c1 = 0; c1 < C; c1++) {
+            uint32_t *e = &a.wide_pair[static_cast<size_t>(c0 * C + c1) * 2];
+            e[0] = kNone;
+            e[1] = r.child == kNone ? 0u : ((r.info & 0xFFu) << 8) | (1u << 16);
+        }
+    }
+    for (int64_t id = 1; id < a.n_nodes; id++) {
+        const uint32_t p = node_parent[id];
+        if (p == 0 || node_parent[p] != 0) continue;  // level-2 nodes only
+        uint32_t *e = &a.wide_pair[static_cast<size_t>(static_cast<int64_t>(node_cls[p]) * C + node_cls[id]) * 2];
+        e[0] = static_cast<uint32_t>(id);
+        e[1] |= a.node_info[id] & 0xFFu;
+    }
+}
+
 // WholeWord hash tables: one entry per distinct (trimmed, folded) keyword = per terminal node of the forward trie
 void build_ww(HostAutomaton &a, const std::vector<uint8_t> &wc, const std::vector<uint32_t> &node_parent,
               const std::vector<uint16_t> &node_cls) {
@@ -464,6 +491,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
     }
     timer.lap("edge table");
     if (family != 4) build_tiers(a, node_parent, node_cls);
+    if (family == 0 && !a.tier.ok) build_wide(a, node_parent, node_cls);
     timer.lap("tier tables");
     // WholeWordLongest with a dictionary whose (trimmed) keywords hold no non-word char: a walk can never leave its word
     // (there is no transition on a non-word char) and a keyword followed by a non-word char is the whole word, so the
@@ -504,6 +532,7 @@ uint64_t automaton_fingerprint(const HostAutomaton &a) {
     bytes(t.pow_c, sizeof t.pow_c); bytes(t.row_off, sizeof t.row_off);
     vec(t.row_words); vec(t.kidmask); vec(t.buckets); num(t.n_buckets); num(t.hash_seed); num(t.n_deep); num(t.n_heads);
     vec(t.vbuckets); num(t.n_vbuckets); num(t.vseed);
+    if (a.wide_ok) { num(a.wide_ok); vec(a.wide_pair); }
     num(a.ww.ok); vec(a.ww.wcls); vec(a.ww.buckets); num(a.ww.n_buckets); vec(a.ww.pool);
     return h;
 }

@@ -176,6 +176,11 @@ struct HostAutomaton {
     std::vector<uint8_t> node_info;    // n_nodes
     std::vector<uint32_t> depth_count; // nodes per depth (diagnostics / tiering)
     TierTables tier;                   // generation-2 tables (tier.ok == false: not applicable)
+    // AhoCorasick family outside the tier envelope (kernel_wide.cuh): 32-bit hit masks by anchored walks over the edge
+    // table; levels 1 and 2 come from a class-pair table when it fits shared memory.  wide_pair[2 * (c0 * C + c1)] =
+    // {level-2 node of the reversed context (c0, c1) or kNone, info2 | info1 << 8 | (level-1 node exists) << 16}
+    bool wide_ok = false;
+    std::vector<uint32_t> wide_pair;
     WwTables ww;                       // WholeWord hash tables (ww.ok == false: not applicable)
     bool ww_plain = true;              // WholeWordLongest: no keyword holds a non-word char (then it equals WholeWord)
 };

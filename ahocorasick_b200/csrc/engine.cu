@@ -21,6 +21,7 @@
 #include "kernel_emit.cuh"
 #include "kernel_sel2.cuh"
 #include "kernel_ww.cuh"
+#include "kernel_wide.cuh"
 #include "tier_launch.hpp"
 
 using namespace acgpu;
@@ -84,6 +85,11 @@ struct Matcher {
     void *d_tier_blob = nullptr;
     L2Window l2win;         // child masks + deep table, kept L2-resident across the streaming traffic
     size_t mask_smem = 0;
+    // AhoCorasick family outside the tier envelope (kernel_wide.cuh)
+    bool use_wide = false;
+    DevWide wide{};
+    void *d_wide_blob = nullptr;
+    size_t wide_smem = 0;
     // WholeWord hash tables (kernel_ww.cuh)
     bool use_ww = false;
     DevWw ww{};
@@ -221,6 +227,30 @@ int upload_tier(Matcher *m) {
     return ACGPU_OK;
 }
 
+int upload_wide(Matcher *m) {
+    m->use_wide = false;
+    if (!m->host.wide_ok || m->use_tier) return ACGPU_OK;
+    const char *force = getenv("ACGPU_FORCE_GEN1");
+    if (force && force[0] == '1') return ACGPU_OK;
+    const bool pair = !m->host.wide_pair.empty();
+    m->wide.C = m->host.n_classes;
+    m->wide.pair = nullptr;
+    if (pair) {
+        const size_t bytes = m->host.wide_pair.size() * 4;
+        CU_TRY(cudaMalloc(&m->d_wide_blob, bytes));
+        m->table_bytes += static_cast<int64_t>(bytes);
+        CU_TRY(cudaMemcpy(m->d_wide_blob, m->host.wide_pair.data(), bytes, cudaMemcpyHostToDevice));
+        m->wide.pair = static_cast<const uint2 *>(m->d_wide_blob);
+    }
+    // at most 512 + 64 * 64 * 8 + 8 * 2 880 = 56 320 bytes: one attribute for every matcher (a per-matcher value would
+    // shrink the limit under a live matcher with a larger table)
+    m->wide_smem = wide_smem_bytes(m->host.n_classes, pair);
+    static_assert(wide_smem_bytes(kWidePairMax, true) <= 64 * 1024, "k_wide_mask shared memory");
+    CU_TRY(cudaFuncSetAttribute(k_wide_mask<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_smem_bytes(kWidePairMax, true)));
+    m->use_wide = true;
+    return ACGPU_OK;
+}
+
 int upload_ww(Matcher *m) {
     const WwTables &t = m->host.ww;
     m->use_ww = false;
@@ -297,10 +327,24 @@ int launch_mask(Matcher *m, const MaskArgs &P, int grid, cudaStream_t st, bool m
     return ACGPU_OK;
 }
 
-// Longest / Shortest, narrow alphabets, one-shot match: start masks (mirrored k_tier_mask) -> exit maps -> scan ->
-// records (kernel_sel2.cuh)
-int enqueue_sel2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint32_t *d_val, int64_t cap,
-                 unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
+// Longest / Shortest, narrow alphabets: start masks (mirrored k_tier_mask) -> exit maps -> scan -> records
+// (kernel_sel2.cuh).  Two phases so that range shards of one haystack can exchange their maps in between:
+//   A  (entry-independent) masks of the window, the exit map of every domain tile, the group maps, and - on request -
+//      the shard's composed map for all 16 entry offsets
+//   B  the true chain from a given entry offset: group / tile entries, records, values
+struct Sel2Run {
+    Matcher *m = nullptr;
+    void *ws = nullptr;
+    cudaStream_t st = nullptr;
+    MaskArgs P{};
+    Sel2Args Q{};
+    size_t o_status = 0, o_ctr = 0;
+    int64_t n = 0, moff = 0, n_rows = 0;
+    bool longest = true;
+};
+
+// n_dom_tiles < 0: the whole window is the chain domain
+int sel2_setup(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t n_dom_tiles, cudaStream_t st, const RunOpts &opt, Sel2Run &R) {
     // the mirrored kernel loads hay[n - 8 - p0, n - p0): rows start at origin <= 0 with origin = mis + n (mod 8)
     const int64_t mis = static_cast<int64_t>((reinterpret_cast<uintptr_t>(d_hay) >> 1) & 7);
     const int64_t r = (mis + n) & 7;
@@ -308,7 +352,8 @@ int enqueue_sel2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint
     const int64_t n_rows = (n - origin + kMaskRow - 1) / kMaskRow;
     const int64_t n_idx = n_rows * kMaskRow;
     const int64_t moff = n_idx - n + origin;
-    const int64_t n_tiles = (n_idx + kS2Tile - 1) / kS2Tile;
+    const int64_t all_tiles = (n_idx + kS2Tile - 1) / kS2Tile;
+    const int64_t n_tiles = n_dom_tiles < 0 ? all_tiles : std::min(n_dom_tiles, all_tiles);
     Scratch S;
     const size_t o_ctr = S.reserve(256);
     const size_t o_cnt = S.reserve(static_cast<size_t>(n_rows) * 4);
@@ -321,11 +366,17 @@ int enqueue_sel2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint
     const size_t o_gent = S.reserve(static_cast<size_t>(n_groups));
     const size_t o_gbase = S.reserve(static_cast<size_t>(n_groups) * 8);
     const size_t o_status = S.reserve(static_cast<size_t>(n_tiles) * sizeof(S2Status));
-    void *ws = nullptr;
-    CU_TRY(cudaMallocAsync(&ws, S.off, st));
-    char *w = static_cast<char *>(ws);
-    CU_TRY(cudaMemsetAsync(w + o_ctr, 0, 256, st));
-    MaskArgs P{};
+    CU_TRY(cudaMallocAsync(&R.ws, S.off, st));
+    char *w = static_cast<char *>(R.ws);
+    R.m = m;
+    R.st = st;
+    R.n = n;
+    R.moff = moff;
+    R.n_rows = n_rows;
+    R.o_status = o_status;
+    R.o_ctr = o_ctr;
+    R.longest = m->dev.family == ACGPU_LONGEST;
+    MaskArgs &P = R.P;
     P.hay = d_hay;
     P.n = n;
     P.emit_from = 0;
@@ -335,11 +386,7 @@ int enqueue_sel2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint
     P.row_count = reinterpret_cast<uint32_t *>(w + o_cnt);
     P.ticket = reinterpret_cast<unsigned int *>(w + o_ctr);
     P.n_rows = n_rows;
-    const int64_t n_chunks = (n_rows + kMaskChunkRows - 1) / kMaskChunkRows;
-    const int grid = static_cast<int>(std::min<int64_t>((n_chunks + kMaskWarps - 1) / kMaskWarps, m->sm_count));
-    int rc = launch_mask(m, P, grid, st, true);
-    if (rc != ACGPU_OK) return rc;
-    Sel2Args Q{};
+    Sel2Args &Q = R.Q;
     Q.masks = P.masks;
     Q.n_idx = n_idx;
     Q.moff = moff;
@@ -351,64 +398,139 @@ int enqueue_sel2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint
     Q.group_map = reinterpret_cast<uint32_t *>(w + o_gmap);
     Q.group_entry = reinterpret_cast<uint8_t *>(w + o_gent);
     Q.group_base = reinterpret_cast<unsigned long long *>(w + o_gbase);
-    Q.total_out = d_total;
     Q.hay = d_hay;
     Q.n = n;
     Q.pos_base = opt.pos_base;
+    return ACGPU_OK;
+}
+
+void sel2_free(Sel2Run &R) {
+    if (R.ws) cudaFreeAsync(R.ws, R.st);
+    R.ws = nullptr;
+}
+
+int sel2_masks(Sel2Run &R) {
+    CU_TRY(cudaMemsetAsync(static_cast<char *>(R.ws) + R.o_ctr, 0, 256, R.st));
+    const int64_t n_chunks = (R.n_rows + kMaskChunkRows - 1) / kMaskChunkRows;
+    const int grid = static_cast<int>(std::min<int64_t>((n_chunks + kMaskWarps - 1) / kMaskWarps, R.m->sm_count));
+    return launch_mask(R.m, R.P, grid, R.st, true);
+}
+
+int sel2_maps(Sel2Run &R, int64_t only_first_tiles = -1) {
+    Sel2Args Q = R.Q;
+    if (only_first_tiles >= 0) Q.n_tiles = std::min(Q.n_tiles, only_first_tiles);
+    if (Q.n_tiles <= 0) return ACGPU_OK;
+    const size_t smem = static_cast<size_t>(kS2SmemWords) * 4;
+    const int sgrid = static_cast<int>(std::min<int64_t>(Q.n_tiles, static_cast<int64_t>(R.m->sm_count) * 16));
+    if (R.longest)
+        k_sel2_map<kModeLongest><<<sgrid, kS2Threads, smem, R.st>>>(Q);
+    else
+        k_sel2_map<kModeShortest><<<sgrid, kS2Threads, smem, R.st>>>(Q);
+    CU_TRY(cudaGetLastError());
+    // the group maps read every tile map of their group: all groups (one-shot) or group 0 only (a re-run of tile 0)
+    k_sel2_group<<<static_cast<unsigned>(only_first_tiles >= 0 ? 1 : R.Q.n_groups), 32, 0, R.st>>>(R.Q);
+    CU_TRY(cudaGetLastError());
+    return ACGPU_OK;
+}
+
+// the composed map of the shard for all 16 entry offsets -> d_map[16] (exit offset | matches << 8)
+int sel2_shard_map(Sel2Run &R, unsigned long long *d_map, unsigned long long *d_scratch_total) {
+    Sel2Args Q = R.Q;
+    Q.entry0 = 0;
+    Q.shard_map = d_map;
+    Q.total_out = d_scratch_total;
+    k_sel2_top<<<1, 1024, static_cast<size_t>(Q.n_groups) * kS2Ent * 4, R.st>>>(Q);
+    CU_TRY(cudaGetLastError());
+    return ACGPU_OK;
+}
+
+int sel2_records(Sel2Run &R, uint32_t entry0, int2 *d_pos, uint32_t *d_val, int64_t cap, unsigned long long *d_total) {
+    Sel2Args Q = R.Q;
+    Q.entry0 = entry0;
+    Q.shard_map = nullptr;
+    Q.total_out = d_total;
     Q.pos_out = d_pos;
     Q.val_out = d_val;
     Q.cap = cap;
-    const bool longest = m->dev.family == ACGPU_LONGEST;
+    if (Q.n_tiles <= 0) {
+        CU_TRY(cudaMemsetAsync(d_total, 0, 8, R.st));
+        return ACGPU_OK;
+    }
     const size_t smem = static_cast<size_t>(kS2SmemWords) * 4;
+    const int sgrid = static_cast<int>(std::min<int64_t>(Q.n_tiles, static_cast<int64_t>(R.m->sm_count) * 16));
+    k_sel2_top<<<1, 1024, static_cast<size_t>(Q.n_groups) * kS2Ent * 4, R.st>>>(Q);
+    CU_TRY(cudaGetLastError());
+    k_sel2_tiles<<<static_cast<unsigned>(Q.n_groups), 32, 0, R.st>>>(Q);
+    CU_TRY(cudaGetLastError());
+    if (cap > 0) {
+        if (R.longest)
+            k_sel2_emit<kModeLongest><<<sgrid, kS2Threads, smem, R.st>>>(Q);
+        else
+            k_sel2_emit<kModeShortest><<<sgrid, kS2Threads, smem, R.st>>>(Q);
+        CU_TRY(cudaGetLastError());
+    }
+    if (cap > 0 && R.m->dev.is_map) {
+        const int vgrid = static_cast<int>(std::min<int64_t>(Q.n_tiles, static_cast<int64_t>(R.m->sm_count) * 16));
+        switch (R.m->tier.b) {
+        case 1: k_sel2_values<1><<<vgrid, kS2Threads, 0, R.st>>>(R.m->dev, R.m->tier, Q); break;
+        case 2: k_sel2_values<2><<<vgrid, kS2Threads, 0, R.st>>>(R.m->dev, R.m->tier, Q); break;
+        case 3: k_sel2_values<3><<<vgrid, kS2Threads, 0, R.st>>>(R.m->dev, R.m->tier, Q); break;
+        case 4: k_sel2_values<4><<<vgrid, kS2Threads, 0, R.st>>>(R.m->dev, R.m->tier, Q); break;
+        default: k_sel2_values<5><<<vgrid, kS2Threads, 0, R.st>>>(R.m->dev, R.m->tier, Q); break;
+        }
+        CU_TRY(cudaGetLastError());
+    }
+    return ACGPU_OK;
+}
+
+int enqueue_sel2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint32_t *d_val, int64_t cap,
+                 unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
+    Sel2Run R;
+    int rc = sel2_setup(m, d_hay, n, -1, st, opt, R);
+    if (rc != ACGPU_OK) return rc;
+    rc = sel2_masks(R);
     // Measured (profiles/r01_s5_summary.md): the look-back over MAPS costs ~12 us per tile (following the chain through
     // the published maps is latency-bound), more than the second resolution pass it saves - opt-in only.
     const char *fused = getenv("ACGPU_SEL2_FUSED");
-    if (fused && fused[0] == '1') {
+    if (rc == ACGPU_OK && fused && fused[0] == '1') {
         // single pass: maps, look-back over the maps, emission (k_sel2_fused)
-        CU_TRY(cudaMemsetAsync(w + o_status, 0, static_cast<size_t>(n_tiles) * sizeof(S2Status), st));
-        Q.status = reinterpret_cast<S2Status *>(w + o_status);
-        Q.tile_counter = reinterpret_cast<unsigned int *>(w + o_ctr + 64);
-        Q.err = reinterpret_cast<unsigned int *>(w + o_ctr + 128);
-        const int fgrid = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(m->sm_count) * 4));
-        if (longest)
-            k_sel2_fused<kModeLongest><<<fgrid, kS2Threads, smem, st>>>(Q);
-        else
-            k_sel2_fused<kModeShortest><<<fgrid, kS2Threads, smem, st>>>(Q);
-        CU_TRY(cudaGetLastError());
-    } else {
-        const int sgrid = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(m->sm_count) * 16));
-        if (longest)
-            k_sel2_map<kModeLongest><<<sgrid, kS2Threads, smem, st>>>(Q);
-        else
-            k_sel2_map<kModeShortest><<<sgrid, kS2Threads, smem, st>>>(Q);
-        CU_TRY(cudaGetLastError());
-        k_sel2_group<<<static_cast<unsigned>(n_groups), 32, 0, st>>>(Q);
-        CU_TRY(cudaGetLastError());
-        k_sel2_top<<<1, 1024, static_cast<size_t>(n_groups) * kS2Ent * 4, st>>>(Q);
-        CU_TRY(cudaGetLastError());
-        k_sel2_tiles<<<static_cast<unsigned>(n_groups), 32, 0, st>>>(Q);
-        CU_TRY(cudaGetLastError());
-        if (cap > 0) {
-            if (longest)
-                k_sel2_emit<kModeLongest><<<sgrid, kS2Threads, smem, st>>>(Q);
+        char *w = static_cast<char *>(R.ws);
+        Sel2Args Q = R.Q;
+        Q.total_out = d_total;
+        Q.pos_out = d_pos;
+        Q.val_out = d_val;
+        Q.cap = cap;
+        const size_t smem = static_cast<size_t>(kS2SmemWords) * 4;
+        cudaError_t e = cudaMemsetAsync(w + R.o_status, 0, static_cast<size_t>(Q.n_tiles) * sizeof(S2Status), st);
+        Q.status = reinterpret_cast<S2Status *>(w + R.o_status);
+        Q.tile_counter = reinterpret_cast<unsigned int *>(w + R.o_ctr + 64);
+        Q.err = reinterpret_cast<unsigned int *>(w + R.o_ctr + 128);
+        const int fgrid = static_cast<int>(std::min<int64_t>(Q.n_tiles, static_cast<int64_t>(m->sm_count) * 4));
+        if (e == cudaSuccess) {
+            if (R.longest)
+                k_sel2_fused<kModeLongest><<<fgrid, kS2Threads, smem, st>>>(Q);
             else
-                k_sel2_emit<kModeShortest><<<sgrid, kS2Threads, smem, st>>>(Q);
-            CU_TRY(cudaGetLastError());
+                k_sel2_fused<kModeShortest><<<fgrid, kS2Threads, smem, st>>>(Q);
+            e = cudaGetLastError();
         }
-    }
-    if (cap > 0 && m->dev.is_map) {
-        const int vgrid = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(m->sm_count) * 16));
-        switch (m->tier.b) {
-        case 1: k_sel2_values<1><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
-        case 2: k_sel2_values<2><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
-        case 3: k_sel2_values<3><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
-        case 4: k_sel2_values<4><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
-        default: k_sel2_values<5><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
+        if (e == cudaSuccess && cap > 0 && m->dev.is_map) {
+            const int vgrid = static_cast<int>(std::min<int64_t>(Q.n_tiles, static_cast<int64_t>(m->sm_count) * 16));
+            switch (m->tier.b) {
+            case 1: k_sel2_values<1><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
+            case 2: k_sel2_values<2><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
+            case 3: k_sel2_values<3><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
+            case 4: k_sel2_values<4><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
+            default: k_sel2_values<5><<<vgrid, kS2Threads, 0, st>>>(m->dev, m->tier, Q); break;
+            }
+            e = cudaGetLastError();
         }
-        CU_TRY(cudaGetLastError());
+        if (e != cudaSuccess) rc = fail(ACGPU_ECUDA, std::string("k_sel2_fused: ") + cudaGetErrorString(e));
+    } else {
+        if (rc == ACGPU_OK) rc = sel2_maps(R);
+        if (rc == ACGPU_OK) rc = sel2_records(R, 0, d_pos, d_val, cap, d_total);
     }
-    CU_TRY(cudaFreeAsync(ws, st));
-    return ACGPU_OK;
+    sel2_free(R);
+    return rc;
 }
 
 // AhoCorasick family, narrow alphabets: hit masks -> row-count scan -> records (kernel_mask.cuh)
@@ -495,6 +617,79 @@ int enqueue_mask(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from
     return rc;
 }
 
+// AhoCorasick family outside the tier envelope: 32-bit hit masks by anchored walks -> row-count scan -> records (kernel_wide.cuh)
+int enqueue_wide(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from, int64_t emit_to, int64_t origin, int2 *d_pos,
+                 uint32_t *d_val, int64_t cap, unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
+    const int64_t n_rows = (emit_to - origin + kMaskRow - 1) / kMaskRow;
+    const int64_t n_blocks = (n_rows + kScanRows - 1) / kScanRows;
+    Scratch S;
+    const size_t o_ctr = S.reserve(256);
+    const size_t o_cnt = S.reserve(static_cast<size_t>(n_rows) * 4);
+    const size_t o_blk = S.reserve(static_cast<size_t>(n_blocks) * 8);
+    const size_t o_mask = S.reserve(static_cast<size_t>(n_rows) * kMaskRow * 4);
+    void *ws = nullptr;
+    CU_TRY(cudaMallocAsync(&ws, S.off, st));
+    char *w = static_cast<char *>(ws);
+    int rc = ACGPU_OK;
+    auto launch_ok = [&](const char *what) {
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && rc == ACGPU_OK) rc = fail(ACGPU_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    };
+    if (cudaMemsetAsync(w + o_ctr, 0, 256, st) != cudaSuccess) rc = fail(ACGPU_ECUDA, "memset failed");
+    if (rc == ACGPU_OK) {
+        WideArgs P{};
+        P.hay = d_hay;
+        P.n = n;
+        P.emit_from = emit_from;
+        P.emit_to = emit_to;
+        P.origin = origin;
+        P.masks = reinterpret_cast<uint32_t *>(w + o_mask);
+        P.row_count = reinterpret_cast<uint32_t *>(w + o_cnt);
+        P.ticket = reinterpret_cast<unsigned int *>(w + o_ctr);
+        P.n_rows = n_rows;
+        const int64_t n_chunks = (n_rows + kMaskChunkRows - 1) / kMaskChunkRows;
+        const int per_sm = std::max<int>(1, std::min<int>(6, static_cast<int>((200 * 1024) / std::max<size_t>(m->wide_smem, 1))));
+        const int grid = static_cast<int>(std::min<int64_t>((n_chunks + kWideWarps - 1) / kWideWarps, static_cast<int64_t>(m->sm_count) * per_sm));
+        if (m->wide.pair)
+            k_wide_mask<true><<<grid, kWideThreads, m->wide_smem, st>>>(m->dev, m->wide, P);
+        else
+            k_wide_mask<false><<<grid, kWideThreads, m->wide_smem, st>>>(m->dev, m->wide, P);
+        launch_ok("k_wide_mask");
+    }
+    if (rc == ACGPU_OK) {
+        ScanArgs SA{};
+        SA.row_count = reinterpret_cast<uint32_t *>(w + o_cnt);
+        SA.block_excl = reinterpret_cast<unsigned long long *>(w + o_blk);
+        SA.done = reinterpret_cast<unsigned int *>(w + o_ctr + 64);
+        SA.total_out = d_total;
+        SA.n_rows = n_rows;
+        k_row_scan<<<static_cast<unsigned>(n_blocks), 1024, 0, st>>>(SA);
+        launch_ok("k_row_scan");
+    }
+    if (rc == ACGPU_OK && cap > 0) {
+        EmitArgs E{};
+        E.hay = d_hay;
+        E.n = n;
+        E.masks = reinterpret_cast<uint32_t *>(w + o_mask);
+        E.row_excl = reinterpret_cast<uint32_t *>(w + o_cnt);
+        E.block_excl = reinterpret_cast<unsigned long long *>(w + o_blk);
+        E.n_rows = n_rows;
+        E.origin = origin;
+        E.pos_base = opt.pos_base;
+        E.pos_out = d_pos;
+        E.val_out = d_val;
+        E.cap = cap;
+        const int egrid = static_cast<int>(std::min<int64_t>((n_rows + kEmitWarps - 1) / kEmitWarps, static_cast<int64_t>(m->sm_count) * 128));
+        if (m->dev.is_map)
+            k_wide_emit<true><<<egrid, kEmitWarps * 32, 0, st>>>(m->dev, E);
+        else
+            k_wide_emit<false><<<egrid, kEmitWarps * 32, 0, st>>>(m->dev, E);
+        launch_ok("k_wide_emit");
+    }
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
 // Enqueue every kernel of one match on `st`.  d_total receives the total number of matches.
 int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from, int64_t emit_to, int2 *d_pos,
                   uint32_t *d_val, int64_t cap, unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
@@ -508,7 +703,7 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
         emit_to = std::min<int64_t>(n, emit_to);
         // k_ac_tier rows start at `origin` <= emit_from, placed so that every lane's 8-char load is 16-byte aligned
         const int64_t mis = static_cast<int64_t>((reinterpret_cast<uintptr_t>(d_hay) >> 1) & 7);
-        const int64_t origin = m->use_tier ? ((emit_from + mis) & ~int64_t(7)) - mis : emit_from;
+        const int64_t origin = (m->use_tier || m->use_wide) ? ((emit_from + mis) & ~int64_t(7)) - mis : emit_from;
         const int64_t span = std::max<int64_t>(0, emit_to - origin);
         const int64_t tile_sz = kAcTile;
         const int64_t n_tiles = emit_to > emit_from ? (span + tile_sz - 1) / tile_sz : 0;
@@ -517,6 +712,7 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
             return ACGPU_OK;
         }
         if (m->use_tier) return enqueue_mask(m, d_hay, n, emit_from, emit_to, origin, d_pos, d_val, cap, d_total, st, opt);
+        if (m->use_wide) return enqueue_wide(m, d_hay, n, emit_from, emit_to, origin, d_pos, d_val, cap, d_total, st, opt);
         size_t bytes = 256 + static_cast<size_t>(n_tiles) * 8;
         void *ws = nullptr;
         CU_TRY(cudaMallocAsync(&ws, bytes, st));
@@ -1181,12 +1377,14 @@ int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t 
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) m->sm_count = prop.multiProcessorCount;
         rc = upload(m);
         if (rc == ACGPU_OK) rc = upload_tier(m);
+        if (rc == ACGPU_OK) rc = upload_wide(m);
         if (rc == ACGPU_OK) rc = upload_ww(m);
     }
     if (rc != ACGPU_OK) {
         if (m->tier.kid_tex) cudaDestroyTextureObject(m->tier.kid_tex);
         if (m->d_tier_blob) cudaFree(m->d_tier_blob);
         if (m->d_ww_blob) cudaFree(m->d_ww_blob);
+        if (m->d_wide_blob) cudaFree(m->d_wide_blob);
         if (m->d_blob) cudaFree(m->d_blob);
         delete m;
         return rc;
@@ -1229,6 +1427,7 @@ int acgpu_destroy(uint64_t handle) {
     if (m->tier.kid_tex) cudaDestroyTextureObject(m->tier.kid_tex);
     if (m->d_tier_blob) cudaFree(m->d_tier_blob);
     if (m->d_ww_blob) cudaFree(m->d_ww_blob);
+    if (m->d_wide_blob) cudaFree(m->d_wide_blob);
     m->magic = 0;
     delete m;
     return ACGPU_OK;
@@ -1258,7 +1457,7 @@ int acgpu_launches_per_match(uint64_t handle) {
     Matcher *m = as_matcher(handle);
     if (!m) return fail(ACGPU_EINVAL, "bad handle");
     switch (m->host.family) {
-    case ACGPU_AHOCORASICK: return m->use_tier ? 3 : 1;
+    case ACGPU_AHOCORASICK: return (m->use_tier || m->use_wide) ? 3 : 1;
     case ACGPU_WHOLEWORD: return m->use_ww ? 1 : 2;
     default: return m->use_tier && m->host.is_map ? 7 : 6;  // one-shot tier path: mask, map, group, top, tiles, emit (+ values)  // one-shot matches; the streaming path always takes the 6-launch route
     }
@@ -1303,6 +1502,110 @@ int acgpu_match_device(uint64_t handle, const void *d_haystack, int64_t n, int64
     cudaFreeAsync(d_total, st);
     if (rc == ACGPU_OK) *n_out = static_cast<int64_t>(total);
     return rc;
+}
+
+// ---- Longest / Shortest range shards of ONE haystack (LongestMatchSet.java:192-265, SetMatchQueue.java:45-95,
+//      ShortestMatchSet.java:182-260).  The selection chain pos -> J(pos) crosses shard boundaries; a shard's effect on it
+//      is a map "entry offset -> (exit offset, matches)" over at most 16 entry offsets, so the shards scan in parallel,
+//      exchange their maps (16 words each, they ride in the count all-gather) and then emit from their true entry.
+namespace {
+constexpr uint64_t kChainMagic = 0xC4A1135AAD0B200ull;
+struct ChainShard {
+    uint64_t magic = kChainMagic;
+    Sel2Run R;
+    int64_t n_domain = 0;
+    unsigned long long *d_tmp = nullptr;  // scratch total of the map pass
+};
+}  // namespace
+
+int acgpu_chain_shard_begin(uint64_t handle, const void *d_window, int64_t n, int64_t n_domain, void *d_map16, uint64_t *shard,
+                            void *cuda_stream) {
+    Matcher *m = as_matcher(handle);
+    if (!m || !shard) return fail(ACGPU_EINVAL, "bad arguments");
+    *shard = 0;
+    if (m->host.family != ACGPU_LONGEST && m->host.family != ACGPU_SHORTEST)
+        return fail(ACGPU_EINVAL, "chain shards are for the Longest / Shortest families (the others shard by range or word start)");
+    if (n <= 0 || n > 0x7FFFFFFFll || !d_window || n_domain <= 0 || n_domain > n) return fail(ACGPU_EINVAL, "bad window");
+    int rc = ensure_device(m);
+    if (rc != ACGPU_OK) return rc;
+    if (!m->use_tier)
+        return fail(ACGPU_EUNSUPPORTED, "chain shards need the start-mask path (at most 31 keyword symbols, keywords of at most 16 chars)");
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    ChainShard *c = new (std::nothrow) ChainShard();
+    if (!c) return fail(ACGPU_ENOMEM, "out of memory");
+    RunOpts opt;
+    // a shard that ends before its window does owns whole tiles: its last chain position must be the last index of a tile
+    const uint16_t *hay = static_cast<const uint16_t *>(d_window);
+    {
+        const int64_t mis = static_cast<int64_t>((reinterpret_cast<uintptr_t>(hay) >> 1) & 7);
+        const int64_t r = (mis + n) & 7;
+        const int64_t origin = r ? r - 8 : 0;
+        const int64_t n_idx = (n - origin + kMaskRow - 1) / kMaskRow * kMaskRow;
+        const int64_t moff = n_idx - n + origin;
+        if (n_domain < n && ((n_domain + moff) % kS2Tile != 0 || n - n_domain < 2 * m->host.max_len + 2)) {
+            delete c;
+            return fail(ACGPU_EINVAL, "a chain shard inside the haystack must end on a tile boundary (acgpu_chain_shard_layout) and "
+                                      "needs 2 * max_len + 2 chars of look-ahead");
+        }
+        c->n_domain = n_domain;
+        rc = sel2_setup(m, hay, n, n_domain < n ? (n_domain + moff) / kS2Tile : -1, st, opt, c->R);
+    }
+    if (rc == ACGPU_OK) rc = sel2_masks(c->R);
+    if (rc == ACGPU_OK) rc = sel2_maps(c->R);
+    if (rc == ACGPU_OK && d_map16) {
+        if (cudaMallocAsync(reinterpret_cast<void **>(&c->d_tmp), 8, st) != cudaSuccess) rc = fail(ACGPU_ECUDA, "cudaMallocAsync failed");
+        if (rc == ACGPU_OK) rc = sel2_shard_map(c->R, static_cast<unsigned long long *>(d_map16), c->d_tmp);
+    }
+    if (rc != ACGPU_OK) {
+        if (c->d_tmp) cudaFreeAsync(c->d_tmp, st);
+        sel2_free(c->R);
+        delete c;
+        return rc;
+    }
+    *shard = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(c));
+    return ACGPU_OK;
+}
+
+int acgpu_chain_shard_finish(uint64_t shard, int32_t entry, int32_t pos_base, void *d_pos, void *d_val, int64_t cap, void *d_total,
+                             void *cuda_stream) {
+    ChainShard *c = reinterpret_cast<ChainShard *>(static_cast<uintptr_t>(shard));
+    if (!c || c->magic != kChainMagic) return fail(ACGPU_EINVAL, "bad shard handle");
+    Sel2Run &R = c->R;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    int rc = ACGPU_OK;
+    if (st != R.st) rc = fail(ACGPU_EINVAL, "finish must use the stream of begin");
+    if (rc == ACGPU_OK && (entry < 0 || entry >= kS2Ent || !d_total || cap < 0 || (cap > 0 && !d_pos) || (cap > 0 && R.m->dev.is_map && !d_val)))
+        rc = fail(ACGPU_EINVAL, "bad arguments");
+    uint32_t entry0 = 0;
+    if (rc == ACGPU_OK && entry > 0) {
+        const int64_t idx = R.moff + entry;  // index-space position the chain enters at
+        if (idx < kS2Ent) {
+            entry0 = static_cast<uint32_t>(idx);
+        } else {
+            // the window is not tile-aligned at its start: hide the starts left of the entry and resolve tile 0 again
+            k_sel2_zero_prefix<<<1, 256, 0, st>>>(R.P.masks, R.moff, idx);
+            if (cudaGetLastError() != cudaSuccess) rc = fail(ACGPU_ECUDA, "k_sel2_zero_prefix failed");
+            if (rc == ACGPU_OK) rc = sel2_maps(R, 1);
+        }
+    }
+    if (rc == ACGPU_OK) {
+        R.Q.pos_base = pos_base;
+        rc = sel2_records(R, entry0, static_cast<int2 *>(d_pos), static_cast<uint32_t *>(d_val), cap, static_cast<unsigned long long *>(d_total));
+    }
+    if (c->d_tmp) cudaFreeAsync(c->d_tmp, R.st);
+    sel2_free(R);
+    c->magic = 0;
+    delete c;
+    return rc;
+}
+
+int acgpu_chain_shard_layout(uint64_t handle, int64_t *tile_chars, int64_t *lookahead_chars, int32_t *map_entries) {
+    Matcher *m = as_matcher(handle);
+    if (!m) return fail(ACGPU_EINVAL, "bad handle");
+    if (tile_chars) *tile_chars = kS2Tile;
+    if (lookahead_chars) *lookahead_chars = kMaskRow;  // a multiple of 256 keeps every shard's window aligned; >= 2 * max_len + 2
+    if (map_entries) *map_entries = kS2Ent;
+    return ACGPU_OK;
 }
 
 int acgpu_match_utf16(uint64_t handle, const uint16_t *haystack, int32_t n, acgpu_result *out) {

@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
     // parity of the output buffer in 8-byte units: record g is 16-byte aligned iff (g + out_par) is even
     const uint32_t out_par = (uint32_t)(reinterpret_cast<uintptr_t>(E.pos_out) >> 3) & 1u;
 
+    const uint32_t lane_code = (uint32_t)lane * 128u;
     int64_t row = (int64_t)blockIdx.x * kEmitWarps + warp;
     uint4 mm_n = make_uint4(0u, 0u, 0u, 0u);
     unsigned long long base_n = 0;
@@ -205,16 +206,18 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
             //      both sides of the flush are aligned.
             const uint32_t par = ((uint32_t)base + out_par) & 1u;
             uint32_t sa = stage_sa + (my_off + par) * 2u;
+            uint32_t cb = lane_code;  // lane * 128, + 32 per mask word
 #pragma unroll
             for (int wi = 0; wi < 4; wi++) {
                 uint32_t w = words[wi];
-                const uint32_t cb = (uint32_t)lane * 128u + (uint32_t)wi * 32u;
                 while (w) {
                     const uint32_t t = (uint32_t)__clz((int)__brev(w));
                     w &= w - 1u;
                     sts_u16(sa, cb + t);
                     sa += 2u;
                 }
+                cb += 32u;
+                asm volatile("" : "+r"(cb));  // keep the word's code base in a register (else it is re-added in every iteration)
             }
             __syncwarp();
             const int32_t e_row = (int32_t)(E.origin + row * kMaskRow) + 1 + E.pos_base;  // end of a keyword whose last char is row position 0

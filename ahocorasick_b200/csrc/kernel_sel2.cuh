@@ -61,6 +61,11 @@ struct Sel2Args {
     int2 *pos_out;
     uint32_t *val_out;
     int64_t cap;
+    // range shards of ONE haystack: the chain enters the shard's first tile at offset entry0 (the exit offset
+    // of the shard before it); shard_map, when given, receives the shard's own composed map - for every entry offset
+    // 0..15: exit offset (relative to the end of the last tile) | matches << 8
+    uint32_t entry0;
+    unsigned long long *shard_map;
 };
 
 // word of one position p of a lane's sub-tile (all relative to the sub-tile start a):
@@ -228,8 +233,18 @@ __global__ void __launch_bounds__(1024, 1) k_sel2_top(const Sel2Args P) {
     extern __shared__ __align__(16) uint32_t s_gm[];
     for (int64_t i = threadIdx.x; i < P.n_groups * kS2Ent; i += blockDim.x) s_gm[i] = P.group_map[i];
     __syncthreads();
+    if (P.shard_map && threadIdx.x >= 32 && threadIdx.x < 32 + kS2Ent) {
+        uint32_t cur = threadIdx.x - 32u;
+        unsigned long long acc = 0;
+        for (int64_t g = 0; g < P.n_groups; g++) {
+            const uint32_t t = s_gm[g * kS2Ent + cur];
+            cur = t & 0xFFu;
+            acc += t >> 8;
+        }
+        P.shard_map[threadIdx.x - 32] = (unsigned long long)cur | (acc << 8);
+    }
     if (threadIdx.x == 0) {
-        uint32_t cur = 0;  // the chain starts at index 0 (entries before haystack position 0 are empty)
+        uint32_t cur = P.entry0;  // one-shot matches: index 0 (entries before haystack position 0 are empty)
         unsigned long long acc = 0;
         for (int64_t g = 0; g < P.n_groups; g++) {
             P.group_entry[g] = (uint8_t)cur;
@@ -240,6 +255,12 @@ __global__ void __launch_bounds__(1024, 1) k_sel2_top(const Sel2Args P) {
         }
         *P.total_out = acc;
     }
+}
+
+// zero the start masks of index positions [from, to): positions a chain entering further right must not see
+__global__ void k_sel2_zero_prefix(uint32_t *masks, int64_t from, int64_t to) {
+    unsigned short *m16 = reinterpret_cast<unsigned short *>(masks);
+    for (int64_t i = from + (int64_t)(blockIdx.x * blockDim.x + threadIdx.x); i < to; i += (int64_t)gridDim.x * blockDim.x) m16[i] = 0;
 }
 
 // one warp per group: every tile learns its entry offset and the index of its first record

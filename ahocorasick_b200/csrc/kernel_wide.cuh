@@ -1,0 +1,352 @@
+// AhoCorasick family for dictionaries OUTSIDE the narrow-alphabet envelope of kernel_mask.cuh (more than 32 character
+// classes - mixed-case, digits, Latin-1, ... - or keywords of 13..32 chars with 5-bit classes): the same three launches
+//
+//   k_wide_mask   every haystack position q is an END anchor (AhoCorasickSet.java:522-535: own match, then the
+//                 suffixMatch chain = the terminal nodes on the path of the reversed-keyword trie spelled by h[q], h[q-1], ...);
+//                 one 32-BIT hit mask per position (bit 32 - d = a keyword of length d ends here) + one count per 256-position row
+//   k_row_scan    (kernel_emit.cuh) exclusive scan of the row counts
+//   k_wide_emit   masks -> (start, end[, value]) records at their final offsets, position-major, longest first
+//
+// k_wide_mask: a warp owns chunks of 32 rows (tickets); a lane owns 8 consecutive positions of a row (one streaming 128-bit
+// load) and walks them IN LOCKSTEP, level by level, so that the 8 dependent gather chains of a lane overlap.  Levels 1 and 2
+// come from a direct-indexed class-pair table in shared memory (<= 64 classes), deeper levels from the open-addressing
+// edge table (device_tables.cuh::trie_step's layout; L2-resident).  Classes of the row and of the 32 chars before it sit in
+// a per-warp shared-memory window.
+#pragma once
+#include "kernel_emit.cuh"
+
+namespace acgpu {
+
+constexpr int kWideWarps = 8;
+constexpr int kWideThreads = kWideWarps * 32;
+constexpr int kWideMaxLen = 32;      // hit masks are 32 bits
+constexpr int kWideLockLevels = 5;   // levels walked in lockstep by the owning lane; deeper walks are compacted over the warp
+constexpr int kWidePairMax = 64;     // class-pair table: C * C * 8 bytes <= 32 KB of shared memory (3 CTAs per SM stay below the L1 carve-out cliff)
+
+struct DevWide {
+    const uint2 *pair;   // [C * C] (c0 * C + c1) -> {level-2 node or kNoneD, info2 | info1 << 8 | level-1 node exists << 16}; nullptr: no table
+    int32_t C;
+};
+
+struct WideArgs {
+    const uint16_t *hay;
+    int64_t n;
+    int64_t emit_from;      // positions (index of a keyword's last char) in [emit_from, emit_to) report
+    int64_t emit_to;
+    int64_t origin;         // first position of row 0: <= emit_from and hay + origin is 16-byte aligned
+    uint32_t *masks;        // [n_rows * 256] one word per position
+    uint32_t *row_count;    // [n_rows]
+    unsigned int *ticket;
+    int64_t n_rows;
+};
+
+__host__ __device__ constexpr size_t wide_smem_bytes(int C, bool pair) {
+    // classes 0..255 | pair table | per warp: class window (32 + 256 halfwords), deep-walk queue (256 nodes, 256 hit words, 256 positions)
+    return 512 + (pair ? (size_t)C * C * 8 : 0) + (size_t)kWideWarps * ((32 + kMaskRow) * 2 + kMaskRow * 9);
+}
+
+template <bool PAIR>
+__global__ void __launch_bounds__(kWideThreads) k_wide_mask(const DevAutomaton A, const DevWide Wd, const WideArgs P) {
+    extern __shared__ __align__(16) unsigned char s_wide[];
+    uint16_t *s_cls8 = reinterpret_cast<uint16_t *>(s_wide);                    // classes of code units 0..255
+    const uint2 *s_pair = reinterpret_cast<const uint2 *>(s_wide + 512);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = Wd.C;
+    unsigned char *s_warp = s_wide + 512 + (PAIR ? (size_t)C * C * 8 : 0) + (size_t)warp * ((32 + kMaskRow) * 2 + kMaskRow * 9);
+    uint32_t *q_node = reinterpret_cast<uint32_t *>(s_warp);
+    uint32_t *q_bits = q_node + kMaskRow;
+    uint16_t *w = reinterpret_cast<uint16_t *>(q_bits + kMaskRow);
+    uint8_t *q_pos = reinterpret_cast<uint8_t *>(w + 32 + kMaskRow);
+    for (int i = tid; i < 256; i += kWideThreads) s_cls8[i] = __ldg(&A.cls[i]);
+    if (PAIR) {
+        uint2 *dst = reinterpret_cast<uint2 *>(s_wide + 512);
+        for (int i = tid; i < C * C; i += kWideThreads) dst[i] = __ldg(&Wd.pair[i]);
+    }
+    __syncthreads();
+    const int max_len = min(A.max_len, kWideMaxLen);
+
+    auto class_of = [&](uint32_t ch) -> uint32_t { return ch < 256u ? (uint32_t)s_cls8[ch] : (uint32_t)__ldg(&A.cls[ch]); };
+
+    while (true) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(P.ticket, 1u);
+        chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
+        const int64_t row0 = (int64_t)chunk * kMaskChunkRows;
+        if (row0 >= P.n_rows) break;
+        const int n_cr = (int)min((int64_t)kMaskChunkRows, P.n_rows - row0);
+        const int64_t c_lo = P.origin + row0 * kMaskRow;
+        // the 32 classes before the chunk
+        {
+            const int64_t p = c_lo - 32 + lane;
+            __syncwarp();
+            w[lane] = (p >= 0 && p < P.n) ? (uint16_t)class_of(__ldg(&P.hay[p])) : (uint16_t)0;
+        }
+        for (int r = 0; r < n_cr; ++r) {
+            const int64_t p0 = c_lo + (int64_t)r * kMaskRow + (int64_t)lane * 8;
+            uint32_t ch[8];
+            if (p0 >= 0 && p0 + 8 <= P.n) {
+                const uint4 v = ldcs_v4_if(P.hay + p0, true);
+                ch[0] = v.x & 0xFFFFu; ch[1] = v.x >> 16; ch[2] = v.y & 0xFFFFu; ch[3] = v.y >> 16;
+                ch[4] = v.z & 0xFFFFu; ch[5] = v.z >> 16; ch[6] = v.w & 0xFFFFu; ch[7] = v.w >> 16;
+#pragma unroll
+                for (int j = 0; j < 8; j++) w[32 + lane * 8 + j] = (uint16_t)class_of(ch[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int64_t p = p0 + j;
+                    w[32 + lane * 8 + j] = (p >= 0 && p < P.n) ? (uint16_t)class_of(__ldg(&P.hay[p])) : (uint16_t)0;
+                }
+            }
+            __syncwarp();
+            // ---- the 8 anchored walks of the lane, in lockstep
+            const uint16_t *wp = w + 32 + lane * 8;  // wp[j - i] = class i positions before position j
+            uint32_t m[8], node[8];
+            uint32_t alive = 0;
+            int d0;  // first level the edge table serves
+            if (PAIR) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t c0 = wp[j], c1 = wp[j - 1];
+                    const uint2 e = s_pair[c0 * (uint32_t)C + c1];
+                    uint32_t mj = 0;
+                    if ((e.y >> 8) & kTerm) mj |= 1u << 31;
+                    node[j] = e.x;
+                    if (e.x != kNoneD && max_len >= 2) {
+                        if (e.y & kTerm) mj |= 1u << 30;
+                        if (e.y & kKids) alive |= 1u << j;
+                    }
+                    m[j] = mj;
+                }
+                d0 = 3;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t c0 = wp[j];
+                    uint32_t mj = 0;
+                    node[j] = kNoneD;
+                    if (c0 != 0u) {
+                        const uint2 rt = __ldg(&A.root[c0]);
+                        if (rt.x != kNoneD) {
+                            node[j] = rt.x;
+                            if (rt.y & kTerm) mj |= 1u << 31;
+                            if (rt.y & kKids) alive |= 1u << j;
+                        }
+                    }
+                    m[j] = mj;
+                }
+                d0 = 2;
+            }
+            const int d_lock = min(max_len, kWideLockLevels);
+            for (int d = d0; alive != 0u && d <= d_lock; ++d) {
+                // first probe of every live walk, issued back to back
+                uint4 e[8];
+                uint32_t slot[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t c = wp[j - d + 1];
+                    if (c == 0u) alive &= ~(1u << j);  // a char that is in no keyword ends every walk
+                    slot[j] = edge_hash_d(node[j], c) & A.edge_mask;
+                    e[j] = make_uint4(kNoneD, 0u, 0u, 0u);
+                    if ((alive >> j) & 1u) e[j] = __ldg(&A.edges[slot[j]]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (!((alive >> j) & 1u)) continue;
+                    const uint32_t c = wp[j - d + 1];
+                    uint4 ej = e[j];
+                    uint32_t i = slot[j];
+                    while (!(ej.x == node[j] && ej.y == c) && ej.x != kNoneD) {  // open addressing: the key sits further along
+                        i = (i + 1u) & A.edge_mask;
+                        ej = __ldg(&A.edges[i]);
+                    }
+                    if (ej.x == kNoneD) {
+                        alive &= ~(1u << j);
+                        continue;
+                    }
+                    node[j] = ej.z;
+                    if (ej.w & kTerm) m[j] |= 1u << (32 - d);
+                    if (!(ej.w & kKids)) alive &= ~(1u << j);
+                }
+            }
+            // ---- walks that are still alive (inside a long keyword: few) are compacted over the warp and finished one
+            //      walk per lane; their hits come back through the warp's shared-memory slots
+            if (max_len > d_lock) {
+                const uint32_t n_mine = (uint32_t)__popc(alive);
+                uint32_t inc = n_mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if (lane >= o) inc += y;
+                }
+                const uint32_t n_deep = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                if (n_deep) {
+                    uint32_t at = inc - n_mine;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if ((alive >> j) & 1u) {
+                            q_node[at] = node[j];
+                            q_pos[at] = (uint8_t)(lane * 8 + j);
+                            ++at;
+                        }
+                    }
+                    __syncwarp();
+                    for (uint32_t k = lane; k < n_deep; k += 32) {
+                        uint32_t nd = q_node[k], info = 0, bits = 0;
+                        const uint32_t pos = q_pos[k];
+                        const uint16_t *cp = w + 32 + pos;
+                        for (int d = d_lock + 1; d <= max_len; ++d) {
+                            const uint32_t c = cp[1 - d];
+                            if (c == 0u || !trie_step(A, nd, c, info)) break;
+                            if (info & kTerm) bits |= 1u << (32 - d);
+                            if (!(info & kKids)) break;
+                        }
+                        q_bits[pos] = bits;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        if ((alive >> j) & 1u) m[j] |= q_bits[lane * 8 + j];
+                }
+            }
+            // ---- positions outside [emit_from, emit_to) report nothing
+            if (p0 < P.emit_from || p0 + 8 > P.emit_to) {
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if (p0 + j < P.emit_from || p0 + j >= P.emit_to) m[j] = 0u;
+            }
+            uint4 *mp = reinterpret_cast<uint4 *>(P.masks + ((size_t)(row0 + r) * kMaskRow + (size_t)lane * 8));
+            mp[0] = make_uint4(m[0], m[1], m[2], m[3]);
+            mp[1] = make_uint4(m[4], m[5], m[6], m[7]);
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) cnt += __popc(m[j]);
+            const uint32_t row_total = __reduce_add_sync(0xFFFFFFFFu, cnt);
+            if (lane == 0) P.row_count[row0 + r] = row_total;
+            // ---- the last 32 classes of this row are the left context of the next
+            const uint16_t keep = w[kMaskRow + lane];
+            __syncwarp();
+            w[lane] = keep;
+        }
+    }
+}
+
+// value index of the keyword of length d whose last char is position q (Maps): the walk again, d steps
+__device__ __forceinline__ uint32_t wide_value(const DevAutomaton &A, const uint16_t *hay, int64_t q, int d) {
+    uint32_t node = 0, info = 0;
+    for (int i = 0; i < d; i++) {
+        if (!trie_step(A, node, (uint32_t)__ldg(&A.cls[__ldg(&hay[q - i])]), info)) return kNoneD;
+    }
+    return __ldg(&A.node_value[node]);
+}
+
+// code = row position << 5 | 32 - length  ->  (start, end); e_row = end of a keyword whose last char is row position 0
+__device__ __forceinline__ int2 decode_rec32(uint32_t code, int32_t e_row) {
+    const int32_t e = e_row + (int32_t)(code >> 5);
+    return make_int2(e - 32 + (int32_t)(code & 31u), e);
+}
+
+// Masks -> records, the 32-bit twin of k_tier_emit (kernel_emit.cuh): a warp takes rows round-robin, every lane expands the
+// bits of its 8 positions into 16-bit codes in shared memory (code = index of the bit in the row's 8 192-bit mask), then
+// the warp decodes two codes per lane into one 16-byte streaming store.
+template <bool kIsMap>
+__global__ void __launch_bounds__(kEmitWarps * 32) k_wide_emit(const DevAutomaton A, const EmitArgs E) {
+    __shared__ __align__(16) int2 s_stage_all[kEmitWarps][kEmitStage + 2];
+    __shared__ uint32_t s_val_all[kIsMap ? kEmitWarps : 1][kIsMap ? kEmitStage : 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int2 *s_stage = s_stage_all[warp];
+    const unsigned short *s_code = reinterpret_cast<const unsigned short *>(s_stage);
+    uint32_t *s_val = s_val_all[kIsMap ? warp : 0];
+    const int64_t stride = (int64_t)gridDim.x * kEmitWarps;
+    const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(s_stage);
+    const uint32_t out_par = (uint32_t)(reinterpret_cast<uintptr_t>(E.pos_out) >> 3) & 1u;
+
+    for (int64_t row = (int64_t)blockIdx.x * kEmitWarps + warp; row < E.n_rows; row += stride) {
+        const uint4 *mrow = reinterpret_cast<const uint4 *>(E.masks + ((size_t)row * kMaskRow + (size_t)lane * 8));
+        const uint4 ma = __ldcs(mrow), mb = __ldcs(mrow + 1);
+        const unsigned long long base = __ldg(E.block_excl + row / kScanRows) + __ldg(E.row_excl + row);
+        const uint32_t words[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) cnt += __popc(words[j]);
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        if (total == 0) continue;
+        const uint32_t my_off = inc - cnt;
+        const int64_t q_row = E.origin + row * kMaskRow;                       // position of the row's first char
+        const int32_t e_row = (int32_t)q_row + 1 + E.pos_base;
+        __syncwarp();
+        if (total <= (uint32_t)kEmitStage && base + total <= (unsigned long long)E.cap) {
+            const uint32_t par = ((uint32_t)base + out_par) & 1u;
+            uint32_t sa = stage_sa + (my_off + par) * 2u;
+            uint32_t cb = (uint32_t)lane * 256u;
+#pragma unroll
+            for (int wi = 0; wi < 8; wi++) {
+                uint32_t wv = words[wi];
+                while (wv) {
+                    const uint32_t t = (uint32_t)__clz((int)__brev(wv));
+                    wv &= wv - 1u;
+                    sts_u16(sa, cb + t);
+                    sa += 2u;
+                }
+                cb += 32u;
+            }
+            __syncwarp();
+            if (kIsMap) {
+                for (uint32_t r = lane; r < total; r += 32) {
+                    const uint32_t code = s_code[r + par];
+                    __stcs(E.val_out + base + r, wide_value(A, E.hay, q_row + (int64_t)(code >> 5), 32 - (int)(code & 31u)));
+                }
+            }
+            int2 *g = E.pos_out + (base - par);  // 16-byte aligned
+            const uint32_t end = par + total, k_hi = end >> 1;
+            if (lane == 0 && par) __stcs(g + 1, decode_rec32(s_code[1], e_row));
+            if (lane == 1 && (end & 1u)) __stcs(g + (end - 1u), decode_rec32(s_code[end - 1u], e_row));
+            int4 *gp = reinterpret_cast<int4 *>(g) + par + lane;
+            const uint32_t *sp = reinterpret_cast<const uint32_t *>(s_code) + par + lane;
+            for (uint32_t k = par + lane; k < k_hi; k += 32, gp += 32, sp += 32) {
+                const uint32_t cc = *sp;
+                const int2 r0 = decode_rec32(cc & 0xFFFFu, e_row), r1 = decode_rec32(cc >> 16, e_row);
+                __stcs(gp, make_int4(r0.x, r0.y, r1.x, r1.y));
+            }
+            __syncwarp();
+            continue;
+        }
+        // ---- dense rows (more than kEmitStage records) and rows that cross the caller's capacity: windows of kEmitStage
+        for (uint32_t win = 0; win < total; win += kEmitStage) {
+            if (cnt && my_off < win + kEmitStage && my_off + cnt > win) {
+                uint32_t o = my_off - win;  // wraps below zero for records of an earlier window
+#pragma unroll
+                for (int wi = 0; wi < 8; wi++) {
+                    uint32_t wv = words[wi];
+                    while (wv) {
+                        const int t = __ffs(wv) - 1;
+                        wv &= wv - 1u;
+                        if (o < (uint32_t)kEmitStage) {
+                            const int32_t e = e_row + lane * 8 + wi;
+                            s_stage[o] = make_int2(e - (32 - t), e);
+                            if (kIsMap) s_val[o] = wide_value(A, E.hay, q_row + lane * 8 + wi, 32 - t);
+                        }
+                        ++o;
+                    }
+                }
+            }
+            __syncwarp();
+            const uint32_t n_win = min((uint32_t)kEmitStage, total - win);
+            const unsigned long long g0 = base + win;
+            const unsigned long long room = g0 < (unsigned long long)E.cap ? (unsigned long long)E.cap - g0 : 0ull;
+            const uint32_t n_out = (uint32_t)min((unsigned long long)n_win, room);
+            for (uint32_t rr = lane; rr < n_out; rr += 32) {
+                __stcs(&E.pos_out[g0 + rr], s_stage[rr]);
+                if (kIsMap) __stcs(&E.val_out[g0 + rr], s_val[rr]);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace acgpu

@@ -12,7 +12,9 @@ left context), so a corpus shards with NO data-path collective:
 The WholeWord family shards the same way by word-START range (``plan_word_shards``).  Longest / Shortest carry a
 selection chain across positions; one haystack is cut at SYNCHRONISATION points - chars that occur in no keyword reset
 every reference automaton - into independent pieces (``plan_sync_shards``; exact, but needs such chars near the even
-split, else the haystack stays whole).  WholeWordLongest shards by haystack only.
+split, else the haystack stays whole) or - for ANY text, also one without such chars - into runs of whole tiles whose
+entry -> exit maps are exchanged and composed (``plan_chain_shards`` / ``compose_chain_maps``, acgpu_chain_shard_*).
+WholeWordLongest shards by haystack or at synchronisation points.
 
 The only exchange is an all-gather of per-rank match counts (8 bytes per rank) so that every rank knows its
 global record offset: ``exchange_counts`` (NCCL on device tensors, gloo on CPU tensors in the tests).
@@ -139,6 +141,71 @@ def match_sync_shard(matcher, d_haystack_ptr: int, shard: SyncShard, d_pos_ptr: 
     _lib.check(_lib.lib().acgpu_match_device(matcher.handle, d_haystack_ptr + 2 * shard.lo, n, 0, n, d_pos_ptr, d_val_ptr, cap,
                                              C.byref(tot), stream_ptr))
     return tot.value
+
+
+@dataclass(frozen=True)
+class ChainShard:
+    rank: int
+    lo: int        # first chain position (haystack position) this rank owns; the rank's window starts here
+    hi: int        # one past the last; every inner boundary is a multiple of the tile size
+    read_to: int   # the window is hay[lo, read_to): the domain plus the look-ahead
+
+    @property
+    def empty(self) -> bool:
+        return self.hi <= self.lo
+
+
+CHAIN_TILE, CHAIN_LOOKAHEAD, CHAIN_ENTRIES = 8192, 256, 16   # acgpu_chain_shard_layout()
+
+
+def plan_chain_shards(n_chars: int, world: int, tile: int = CHAIN_TILE, lookahead: int = CHAIN_LOOKAHEAD) -> List[ChainShard]:
+    """Longest / Shortest: cut ONE haystack into `world` runs of whole tiles.  Unlike plan_sync_shards this needs
+    nothing from the text: the selection chain that crosses every boundary is composed from the shards' entry -> exit maps
+    (compose_chain_maps).  Ranks beyond the last tile get empty shards."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    bounds = [0]
+    for r in range(1, world):
+        b = (n_chars * r // world + tile // 2) // tile * tile
+        if b + lookahead > n_chars:       # an inner shard needs its look-ahead inside the haystack
+            b = n_chars
+        bounds.append(max(bounds[-1], min(b, n_chars)))
+    bounds.append(n_chars)
+    for r in range(1, world):             # a boundary that fell back to n_chars closes the haystack: nothing after it
+        if bounds[r] == n_chars:
+            bounds[r + 1:] = [n_chars] * (world - r)
+            break
+    return [ChainShard(r, bounds[r], bounds[r + 1], bounds[r + 1] if bounds[r + 1] == n_chars else bounds[r + 1] + lookahead)
+            for r in range(world)]
+
+
+def compose_chain_maps(maps: Sequence[Sequence[int]]) -> Tuple[List[int], List[int], int]:
+    """maps[r][e] = (exit offset | matches << 8) of shard r entered at offset e (acgpu_chain_shard_begin; an EMPTY shard
+    contributes the identity map [0, 1, ..., 15]).  Returns (entry offset of every rank, index of every rank's first record,
+    total matches): entry_0 = 0, entry_{r+1} = exit offset of maps[r][entry_r]."""
+    entries, firsts, cur, acc = [], [], 0, 0
+    for mp in maps:
+        entries.append(cur)
+        firsts.append(acc)
+        t = int(mp[cur])
+        cur, acc = t & 0xFF, acc + (t >> 8)
+    return entries, firsts, acc
+
+
+def chain_shard_begin(matcher, d_window_ptr: int, n_window: int, n_domain: int, d_map_ptr: int, stream_ptr=None) -> int:
+    """Phase A of a chain shard (entry-independent): start masks of the window, the exit map of every tile, and the shard's
+    composed map into d_map_ptr (16 device uint64).  Returns the shard handle for chain_shard_finish."""
+    import ctypes as C
+    from . import _lib
+    h = C.c_uint64(0)
+    _lib.check(_lib.lib().acgpu_chain_shard_begin(matcher.handle, d_window_ptr, n_window, n_domain, d_map_ptr, C.byref(h), stream_ptr))
+    return h.value
+
+
+def chain_shard_finish(shard: int, entry: int, pos_base: int, d_pos_ptr: int, d_val_ptr, cap: int, d_total_ptr: int, stream_ptr=None):
+    """Phase B: the records of the shard for the chain entering at offset `entry`; positions are window positions + pos_base."""
+    from . import _lib
+    _lib.check(_lib.lib().acgpu_chain_shard_finish(shard, entry, pos_base, d_pos_ptr, d_val_ptr, cap, d_total_ptr, stream_ptr))
 
 
 def deal_haystacks(n_haystacks: int, world: int, rank: int) -> List[int]:

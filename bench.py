@@ -45,8 +45,13 @@ def parse_args():
     ap.add_argument("--haystacks", type=int, default=32, help="haystacks in the corpus (total over all ranks)")
     ap.add_argument("--chars", type=int, default=1_000_000_000, help="UTF-16 chars per haystack")
     ap.add_argument("--keywords", type=int, default=1_000_000)
-    ap.add_argument("--e2e-chars", type=int, default=250_000_000)
+    ap.add_argument("--e2e-chars", type=int, default=1_000_000_000, help="chars of the end-to-end haystack (default: a full haystack)")
+    ap.add_argument("--no-replay", action="store_true", help="skip the e2e leg with the counting listener (C++ mirror)")
     ap.add_argument("--cpu-sample-chars", type=int, default=16_000_000, help="chars per host thread per CPU pass")
+    ap.add_argument("--shard", default="haystack", choices=["haystack", "range"],
+                    help="haystack: the corpus' haystacks are dealt to the ranks (default); range: EVERY haystack is cut by end-position "
+                         "range across the ranks (plan_range_shards), each rank holds only its slice, the per-shard match counts are "
+                         "all-gathered inside the timed region and the rank-ordered stream is checked against the single-GPU stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -129,6 +134,35 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- e2e with listener replay (C++ mirror)
+
+def replay_measure(kws, host, ne, device, steps):
+    """AhoCorasickSet.match(String, SetMatchListener) through include/acgpu.hpp with a counting listener (tools/e2e_replay.cpp)."""
+    from ahocorasick_b200 import _lib
+    src = os.path.join(ROOT, "tools", "e2e_replay.cpp")
+    so = os.path.join(ROOT, "tools", "libe2e_replay.so")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    deps = [src, os.path.join(ROOT, "include", "acgpu.hpp"), os.path.join(ROOT, "include", "acgpu.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", src, "-I" + os.path.join(ROOT, "include"),
+                               "-L" + libdir, "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir, "-o", so])
+    shim = C.CDLL(so)
+    shim.e2e_replay_count.restype = C.c_double
+    shim.e2e_replay_count.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_int64)]
+    chars, offsets = W.keywords_to_arrays(kws)
+    chars = np.ascontiguousarray(chars)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    matches = C.c_int64(0)
+    secs = shim.e2e_replay_count(chars.ctypes.data, offsets.ctypes.data, len(kws), host.data_ptr(), ne, device, 1, steps,
+                                 C.byref(matches))
+    if secs < 0:
+        raise RuntimeError("e2e_replay_count failed")
+    return {"value": ne * 2 / secs / 1e9, "unit": UNIT, "ms_per_call": secs * 1e3, "listener_calls_per_call": matches.value,
+            "steps": steps, "note": "acgpu::AhoCorasickSet::match(String, counting listener) - include/acgpu.hpp; one host thread "
+                                    "replays every match"}
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -295,31 +329,44 @@ def run_ours(args):
                 "haystack_only_frac": (2 * n / (launch_ms * 1e-3) / 1e9) / peak,
                 "frac_of_nominal_8000": achieved / 8000.0}  # also against the nominal HBM3e figure
 
-    # end-to-end through the host-buffer C-ABI call (H2D + kernels + D2H inside the timed region)
+    # end-to-end through the host-buffer C-ABI call a user of the mirrors makes (acgpu_match_utf16_compact): H2D of the
+    # haystack from pinned memory, kernels, D2H of the match stream, all inside the timed region; one FULL haystack of the
+    # config per call, --steps calls after 2 warm-up calls
     e2e = None
     if not args.no_e2e:
-        ne = min(n, args.e2e_chars)
-        spec0 = W.HaystackSpec("lower", 2005 + (mine[0] if mine else 0), kws)
+        ne = min(n, args.e2e_chars, 0x7FFFFFFF)
         host = torch.empty(ne, dtype=torch.int16, pin_memory=True)
-        host.copy_(W.make_haystack_torch(spec0, ne, device=dev).cpu())
-        res = _lib.Result()
-        times, n_rec = [], 0
-        for it in range(3):
+        host.copy_(hays[0][:ne] if hays else W.make_haystack_torch(W.HaystackSpec("lower", 2005, kws), ne, device=dev))
+        torch.cuda.synchronize()
+        res = _lib.Matches()
+        times, n_rec, kind = [], 0, 0
+        e2e_steps = max(1, args.steps)
+        for it in range(2 + e2e_steps):
             barrier()
             t0 = time.perf_counter()
-            _lib.check(lib.acgpu_match_utf16(matcher.handle, host.data_ptr(), ne, C.byref(res)))
+            _lib.check(lib.acgpu_match_utf16_compact(matcher.handle, host.data_ptr(), ne, C.byref(res)))
             dt = time.perf_counter() - t0
-            n_rec = int(res.n)
-            lib.acgpu_free_result(C.byref(res))
-            if it > 0:
+            n_rec, kind = int(res.n), int(res.kind)
+            lib.acgpu_free_matches(C.byref(res))
+            if it >= 2:
                 times.append(dt)
         t_e = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        d2h = ne * 2 if kind == _lib.MATCHES_MASKS else n_rec * 8
         e2e = {"value": world * ne * 2 / float(t_e.item()) / 1e9, "unit": UNIT, "h2d_bytes_per_step": ne * 2,
-               "d2h_bytes_per_step": n_rec * 8,
-               "note": "acgpu_match_utf16 on one %d-char haystack per rank from pinned host memory, "
-                       "records copied back to host; mean of 2 after 1 warm-up" % ne}
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_call": float(t_e.item()) * 1e3,
+               "matches_per_call": n_rec, "wire_format": "hit masks, 2 B/char" if kind == _lib.MATCHES_MASKS else "records, 8 B/match",
+               "note": "acgpu_match_utf16_compact on one %d-char haystack per rank from pinned host memory, match stream "
+                       "copied back to pinned host memory; mean of %d calls after 2 warm-ups (max over ranks)" % (ne, e2e_steps)}
+        # the same call through the C++ mirror of the reference API with a counting SetMatchListener: + one listener call
+        # per match on one host thread (what the CPU arm pays inside its loop)
+        if rank == 0 and world == 1 and not args.no_replay:
+            try:
+                e2e["with_replay"] = replay_measure(kws, host, ne, local_rank, max(1, min(2, args.steps)))
+            except Exception as exc:  # the shim needs g++; the headline does not depend on it
+                e2e["with_replay"] = {"error": str(exc)[:200]}
+        del host
 
     cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -343,10 +390,136 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_range(args):
+    """--shard range (SURVEY 8e / north_star: "large corpora shard by byte range across the GPUs of one box with boundary
+    overlap; NCCL only all-gathers per-shard match counts and offsets").  Every haystack of the corpus is ONE match() whose
+    end positions are cut into `world` ranges; rank r generates and holds only chars [read_from, emit_to) of each haystack."""
+    import torch
+    import torch.distributed as dist
+    import ahocorasick_b200 as ac
+    from ahocorasick_b200 import _lib
+    from ahocorasick_b200.sharding import plan_range_shards
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    cfg = W.config(4, scale=args.keywords / 1_000_000)
+    kws = cfg["keywords"]
+    matcher = ac.AhoCorasickSet(kws, True, device=local_rank)
+    max_len = matcher.info()["max_len"]
+    n = args.chars
+    shard = plan_range_shards(n, world, max_len, align=64)[rank]
+    s0 = shard.read_from // W.BLOCK * W.BLOCK        # the generator starts at multiples of its block; extra chars are context only
+    n_loc = shard.emit_to - s0
+    hays = [W.make_haystack_torch(W.HaystackSpec("lower", 2005 + i, kws), n_loc, start=s0, device=dev) for i in range(args.haystacks)]
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+    counts = []
+    for h in hays:
+        tot = C.c_int64(0)
+        _lib.check(lib.acgpu_match_device(matcher.handle, h.data_ptr(), n_loc, shard.emit_from - s0, shard.emit_to - s0, None, None, 0,
+                                          C.byref(tot), sp))
+        counts.append(tot.value)
+    cap = max(counts + [1])
+    d_pos = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+    d_tot = torch.zeros(len(hays), dtype=torch.int64, device=dev)
+    gathered = torch.zeros((len(hays), world), dtype=torch.int64, device=dev)
+
+    def step():
+        for j, h in enumerate(hays):
+            _lib.check(lib.acgpu_match_device_async(matcher.handle, h.data_ptr(), n_loc, shard.emit_from - s0, shard.emit_to - s0,
+                                                    d_pos.data_ptr(), None, cap, d_tot[j:].data_ptr(), sp))
+            if world > 1:  # every rank learns every shard's count (its global record offset = the sum of the lower ranks')
+                dist.all_gather_into_tensor(gathered[j], d_tot[j:j + 1])
+            else:
+                gathered[j] = d_tot[j:j + 1]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t_ms.item()) / args.steps
+    per_shard = gathered.cpu().tolist()
+    assert [row[rank] for row in per_shard] == counts, "match counts changed between runs"
+    total_matches = int(sum(sum(row) for row in per_shard))
+
+    # ---- the rank-ordered concatenation is the single-GPU stream: a position-weighted checksum of the LAST haystack's
+    #      records (positions shifted to the whole haystack, offsets from the gathered counts) against rank 0 scanning
+    #      that whole haystack alone
+    def checksum(pos, first_index, shift):
+        if pos.shape[0] == 0:
+            return torch.zeros(3, dtype=torch.int64, device=dev)
+        idx = torch.arange(first_index, first_index + pos.shape[0], dtype=torch.int64, device=dev)
+        st, en = pos[:, 0].long() + shift, pos[:, 1].long() + shift
+        mix = (st * 1_000_003 + en * 7_919 + 1) * ((idx % 1_000_033) + 1)   # wraps mod 2^64: order-sensitive
+        return torch.stack([torch.tensor(pos.shape[0], dtype=torch.int64, device=dev), mix.sum(), (st ^ (en << 20)).sum()])
+
+    last = len(hays) - 1
+    offset = int(sum(per_shard[last][:rank]))
+    mine = checksum(d_pos[:counts[last]], offset, s0)
+    if world > 1:
+        dist.all_reduce(mine, op=dist.ReduceOp.SUM)
+    check = None
+    if rank == 0:
+        del hays[:-1]
+        whole = W.make_haystack_torch(W.HaystackSpec("lower", 2005 + last, kws), n, device=dev)
+        tot = C.c_int64(0)
+        _lib.check(lib.acgpu_match_device(matcher.handle, whole.data_ptr(), n, 0, n, None, None, 0, C.byref(tot), sp))
+        d_all = torch.empty((max(tot.value, 1), 2), dtype=torch.int32, device=dev)
+        _lib.check(lib.acgpu_match_device(matcher.handle, whole.data_ptr(), n, 0, n, d_all.data_ptr(), None, tot.value, C.byref(tot), sp))
+        ref = checksum(d_all[:tot.value], 0, 0)
+        check = bool(torch.equal(ref, mine))
+        if not check:
+            raise SystemExit("bench.py --shard range: the sharded stream differs from the single-GPU stream: %r vs %r" % (mine.tolist(), ref.tolist()))
+    if rank == 0:
+        total_chars = args.haystacks * n
+        line = {
+            "metric": METRIC, "value": total_chars * 2 / (ms_per_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u16", "data": "synthetic",
+            "config": dict(workload_config(args), sharding="every haystack cut by END-position range across %d ranks (boundaries aligned "
+                           "to 64 chars, %d chars of left context per shard); one NCCL all-gather of the shard counts per haystack INSIDE "
+                           "the timed region" % (world, max_len - 1)),
+            "matches_per_s": total_matches / (ms_per_step * 1e-3), "matches_per_step": total_matches, "clocks": clocks,
+            "gpu_launches": lib.acgpu_launches_per_match(matcher.handle) * args.haystacks * args.steps,
+            "collectives_per_step": args.haystacks if world > 1 else 0,
+            "range_shard_stream_equals_single_gpu_stream": check, "shard_counts_last_haystack": per_shard[last],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.shard == "range":
+        run_range(args)
     else:
         run_ours(args)
 

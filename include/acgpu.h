@@ -156,6 +156,31 @@ int64_t acgpu_masks_to_records(const uint16_t *masks, int64_t n_chars, int64_t f
 int acgpu_match_device(uint64_t handle, const void *d_haystack, int64_t n, int64_t emit_from, int64_t emit_to,
                        void *d_pos, void *d_val, int64_t cap, int64_t *n_out, void *cuda_stream);
 
+/*
+ * Longest / Shortest: range shards of ONE resident haystack.  The reference's selection state crosses any
+ * cut (LongestMatchSet.java:192-265 + SetMatchQueue.java:45-95, ShortestMatchSet.java:182-260): it is the position the
+ * scan has consumed up to ("chain position").  A shard's effect on it is a small map - for each of the 16 possible entry
+ * offsets: where the chain leaves the shard and how many matches it emits on the way - so shards scan in parallel,
+ * exchange their maps (they ride in the all-gather of the counts) and then emit from their true entry:
+ *
+ *   rank r:  acgpu_chain_shard_begin(h, d_window_r, n_r, n_domain_r, d_map_r, &s, stream)      (entry-independent work)
+ *            all-gather d_map (16 x uint64 per rank: exit offset | matches << 8)
+ *            entry_0 = 0;  entry_{r+1} = exit offset of map_r[entry_r];  first record of rank r = sum of the matches before
+ *            acgpu_chain_shard_finish(s, entry_r, pos_base_r, d_pos, d_val, cap, d_total, stream)
+ *
+ * Geometry (acgpu_chain_shard_layout): shard r owns the chain positions [lo_r, hi_r) of the haystack; its window is
+ * hay[lo_r, min(N, hi_r + lookahead)) in a 16-byte aligned device buffer of its own; lo_0 = 0 and every inner boundary
+ * is a multiple of tile_chars (ahocorasick_b200/sharding.py::plan_chain_shards).  n_domain = hi_r - lo_r, or n for the
+ * last shard.  Entry / exit offsets are relative to lo_r / hi_r and smaller than map_entries (a match is at most 16 chars).
+ * Records are positions in the window plus pos_base (pass lo_r for haystack positions).  finish() releases the shard.
+ * Needs the start-mask path (at most 31 keyword symbols, keywords of at most 16 chars): ACGPU_EUNSUPPORTED otherwise.
+ */
+int acgpu_chain_shard_layout(uint64_t handle, int64_t *tile_chars, int64_t *lookahead_chars, int32_t *map_entries);
+int acgpu_chain_shard_begin(uint64_t handle, const void *d_window, int64_t n, int64_t n_domain, void *d_map16, uint64_t *shard,
+                            void *cuda_stream);
+int acgpu_chain_shard_finish(uint64_t shard, int32_t entry, int32_t pos_base, void *d_pos, void *d_val, int64_t cap, void *d_total,
+                             void *cuda_stream);
+
 /* Async flavour for benchmarking: enqueues the kernels only; the total lands in *d_total (device int64). */
 int acgpu_match_device_async(uint64_t handle, const void *d_haystack, int64_t n, int64_t emit_from,
                              int64_t emit_to, void *d_pos, void *d_val, int64_t cap, void *d_total,

@@ -144,6 +144,13 @@ int acgpu_match_device_async(uint64_t, const void *, int64_t, int64_t, int64_t, 
     return fail(ACGPU_ENODEVICE, "mock: no device entry points");
 }
 int acgpu_launches_per_match(uint64_t) { return 0; }
+int acgpu_chain_shard_layout(uint64_t, int64_t *, int64_t *, int32_t *) { return fail(ACGPU_ENODEVICE, "mock: no device entry points"); }
+int acgpu_chain_shard_begin(uint64_t, const void *, int64_t, int64_t, void *, uint64_t *, void *) {
+    return fail(ACGPU_ENODEVICE, "mock: no device entry points");
+}
+int acgpu_chain_shard_finish(uint64_t, int32_t, int32_t, void *, void *, int64_t, void *, void *) {
+    return fail(ACGPU_ENODEVICE, "mock: no device entry points");
+}
 // Readable: every feed is buffered and reports nothing; end() reports the whole stream (a legal split of "the records
 // that are final so far"), positions as stream offsets.
 int acgpu_stream_begin(uint64_t h, uint64_t *s) {

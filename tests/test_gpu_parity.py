@@ -749,3 +749,332 @@ def test_concurrent_match_on_one_instance(family):
     if errors:
         raise errors[0]
     assert sum(len(w) for w in want) > 1000
+
+
+# ---------------------------------------------------------------- compact wire format (acgpu_match_utf16_compact)
+
+def _compact_raw(m, hay):
+    """(kind, n, records) of one acgpu_match_utf16_compact call."""
+    import ctypes as C
+    from ahocorasick_b200 import _lib
+    from ahocorasick_b200.matchers import _Records
+    arr = hay if isinstance(hay, np.ndarray) else np.frombuffer(hay.encode("utf-16-le"), dtype=np.uint16)
+    res = _lib.Matches()
+    _lib.check(_lib.lib().acgpu_match_utf16_compact(m.handle, arr.ctypes.data if arr.size else None, arr.size, C.byref(res)))
+    try:
+        kind, n = int(res.kind), int(res.n)
+        if kind == _lib.MATCHES_MASKS:
+            assert int(res.n_chars) == arr.size
+        rec = _Records(res, False)
+        return kind, n, rec
+    finally:
+        _lib.lib().acgpu_free_matches(C.byref(res))
+
+
+def test_compact_masks_equal_records_and_oracle():
+    """Dense AhoCorasickSet streams come back as per-char hit masks (2 B/char on the wire); expanded in the mirror they
+    must be the very stream acgpu_match_utf16 returns as records and the oracle's - across 8 Mi-char pipeline chunks,
+    odd lengths and unaligned host pointers.  Sparse streams and Maps stay records."""
+    from ahocorasick_b200 import _lib
+    rng = random.Random(5150)
+    kws = ["a", "ab", "ba", "bab", "abba", "b" * 7, "ab" * 8, "a" * 16, "bbbab"]
+    gs = ac.AhoCorasickSet(kws, True)
+    om = ora.Matcher("ahocorasick", kws)
+    big = np.frombuffer("".join(rng.choice("ab ") for _ in range(1 << 16)).encode("utf-16-le"), dtype=np.uint16)
+    big = np.tile(big, 300)[: (2 << 23) + 12_347]            # two full pipeline chunks and a ragged third
+    big = big.copy()
+    big[rng.randrange(big.size)] = ord("b")
+    for n, off in ((1, 0), (7, 0), (255, 0), (70_001, 0), (70_001, 1), (70_001, 3), (big.size, 0), (big.size - 5, 5)):
+        hay = big[off:off + n]
+        kind, cnt, rec = _compact_raw(gs, hay)
+        plain = gs.match_records(hay, compact=False)
+        first = min(n, 1 << 23)  # the first pipeline chunk decides the wire format
+        dense = int((plain.end <= first).sum()) >= 0.25 * first
+        assert (kind == _lib.MATCHES_MASKS) == dense, (n, off)
+        assert n < 255 or dense
+        assert cnt == len(plain) == len(rec), (n, off, cnt, len(plain))
+        assert np.array_equal(rec.start, plain.start) and np.array_equal(rec.end, plain.end), (n, off)
+        if n <= 70_001:
+            want = om.match(hay, cap=4 * n + 16)
+            assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"]), (n, off)
+    want = om.match(big, cap=2 * big.size)
+    rec = gs.match_records(big)
+    assert len(rec) == len(want) and np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"])
+    # listener replay through the mirror: early stop inside a position's records (longest first)
+    hay = "abbab" * 3
+    full = [(s, e) for s, e, _ in oracle_stream(om, hay)]
+    for k in range(1, len(full) + 2):
+        assert gpu_set_stream(gs, hay, stop_after=k) == full[:k]
+    # sparse stream: records on the wire
+    sparse = ac.AhoCorasickSet(["abbab", "bbbbbbb"], True)
+    kind, cnt, rec = _compact_raw(sparse, big[:500_000])
+    assert kind == _lib.MATCHES_RECORDS and cnt == len(sparse.match_records(big[:500_000], compact=False))
+    # empty haystack, empty dictionary
+    kind, cnt, _ = _compact_raw(gs, big[:0])
+    assert cnt == 0
+    kind, cnt, _ = _compact_raw(ac.AhoCorasickSet([], True), big[:1000])
+    assert cnt == 0 and kind == _lib.MATCHES_RECORDS
+
+
+def test_compact_call_for_maps_and_other_families_is_records():
+    from ahocorasick_b200 import _lib
+    kws = ["a", "ab", "ba", "bab"]
+    hay = "abbab ab" * 5000
+    for fam in FAMILIES:
+        m = SETS[fam](kws, True)
+        kind, cnt, rec = _compact_raw(m, hay)
+        want = oracle_stream(ora.Matcher(fam, kws), hay)
+        assert (kind == _lib.MATCHES_MASKS) == (fam == "ahocorasick")
+        assert list(zip(rec.start.tolist(), rec.end.tolist())) == [(s, e) for s, e, _ in want], fam
+    gm = ac.AhoCorasickMap(kws, list(range(4)), True)
+    assert gpu_map_stream(gm, hay) == oracle_stream(ora.Matcher("ahocorasick", kws, n_values=4), hay)
+
+
+# ---------------------------------------------------------------- AhoCorasick outside the narrow-alphabet envelope (kernel_wide.cuh)
+
+def _launches(m):
+    from ahocorasick_b200 import _lib
+    return _lib.lib().acgpu_launches_per_match(m.handle)
+
+
+@pytest.mark.parametrize("alphabet,max_kw", [
+    ("abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ'", 24),          # 53 symbols: class-pair table in shared memory
+    ("abcdefghijklmnopqrstuvwxyz", 32),                                      # 26 symbols, keywords longer than 12: 32-bit masks
+    ("".join(chr(c) for c in range(0x30, 0x30 + 70)) + "αβγδεжзий", 9),      # 79 symbols incl. Greek / Cyrillic: no pair table
+    ("".join(chr(c) for c in range(0x400, 0x400 + 200)), 5),                 # 200 symbols beyond Latin-1
+])
+def test_wide_path_alphabets_and_boundary_lengths(alphabet, max_kw):
+    """Dictionaries the tier path cannot take (more than 31 symbols, keywords of 13..32 chars) run k_wide_mask / k_wide_emit:
+    Set and Map streams equal the oracle's for haystack lengths that straddle lane, row and chunk boundaries, for
+    case-insensitive matching, end-range shards and the Readable overload."""
+    rng = random.Random(len(alphabet) * 1000 + max_kw)
+    kws = sorted({_rand_word(rng, alphabet, 1, max_kw) for _ in range(600)})
+    kws += [alphabet[0] * k for k in (1, 2, max_kw)] + [alphabet[:max_kw]]
+    values = list(range(len(kws)))
+    om = ora.Matcher("ahocorasick", kws, n_values=len(kws))
+    gs, gm = ac.AhoCorasickSet(kws, True), ac.AhoCorasickMap(kws, values, True)
+    assert _launches(gs) == 3 and _launches(gm) == 3          # mask, scan, emit - not the generation-1 single kernel
+    base = [rng.choice(alphabet + "  ") for _ in range(70_001)]
+    for _ in range(1500):
+        k = rng.choice(kws)
+        at = rng.randrange(0, len(base) - len(k))
+        base[at:at + len(k)] = k
+    base = "".join(base)
+    for n in (0, 1, 7, 8, 9, 31, 32, 33, 255, 256, 257, 8191, 8192, 8193, 70_001):
+        hay = base[:n]
+        want = oracle_stream(om, hay)
+        pos, _ = _records(gs, hay)
+        assert pos == [(s, e) for s, e, _ in want], (n,)
+        pos, val = _records(gm, hay)
+        assert pos == [(s, e) for s, e, _ in want] and [int(v) for v in val] == [v for _, _, v in want], (n,)
+    # unaligned host pointer, case-insensitive twin, Readable
+    arr = np.frombuffer(base.encode("utf-16-le"), dtype=np.uint16)
+    for off in (1, 3, 5):
+        want = om.match(arr[off:], cap=1 << 20)
+        rec = gm.match_records(arr[off:])
+        assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"]) and \
+            np.array_equal(rec.value.astype(np.int64), want["value"].astype(np.int64))
+    oi = ora.Matcher("ahocorasick", kws, n_values=len(kws), case_sensitive=False)
+    gi = ac.AhoCorasickMap(kws, values, False)
+    mixed = "".join(c.upper() if rng.random() < 0.3 else c for c in base)
+    assert gpu_map_stream(gi, mixed) == oracle_stream(oi, mixed)
+    c = Collect()
+    gm.match(io.StringIO(base), c)
+    assert [v[0] for v in c.calls] == [int(r["value"]) for r in om.match(base, readable=True)]
+
+
+def test_wide_path_dense_rows_and_range_shards():
+    """a^1..a^32 over 'aaaa...' emits 32 records per position (rows overflow the staging window of k_wide_emit); end-range
+    shards of a resident haystack concatenate to the single stream; a capacity below the total truncates the stream only."""
+    import ctypes as C
+    import torch
+    from ahocorasick_b200 import _lib
+    from ahocorasick_b200.sharding import plan_range_shards
+    kws = ["a" * i for i in range(1, 33)] + ["ab", "ba" * 9, "b" * 21, "abAB", "Zz"]
+    hay = "a" * 2100 + "b" * 40 + ("ab" * 700) + "abABZz" * 50 + "a" * 513
+    want = ora.Matcher("ahocorasick", kws, n_values=len(kws)).match(hay, cap=1 << 18)
+    gs, gm = ac.AhoCorasickSet(kws, True), ac.AhoCorasickMap(kws, list(range(len(kws))), True)
+    assert _launches(gs) == 3
+    rec = gs.match_records(hay)
+    assert len(rec) == len(want) > 60_000 and np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"])
+    rec = gm.match_records(hay)
+    assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.value.astype(np.int64), want["value"].astype(np.int64))
+    arr = np.frombuffer(hay.encode("utf-16-le"), dtype=np.uint16)
+    d_hay = torch.from_numpy(arr.astype(np.int16)).cuda()
+    d_pos = torch.empty((len(want) + 16, 2), dtype=torch.int32, device="cuda")
+    want_pos = np.stack([want["start"], want["end"]], axis=1).astype(np.int32)
+    lib = _lib.lib()
+
+    def run(lo, hi, cap):
+        tot = C.c_int64(0)
+        _lib.check(lib.acgpu_match_device(gs.handle, d_hay.data_ptr(), arr.size, lo, hi, d_pos.data_ptr(), None, cap, C.byref(tot), None))
+        torch.cuda.synchronize()
+        return tot.value, d_pos[:min(tot.value, cap)].cpu().numpy()
+
+    for world in (2, 3, 8):
+        parts = [run(sh.emit_from, sh.emit_to, len(want) + 16)[1].copy()
+                 for sh in plan_range_shards(arr.size, world, max_len=32, align=1 if world == 3 else 8)]
+        got = np.concatenate(parts, axis=0)
+        assert got.shape == want_pos.shape and np.array_equal(got, want_pos), world
+    total, part = run(0, arr.size, 1000)
+    assert total == len(want) and np.array_equal(part, want_pos[:1000])
+
+
+@pytest.mark.parametrize("scale,n", [(0.1, 2_000_000), (1.0, 4_000_000)])
+def test_wide_path_real_dictionary(scale, n):
+    """workloads.config(5): 236 000 English-like words (1-24 chars, mixed case, apostrophes - the reference's README quotes a
+    235 886-word English dictionary) over English-like text, case-sensitive: Set and Map streams equal the oracle's."""
+    c = W.config(5, scale=scale)
+    kws = c["keywords"]
+    hay = W.make_haystack(c["spec"], n)
+    want = ora.Matcher("ahocorasick", kws, n_values=len(kws)).match(hay, cap=2 * n)
+    gs = ac.AhoCorasickSet(kws, True)
+    assert _launches(gs) == 3 and gs.info()["n_classes"] == 54 and gs.info()["max_len"] == 24
+    rec = gs.match_records(hay)
+    assert len(rec) == len(want) > n // 2
+    assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"])
+    rec = ac.AhoCorasickMap(kws, list(range(len(kws))), True).match_records(hay)
+    assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"])
+    assert np.array_equal(rec.value.astype(np.int64), want["value"].astype(np.int64))
+
+
+# ---------------------------------------------------------------- Longest / Shortest: range shards with composed chain maps
+
+@pytest.mark.parametrize("family,is_map", [("longest", False), ("longest", True), ("shortest", False), ("shortest", True)])
+@pytest.mark.parametrize("text", ["periodic", "random", "sparse"])
+def test_chain_shards_compose_to_the_single_stream(family, is_map, text):
+    """SURVEY 8e, general cut: ONE haystack with NO synchronisation point (every char occurs in a keyword; the periodic
+    text has interleaved chains that never merge) is cut into runs of whole tiles; every shard scans its own window
+    (a separate device buffer holding only [lo, hi + look-ahead)), the 16-entry maps are composed, every shard emits from
+    its true entry - the rank-ordered concatenation is the oracle's stream, values included."""
+    import ctypes as C
+    import torch
+    from ahocorasick_b200 import _lib
+    from ahocorasick_b200.sharding import (CHAIN_ENTRIES, chain_shard_begin, chain_shard_finish, compose_chain_maps,
+                                           plan_chain_shards)
+    rng = random.Random(hash((family, is_map, text)) & 0xFFFF)
+    n = 8192 * 9 + 1234
+    if text == "periodic":
+        kws = ["ab", "ba", "aba", "bab", "abab", "b" * 5]
+        hay = ("ab" * (n // 2 + 1))[:n]
+    elif text == "random":
+        kws = sorted({_rand_word(rng, "abc", 1, 9) for _ in range(60)}) + ["a" * 16, "cab" * 5]
+        hay = "".join(rng.choice("abc") for _ in range(n))
+    else:
+        kws = sorted({_rand_word(rng, "abcdefgh", 3, 12) for _ in range(40)})
+        base = [rng.choice("abcdefgh") for _ in range(n)]
+        for _ in range(n // 40):
+            k = rng.choice(kws)
+            at = rng.randrange(0, n - len(k))
+            base[at:at + len(k)] = k
+        hay = "".join(base)
+    arr = np.frombuffer(hay.encode("utf-16-le"), dtype=np.uint16)
+    want = ora.Matcher(family, kws, n_values=len(kws) if is_map else -1).match(hay, cap=n)
+    want_pos = np.stack([want["start"], want["end"]], axis=1).astype(np.int64)
+    m = (MAPS if is_map else SETS)[family](*((kws, list(range(len(kws))), True) if is_map else (kws, True)))
+    classes, has_other = m.char_classes()
+    assert all(classes[ord(c)] != 0 for c in set(hay))            # no synchronisation point anywhere
+    tile, look, ent = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+    _lib.check(_lib.lib().acgpu_chain_shard_layout(m.handle, C.byref(tile), C.byref(look), C.byref(ent)))
+    assert (tile.value, look.value, ent.value) == (8192, 256, CHAIN_ENTRIES)
+    cap = len(want) + 16
+    for world in (1, 2, 3, 5, 9, 12):
+        shards = plan_chain_shards(n, world)
+        assert len(shards) == world and shards[0].lo == 0 and shards[-1].hi == n
+        handles, maps, bufs = [], [], []
+        for sh in shards:
+            if sh.empty:
+                handles.append(None)
+                maps.append(list(range(CHAIN_ENTRIES)))
+                continue
+            d_win = torch.from_numpy(arr[sh.lo:sh.read_to].astype(np.int16)).cuda()     # the rank's own buffer
+            d_map = torch.zeros(CHAIN_ENTRIES, dtype=torch.int64, device="cuda")
+            n_dom = sh.hi - sh.lo if sh.hi < n else sh.read_to - sh.lo
+            handles.append(chain_shard_begin(m, d_win.data_ptr(), sh.read_to - sh.lo, n_dom, d_map.data_ptr()))
+            bufs.append((d_win, d_map))
+            torch.cuda.synchronize()
+            maps.append(d_map.cpu().tolist())
+        entries, firsts, total = compose_chain_maps(maps)
+        assert total == len(want), (world, total, len(want))
+        pos_parts, val_parts = [], []
+        for sh, h, entry, first in zip(shards, handles, entries, firsts):
+            if h is None:
+                continue
+            d_pos = torch.empty((cap, 2), dtype=torch.int32, device="cuda")
+            d_val = torch.empty(cap, dtype=torch.int32, device="cuda")
+            d_tot = torch.zeros(1, dtype=torch.int64, device="cuda")
+            chain_shard_finish(h, entry, sh.lo, d_pos.data_ptr(), d_val.data_ptr() if is_map else None, cap, d_tot.data_ptr())
+            torch.cuda.synchronize()
+            k = int(d_tot.item())
+            assert first == sum(p.shape[0] for p in pos_parts)
+            pos_parts.append(d_pos[:k].cpu().numpy().astype(np.int64))
+            val_parts.append(d_val[:k].cpu().numpy().astype(np.int64))
+        got = np.concatenate(pos_parts, axis=0)
+        assert got.shape == want_pos.shape and np.array_equal(got, want_pos), (world, family, text)
+        if is_map:
+            assert np.array_equal(np.concatenate(val_parts), want["value"].astype(np.int64)), world
+    assert len(want) > 1000
+
+
+def test_chain_shards_whole_buffer_pointers_and_refusals():
+    """The shards of a haystack that is resident as ONE buffer (pointer = base + 2 * lo: boundaries are multiples of the tile,
+    so every window stays aligned), an unaligned base (the first tile is resolved again behind a hidden prefix), and the
+    argument checks."""
+    import ctypes as C
+    import torch
+    from ahocorasick_b200 import _lib
+    from ahocorasick_b200.sharding import chain_shard_begin, chain_shard_finish, compose_chain_maps, plan_chain_shards
+    kws = ["ab", "ba", "aba", "bab", "bbbbabab"]
+    n = 8192 * 5 + 77
+    hay = ("abb" * (n // 3 + 1))[:n]
+    arr = np.frombuffer(hay.encode("utf-16-le"), dtype=np.uint16)
+    want = ora.Matcher("longest", kws).match(hay, cap=n)
+    want_pos = np.stack([want["start"], want["end"]], axis=1).astype(np.int64)
+    m = ac.LongestMatchSet(kws, True)
+    cap = len(want) + 16
+    for shift in (0, 3):                                   # shift 3: the base pointer is not 16-byte aligned
+        d_all = torch.zeros(n + 8, dtype=torch.int16, device="cuda")
+        d_all[shift:shift + n] = torch.from_numpy(arr.astype(np.int16)).cuda()
+        base = d_all.data_ptr() + 2 * shift
+        shards = plan_chain_shards(n, 1 if shift else 4)
+        maps, handles = [], []
+        for sh in shards:
+            d_map = torch.zeros(16, dtype=torch.int64, device="cuda")
+            n_dom = sh.hi - sh.lo if sh.hi < n else sh.read_to - sh.lo
+            handles.append(chain_shard_begin(m, base + 2 * sh.lo, sh.read_to - sh.lo, n_dom, d_map.data_ptr()))
+            torch.cuda.synchronize()
+            maps.append(d_map.cpu().tolist())
+        entries, _, total = compose_chain_maps(maps)
+        assert total == len(want)
+        parts = []
+        for sh, h, entry in zip(shards, handles, entries):
+            d_pos = torch.empty((cap, 2), dtype=torch.int32, device="cuda")
+            d_tot = torch.zeros(1, dtype=torch.int64, device="cuda")
+            chain_shard_finish(h, entry, sh.lo, d_pos.data_ptr(), None, cap, d_tot.data_ptr())
+            torch.cuda.synchronize()
+            parts.append(d_pos[:int(d_tot.item())].cpu().numpy().astype(np.int64))
+        assert np.array_equal(np.concatenate(parts, axis=0), want_pos), shift
+    # an unaligned LAST shard entered at a non-zero offset: the first tile is resolved again behind the hidden prefix
+    tail = arr[8192 * 2:].astype(np.int16)
+    d_tail = torch.zeros(tail.size + 8, dtype=torch.int16, device="cuda")
+    d_tail[5:5 + tail.size] = torch.from_numpy(tail).cuda()
+    om = ora.Matcher("longest", kws)
+    for entry in (0, 1, 2, 7):
+        d_map = torch.zeros(16, dtype=torch.int64, device="cuda")
+        h = chain_shard_begin(m, d_tail.data_ptr() + 10, tail.size, tail.size, d_map.data_ptr())
+        d_pos = torch.empty((cap, 2), dtype=torch.int32, device="cuda")
+        d_tot = torch.zeros(1, dtype=torch.int64, device="cuda")
+        chain_shard_finish(h, entry, 0, d_pos.data_ptr(), None, cap, d_tot.data_ptr())
+        torch.cuda.synchronize()
+        w = om.match(arr[8192 * 2 + entry:], cap=n)       # entering at `entry` = the haystack that starts there
+        got = d_pos[:int(d_tot.item())].cpu().numpy().astype(np.int64)
+        assert np.array_equal(got[:, 0], w["start"].astype(np.int64) + entry) and np.array_equal(got[:, 1], w["end"].astype(np.int64) + entry), entry
+    # refusals
+    d_map = torch.zeros(16, dtype=torch.int64, device="cuda")
+    h = C.c_uint64(0)
+    lib = _lib.lib()
+    d_all = torch.from_numpy(arr.astype(np.int16)).cuda()
+    assert lib.acgpu_chain_shard_begin(m.handle, d_all.data_ptr(), n, 1000, d_map.data_ptr(), C.byref(h), None) == _lib.EINVAL   # not a tile boundary
+    assert lib.acgpu_chain_shard_begin(ac.AhoCorasickSet(kws, True).handle, d_all.data_ptr(), n, n, d_map.data_ptr(), C.byref(h), None) == _lib.EINVAL
+    wide = ac.LongestMatchSet(["".join(chr(0x41 + i) for i in range(40)), "ab"], True)
+    assert lib.acgpu_chain_shard_begin(wide.handle, d_all.data_ptr(), n, n, d_map.data_ptr(), C.byref(h), None) == _lib.EUNSUPPORTED

@@ -263,3 +263,74 @@ def test_sync_point_shards_wholewordlongest(cs):
             assert got == want, (cs, kws, hay, world)
             n_cut += 1
     assert n_cut > 100
+
+
+def _chain_worker(rank, world, port, q):
+    """world-size-2 gloo: every rank owns one chain shard (modelled by the oracle: the stream of the haystack that starts at
+    the shard's entry, cut where the chain leaves the shard), the 16-entry maps ride in ONE all-gather, every rank
+    composes the same entries."""
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [here, os.path.dirname(here)]
+    from oracle import oracle as ora
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        kws = ["ab", "ba", "aba", "bab", "abab"]
+        n = 8192 * 4 + 99
+        hay = ("ab" * n)[:n]                                  # periodic: no synchronisation point, chains never merge
+        om = ora.Matcher("longest", kws)
+        shards = sharding.plan_chain_shards(n, world)
+        sh = shards[rank]
+
+        def run(entry):
+            """(records with chain position in [lo + entry, hi), exit offset) - the shard's semantics, by the oracle"""
+            recs = om.match(hay[sh.lo + entry:], cap=n)
+            out, exit_off = [], 0
+            for r in recs:
+                s, e = int(r["start"]) + sh.lo + entry, int(r["end"]) + sh.lo + entry
+                if s >= sh.hi:
+                    break
+                out.append((s, e))
+                exit_off = max(0, e - sh.hi)
+            return out, exit_off
+
+        mp = []
+        for e in range(sharding.CHAIN_ENTRIES):
+            recs, ex = run(e)
+            mp.append(ex | (len(recs) << 8))
+        mine = torch.tensor(mp, dtype=torch.int64)
+        parts = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        entries, firsts, total = sharding.compose_chain_maps([p.tolist() for p in parts])
+        recs, _ = run(entries[rank])
+        q.put((rank, entries, firsts, total, recs))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_chain_maps_compose_over_gloo():
+    import multiprocessing as mp
+    from oracle import oracle as ora
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + random.randrange(2000)
+    world = 2
+    ps = [ctx.Process(target=_chain_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=60) for _ in range(world))
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    kws = ["ab", "ba", "aba", "bab", "abab"]
+    n = 8192 * 4 + 99
+    hay = ("ab" * n)[:n]
+    want = [(int(r["start"]), int(r["end"])) for r in ora.Matcher("longest", kws).match(hay, cap=n)]
+    assert res[0][1] == res[1][1] and res[0][3] == res[1][3] == len(want)      # every rank composed the same picture
+    got = res[0][4] + res[1][4]
+    assert got == want
+    assert res[1][2][1] == len(res[0][4])                                       # rank 1's first record index

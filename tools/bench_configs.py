@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""Kernel-resident and end-to-end throughput of BASELINE.json configs[0..3] on one B200 (the headline config[4] is
-bench.py).  One JSON line per (config, matcher).  Inputs are generated on the device; timing = CUDA events on the
+"""Kernel-resident and end-to-end throughput of BASELINE.json configs[0..3] (and of workloads.config(5), the "real
+dictionary" workload) on one B200 (the headline config[4] is bench.py).  One JSON line per (config, matcher).  Inputs are generated on the device; timing = CUDA events on the
 launch stream, haystacks larger than L2.
 
   python tools/bench_configs.py [--scale S] [--configs 0,1,2,3]
@@ -41,6 +41,9 @@ def matchers_for(idx, cfg):
         return [("WholeWordMatchSet", ac.WholeWordMatchSet(kws, True, wc, tg)),
                 ("WholeWordMatchMap", ac.WholeWordMatchMap(kws, vals, True, wc, tg)),
                 ("WholeWordLongestMatchSet(+phrases)", ac.WholeWordLongestMatchSet(phrases, True, wc, tg))]
+    if idx == 5:  # the "real dictionary" workload (workloads.config(5)): outside the narrow-alphabet envelope -> kernel_wide.cuh
+        return [("AhoCorasickSet(english-like, 53 symbols, len 1-24)", ac.AhoCorasickSet(kws, True)),
+                ("AhoCorasickMap(english-like)", ac.AhoCorasickMap(kws, vals, True))]
     raise ValueError(idx)
 
 

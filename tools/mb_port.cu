@@ -102,7 +102,7 @@ k_port(const uint32_t *table, cudaTextureObject_t tex, uint32_t tmask, const uin
                 }
             }
             if (STREAM == 0) v = make_uint4(c * 977u + r, lane, r * 31u, c);
-            uint32_t h = mix(v.x ^ (v.y * 0x9E3779B1u) ^ v.z ^ (v.w << 7) ^ (uint32_t)(row0 + r));
+            uint32_t h = mix(v.x ^ (v.y * 0x9E3779B1u) ^ v.z ^ (v.w << 7) ^ (uint32_t)(row0 + r) ^ ((uint32_t)lane * 0x85EBCA6Bu));
             uint32_t g[G > 0 ? G : 1];
 #pragma unroll
             for (int j = 0; j < G; j++) {
@@ -160,8 +160,8 @@ void run(const char *name, const uint32_t *table, cudaTextureObject_t tex, uint3
     }
     const double gathers = (double)n_rows * 32 * G, stream_sectors = STREAM ? (double)n_rows * 32 : 0.0;  // 16 in + 16 out per row
     const double cyc = best * 1e-3 * 1.965e9;
-    std::printf("%-34s smem %3zu KB  %7.3f ms  gathers %6.1f M  stream sectors %6.1f M  sectors/cycle/SM %.3f\n", name, smem / 1024, best,
-                gathers / 1e6, stream_sectors / 1e6, (gathers + stream_sectors) / sms / cyc);
+    std::printf("%-34s smem %3zu KB  %7.3f ms  gathers %6.1f M  stream sectors %6.1f M  gather sectors/cycle/SM %.3f  all sectors/cycle/SM %.3f\n", name,
+                smem / 1024, best, gathers / 1e6, stream_sectors / 1e6, gathers / sms / cyc, (gathers + stream_sectors) / sms / cyc);
 }
 
 int main() {
@@ -192,7 +192,7 @@ int main() {
     const uint32_t tmask = n_tab - 1;
     const size_t need = (size_t)kWarps * (4 * kRowBytes + 64);
     std::printf("SMs %d, table 2 MB, %ld rows of 512 B\n", sms, (long)n_rows);
-    for (size_t kb : {68, 160, 185, 200, 217, 227}) {
+    for (size_t kb : {68, 160, 170, 178, 185, 192, 200}) {
         const size_t smem = kb * 1024;
         if (smem < need) continue;
         run<0, 1, 4>("gather TEX x4", table, tex, tmask, in, out, n_rows, ticket, sink, smem, sms);

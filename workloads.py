@@ -86,6 +86,78 @@ def keywords_to_arrays(keywords: List[str]) -> Tuple[np.ndarray, np.ndarray]:
     return chars, offsets
 
 
+_ONSETS = ["", "b", "c", "d", "f", "g", "h", "j", "k", "l", "m", "n", "p", "r", "s", "t", "v", "w", "y", "z", "bl", "br", "ch", "cl", "cr",
+           "dr", "fl", "fr", "gl", "gr", "pl", "pr", "qu", "sc", "sh", "sk", "sl", "sm", "sn", "sp", "st", "str", "sw", "th", "tr", "tw", "wh"]
+_VOWELS = ["a", "e", "i", "o", "u", "a", "e", "i", "o", "ai", "ea", "ee", "ie", "io", "oa", "oo", "ou", "ue", "y"]
+_CODAS = ["", "", "", "b", "ck", "d", "g", "l", "ll", "m", "n", "nd", "ng", "nt", "p", "r", "rd", "rs", "s", "ss", "st", "t", "th", "x"]
+_SUFFIXES = ["", "", "", "", "s", "ed", "ing", "ly", "er", "est", "ness", "ment", "tion", "able", "'s", "n't", "'ll", "'re"]
+
+
+def make_english_like(n: int = 236_000, seed: int = 1006, max_len: int = 24) -> List[str]:
+    """n distinct English-LIKE words (README.md:130 of the reference quotes a 235 886-word English dictionary): 1-6
+    syllables of onset + vowel + coda, common suffixes, apostrophes ("'s", "n't"), 1..max_len chars; 20 % Capitalised, 5 %
+    UPPER CASE, the rest lower case - a case-sensitive dictionary over 53 symbols.  Deterministic in (n, seed)."""
+    out: List[str] = ["a", "I", "an", "the", "of", "to", "in", "it", "is", "The", "A"]
+    seen = set(out)
+    counter = 0
+    while len(out) < n:
+        batch = 4096
+        h = hash_np(seed, np.arange(counter, counter + batch * 24, dtype=np.uint64)).reshape(batch, 24)
+        counter += batch * 24
+        for row in h:
+            k = 1 + int(row[0] % np.uint64(100)) * 6 // 100 if int(row[1] & np.uint64(3)) else 1 + int(row[0] % np.uint64(3))
+            parts = []
+            for j in range(k):
+                parts.append(_ONSETS[int(row[2 + 3 * j] % np.uint64(len(_ONSETS)))])
+                parts.append(_VOWELS[int(row[3 + 3 * j] % np.uint64(len(_VOWELS)))])
+                parts.append(_CODAS[int(row[4 + 3 * j] % np.uint64(len(_CODAS)))])
+            w = "".join(parts) + _SUFFIXES[int(row[20] % np.uint64(len(_SUFFIXES)))]
+            if not w or len(w) > max_len or w[0] == "'":
+                continue
+            style = int(row[21] % np.uint64(20))
+            if style < 4:
+                w = w[0].upper() + w[1:]
+            elif style == 4:
+                w = w.upper()
+            if w not in seen:
+                seen.add(w)
+                out.append(w)
+                if len(out) == n:
+                    break
+    return out
+
+
+ENGLISH_BLOCK = 1 << 20  # chars per independently generated text block
+_SEPS = [" ", " ", " ", " ", " ", " ", ", ", ". ", "; ", "\n", " - ", "? "]
+
+
+def _english_block(spec: "HaystackSpec", block: int) -> np.ndarray:
+    """Block `block` of the infinite English-like text of spec: dictionary words (85 %) and out-of-dictionary words
+    (15 %) separated by spaces and punctuation, exactly ENGLISH_BLOCK chars."""
+    words = spec.words
+    nw = len(words)
+    per = ENGLISH_BLOCK // 3 + 64  # more tokens than can fit
+    h = hash_np(spec.seed ^ 0xE791, np.arange(block * per * 2, (block + 1) * per * 2, dtype=np.uint64)).reshape(per, 2)
+    pick = (h[:, 0] % np.uint64(nw)).astype(np.int64)
+    # skew towards the head of the dictionary (short, frequent words)
+    pick = np.where((h[:, 1] & np.uint64(3)) == 0, pick % 512, pick)
+    oov = ((h[:, 1] >> np.uint64(8)) % np.uint64(100)) < 15
+    sep = ((h[:, 1] >> np.uint64(16)) % np.uint64(len(_SEPS))).astype(np.int64)
+    parts, total = [], 0
+    for i in range(per):
+        w = words[pick[i]]
+        if oov[i]:
+            w = w[::-1] + "q"
+        parts.append(w)
+        parts.append(_SEPS[sep[i]])
+        total += len(w) + len(_SEPS[sep[i]])
+        if total >= ENGLISH_BLOCK:
+            break
+    text = "".join(parts)
+    assert len(text) >= ENGLISH_BLOCK
+    return np.frombuffer(text[:ENGLISH_BLOCK].encode("utf-16-le"), dtype=np.uint16)
+
+
 # ----------------------------------------------------------------------------- haystacks
 
 BLOCK = 64  # one planted keyword per 64-char block
@@ -99,12 +171,14 @@ class HaystackSpec:
       'mixed'  : random case A-Za-z, 5 % Latin-1/Greek/Cyrillic letters, planted keywords in random case (config 1)
       'words'  : words separated by punctuation runs; 10 % of the words are keywords, 10 % keywords with an
                  extra word char glued on                                                (config 3)
+      'english': English-like running text built from the dictionary's own words         (config 5, the "real dictionary")
     """
 
     def __init__(self, style: str, seed: int, keywords: List[str], plant: bool = True):
         self.style = style
         self.seed = seed
         self.plant = plant
+        self.words = keywords if style == "english" else None
         self.kw_chars, self.kw_offsets = keywords_to_arrays(keywords)
         self.kw_lens = np.diff(self.kw_offsets)
         self.max_len = int(self.kw_lens.max()) if len(keywords) else 0
@@ -139,6 +213,10 @@ def _base_chars_np(spec: HaystackSpec, start: int, n: int) -> np.ndarray:
 def make_haystack(spec: HaystackSpec, n: int, start: int = 0) -> np.ndarray:
     """chars [start, start+n) of the infinite haystack defined by spec (start must be a multiple of BLOCK)."""
     assert start % BLOCK == 0
+    if spec.style == "english":
+        b0, b1 = start // ENGLISH_BLOCK, (start + n + ENGLISH_BLOCK - 1) // ENGLISH_BLOCK
+        text = np.concatenate([_english_block(spec, b) for b in range(b0, max(b1, b0 + 1))])
+        return text[start - b0 * ENGLISH_BLOCK:start - b0 * ENGLISH_BLOCK + n].copy()
     out = _base_chars_np(spec, start, n)
     if not spec.plant or spec.kw_lens.size == 0 or spec.max_len > BLOCK - 4:
         return out
@@ -207,6 +285,20 @@ def make_haystack_torch(spec: HaystackSpec, n: int, start: int = 0, device="cuda
     10^9-char haystack needs no large temporaries.  Returns an int16 tensor holding the uint16 code units."""
     import torch
     assert start % BLOCK == 0 and chunk % BLOCK == 0
+    if spec.style == "english":
+        # text blocks are built on the host (word-level generator); long haystacks tile a 32-block period
+        period = 32 * ENGLISH_BLOCK
+        if out is None:
+            out = torch.empty(n, dtype=torch.int16, device=device)
+        if n <= period:
+            out.copy_(torch.from_numpy(make_haystack(spec, n, start).view(np.int16)).to(device))
+            return out
+        assert start % period == 0
+        base = torch.from_numpy(make_haystack(spec, period, 0).view(np.int16)).to(device)
+        for c0 in range(0, n, period):
+            m = min(period, n - c0)
+            out[c0:c0 + m] = base[:m]
+        return out
     assert spec.style in ("lower", "mixed", "words")
     if out is None:
         out = torch.empty(n, dtype=torch.int16, device=device)
@@ -304,4 +396,10 @@ def config(idx: int, scale: float = 1.0):
         kws = make_keywords(max(10, int(1_000_000 * scale)), 1005)
         return dict(family="ahocorasick", is_map=False, cs=True, keywords=kws,
                     spec=HaystackSpec("lower", 2005, kws), n=int(1_000_000_000 * scale))
+    if idx == 5:
+        # not a BASELINE config: the "real dictionary" workload of VERDICT r01 (README.md:130 of the reference: 235 886 English
+        # words) - 236 000 English-like words, 1-24 chars, mixed case and apostrophes (53 symbols), case-sensitive
+        kws = make_english_like(max(50, int(236_000 * scale)), 1006)
+        return dict(family="ahocorasick", is_map=False, cs=True, keywords=kws,
+                    spec=HaystackSpec("english", 2006, kws), n=int(1_000_000_000 * scale))
     raise ValueError(idx)
