@@ -21,7 +21,7 @@ EXPORTS = [
     "acgpu_match_utf16", "acgpu_free_result", "acgpu_match_device", "acgpu_match_device_async",
     "acgpu_launches_per_match", "acgpu_stream_begin", "acgpu_stream_feed", "acgpu_stream_end",
     "acgpu_last_error", "acgpu_version", "acgpu_match_utf16_compact", "acgpu_free_matches", "acgpu_masks_to_records",
-    "acgpu_chain_shard_layout", "acgpu_chain_shard_begin", "acgpu_chain_shard_finish",
+    "acgpu_chain_shard_layout", "acgpu_chain_shard_begin", "acgpu_chain_shard_finish", "acgpu_stream_set_values_only",
 ]
 
 
@@ -83,6 +83,8 @@ def lib():
     L.acgpu_launches_per_match.argtypes = [u64]
     L.acgpu_stream_begin.restype = C.c_int
     L.acgpu_stream_begin.argtypes = [u64, C.POINTER(u64)]
+    L.acgpu_stream_set_values_only.restype = C.c_int
+    L.acgpu_stream_set_values_only.argtypes = [u64, C.c_int]
     L.acgpu_stream_feed.restype = C.c_int
     L.acgpu_stream_feed.argtypes = [u64, vp, i32, C.POINTER(Result)]
     L.acgpu_stream_end.restype = C.c_int

@@ -933,8 +933,21 @@ std::vector<PinnedBlock> g_pin_free;
 std::vector<PinnedBlock> g_pin_live;
 constexpr size_t kPinCacheBlocks = 4;
 
-bool pin_take(size_t bytes, PinnedBlock *out) {
+// sizes are rounded up to {1, 1.25, 1.5, 1.75} x 2^k so that the blocks of consecutive calls / feeds (whose record counts
+// differ by a few percent) are interchangeable in the cache - cudaHostAlloc costs ~0.3 s per GB
+size_t pin_bucket(size_t bytes) {
     bytes = std::max<size_t>(bytes, 1 << 20);
+    size_t p2 = size_t(1) << 20;
+    while (p2 * 2 <= bytes) p2 *= 2;
+    for (int q = 4; q <= 8; q++) {
+        const size_t b = p2 / 4 * q;
+        if (b >= bytes) return b;
+    }
+    return p2 * 2;
+}
+
+bool pin_take(size_t bytes, PinnedBlock *out) {
+    bytes = pin_bucket(bytes);
     {
         std::lock_guard<std::mutex> lk(g_pin_mu);
         int best = -1;
@@ -949,11 +962,8 @@ bool pin_take(size_t bytes, PinnedBlock *out) {
         }
     }
     PinnedBlock b;
-    b.bytes = align_up(bytes + bytes / 8, 1 << 20);
-    if (cudaHostAlloc(&b.p, b.bytes, cudaHostAllocDefault) != cudaSuccess) {
-        b.bytes = align_up(bytes, 1 << 20);
-        if (cudaHostAlloc(&b.p, b.bytes, cudaHostAllocDefault) != cudaSuccess) return false;
-    }
+    b.bytes = bytes;
+    if (cudaHostAlloc(&b.p, b.bytes, cudaHostAllocDefault) != cudaSuccess) return false;
     std::lock_guard<std::mutex> lk(g_pin_mu);
     g_pin_live.push_back(b);
     *out = b;
@@ -1555,6 +1565,11 @@ int acgpu_chain_shard_begin(uint64_t handle, const void *d_window, int64_t n, in
     if (rc == ACGPU_OK && d_map16) {
         if (cudaMallocAsync(reinterpret_cast<void **>(&c->d_tmp), 8, st) != cudaSuccess) rc = fail(ACGPU_ECUDA, "cudaMallocAsync failed");
         if (rc == ACGPU_OK) rc = sel2_shard_map(c->R, static_cast<unsigned long long *>(d_map16), c->d_tmp);
+        // a window that does not start on a tile boundary of its own index space (only the LAST shard may) has no rows
+        // for the entry offsets > 0: they would index its first tile at moff + entry >= 16
+        if (rc == ACGPU_OK && c->R.moff != 0 &&
+            cudaMemsetAsync(static_cast<unsigned long long *>(d_map16) + 1, 0xFF, (kS2Ent - 1) * 8, st) != cudaSuccess)
+            rc = fail(ACGPU_ECUDA, "cudaMemsetAsync failed");
     }
     if (rc != ACGPU_OK) {
         if (c->d_tmp) cudaFreeAsync(c->d_tmp, st);
@@ -1688,9 +1703,13 @@ int64_t acgpu_masks_to_records(const uint16_t *masks, int64_t n_chars, int64_t f
 
 void acgpu_free_result(acgpu_result *r) {
     if (!r) return;
-    if (r->pos && !pin_release(r->pos)) {  // streaming results are plain heap blocks
-        free(const_cast<int32_t *>(r->pos));
-        free(const_cast<uint32_t *>(r->val));
+    if (r->pos) {
+        if (!pin_release(r->pos)) {  // not from the pinned cache: plain heap blocks
+            free(const_cast<int32_t *>(r->pos));
+            free(const_cast<uint32_t *>(r->val));
+        }
+    } else if (r->val) {
+        pin_release(r->val);  // values-only stream results: the block starts at the values
     }
     fill_empty(r);
 }
@@ -1726,6 +1745,24 @@ struct StreamCtx {
     unsigned long long *d_total = nullptr;
     double density = 0.0;  // records per finalised char seen so far (max over feeds): sizes the next feed's record buffer
     bool dma_pending = false;  // a DMA straight from the caller's page-locked buffer is in flight (acgpu.h: host buffers are only read during the call)
+    // ---- pipelined feeds (AhoCorasick / WholeWord): the block of feed k is uploaded on st_up while the records of block
+    //      k-1 come down on st, and feed k returns the records of block k-1 ("the records that are final so far" - one
+    //      block later); end() returns the rest.  PCIe runs in both directions at once and no feed waits for its own scan.
+    bool pipelined = false;
+    bool values_only = false;  // acgpu_stream_set_values_only: ReadableMatchListener sees values only - leave the positions on the device
+    cudaStream_t st_up = nullptr, st_dn = nullptr;
+    cudaEvent_t ev_dn = nullptr;
+    cudaEvent_t ev_up = nullptr, ev_scan = nullptr;
+    struct Pending {
+        bool live = false;
+        int2 *d_pos = nullptr;
+        uint32_t *d_val = nullptr;
+        int64_t cap = 0, span = 0;
+        // what was scanned (a block whose records overflowed cap is scanned again into an exact buffer)
+        const uint16_t *win = nullptr;
+        int64_t avail = 0, ctx = 0, limit = 0, base = 0;
+    } pend;
+    unsigned long long *h_total = nullptr;  // pinned: the match count of the pending block
 };
 
 StreamCtx *as_stream(uint64_t h) {
@@ -1742,8 +1779,22 @@ void stream_free(StreamCtx *s) {
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
         if (s->d_win[i]) cudaFree(s->d_win[i]);
     }
+    if (s->pend.d_pos) cudaFree(s->pend.d_pos);
+    if (s->pend.d_val) cudaFree(s->pend.d_val);
     if (s->d_carry) cudaFree(s->d_carry);
     if (s->d_total) cudaFree(s->d_total);
+    if (s->h_total) cudaFreeHost(s->h_total);
+    if (s->ev_up) cudaEventDestroy(s->ev_up);
+    if (s->ev_scan) cudaEventDestroy(s->ev_scan);
+    if (s->st_up) {
+        cudaStreamSynchronize(s->st_up);
+        cudaStreamDestroy(s->st_up);
+    }
+    if (s->st_dn) {
+        cudaStreamSynchronize(s->st_dn);
+        cudaStreamDestroy(s->st_dn);
+    }
+    if (s->ev_dn) cudaEventDestroy(s->ev_dn);
     if (s->st) cudaStreamDestroy(s->st);
     s->magic = 0;
     delete s;
@@ -1768,9 +1819,10 @@ int stream_reserve(StreamCtx *s, int which, int64_t chars) {
 int stream_append(StreamCtx *s, const uint16_t *chars, int64_t n) {
     int rc = stream_reserve(s, s->cur, s->len + n);
     if (rc != ACGPU_OK) return rc;
+    cudaStream_t up = s->pipelined ? s->st_up : s->st;
     cudaPointerAttributes attr{};
     if (cudaPointerGetAttributes(&attr, chars) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
-        CU_TRY(cudaMemcpyAsync(s->d_win[s->cur] + s->len, chars, static_cast<size_t>(n) * 2, cudaMemcpyHostToDevice, s->st));
+        CU_TRY(cudaMemcpyAsync(s->d_win[s->cur] + s->len, chars, static_cast<size_t>(n) * 2, cudaMemcpyHostToDevice, up));
         s->dma_pending = true;
         s->len += n;
         return ACGPU_OK;
@@ -1783,8 +1835,8 @@ int stream_append(StreamCtx *s, const uint16_t *chars, int64_t n) {
         CU_TRY(cudaEventSynchronize(s->ev[k]));  // staging buffer k free again
         std::memcpy(s->h_pin[k], chars + done, static_cast<size_t>(c) * 2);
         CU_TRY(cudaMemcpyAsync(s->d_win[s->cur] + s->len + done, s->h_pin[k], static_cast<size_t>(c) * 2,
-                               cudaMemcpyHostToDevice, s->st));
-        CU_TRY(cudaEventRecord(s->ev[k], s->st));
+                               cudaMemcpyHostToDevice, up));
+        CU_TRY(cudaEventRecord(s->ev[k], up));
         done += c;
         k ^= 1;
     }
@@ -1846,12 +1898,13 @@ int stream_process(StreamCtx *s, bool final, acgpu_result *out) {
     if (total > 0) {
         // one page-locked block from the process-wide cache: positions, then values (acgpu_free_result hands it back)
         PinnedBlock blk;
-        const size_t pos_bytes = align_up(static_cast<size_t>(total) * 8, 16);
+        const bool want_pos = !(s->values_only && m->host.is_map);
+        const size_t pos_bytes = want_pos ? align_up(static_cast<size_t>(total) * 8, 16) : 0;
         if (!pin_take(pos_bytes + (m->host.is_map ? static_cast<size_t>(total) * 4 : 0), &blk))
             return fail(ACGPU_ENOMEM, "out of pinned host memory for the match records");
-        int32_t *h_pos = static_cast<int32_t *>(blk.p);
+        int32_t *h_pos = want_pos ? static_cast<int32_t *>(blk.p) : nullptr;
         uint32_t *h_val = m->host.is_map ? reinterpret_cast<uint32_t *>(static_cast<char *>(blk.p) + pos_bytes) : nullptr;
-        cudaError_t e = cudaMemcpyAsync(h_pos, d_pos, static_cast<size_t>(total) * 8, cudaMemcpyDeviceToHost, s->st);
+        cudaError_t e = want_pos ? cudaMemcpyAsync(h_pos, d_pos, static_cast<size_t>(total) * 8, cudaMemcpyDeviceToHost, s->st) : cudaSuccess;
         if (e == cudaSuccess && h_val) e = cudaMemcpyAsync(h_val, d_val, static_cast<size_t>(total) * 4, cudaMemcpyDeviceToHost, s->st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
         if (e != cudaSuccess) {
@@ -1896,6 +1949,178 @@ int stream_process(StreamCtx *s, bool final, acgpu_result *out) {
     return ACGPU_OK;
 }
 
+// ---- pipelined feeds -----------------------------------------------------------------------------------------
+
+int stream_scan_block(StreamCtx *s, const StreamCtx::Pending &b, int2 *d_pos, uint32_t *d_val, int64_t cap) {
+    Matcher *m = s->m;
+    RunOpts opt;
+    opt.pos_base = static_cast<int32_t>(static_cast<uint32_t>(b.base));
+    opt.ctx = b.ctx;
+    if (m->host.family == ACGPU_AHOCORASICK)
+        return enqueue_match(m, b.win, b.avail, b.ctx, b.avail, d_pos, d_val, cap, s->d_total, s->st, opt);
+    opt.entry0 = 0;
+    opt.chain_n = b.limit;
+    opt.abs0 = b.base == 0 ? 0 : -1;
+    return enqueue_match(m, b.win, b.avail, 0, b.avail, d_pos, d_val, cap, s->d_total, s->st, opt);
+}
+
+// The records of the pending block, in two steps so that the scan of the NEXT block can be enqueued in between:
+//   begin  waits for the block's scan (its count is in pinned memory), takes a pinned block and starts the download on st_dn
+//   end    waits for the download and hands the block out
+struct Collected {
+    bool live = false;
+    int64_t total = 0;
+    PinnedBlock blk;
+    int32_t *h_pos = nullptr;
+    uint32_t *h_val = nullptr;
+    int2 *d_pos = nullptr;
+    uint32_t *d_val = nullptr;
+};
+
+int stream_collect_begin(StreamCtx *s, Collected &c) {
+    StreamCtx::Pending &b = s->pend;
+    if (!b.live) return ACGPU_OK;
+    b.live = false;
+    Matcher *m = s->m;
+    CU_TRY(cudaEventSynchronize(s->ev_scan));
+    const int64_t total = static_cast<int64_t>(*s->h_total);
+    if (total > b.cap) {
+        // denser than the buffer: the kernels counted everything; scan the block again (its window is still intact)
+        cudaFreeAsync(b.d_pos, s->st);
+        if (b.d_val) cudaFreeAsync(b.d_val, s->st);
+        b.d_pos = nullptr;
+        b.d_val = nullptr;
+        b.cap = total;
+        CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&b.d_pos), static_cast<size_t>(total) * 8, s->st));
+        if (m->host.is_map) CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&b.d_val), static_cast<size_t>(total) * 4, s->st));
+        int rc = stream_scan_block(s, b, b.d_pos, b.d_val, b.cap);
+        if (rc != ACGPU_OK) return rc;
+        CU_TRY(cudaEventRecord(s->ev_scan, s->st));
+    }
+    s->density = std::max(s->density, static_cast<double>(total) / static_cast<double>(std::max<int64_t>(b.span, 1)));
+    c.d_pos = b.d_pos;
+    c.d_val = b.d_val;
+    b.d_pos = nullptr;
+    b.d_val = nullptr;
+    c.total = total;
+    c.live = true;
+    if (total > 0) {
+        const bool want_pos = !(s->values_only && m->host.is_map);
+        const size_t pos_bytes = want_pos ? align_up(static_cast<size_t>(total) * 8, 16) : 0;
+        if (!pin_take(pos_bytes + (m->host.is_map ? static_cast<size_t>(total) * 4 : 0), &c.blk))
+            return fail(ACGPU_ENOMEM, "out of pinned host memory for the match records");
+        c.h_pos = want_pos ? static_cast<int32_t *>(c.blk.p) : nullptr;
+        c.h_val = m->host.is_map ? reinterpret_cast<uint32_t *>(static_cast<char *>(c.blk.p) + pos_bytes) : nullptr;
+        CU_TRY(cudaStreamWaitEvent(s->st_dn, s->ev_scan, 0));
+        if (c.h_pos) CU_TRY(cudaMemcpyAsync(c.h_pos, c.d_pos, static_cast<size_t>(total) * 8, cudaMemcpyDeviceToHost, s->st_dn));
+        if (c.h_val) CU_TRY(cudaMemcpyAsync(c.h_val, c.d_val, static_cast<size_t>(total) * 4, cudaMemcpyDeviceToHost, s->st_dn));
+    }
+    CU_TRY(cudaEventRecord(s->ev_dn, s->st_dn));
+    return ACGPU_OK;
+}
+
+int stream_collect_end(StreamCtx *s, Collected &c, int rc, acgpu_result *out) {
+    fill_empty(out);
+    if (!c.live) return rc;
+    c.live = false;
+    const cudaError_t e = cudaEventSynchronize(s->ev_dn);
+    if (e != cudaSuccess && rc == ACGPU_OK) rc = fail(ACGPU_ECUDA, std::string("stream download: ") + cudaGetErrorString(e));
+    if (c.d_pos) cudaFreeAsync(c.d_pos, s->st_dn);
+    if (c.d_val) cudaFreeAsync(c.d_val, s->st_dn);
+    if (rc == ACGPU_OK && c.total > 0) {
+        out->n = c.total;
+        out->pos = c.h_pos;
+        out->val = c.h_val;
+    } else if (c.blk.p) {
+        pin_release(c.blk.p);
+    }
+    return rc;
+}
+
+int stream_collect(StreamCtx *s, acgpu_result *out) {
+    Collected c;
+    const int rc = stream_collect_begin(s, c);
+    return stream_collect_end(s, c, rc, out);
+}
+
+// enqueue the scan of what the window can finalise (no host wait), remember it as the pending block, slide the window
+int stream_enqueue(StreamCtx *s, bool final) {
+    Matcher *m = s->m;
+    const int family = m->host.family;
+    const int64_t L = m->host.max_len;
+    const int64_t avail = s->len;
+    const int64_t limit = family == ACGPU_AHOCORASICK ? avail : (final ? avail : std::max<int64_t>(s->ctx, avail - (2 * L + 2)));
+    CU_TRY(cudaEventRecord(s->ev_up, s->st_up));
+    CU_TRY(cudaStreamWaitEvent(s->st, s->ev_up, 0));  // the block has landed before anything on st touches the window
+    if (limit <= s->ctx) return ACGPU_OK;
+    StreamCtx::Pending &b = s->pend;
+    b.span = limit - s->ctx;
+    b.cap = std::max<int64_t>(1 << 16, std::max<int64_t>(b.span / 4, static_cast<int64_t>(1.25 * s->density * static_cast<double>(b.span)) + 1024));
+    b.win = s->d_win[s->cur];
+    b.avail = avail;
+    b.ctx = s->ctx;
+    b.limit = limit;
+    b.base = s->base;
+    CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&b.d_pos), static_cast<size_t>(b.cap) * 8, s->st));
+    if (m->host.is_map) CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&b.d_val), static_cast<size_t>(b.cap) * 4, s->st));
+    int rc = stream_scan_block(s, b, b.d_pos, b.d_val, b.cap);
+    if (rc != ACGPU_OK) return rc;
+    CU_TRY(cudaMemcpyAsync(s->h_total, s->d_total, 8, cudaMemcpyDeviceToHost, s->st));
+    CU_TRY(cudaEventRecord(s->ev_scan, s->st));
+    b.live = true;
+    s->chain = s->base + limit;
+    // slide: keep the context the next block needs at the front of the other window (the scanned window stays intact
+    // until the slide after the NEXT scan: an overflowing block can be scanned again)
+    const int64_t keep_from = family == ACGPU_AHOCORASICK ? std::max<int64_t>(0, avail - std::max<int64_t>(0, L - 1))
+                                                            : std::max<int64_t>(0, limit - 1);
+    const int64_t keep = avail - keep_from;
+    const int other = s->cur ^ 1;
+    rc = stream_reserve(s, other, std::max<int64_t>(keep, 1));
+    if (rc != ACGPU_OK) return rc;
+    if (keep > 0)
+        CU_TRY(cudaMemcpyAsync(s->d_win[other], s->d_win[s->cur] + keep_from, static_cast<size_t>(keep) * 2,
+                               cudaMemcpyDeviceToDevice, s->st));
+    s->cur = other;
+    s->base += keep_from;
+    s->len = keep;
+    s->ctx = (family == ACGPU_AHOCORASICK) ? keep : std::min<int64_t>(keep, limit - keep_from);
+    return ACGPU_OK;
+}
+
+// two results -> one (end(): the pending block, then the final flush)
+int merge_results(acgpu_result *a, acgpu_result *b, bool is_map, acgpu_result *out) {
+    if (a->n == 0) {
+        *out = *b;
+        return ACGPU_OK;
+    }
+    if (b->n == 0) {
+        *out = *a;
+        return ACGPU_OK;
+    }
+    const int64_t n = a->n + b->n;
+    PinnedBlock blk;
+    const bool want_pos = a->pos && b->pos;
+    const size_t pos_bytes = want_pos ? align_up(static_cast<size_t>(n) * 8, 16) : 0;
+    if (!pin_take(pos_bytes + (is_map ? static_cast<size_t>(n) * 4 : 0), &blk)) return fail(ACGPU_ENOMEM, "out of pinned host memory");
+    int32_t *pos = want_pos ? static_cast<int32_t *>(blk.p) : nullptr;
+    if (want_pos) {
+        std::memcpy(pos, a->pos, static_cast<size_t>(a->n) * 8);
+        std::memcpy(pos + 2 * a->n, b->pos, static_cast<size_t>(b->n) * 8);
+    }
+    uint32_t *val = nullptr;
+    if (is_map) {
+        val = reinterpret_cast<uint32_t *>(static_cast<char *>(blk.p) + pos_bytes);
+        std::memcpy(val, a->val, static_cast<size_t>(a->n) * 4);
+        std::memcpy(val + a->n, b->val, static_cast<size_t>(b->n) * 4);
+    }
+    acgpu_free_result(a);
+    acgpu_free_result(b);
+    out->n = n;
+    out->pos = pos;
+    out->val = val;
+    return ACGPU_OK;
+}
+
 }  // namespace
 
 int acgpu_stream_begin(uint64_t handle, uint64_t *stream_handle) {
@@ -1914,11 +2139,33 @@ int acgpu_stream_begin(uint64_t handle, uint64_t *stream_handle) {
     }
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s->d_carry), 16);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s->d_total), 8);
+    {
+        const int fam = m->host.family;
+        const char *sync = getenv("ACGPU_STREAM_SYNC");
+        s->pipelined = (fam == ACGPU_AHOCORASICK || fam == ACGPU_WHOLEWORD || (fam == ACGPU_WHOLEWORDLONGEST && m->use_ww)) &&
+                       !(sync && sync[0] == '1');
+    }
+    if (s->pipelined) {
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st_up, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st_dn, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_dn, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_up, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_scan, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&s->h_total), 8, cudaHostAllocDefault);
+    }
     if (e != cudaSuccess) {
         stream_free(s);
         return fail(ACGPU_ECUDA, std::string("stream setup: ") + cudaGetErrorString(e));
     }
     *stream_handle = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(s));
+    return ACGPU_OK;
+}
+
+int acgpu_stream_set_values_only(uint64_t stream_handle, int on) {
+    StreamCtx *s = as_stream(stream_handle);
+    if (!s) return fail(ACGPU_EINVAL, "bad stream handle");
+    if (!s->m->host.is_map && on) return fail(ACGPU_EINVAL, "a Set stream has no values");
+    s->values_only = on != 0;
     return ACGPU_OK;
 }
 
@@ -1929,6 +2176,20 @@ int acgpu_stream_feed(uint64_t stream_handle, const uint16_t *chars, int32_t n, 
     CU_TRY(cudaSetDevice(s->m->device));
     if (n == 0) return ACGPU_OK;
     int rc = stream_append(s, chars, n);
+    if (s->pipelined) {
+        // upload of this block (st_up) || download of the previous block's records (st); then this block's scan is
+        // enqueued and the call returns without waiting for it
+        Collected col;
+        if (rc == ACGPU_OK) rc = stream_collect_begin(s, col);   // download of block k-1 on st_dn ...
+        if (rc == ACGPU_OK) rc = stream_enqueue(s, false);       // ... while block k is scanned on st
+        rc = stream_collect_end(s, col, rc, out);
+        if (s->dma_pending || rc != ACGPU_OK) {
+            s->dma_pending = false;
+            const cudaError_t e = cudaStreamSynchronize(s->st_up);  // the caller's buffer is free again
+            if (e != cudaSuccess && rc == ACGPU_OK) rc = fail(ACGPU_ECUDA, std::string("stream upload: ") + cudaGetErrorString(e));
+        }
+        return rc;
+    }
     if (rc == ACGPU_OK) rc = stream_process(s, false, out);
     if (s->dma_pending) {
         // nothing was finalised (a feed shorter than the look-ahead) or an error cut the call short: the upload still
@@ -1947,7 +2208,20 @@ int acgpu_stream_end(uint64_t stream_handle, acgpu_result *out) {
     if (out) {
         fill_empty(out);
         cudaSetDevice(s->m->device);
-        rc = stream_process(s, true, out);
+        if (s->pipelined) {
+            acgpu_result a, b;
+            fill_empty(&b);
+            rc = stream_collect(s, &a);
+            if (rc == ACGPU_OK) rc = stream_enqueue(s, true);
+            if (rc == ACGPU_OK) rc = stream_collect(s, &b);
+            if (rc == ACGPU_OK) rc = merge_results(&a, &b, s->m->host.is_map, out);
+            if (rc != ACGPU_OK) {
+                acgpu_free_result(&a);
+                acgpu_free_result(&b);
+            }
+        } else {
+            rc = stream_process(s, true, out);
+        }
     }
     stream_free(s);
     return rc;

@@ -17,6 +17,9 @@
 
 namespace acgpu {
 
+#ifndef ACGPU_WIDE_MIN_CTAS
+#define ACGPU_WIDE_MIN_CTAS 3   // resident CTAs per SM the register allocation must allow (measured on config 5: 3 -> 47.7, 4 -> 47.3, 5 -> 44.5, 6 -> 35.3 GB/s)
+#endif
 constexpr int kWideWarps = 8;
 constexpr int kWideThreads = kWideWarps * 32;
 constexpr int kWideMaxLen = 32;      // hit masks are 32 bits
@@ -46,7 +49,7 @@ __host__ __device__ constexpr size_t wide_smem_bytes(int C, bool pair) {
 }
 
 template <bool PAIR>
-__global__ void __launch_bounds__(kWideThreads) k_wide_mask(const DevAutomaton A, const DevWide Wd, const WideArgs P) {
+__global__ void __launch_bounds__(kWideThreads, ACGPU_WIDE_MIN_CTAS) k_wide_mask(const DevAutomaton A, const DevWide Wd, const WideArgs P) {
     extern __shared__ __align__(16) unsigned char s_wide[];
     uint16_t *s_cls8 = reinterpret_cast<uint16_t *>(s_wide);                    // classes of code units 0..255
     const uint2 *s_pair = reinterpret_cast<const uint2 *>(s_wide + 512);

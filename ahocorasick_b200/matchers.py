@@ -165,6 +165,10 @@ class _Records:
             if k != n:
                 raise _lib.AcgpuError(_lib.ECUDA, "hit masks hold %d matches, the call reported %d" % (k, n))
             self.start, self.end, self.value = pos[:, 0], pos[:, 1], None
+        elif n and not res.pos:
+            # values-only stream results (acgpu_stream_set_values_only): the positions stayed on the device
+            self.start = self.end = None
+            self.value = np.ctypeslib.as_array(res.val, shape=(n,)).copy()
         elif n:
             pos = np.ctypeslib.as_array(res.pos, shape=(n, 2)).copy()
             self.start, self.end = pos[:, 0], pos[:, 1]
@@ -174,7 +178,7 @@ class _Records:
             self.value = np.zeros(0, np.uint32) if is_map else None
 
     def __len__(self):
-        return self.start.size
+        return self.start.size if self.start is not None else self.value.size
 
 
 class _Matcher:

@@ -179,17 +179,22 @@ def plan_chain_shards(n_chars: int, world: int, tile: int = CHAIN_TILE, lookahea
             for r in range(world)]
 
 
-def compose_chain_maps(maps: Sequence[Sequence[int]]) -> Tuple[List[int], List[int], int]:
+def compose_chain_maps(maps: Sequence[Sequence[int]]) -> Tuple[List[int], List[int]]:
     """maps[r][e] = (exit offset | matches << 8) of shard r entered at offset e (acgpu_chain_shard_begin; an EMPTY shard
-    contributes the identity map [0, 1, ..., 15]).  Returns (entry offset of every rank, index of every rank's first record,
-    total matches): entry_0 = 0, entry_{r+1} = exit offset of maps[r][entry_r]."""
+    contributes the identity map [0, 1, ..., 15]).  Returns (entry offset of every rank, index of every rank's first record):
+    entry_0 = 0, entry_{r+1} = exit offset of maps[r][entry_r].  The map of the LAST shard is never consulted (nothing follows
+    it; its window need not be tile-aligned, and then only its entry-0 row is meaningful) - the total is the sum of the
+    counts the shards report when they finish."""
     entries, firsts, cur, acc = [], [], 0, 0
-    for mp in maps:
+    for r, mp in enumerate(maps):
         entries.append(cur)
         firsts.append(acc)
-        t = int(mp[cur])
-        cur, acc = t & 0xFF, acc + (t >> 8)
-    return entries, firsts, acc
+        if r + 1 < len(maps):
+            t = int(mp[cur])
+            if t < 0 or (t & 0xFF) >= CHAIN_ENTRIES:
+                raise ValueError("shard %d has no map row for entry offset %d (its window is not tile-aligned)" % (r, cur))
+            cur, acc = t & 0xFF, acc + (t >> 8)
+    return entries, firsts
 
 
 def chain_shard_begin(matcher, d_window_ptr: int, n_window: int, n_domain: int, d_map_ptr: int, stream_ptr=None) -> int:

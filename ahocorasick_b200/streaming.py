@@ -45,6 +45,10 @@ class DeviceStream:
         h = C.c_uint64(0)
         check(_lib.lib().acgpu_stream_begin(matcher.handle, C.byref(h)))
         self._h = h.value
+        # ReadableMatchListener sees values only: the positions need not cross PCIe - except for ShortestMatchMap, whose
+        # replay compares the match ends with the CharBuffer fill boundaries (quirk Q4)
+        if matcher._is_map and matcher._family != _lib.SHORTEST:
+            check(_lib.lib().acgpu_stream_set_values_only(self._h, 1))
 
     def feed(self, chars: np.ndarray):
         from .matchers import _Records

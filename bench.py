@@ -52,6 +52,9 @@ def parse_args():
                     help="haystack: the corpus' haystacks are dealt to the ranks (default); range: EVERY haystack is cut by end-position "
                          "range across the ranks (plan_range_shards), each rank holds only its slice, the per-shard match counts are "
                          "all-gathered inside the timed region and the rank-ordered stream is checked against the single-GPU stream")
+    ap.add_argument("--config", type=int, default=4, choices=[0, 1, 2, 3, 4, 5],
+                    help="BASELINE.json configs[i] (default 4 = the headline: the metric is quoted on it); 0-3: the other configs, one "
+                         "JSON line per matcher with the same keys; 5: the English-like 'real dictionary' workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -317,14 +320,21 @@ def run_ours(args):
     achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
     # DRAM bytes of the same three launches from the committed ncu --set full captures (profiles/traffic.json), scaled
     # to this haystack length; null when the captures are for another workload
-    traffic = None
+    traffic, traffic_note = None, "no capture"
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         t = json.load(open(tpath))
-        if t.get("keywords") == args.keywords:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import make_traffic
+        if t.get("keywords") != args.keywords:
+            traffic_note = "capture is for another dictionary"
+        elif t.get("kernel_sources_sha") != make_traffic.kernel_sources_sha():
+            traffic_note = "stale: the kernels changed since the ncu capture (re-run tools/make_traffic.py)"
+        else:
             traffic = t["dram_bytes_per_char"] * n
+            traffic_note = "ncu --set full capture of these kernel sources (%s)" % t.get("source", "")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_tier_mask + k_row_scan + k_tier_emit (one match)", "peak_source": peak_src,
+                "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_tier_mask + k_row_scan + k_tier_emit (one match)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
                 "haystack_only_frac": (2 * n / (launch_ms * 1e-3) / 1e9) / peak,
                 "frac_of_nominal_8000": achieved / 8000.0}  # also against the nominal HBM3e figure
@@ -514,10 +524,63 @@ def run_range(args):
         dist.destroy_process_group()
 
 
+CONFIG_NAMES = {
+    0: "configs[0]: AhoCorasickSet, 1 000 ASCII keywords (len 3-12), case-sensitive, all overlapping matches, 8e6 chars",
+    1: "configs[1]: AhoCorasickMap(dict, dict, false), 100k keywords case-insensitive, 5e8 chars of mixed-case text with Latin-1 / Greek / Cyrillic letters",
+    2: "configs[2]: LongestMatchMap and ShortestMatchSet, 100k nested keywords, leftmost non-overlapping selection, 2e9 chars",
+    3: "configs[3]: WholeWordMatchSet / Map with custom word chars ['_','='], 50k keywords, 2e9 chars of mixed-punctuation text (Map also via Readable)",
+    5: "real dictionary (not a BASELINE config): AhoCorasickSet / Map, 236 000 English-like words (1-24 chars, mixed case, apostrophes), case-sensitive, 1e9 chars",
+}
+
+
+def run_config(args):
+    """configs[0..3] (and 5) on one GPU with the same JSON keys as the headline line; one line per matcher."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_configs
+    from oracle import oracle as ora
+    cfg = W.config(args.config)
+    cores = os.cpu_count() or 1
+    for d in bench_configs.measure([args.config], steps=args.steps, warmup=args.warmup):
+        cpu = None
+        if not args.no_cpu_baseline:
+            # the oracle on one host thread over a bounded sample of the same workload (the families other than AhoCorasick
+            # have no count-only entry: the sample is small)
+            fam = {"AhoCorasick": "ahocorasick", "Longest": "longest", "Shortest": "shortest", "WholeWordLongest": "wholewordlongest",
+                   "WholeWord": "wholeword"}[next(k for k in ("WholeWordLongest", "WholeWord", "AhoCorasick", "Longest", "Shortest") if d["matcher"].startswith(k))]
+            n_s = 4_000_000
+            sample = W.make_haystack(cfg["spec"], n_s)
+            kw = dict(case_sensitive=cfg["cs"])
+            if "word_chars" in cfg and fam.startswith("wholeword"):
+                kw["word_chars_table"] = ora.word_chars(2, *cfg["word_chars"])
+            try:
+                om = ora.Matcher(fam, cfg["keywords"], n_values=len(cfg["keywords"]) if "Map" in d["matcher"] else -1, **kw)
+                t0 = time.perf_counter()
+                om.match(sample, cap=2 * n_s)
+                dt = time.perf_counter() - t0
+                cpu = {"value": n_s * 2 / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+                       "sample": "1 thread x %d chars (literal C restatement of the reference loop; no JVM in this image)" % n_s}
+            except ora.OracleError:
+                cpu = None
+        line = {"metric": METRIC, "value": d["haystack_GB_per_s"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": d["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+                "config": {"workload": CONFIG_NAMES[args.config], "matcher": d["matcher"], "chars": d["chars"], "keywords": d["keywords"],
+                           "l2": "inputs larger than L2"},
+                "matches_per_s": d["matches_per_s"], "matches_per_step": d["matches"],
+                "e2e": {"value": d["e2e_GB_per_s"], "unit": UNIT, "h2d_bytes_per_step": d["e2e_chars"] * 2, "d2h_bytes_per_step": d["e2e_d2h_bytes"],
+                        "note": "acgpu_match_utf16 on a %d-char haystack from pinned host memory, best of 2 after 1 warm-up" % d["e2e_chars"],
+                        "readable_stream_GB_per_s": d["readable_stream_GB_per_s"]},
+                "gpu_launches": d["launches_per_match"] * args.steps, "roofline": dict(d["roofline"], unit="GB/s", traffic=None,
+                                                                                        kernel="all launches of one match"),
+                "cpu_baseline": cpu, "dictionary": d["info"]}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != 4:
+        run_config(args)
     elif args.shard == "range":
         run_range(args)
     else:

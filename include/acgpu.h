@@ -171,7 +171,8 @@ int acgpu_match_device(uint64_t handle, const void *d_haystack, int64_t n, int64
  * Geometry (acgpu_chain_shard_layout): shard r owns the chain positions [lo_r, hi_r) of the haystack; its window is
  * hay[lo_r, min(N, hi_r + lookahead)) in a 16-byte aligned device buffer of its own; lo_0 = 0 and every inner boundary
  * is a multiple of tile_chars (ahocorasick_b200/sharding.py::plan_chain_shards).  n_domain = hi_r - lo_r, or n for the
- * last shard.  Entry / exit offsets are relative to lo_r / hi_r and smaller than map_entries (a match is at most 16 chars).
+ * last shard (whose map nobody consults: when its window is not tile-aligned only row 0 is filled, the others are ~0).
+ * Entry / exit offsets are relative to lo_r / hi_r and smaller than map_entries (a match is at most 16 chars).
  * Records are positions in the window plus pos_base (pass lo_r for haystack positions).  finish() releases the shard.
  * Needs the start-mask path (at most 31 keyword symbols, keywords of at most 16 chars): ACGPU_EUNSUPPORTED otherwise.
  */
@@ -194,8 +195,14 @@ int acgpu_launches_per_match(uint64_t handle);
  * begin -> feed* -> end.  Each feed copies the block through pinned double buffers (cudaMemcpyAsync),
  * scans it with the automaton context carried over from previous blocks, and returns the records that
  * are final so far, in order; positions are offsets in the whole stream.  end() flushes the rest.
+ * AhoCorasick / WholeWord streams are PIPELINED: the block of feed k goes up while the records of block k-1 come down,
+ * and feed k returns the records of block k-1 (one block later than they could be known; no feed waits for its own scan).
  */
 int acgpu_stream_begin(uint64_t handle, uint64_t *stream_handle);
+/* ReadableMatchListener.match(T value) sees VALUES only (ReadableMatchListener.java:7): with values_only on, the feeds of a
+ * Map stream return val[] alone (pos == NULL) and the positions never cross PCIe - 4 instead of 12 bytes per match.  Leave
+ * it off for ShortestMatchMap: its replay needs the match ends (quirk Q4, ShortestMatchMap.java:241-249). */
+int acgpu_stream_set_values_only(uint64_t stream_handle, int on);
 int acgpu_stream_feed(uint64_t stream_handle, const uint16_t *chars, int32_t n, acgpu_result *out);
 int acgpu_stream_end(uint64_t stream_handle, acgpu_result *out);
 

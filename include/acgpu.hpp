@@ -360,6 +360,8 @@ class Handle {
         } st;
         check(acgpu_stream_begin(h_, &st.s));
         const bool shortest = family_ == ACGPU_SHORTEST;
+        // the listener sees values only: leave the positions on the device, except for the Q4 replay of ShortestMatchMap
+        check(acgpu_stream_set_values_only(st.s, shortest ? 0 : 1));
         std::unordered_set<int64_t> boundaries;
         int64_t n_read = 0;
         std::vector<char16_t> block(blockChars + (size_t)cbs);

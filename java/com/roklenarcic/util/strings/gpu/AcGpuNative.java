@@ -39,6 +39,7 @@ final class AcGpuNative {
 
     /** acgpu_stream_begin / feed / end; feed and end return {pos, val} like match (only val is used). */
     static native long streamBegin(long handle);
+    static native void streamValuesOnly(long stream, boolean on);   // acgpu_stream_set_values_only
 
     static native Object[] streamFeed(long stream, char[] buf, int n);
 

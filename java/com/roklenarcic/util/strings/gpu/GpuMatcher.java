@@ -151,6 +151,7 @@ abstract class GpuMatcher<T> implements AutoCloseable {
         final boolean shortest = family == AcGpuNative.SHORTEST;
         final java.util.HashSet<Long> boundaries = new java.util.HashSet<Long>();
         long s = AcGpuNative.streamBegin(live());
+        AcGpuNative.streamValuesOnly(s, !shortest); // the listener sees values only; ShortestMatchMap's Q4 replay needs the ends
         boolean ended = false;
         try {
             char[] block = new char[blockChars + cbs];

@@ -32,7 +32,7 @@ static jobjectArray wrap_result(JNIEnv *env, acgpu_result *r) {
         acgpu_free_result(r);
         return NULL;
     }
-    if (r->n) (*env)->SetIntArrayRegion(env, pos, 0, (jsize)(2 * r->n), (const jint *)r->pos);
+    if (r->n && r->pos) (*env)->SetIntArrayRegion(env, pos, 0, (jsize)(2 * r->n), (const jint *)r->pos); /* values-only streams: zeros */
     (*env)->SetObjectArrayElement(env, out, 0, pos);
     if (r->val) {
         jintArray val = (*env)->NewIntArray(env, (jsize)r->n);
@@ -139,6 +139,11 @@ JNIEXPORT jlong JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_stream
     int rc = acgpu_stream_begin((uint64_t)h, &s);
     if (rc != ACGPU_OK) throw_for(env, rc);
     return (jlong)s;
+}
+
+JNIEXPORT void JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_streamValuesOnly(JNIEnv *env, jclass c, jlong s, jboolean on) {
+    int rc = acgpu_stream_set_values_only((uint64_t)s, on ? 1 : 0);
+    if (rc != ACGPU_OK) throw_for(env, rc);
 }
 
 JNIEXPORT jobjectArray JNICALL Java_com_roklenarcic_util_strings_gpu_AcGpuNative_streamFeed(JNIEnv *env, jclass c,

@@ -13,7 +13,7 @@ int main(void) {
                        (fn)acgpu_info, (fn)acgpu_char_classes, (fn)acgpu_match_utf16, (fn)acgpu_free_result, (fn)acgpu_match_device,
                        (fn)acgpu_match_device_async, (fn)acgpu_launches_per_match, (fn)acgpu_stream_begin, (fn)acgpu_stream_feed,
                        (fn)acgpu_stream_end, (fn)acgpu_last_error, (fn)acgpu_version, (fn)acgpu_match_utf16_compact, (fn)acgpu_free_matches,
-                       (fn)acgpu_masks_to_records, (fn)acgpu_chain_shard_layout, (fn)acgpu_chain_shard_begin, (fn)acgpu_chain_shard_finish};
+                       (fn)acgpu_masks_to_records, (fn)acgpu_chain_shard_layout, (fn)acgpu_chain_shard_begin, (fn)acgpu_chain_shard_finish, (fn)acgpu_stream_set_values_only};
     unsigned i, n_syms = (unsigned)(sizeof syms / sizeof syms[0]);
     for (i = 0; i < n_syms; i++)
         if (!syms[i]) return 10;

@@ -157,6 +157,7 @@ int acgpu_stream_begin(uint64_t h, uint64_t *s) {
     *s = (uint64_t)(uintptr_t) new MockStream{(Mock *)(uintptr_t)h, {}};
     return ACGPU_OK;
 }
+int acgpu_stream_set_values_only(uint64_t, int) { return ACGPU_OK; }  // the mock keeps returning positions too (legal: a superset)
 int acgpu_stream_feed(uint64_t s, const uint16_t *chars, int32_t n, acgpu_result *out) {
     MockStream *st = (MockStream *)(uintptr_t)s;
     st->chars.insert(st->chars.end(), chars, chars + n);

@@ -931,7 +931,7 @@ def test_wide_path_real_dictionary(scale, n):
     gs = ac.AhoCorasickSet(kws, True)
     assert _launches(gs) == 3 and gs.info()["n_classes"] == 54 and gs.info()["max_len"] == 24
     rec = gs.match_records(hay)
-    assert len(rec) == len(want) > n // 2
+    assert len(rec) == len(want) > n // 8
     assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"])
     rec = ac.AhoCorasickMap(kws, list(range(len(kws))), True).match_records(hay)
     assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"])
@@ -994,8 +994,7 @@ def test_chain_shards_compose_to_the_single_stream(family, is_map, text):
             bufs.append((d_win, d_map))
             torch.cuda.synchronize()
             maps.append(d_map.cpu().tolist())
-        entries, firsts, total = compose_chain_maps(maps)
-        assert total == len(want), (world, total, len(want))
+        entries, firsts = compose_chain_maps(maps)
         pos_parts, val_parts = [], []
         for sh, h, entry, first in zip(shards, handles, entries, firsts):
             if h is None:
@@ -1044,8 +1043,7 @@ def test_chain_shards_whole_buffer_pointers_and_refusals():
             handles.append(chain_shard_begin(m, base + 2 * sh.lo, sh.read_to - sh.lo, n_dom, d_map.data_ptr()))
             torch.cuda.synchronize()
             maps.append(d_map.cpu().tolist())
-        entries, _, total = compose_chain_maps(maps)
-        assert total == len(want)
+        entries, _ = compose_chain_maps(maps)
         parts = []
         for sh, h, entry in zip(shards, handles, entries):
             d_pos = torch.empty((cap, 2), dtype=torch.int32, device="cuda")

@@ -269,3 +269,41 @@ def test_oracle_reproduces_committed_streams(case):
                         word_chars_table=wc)
         assert [list(t) for t in stream_v(m.match(case["haystack"]))] == want["string"]
         assert [int(r["value"]) for r in m.match(case["haystack"], readable=True)] == want["readable_values"]
+
+
+def test_java_char_tables_cover_all_65536_code_units_like_unicodedata():
+    """Appendix B of SURVEY.md: Character.toLowerCase(char) / Character.isLetterOrDigit(char) per UTF-16 code unit, Unicode 15.
+    All 65 536 entries of the generated table (oracle/java_char_tables.h; the product's csrc/java_char_tables.h must be the
+    same file, and the product's word-character table is checked through the C ABI) against Python's unicodedata."""
+    import ctypes as C
+    import hashlib
+    import os
+    import unicodedata
+    import numpy as np
+    from oracle import oracle as ora
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    a = open(os.path.join(root, "oracle", "java_char_tables.h"), "rb").read()
+    b = open(os.path.join(root, "ahocorasick_b200", "csrc", "java_char_tables.h"), "rb").read()
+    assert hashlib.sha256(a).digest() == hashlib.sha256(b).digest()
+    assert unicodedata.unidata_version.startswith("15."), "regenerate the expectation for another Unicode version"
+    lib = ora.lib()
+    changed = 0
+    for c in range(65536):
+        ch = chr(c)
+        if 0xD800 <= c <= 0xDFFF:
+            want_lower, want_lod = c, False          # surrogates: unchanged, never letters (quirk Q8)
+        else:
+            low = ch.lower()
+            want_lower = ord(low) if len(low) == 1 else (0x69 if c == 0x130 else c)
+            want_lod = unicodedata.category(ch) in ("Lu", "Ll", "Lt", "Lm", "Lo", "Nd")
+        assert lib.ora_to_lower(c) == want_lower, hex(c)
+        assert bool(lib.ora_is_letter_or_digit(c)) == want_lod, hex(c)
+        changed += want_lower != c
+    assert changed == 1173  # 1 172 simple mappings + U+0130 (full mapping "i" + U+0307, Java returns U+0069)
+    # the product's copy, through the C ABI (host-only call): default word characters = isLetterOrDigit + '-' + '_'
+    from ahocorasick_b200 import _lib
+    out = np.zeros(65536, np.uint8)
+    _lib.check(_lib.lib().acgpu_word_chars(0, None, None, 0, out.ctypes.data))
+    want = np.array([1 if (not 0xD800 <= c <= 0xDFFF and unicodedata.category(chr(c)) in ("Lu", "Ll", "Lt", "Lm", "Lo", "Nd")) or c in (0x2D, 0x5F)
+                     else 0 for c in range(65536)], dtype=np.uint8)
+    assert np.array_equal(out, want) and int(want.sum()) == 49335 + 2

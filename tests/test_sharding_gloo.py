@@ -305,9 +305,11 @@ def _chain_worker(rank, world, port, q):
         mine = torch.tensor(mp, dtype=torch.int64)
         parts = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine)
-        entries, firsts, total = sharding.compose_chain_maps([p.tolist() for p in parts])
+        entries, firsts = sharding.compose_chain_maps([p.tolist() for p in parts])
         recs, _ = run(entries[rank])
-        q.put((rank, entries, firsts, total, recs))
+        counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([len(recs)], dtype=torch.int64))
+        q.put((rank, entries, firsts, int(sum(int(c.item()) for c in counts)), recs))
     finally:
         dist.destroy_process_group()
 

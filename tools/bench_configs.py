@@ -47,20 +47,15 @@ def matchers_for(idx, cfg):
     raise ValueError(idx)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="0,1,2,3")
-    ap.add_argument("--scale", type=float, default=1.0, help="shrinks the haystack (dictionary stays full size)")
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--e2e-chars", type=int, default=100_000_000)
-    args = ap.parse_args()
+def measure(configs, scale=1.0, steps=5, warmup=3, e2e_chars=100_000_000):
+    """Yields one dict per (config, matcher)."""
+    args = argparse.Namespace(scale=scale, steps=steps, warmup=warmup, e2e_chars=e2e_chars)
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     lib = _lib.lib()
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    for idx in [int(x) for x in args.configs.split(",")]:
+    for idx in configs:
         cfg = W.config(idx)
         n = max(1 << 20, int(cfg["n"] * args.scale))
         n = min(n, 2_000_000_000)
@@ -99,10 +94,12 @@ def main():
             host.copy_(hay[:ne])
             res = _lib.Result()
             ts = []
+            res_n = 0
             for it in range(3):
                 t0 = time.perf_counter()
                 _lib.check(lib.acgpu_match_utf16(m.handle, host.data_ptr(), ne, C.byref(res)))
                 ts.append(time.perf_counter() - t0)
+                res_n = res.n
                 lib.acgpu_free_result(C.byref(res))
             stream_gbps = None
             if is_map:
@@ -114,6 +111,8 @@ def main():
                     t0 = time.perf_counter()
                     sh = C.c_uint64(0)
                     _lib.check(lib.acgpu_stream_begin(m.handle, C.byref(sh)))
+                    if m._family != _lib.SHORTEST:   # what every host mirror does: ReadableMatchListener sees values only
+                        _lib.check(lib.acgpu_stream_set_values_only(sh.value, 1))
                     n_rec = 0
                     for lo in range(0, ne, blk):
                         _lib.check(lib.acgpu_stream_feed(sh.value, host.data_ptr() + 2 * lo, min(blk, ne - lo), C.byref(res)))
@@ -125,17 +124,30 @@ def main():
                     dt = time.perf_counter() - t0
                     best = dt if best is None else min(best, dt)
                 stream_gbps = 2 * ne / best / 1e9
-            print(json.dumps({
+            yield {
                 "config": idx, "matcher": name, "chars": n, "keywords": len(cfg["keywords"]), "matches": tot.value,
                 "ms": ms, "haystack_GB_per_s": 2 * n / ms / 1e6, "matches_per_s": tot.value / ms * 1e3,
                 "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "frac": alg / ms / 1e6 / peak,
                              "algorithmic_bytes": alg},
-                "e2e_GB_per_s": 2 * ne / min(ts[1:]) / 1e9, "e2e_chars": ne, "readable_stream_GB_per_s": stream_gbps,
-                "launches_per_match": lib.acgpu_launches_per_match(m.handle), "info": m.info()}), flush=True)
+                "e2e_GB_per_s": 2 * ne / min(ts[1:]) / 1e9, "e2e_chars": ne, "e2e_d2h_bytes": int(res_n) * rec,
+                "readable_stream_GB_per_s": stream_gbps,
+                "launches_per_match": lib.acgpu_launches_per_match(m.handle), "info": m.info()}
             del d_pos, d_val
             m.close()
         del hay
         torch.cuda.empty_cache()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="0,1,2,3")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrinks the haystack (dictionary stays full size)")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--e2e-chars", type=int, default=100_000_000)
+    args = ap.parse_args()
+    for d in measure([int(x) for x in args.configs.split(",")], args.scale, args.steps, args.warmup, args.e2e_chars):
+        print(json.dumps(d), flush=True)
 
 
 if __name__ == "__main__":

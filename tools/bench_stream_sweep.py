@@ -22,6 +22,8 @@ def run(lib, m, host, ne, sizes):
     res = _lib.Result()
     sh = C.c_uint64(0)
     _lib.check(lib.acgpu_stream_begin(m.handle, C.byref(sh)))
+    if m._is_map and m._family != _lib.SHORTEST:   # what every host mirror does: ReadableMatchListener sees values only
+        _lib.check(lib.acgpu_stream_set_values_only(sh.value, 1))
     lo, k, n_rec = 0, 0, 0
     t0 = time.perf_counter()
     while lo < ne:
