@@ -133,7 +133,7 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
         }
     }
     t.n_deep = n_deep;
-    if (a.max_len > K) t.kidmask.assign(entries, 0);
+    if (a.max_len > K) t.kidmask.assign(entries * 2, 0);  // {backward, forward} word per level-K context
     for (int64_t id = 1; id < n; id++) {
         const int d = depth[id];
         const uint32_t inf = a.node_info[id];
@@ -149,7 +149,22 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
             if (inf & kInfoTerminal) rw[0] |= 1u << ((radix[id] % C + 16 - K) & 31);
             if (inf & kInfoHasChildren) rw[1] |= 1u << (radix[id] % C);
             if (inf & kInfoTerminal) t.term_levels |= 1u << d;
-            if (!t.kidmask.empty()) t.kidmask[radix[id]] = kids[id];
+            if (!t.kidmask.empty()) t.kidmask[2 * static_cast<size_t>(radix[id])] = kids[id];
+        }
+    }
+    // forward words: position q + 1 asks "does the level-(K+1) node (c[q+1], c[q], ..., c[q+1-K]) exist" = bit c[q+1-K] of
+    // the backward word of context (c[q+1], ..., c[q+2-K]); filed under the context of position q, G = (c[q], ..., c[q+1-K]),
+    // as bit c[q+1] - so ONE gather at G answers positions q (backward word) and q + 1 (forward word)
+    if (!t.kidmask.empty()) {
+        const uint64_t top = entries / C;  // C^(K-1)
+        for (uint64_t g = 0; g < entries; g++) {
+            uint32_t back = t.kidmask[2 * g];
+            const uint64_t e = g % C, rest = g / C;  // e = the most recent class of g, rest = the K-1 classes before it
+            while (back) {
+                const uint32_t a_cls = static_cast<uint32_t>(__builtin_ctz(back));
+                back &= back - 1;
+                t.kidmask[2 * (rest + a_cls * top) + 1] |= 1u << e;
+            }
         }
     }
     // ---- path-compressed deep table

@@ -81,7 +81,7 @@ struct TierTables {
     // (bit c).
     uint32_t row_off[10] = {0};      // word offset of level j's rows inside row_words (j = 1..K)
     std::vector<uint32_t> row_words;
-    std::vector<uint32_t> kidmask;   // per level-K entry, bit c = the node has a child on class c
+    std::vector<uint32_t> kidmask;   // two words per level-K context G = (c[q], .., c[q+1-K]): [2G] bit c = G continues backwards with class c (child mask of the node); [2G+1] bit e = the context of the NEXT position, (e, c[q], .., c[q+2-K]), continues with c[q+1-K]
     std::vector<uint32_t> buckets;   // 8 words per bucket: 2 entries x {x, y, z, w}
     uint32_t n_buckets = 0;
     uint64_t hash_seed = 0;

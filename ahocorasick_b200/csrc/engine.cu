@@ -179,7 +179,7 @@ int upload_tier(Matcher *m) {
         cudaResourceDesc rd{};
         rd.resType = cudaResourceTypeLinear;
         rd.res.linear.devPtr = b + o_kid;
-        rd.res.linear.desc = cudaCreateChannelDesc<unsigned int>();
+        rd.res.linear.desc = cudaCreateChannelDesc<uint2>();  // {backward, forward} continuation masks of one context
         rd.res.linear.sizeInBytes = t.kidmask.size() * 4;
         cudaTextureDesc td{};
         td.readMode = cudaReadModeElementType;

@@ -25,7 +25,7 @@ namespace acgpu {
 #endif
 constexpr int kMaskWarps = ACGPU_MASK_WARPS;
 #ifndef ACGPU_ABL
-#define ACGPU_ABL 0       // ablation builds (tools/gpu_quick.sh VARIANTS): 1 no child-mask gather, 2 no deep probes, 8 gathers split TEX/LSU
+#define ACGPU_ABL 0       // ablation builds (tools/gpu_exp.sh VARIANTS): 1 no continuation-mask gather, 2 no deep probes
 #endif
 #ifndef ACGPU_KID_TEX
 #define ACGPU_KID_TEX 1   // child masks are gathered through the texture pipe (the LSU data pipe is the kernel's bottleneck)
@@ -284,7 +284,9 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
                     rs[k] = acc;
                 }
             }
-            uint32_t m[8], ki[8];
+            // one gather per PAIR of positions: the entry of position j's context holds the backward continuation mask
+            // (position j) and the forward one (position j + 1) - 0.275 instead of 0.49 gathers per position on configs[4]
+            uint32_t m[8], need = 0, rkv[4];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 const uint32_t cj = c4[j] >> 2;
@@ -303,21 +305,24 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
                 if (LOW == 1 && j >= 1) m[j - 1] |= (wk.y >> (14 + K)) & (1u << (17 - K));
                 // class K positions back: the child the context needs (class 0 = "in no keyword" never has one)
                 const uint32_t ck = j >= K ? c4[j >= K ? j - K : 0] >> 2 : pc[j >= K ? 0 : K - j];
-                const bool kids = ((wk.y >> cj) & 1u) && ck != 0u;
-                const uint32_t rk = rs[K - 1] * C + c4[j];  // byte offset of the level-K entry's child mask
+                if (((wk.y >> cj) & 1u) && ck != 0u) need |= 1u << j;
+                if (!(j & 1)) rkv[j >> 1] = rs[K - 1] * C + c4[j];  // byte offset / 2 of the context's entry
 #pragma unroll
                 for (int k = K - 1; k >= 2; k--) rs[k] = rs[k - 1] * C + c4[j];
                 if (K >= 2) rs[1] = c4[j];
                 m[j] = mj;
+            }
+            uint2 kq[4];
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const bool g = deeper && ((need >> (2 * p)) & 3u) != 0u;
 #if ACGPU_ABL & 1
-                ki[j] = 0u;
-#elif ACGPU_ABL & 8
-                ki[j] = (j & 1) ? ((deeper && kids) ? tex1Dfetch<unsigned int>(T.kid_tex, (int)(rk >> 2)) : 0u)
-                                : (deeper ? ldg_u32_if(reinterpret_cast<const unsigned char *>(T.kidmask) + rk, kids) : 0u);
+                kq[p] = make_uint2(0u, 0u);
 #elif ACGPU_KID_TEX
-                ki[j] = (deeper && kids) ? tex1Dfetch<unsigned int>(T.kid_tex, (int)(rk >> 2)) : 0u;
+                kq[p] = g ? tex1Dfetch<uint2>(T.kid_tex, (int)(rkv[p] >> 2)) : make_uint2(0u, 0u);
 #else
-                ki[j] = deeper ? ldg_u32_if(kid_bytes + rk, kids) : 0u;
+                kq[p] = make_uint2(0u, 0u);
+                if (g) kq[p] = __ldg(reinterpret_cast<const uint2 *>(kid_bytes + rkv[p] * 2u));
 #endif
             }
             if (LOW == 1) {  // position 7's level K-1 bit sits in the row the NEXT position would read
@@ -338,9 +343,11 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
             // ---- which contexts continue to level K + 1
             uint32_t pm = 0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int p = 0; p < 4; p++) {
+                const int j = 2 * p;
                 const uint32_t ck = j >= K ? c4[j >= K ? j - K : 0] >> 2 : pc[j >= K ? 0 : K - j];
-                pm |= ((ki[j] >> ck) & 1u) << j;
+                pm |= ((kq[p].x >> ck) & 1u) << j;
+                pm |= ((kq[p].y >> (c4[j + 1] >> 2)) & 1u) << (j + 1);
             }
             pm &= vm;
 #if ACGPU_ABL & 2

@@ -16,8 +16,8 @@ namespace acgpu {
 struct DevTier {
     const uint32_t *row_words;   // direct-indexed level tables in row layout (copied to shared memory by every CTA)
     const uint32_t *cls8;        // 64 words: class of code units 0..255, one byte each
-    const uint32_t *kidmask;     // [C^K] exact child masks of the level-K entries (nullptr: no deeper levels)
-    cudaTextureObject_t kid_tex; // the same table as a linear texture (k_tier_mask gathers it through the TEX pipe)
+    const uint32_t *kidmask;     // [C^K][2] exact continuation masks of the level-K contexts: backward (this position), forward (the next one); nullptr: no deeper levels
+    cudaTextureObject_t kid_tex; // the same table as a linear uint2 texture (k_tier_mask gathers it through the TEX pipe)
     const uint4 *buckets;        // deep table: 2 entries per 32-byte bucket, see TierTables in builder.hpp
     const uint4 *vbuckets;       // Map values: {key lo, key hi, value, 0}, 2 per bucket, key = packed classes | (length - 1) << 60
     unsigned long long vseed;
