@@ -22,6 +22,7 @@ EXPORTS = [
     "acgpu_launches_per_match", "acgpu_stream_begin", "acgpu_stream_feed", "acgpu_stream_end",
     "acgpu_last_error", "acgpu_version", "acgpu_match_utf16_compact", "acgpu_free_matches", "acgpu_masks_to_records",
     "acgpu_chain_shard_layout", "acgpu_chain_shard_begin", "acgpu_chain_shard_finish", "acgpu_stream_set_values_only",
+    "acgpu_create", "acgpu_desc_fingerprint",
 ]
 
 
@@ -61,6 +62,10 @@ def lib():
     vp, i64, i32, u64 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64
     L.acgpu_create_from_keywords.restype = C.c_int
     L.acgpu_create_from_keywords.argtypes = [C.c_int, vp, vp, vp, i64, i64, C.c_int, vp, C.c_int, C.POINTER(u64)]
+    L.acgpu_create.restype = C.c_int
+    L.acgpu_create.argtypes = [vp, C.POINTER(u64)]
+    L.acgpu_desc_fingerprint.restype = C.c_int
+    L.acgpu_desc_fingerprint.argtypes = [vp, C.POINTER(u64)]
     L.acgpu_build_fingerprint.restype = C.c_int
     L.acgpu_build_fingerprint.argtypes = [C.c_int, vp, vp, vp, i64, i64, C.c_int, vp, C.POINTER(u64), C.POINTER(C.c_double)]
     L.acgpu_destroy.restype = C.c_int

@@ -88,7 +88,7 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
     int K = 0;
     uint64_t entries = 1, lower_bytes = 0;  // entries = C^K = rows of level K+1
     while (K < a.max_len && K < 8) {
-        const uint64_t lower_next = lower_bytes + (K >= 1 ? entries / C * 4 : 0);  // level K becomes a lower level
+        const uint64_t lower_next = lower_bytes + (K >= 1 ? entries / C * 8 : 0);  // level K becomes a lower level (8 bytes per row in the pair layout, 4 in the single one)
         if (lower_next + entries * 8 + 64 > kTierRowBytes) break;
         lower_bytes = lower_next;
         entries *= C;
@@ -164,6 +164,42 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
                 const uint32_t a_cls = static_cast<uint32_t>(__builtin_ctz(back));
                 back &= back - 1;
                 t.kidmask[2 * (rest + a_cls * top) + 1] |= 1u << e;
+            }
+        }
+    }
+    // ---- pair rows (k_tier_pair): {fwd, back} per row of every level, see TierTables
+    if (C <= 31) {
+        uint32_t off = 0;
+        uint64_t rows = 1;  // C^(j-1)
+        for (int j = 1; j <= K; j++) {
+            t.prow_off[j] = off;
+            off += static_cast<uint32_t>(rows * 2);
+            rows *= C;
+        }
+        if (C <= 30 && K >= 2) {
+            t.prow_off[0] = off;  // compact fwd words of level K-1
+            off += static_cast<uint32_t>(t.pow_c[K - 1]);  // C^(K-2) rows
+            off = (off + 1u) & ~1u;
+            t.pair_low_bit = 1u << ((C + 17 - K) & 31);
+        }
+        t.prow_words.assign(off, 0);
+        t.pair_gate_bit = 1u << ((C + 16 - K) & 31);
+        for (int64_t id = 1; id < n; id++) {
+            const int d = depth[id];
+            if (d > K || !(a.node_info[id] & kInfoTerminal)) continue;
+            const uint32_t top = t.pow_c[d];  // C^(d-1)
+            const uint32_t bit_f = 1u << ((radix[id] % C + 16 - d) & 31), bit_b = 1u << ((radix[id] / top + 16 - d) & 31);
+            t.prow_words[t.prow_off[d] + 2 * static_cast<size_t>(radix[id] / C)] |= bit_f;
+            t.prow_words[t.prow_off[d] + 2 * static_cast<size_t>(radix[id] % top) + 1] |= bit_b;
+            if (d == K - 1 && t.pair_low_bit) {
+                t.prow_words[t.prow_off[K] + 2 * static_cast<size_t>(radix[id])] |= t.pair_low_bit;
+                t.prow_words[t.prow_off[0] + radix[id] / C] |= bit_f;
+            }
+        }
+        if (!t.kidmask.empty()) {
+            const uint64_t top = entries / C;  // C^(K-1)
+            for (uint64_t g = 0; g < entries; g++) {
+                if (t.kidmask[2 * g] | t.kidmask[2 * g + 1]) t.prow_words[t.prow_off[K] + 2 * static_cast<size_t>(g % top)] |= t.pair_gate_bit;
             }
         }
     }
@@ -545,7 +581,7 @@ uint64_t automaton_fingerprint(const HostAutomaton &a) {
     const TierTables &t = a.tier;
     num(t.ok); num((uint64_t)t.C); num((uint64_t)t.b); num((uint64_t)t.K); num(t.term_levels);
     bytes(t.pow_c, sizeof t.pow_c); bytes(t.row_off, sizeof t.row_off);
-    vec(t.row_words); vec(t.kidmask); vec(t.buckets); num(t.n_buckets); num(t.hash_seed); num(t.n_deep); num(t.n_heads);
+    vec(t.row_words); vec(t.prow_words); bytes(t.prow_off, sizeof t.prow_off); num(t.pair_gate_bit); num(t.pair_low_bit); vec(t.kidmask); vec(t.buckets); num(t.n_buckets); num(t.hash_seed); num(t.n_deep); num(t.n_heads);
     vec(t.vbuckets); num(t.n_vbuckets); num(t.vseed);
     if (a.wide_ok) { num(a.wide_ok); vec(a.wide_pair); }
     num(a.ww.ok); vec(a.ww.wcls); vec(a.ww.buckets); num(a.ww.n_buckets); vec(a.ww.pool);

@@ -82,6 +82,21 @@ struct TierTables {
     uint32_t row_off[10] = {0};      // word offset of level j's rows inside row_words (j = 1..K)
     std::vector<uint32_t> row_words;
     std::vector<uint32_t> kidmask;   // two words per level-K context G = (c[q], .., c[q+1-K]): [2G] bit c = G continues backwards with class c (child mask of the node); [2G+1] bit e = the context of the NEXT position, (e, c[q], .., c[q+2-K]), continues with c[q+1-K]
+    // PAIR rows for k_tier_pair (kernel_pair.cuh), at most 31 classes: one 8-byte row {fwd, back} answers TWO positions.
+    // The row of level j for the pair (q, q + 1) is the mixed-radix number of the j-1 classes c[q], .., c[q-j+2] (c[q]
+    // lowest digit).  fwd: the terminal bit of node (a, row) - a keyword of length j ending at q + 1 with class a there -
+    // at bit (a + 16 - j) & 31; back: the terminal bit of node (row, y) - a keyword of length j ending at q whose first
+    // class is y - at bit (y + 16 - j) & 31.  Level K's fwd word also carries the GATE bit (pair_gate_bit, a position no
+    // class uses): some level-K context (row, y) has a continuation mask that is not empty, i.e. the pair's gather of
+    // kidmask can find something.
+    // With at most 30 classes the level-K fwd word has a second spare position, the LOW bit (pair_low_bit): the K-1
+    // classes that name the row are a keyword (it ends at q) - and prow_off[0] is a compact copy of level K-1's fwd words
+    // (one word per row) for the odd position, so dictionaries whose only keywords below level K are of length K-1 pay
+    // one 8-byte and one 4-byte shared load per pair.
+    uint32_t prow_off[10] = {0};     // word offset of level j's pair rows inside prow_words (j = 1..K), even; [0]: compact level K-1
+    std::vector<uint32_t> prow_words;
+    uint32_t pair_gate_bit = 0;
+    uint32_t pair_low_bit = 0;
     std::vector<uint32_t> buckets;   // 8 words per bucket: 2 entries x {x, y, z, w}
     uint32_t n_buckets = 0;
     uint64_t hash_seed = 0;

@@ -12,6 +12,8 @@
 #include <string>
 #include <initializer_list>
 #include <vector>
+#include <unordered_map>
+#include <stdexcept>
 
 #include "../../include/acgpu.h"
 #include "builder.hpp"
@@ -85,6 +87,7 @@ struct Matcher {
     void *d_tier_blob = nullptr;
     L2Window l2win;         // child masks + deep table, kept L2-resident across the streaming traffic
     size_t mask_smem = 0;
+    bool mask_pair = false;   // k_tier_pair (generation 4, pair rows) instead of k_tier_mask
     // AhoCorasick family outside the tier envelope (kernel_wide.cuh)
     bool use_wide = false;
     DevWide wide{};
@@ -148,7 +151,10 @@ int upload_tier(Matcher *m) {
     if (!t.ok || m->host.family == ACGPU_WHOLEWORD || m->host.family == ACGPU_WHOLEWORDLONGEST) return ACGPU_OK;
     const char *force = getenv("ACGPU_FORCE_GEN1");
     if (force && force[0] == '1') return ACGPU_OK;
-    m->mask_smem = mask_smem_bytes(t.row_words.size());
+    // generation 4 (k_tier_pair, pair rows) whenever the dictionary has them; ACGPU_MASK_GEN=3 keeps k_tier_mask (A/B runs)
+    const char *gen = getenv("ACGPU_MASK_GEN");
+    m->mask_pair = !t.prow_words.empty() && !(gen && gen[0] == '3');
+    m->mask_smem = mask_smem_bytes(m->mask_pair ? t.prow_words.size() : t.row_words.size());
     if (m->mask_smem > 227 * 1024) return ACGPU_OK;
     size_t off = 0;
     auto reserve = [&](size_t bytes) {
@@ -157,6 +163,7 @@ int upload_tier(Matcher *m) {
         return o;
     };
     size_t o_rows = reserve(t.row_words.size() * 4);
+    size_t o_prows = reserve(t.prow_words.size() * 4);
     size_t o_cls8 = reserve(256);
     size_t o_kid = reserve(t.kidmask.size() * 4);
     size_t o_deep = reserve(t.buckets.size() * 4);
@@ -167,6 +174,7 @@ int upload_tier(Matcher *m) {
     uint8_t cls8[256];
     for (int c = 0; c < 256; c++) cls8[c] = static_cast<uint8_t>(m->host.cls[c]);
     if (!t.row_words.empty()) CU_TRY(cudaMemcpy(b + o_rows, t.row_words.data(), t.row_words.size() * 4, cudaMemcpyHostToDevice));
+    if (!t.prow_words.empty()) CU_TRY(cudaMemcpy(b + o_prows, t.prow_words.data(), t.prow_words.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(b + o_cls8, cls8, 256, cudaMemcpyHostToDevice));
     if (!t.kidmask.empty()) CU_TRY(cudaMemcpy(b + o_kid, t.kidmask.data(), t.kidmask.size() * 4, cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(b + o_deep, t.buckets.data(), t.buckets.size() * 4, cudaMemcpyHostToDevice));
@@ -196,6 +204,11 @@ int upload_tier(Matcher *m) {
     d.row_words = reinterpret_cast<const uint32_t *>(b + o_rows);
     d.n_row_words = static_cast<uint32_t>(t.row_words.size());
     for (int j = 0; j < 10; j++) d.row_off[j] = t.row_off[j];
+    d.prow_words = t.prow_words.empty() ? nullptr : reinterpret_cast<const uint32_t *>(b + o_prows);
+    d.n_prow_words = static_cast<uint32_t>(t.prow_words.size());
+    for (int j = 0; j < 10; j++) d.prow_off[j] = t.prow_off[j];
+    d.pair_gate_bit = t.pair_gate_bit;
+    d.pair_low_bit = t.pair_low_bit;
     {
         // L2 residency window over [child masks | deep table] (adjacent in the blob)
         int max_win = 0, max_persist = 0;
@@ -282,10 +295,11 @@ int upload_ww(Matcher *m) {
 }
 
 // k_tier_mask: variant 1 reads level K-1 from the spare bit of the level-K rows, which exists for at most 31 classes
-int mask_low_variant(const DevTier &t) {
+// (k_tier_pair: its LOW bit, which exists for at most 30 classes)
+int mask_low_variant(const DevTier &t, bool pair) {
     const uint32_t below = t.term_levels & ((1u << t.K) - 1u);  // bits 1..K-1 (bit 0 is never set)
     if (below == 0) return 2;
-    if (below == (1u << (t.K - 1)) && t.C <= 31) return 1;
+    if (below == (1u << (t.K - 1)) && (pair ? t.pair_low_bit != 0u : t.C <= 31)) return 1;
     return 0;
 }
 
@@ -311,17 +325,17 @@ struct RunOpts {
 };
 
 int launch_mask(Matcher *m, const MaskArgs &P, int grid, cudaStream_t st, bool mir = false) {
-    const int low = mask_low_variant(m->tier);
+    const int low = mask_low_variant(m->tier, m->mask_pair);
     cudaError_t e;
     switch (m->tier.K) {
-    case 1: e = mask_launch_1(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
-    case 2: e = mask_launch_2(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
-    case 3: e = mask_launch_3(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
-    case 4: e = mask_launch_4(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
-    case 5: e = mask_launch_5(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
-    case 6: e = mask_launch_6(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
-    case 7: e = mask_launch_7(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
-    default: e = mask_launch_8(low, mir, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 1: e = mask_launch_1(low, mir, m->mask_pair, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 2: e = mask_launch_2(low, mir, m->mask_pair, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 3: e = mask_launch_3(low, mir, m->mask_pair, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 4: e = mask_launch_4(low, mir, m->mask_pair, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 5: e = mask_launch_5(low, mir, m->mask_pair, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 6: e = mask_launch_6(low, mir, m->mask_pair, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    case 7: e = mask_launch_7(low, mir, m->mask_pair, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
+    default: e = mask_launch_8(low, mir, m->mask_pair, m->dev, m->tier, P, grid, m->mask_smem, m->l2win, st); break;
     }
     CU_TRY(e);
     return ACGPU_OK;
@@ -1328,7 +1342,7 @@ struct HostCall {
 extern "C" {
 
 const char *acgpu_last_error(void) { return g_err.c_str(); }
-const char *acgpu_version(void) { return "acgpu 0.2 (sm_100a; tiered hit-mask kernels, generation 3)"; }
+const char *acgpu_version(void) { return "acgpu 0.2 (sm_100a; tiered hit-mask kernels, generation 4: pair rows)"; }
 
 int acgpu_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, int32_t n, uint8_t *out65536) {
     if (!out65536 || mode < 0 || mode > 2 || n < 0) return fail(ACGPU_EINVAL, "bad arguments");
@@ -1336,28 +1350,10 @@ int acgpu_word_chars(int mode, const uint16_t *chars, const uint8_t *toggles, in
     return ACGPU_OK;
 }
 
-int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t *offsets, const uint8_t *is_null,
-                               int64_t n_keywords, int64_t n_values, int case_sensitive, const uint8_t *word_chars,
-                               int device, uint64_t *handle) {
-    if (!handle || n_keywords < 0 || (n_keywords > 0 && (!chars || !offsets))) return fail(ACGPU_EINVAL, "bad arguments");
-    *handle = 0;
-    Matcher *m = new (std::nothrow) Matcher();
-    if (!m) return fail(ACGPU_ENOMEM, "out of memory");
-    try {
-        m->host = build_automaton(family, chars, offsets, is_null, n_keywords, n_values, case_sensitive != 0, word_chars);
-    } catch (const IllegalArgument &e) {
-        delete m;
-        return fail(ACGPU_EILLEGALARG, e.what());
-    } catch (const std::domain_error &e) {
-        delete m;
-        return fail(ACGPU_EUNSUPPORTED, e.what());
-    } catch (const std::bad_alloc &) {
-        delete m;
-        return fail(ACGPU_ENOMEM, "out of memory while flattening the dictionary");
-    } catch (const std::exception &e) {
-        delete m;
-        return fail(ACGPU_EINVAL, e.what());
-    }
+namespace {
+
+// device half of a constructor: m->host is flattened, bring the tables to `device`
+int finish_create(Matcher *m, int family, int device, uint64_t *handle) {
     if ((family == ACGPU_LONGEST || family == ACGPU_SHORTEST) && m->host.max_len + 1 > kSelMaxLen) {
         delete m;
         return fail(ACGPU_EUNSUPPORTED, "Longest/Shortest selection kernels support keywords up to 2047 chars");
@@ -1401,6 +1397,148 @@ int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t 
     }
     *handle = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(m));
     return ACGPU_OK;
+}
+
+// flatten with the C++ builder, mapping its exceptions onto the ABI's codes; 0 and `out` filled on success
+int flatten(int family, const uint16_t *chars, const int64_t *offsets, const uint8_t *is_null, int64_t n_keywords, int64_t n_values,
+            bool case_sensitive, const uint8_t *word_chars, HostAutomaton &out) {
+    try {
+        out = build_automaton(family, chars, offsets, is_null, n_keywords, n_values, case_sensitive, word_chars);
+    } catch (const IllegalArgument &e) {
+        return fail(ACGPU_EILLEGALARG, e.what());
+    } catch (const std::domain_error &e) {
+        return fail(ACGPU_EUNSUPPORTED, e.what());
+    } catch (const std::bad_alloc &) {
+        return fail(ACGPU_ENOMEM, "out of memory while flattening the dictionary");
+    } catch (const std::exception &e) {
+        return fail(ACGPU_EINVAL, e.what());
+    }
+    return ACGPU_OK;
+}
+
+// The dictionary a trie descriptor spells, in the arrays acgpu_create_from_keywords takes.  Sets: one keyword per terminal
+// state, in state order.  Maps: entry v = the keyword whose state carries value index v, every other entry null - so the
+// builder's "value = index of the entry" reproduces the descriptor's indices.
+struct DescKeywords {
+    std::vector<uint16_t> chars;
+    std::vector<int64_t> offsets;
+    std::vector<uint8_t> is_null;
+    int64_t n_keywords = 0, n_values = -1;
+};
+
+int keywords_of_desc(const acgpu_automaton_desc *d, DescKeywords &K) {
+    if (!d || d->struct_size < static_cast<int32_t>(sizeof(acgpu_automaton_desc))) return fail(ACGPU_EINVAL, "acgpu_automaton_desc: bad struct_size");
+    if (d->family < 0 || d->family > 4 || d->n_states < 1 || !d->parent || !d->edge_char || !d->terminal)
+        return fail(ACGPU_EINVAL, "acgpu_automaton_desc: family / n_states / parent / edge_char / terminal");
+    if (d->is_map && (!d->value || d->n_values < 0)) return fail(ACGPU_EINVAL, "acgpu_automaton_desc: a Map needs value[] and n_values");
+    const int64_t n = d->n_states;
+    if (d->parent[0] != -1) return fail(ACGPU_EINVAL, "acgpu_automaton_desc: state 0 must be the root (parent -1)");
+    std::vector<int32_t> depth(static_cast<size_t>(n), 0);
+    for (int64_t s = 1; s < n; s++) {
+        const int32_t p = d->parent[s];
+        if (p < 0 || p >= s) return fail(ACGPU_EINVAL, "acgpu_automaton_desc: parent[s] must be in [0, s)");
+        depth[s] = depth[p] + 1;
+    }
+    std::vector<int64_t> state_of;  // entry -> terminal state (-1: null entry)
+    if (d->is_map) {
+        state_of.assign(static_cast<size_t>(d->n_values), -1);
+        for (int64_t s = 1; s < n; s++) {
+            if (!d->terminal[s]) continue;
+            const uint32_t v = d->value[s];
+            if (static_cast<int64_t>(v) >= d->n_values) return fail(ACGPU_EINVAL, "acgpu_automaton_desc: value index out of range");
+            if (state_of[v] >= 0) return fail(ACGPU_EINVAL, "acgpu_automaton_desc: a value index is carried by two states");
+            state_of[v] = s;
+        }
+        K.n_values = d->n_values;
+    } else {
+        for (int64_t s = 1; s < n; s++)
+            if (d->terminal[s]) state_of.push_back(s);
+    }
+    K.n_keywords = static_cast<int64_t>(state_of.size());
+    K.offsets.assign(state_of.size() + 1, 0);
+    K.is_null.assign(state_of.size(), 0);
+    int64_t total = 0;
+    for (size_t k = 0; k < state_of.size(); k++) {
+        K.offsets[k] = total;
+        if (state_of[k] < 0) K.is_null[k] = 1; else total += depth[state_of[k]];
+    }
+    K.offsets[state_of.size()] = total;
+    K.chars.assign(static_cast<size_t>(std::max<int64_t>(total, 1)), 0);
+    for (size_t k = 0; k < state_of.size(); k++) {
+        int64_t s = state_of[k];
+        if (s < 0) continue;
+        int64_t at = K.offsets[k] + depth[s];
+        for (; s > 0; s = d->parent[s]) K.chars[static_cast<size_t>(--at)] = d->edge_char[s];
+    }
+    if (d->fail) {
+        // the links the trie implies (BFS order = state order is not required: process by depth)
+        std::unordered_map<uint64_t, int32_t> child;
+        child.reserve(static_cast<size_t>(n) * 2);
+        for (int64_t s = 1; s < n; s++) child[(static_cast<uint64_t>(d->parent[s]) << 16) | d->edge_char[s]] = static_cast<int32_t>(s);
+        std::vector<int32_t> order(static_cast<size_t>(n));
+        for (int64_t s = 0; s < n; s++) order[s] = static_cast<int32_t>(s);
+        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return depth[x] < depth[y]; });
+        std::vector<int32_t> f(static_cast<size_t>(n), 0);
+        for (int32_t s : order) {
+            if (depth[s] <= 1) continue;
+            int32_t t = f[d->parent[s]];
+            while (true) {
+                auto it = child.find((static_cast<uint64_t>(t) << 16) | d->edge_char[s]);
+                if (it != child.end()) { f[s] = it->second; break; }
+                if (t == 0) break;
+                t = f[t];
+            }
+        }
+        for (int64_t s = 0; s < n; s++)
+            if (d->fail[s] != f[s]) return fail(ACGPU_EINVAL, "acgpu_automaton_desc: fail[] does not match the failure links of the trie");
+    }
+    return ACGPU_OK;
+}
+
+}  // namespace
+
+int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t *offsets, const uint8_t *is_null,
+                               int64_t n_keywords, int64_t n_values, int case_sensitive, const uint8_t *word_chars,
+                               int device, uint64_t *handle) {
+    if (!handle || n_keywords < 0 || (n_keywords > 0 && (!chars || !offsets))) return fail(ACGPU_EINVAL, "bad arguments");
+    *handle = 0;
+    Matcher *m = new (std::nothrow) Matcher();
+    if (!m) return fail(ACGPU_ENOMEM, "out of memory");
+    const int rc = flatten(family, chars, offsets, is_null, n_keywords, n_values, case_sensitive != 0, word_chars, m->host);
+    if (rc != ACGPU_OK) {
+        delete m;
+        return rc;
+    }
+    return finish_create(m, family, device, handle);
+}
+
+int acgpu_create(const acgpu_automaton_desc *desc, uint64_t *handle) {
+    if (!handle) return fail(ACGPU_EINVAL, "bad arguments");
+    *handle = 0;
+    DescKeywords K;
+    int rc = keywords_of_desc(desc, K);
+    if (rc != ACGPU_OK) return rc;
+    Matcher *m = new (std::nothrow) Matcher();
+    if (!m) return fail(ACGPU_ENOMEM, "out of memory");
+    rc = flatten(desc->family, K.chars.data(), K.offsets.data(), K.is_null.data(), K.n_keywords, K.n_values, desc->case_sensitive != 0,
+                 desc->word_chars, m->host);
+    if (rc != ACGPU_OK) {
+        delete m;
+        return rc;
+    }
+    return finish_create(m, desc->family, desc->device, handle);
+}
+
+int acgpu_desc_fingerprint(const acgpu_automaton_desc *desc, uint64_t *fingerprint) {
+    if (!fingerprint) return fail(ACGPU_EINVAL, "bad arguments");
+    DescKeywords K;
+    int rc = keywords_of_desc(desc, K);
+    if (rc != ACGPU_OK) return rc;
+    HostAutomaton a;
+    rc = flatten(desc->family, K.chars.data(), K.offsets.data(), K.is_null.data(), K.n_keywords, K.n_values, desc->case_sensitive != 0,
+                 desc->word_chars, a);
+    if (rc == ACGPU_OK) *fingerprint = automaton_fingerprint(a);
+    return rc;
 }
 
 int acgpu_build_fingerprint(int family, const uint16_t *chars, const int64_t *offsets, const uint8_t *is_null,

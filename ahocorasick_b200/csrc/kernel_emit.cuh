@@ -111,16 +111,33 @@ __device__ __forceinline__ void sts_v2(uint32_t saddr, int32_t x, int32_t y) {
 __device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t x) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"((unsigned short)x) : "memory");
 }
+// index of the highest set bit (0xFFFFFFFF: none) and a shift that is defined for every count (>= 32 gives 0)
+__device__ __forceinline__ uint32_t flo32(uint32_t x) {
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+    return r;
+}
+__device__ __forceinline__ uint32_t shl32(uint32_t x, uint32_t s) {
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(s));
+    return r;
+}
 // code = row position << 4 | 16 - length  ->  (start, end); e_row = end of a keyword whose last char is row position 0
 __device__ __forceinline__ int2 decode_rec(uint32_t code, int32_t e_row) {
     const int32_t e = e_row + (int32_t)(code >> 4);
     return make_int2(e - 16 + (int32_t)(code & 15u), e);
 }
 
+#ifndef ACGPU_EMIT_MIN_CTAS
+#define ACGPU_EMIT_MIN_CTAS 6  // resident CTAs per SM the register allocation must allow (63 registers gave 4 = half the warps)
+#endif
+// The common path stages 2-byte codes (kEmitStage + 2 of them per warp); rows that do not fit take windows of kEmitWin
+// 8-byte records through the same bytes.
+constexpr int kEmitWin = (kEmitStage + 2) / 4;
 template <bool kIsMap>
-__global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomaton A, const DevTier T, const EmitArgs E) {
-    __shared__ __align__(16) int2 s_stage_all[kEmitWarps][kEmitStage + 2];
-    __shared__ uint32_t s_val_all[kIsMap ? kEmitWarps : 1][kIsMap ? kEmitStage : 1];
+__global__ void __launch_bounds__(kEmitWarps * 32, ACGPU_EMIT_MIN_CTAS) k_tier_emit(const DevAutomaton A, const DevTier T, const EmitArgs E) {
+    __shared__ __align__(16) int2 s_stage_all[kEmitWarps][kEmitWin + 1];
+    __shared__ uint32_t s_val_all[kIsMap ? kEmitWarps : 1][kIsMap ? kEmitWin : 1];
     __shared__ __align__(16) uint32_t s_cls[64];
     __shared__ uint2 s_pack_all[kIsMap ? kEmitWarps : 1][kIsMap ? 34 : 1];  // packed classes of the row: [0,1] = the 16 chars before it
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -135,25 +152,31 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
     }
     const int b = T.b;
     const uint32_t cm = (1u << b) - 1u, sh = 1u << b;
-    const int64_t stride = (int64_t)gridDim.x * kEmitWarps;
     const uint32_t stage_sa = (uint32_t)__cvta_generic_to_shared(s_stage);
     // parity of the output buffer in 8-byte units: record g is 16-byte aligned iff (g + out_par) is even
     const uint32_t out_par = (uint32_t)(reinterpret_cast<uintptr_t>(E.pos_out) >> 3) & 1u;
 
     const uint32_t lane_code = (uint32_t)lane * 128u;
-    int64_t row = (int64_t)blockIdx.x * kEmitWarps + warp;
+    // rows are taken round-robin; 32-bit row arithmetic (n_rows < 2^31) and running pointers keep the prefetch cheap
+    const int n_rows = (int)E.n_rows, stride = (int)gridDim.x * kEmitWarps;
+    int row = (int)blockIdx.x * kEmitWarps + warp;
+    const uint4 *mp = reinterpret_cast<const uint4 *>(E.masks) + ((size_t)row * 32 + lane);
+    const uint32_t *rp = E.row_excl + row;
     uint4 mm_n = make_uint4(0u, 0u, 0u, 0u);
     unsigned long long base_n = 0;
-    if (row < E.n_rows) {
-        mm_n = __ldcs(reinterpret_cast<const uint4 *>(E.masks + ((size_t)row * 32 + lane) * 4));
-        base_n = __ldg(E.block_excl + row / kScanRows) + __ldg(E.row_excl + row);
+    if (row < n_rows) {
+        mm_n = __ldcs(mp);
+        base_n = __ldg(E.block_excl + (row >> 12)) + __ldg(rp);
     }
-    for (; row < E.n_rows; row += stride) {
+    static_assert(kScanRows == 4096, "row >> 12 is the scan block of a row");
+    for (; row < n_rows; row += stride) {
         const uint4 mm = mm_n;
         const unsigned long long base = base_n;
-        if (row + stride < E.n_rows) {
-            mm_n = __ldcs(reinterpret_cast<const uint4 *>(E.masks + ((size_t)(row + stride) * 32 + lane) * 4));
-            base_n = __ldg(E.block_excl + (row + stride) / kScanRows) + __ldg(E.row_excl + row + stride);
+        mp += (size_t)stride * 32;
+        rp += stride;
+        if (row + stride < n_rows) {
+            mm_n = __ldcs(mp);
+            base_n = __ldg(E.block_excl + ((row + stride) >> 12)) + __ldg(rp);
         }
         const uint32_t cnt = __popc(mm.x) + __popc(mm.y) + __popc(mm.z) + __popc(mm.w);
         uint32_t inc = cnt;
@@ -165,7 +188,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
         const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
         if (total == 0) continue;
         const uint32_t my_off = inc - cnt;
-        const int64_t p0 = E.origin + row * kMaskRow + (int64_t)lane * 8;
+        const int64_t p0 = E.origin + (int64_t)row * kMaskRow + (int64_t)lane * 8;
         const int32_t e0 = (int32_t)(p0 + 1) + E.pos_base;  // end (exclusive) of a keyword whose last char is position p0
         const uint32_t words[4] = {mm.x, mm.y, mm.z, mm.w};
 
@@ -178,7 +201,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
             P0 = pack8(c4, sh);
             Pack8 h{0u, 0u};
             if (lane < 2) {
-                const int64_t q0 = E.origin + row * kMaskRow - 16 + (int64_t)lane * 8;
+                const int64_t q0 = E.origin + (int64_t)row * kMaskRow - 16 + (int64_t)lane * 8;
                 const bool inq = q0 >= 0 && q0 + 8 <= E.n;
                 const uint4 hv = ldcs_v4_if(E.hay + q0, inq);
                 uint32_t h4[8];
@@ -206,21 +229,32 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
             //      both sides of the flush are aligned.
             const uint32_t par = ((uint32_t)base + out_par) & 1u;
             uint32_t sa = stage_sa + (my_off + par) * 2u;
-            uint32_t cb = lane_code;  // lane * 128, + 32 per mask word
+            // A word holds two positions, the first one in the low half and a position's longest keyword in its lowest
+            // bit: reversed, the order of the records is "highest bit first", one FLO per record.  Three predicated,
+            // branch-free steps cover almost every word (0.87 records per position on configs[4]); a rare fuller word
+            // finishes in a loop.  Records of a word are stored at fixed offsets from the word's first slot.
 #pragma unroll
             for (int wi = 0; wi < 4; wi++) {
-                uint32_t w = words[wi];
-                while (w) {
-                    const uint32_t t = (uint32_t)__clz((int)__brev(w));
-                    w &= w - 1u;
-                    sts_u16(sa, cb + t);
-                    sa += 2u;
+                uint32_t w = __brev(words[wi]);
+                const uint32_t cb31 = lane_code + 32u * wi + 31u;  // code of the word's bit 0 = reversed bit 31
+                const uint32_t pcw = (uint32_t)__popc(w);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    const uint32_t f = flo32(w);  // 0xFFFFFFFF for an empty word: the store is predicated off
+                    if (w) sts_u16(sa + 2u * i, cb31 - f);
+                    w ^= shl32(1u, f);  // the bit is set (empty word: the shift gives 0)
                 }
-                cb += 32u;
-                asm volatile("" : "+r"(cb));  // keep the word's code base in a register (else it is re-added in every iteration)
+                uint32_t s2 = sa + 6u;
+                while (w) {
+                    const uint32_t f = flo32(w);
+                    sts_u16(s2, cb31 - f);
+                    s2 += 2u;
+                    w ^= shl32(1u, f);  // the bit is set (empty word: the shift gives 0)
+                }
+                sa += 2u * pcw;
             }
             __syncwarp();
-            const int32_t e_row = (int32_t)(E.origin + row * kMaskRow) + 1 + E.pos_base;  // end of a keyword whose last char is row position 0
+            const int32_t e_row = (int32_t)(E.origin + (int64_t)row * kMaskRow) + 1 + E.pos_base;  // end of a keyword whose last char is row position 0
             if (kIsMap) {
                 // ---- values, one RECORD per lane: the code says which position and length it is; the contexts come from
                 //      the row's packed classes in shared memory
@@ -240,17 +274,23 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
             if (lane == 1 && (end & 1u)) __stcs(g + (end - 1u), decode_rec(s_code[end - 1u], e_row));
             int4 *gp = reinterpret_cast<int4 *>(g) + par + lane;
             const uint32_t *sp = reinterpret_cast<const uint32_t *>(s_code) + par + lane;
-            for (uint32_t k = par + lane; k < k_hi; k += 32, gp += 32, sp += 32) {
-                const uint32_t cc = *sp;
-                const int2 r0 = decode_rec(cc & 0xFFFFu, e_row), r1 = decode_rec(cc >> 16, e_row);
-                __stcs(gp, make_int4(r0.x, r0.y, r1.x, r1.y));
+            const uint32_t k0 = par + lane;
+            // at most kEmitStage / 2 + 1 pairs: a fixed trip count keeps every address an immediate offset
+#pragma unroll
+            for (int i = 0; i < (kEmitStage / 2 + 1 + 31) / 32; i++) {
+                if (par + 32u * i >= k_hi) break;  // warp-uniform
+                if (k0 + 32u * i < k_hi) {
+                    const uint32_t cc = sp[32 * i];
+                    const int2 r0 = decode_rec(cc & 0xFFFFu, e_row), r1 = decode_rec(cc >> 16, e_row);
+                    __stcs(gp + 32 * i, make_int4(r0.x, r0.y, r1.x, r1.y));
+                }
             }
             __syncwarp();
             continue;
         }
 
-        for (uint32_t win = 0; win < total; win += kEmitStage) {
-            if (cnt && my_off < win + kEmitStage && my_off + cnt > win) {
+        for (uint32_t win = 0; win < total; win += kEmitWin) {
+            if (cnt && my_off < win + kEmitWin && my_off + cnt > win) {
                 uint32_t o = my_off - win;  // wraps below zero for records of an earlier window
 #pragma unroll
                 for (int wi = 0; wi < 4; wi++) {
@@ -259,7 +299,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
                         const int t = __ffs(w) - 1;
                         w &= w - 1u;
                         const int j = 2 * wi + (t >> 4), d = 16 - (t & 15);
-                        if (o < (uint32_t)kEmitStage) {
+                        if (o < (uint32_t)kEmitWin) {
                             const int32_t e = e0 + j;
                             s_stage[o] = make_int2(e - d, e);
                             if (kIsMap) s_val[o] = tier_value_rt(T, context_of(P0, P1, P2, j, b), cm, d);
@@ -269,7 +309,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_tier_emit(const DevAutomato
                 }
             }
             __syncwarp();
-            const uint32_t n_win = min((uint32_t)kEmitStage, total - win);
+            const uint32_t n_win = min((uint32_t)kEmitWin, total - win);
             const unsigned long long g0 = base + win;
             const unsigned long long room = g0 < (unsigned long long)E.cap ? (unsigned long long)E.cap - g0 : 0ull;
             const uint32_t n_out = (uint32_t)min((unsigned long long)n_win, room);

@@ -88,9 +88,10 @@ __device__ __forceinline__ uint32_t ldg_u32_if(const void *p, bool on) {
     return x;
 }
 
-// scaled classes (class * 4) of the 8 chars at kernel positions [p0, p0 + 8); v is the prefetched vector, valid when
-// `inside` (the 8 chars lie inside [0, n)); positions outside [0, n) give class 0
-template <bool MIR = false>
+// scaled classes (class * SCALE; s_cls4 holds the first 256 code units at the same scale) of the 8 chars at kernel
+// positions [p0, p0 + 8); v is the prefetched vector, valid when `inside` (the 8 chars lie inside [0, n)); positions
+// outside [0, n) give class 0
+template <bool MIR = false, int SCALE = 4>
 __device__ __forceinline__ void classify8x4(const DevAutomaton &A, const uint16_t *hay, int64_t n, int64_t p0, bool inside, const uint4 v,
                                             const uint8_t *s_cls4, uint32_t (&c4)[8]) {
     if (inside) {
@@ -103,13 +104,13 @@ __device__ __forceinline__ void classify8x4(const DevAutomaton &A, const uint16_
             const uint32_t ch[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16,
                                     v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
 #pragma unroll
-            for (int j = 0; j < 8; j++) c4[j] = ch[j] < 256u ? (uint32_t)s_cls4[ch[j]] : (uint32_t)__ldg(&A.cls[ch[j]]) * 4u;
+            for (int j = 0; j < 8; j++) c4[j] = ch[j] < 256u ? (uint32_t)s_cls4[ch[j]] : (uint32_t)__ldg(&A.cls[ch[j]]) * (uint32_t)SCALE;
         }
     } else {
 #pragma unroll
         for (int j = 0; j < 8; j++) {
             const int64_t p = p0 + j;
-            c4[j] = (p >= 0 && p < n) ? (uint32_t)__ldg(&A.cls[__ldg(&hay[MIR ? n - 1 - p : p])]) * 4u : 0u;
+            c4[j] = (p >= 0 && p < n) ? (uint32_t)__ldg(&A.cls[__ldg(&hay[MIR ? n - 1 - p : p])]) * (uint32_t)SCALE : 0u;
         }
     }
 }
@@ -131,11 +132,12 @@ __device__ __forceinline__ uint4 load8(const uint16_t *hay, int64_t n, int64_t p
 struct Pack8 {
     uint32_t hi, lo;  // hi: positions 0..3, lo: positions 4..7 (position 7 = most recent = lowest bits of lo)
 };
+template <int SCALE = 4>
 __device__ __forceinline__ Pack8 pack8(const uint32_t (&c4)[8], uint32_t sh) {
     Pack8 p;
-    // every c4 is a multiple of 4, so the scaled sum is 4 x the packed classes
-    p.hi = (((c4[0] * sh + c4[1]) * sh + c4[2]) * sh + c4[3]) >> 2;
-    p.lo = (((c4[4] * sh + c4[5]) * sh + c4[6]) * sh + c4[7]) >> 2;
+    // every c4 is a multiple of SCALE, so the scaled sum is SCALE x the packed classes
+    p.hi = (((c4[0] * sh + c4[1]) * sh + c4[2]) * sh + c4[3]) / (uint32_t)SCALE;
+    p.lo = (((c4[4] * sh + c4[5]) * sh + c4[6]) * sh + c4[7]) / (uint32_t)SCALE;
     return p;
 }
 __device__ __forceinline__ unsigned long long pack64(const Pack8 &p, int b) { return ((unsigned long long)p.hi << (4 * b)) | p.lo; }

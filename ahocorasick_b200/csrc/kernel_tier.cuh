@@ -15,6 +15,11 @@ namespace acgpu {
 
 struct DevTier {
     const uint32_t *row_words;   // direct-indexed level tables in row layout (copied to shared memory by every CTA)
+    const uint32_t *prow_words;  // the same levels in PAIR layout ({fwd, back} per row, TierTables::prow_words) for k_tier_pair; nullptr: more than 31 classes
+    uint32_t n_prow_words;
+    uint32_t prow_off[10];
+    uint32_t pair_gate_bit;
+    uint32_t pair_low_bit;       // 0: no LOW bit (more than 30 classes), level K-1 takes its own pair-row load
     const uint32_t *cls8;        // 64 words: class of code units 0..255, one byte each
     const uint32_t *kidmask;     // [C^K][2] exact continuation masks of the level-K contexts: backward (this position), forward (the next one); nullptr: no deeper levels
     cudaTextureObject_t kid_tex; // the same table as a linear uint2 texture (k_tier_mask gathers it through the TEX pipe)

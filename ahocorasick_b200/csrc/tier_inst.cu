@@ -1,6 +1,7 @@
 // One translation unit per K: nvcc ... -DTIER_K=k tier_inst.cu
 #include "kernel_tier.cuh"
 #include "kernel_mask.cuh"
+#include "kernel_pair.cuh"
 #include "tier_launch.hpp"
 
 #ifndef TIER_K
@@ -33,11 +34,12 @@ cudaError_t launch_windowed(Kern kern, int grid, int block, size_t smem, const L
     return cudaLaunchKernelEx(&cfg, kern, A, T, P);
 }
 
-template <int LOW, bool MIR>
+template <int LOW, bool MIR, bool PAIR>
 cudaError_t launch_mask_variant(const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, const L2Window &W,
                                 cudaStream_t st) {
     static size_t attr_smem[64] = {0};
-    const void *fn = reinterpret_cast<const void *>(k_tier_mask<TIER_K, LOW, MIR>);
+    auto kern = PAIR ? k_tier_pair<TIER_K, LOW, MIR> : k_tier_mask<TIER_K, LOW, MIR>;
+    const void *fn = reinterpret_cast<const void *>(kern);
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -46,7 +48,7 @@ cudaError_t launch_mask_variant(const DevAutomaton &A, const DevTier &T, const M
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_smem[dev] = smem;
     }
-    return launch_windowed(k_tier_mask<TIER_K, LOW, MIR>, grid, kMaskThreads, smem, W, st, A, T, P);
+    return launch_windowed(kern, grid, kMaskThreads, smem, W, st, A, T, P);
 }
 
 }  // namespace
@@ -54,21 +56,18 @@ cudaError_t launch_mask_variant(const DevAutomaton &A, const DevTier &T, const M
 #define ACGPU_CAT2(a, b) a##b
 #define ACGPU_CAT(a, b) ACGPU_CAT2(a, b)
 
-cudaError_t ACGPU_CAT(mask_launch_, TIER_K)(int low, bool mir, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid,
+cudaError_t ACGPU_CAT(mask_launch_, TIER_K)(int low, bool mir, bool pair, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid,
                                             size_t smem, const L2Window &W, cudaStream_t st) {
     if (TIER_K == 1) low = 2;
-    if (mir) {
-        switch (low) {
-        case 0: return launch_mask_variant<0, true>(A, T, P, grid, smem, W, st);
-        case 1: return launch_mask_variant<1, true>(A, T, P, grid, smem, W, st);
-        default: return launch_mask_variant<2, true>(A, T, P, grid, smem, W, st);
-        }
-    }
-    switch (low) {
-    case 0: return launch_mask_variant<0, false>(A, T, P, grid, smem, W, st);
-    case 1: return launch_mask_variant<1, false>(A, T, P, grid, smem, W, st);
-    default: return launch_mask_variant<2, false>(A, T, P, grid, smem, W, st);
-    }
+#define ACGPU_MASK_CASE(L, M, Q) \
+    if (low == L && mir == M && pair == Q) return launch_mask_variant<L, M, Q>(A, T, P, grid, smem, W, st);
+    if (low < 0 || low > 2) low = 2;
+    ACGPU_MASK_CASE(0, false, false) ACGPU_MASK_CASE(1, false, false) ACGPU_MASK_CASE(2, false, false)
+    ACGPU_MASK_CASE(0, true, false) ACGPU_MASK_CASE(1, true, false) ACGPU_MASK_CASE(2, true, false)
+    ACGPU_MASK_CASE(0, false, true) ACGPU_MASK_CASE(1, false, true) ACGPU_MASK_CASE(2, false, true)
+    ACGPU_MASK_CASE(0, true, true) ACGPU_MASK_CASE(1, true, true) ACGPU_MASK_CASE(2, true, true)
+#undef ACGPU_MASK_CASE
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace acgpu

@@ -20,9 +20,10 @@ struct L2Window {
 
 // mir: the kernel reads the haystack right to left (start anchors over the forward trie: Longest / Shortest).
 // low: 0 = every level below K may hold keywords, 1 = only level K-1 does (and rides in the level-K rows), 2 = none does.
+// pair: k_tier_pair (kernel_pair.cuh, pair rows) instead of k_tier_mask.
 // k_tier_mask<K, LOW> (kernel_mask.cuh): persistent, one CTA per SM; no inter-CTA waiting, plain launch.
 #define ACGPU_DECLARE_MASK(k) \
-    cudaError_t mask_launch_##k(int low, bool mir, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, const L2Window &W, cudaStream_t st);
+    cudaError_t mask_launch_##k(int low, bool mir, bool pair, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, const L2Window &W, cudaStream_t st);
 ACGPU_DECLARE_MASK(1)
 ACGPU_DECLARE_MASK(2)
 ACGPU_DECLARE_MASK(3)

@@ -212,6 +212,25 @@ class _Matcher:
         self._h = h.value
         self._device = device
 
+    @classmethod
+    def from_trie(cls, trie, values: Optional[Sequence] = None, device: int = 0):
+        """A matcher from an already flattened goto trie (trie_desc.FlatTrie -> acgpu_create): what a Java-side builder hands
+        over instead of the keyword strings.  `values`: the Map's value objects, indexed by the trie's value indices."""
+        if trie.family != cls._family or trie.is_map != cls._is_map:
+            raise ValueError("the trie was flattened for another matcher class")
+        self = cls.__new__(cls)
+        self._values = list(values) if values is not None else None
+        self._caseSensitive = trie.case_sensitive
+        if trie.family in (_lib.WHOLEWORD, _lib.WHOLEWORDLONGEST):
+            self._wordChars = trie.word_flags if trie.word_flags is not None else WordCharacters.generateWordCharsFlags()
+        self._h = 0
+        h = C.c_uint64(0)
+        d = trie.desc(device)
+        check(_lib.lib().acgpu_create(C.byref(d), C.byref(h)))
+        self._h = h.value
+        self._device = device
+        return self
+
     def close(self):
         h = getattr(self, "_h", 0)
         if h:

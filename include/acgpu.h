@@ -81,6 +81,40 @@ int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t 
                                uint64_t *handle);
 int acgpu_destroy(uint64_t handle);
 
+/*
+ * The same constructors for a caller that has ALREADY built the dictionary trie - the Java-side builder of BASELINE.json
+ * north_star (1): the reference's own constructor loops (null skip, keyword/value zip, "last duplicate wins", lower-casing of
+ * keyword chars, WordCharacters.trim - AhoCorasickSet.java:20-66, AhoCorasickMap.java:24-77, WholeWordMatchSet.java:138-205)
+ * run unchanged in Java and hand over the flattened goto trie instead of the keyword strings; libacgpu derives its device
+ * tables (class remap, anchored tiers, hashes) from it and uploads them once.
+ *   states are numbered so that parent[s] < s, state 0 is the root (parent[0] = -1);
+ *   edge_char[s] = the UTF-16 unit on the edge parent[s] -> s (already lower-cased when case_sensitive == 0);
+ *   terminal[s] != 0 : a keyword ends in s;  value[s] = its value index (Maps; < n_values; no index twice);
+ *   fail (optional)  : the failure link of every state as the Java builder computed it (AhoCorasickSet.java:68-191 BFS);
+ *                      when given it is checked against the links the trie implies (ACGPU_EINVAL on a mismatch) - the
+ *                      anchored kernels themselves never follow failure links.
+ * struct_size = sizeof(acgpu_automaton_desc) of the caller, so the struct can grow.
+ */
+typedef struct {
+    int32_t struct_size;
+    int32_t family;          /* enum acgpu_family */
+    int32_t is_map;
+    int32_t case_sensitive;
+    int32_t device;
+    int32_t reserved;
+    int64_t n_states;
+    const int32_t *parent;     /* [n_states] */
+    const uint16_t *edge_char; /* [n_states] */
+    const uint8_t *terminal;   /* [n_states] */
+    const uint32_t *value;     /* [n_states] or NULL (Sets) */
+    int64_t n_values;          /* Maps: entries of the Java-side values array */
+    const uint8_t *word_chars; /* WholeWord families: 65536 flags, NULL = default table */
+    const int32_t *fail;       /* [n_states] or NULL */
+} acgpu_automaton_desc;
+int acgpu_create(const acgpu_automaton_desc *desc, uint64_t *handle);
+/* host only: the fingerprint acgpu_build_fingerprint would give for the dictionary the descriptor spells */
+int acgpu_desc_fingerprint(const acgpu_automaton_desc *desc, uint64_t *fingerprint);
+
 /* Diagnostics, host only (no device needed): runs the same dictionary flattening as acgpu_create_from_keywords and
  * returns a 64-bit fingerprint of every table it would upload.  Flattening is deterministic; large dictionaries are
  * inserted concurrently (one shard per first character class) and must give the fingerprint of the serial insert

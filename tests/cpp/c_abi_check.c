@@ -13,7 +13,8 @@ int main(void) {
                        (fn)acgpu_info, (fn)acgpu_char_classes, (fn)acgpu_match_utf16, (fn)acgpu_free_result, (fn)acgpu_match_device,
                        (fn)acgpu_match_device_async, (fn)acgpu_launches_per_match, (fn)acgpu_stream_begin, (fn)acgpu_stream_feed,
                        (fn)acgpu_stream_end, (fn)acgpu_last_error, (fn)acgpu_version, (fn)acgpu_match_utf16_compact, (fn)acgpu_free_matches,
-                       (fn)acgpu_masks_to_records, (fn)acgpu_chain_shard_layout, (fn)acgpu_chain_shard_begin, (fn)acgpu_chain_shard_finish, (fn)acgpu_stream_set_values_only};
+                       (fn)acgpu_masks_to_records, (fn)acgpu_chain_shard_layout, (fn)acgpu_chain_shard_begin, (fn)acgpu_chain_shard_finish, (fn)acgpu_stream_set_values_only,
+                       (fn)acgpu_create, (fn)acgpu_desc_fingerprint};
     unsigned i, n_syms = (unsigned)(sizeof syms / sizeof syms[0]);
     for (i = 0; i < n_syms; i++)
         if (!syms[i]) return 10;
@@ -38,6 +39,31 @@ int main(void) {
     if (strcmp(acgpu_last_error(), "as if contains non-word characters.") != 0) return 18;
     if (acgpu_build_fingerprint(ACGPU_WHOLEWORDLONGEST, chars, offsets, is_null, 5, -1, 1, NULL, &fp3, NULL) != ACGPU_OK) return 19;
     if (acgpu_destroy(0) != ACGPU_EINVAL) return 20;
+    {
+        /* the same dictionary as a flattened goto trie (acgpu_automaton_desc): h e | s h e | r s below "he" */
+        const int32_t parent[] = {-1, 0, 1, 0, 3, 4, 2, 6};
+        const uint16_t edge[] = {0, 'h', 'e', 's', 'h', 'e', 'r', 's'};
+        const uint8_t term[] = {0, 0, 1, 0, 0, 1, 0, 1};
+        const uint32_t value[] = {0, 0, 0, 0, 0, 1, 0, 2};
+        const int32_t fail_links[] = {0, 0, 0, 0, 1, 2, 0, 3};
+        acgpu_automaton_desc d;
+        uint64_t fpd = 0;
+        memset(&d, 0, sizeof d);
+        d.struct_size = (int32_t)sizeof d;
+        d.family = ACGPU_AHOCORASICK;
+        d.is_map = 1;
+        d.n_states = 8;
+        d.parent = parent;
+        d.edge_char = edge;
+        d.terminal = term;
+        d.value = value;
+        d.n_values = 4;
+        d.fail = fail_links;
+        if (acgpu_desc_fingerprint(&d, &fpd) != ACGPU_OK) return 40;
+        if (fpd != fp1) return 41;
+        d.struct_size = 8;
+        if (acgpu_desc_fingerprint(&d, &fpd) != ACGPU_EINVAL) return 42;
+    }
     if (!acgpu_version() || !*acgpu_version()) return 21;
     acgpu_result empty = {0, NULL, NULL};
     acgpu_free_result(&empty); /* releasing an empty result is a no-op */

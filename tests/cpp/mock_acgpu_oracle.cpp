@@ -61,6 +61,34 @@ int acgpu_create_from_keywords(int family, const uint16_t *chars, const int64_t 
     *handle = (uint64_t)(uintptr_t) new Mock{m, n_values >= 0, family};
     return ACGPU_OK;
 }
+// the trie descriptor: the dictionary it spells (Maps: entry v = the keyword of the state with value index v) through the oracle
+int acgpu_create(const acgpu_automaton_desc *d, uint64_t *handle) {
+    if (!d || !handle || d->struct_size < (int32_t)sizeof(acgpu_automaton_desc) || d->n_states < 1) return fail(ACGPU_EINVAL, "mock: bad descriptor");
+    std::vector<int64_t> state_of;
+    if (d->is_map) {
+        state_of.assign((size_t)d->n_values, -1);
+        for (int64_t s = 1; s < d->n_states; s++)
+            if (d->terminal[s]) state_of[d->value[s]] = s;
+    } else {
+        for (int64_t s = 1; s < d->n_states; s++)
+            if (d->terminal[s]) state_of.push_back(s);
+    }
+    std::vector<uint16_t> chars;
+    std::vector<int64_t> offsets(1, 0);
+    std::vector<uint8_t> is_null;
+    for (int64_t s : state_of) {
+        std::vector<uint16_t> rev;
+        for (int64_t t = s; t > 0; t = d->parent[t]) rev.push_back(d->edge_char[t]);
+        chars.insert(chars.end(), rev.rbegin(), rev.rend());
+        offsets.push_back((int64_t)chars.size());
+        is_null.push_back(s < 0 ? 1 : 0);
+    }
+    chars.push_back(0);
+    is_null.push_back(0);
+    return acgpu_create_from_keywords(d->family, chars.data(), offsets.data(), is_null.data(), (int64_t)state_of.size(),
+                                      d->is_map ? d->n_values : -1, d->case_sensitive, d->word_chars, d->device, handle);
+}
+int acgpu_desc_fingerprint(const acgpu_automaton_desc *, uint64_t *) { return fail(ACGPU_EUNSUPPORTED, "mock: no builder"); }
 int acgpu_build_fingerprint(int, const uint16_t *, const int64_t *, const uint8_t *, int64_t, int64_t, int, const uint8_t *, uint64_t *,
                             double *) {
     return fail(ACGPU_EUNSUPPORTED, "mock: no builder");

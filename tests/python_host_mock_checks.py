@@ -104,4 +104,18 @@ for bad in (None,):
         raise SystemExit("TypeError expected")
     except TypeError:
         pass
+# constructors from a flattened goto trie (acgpu_create, trie_desc.flatten_trie = the Java-side builder's loops)
+from ahocorasick_b200 import trie_desc
+_FAM = {"ahocorasick": 0, "longest": 1, "shortest": 2, "wholeword": 3, "wholewordlongest": 4}
+for family in MAPS:
+    kws = ["he", "she", None, "hers", "his", "he", "", "She"]
+    hay = "ushers and She said his is hers; he!"
+    for cs in (True, False):
+        nv = len(kws) - 1  # a shorter values Iterable: the zip drops the last keyword
+        want = oracle_calls(ora.Matcher(family, kws, n_values=nv, case_sensitive=cs), hay)
+        gm = MAPS[family].from_trie(trie_desc.flatten_trie(_FAM[family], kws, list(range(nv)), cs), list(range(nv)))
+        c = Collect()
+        gm.match(hay, c)
+        assert c.calls == want, (family, cs, c.calls, want)
+        n_checks += 1
 print("python host mirror ok: %d checks" % n_checks)

@@ -1076,3 +1076,41 @@ def test_chain_shards_whole_buffer_pointers_and_refusals():
     assert lib.acgpu_chain_shard_begin(ac.AhoCorasickSet(kws, True).handle, d_all.data_ptr(), n, n, d_map.data_ptr(), C.byref(h), None) == _lib.EINVAL
     wide = ac.LongestMatchSet(["".join(chr(0x41 + i) for i in range(40)), "ab"], True)
     assert lib.acgpu_chain_shard_begin(wide.handle, d_all.data_ptr(), n, n, d_map.data_ptr(), C.byref(h), None) == _lib.EUNSUPPORTED
+
+
+@pytest.mark.parametrize("family", FAMILIES)
+@pytest.mark.parametrize("cs", [True, False])
+def test_create_from_trie_descriptor(family, cs):
+    """acgpu_create(const acgpu_automaton_desc*): a matcher built from the flattened goto trie a Java-side builder hands over
+    (trie_desc.flatten_trie restates the reference's constructor loops: null skip, zip, last duplicate wins) gives the
+    oracle's ordered stream - nulls, empty keywords, duplicates, a shorter values Iterable, failure links checked."""
+    from ahocorasick_b200 import _lib, trie_desc
+    fam_id = {"ahocorasick": 0, "longest": 1, "shortest": 2, "wholeword": 3, "wholewordlongest": 4}[family]
+    rng = random.Random(hash((family, cs, "desc")) & 0xFFFF)
+    for it in range(40):
+        alphabet = rng.choice(["ab", "abc", "abAB", "abcdeXYZ"])
+        nk = rng.randint(1, 12)
+        kws = [_rand_word(rng, alphabet, 1, rng.choice([2, 3, 5, 9])) for _ in range(nk)]
+        if rng.random() < 0.4:
+            kws.insert(rng.randint(0, len(kws)), rng.choice([None, "", kws[0]]))
+        sep = " " if family.startswith("wholeword") or rng.random() < 0.3 else ""
+        hay = "".join(rng.choice(alphabet + sep * 2) for _ in range(rng.randint(0, 300)))
+        nv = rng.choice([len(kws), max(0, len(kws) - 1)])
+        want = oracle_stream(ora.Matcher(family, kws, n_values=nv, case_sensitive=cs), hay)
+        trie = trie_desc.flatten_trie(fam_id, kws, list(range(nv)), cs)
+        m = MAPS[family].from_trie(trie, list(range(nv)))
+        assert gpu_map_stream(m, hay) == want, (kws, hay, cs, nv)
+        want_set = [(s, e) for s, e, _ in oracle_stream(ora.Matcher(family, kws, case_sensitive=cs), hay)]
+        s = SETS[family].from_trie(trie_desc.flatten_trie(fam_id, kws, None, cs))
+        assert gpu_set_stream(s, hay) == want_set, (kws, hay, cs)
+    # a larger dictionary through the tier path, and a descriptor the library must refuse
+    kws = W.make_keywords(5000, 77)
+    hay = W.make_haystack(W.HaystackSpec("lower", 5, kws), 300_000)
+    trie = trie_desc.flatten_trie(fam_id, kws, list(range(len(kws))), cs)
+    got = MAPS[family].from_trie(trie, list(range(len(kws)))).match_records(hay)
+    want = ora.Matcher(family, kws, n_values=len(kws), case_sensitive=cs).match(hay)
+    assert np.array_equal(got.start, want["start"]) and np.array_equal(got.end, want["end"])
+    assert np.array_equal(got.value.astype(np.int64), want["value"].astype(np.int64))
+    trie.fail[len(trie.fail) // 2] ^= 1
+    with pytest.raises(_lib.AcgpuError):
+        MAPS[family].from_trie(trie, list(range(len(kws))))

@@ -205,3 +205,50 @@ def test_integration_doc_names_every_entry_point():
     assert not missing, missing
     for s in ("acgpu_last_error", "acgpu_free_result"):
         assert s in doc
+
+
+def test_trie_descriptor_flattens_like_the_keyword_constructor():
+    """acgpu_create(const acgpu_automaton_desc*) (host half, acgpu_desc_fingerprint): the tables derived from a flattened
+    goto trie are those of acgpu_create_from_keywords for the dictionary the trie spells - Maps keep their value indices,
+    Sets re-insert the keywords in trie order (which reproduces the state numbering); failure links, when given, are
+    checked; malformed descriptors are refused."""
+    import workloads as W
+    from ahocorasick_b200 import _lib, trie_desc
+    from ahocorasick_b200.matchers import _pack_keywords
+
+    def fp_kw(family, kws, n_values, cs):
+        chars, offsets, is_null, n = _pack_keywords(kws)
+        fp = C.c_uint64(0)
+        _lib.check(_lib.lib().acgpu_build_fingerprint(family, chars.ctypes.data, offsets.ctypes.data, is_null.ctypes.data, n, n_values,
+                                                      int(cs), None, C.byref(fp), None))
+        return fp.value
+
+    kws = W.make_keywords(4000, 21) + ["a", "ab", "abc"]
+    for family in range(5):
+        for cs in (True, False):
+            t = trie_desc.flatten_trie(family, kws + [None], list(range(len(kws) + 1)), cs)
+            assert t.fingerprint() == fp_kw(family, kws + [None], len(kws) + 1, cs), (family, cs)
+            t = trie_desc.flatten_trie(family, kws, None, cs)
+            # the dictionary in trie order: one keyword per terminal state, ascending
+            words = []
+            for s in np.flatnonzero(t.terminal):
+                u = []
+                while s > 0:
+                    u.append(int(t.edge_char[s]))
+                    s = int(t.parent[s])
+                words.append("".join(map(chr, reversed(u))))
+            assert sorted(words) == sorted(set(kws))
+            assert t.fingerprint() == fp_kw(family, words, -1, cs), (family, cs)
+    t = trie_desc.flatten_trie(0, ["abcd", "bcd", "cd"], None, True)
+    assert t.fail.tolist() == [0, 0, 5, 6, 7, 0, 8, 9, 0, 0]
+    t.fail[3] = 2
+    with pytest.raises(_lib.AcgpuError):
+        t.fingerprint()
+    t = trie_desc.flatten_trie(0, ["ab", "b"], [0, 1], True)
+    t.value[:] = 1  # two states carry one value index
+    with pytest.raises(_lib.AcgpuError):
+        t.fingerprint()
+    t = trie_desc.flatten_trie(0, ["ab", "b"], None, True)
+    t.parent[1] = 2  # parents must precede children
+    with pytest.raises(_lib.AcgpuError):
+        t.fingerprint()
