@@ -21,6 +21,7 @@
 #include "kernel_tier.cuh"
 #include "kernel_mask.cuh"
 #include "kernel_emit.cuh"
+#include "kernel_fuse.cuh"
 #include "kernel_sel2.cuh"
 #include "kernel_ww.cuh"
 #include "kernel_wide.cuh"
@@ -88,6 +89,7 @@ struct Matcher {
     L2Window l2win;         // child masks + deep table, kept L2-resident across the streaming traffic
     size_t mask_smem = 0;
     bool mask_pair = false;   // k_tier_pair (generation 4, pair rows) instead of k_tier_mask
+    size_t fuse_smem = 0;     // k_tier_fused (generation 5, one launch): shared memory it needs; 0 = not available
     // AhoCorasick family outside the tier envelope (kernel_wide.cuh)
     bool use_wide = false;
     DevWide wide{};
@@ -155,6 +157,15 @@ int upload_tier(Matcher *m) {
     const char *gen = getenv("ACGPU_MASK_GEN");
     m->mask_pair = !t.prow_words.empty() && !(gen && gen[0] == '3');
     m->mask_smem = mask_smem_bytes(m->mask_pair ? t.prow_words.size() : t.row_words.size());
+    {
+        // generation 5 (k_tier_fused: masks and records in one persistent launch) - opt-in (ACGPU_FUSE=1): parity-green, but
+        // measured 7.1 ms against 3.8 ms per 10^9 chars on configs[4] (profiles/r02_fused_summary.md)
+        int max_smem = 0;
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device);
+        const size_t need = fuse_smem_bytes(t.row_words.size(), m->dev.is_map != 0);
+        const char *fz = getenv("ACGPU_FUSE");
+        m->fuse_smem = (need <= static_cast<size_t>(max_smem) && fz && fz[0] == '1') ? need : 0;
+    }
     if (m->mask_smem > 227 * 1024) return ACGPU_OK;
     size_t off = 0;
     auto reserve = [&](size_t bytes) {
@@ -596,36 +607,143 @@ int enqueue_mask_scan(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit
     return ACGPU_OK;
 }
 
+void fill_emit_args(EmitArgs &E, const uint16_t *d_hay, int64_t n, char *w, const MaskWs &L, int64_t origin, int2 *d_pos, uint32_t *d_val,
+                    int64_t cap, const RunOpts &opt) {
+    E.hay = d_hay;
+    E.n = n;
+    E.masks = reinterpret_cast<uint32_t *>(w + L.o_mask);
+    E.row_excl = reinterpret_cast<uint32_t *>(w + L.o_cnt);
+    E.block_excl = reinterpret_cast<unsigned long long *>(w + L.o_blk);
+    E.n_rows = L.n_rows;
+    E.origin = origin;
+    E.pos_base = opt.pos_base;
+    E.pos_out = d_pos;
+    E.val_out = d_val;
+    E.cap = cap;
+}
+
+int launch_emit(Matcher *m, const EmitArgs &E, cudaStream_t st) {
+    // many small CTAs: the hardware scheduler evens out SMs that run at different speeds (measured: 128 per SM beats 8 by 12%)
+    static const char *gm = getenv("ACGPU_EMIT_GRID");
+    const int per_sm = gm ? std::max(1, atoi(gm)) : 128;
+    const int egrid = static_cast<int>(std::min<int64_t>((E.n_rows + kEmitWarps - 1) / kEmitWarps, static_cast<int64_t>(m->sm_count) * per_sm));
+    if (m->dev.is_map)
+        k_tier_emit<true><<<egrid, kEmitWarps * 32, 0, st>>>(m->dev, m->tier, E);
+    else
+        k_tier_emit<false><<<egrid, kEmitWarps * 32, 0, st>>>(m->dev, m->tier, E);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ACGPU_ECUDA, std::string("k_tier_emit: ") + cudaGetErrorString(e));
+    return ACGPU_OK;
+}
+
+// Tunables of the fused run (env: experiments, tools/gpu_r2o.sh)
+struct FuseTuning {
+    int ticket_rows = 16;   // rows of 256 positions per ticket
+    int ring_mb = 64;       // ring of hit masks (stays in the 126 MB L2)
+    int high_mb = 32;       // makers run at most this many MB of masks ahead of the expanders
+    int64_t min_rows = 8192;
+};
+const FuseTuning &fuse_tuning() {
+    static const FuseTuning t = [] {
+        FuseTuning v;
+        if (const char *e = getenv("ACGPU_FUSE_ROWS")) v.ticket_rows = std::min(32, std::max(1, atoi(e)));
+        if (const char *e = getenv("ACGPU_FUSE_RING_MB")) v.ring_mb = std::max(1, atoi(e));
+        if (const char *e = getenv("ACGPU_FUSE_HIGH_MB")) v.high_mb = std::max(1, atoi(e));
+        if (const char *e = getenv("ACGPU_FUSE_MIN_ROWS")) v.min_rows = std::max<int64_t>(1, atoll(e));
+        return v;
+    }();
+    return t;
+}
+
+cudaError_t launch_fuse(Matcher *m, const MaskArgs &P, const FuseArgs &F, int grid, cudaStream_t st) {
+    const int low = mask_low_variant(m->tier, false);
+    const bool is_map = m->dev.is_map != 0;
+    switch (m->tier.K) {
+    case 1: return fuse_launch_1(low, is_map, m->dev, m->tier, P, F, grid, m->fuse_smem, st);
+    case 2: return fuse_launch_2(low, is_map, m->dev, m->tier, P, F, grid, m->fuse_smem, st);
+    case 3: return fuse_launch_3(low, is_map, m->dev, m->tier, P, F, grid, m->fuse_smem, st);
+    case 4: return fuse_launch_4(low, is_map, m->dev, m->tier, P, F, grid, m->fuse_smem, st);
+    case 5: return fuse_launch_5(low, is_map, m->dev, m->tier, P, F, grid, m->fuse_smem, st);
+    case 6: return fuse_launch_6(low, is_map, m->dev, m->tier, P, F, grid, m->fuse_smem, st);
+    case 7: return fuse_launch_7(low, is_map, m->dev, m->tier, P, F, grid, m->fuse_smem, st);
+    default: return fuse_launch_8(low, is_map, m->dev, m->tier, P, F, grid, m->fuse_smem, st);
+    }
+}
+
+// k_tier_fused: one persistent launch makes the hit masks and expands them into records (kernel_fuse.cuh)
+int enqueue_fused(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from, int64_t emit_to, int64_t origin, int2 *d_pos,
+                  uint32_t *d_val, int64_t cap, unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
+    const FuseTuning &tune = fuse_tuning();
+    const int64_t n_rows = (emit_to - origin + kMaskRow - 1) / kMaskRow;
+    const int64_t tr = tune.ticket_rows;
+    const int64_t n_tickets = (n_rows + tr - 1) / tr;
+    const int64_t ticket_bytes = tr * kMaskRow * 2;
+    int64_t ring = 1;
+    while (ring * 2 * ticket_bytes <= static_cast<int64_t>(tune.ring_mb) << 20) ring *= 2;
+    while (ring / 2 >= n_tickets && ring > 1) ring /= 2;  // short runs: no more slots than tickets (rounded up to a power of two)
+    const int64_t high = std::max<int64_t>(1, std::min<int64_t>(ring, (static_cast<int64_t>(tune.high_mb) << 20) / ticket_bytes));
+    const int64_t n_pad = (n_tickets + kFuseScanStep - 1) / kFuseScanStep * kFuseScanStep;
+    Scratch S;
+    const size_t o_ab = S.reserve(256);
+    const size_t o_agg = S.reserve(static_cast<size_t>(n_pad) * 4);
+    const size_t o_excl = S.reserve(static_cast<size_t>(n_pad) * 8);
+    const size_t o_exp = S.reserve(static_cast<size_t>(n_tickets) * 4);
+    const size_t o_zero_end = S.off;
+    const size_t o_ring = S.reserve(static_cast<size_t>(ring * ticket_bytes));
+    void *ws = nullptr;
+    CU_TRY(cudaMallocAsync(&ws, S.off, st));
+    char *w = static_cast<char *>(ws);
+    int rc = ACGPU_OK;
+    if (cudaMemsetAsync(w, 0, o_zero_end, st) != cudaSuccess) rc = fail(ACGPU_ECUDA, "memset failed");
+    if (rc == ACGPU_OK) {
+        MaskArgs P{};
+        P.hay = d_hay;
+        P.n = n;
+        P.emit_from = emit_from;
+        P.emit_to = emit_to;
+        P.origin = origin;
+        P.masks = reinterpret_cast<uint32_t *>(w + o_ring);
+        P.n_rows = n_rows;
+        FuseArgs F{};
+        F.E.hay = d_hay;
+        F.E.n = n;
+        F.E.n_rows = n_rows;
+        F.E.origin = origin;
+        F.E.pos_base = opt.pos_base;
+        F.E.pos_out = d_pos;
+        F.E.val_out = d_val;
+        F.E.cap = cap;
+        F.agg = reinterpret_cast<uint32_t *>(w + o_agg);
+        F.excl = reinterpret_cast<unsigned long long *>(w + o_excl);
+        F.expanded = reinterpret_cast<uint32_t *>(w + o_exp);
+        F.ab = reinterpret_cast<unsigned long long *>(w + o_ab);
+        F.total_out = d_total;
+        F.n_tickets = static_cast<uint32_t>(n_tickets);
+        F.ticket_rows = static_cast<uint32_t>(tr);
+        F.ring_tickets = static_cast<uint32_t>(ring);
+        F.high = static_cast<uint32_t>(high);
+        const int grid = static_cast<int>(std::min<int64_t>((n_tickets + kMaskWarps - 1) / kMaskWarps + 1, m->sm_count));
+        const cudaError_t e = launch_fuse(m, P, F, grid, st);
+        if (e != cudaSuccess) rc = fail(ACGPU_ECUDA, std::string("k_tier_fused: ") + cudaGetErrorString(e));
+    }
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
 int enqueue_mask(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from, int64_t emit_to, int64_t origin, int2 *d_pos,
                  uint32_t *d_val, int64_t cap, unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
-    const MaskWs L = mask_ws_layout(emit_to, origin);
+    const MaskWs whole = mask_ws_layout(emit_to, origin);
+    if (m->fuse_smem && cap > 0 && whole.n_rows >= fuse_tuning().min_rows)
+        return enqueue_fused(m, d_hay, n, emit_from, emit_to, origin, d_pos, d_val, cap, d_total, st, opt);
+    const MaskWs &L = whole;
     void *ws = nullptr;
     CU_TRY(cudaMallocAsync(&ws, L.bytes, st));
     char *w = static_cast<char *>(ws);
     int rc = enqueue_mask_scan(m, d_hay, n, emit_from, emit_to, origin, w, L, d_total, st);
     if (rc == ACGPU_OK && cap > 0) {
         EmitArgs E{};
-        E.hay = d_hay;
-        E.n = n;
-        E.masks = reinterpret_cast<uint32_t *>(w + L.o_mask);
-        E.row_excl = reinterpret_cast<uint32_t *>(w + L.o_cnt);
-        E.block_excl = reinterpret_cast<unsigned long long *>(w + L.o_blk);
-        E.n_rows = L.n_rows;
-        E.origin = origin;
-        E.pos_base = opt.pos_base;
-        E.pos_out = d_pos;
-        E.val_out = d_val;
-        E.cap = cap;
-        // many small CTAs: the hardware scheduler evens out SMs that run at different speeds (measured: 128 per SM beats 8 by 12%)
-        const char *gm = getenv("ACGPU_EMIT_GRID");
-        const int per_sm = gm ? std::max(1, atoi(gm)) : 128;
-        const int egrid = static_cast<int>(std::min<int64_t>((L.n_rows + kEmitWarps - 1) / kEmitWarps, static_cast<int64_t>(m->sm_count) * per_sm));
-        if (m->dev.is_map)
-            k_tier_emit<true><<<egrid, kEmitWarps * 32, 0, st>>>(m->dev, m->tier, E);
-        else
-            k_tier_emit<false><<<egrid, kEmitWarps * 32, 0, st>>>(m->dev, m->tier, E);
-        const cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) rc = fail(ACGPU_ECUDA, std::string("k_tier_emit: ") + cudaGetErrorString(e));
+        fill_emit_args(E, d_hay, n, w, L, origin, d_pos, d_val, cap, opt);
+        rc = launch_emit(m, E, st);
     }
     cudaFreeAsync(ws, st);  // on every path (no scratch leak when a launch fails)
     return rc;

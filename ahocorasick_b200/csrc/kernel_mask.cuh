@@ -152,9 +152,9 @@ __device__ __forceinline__ unsigned long long context_of(const Pack8 &P0, const 
 // One queued context: levels K+1.. against the deep table; hits are OR-ed into the stored mask of the position and
 // added to its row's count.
 template <int K>
-__device__ __noinline__ void deep_resolve(const uint4 *buckets, unsigned long long hash_seed, uint32_t n_buckets, int b,
-                                          uint32_t inv_b, unsigned long long ctx, uint32_t pos, int max_len, uint32_t *masks,
-                                          uint32_t *row_count) {
+__device__ __noinline__ uint32_t deep_resolve(const uint4 *buckets, unsigned long long hash_seed, uint32_t n_buckets, int b,
+                                              uint32_t inv_b, unsigned long long ctx, uint32_t pos, int max_len, uint32_t *masks,
+                                              uint32_t *row_count) {
     DevTier T;  // only the fields deep_bits reads
     T.buckets = buckets;
     T.hash_seed = hash_seed;
@@ -164,13 +164,29 @@ __device__ __noinline__ void deep_resolve(const uint4 *buckets, unsigned long lo
     const uint32_t bits = deep_bits<K>(T, ctx, (1u << b) - 1u, max_len);
     if (bits) {
         atomicOr(masks + (pos >> 1), (__brev(bits) >> (16 + K)) << ((pos & 1u) * 16u));
-        atomicAdd(row_count + (pos >> 8), (uint32_t)__popc(bits));
+        if (row_count) atomicAdd(row_count + (pos >> 8), (uint32_t)__popc(bits));  // fused runs (kernel_fuse.cuh) count per ticket instead
     }
+    return (uint32_t)__popc(bits);
 }
 
-template <int K, int LOW, bool MIR>
-__global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomaton A, const DevTier T, const MaskArgs P) {
-    extern __shared__ __align__(16) uint32_t s_mem[];
+// How a warp of the mask kernel gets its work.  PlainSched: tickets of kMaskChunkRows rows from one counter, masks and row
+// counts at the rows' own places (k_tier_mask, three launches per match).  kernel_fuse.cuh has the scheduler of the
+// single-launch path, where a warp alternates between making masks and expanding them.
+struct PlainSched {
+    static constexpr bool kFused = false;
+    unsigned int *ticket;
+    __device__ __forceinline__ uint32_t next(int lane) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(ticket, 1u);
+        return __shfl_sync(0xFFFFFFFFu, chunk, 0);
+    }
+    __device__ __forceinline__ int rows() const { return kMaskChunkRows; }
+    __device__ __forceinline__ int64_t mask_row0(uint32_t, int64_t row0) const { return row0; }
+    __device__ __forceinline__ void finish(uint32_t, uint32_t, int) {}
+};
+
+template <int K, int LOW, bool MIR, class Sched>
+__device__ __forceinline__ void tier_mask_body(const DevAutomaton &A, const DevTier &T, const MaskArgs &P, Sched &S, uint32_t *s_mem) {
     uint8_t *s_cls4 = reinterpret_cast<uint8_t *>(s_mem);
     const unsigned char *s_tab = reinterpret_cast<const unsigned char *>(s_mem + 64);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -201,21 +217,22 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
     const unsigned char *kid_bytes = reinterpret_cast<const unsigned char *>(T.kidmask);
 #endif
     uint32_t q_cnt = 0;
+    uint32_t deep_hits = 0, shallow_hits = 0;  // fused runs: records of the current ticket (per lane / warp-uniform)
 
     // entries [first, first + count) of the queue (count <= 32) against the deep table.  (A separate gather kernel fed
     // from a candidate list measured 3% slower end to end and costs 1.5 GB of scratch per 10^9 chars.)
     auto probe = [&](uint32_t first, uint32_t count) {
         if ((uint32_t)lane < count)
-            deep_resolve<K>(T.buckets, T.hash_seed, T.n_buckets, T.b, T.inv_b, s_qctx[first + lane], s_qpos[first + lane], A.max_len,
-                            P.masks, P.row_count);
+            deep_hits += deep_resolve<K>(T.buckets, T.hash_seed, T.n_buckets, T.b, T.inv_b, s_qctx[first + lane], s_qpos[first + lane], A.max_len,
+                                         P.masks, Sched::kFused ? nullptr : P.row_count);
     };
+    const int t_rows = S.rows();
     while (true) {
-        uint32_t chunk = 0;
-        if (lane == 0) chunk = atomicAdd(P.ticket, 1u);
-        chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
-        const int64_t row0 = (int64_t)chunk * kMaskChunkRows;
-        if (row0 >= P.n_rows) break;
-        const int n_cr = (int)min((int64_t)kMaskChunkRows, P.n_rows - row0);  // rows of this chunk
+        const uint32_t chunk = S.next(lane);
+        const int64_t row0 = (int64_t)chunk * t_rows;
+        if (chunk == 0xFFFFFFFFu || row0 >= P.n_rows) break;
+        const int n_cr = (int)min((int64_t)t_rows, P.n_rows - row0);  // rows of this chunk
+        const int64_t m_row0 = S.mask_row0(chunk, row0);               // where the chunk's masks go (fused runs: a ring)
         // 64-bit position arithmetic once per chunk; rows use 32-bit offsets from here
         const int64_t c_lo = P.origin + row0 * kMaskRow, c_hi = c_lo + (int64_t)n_cr * kMaskRow;
         const bool chunk_in = c_lo - 16 >= 0 && c_hi <= P.n;                    // every load of the chunk is inside the haystack
@@ -248,8 +265,8 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
             car1.hi = __shfl_sync(0xFFFFFFFFu, h.hi, 1); car1.lo = __shfl_sync(0xFFFFFFFFu, h.lo, 1);
         }
         // per-chunk bases of the outputs
-        uint4 *mp = reinterpret_cast<uint4 *>(P.masks) + (MIR ? (size_t)(P.n_rows - 1 - row0) * 32 + (31 - lane) : (size_t)row0 * 32 + lane);
-        const uint32_t q0 = (uint32_t)(row0 * kMaskRow) + lane * 8;
+        uint4 *mp = reinterpret_cast<uint4 *>(P.masks) + (MIR ? (size_t)(P.n_rows - 1 - row0) * 32 + (31 - lane) : (size_t)m_row0 * 32 + lane);
+        const uint32_t q0 = (uint32_t)(m_row0 * kMaskRow) + lane * 8;
         for (int r = 0; r < n_cr; ++r) {
             const uint4 vnn = fetch(r + 2);
             uint32_t c4[8];
@@ -365,7 +382,10 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
                 *(mp + r * 32) = mw;
             const uint32_t cnt = __popc(mw.x) + __popc(mw.y) + __popc(mw.z) + __popc(mw.w);
             const uint32_t row_total = __reduce_add_sync(0xFFFFFFFFu, cnt);
-            if (lane == 0) P.row_count[MIR ? P.n_rows - 1 - (row0 + r) : row0 + r] = row_total;
+            if (Sched::kFused)
+                shallow_hits += row_total;
+            else if (lane == 0)
+                P.row_count[MIR ? P.n_rows - 1 - (row0 + r) : row0 + r] = row_total;
             __syncwarp();
             // ---- queue the continuing contexts; probe whenever 32 are waiting
             while (true) {
@@ -389,8 +409,24 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomato
                 }
             }
         }
+        if (Sched::kFused) {
+            // the ticket's masks must be final before it is handed to the emit side: drain the queue now
+            if (q_cnt) probe(0u, q_cnt);
+            q_cnt = 0;
+            const uint32_t total = shallow_hits + __reduce_add_sync(0xFFFFFFFFu, deep_hits);
+            shallow_hits = 0;
+            deep_hits = 0;
+            S.finish(chunk, total, lane);
+        }
     }
     if (q_cnt) probe(0u, q_cnt);
+}
+
+template <int K, int LOW, bool MIR>
+__global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomaton A, const DevTier T, const MaskArgs P) {
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    PlainSched S{P.ticket};
+    tier_mask_body<K, LOW, MIR>(A, T, P, S, s_mem);
 }
 
 }  // namespace acgpu

@@ -2,6 +2,7 @@
 #include "kernel_tier.cuh"
 #include "kernel_mask.cuh"
 #include "kernel_pair.cuh"
+#include "kernel_fuse.cuh"
 #include "tier_launch.hpp"
 
 #ifndef TIER_K
@@ -51,6 +52,22 @@ cudaError_t launch_mask_variant(const DevAutomaton &A, const DevTier &T, const M
     return launch_windowed(kern, grid, kMaskThreads, smem, W, st, A, T, P);
 }
 
+template <int LOW, bool MAP>
+cudaError_t launch_fuse_variant(const DevAutomaton &A, const DevTier &T, const MaskArgs &P, const FuseArgs &F, int grid, size_t smem, cudaStream_t st) {
+    static size_t attr_smem[64] = {0};
+    auto kern = k_tier_fused<TIER_K, LOW, MAP>;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || attr_smem[dev] < smem) {
+        e = cudaFuncSetAttribute(reinterpret_cast<const void *>(kern), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_smem[dev] = smem;
+    }
+    kern<<<grid, kMaskThreads, smem, st>>>(A, T, P, F);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 #define ACGPU_CAT2(a, b) a##b
@@ -67,6 +84,17 @@ cudaError_t ACGPU_CAT(mask_launch_, TIER_K)(int low, bool mir, bool pair, const 
     ACGPU_MASK_CASE(0, false, true) ACGPU_MASK_CASE(1, false, true) ACGPU_MASK_CASE(2, false, true)
     ACGPU_MASK_CASE(0, true, true) ACGPU_MASK_CASE(1, true, true) ACGPU_MASK_CASE(2, true, true)
 #undef ACGPU_MASK_CASE
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t ACGPU_CAT(fuse_launch_, TIER_K)(int low, bool is_map, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, const FuseArgs &F, int grid,
+                                            size_t smem, cudaStream_t st) {
+    if (TIER_K == 1 || low < 0 || low > 2) low = 2;
+#define ACGPU_FUSE_CASE(L, M) \
+    if (low == L && is_map == M) return launch_fuse_variant<L, M>(A, T, P, F, grid, smem, st);
+    ACGPU_FUSE_CASE(0, false) ACGPU_FUSE_CASE(1, false) ACGPU_FUSE_CASE(2, false)
+    ACGPU_FUSE_CASE(0, true) ACGPU_FUSE_CASE(1, true) ACGPU_FUSE_CASE(2, true)
+#undef ACGPU_FUSE_CASE
     return cudaErrorInvalidValue;
 }
 

@@ -9,6 +9,7 @@ namespace acgpu {
 
 struct DevTier;
 struct MaskArgs;
+struct FuseArgs;
 
 // Tables that every probe gathers from (child masks + deep table): the launches ask L2 to keep them resident while the
 // haystack, mask and record streams pass through (cudaLaunchAttributeAccessPolicyWindow; bytes == 0: no window).
@@ -22,8 +23,10 @@ struct L2Window {
 // low: 0 = every level below K may hold keywords, 1 = only level K-1 does (and rides in the level-K rows), 2 = none does.
 // pair: k_tier_pair (kernel_pair.cuh, pair rows) instead of k_tier_mask.
 // k_tier_mask<K, LOW> (kernel_mask.cuh): persistent, one CTA per SM; no inter-CTA waiting, plain launch.
+// fuse_launch_k: k_tier_fused<K, LOW, isMap> (kernel_fuse.cuh) - masks and records in one persistent launch.
 #define ACGPU_DECLARE_MASK(k) \
-    cudaError_t mask_launch_##k(int low, bool mir, bool pair, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, const L2Window &W, cudaStream_t st);
+    cudaError_t mask_launch_##k(int low, bool mir, bool pair, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, const L2Window &W, cudaStream_t st); \
+    cudaError_t fuse_launch_##k(int low, bool is_map, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, const FuseArgs &F, int grid, size_t smem, cudaStream_t st);
 ACGPU_DECLARE_MASK(1)
 ACGPU_DECLARE_MASK(2)
 ACGPU_DECLARE_MASK(3)
