@@ -346,6 +346,71 @@ void build_wide(HostAutomaton &a, const std::vector<uint32_t> &node_parent, cons
         e[0] = static_cast<uint32_t>(id);
         e[1] |= a.node_info[id] & 0xFFu;
     }
+    // ---- path-compressed edges below level 2 (HostAutomaton::wide_chain, wide_pair16)
+    const int64_t N = a.n_nodes;
+    std::vector<uint32_t> first(static_cast<size_t>(N) + 1, 0), kids(static_cast<size_t>(N > 1 ? N - 1 : 0));
+    for (int64_t id = 1; id < N; id++) ++first[node_parent[id] + 1];
+    for (int64_t i = 0; i < N; i++) first[i + 1] += first[i];
+    {
+        std::vector<uint32_t> at(first.begin(), first.end() - 1);
+        for (int64_t id = 1; id < N; id++) kids[at[node_parent[id]]++] = static_cast<uint32_t>(id);
+        for (int64_t n = 0; n < N; n++)  // children in class order
+            std::sort(kids.begin() + first[n], kids.begin() + first[n + 1], [&](uint32_t x, uint32_t y) { return node_cls[x] < node_cls[y]; });
+    }
+    auto n_kids = [&](uint32_t n) { return first[n + 1] - first[n]; };
+    auto kid_mask = [&](uint32_t n) {
+        uint64_t m = 0;
+        for (uint32_t k = first[n]; k < first[n + 1]; k++) m |= 1ull << node_cls[kids[k]];
+        return m;
+    };
+    a.wide_chain.clear();
+    // junctions in breadth-first order; a junction's children take the next n_kids entries.  entry_of[i] = the child node
+    // that entry i describes (filled in below).
+    std::vector<uint32_t> entry_child;
+    a.wide_pair16.assign(static_cast<size_t>(C * C * 4), 0);
+    for (int64_t c0 = 0; c0 < C; c0++)
+        for (int64_t c1 = 0; c1 < C; c1++) a.wide_pair16[static_cast<size_t>(c0 * C + c1) * 4 + 1] = a.wide_pair[static_cast<size_t>(c0 * C + c1) * 2 + 1];
+    std::vector<std::pair<uint32_t, uint32_t>> todo;  // (junction, first entry of its children)
+    auto reserve_children = [&](uint32_t j) {
+        const uint32_t at = static_cast<uint32_t>(entry_child.size());
+        for (uint32_t k = first[j]; k < first[j + 1]; k++) entry_child.push_back(kids[k]);
+        todo.emplace_back(j, at);
+        return at;
+    };
+    for (int64_t id = 1; id < N; id++) {
+        const uint32_t p2 = node_parent[id];
+        if (p2 == 0 || node_parent[p2] != 0) continue;  // level-2 nodes only
+        uint32_t *e = &a.wide_pair16[static_cast<size_t>(static_cast<int64_t>(node_cls[p2]) * C + node_cls[id]) * 4];
+        e[1] |= (a.node_info[id] & 0xFFu) | 1u << 17;
+        const uint64_t m = kid_mask(static_cast<uint32_t>(id));
+        e[2] = static_cast<uint32_t>(m);
+        e[3] = static_cast<uint32_t>(m >> 32);
+        e[0] = m ? reserve_children(static_cast<uint32_t>(id)) : 0u;
+    }
+    for (size_t t = 0; t < todo.size(); t++) {
+        const uint32_t j = todo[t].first, at = todo[t].second;
+        for (uint32_t k = 0; k < n_kids(j); k++) {
+            const uint32_t child = entry_child[at + k];
+            uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            uint32_t n = child, L = 0, term = (a.node_info[child] & kInfoTerminal) ? 1u : 0u;
+            while (n_kids(n) == 1 && L < static_cast<uint32_t>(kWideChainMax)) {
+                n = kids[first[n]];
+                w[4 + ((7u - L) >> 2)] |= static_cast<uint32_t>(node_cls[n]) << (((7u - L) & 3u) * 8u);  // step k in byte 7 - k
+                ++L;
+                if (a.node_info[n] & kInfoTerminal) term |= 1u << L;
+            }
+            const uint64_t m = kid_mask(n);
+            w[0] = static_cast<uint32_t>(m);
+            w[1] = static_cast<uint32_t>(m >> 32);
+            w[2] = m ? reserve_children(n) : 0u;
+            w[3] = L | term << 4;
+            w[6] = n;
+            const size_t o = static_cast<size_t>(at + k) * 8;
+            if (a.wide_chain.size() < o + 8) a.wide_chain.resize(std::max(o + 8, a.wide_chain.size() * 2), 0);
+            std::memcpy(&a.wide_chain[o], w, sizeof w);
+        }
+    }
+    a.wide_chain.resize(entry_child.size() * 8);
 }
 
 // WholeWord hash tables: one entry per distinct (trimmed, folded) keyword = per terminal node of the forward trie
@@ -583,7 +648,7 @@ uint64_t automaton_fingerprint(const HostAutomaton &a) {
     bytes(t.pow_c, sizeof t.pow_c); bytes(t.row_off, sizeof t.row_off);
     vec(t.row_words); vec(t.prow_words); bytes(t.prow_off, sizeof t.prow_off); num(t.pair_gate_bit); num(t.pair_low_bit); vec(t.kidmask); vec(t.buckets); num(t.n_buckets); num(t.hash_seed); num(t.n_deep); num(t.n_heads);
     vec(t.vbuckets); num(t.n_vbuckets); num(t.vseed);
-    if (a.wide_ok) { num(a.wide_ok); vec(a.wide_pair); }
+    if (a.wide_ok) { num(a.wide_ok); vec(a.wide_pair); vec(a.wide_chain); vec(a.wide_pair16); }
     num(a.ww.ok); vec(a.ww.wcls); vec(a.ww.buckets); num(a.ww.n_buckets); vec(a.ww.pool);
     return h;
 }

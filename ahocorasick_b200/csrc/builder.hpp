@@ -67,6 +67,7 @@ struct IllegalArgument : std::runtime_error {
 //     a key that exists, and the builder guarantees that no bucket on a key's probe path holds another entry with
 //     the same tag - a tag match is exact.
 constexpr int kTierChainMax = 8;
+constexpr int kWideChainMax = 8;
 struct TierTables {
     bool ok = false;
     int32_t C = 0;        // radix = number of classes (including class 0 = other)
@@ -196,6 +197,21 @@ struct HostAutomaton {
     // {level-2 node of the reversed context (c0, c1) or kNone, info2 | info1 << 8 | (level-1 node exists) << 16}
     bool wide_ok = false;
     std::vector<uint32_t> wide_pair;
+    // Path-compressed edges below level 2 for k_wide_tile (with the pair table, i.e. at most 64 classes).  A JUNCTION is
+    // a level-2 node, a node with several children, or the end of a chain that outgrew one entry; every edge that leaves a
+    // junction has one 32-byte ENTRY describing the child and the unbranched chain hanging below it, and the entries of
+    // one junction's children are CONTIGUOUS, in class order.  With the junction's exact child mask a walk finds its
+    // next entry by a population count - no hashing, no probing, never a gather for an edge that does not exist:
+    //     [0,1] 64-bit child mask of the node at the END of the chain (bit c: it has a child of class c)
+    //     [2]   index of the first entry of the end node's children
+    //     [3]   chain length L (bits 0..3) | terminal flags << 4 (bit i: the i-th node of the run is a keyword end, 0 = the child)
+    //     [4,5] the classes of the L chain steps, 8 bits each (L <= 8), step k in byte 7 - k of the 64-bit word: the same
+    //           order as the haystack classes they are compared with (the walk runs right to left)
+    //     [6]   node id of the end node   [7] 0
+    // wide_pair16[4 * (c0 * C + c1)] = {first entry of the level-2 node's children, info2 | info1 << 8 | (level-1 node
+    // exists) << 16 | (level-2 node exists) << 17, child mask lo, hi} is the shared-memory table of levels 1 and 2.
+    std::vector<uint32_t> wide_chain;
+    std::vector<uint32_t> wide_pair16;
     WwTables ww;                       // WholeWord hash tables (ww.ok == false: not applicable)
     bool ww_plain = true;              // WholeWordLongest: no keyword holds a non-word char (then it equals WholeWord)
 };

@@ -95,6 +95,7 @@ struct Matcher {
     DevWide wide{};
     void *d_wide_blob = nullptr;
     size_t wide_smem = 0;
+    bool wide_tile = false;   // k_wide_tile (pair table + path-compressed edges) instead of k_wide_mask
     // WholeWord hash tables (kernel_ww.cuh)
     bool use_ww = false;
     DevWw ww{};
@@ -259,12 +260,29 @@ int upload_wide(Matcher *m) {
     const bool pair = !m->host.wide_pair.empty();
     m->wide.C = m->host.n_classes;
     m->wide.pair = nullptr;
+    m->wide.chain = nullptr;
+    m->wide.pair16 = nullptr;
+    m->wide_tile = false;
     if (pair) {
-        const size_t bytes = m->host.wide_pair.size() * 4;
-        CU_TRY(cudaMalloc(&m->d_wide_blob, bytes));
-        m->table_bytes += static_cast<int64_t>(bytes);
-        CU_TRY(cudaMemcpy(m->d_wide_blob, m->host.wide_pair.data(), bytes, cudaMemcpyHostToDevice));
-        m->wide.pair = static_cast<const uint2 *>(m->d_wide_blob);
+        const size_t pair_bytes = align_up(m->host.wide_pair.size() * 4, 256), pair16_bytes = align_up(m->host.wide_pair16.size() * 4, 256);
+        const size_t chain_bytes = m->host.wide_chain.size() * 4;
+        CU_TRY(cudaMalloc(&m->d_wide_blob, pair_bytes + pair16_bytes + chain_bytes + 256));
+        m->table_bytes += static_cast<int64_t>(pair_bytes + pair16_bytes + chain_bytes);
+        char *b = static_cast<char *>(m->d_wide_blob);
+        CU_TRY(cudaMemcpy(b, m->host.wide_pair.data(), m->host.wide_pair.size() * 4, cudaMemcpyHostToDevice));
+        m->wide.pair = reinterpret_cast<const uint2 *>(b);
+        int max_smem = 0;
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device);
+        if (!m->host.wide_pair16.empty() && wide_tile_smem_bytes(m->host.n_classes) <= static_cast<size_t>(max_smem)) {
+            CU_TRY(cudaMemcpy(b + pair_bytes, m->host.wide_pair16.data(), m->host.wide_pair16.size() * 4, cudaMemcpyHostToDevice));
+            if (chain_bytes) CU_TRY(cudaMemcpy(b + pair_bytes + pair16_bytes, m->host.wide_chain.data(), chain_bytes, cudaMemcpyHostToDevice));
+            m->wide.pair16 = reinterpret_cast<const uint4 *>(b + pair_bytes);
+            m->wide.chain = reinterpret_cast<const uint4 *>(b + pair_bytes + pair16_bytes);
+            // generation 2 of the wide path (k_wide_tile: CTA-wide walk queue over path-compressed edges); ACGPU_WIDE_GEN=1 keeps k_wide_mask (A/B runs)
+            const char *gen = getenv("ACGPU_WIDE_GEN");
+            m->wide_tile = !(gen && gen[0] == '1');
+            CU_TRY(cudaFuncSetAttribute(k_wide_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide_tile_smem_bytes(kWidePairMax)));
+        }
     }
     // at most 512 + 64 * 64 * 8 + 8 * 2 880 = 56 320 bytes: one attribute for every matcher (a per-matcher value would
     // shrink the limit under a live matcher with a larger table)
@@ -759,6 +777,11 @@ int enqueue_wide(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from
     const size_t o_cnt = S.reserve(static_cast<size_t>(n_rows) * 4);
     const size_t o_blk = S.reserve(static_cast<size_t>(n_blocks) * 8);
     const size_t o_mask = S.reserve(static_cast<size_t>(n_rows) * kMaskRow * 4);
+    // k_wide_tile hands the walks of its thin late rounds to k_wide_tail: room for one walk per four positions (a tile
+    // that finds the list full finishes its walks itself)
+    static const char *tail_env = getenv("ACGPU_WIDE_TAIL");
+    const int64_t tail_cap = (m->wide_tile && !(tail_env && tail_env[0] == '0')) ? std::max<int64_t>(4096, n_rows * kMaskRow / 4) : 0;
+    const size_t o_tail = S.reserve(static_cast<size_t>(tail_cap) * 16);
     void *ws = nullptr;
     CU_TRY(cudaMallocAsync(&ws, S.off, st));
     char *w = static_cast<char *>(ws);
@@ -779,10 +802,21 @@ int enqueue_wide(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from
         P.row_count = reinterpret_cast<uint32_t *>(w + o_cnt);
         P.ticket = reinterpret_cast<unsigned int *>(w + o_ctr);
         P.n_rows = n_rows;
+        P.tail = reinterpret_cast<uint4 *>(w + o_tail);
+        P.tail_count = reinterpret_cast<unsigned int *>(w + o_ctr + 128);
+        P.tail_cap = static_cast<uint32_t>(std::min<int64_t>(tail_cap, 0x7FFFFFFF));
         const int64_t n_chunks = (n_rows + kMaskChunkRows - 1) / kMaskChunkRows;
         const int per_sm = std::max<int>(1, std::min<int>(6, static_cast<int>((200 * 1024) / std::max<size_t>(m->wide_smem, 1))));
         const int grid = static_cast<int>(std::min<int64_t>((n_chunks + kWideWarps - 1) / kWideWarps, static_cast<int64_t>(m->sm_count) * per_sm));
-        if (m->wide.pair)
+        if (m->wide_tile) {
+            const int64_t n_tiles = (n_rows + kWtRows - 1) / kWtRows;
+            const int tgrid = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(m->sm_count) * 2));
+            k_wide_tile<<<tgrid, kWtThreads, wide_tile_smem_bytes(m->wide.C), st>>>(m->dev, m->wide, P);
+            if (P.tail_cap) {
+                launch_ok("k_wide_tile");
+                k_wide_tail<<<m->sm_count * 8, 256, 0, st>>>(m->dev, m->wide, P);
+            }
+        } else if (m->wide.pair)
             k_wide_mask<true><<<grid, kWideThreads, m->wide_smem, st>>>(m->dev, m->wide, P);
         else
             k_wide_mask<false><<<grid, kWideThreads, m->wide_smem, st>>>(m->dev, m->wide, P);
@@ -1723,7 +1757,7 @@ int acgpu_launches_per_match(uint64_t handle) {
     Matcher *m = as_matcher(handle);
     if (!m) return fail(ACGPU_EINVAL, "bad handle");
     switch (m->host.family) {
-    case ACGPU_AHOCORASICK: return (m->use_tier || m->use_wide) ? 3 : 1;
+    case ACGPU_AHOCORASICK: return m->use_tier ? 3 : (m->use_wide ? (m->wide_tile ? 4 : 3) : 1);  // wide, generation 2: tile, tail, scan, emit
     case ACGPU_WHOLEWORD: return m->use_ww ? 1 : 2;
     default: return m->use_tier && m->host.is_map ? 7 : 6;  // one-shot tier path: mask, map, group, top, tiles, emit (+ values)  // one-shot matches; the streaming path always takes the 6-launch route
     }

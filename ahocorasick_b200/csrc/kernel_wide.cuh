@@ -24,11 +24,14 @@ constexpr int kWideWarps = 8;
 constexpr int kWideThreads = kWideWarps * 32;
 constexpr int kWideMaxLen = 32;      // hit masks are 32 bits
 constexpr int kWideLockLevels = 5;   // levels walked in lockstep by the owning lane; deeper walks are compacted over the warp
-constexpr int kWidePairMax = 64;     // class-pair table: C * C * 8 bytes <= 32 KB of shared memory (3 CTAs per SM stay below the L1 carve-out cliff)
+constexpr int kWidePairMax = 64;
+constexpr int kWideChainMaxD = 8;   // = kWideChainMax of builder.hpp: chain steps per path-compressed entry     // class-pair table: C * C * 8 bytes <= 32 KB of shared memory (3 CTAs per SM stay below the L1 carve-out cliff)
 
 struct DevWide {
     const uint2 *pair;   // [C * C] (c0 * C + c1) -> {level-2 node or kNoneD, info2 | info1 << 8 | level-1 node exists << 16}; nullptr: no table
     int32_t C;
+    const uint4 *chain;   // path-compressed edges below level 2 (HostAutomaton::wide_chain): two uint4 per 32-byte entry; nullptr: none
+    const uint4 *pair16;  // [C * C] k_wide_tile's table of levels 1 and 2 (HostAutomaton::wide_pair16)
 };
 
 struct WideArgs {
@@ -41,6 +44,10 @@ struct WideArgs {
     uint32_t *row_count;    // [n_rows]
     unsigned int *ticket;
     int64_t n_rows;
+    // k_wide_tile -> k_wide_tail: walks a tile hands over instead of finishing them in thin rounds {entry, position, depth, 0}
+    uint4 *tail;
+    unsigned int *tail_count;   // [0] walks handed over
+    uint32_t tail_cap;
 };
 
 __host__ __device__ constexpr size_t wide_smem_bytes(int C, bool pair) {
@@ -229,6 +236,323 @@ __global__ void __launch_bounds__(kWideThreads, ACGPU_WIDE_MIN_CTAS) k_wide_mask
             const uint16_t keep = w[kMaskRow + lane];
             __syncwarp();
             w[lane] = keep;
+        }
+    }
+}
+
+// k_wide_tile: the mask kernel of dictionaries with a class-pair table (at most 64 classes) - generation 2 of the wide path.
+//
+// k_wide_mask is latency-bound: a warp's row waits for its longest walk, one dependent L2 gather per level, and a walk
+// that dies pays a last gather (plus open-addressing probes) to learn it (ncu: 36 % of the lanes active, 10 long-scoreboard
+// stalls per issue, 16 % of the L2 bandwidth).  Here a CTA owns a TILE of 4 096 positions:
+//   * levels 1 and 2 of every position come from the pair table in shared memory, which also holds the level-2 node's
+//     exact child mask: only walks whose next edge exists are pushed to the queue of the CTA;
+//   * the queue is worked off in ROUNDS: every thread takes up to 8 walks, issues their gathers back to back and advances
+//     each to its next branch point.  Edges are PATH-COMPRESSED and addressed without hashing (HostAutomaton::wide_chain:
+//     one 32-byte entry = a child and the unbranched chain below it, the child mask of the chain's end and the index of
+//     that node's first child entry; the next entry is first + popcount(mask below the class)), so a walk costs exactly
+//     one gathered sector per branch point and never a gather that finds nothing;
+//   * hits are OR-ed into the tile's masks in shared memory; masks and row counts leave with coalesced 128-bit stores.
+// The number of rounds does not depend on the tile size, so a large tile amortises the latency of the thin late rounds,
+// and the rounds of the two resident CTAs of an SM overlap.
+constexpr int kWtThreads = 512;
+constexpr int kWtTile = 4096;                       // positions per tile = 16 rows
+constexpr int kWtRows = kWtTile / kMaskRow;
+constexpr int kWtPer = kWtTile / kWtThreads;        // positions (and at most walks per round) per thread
+constexpr int kWtIlp = 4;                           // gathers a thread keeps in flight
+constexpr int kWtHalo = 40;                         // class bytes kept before the tile (walks look 31 back, the 8-byte compare 7 more)
+constexpr int kWtMinRounds = 3;                     // rounds a tile always runs itself
+constexpr int kWtHandOver = 768;                    // walks left at which a tile hands them to k_wide_tail
+
+__host__ __device__ constexpr size_t wide_tile_smem_bytes(int C) {
+    // classes 0..255 | pair table (16 bytes per class pair) | class window (halo + tile bytes) | masks | queue (8 bytes per walk) | counters
+    return 512 + (size_t)C * C * 16 + (kWtHalo + kWtTile + 8) + kWtTile * 4 + kWtTile * 8 + 32;
+}
+
+__device__ __forceinline__ uint32_t rank64(uint32_t lo, uint32_t hi, uint32_t c) {  // set bits of (hi:lo) below bit c
+    return c < 32u ? (uint32_t)__popc(lo & ((1u << c) - 1u)) : (uint32_t)__popc(lo) + (uint32_t)__popc(hi & ((1u << (c - 32u)) - 1u));
+}
+__device__ __forceinline__ bool bit64(uint32_t lo, uint32_t hi, uint32_t c) { return ((c < 32u ? lo >> c : hi >> (c - 32u)) & 1u) != 0u; }
+
+__global__ void __launch_bounds__(kWtThreads, 2) k_wide_tile(const DevAutomaton A, const DevWide Wd, const WideArgs P) {
+    extern __shared__ __align__(16) unsigned char s_wide[];
+    uint16_t *s_cls8 = reinterpret_cast<uint16_t *>(s_wide);
+    const uint4 *s_pair = reinterpret_cast<const uint4 *>(s_wide + 512);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = Wd.C;
+    unsigned char *s_after = s_wide + 512 + (size_t)C * C * 16;
+    uint8_t *w = s_after;                                                       // w[kWtHalo + p] = class of tile position p (at most 64 classes)
+    uint32_t *s_mask = reinterpret_cast<uint32_t *>(s_after + (kWtHalo + kWtTile + 8));
+    uint2 *s_q = reinterpret_cast<uint2 *>(s_mask + kWtTile);                   // {entry to load, position | depth << 16}
+    uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_q + kWtTile);              // [0], [1]: walks queued for even / odd rounds; [2]: tile; [3]: hand-over slot
+    for (int i = tid; i < 256; i += kWtThreads) s_cls8[i] = __ldg(&A.cls[i]);
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(s_wide + 512);
+        for (int i = tid; i < C * C; i += kWtThreads) dst[i] = __ldg(&Wd.pair16[i]);
+    }
+    if (tid < 2) s_cnt[tid] = 0u;
+    const int max_len = min(A.max_len, kWideMaxLen);
+    const int64_t n_tiles = (P.n_rows + kWtRows - 1) / kWtRows;
+    auto class_of = [&](uint32_t ch) -> uint32_t { return ch < 256u ? (uint32_t)s_cls8[ch] : (uint32_t)__ldg(&A.cls[ch]); };
+    // a warp appends its lanes' walks (flag per lane) to the queue counted by *cnt
+    auto push = [&](bool on, uint32_t entry, uint32_t pd, uint32_t *cnt) {
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, on);
+        if (!bal) return;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cnt, (uint32_t)__popc(bal));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (on) s_q[base + __popc(bal & ((1u << lane) - 1u))] = make_uint2(entry, pd);
+    };
+
+    while (true) {
+        __syncthreads();  // the previous tile's masks are out, the tables are in
+        if (tid == 0) s_cnt[2] = atomicAdd(P.ticket, 1u);
+        __syncthreads();
+        const int64_t tile = s_cnt[2];
+        if (tile >= n_tiles) break;
+        const int64_t row0 = tile * kWtRows;
+        const int64_t t_lo = P.origin + row0 * kMaskRow;
+        // ---- classes of the tile and of the chars before it
+        uint2 own;  // the thread's 8 classes, position j in byte j
+        {
+            const int64_t p0 = t_lo + (int64_t)tid * kWtPer;
+            uint32_t c[8];
+            if (p0 >= 0 && p0 + 8 <= P.n) {
+                const uint4 v = ldcs_v4_if(P.hay + p0, true);
+                c[0] = class_of(v.x & 0xFFFFu); c[1] = class_of(v.x >> 16); c[2] = class_of(v.y & 0xFFFFu); c[3] = class_of(v.y >> 16);
+                c[4] = class_of(v.z & 0xFFFFu); c[5] = class_of(v.z >> 16); c[6] = class_of(v.w & 0xFFFFu); c[7] = class_of(v.w >> 16);
+            } else {
+#pragma unroll
+                for (int j = 0; j < kWtPer; j++) {
+                    const int64_t p = p0 + j;
+                    c[j] = (p >= 0 && p < P.n) ? class_of(__ldg(&P.hay[p])) : 0u;
+                }
+            }
+            own = make_uint2(c[0] | c[1] << 8 | c[2] << 16 | c[3] << 24, c[4] | c[5] << 8 | c[6] << 16 | c[7] << 24);
+            *reinterpret_cast<uint2 *>(w + kWtHalo + tid * kWtPer) = own;  // kWtHalo is a multiple of 8
+            if (tid < kWtHalo) {
+                const int64_t p = t_lo - kWtHalo + tid;
+                w[tid] = (p >= 0 && p < P.n) ? (uint8_t)class_of(__ldg(&P.hay[p])) : (uint8_t)0;
+            }
+        }
+        __syncthreads();
+        // ---- levels 1 and 2; a walk whose level-3 edge exists is queued for round 0
+        {
+            const uint32_t before = *reinterpret_cast<const uint32_t *>(w + kWtHalo + tid * kWtPer - 4);  // the 4 classes before the thread's
+            uint32_t m[kWtPer];
+#pragma unroll
+            for (int j = 0; j < kWtPer; j++) {
+                // classes of positions j, j - 1, j - 2
+                auto cls_rel = [&](int r) -> uint32_t {
+                    return r >= 4 ? (own.y >> (8 * (r - 4))) & 0xFFu : (r >= 0 ? (own.x >> (8 * r)) & 0xFFu : (before >> (8 * (4 + r))) & 0xFFu);
+                };
+                const uint32_t c0 = cls_rel(j), c1 = cls_rel(j - 1), c2 = cls_rel(j - 2);
+                const uint4 e = s_pair[c0 * (uint32_t)C + c1];
+                uint32_t mj = 0;
+                if ((e.y >> 8) & kTerm) mj |= 1u << 31;
+                if (((e.y >> 17) & 1u) && max_len >= 2 && (e.y & kTerm)) mj |= 1u << 30;
+                const bool on = ((e.y >> 17) & 1u) && max_len >= 3 && bit64(e.z, e.w, c2);  // class 0 is in no mask
+                m[j] = mj;
+                push(on, e.x + rank64(e.z, e.w, c2), (uint32_t)(tid * kWtPer + j) | 2u << 16, &s_cnt[0]);
+            }
+            uint4 *mp = reinterpret_cast<uint4 *>(s_mask + tid * kWtPer);
+            mp[0] = make_uint4(m[0], m[1], m[2], m[3]);
+            mp[1] = make_uint4(m[4], m[5], m[6], m[7]);
+        }
+        __syncthreads();
+        // ---- rounds
+        for (uint32_t round = 0;; ++round) {
+            const uint32_t n_q = s_cnt[round & 1u];
+            if (n_q == 0u) break;
+            // a thin round costs the whole CTA a gather latency: once few walks are left they are handed to k_wide_tail
+            if (round >= (uint32_t)kWtMinRounds && n_q <= (uint32_t)kWtHandOver && P.tail_cap) {
+                if (tid == 0) {
+                    const uint32_t at = atomicAdd(P.tail_count, n_q);
+                    if (at + n_q > P.tail_cap) {
+                        atomicSub(P.tail_count, n_q);
+                        s_cnt[3] = 0xFFFFFFFFu;
+                    } else {
+                        s_cnt[3] = at;
+                    }
+                }
+                __syncthreads();
+                const uint32_t at = s_cnt[3];
+                if (at != 0xFFFFFFFFu) {
+                    const uint32_t pos0 = (uint32_t)(row0 * kMaskRow);
+                    for (uint32_t k = tid; k < n_q; k += kWtThreads) {
+                        const uint2 q = s_q[k];
+                        P.tail[at + k] = make_uint4(q.x, pos0 + (q.y & 0xFFFFu), q.y >> 16, 0u);
+                    }
+                    __syncthreads();
+                    if (tid == 0) s_cnt[round & 1u] = 0u;
+                    break;
+                }
+            }
+            uint2 mine[kWtPer];
+#pragma unroll
+            for (int i = 0; i < kWtPer; i++) {
+                const uint32_t k = (uint32_t)tid + (uint32_t)i * kWtThreads;
+                mine[i] = k < n_q ? s_q[k] : make_uint2(kNoneD, 0u);
+            }
+            __syncthreads();  // every walk of this round is in registers: the queue can take the survivors
+            if (tid == 0) s_cnt[round & 1u] = 0u;
+            uint32_t alive = 0;  // bit i: walk i of this thread goes on (its next entry and depth replace mine[i])
+#pragma unroll
+            for (int i0 = 0; i0 < kWtPer; i0 += kWtIlp) {
+                if ((uint32_t)(i0 * kWtThreads) >= n_q) break;  // uniform over the CTA
+                uint4 ea[kWtIlp], eb[kWtIlp];
+#pragma unroll
+                for (int i = 0; i < kWtIlp; i++) {
+                    const uint2 q = mine[i0 + i];
+                    ea[i] = make_uint4(0u, 0u, 0u, 0u);
+                    eb[i] = ea[i];
+                    if (q.x != kNoneD) {
+                        ea[i] = __ldg(Wd.chain + (size_t)q.x * 2);
+                        eb[i] = __ldg(Wd.chain + (size_t)q.x * 2 + 1);  // the same sector
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < kWtIlp; i++) {
+                    const uint2 q = mine[i0 + i];
+                    if (q.x == kNoneD) continue;
+                    const int pos = (int)(q.y & 0xFFFFu);
+                    int d = (int)(q.y >> 16) + 1;  // depth of the entry's child
+                    const uint4 e = ea[i];
+                    const int L = (int)(e.w & 15u);
+                    const uint32_t term = e.w >> 4;
+                    // the L chain classes against the context, all at once: the 8 class bytes that end at the class step 0
+                    // must equal, most recent in the top byte - the order the entry keeps its chain in
+                    const int a7 = kWtHalo + pos - d - 7;  // >= 2
+                    const uint32_t *wp = reinterpret_cast<const uint32_t *>(w + (a7 & ~3));
+                    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], sh = (uint32_t)(a7 & 3) * 8u;
+                    const uint32_t x_lo = __funnelshift_r(w0, w1, sh) ^ eb[i].x, x_hi = __funnelshift_r(w1, w2, sh) ^ eb[i].y;
+                    const int mtc = min(L, (x_hi ? __clz((int)x_hi) : 32 + __clz((int)x_lo)) >> 3);  // steps that match before the first that does not
+                    // terminal flags of the child and of the matched steps -> hit bits 32 - d, 32 - d - 1, ..
+                    const uint32_t t_ok = term & ((2u << mtc) - 1u);
+                    const uint32_t hits = (__brev(t_ok) >> (d - 1));
+                    if (hits) atomicOr(&s_mask[pos], hits);
+                    d += mtc;
+                    if (mtc == L && d < max_len) {
+                        const uint32_t c = w[kWtHalo + pos - d];
+                        if (bit64(e.x, e.y, c)) {
+                            alive |= 1u << (i0 + i);
+                            mine[i0 + i] = make_uint2(e.z + rank64(e.x, e.y, c), (uint32_t)pos | (uint32_t)d << 16);
+                        }
+                    }
+                }
+            }
+            // ---- survivors -> queue of the next round: one reservation per warp
+            {
+                const uint32_t n_mine = (uint32_t)__popc(alive);
+                uint32_t inc = n_mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if (lane >= o) inc += y;
+                }
+                const uint32_t n_warp = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                uint32_t base = 0;
+                if (lane == 31 && n_warp) base = atomicAdd(&s_cnt[(round + 1u) & 1u], n_warp);
+                base = __shfl_sync(0xFFFFFFFFu, base, 31) + inc - n_mine;
+#pragma unroll
+                for (int i = 0; i < kWtPer; i++)
+                    if ((alive >> i) & 1u) s_q[base++] = mine[i];
+            }
+            __syncthreads();  // the survivors are queued
+        }
+        // ---- masks and row counts leave the tile
+        {
+            const int64_t p0 = t_lo + (int64_t)tid * kWtPer;
+            uint32_t m[kWtPer];
+#pragma unroll
+            for (int j = 0; j < kWtPer; j++) m[j] = s_mask[tid * kWtPer + j];
+            if (p0 < P.emit_from || p0 + kWtPer > P.emit_to) {
+#pragma unroll
+                for (int j = 0; j < kWtPer; j++)
+                    if (p0 + j < P.emit_from || p0 + j >= P.emit_to) m[j] = 0u;
+            }
+            const int64_t row = row0 + warp;  // a warp's 256 positions are one row
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int j = 0; j < kWtPer; j++) cnt += __popc(m[j]);
+            const uint32_t row_total = __reduce_add_sync(0xFFFFFFFFu, cnt);
+            if (row < P.n_rows) {
+                uint4 *mp = reinterpret_cast<uint4 *>(P.masks + ((size_t)row * kMaskRow + (size_t)lane * kWtPer));
+                mp[0] = make_uint4(m[0], m[1], m[2], m[3]);
+                mp[1] = make_uint4(m[4], m[5], m[6], m[7]);
+                if (lane == 0) P.row_count[row] = row_total;
+            }
+        }
+    }
+}
+
+// k_wide_tail: the walks k_wide_tile handed over, one per lane, refilled from the list as lanes finish.  A step = the
+// walk's entry (one sector) + the up to 9 haystack chars it is compared with; hits are OR-ed into the masks the tile
+// already stored and added to the row counts (k_row_scan runs after this kernel).
+__global__ void __launch_bounds__(256) k_wide_tail(const DevAutomaton A, const DevWide Wd, const WideArgs P) {
+    __shared__ uint16_t s_cls8[256];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 256; i += 256) s_cls8[i] = __ldg(&A.cls[i]);
+    __syncthreads();
+    const int max_len = min(A.max_len, kWideMaxLen);
+    const uint32_t n_tail = min(P.tail_count[0], P.tail_cap);
+    auto class_at = [&](int64_t p) -> uint32_t {
+        if (p < 0 || p >= P.n) return 0u;
+        const uint32_t ch = __ldg(&P.hay[p]);
+        return ch < 256u ? (uint32_t)s_cls8[ch] : (uint32_t)__ldg(&A.cls[ch]);
+    };
+    // every warp owns an equal slice of the list (no shared ticket: one atomic per refill convoys on a single address)
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5), wid = blockIdx.x * (blockDim.x >> 5) + (tid >> 5);
+    const uint32_t per = (n_tail + n_warps - 1u) / n_warps;
+    uint32_t next = min(n_tail, wid * per);
+    const uint32_t last = min(n_tail, next + per);
+    bool have = false;
+    uint32_t entry = 0, pos = 0;
+    int d = 0;
+    while (true) {
+        // ---- lanes without a walk take the next ones of the warp's slice
+        const uint32_t need = __ballot_sync(0xFFFFFFFFu, !have);
+        if (need) {
+            if (!have) {
+                const uint32_t k = next + (uint32_t)__popc(need & ((1u << lane) - 1u));
+                if (k < last) {
+                    const uint4 t = P.tail[k];
+                    entry = t.x;
+                    pos = t.y;
+                    d = (int)t.z;
+                    have = true;
+                }
+            }
+            next = min(last, next + (uint32_t)__popc(need));
+            if (!__ballot_sync(0xFFFFFFFFu, have)) break;  // the slice is empty and every lane is done
+        }
+        if (!have) continue;
+        const uint4 e = __ldg(Wd.chain + (size_t)entry * 2), ch = __ldg(Wd.chain + (size_t)entry * 2 + 1);
+        const int64_t q = P.origin + (int64_t)pos;  // haystack position of the walk's END anchor
+        d += 1;
+        const int L = (int)(e.w & 15u);
+        const uint32_t term = e.w >> 4;
+        uint32_t same = 0;
+#pragma unroll
+        for (int k = 0; k < kWideChainMaxD; k++) {
+            const uint32_t want = ((k < 4 ? ch.y >> (8 * (3 - k)) : ch.x >> (8 * (7 - k))) & 0xFFu);  // step k in byte 7 - k
+            same |= (k < L && class_at(q - d - k) == want) ? 1u << k : 0u;
+        }
+        const int mtc = __ffs(~same) - 1;
+        const uint32_t t_ok = term & ((2u << mtc) - 1u);
+        const uint32_t hits = (q >= P.emit_from && q < P.emit_to) ? (__brev(t_ok) >> (d - 1)) : 0u;
+        if (hits) {
+            atomicOr(P.masks + pos, hits);
+            atomicAdd(P.row_count + (pos >> 8), (uint32_t)__popc(hits));
+        }
+        d += mtc;
+        have = false;
+        if (mtc == L && d < max_len) {
+            const uint32_t c = class_at(q - d);
+            if (bit64(e.x, e.y, c)) {
+                entry = e.z + rank64(e.x, e.y, c);
+                have = true;
+            }
         }
     }
 }

@@ -853,7 +853,7 @@ def test_wide_path_alphabets_and_boundary_lengths(alphabet, max_kw):
     values = list(range(len(kws)))
     om = ora.Matcher("ahocorasick", kws, n_values=len(kws))
     gs, gm = ac.AhoCorasickSet(kws, True), ac.AhoCorasickMap(kws, values, True)
-    assert _launches(gs) == 3 and _launches(gm) == 3          # mask, scan, emit - not the generation-1 single kernel
+    assert _launches(gs) in (3, 4) and _launches(gm) in (3, 4)  # mask (tile + tail), scan, emit - not the generation-1 single kernel
     base = [rng.choice(alphabet + "  ") for _ in range(70_001)]
     for _ in range(1500):
         k = rng.choice(kws)
@@ -894,7 +894,7 @@ def test_wide_path_dense_rows_and_range_shards():
     hay = "a" * 2100 + "b" * 40 + ("ab" * 700) + "abABZz" * 50 + "a" * 513
     want = ora.Matcher("ahocorasick", kws, n_values=len(kws)).match(hay, cap=1 << 18)
     gs, gm = ac.AhoCorasickSet(kws, True), ac.AhoCorasickMap(kws, list(range(len(kws))), True)
-    assert _launches(gs) == 3
+    assert _launches(gs) in (3, 4)
     rec = gs.match_records(hay)
     assert len(rec) == len(want) > 60_000 and np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"])
     rec = gm.match_records(hay)
@@ -929,7 +929,7 @@ def test_wide_path_real_dictionary(scale, n):
     hay = W.make_haystack(c["spec"], n)
     want = ora.Matcher("ahocorasick", kws, n_values=len(kws)).match(hay, cap=2 * n)
     gs = ac.AhoCorasickSet(kws, True)
-    assert _launches(gs) == 3 and gs.info()["n_classes"] == 54 and gs.info()["max_len"] == 24
+    assert _launches(gs) in (3, 4) and gs.info()["n_classes"] == 54 and gs.info()["max_len"] == 24
     rec = gs.match_records(hay)
     assert len(rec) == len(want) > n // 8
     assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"])
