@@ -780,7 +780,8 @@ int enqueue_wide(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from
     // k_wide_tile hands the walks of its thin late rounds to k_wide_tail: room for one walk per four positions (a tile
     // that finds the list full finishes its walks itself)
     static const char *tail_env = getenv("ACGPU_WIDE_TAIL");
-    const int64_t tail_cap = (m->wide_tile && !(tail_env && tail_env[0] == '0')) ? std::max<int64_t>(4096, n_rows * kMaskRow / 4) : 0;
+    int64_t tail_cap = (m->wide_tile && !(tail_env && tail_env[0] == '0')) ? std::max<int64_t>(4096, n_rows * kMaskRow / 4) : 0;
+    if (const char *tc = getenv("ACGPU_WIDE_TAIL_CAP")) tail_cap = tail_cap ? std::max<int64_t>(1, atoll(tc)) : 0;  // tests: force the "list full" path
     const size_t o_tail = S.reserve(static_cast<size_t>(tail_cap) * 16);
     void *ws = nullptr;
     CU_TRY(cudaMallocAsync(&ws, S.off, st));
@@ -805,6 +806,9 @@ int enqueue_wide(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from
         P.tail = reinterpret_cast<uint4 *>(w + o_tail);
         P.tail_count = reinterpret_cast<unsigned int *>(w + o_ctr + 128);
         P.tail_cap = static_cast<uint32_t>(std::min<int64_t>(tail_cap, 0x7FFFFFFF));
+        const char *mr = getenv("ACGPU_WT_MIN_ROUNDS"), *ho = getenv("ACGPU_WT_HANDOVER");  // tuning runs and tests
+        P.min_rounds = mr ? static_cast<uint32_t>(atoi(mr)) : kWtMinRounds;
+        P.hand_over = ho ? static_cast<uint32_t>(atoi(ho)) : kWtHandOver;
         const int64_t n_chunks = (n_rows + kMaskChunkRows - 1) / kMaskChunkRows;
         const int per_sm = std::max<int>(1, std::min<int>(6, static_cast<int>((200 * 1024) / std::max<size_t>(m->wide_smem, 1))));
         const int grid = static_cast<int>(std::min<int64_t>((n_chunks + kWideWarps - 1) / kWideWarps, static_cast<int64_t>(m->sm_count) * per_sm));

@@ -48,6 +48,7 @@ struct WideArgs {
     uint4 *tail;
     unsigned int *tail_count;   // [0] walks handed over
     uint32_t tail_cap;
+    uint32_t min_rounds, hand_over;  // a tile runs min_rounds rounds itself and hands its walks over once at most hand_over are left
 };
 
 __host__ __device__ constexpr size_t wide_smem_bytes(int C, bool pair) {
@@ -261,8 +262,8 @@ constexpr int kWtRows = kWtTile / kMaskRow;
 constexpr int kWtPer = kWtTile / kWtThreads;        // positions (and at most walks per round) per thread
 constexpr int kWtIlp = 4;                           // gathers a thread keeps in flight
 constexpr int kWtHalo = 40;                         // class bytes kept before the tile (walks look 31 back, the 8-byte compare 7 more)
-constexpr int kWtMinRounds = 3;                     // rounds a tile always runs itself
-constexpr int kWtHandOver = 768;                    // walks left at which a tile hands them to k_wide_tail
+constexpr int kWtMinRounds = 3;                     // rounds a tile always runs itself (default of WideArgs::min_rounds)
+constexpr int kWtHandOver = 768;                    // walks left at which a tile hands them to k_wide_tail (default of WideArgs::hand_over)
 
 __host__ __device__ constexpr size_t wide_tile_smem_bytes(int C) {
     // classes 0..255 | pair table (16 bytes per class pair) | class window (halo + tile bytes) | masks | queue (8 bytes per walk) | counters
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(kWtThreads, 2) k_wide_tile(const DevAutomaton 
             const uint32_t n_q = s_cnt[round & 1u];
             if (n_q == 0u) break;
             // a thin round costs the whole CTA a gather latency: once few walks are left they are handed to k_wide_tail
-            if (round >= (uint32_t)kWtMinRounds && n_q <= (uint32_t)kWtHandOver && P.tail_cap) {
+            if (round >= P.min_rounds && n_q <= P.hand_over && P.tail_cap) {
                 if (tid == 0) {
                     const uint32_t at = atomicAdd(P.tail_count, n_q);
                     if (at + n_q > P.tail_cap) {

@@ -938,6 +938,23 @@ def test_wide_path_real_dictionary(scale, n):
     assert np.array_equal(rec.value.astype(np.int64), want["value"].astype(np.int64))
 
 
+@pytest.mark.parametrize("cap,min_rounds,hand_over", [(1, 0, 4096), (100, 1, 4096), (10_000_000, 0, 4096), (10_000_000, 9, 64)])
+def test_wide_path_tail_hand_over_corner_cases(monkeypatch, cap, min_rounds, hand_over):
+    """k_wide_tile hands the walks of its thin rounds to k_wide_tail: a full list (the tile finishes its walks itself), a
+    hand-over before the first round (every walk goes through k_wide_tail) and a late one give the oracle's stream."""
+    monkeypatch.setenv("ACGPU_WIDE_TAIL_CAP", str(cap))
+    monkeypatch.setenv("ACGPU_WT_MIN_ROUNDS", str(min_rounds))
+    monkeypatch.setenv("ACGPU_WT_HANDOVER", str(hand_over))
+    c = W.config(5, scale=0.05)
+    kws = c["keywords"]
+    n = 300_001
+    hay = W.make_haystack(c["spec"], n)
+    want = ora.Matcher("ahocorasick", kws, n_values=len(kws)).match(hay, cap=2 * n)
+    rec = ac.AhoCorasickSet(kws, True).match_records(hay)
+    assert len(rec) == len(want) > n // 8
+    assert np.array_equal(rec.start, want["start"]) and np.array_equal(rec.end, want["end"])
+
+
 # ---------------------------------------------------------------- Longest / Shortest: range shards with composed chain maps
 
 @pytest.mark.parametrize("family,is_map", [("longest", False), ("longest", True), ("shortest", False), ("shortest", True)])
