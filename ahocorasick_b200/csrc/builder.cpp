@@ -494,11 +494,18 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
             // char in the first word-char check but the raw char when scrolling.  The two views agree
             // (and the "maximal run of word chars" formulation is exact) iff the table is closed under
             // toLowerCase, which holds for the default table and every toggle of caseless chars.
-            for (uint32_t c = 0; c < 65536; c++) {
-                if (wc[c] != wc[lower[c]]) {
+            bool closed = true;
+            for (uint32_t c = 0; c < 65536 && closed; c++) closed = wc[c] == wc[lower[c]];
+            if (!closed) {
+                if (family != 3)
                     throw std::domain_error(
-                        "case-insensitive WholeWord matcher with a word-character table that is not closed under "
+                        "case-insensitive WholeWordLongest matcher with a word-character table that is not closed under "
                         "Character.toLowerCase is not implemented on the GPU path (reference quirk Q7)");
+                // WholeWord: the reference's loop is followed literally (kernel_wwlit.cuh); it needs both views of the table
+                a.ww_literal = true;
+                a.wordbits_fold.assign(2048, 0);
+                for (uint32_t c = 0; c < 65536; c++) {
+                    if (wc[lower[c]]) a.wordbits_fold[c >> 5] |= 1u << (c & 31);
                 }
             }
         }
@@ -612,7 +619,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
     // WholeWordLongest with a dictionary whose (trimmed) keywords hold no non-word char: a walk can never leave its word
     // (there is no transition on a non-word char) and a keyword followed by a non-word char is the whole word, so the
     // family coincides with WholeWord and takes its hash path.
-    if (family == 3 || (family == 4 && a.ww_plain)) build_ww(a, wc, node_parent, node_cls);
+    if ((family == 3 && !a.ww_literal) || (family == 4 && a.ww_plain)) build_ww(a, wc, node_parent, node_cls);
     timer.lap("whole-word hash");
     return a;
 }
@@ -649,6 +656,7 @@ uint64_t automaton_fingerprint(const HostAutomaton &a) {
     vec(t.row_words); vec(t.prow_words); bytes(t.prow_off, sizeof t.prow_off); num(t.pair_gate_bit); num(t.pair_low_bit); vec(t.kidmask); vec(t.buckets); num(t.n_buckets); num(t.hash_seed); num(t.n_deep); num(t.n_heads);
     vec(t.vbuckets); num(t.n_vbuckets); num(t.vseed);
     if (a.wide_ok) { num(a.wide_ok); vec(a.wide_pair); vec(a.wide_chain); vec(a.wide_pair16); }
+    if (a.ww_literal) { num(a.ww_literal); vec(a.wordbits_fold); }
     num(a.ww.ok); vec(a.ww.wcls); vec(a.ww.buckets); num(a.ww.n_buckets); vec(a.ww.pool);
     return h;
 }

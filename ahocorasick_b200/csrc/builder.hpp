@@ -214,6 +214,13 @@ struct HostAutomaton {
     std::vector<uint32_t> wide_pair16;
     WwTables ww;                       // WholeWord hash tables (ww.ok == false: not applicable)
     bool ww_plain = true;              // WholeWordLongest: no keyword holds a non-word char (then it equals WholeWord)
+    // Quirk Q7: a case-insensitive WholeWord matcher whose word-char table is not closed under Character.toLowerCase.  The
+    // reference tests the LOWER-CASED char where a walk fails (WholeWordMatchSet.java:96-101) and the RAW char in its two
+    // scroll loops (:113,118; the Readable overload lower-cases there too, WholeWordMatchMap.java:328), and its trie may
+    // hold chars that are no word chars - "maximal runs of word chars" no longer describes it.  Such matchers follow the
+    // loop literally (kernel_wwlit.cuh) and need the table in both views.
+    bool ww_literal = false;
+    std::vector<uint32_t> wordbits_fold;  // 2048 words: bit c = wordChars[toLowerCase(c)] (ww_literal only)
 };
 
 // Throws IllegalArgument with the reference's message for WholeWord keywords holding non-word chars.

@@ -12,6 +12,7 @@ constexpr uint32_t kKids = 2u;
 struct DevAutomaton {
     const uint16_t *cls;       // [65536] code unit -> class (case folding folded in)
     const uint32_t *wordbits;  // [2048] raw word-char bitmap (WholeWord), else nullptr
+    const uint32_t *wordbits_fold;  // [2048] bit c = wordChars[toLowerCase(c)] (literal WholeWord matchers, quirk Q7), else nullptr
     const uint2 *root;         // [n_classes] {child, info}
     const uint4 *edges;        // open addressing, {parent, cls, child, info}; empty: parent == kNoneD
     const uint32_t *node_value;  // [n_nodes]

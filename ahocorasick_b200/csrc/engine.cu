@@ -25,6 +25,7 @@
 #include "kernel_sel2.cuh"
 #include "kernel_ww.cuh"
 #include "kernel_wide.cuh"
+#include "kernel_wwlit.cuh"
 #include "tier_launch.hpp"
 
 using namespace acgpu;
@@ -120,6 +121,7 @@ int upload(Matcher *m) {
     };
     size_t o_cls = reserve(65536 * sizeof(uint16_t));
     size_t o_word = reserve(a.wordbits.size() * sizeof(uint32_t));
+    size_t o_wfold = reserve(a.wordbits_fold.size() * sizeof(uint32_t));
     size_t o_root = reserve(a.root.size() * sizeof(RootEdge));
     size_t o_edges = reserve(a.edges.size() * sizeof(Edge));
     size_t o_val = reserve(a.node_value.size() * sizeof(uint32_t));
@@ -129,12 +131,15 @@ int upload(Matcher *m) {
     CU_TRY(cudaMemcpy(b + o_cls, a.cls.data(), 65536 * sizeof(uint16_t), cudaMemcpyHostToDevice));
     if (!a.wordbits.empty())
         CU_TRY(cudaMemcpy(b + o_word, a.wordbits.data(), a.wordbits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (!a.wordbits_fold.empty())
+        CU_TRY(cudaMemcpy(b + o_wfold, a.wordbits_fold.data(), a.wordbits_fold.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(b + o_root, a.root.data(), a.root.size() * sizeof(RootEdge), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(b + o_edges, a.edges.data(), a.edges.size() * sizeof(Edge), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(b + o_val, a.node_value.data(), a.node_value.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     DevAutomaton &d = m->dev;
     d.cls = reinterpret_cast<const uint16_t *>(b + o_cls);
     d.wordbits = a.wordbits.empty() ? nullptr : reinterpret_cast<const uint32_t *>(b + o_word);
+    d.wordbits_fold = a.wordbits_fold.empty() ? nullptr : reinterpret_cast<const uint32_t *>(b + o_wfold);
     d.root = reinterpret_cast<const uint2 *>(b + o_root);
     d.edges = reinterpret_cast<const uint4 *>(b + o_edges);
     d.node_value = reinterpret_cast<const uint32_t *>(b + o_val);
@@ -351,6 +356,7 @@ struct RunOpts {
     int64_t chain_n = -1;  // chain domain [0, chain_n); -1 => n
     int64_t *d_carry = nullptr;  // [2] int64 (selection families)
     int64_t abs0 = 0;      // window position of the first char of the input, -1 = before this window (WholeWordLongest)
+    bool folded_scroll = false;  // literal WholeWord matchers (quirk Q7): the Readable overloads scroll on the lower-cased char
 };
 
 int launch_mask(Matcher *m, const MaskArgs &P, int grid, cudaStream_t st, bool mir = false) {
@@ -860,6 +866,66 @@ int enqueue_wide(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from
     return rc;
 }
 
+// WholeWord, case-insensitive with a word-character table that is not closed under toLowerCase (quirk Q7): the reference's
+// loop, literally, one thread per synchronisation point (kernel_wwlit.cuh): count, scan, write
+int enqueue_ww_literal(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint32_t *d_val, int64_t cap, unsigned long long *d_total,
+                       cudaStream_t st, const RunOpts &opt) {
+    const int64_t n_rows = (n + kMaskRow - 1) / kMaskRow;
+    const int64_t n_blocks = (n_rows + kScanRows - 1) / kScanRows;
+    Scratch S;
+    const size_t o_ctr = S.reserve(256);
+    const size_t o_cnt = S.reserve(static_cast<size_t>(n_rows) * 4);
+    const size_t o_blk = S.reserve(static_cast<size_t>(n_blocks) * 8);
+    void *ws = nullptr;
+    CU_TRY(cudaMallocAsync(&ws, S.off, st));
+    char *w = static_cast<char *>(ws);
+    int rc = ACGPU_OK;
+    auto launch_ok = [&](const char *what) {
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && rc == ACGPU_OK) rc = fail(ACGPU_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    };
+    if (cudaMemsetAsync(w + o_ctr, 0, 256, st) != cudaSuccess) rc = fail(ACGPU_ECUDA, "memset failed");
+    WwLitArgs P{};
+    P.hay = d_hay;
+    P.n = n;
+    P.n_rows = n_rows;
+    P.row_count = reinterpret_cast<uint32_t *>(w + o_cnt);
+    P.row_excl = P.row_count;
+    P.block_excl = reinterpret_cast<unsigned long long *>(w + o_blk);
+    P.pos_base = opt.pos_base;
+    P.scroll_folded = opt.folded_scroll ? 1 : 0;
+    P.pos_out = d_pos;
+    P.val_out = d_val;
+    P.cap = cap;
+    const int grid = static_cast<int>(std::min<int64_t>(n_rows, static_cast<int64_t>(m->sm_count) * 8));
+    if (rc == ACGPU_OK) {
+        if (m->dev.is_map)
+            k_ww_literal<false, true><<<grid, kMaskRow, 0, st>>>(m->dev, P);
+        else
+            k_ww_literal<false, false><<<grid, kMaskRow, 0, st>>>(m->dev, P);
+        launch_ok("k_ww_literal (count)");
+    }
+    if (rc == ACGPU_OK) {
+        ScanArgs SA{};
+        SA.row_count = P.row_count;
+        SA.block_excl = reinterpret_cast<unsigned long long *>(w + o_blk);
+        SA.done = reinterpret_cast<unsigned int *>(w + o_ctr + 64);
+        SA.total_out = d_total;
+        SA.n_rows = n_rows;
+        k_row_scan<<<static_cast<unsigned>(n_blocks), 1024, 0, st>>>(SA);
+        launch_ok("k_row_scan");
+    }
+    if (rc == ACGPU_OK && cap > 0) {
+        if (m->dev.is_map)
+            k_ww_literal<true, true><<<grid, kMaskRow, 0, st>>>(m->dev, P);
+        else
+            k_ww_literal<true, false><<<grid, kMaskRow, 0, st>>>(m->dev, P);
+        launch_ok("k_ww_literal (write)");
+    }
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
 // Enqueue every kernel of one match on `st`.  d_total receives the total number of matches.
 int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from, int64_t emit_to, int2 *d_pos,
                   uint32_t *d_val, int64_t cap, unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
@@ -916,6 +982,10 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
     if (n == 0 || chain_n == 0) {
         CU_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
         return ACGPU_OK;
+    }
+    if (m->host.ww_literal) {
+        if (opt.ctx != 0 || chain_n != n) return fail(ACGPU_EINVAL, "literal WholeWord matchers scan whole haystacks");
+        return enqueue_ww_literal(m, d_hay, n, d_pos, d_val, cap, d_total, st, opt);
     }
     const bool chain = A.family != ACGPU_WHOLEWORD && !(A.family == ACGPU_WHOLEWORDLONGEST && m->use_ww);
     if (m->use_ww) {
@@ -1186,6 +1256,7 @@ struct HostCall {
     unsigned long long *h_total = nullptr;   // [2] pinned
     PinnedBlock blk;                          // result block: pos[cap] then val[cap]
     int64_t cap = 0, count = 0;               // records the block can hold / holds
+    bool readable_view = false;               // literal WholeWord matchers: the semantics of the Readable overloads (RunOpts::folded_scroll)
 
     explicit HostCall(Matcher *mm) : m(mm), is_map(mm->host.is_map) {}
 
@@ -1415,6 +1486,7 @@ struct HostCall {
             CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_pos[0]), static_cast<size_t>(dcap) * 8, s_k));
             if (is_map) CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_val[0]), static_cast<size_t>(dcap) * 4, s_k));
             RunOpts opt;
+            opt.folded_scroll = readable_view;
             int rc = enqueue_match(m, d_hay, n, 0, n, d_pos[0], d_val[0], dcap, d_total, s_k, opt);
             if (rc != ACGPU_OK) return rc;
             CU_TRY(cudaMemcpyAsync(h_total, d_total, 8, cudaMemcpyDeviceToHost, s_k));
@@ -1762,7 +1834,7 @@ int acgpu_launches_per_match(uint64_t handle) {
     if (!m) return fail(ACGPU_EINVAL, "bad handle");
     switch (m->host.family) {
     case ACGPU_AHOCORASICK: return m->use_tier ? 3 : (m->use_wide ? (m->wide_tile ? 4 : 3) : 1);  // wide, generation 2: tile, tail, scan, emit
-    case ACGPU_WHOLEWORD: return m->use_ww ? 1 : 2;
+    case ACGPU_WHOLEWORD: return m->host.ww_literal ? 3 : (m->use_ww ? 1 : 2);
     default: return m->use_tier && m->host.is_map ? 7 : 6;  // one-shot tier path: mask, map, group, top, tiles, emit (+ values)  // one-shot matches; the streaming path always takes the 6-launch route
     }
 }
@@ -2057,6 +2129,10 @@ struct StreamCtx {
         int64_t avail = 0, ctx = 0, limit = 0, base = 0;
     } pend;
     unsigned long long *h_total = nullptr;  // pinned: the match count of the pending block
+    // literal WholeWord matchers (quirk Q7): a segment of the reference's loop can be as long as the input, so the feeds
+    // are only collected and acgpu_stream_end scans the whole input in one call (every record arrives with the end)
+    bool literal = false;
+    std::vector<uint16_t> collected;
 };
 
 StreamCtx *as_stream(uint64_t h) {
@@ -2426,6 +2502,11 @@ int acgpu_stream_begin(uint64_t handle, uint64_t *stream_handle) {
     StreamCtx *s = new (std::nothrow) StreamCtx();
     if (!s) return fail(ACGPU_ENOMEM, "out of memory");
     s->m = m;
+    if (m->host.ww_literal) {
+        s->literal = true;
+        *stream_handle = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(s));
+        return ACGPU_OK;
+    }
     cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; i++) {
         e = cudaMallocHost(reinterpret_cast<void **>(&s->h_pin[i]), kPinChars * 2);
@@ -2469,6 +2550,15 @@ int acgpu_stream_feed(uint64_t stream_handle, const uint16_t *chars, int32_t n, 
     fill_empty(out);
     CU_TRY(cudaSetDevice(s->m->device));
     if (n == 0) return ACGPU_OK;
+    if (s->literal) {
+        if (s->collected.size() + static_cast<size_t>(n) > 0x7FFFFFFFull) return fail(ACGPU_EINVAL, "stream longer than a Java int");
+        try {
+            s->collected.insert(s->collected.end(), chars, chars + n);
+        } catch (const std::bad_alloc &) {
+            return fail(ACGPU_ENOMEM, "out of memory collecting the stream");
+        }
+        return ACGPU_OK;
+    }
     int rc = stream_append(s, chars, n);
     if (s->pipelined) {
         // upload of this block (st_up) || download of the previous block's records (st); then this block's scan is
@@ -2502,7 +2592,15 @@ int acgpu_stream_end(uint64_t stream_handle, acgpu_result *out) {
     if (out) {
         fill_empty(out);
         cudaSetDevice(s->m->device);
-        if (s->pipelined) {
+        if (s->literal) {
+            if (!s->collected.empty()) {
+                HostCall hc(s->m);
+                hc.readable_view = true;
+                rc = hc.init();
+                if (rc == ACGPU_OK) rc = hc.run_whole(s->collected.data(), static_cast<int64_t>(s->collected.size()));
+                rc = hc.finish(rc, out);
+            }
+        } else if (s->pipelined) {
             acgpu_result a, b;
             fill_empty(&b);
             rc = stream_collect(s, &a);

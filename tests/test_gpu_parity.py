@@ -162,6 +162,40 @@ def test_wholeword_custom_word_chars_config3_style():
         ac.WholeWordMatchSet(["abc"], True, ["_", "="])
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_wholeword_case_insensitive_tables_not_closed_under_lowercase(seed):
+    """Quirk Q7 (WholeWordMatchSet.java:96-101 vs :113,118; Readable: WholeWordMatchMap.java:325-339): with a custom
+    word-character table that is NOT closed under toLowerCase the case-insensitive loop tests two different views of the
+    table and its trie can hold non-word chars.  The GPU path follows the loop literally (kernel_wwlit.cuh): String and
+    Readable overloads, Set and Map, equal the oracle's - also on text without any synchronisation point."""
+    rng = random.Random(7700 + seed)
+    letters = "abcdeABCDE"
+    if seed % 2 == 0:   # generateWordCharsFlags(char[]): only the listed chars are word chars
+        chars = [c for c in letters + "-_1" if rng.random() < 0.6] or ["A"]
+        args, table = (chars,), ora.word_chars(1, chars, [])
+    else:               # generateWordCharsFlags(char[], boolean[]): the default table with some chars toggled off
+        chars = [c for c in letters if rng.random() < 0.4] or ["a"]
+        toggles = [False] * len(chars)
+        args, table = (chars, toggles), ora.word_chars(2, chars, toggles)
+    closed = all(bool(table[ord(c)]) == bool(table[ord(c.lower())]) for c in letters)
+    word = [c for c in letters + "-_1" if table[ord(c)]]
+    kws = sorted({"".join(rng.choice(word) for _ in range(rng.randint(1, 5))) for _ in range(40)})
+    values = list(range(len(kws)))
+    om = ora.Matcher("wholeword", kws, n_values=len(kws), case_sensitive=False, word_chars_table=table)
+    gs = ac.WholeWordMatchSet(kws, False, *args)
+    gm = ac.WholeWordMatchMap(kws, values, False, *args)
+    hays = ["", "a", "A b", "".join(rng.choice(letters) for _ in range(3000))]   # the last one: no separator at all
+    for n, sep in ((50, " "), (700, " .,;"), (5000, " "), (70_001, " -_,")):
+        hays.append("".join(rng.choice(sep) if rng.random() < 0.25 else rng.choice(letters + "1") for _ in range(n)))
+    for hay in hays:
+        want = oracle_stream(om, hay)
+        assert gpu_set_stream(gs, hay) == [(s, e) for s, e, _ in want], (closed, len(hay))
+        assert gpu_map_stream(gm, hay) == want, (closed, len(hay))
+        c = Collect()
+        gm.match(io.StringIO(hay), c)
+        assert [v[0] for v in c.calls] == [int(r["value"]) for r in om.match(hay, readable=True)], (closed, len(hay))
+
+
 @pytest.mark.parametrize("gen1", [False, True])
 @pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
 def test_baseline_configs_scaled(cfg, gen1, monkeypatch):
