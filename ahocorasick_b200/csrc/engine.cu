@@ -159,9 +159,18 @@ int upload_tier(Matcher *m) {
     if (!t.ok || m->host.family == ACGPU_WHOLEWORD || m->host.family == ACGPU_WHOLEWORDLONGEST) return ACGPU_OK;
     const char *force = getenv("ACGPU_FORCE_GEN1");
     if (force && force[0] == '1') return ACGPU_OK;
-    // generation 4 (k_tier_pair, pair rows) whenever the dictionary has them; ACGPU_MASK_GEN=3 keeps k_tier_mask (A/B runs)
+    // generation 4 (k_tier_pair, pair rows) or generation 3 (k_tier_mask).  The pair kernel's gate bit skips the gather of
+    // pairs whose level-K row has no continuation at all: on configs[1] (100 k keywords) it wins 2 %; on a saturated
+    // dictionary (configs[4]: most level-K contexts continue) next to nothing is skipped and k_tier_mask is 1.4 % faster
+    // (profiles/r02_summary.md).  ACGPU_MASK_GEN=3 / 4 forces one (A/B runs).
     const char *gen = getenv("ACGPU_MASK_GEN");
-    m->mask_pair = !t.prow_words.empty() && !(gen && gen[0] == '3');
+    bool saturated = false;
+    if (!t.kidmask.empty()) {
+        size_t live = 0;
+        for (size_t i = 0; i < t.kidmask.size(); i += 2) live += (t.kidmask[i] | t.kidmask[i + 1]) != 0u;
+        saturated = live * 4 > (t.kidmask.size() / 2) * 3;  // more than three quarters of the contexts continue
+    }
+    m->mask_pair = !t.prow_words.empty() && (gen ? gen[0] != '3' : !saturated);
     m->mask_smem = mask_smem_bytes(m->mask_pair ? t.prow_words.size() : t.row_words.size());
     {
         // generation 5 (k_tier_fused: masks and records in one persistent launch) - opt-in (ACGPU_FUSE=1): parity-green, but

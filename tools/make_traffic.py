@@ -10,7 +10,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KERNEL_SOURCES = ["kernel_tier.cuh", "kernel_mask.cuh", "kernel_emit.cuh"]
+KERNEL_SOURCES = ["kernel_tier.cuh", "kernel_mask.cuh", "kernel_pair.cuh", "kernel_emit.cuh"]
 
 
 def kernel_sources_sha():
