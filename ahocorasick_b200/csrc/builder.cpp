@@ -321,6 +321,50 @@ void build_tiers(HostAutomaton &a, const std::vector<uint32_t> &node_parent, con
     }
 }
 
+// Map values of the wide path (HostAutomaton::wide_vals)
+void build_wide_values(HostAutomaton &a, const std::vector<uint32_t> &node_parent, const std::vector<uint16_t> &node_cls) {
+    a.wide_vals.clear();
+    a.wide_n_vbuckets = 0;
+    if (!a.is_map) return;
+    struct Key { uint64_t h; uint32_t len, value; };
+    std::vector<Key> keys;
+    std::vector<uint16_t> tmp;
+    for (int64_t id = 1; id < a.n_nodes; id++) {
+        if (!(a.node_info[id] & kInfoTerminal)) continue;
+        tmp.clear();
+        for (uint32_t cur = static_cast<uint32_t>(id); cur != 0; cur = node_parent[cur]) tmp.push_back(node_cls[cur]);
+        WideValHash h;  // the trie is over reversed keywords: root -> node spells the keyword from its last char back
+        for (size_t i = tmp.size(); i-- > 0;) h.add(tmp[i]);
+        keys.push_back(Key{h.finish(static_cast<uint32_t>(tmp.size())), static_cast<uint32_t>(tmp.size()), a.node_value[id]});
+    }
+    {
+        std::vector<std::pair<uint64_t, uint32_t>> seen;
+        seen.reserve(keys.size());
+        for (const Key &k : keys) seen.emplace_back(k.h, k.len);
+        std::sort(seen.begin(), seen.end());
+        if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) return;  // (hash, length) collision: no table, the emit kernel walks
+    }
+    const uint64_t nb = std::max<uint64_t>(4, keys.size());  // two entries per bucket: load factor 0.5
+    if (nb > 0x7FFFFFFFull) return;
+    a.wide_n_vbuckets = static_cast<uint32_t>(nb);
+    a.wide_vals.assign(static_cast<size_t>(nb) * 8, 0u);
+    for (const Key &k : keys) {
+        uint32_t bk = static_cast<uint32_t>((static_cast<uint64_t>(static_cast<uint32_t>(k.h >> 32)) * nb) >> 32);
+        while (true) {
+            uint32_t *e = &a.wide_vals[static_cast<size_t>(bk) * 8];
+            const int slot = e[2] == 0u ? 0 : (e[6] == 0u ? 1 : -1);
+            if (slot >= 0) {
+                e[slot * 4 + 0] = static_cast<uint32_t>(k.h);
+                e[slot * 4 + 1] = static_cast<uint32_t>(k.h >> 32);
+                e[slot * 4 + 2] = k.len | 0x80000000u;
+                e[slot * 4 + 3] = k.value;
+                break;
+            }
+            bk = bk + 1u == a.wide_n_vbuckets ? 0u : bk + 1u;
+        }
+    }
+}
+
 // AhoCorasick family outside the tier envelope: class-pair table for levels 1 and 2 of the anchored walk (kernel_wide.cuh)
 constexpr int kWideMaxLenHost = 32, kWidePairMaxHost = 64;
 void build_wide(HostAutomaton &a, const std::vector<uint32_t> &node_parent, const std::vector<uint16_t> &node_cls) {
@@ -329,7 +373,10 @@ void build_wide(HostAutomaton &a, const std::vector<uint32_t> &node_parent, cons
     if (!a.has_other || a.max_len < 1 || a.max_len > kWideMaxLenHost) return;
     a.wide_ok = true;
     const int64_t C = a.n_classes;
-    if (C > kWidePairMaxHost) return;  // the walk starts at the root table instead
+    if (C > kWidePairMaxHost) {  // the walk starts at the root table instead
+        build_wide_values(a, node_parent, node_cls);
+        return;
+    }
     a.wide_pair.assign(static_cast<size_t>(C * C * 2), 0);
     for (int64_t c0 = 0; c0 < C; c0++) {
         const RootEdge &r = a.root[c0];
@@ -411,6 +458,7 @@ void build_wide(HostAutomaton &a, const std::vector<uint32_t> &node_parent, cons
         }
     }
     a.wide_chain.resize(entry_child.size() * 8);
+    build_wide_values(a, node_parent, node_cls);
 }
 
 // WholeWord hash tables: one entry per distinct (trimmed, folded) keyword = per terminal node of the forward trie
@@ -655,7 +703,7 @@ uint64_t automaton_fingerprint(const HostAutomaton &a) {
     bytes(t.pow_c, sizeof t.pow_c); bytes(t.row_off, sizeof t.row_off);
     vec(t.row_words); vec(t.prow_words); bytes(t.prow_off, sizeof t.prow_off); num(t.pair_gate_bit); num(t.pair_low_bit); vec(t.kidmask); vec(t.buckets); num(t.n_buckets); num(t.hash_seed); num(t.n_deep); num(t.n_heads);
     vec(t.vbuckets); num(t.n_vbuckets); num(t.vseed);
-    if (a.wide_ok) { num(a.wide_ok); vec(a.wide_pair); vec(a.wide_chain); vec(a.wide_pair16); }
+    if (a.wide_ok) { num(a.wide_ok); vec(a.wide_pair); vec(a.wide_chain); vec(a.wide_pair16); vec(a.wide_vals); num(a.wide_n_vbuckets); }
     if (a.ww_literal) { num(a.ww_literal); vec(a.wordbits_fold); }
     num(a.ww.ok); vec(a.ww.wcls); vec(a.ww.buckets); num(a.ww.n_buckets); vec(a.ww.pool);
     return h;

@@ -162,6 +162,28 @@ inline uint32_t value_hash32(uint32_t lo, uint32_t hi) {
     return h;
 }
 
+// hash of a keyword's class string for HostAutomaton::wide_vals: feed the classes in the order a match meets them walking
+// back from its last char, then finish with the length
+struct WideValHash {
+    uint64_t h = 0xCBF29CE484222325ull;
+#ifdef __CUDACC__
+    __host__ __device__
+#endif
+    inline void add(uint32_t c) { h = (h ^ c) * 0x100000001B3ull; }
+#ifdef __CUDACC__
+    __host__ __device__
+#endif
+    inline uint64_t finish(uint32_t len) {
+        uint64_t x = h ^ (static_cast<uint64_t>(len) * 0x9E3779B97F4A7C15ull);
+        x ^= x >> 29;
+        x *= 0xBF58476D1CE4E5B9ull;
+        x ^= x >> 32;
+        x *= 0x94D049BB133111EBull;
+        x ^= x >> 29;
+        return x;
+    }
+};
+
 inline uint64_t deep_hash64(uint64_t key, uint64_t seed) {
     uint64_t h = key ^ seed;
     h ^= h >> 29;
@@ -212,6 +234,13 @@ struct HostAutomaton {
     // exists) << 16 | (level-2 node exists) << 17, child mask lo, hi} is the shared-memory table of levels 1 and 2.
     std::vector<uint32_t> wide_chain;
     std::vector<uint32_t> wide_pair16;
+    // Map values of the wide path: keyword -> value by a 64-bit hash of its class string (wide_value_hash: the classes as
+    // a match meets them walking back from its last char), two 16-byte entries {hash lo, hash hi, length | 1 << 31, value}
+    // per 32-byte bucket, linear probing over buckets.  A record is a real match, so its key is in the table: the builder
+    // checks that no two keywords share (hash, length), and a hit on those IS the keyword - one gather per record.
+    // Empty: no table (Set, or a hash collision) - k_wide_emit walks the trie again instead.
+    std::vector<uint32_t> wide_vals;
+    uint32_t wide_n_vbuckets = 0;
     WwTables ww;                       // WholeWord hash tables (ww.ok == false: not applicable)
     bool ww_plain = true;              // WholeWordLongest: no keyword holds a non-word char (then it equals WholeWord)
     // Quirk Q7: a case-insensitive WholeWord matcher whose word-char table is not closed under Character.toLowerCase.  The

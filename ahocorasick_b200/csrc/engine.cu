@@ -95,6 +95,7 @@ struct Matcher {
     bool use_wide = false;
     DevWide wide{};
     void *d_wide_blob = nullptr;
+    void *d_wide_vals = nullptr;   // Map values by keyword hash (HostAutomaton::wide_vals)
     size_t wide_smem = 0;
     bool wide_tile = false;   // k_wide_tile (pair table + path-compressed edges) instead of k_wide_mask
     // WholeWord hash tables (kernel_ww.cuh)
@@ -276,7 +277,20 @@ int upload_wide(Matcher *m) {
     m->wide.pair = nullptr;
     m->wide.chain = nullptr;
     m->wide.pair16 = nullptr;
+    m->wide.vals = nullptr;
+    m->wide.n_vbuckets = 0;
     m->wide_tile = false;
+    {
+        const char *vw = getenv("ACGPU_WIDE_VALUES");  // ACGPU_WIDE_VALUES=walk: the second trie walk per record (A/B runs)
+        if (!m->host.wide_vals.empty() && !(vw && vw[0] == 'w')) {
+            const size_t bytes = m->host.wide_vals.size() * 4;
+            CU_TRY(cudaMalloc(&m->d_wide_vals, bytes));
+            m->table_bytes += static_cast<int64_t>(bytes);
+            CU_TRY(cudaMemcpy(m->d_wide_vals, m->host.wide_vals.data(), bytes, cudaMemcpyHostToDevice));
+            m->wide.vals = static_cast<const uint4 *>(m->d_wide_vals);
+            m->wide.n_vbuckets = m->host.wide_n_vbuckets;
+        }
+    }
     if (pair) {
         const size_t pair_bytes = align_up(m->host.wide_pair.size() * 4, 256), pair16_bytes = align_up(m->host.wide_pair16.size() * 4, 256);
         const size_t chain_bytes = m->host.wide_chain.size() * 4;
@@ -866,9 +880,9 @@ int enqueue_wide(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from
         E.cap = cap;
         const int egrid = static_cast<int>(std::min<int64_t>((n_rows + kEmitWarps - 1) / kEmitWarps, static_cast<int64_t>(m->sm_count) * 128));
         if (m->dev.is_map)
-            k_wide_emit<true><<<egrid, kEmitWarps * 32, 0, st>>>(m->dev, E);
+            k_wide_emit<true><<<egrid, kEmitWarps * 32, 0, st>>>(m->dev, m->wide, E);
         else
-            k_wide_emit<false><<<egrid, kEmitWarps * 32, 0, st>>>(m->dev, E);
+            k_wide_emit<false><<<egrid, kEmitWarps * 32, 0, st>>>(m->dev, m->wide, E);
         launch_ok("k_wide_emit");
     }
     cudaFreeAsync(ws, st);
@@ -1628,6 +1642,7 @@ int finish_create(Matcher *m, int family, int device, uint64_t *handle) {
         if (m->d_tier_blob) cudaFree(m->d_tier_blob);
         if (m->d_ww_blob) cudaFree(m->d_ww_blob);
         if (m->d_wide_blob) cudaFree(m->d_wide_blob);
+        if (m->d_wide_vals) cudaFree(m->d_wide_vals);
         if (m->d_blob) cudaFree(m->d_blob);
         delete m;
         return rc;
@@ -1813,6 +1828,7 @@ int acgpu_destroy(uint64_t handle) {
     if (m->d_tier_blob) cudaFree(m->d_tier_blob);
     if (m->d_ww_blob) cudaFree(m->d_ww_blob);
     if (m->d_wide_blob) cudaFree(m->d_wide_blob);
+    if (m->d_wide_vals) cudaFree(m->d_wide_vals);
     m->magic = 0;
     delete m;
     return ACGPU_OK;

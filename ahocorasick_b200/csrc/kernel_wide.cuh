@@ -32,6 +32,8 @@ struct DevWide {
     int32_t C;
     const uint4 *chain;   // path-compressed edges below level 2 (HostAutomaton::wide_chain): two uint4 per 32-byte entry; nullptr: none
     const uint4 *pair16;  // [C * C] k_wide_tile's table of levels 1 and 2 (HostAutomaton::wide_pair16)
+    const uint4 *vals;    // Map values by keyword hash (HostAutomaton::wide_vals), two entries per bucket; nullptr: walk the trie
+    uint32_t n_vbuckets;
 };
 
 struct WideArgs {
@@ -368,13 +370,18 @@ __global__ void __launch_bounds__(kWtThreads, 2) k_wide_tile(const DevAutomaton 
             // a thin round costs the whole CTA a gather latency: once few walks are left they are handed to k_wide_tail
             if (round >= P.min_rounds && n_q <= P.hand_over && P.tail_cap) {
                 if (tid == 0) {
-                    const uint32_t at = atomicAdd(P.tail_count, n_q);
-                    if (at + n_q > P.tail_cap) {
-                        atomicSub(P.tail_count, n_q);
-                        s_cnt[3] = 0xFFFFFFFFu;
-                    } else {
-                        s_cnt[3] = at;
+                    // reserve by compare-and-swap: a reservation that does not fit must never show in the count, or a
+                    // neighbour's slots would end up beyond the final count
+                    uint32_t at = *reinterpret_cast<volatile unsigned int *>(P.tail_count), got = 0xFFFFFFFFu;
+                    while (at + n_q <= P.tail_cap) {
+                        const uint32_t seen = atomicCAS(P.tail_count, at, at + n_q);
+                        if (seen == at) {
+                            got = at;
+                            break;
+                        }
+                        at = seen;
                     }
+                    s_cnt[3] = got;
                 }
                 __syncthreads();
                 const uint32_t at = s_cnt[3];
@@ -558,8 +565,24 @@ __global__ void __launch_bounds__(256) k_wide_tail(const DevAutomaton A, const D
     }
 }
 
-// value index of the keyword of length d whose last char is position q (Maps): the walk again, d steps
-__device__ __forceinline__ uint32_t wide_value(const DevAutomaton &A, const uint16_t *hay, int64_t q, int d) {
+// value index of the keyword of length d whose last char is position q (Maps).  With the keyword-hash table: hash the d
+// classes, one gathered bucket (the record is a real match, so the key is there and (hash, length) names it); without:
+// the walk again, d steps.
+__device__ __forceinline__ uint32_t wide_value(const DevAutomaton &A, const DevWide &Wd, const uint16_t *hay, int64_t q, int d) {
+    if (Wd.vals) {
+        WideValHash h;
+        for (int i = 0; i < d; i++) h.add((uint32_t)__ldg(&A.cls[__ldg(&hay[q - i])]));
+        const unsigned long long x = h.finish((uint32_t)d);
+        const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32), tag = (uint32_t)d | 0x80000000u;
+        uint32_t bk = __umulhi(hi, Wd.n_vbuckets);
+        for (uint32_t tries = 0; tries < Wd.n_vbuckets; tries++) {
+            const uint4 e0 = __ldg(Wd.vals + (size_t)bk * 2), e1 = __ldg(Wd.vals + (size_t)bk * 2 + 1);
+            if (e0.x == lo && e0.y == hi && e0.z == tag) return e0.w;
+            if (e1.x == lo && e1.y == hi && e1.z == tag) return e1.w;
+            bk = bk + 1u == Wd.n_vbuckets ? 0u : bk + 1u;
+        }
+        return kNoneD;
+    }
     uint32_t node = 0, info = 0;
     for (int i = 0; i < d; i++) {
         if (!trie_step(A, node, (uint32_t)__ldg(&A.cls[__ldg(&hay[q - i])]), info)) return kNoneD;
@@ -577,7 +600,7 @@ __device__ __forceinline__ int2 decode_rec32(uint32_t code, int32_t e_row) {
 // bits of its 8 positions into 16-bit codes in shared memory (code = index of the bit in the row's 8 192-bit mask), then
 // the warp decodes two codes per lane into one 16-byte streaming store.
 template <bool kIsMap>
-__global__ void __launch_bounds__(kEmitWarps * 32) k_wide_emit(const DevAutomaton A, const EmitArgs E) {
+__global__ void __launch_bounds__(kEmitWarps * 32) k_wide_emit(const DevAutomaton A, const DevWide Wd, const EmitArgs E) {
     __shared__ __align__(16) int2 s_stage_all[kEmitWarps][kEmitStage + 2];
     __shared__ uint32_t s_val_all[kIsMap ? kEmitWarps : 1][kIsMap ? kEmitStage : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -627,7 +650,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_wide_emit(const DevAutomato
             if (kIsMap) {
                 for (uint32_t r = lane; r < total; r += 32) {
                     const uint32_t code = s_code[r + par];
-                    __stcs(E.val_out + base + r, wide_value(A, E.hay, q_row + (int64_t)(code >> 5), 32 - (int)(code & 31u)));
+                    __stcs(E.val_out + base + r, wide_value(A, Wd, E.hay, q_row + (int64_t)(code >> 5), 32 - (int)(code & 31u)));
                 }
             }
             int2 *g = E.pos_out + (base - par);  // 16-byte aligned
@@ -657,7 +680,7 @@ __global__ void __launch_bounds__(kEmitWarps * 32) k_wide_emit(const DevAutomato
                         if (o < (uint32_t)kEmitStage) {
                             const int32_t e = e_row + lane * 8 + wi;
                             s_stage[o] = make_int2(e - (32 - t), e);
-                            if (kIsMap) s_val[o] = wide_value(A, E.hay, q_row + lane * 8 + wi, 32 - t);
+                            if (kIsMap) s_val[o] = wide_value(A, Wd, E.hay, q_row + lane * 8 + wi, 32 - t);
                         }
                         ++o;
                     }
