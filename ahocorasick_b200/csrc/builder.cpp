@@ -668,6 +668,10 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
     // (there is no transition on a non-word char) and a keyword followed by a non-word char is the whole word, so the
     // family coincides with WholeWord and takes its hash path.
     if ((family == 3 && !a.ww_literal) || (family == 4 && a.ww_plain)) build_ww(a, wc, node_parent, node_cls);
+    if (family == 4 && !a.ww_plain && a.has_other && a.n_classes < 32768 && a.max_len <= kWwMaxLen - 1) {
+        a.wwl_wcls.resize(65536);
+        for (uint32_t c = 0; c < 65536; c++) a.wwl_wcls[c] = static_cast<uint16_t>(a.cls[c] | (wc[c] ? 0x8000u : 0u));
+    }
     timer.lap("whole-word hash");
     return a;
 }
@@ -705,6 +709,7 @@ uint64_t automaton_fingerprint(const HostAutomaton &a) {
     vec(t.vbuckets); num(t.n_vbuckets); num(t.vseed);
     if (a.wide_ok) { num(a.wide_ok); vec(a.wide_pair); vec(a.wide_chain); vec(a.wide_pair16); vec(a.wide_vals); num(a.wide_n_vbuckets); }
     if (a.ww_literal) { num(a.ww_literal); vec(a.wordbits_fold); }
+    vec(a.wwl_wcls);
     num(a.ww.ok); vec(a.ww.wcls); vec(a.ww.buckets); num(a.ww.n_buckets); vec(a.ww.pool);
     return h;
 }

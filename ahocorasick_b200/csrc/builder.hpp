@@ -243,6 +243,7 @@ struct HostAutomaton {
     uint32_t wide_n_vbuckets = 0;
     WwTables ww;                       // WholeWord hash tables (ww.ok == false: not applicable)
     bool ww_plain = true;              // WholeWordLongest: no keyword holds a non-word char (then it equals WholeWord)
+    std::vector<uint16_t> wwl_wcls;    // WholeWordLongest with phrases (k_wwl_starts): code unit -> class | word-char flag << 15; empty: not applicable
     // Quirk Q7: a case-insensitive WholeWord matcher whose word-char table is not closed under Character.toLowerCase.  The
     // reference tests the LOWER-CASED char where a walk fails (WholeWordMatchSet.java:96-101) and the RAW char in its two
     // scroll loops (:113,118; the Readable overload lower-cases there too, WholeWordMatchMap.java:328), and its trie may

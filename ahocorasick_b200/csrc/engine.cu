@@ -98,6 +98,9 @@ struct Matcher {
     void *d_wide_vals = nullptr;   // Map values by keyword hash (HostAutomaton::wide_vals)
     size_t wide_smem = 0;
     bool wide_tile = false;   // k_wide_tile (pair table + path-compressed edges) instead of k_wide_mask
+    // WholeWordLongest with phrase keywords: walk starts compacted by k_wwl_starts (kernel_ww.cuh)
+    bool use_wwl2 = false;
+    uint16_t *d_wwl_wcls = nullptr;
     // WholeWord hash tables (kernel_ww.cuh)
     bool use_ww = false;
     DevWw ww{};
@@ -324,6 +327,17 @@ int upload_wide(Matcher *m) {
 int upload_ww(Matcher *m) {
     const WwTables &t = m->host.ww;
     m->use_ww = false;
+    m->use_wwl2 = false;
+    {
+        const char *force = getenv("ACGPU_FORCE_GEN1"), *gen = getenv("ACGPU_WWL_GEN");  // ACGPU_WWL_GEN=1: the generation-1 chain over every position (A/B runs)
+        if (m->host.family == ACGPU_WHOLEWORDLONGEST && !m->host.wwl_wcls.empty() && !(force && force[0] == '1') && !(gen && gen[0] == '1')) {
+            CU_TRY(cudaMalloc(reinterpret_cast<void **>(&m->d_wwl_wcls), 65536 * 2));
+            m->table_bytes += 65536 * 2;
+            CU_TRY(cudaMemcpy(m->d_wwl_wcls, m->host.wwl_wcls.data(), 65536 * 2, cudaMemcpyHostToDevice));
+            CU_TRY(cudaFuncSetAttribute(k_wwl_starts, cudaFuncAttributeMaxDynamicSharedMemorySize, (kWwTile + 16 * 16 + 2) * 2));
+            m->use_wwl2 = true;
+        }
+    }
     if (!t.ok || (m->host.family != ACGPU_WHOLEWORD && m->host.family != ACGPU_WHOLEWORDLONGEST)) return ACGPU_OK;
     const char *force = getenv("ACGPU_FORCE_GEN1");
     if (force && force[0] == '1') return ACGPU_OK;
@@ -949,6 +963,138 @@ int enqueue_ww_literal(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos
     return rc;
 }
 
+// The generation-1 selection passes over per-start values v (k_sel_map / group / top / entries / emit): P comes with the
+// values, the chain domain, the mode and the outputs filled in; the tile scratch is allocated here.
+int enqueue_selection(Matcher *m, SelArgs P, bool chain, cudaStream_t st) {
+    const DevAutomaton &A = m->dev;
+    const int64_t n_tiles = (P.n + kSelTile - 1) / kSelTile;
+    const int64_t n_groups = (n_tiles + kSelGroup - 1) / kSelGroup;
+    if (n_tiles == 0) {
+        CU_TRY(cudaMemsetAsync(P.total_out, 0, sizeof(unsigned long long), st));
+        return ACGPU_OK;
+    }
+    Scratch S;
+    size_t o_ctr = S.reserve(256);
+    size_t o_status = S.reserve(static_cast<size_t>(n_tiles) * 8);
+    size_t o_zero_end = S.off;  // everything up to here is zero-initialised
+    size_t o_exit1 = 0, o_exit2 = 0, o_entry2 = 0, o_entry1 = 0;
+    if (chain) {
+        o_exit1 = S.reserve(static_cast<size_t>(n_tiles) * P.M * sizeof(uint16_t));
+        o_exit2 = S.reserve(static_cast<size_t>(n_groups) * P.M * sizeof(uint16_t));
+        o_entry2 = S.reserve(static_cast<size_t>(n_groups) * sizeof(int64_t));
+        o_entry1 = S.reserve(static_cast<size_t>(n_tiles) * sizeof(int32_t));
+    }
+    void *ws = nullptr;
+    CU_TRY(cudaMallocAsync(&ws, S.off, st));
+    char *b = static_cast<char *>(ws);
+    int rc = ACGPU_OK;
+    auto launch_ok = [&](const char *what) {
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && rc == ACGPU_OK) rc = fail(ACGPU_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    };
+    if (cudaMemsetAsync(ws, 0, o_zero_end, st) != cudaSuccess) rc = fail(ACGPU_ECUDA, "memset failed");
+    P.n_tiles = n_tiles;
+    P.n_groups = n_groups;
+    if (P.carry_out && rc == ACGPU_OK && cudaMemsetAsync(P.carry_out, 0xFF, 8, st) != cudaSuccess) rc = fail(ACGPU_ECUDA, "memset failed");  // -1 = chain did not cross chain_n
+    P.tile_counter = reinterpret_cast<unsigned int *>(b + o_ctr);
+    P.status = reinterpret_cast<unsigned long long *>(b + o_status);
+    if (chain && rc == ACGPU_OK) {
+        P.exit1 = reinterpret_cast<uint16_t *>(b + o_exit1);
+        P.exit2 = reinterpret_cast<uint16_t *>(b + o_exit2);
+        P.entry2 = reinterpret_cast<int64_t *>(b + o_entry2);
+        P.entry1 = reinterpret_cast<int32_t *>(b + o_entry1);
+        const int grid_map = static_cast<int>(std::min<int64_t>(n_tiles, m->sm_count * 4));
+        k_sel_map<<<grid_map, kThreads, 0, st>>>(P);
+        launch_ok("k_sel_map");
+        k_sel_group<<<static_cast<unsigned>(n_groups), kThreads, 0, st>>>(P);
+        launch_ok("k_sel_group");
+        k_sel_top<<<1, 32, 0, st>>>(P);
+        launch_ok("k_sel_top");
+        k_sel_entries<<<static_cast<unsigned>((n_groups + 127) / 128), 128, 0, st>>>(P);
+        launch_ok("k_sel_entries");
+    }
+    if (rc == ACGPU_OK) {
+        const int grid = static_cast<int>(std::min<int64_t>(n_tiles, m->sm_count * 4));
+        if (A.is_map)
+            k_sel_emit<true><<<grid, kThreads, kSelEmitSmem, st>>>(A, P);
+        else
+            k_sel_emit<false><<<grid, kThreads, kSelEmitSmem, st>>>(A, P);
+        launch_ok("k_sel_emit");
+    }
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
+// WholeWordLongest with phrase keywords, one-shot: walk starts compacted by k_wwl_starts (kernel_ww.cuh), then the
+// selection passes over the compacted starts (one position in ~six) instead of every haystack position
+int enqueue_wwl2(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint32_t *d_val, int64_t cap, unsigned long long *d_total,
+                 cudaStream_t st, const RunOpts &opt) {
+    const DevAutomaton &A = m->dev;
+    const int64_t mis = static_cast<int64_t>((reinterpret_cast<uintptr_t>(d_hay) >> 1) & 7);
+    const int64_t origin = -mis;  // <= 0, hay + origin 16-byte aligned
+    const int64_t n_tiles = (n - origin + kWwTile - 1) / kWwTile;
+    const int64_t cap_m = n / 2 + 2;  // walk starts are at least two positions apart (+ the first char of the input)
+    Scratch S;
+    const size_t o_ctr = S.reserve(256);
+    const size_t o_status = S.reserve(static_cast<size_t>(n_tiles) * 8);
+    const size_t o_zero_end = S.off;
+    const size_t o_wpos = S.reserve(static_cast<size_t>(cap_m) * 4);
+    const size_t o_v = S.reserve(static_cast<size_t>(cap_m) * 2);
+    void *ws = nullptr;
+    CU_TRY(cudaMallocAsync(&ws, S.off, st));
+    char *b = static_cast<char *>(ws);
+    int rc = ACGPU_OK;
+    if (cudaMemsetAsync(ws, 0, o_zero_end, st) != cudaSuccess) rc = fail(ACGPU_ECUDA, "memset failed");
+    unsigned long long n_starts = 0;
+    if (rc == ACGPU_OK) {
+        WwlArgs W{};
+        W.hay = d_hay;
+        W.n = n;
+        W.origin = origin;
+        W.n_tiles = n_tiles;
+        W.wpos = reinterpret_cast<int32_t *>(b + o_wpos);
+        W.v = reinterpret_cast<uint16_t *>(b + o_v);
+        W.cap = cap_m;
+        W.total_out = reinterpret_cast<unsigned long long *>(b + o_ctr + 64);
+        W.tile_counter = reinterpret_cast<unsigned int *>(b + o_ctr);
+        W.status = reinterpret_cast<unsigned long long *>(b + o_status);
+        DevWw T{};
+        T.wcls = m->d_wwl_wcls;
+        T.max_len = A.max_len;
+        const size_t smem = static_cast<size_t>(kWwTile + 16 * ((A.max_len + 1 + 15) / 16) + 2) * 2;
+        const int grid = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(m->sm_count) * 6));
+        k_wwl_starts<<<grid, kWwThreads, smem, st>>>(A, T, W);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(ACGPU_ECUDA, "k_wwl_starts failed to launch");
+        // the selection grid depends on the number of walk starts: one small read-back in the middle of the call
+        if (rc == ACGPU_OK && (cudaMemcpyAsync(&n_starts, W.total_out, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                               cudaStreamSynchronize(st) != cudaSuccess))
+            rc = fail(ACGPU_ECUDA, "k_wwl_starts failed");
+    }
+    if (rc == ACGPU_OK) {
+        SelArgs P{};
+        P.v = reinterpret_cast<const uint16_t *>(b + o_v);
+        P.n_v = static_cast<int64_t>(n_starts);
+        P.n = static_cast<int64_t>(n_starts);
+        P.M = A.max_len + 2;
+        P.halo = std::max(0, A.max_len - 1);
+        P.dom_lo = 0;
+        P.mode = kModeWholeWordLongest;
+        P.entry0 = 0;
+        P.carry_out = nullptr;
+        P.wpos = reinterpret_cast<const int32_t *>(b + o_wpos);
+        P.hay = d_hay;
+        P.n_hay = n;
+        P.pos_base = opt.pos_base;
+        P.pos_out = d_pos;
+        P.val_out = d_val;
+        P.cap = cap;
+        P.total_out = d_total;
+        rc = enqueue_selection(m, P, true, st);
+    }
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
 // Enqueue every kernel of one match on `st`.  d_total receives the total number of matches.
 int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from, int64_t emit_to, int2 *d_pos,
                   uint32_t *d_val, int64_t cap, unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
@@ -1051,25 +1197,14 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
     }
     if (chain && m->use_tier && opt.ctx == 0 && chain_n == n && opt.entry0 == 0 && !opt.d_carry)
         return enqueue_sel2(m, d_hay, n, d_pos, d_val, cap, d_total, st, opt);
-    const int32_t M = A.max_len + (A.family == ACGPU_WHOLEWORDLONGEST ? 2 : 1);  // exit offsets are < M
+    if (m->use_wwl2 && opt.ctx == 0 && chain_n == n && opt.entry0 == 0 && !opt.d_carry)
+        return enqueue_wwl2(m, d_hay, n, d_pos, d_val, cap, d_total, st, opt);
     const int64_t n_tiles = (chain_n + kSelTile - 1) / kSelTile;
-    const int64_t n_groups = (n_tiles + kSelGroup - 1) / kSelGroup;
     Scratch S;
-    size_t o_ctr = S.reserve(256);
-    size_t o_status = S.reserve(static_cast<size_t>(n_tiles) * 8);
-    size_t o_zero_end = S.off;  // everything up to here is zero-initialised
     size_t o_v = S.reserve(static_cast<size_t>(n) * sizeof(uint16_t));
-    size_t o_exit1 = 0, o_exit2 = 0, o_entry2 = 0, o_entry1 = 0;
-    if (chain) {
-        o_exit1 = S.reserve(static_cast<size_t>(n_tiles) * M * sizeof(uint16_t));
-        o_exit2 = S.reserve(static_cast<size_t>(n_groups) * M * sizeof(uint16_t));
-        o_entry2 = S.reserve(static_cast<size_t>(n_groups) * sizeof(int64_t));
-        o_entry1 = S.reserve(static_cast<size_t>(n_tiles) * sizeof(int32_t));
-    }
     void *ws = nullptr;
     CU_TRY(cudaMallocAsync(&ws, S.off, st));
     char *b = static_cast<char *>(ws);
-    CU_TRY(cudaMemsetAsync(ws, 0, o_zero_end, st));
 
     FwArgs F{};
     F.hay = d_hay;
@@ -1078,8 +1213,9 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
     F.p_hi = n;
     F.v = reinterpret_cast<uint16_t *>(b + o_v);
     F.abs0 = opt.abs0;
-    if (opt.ctx > 0) CU_TRY(cudaMemsetAsync(F.v, 0, static_cast<size_t>(opt.ctx) * sizeof(uint16_t), st));
-    {
+    int rc = ACGPU_OK;
+    if (opt.ctx > 0 && cudaMemsetAsync(F.v, 0, static_cast<size_t>(opt.ctx) * sizeof(uint16_t), st) != cudaSuccess) rc = fail(ACGPU_ECUDA, "memset failed");
+    if (rc == ACGPU_OK) {
         const int64_t ft = (n + kFwTile - 1) / kFwTile;
         const int grid = static_cast<int>(std::min<int64_t>(ft, persistent));
         if (A.family == ACGPU_LONGEST)
@@ -1090,58 +1226,33 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
             k_fwd_v<4><<<grid, kThreads, 0, st>>>(A, F);
         else
             k_fwd_v<3><<<grid, kThreads, 0, st>>>(A, F);
-        CU_TRY(cudaGetLastError());
+        if (cudaGetLastError() != cudaSuccess) rc = fail(ACGPU_ECUDA, "k_fwd_v failed to launch");
     }
-
-    SelArgs P{};
-    P.v = F.v;
-    P.n_v = n;
-    P.n = chain_n;
-    P.M = M;
-    P.halo = std::max(0, A.max_len - 1);
-    P.dom_lo = opt.ctx;
-    P.mode = A.family == ACGPU_LONGEST ? kModeLongest
-             : (A.family == ACGPU_SHORTEST ? kModeShortest
-                                           : (A.family == ACGPU_WHOLEWORDLONGEST ? kModeWholeWordLongest : kModeWholeWord));
-    P.n_tiles = n_tiles;
-    P.n_groups = n_groups;
-    P.entry0 = opt.entry0;
-    P.carry_out = reinterpret_cast<long long *>(opt.d_carry);
-    if (opt.d_carry) CU_TRY(cudaMemsetAsync(opt.d_carry, 0xFF, 8, st));  // -1 = chain did not cross chain_n
-    P.hay = d_hay;
-    P.n_hay = n;
-    P.pos_base = opt.pos_base;
-    P.pos_out = d_pos;
-    P.val_out = d_val;
-    P.cap = cap;
-    P.total_out = d_total;
-    P.tile_counter = reinterpret_cast<unsigned int *>(b + o_ctr);
-    P.status = reinterpret_cast<unsigned long long *>(b + o_status);
-    if (chain) {
-        P.exit1 = reinterpret_cast<uint16_t *>(b + o_exit1);
-        P.exit2 = reinterpret_cast<uint16_t *>(b + o_exit2);
-        P.entry2 = reinterpret_cast<int64_t *>(b + o_entry2);
-        P.entry1 = reinterpret_cast<int32_t *>(b + o_entry1);
-        const int grid_map = static_cast<int>(std::min<int64_t>(n_tiles, m->sm_count * 4));
-        k_sel_map<<<grid_map, kThreads, 0, st>>>(P);
-        CU_TRY(cudaGetLastError());
-        k_sel_group<<<static_cast<unsigned>(n_groups), kThreads, 0, st>>>(P);
-        CU_TRY(cudaGetLastError());
-        k_sel_top<<<1, 32, 0, st>>>(P);
-        CU_TRY(cudaGetLastError());
-        k_sel_entries<<<static_cast<unsigned>((n_groups + 127) / 128), 128, 0, st>>>(P);
-        CU_TRY(cudaGetLastError());
+    if (rc == ACGPU_OK) {
+        SelArgs P{};
+        P.v = F.v;
+        P.n_v = n;
+        P.n = chain_n;
+        P.M = A.max_len + (A.family == ACGPU_WHOLEWORDLONGEST ? 2 : 1);  // exit offsets are < M
+        P.halo = std::max(0, A.max_len - 1);
+        P.dom_lo = opt.ctx;
+        P.mode = A.family == ACGPU_LONGEST ? kModeLongest
+                 : (A.family == ACGPU_SHORTEST ? kModeShortest
+                                               : (A.family == ACGPU_WHOLEWORDLONGEST ? kModeWholeWordLongest : kModeWholeWord));
+        P.entry0 = opt.entry0;
+        P.carry_out = reinterpret_cast<long long *>(opt.d_carry);
+        P.hay = d_hay;
+        P.n_hay = n;
+        P.pos_base = opt.pos_base;
+        P.pos_out = d_pos;
+        P.val_out = d_val;
+        P.cap = cap;
+        P.total_out = d_total;
+        (void)n_tiles;
+        rc = enqueue_selection(m, P, chain, st);
     }
-    {
-        const int grid = static_cast<int>(std::min<int64_t>(n_tiles, m->sm_count * 4));
-        if (A.is_map)
-            k_sel_emit<true><<<grid, kThreads, kSelEmitSmem, st>>>(A, P);
-        else
-            k_sel_emit<false><<<grid, kThreads, kSelEmitSmem, st>>>(A, P);
-        CU_TRY(cudaGetLastError());
-    }
-    CU_TRY(cudaFreeAsync(ws, st));
-    return ACGPU_OK;
+    cudaFreeAsync(ws, st);
+    return rc;
 }
 
 int ensure_device(Matcher *m) {
@@ -1643,6 +1754,7 @@ int finish_create(Matcher *m, int family, int device, uint64_t *handle) {
         if (m->d_ww_blob) cudaFree(m->d_ww_blob);
         if (m->d_wide_blob) cudaFree(m->d_wide_blob);
         if (m->d_wide_vals) cudaFree(m->d_wide_vals);
+        if (m->d_wwl_wcls) cudaFree(m->d_wwl_wcls);
         if (m->d_blob) cudaFree(m->d_blob);
         delete m;
         return rc;
@@ -1829,6 +1941,7 @@ int acgpu_destroy(uint64_t handle) {
     if (m->d_ww_blob) cudaFree(m->d_ww_blob);
     if (m->d_wide_blob) cudaFree(m->d_wide_blob);
     if (m->d_wide_vals) cudaFree(m->d_wide_vals);
+    if (m->d_wwl_wcls) cudaFree(m->d_wwl_wcls);
     m->magic = 0;
     delete m;
     return ACGPU_OK;

@@ -254,4 +254,141 @@ __global__ void __launch_bounds__(kWwThreads) k_ww_scan(const DevWw W, const WwA
     }
 }
 
+// ---------------------------------------------------------------- WholeWordLongest with phrases: compacted walk starts
+//
+// WholeWordLongestMatchSet.java:47-182 walks the trie from the first char of the input and from every word start, over
+// word AND non-word chars, until there is no transition (position idx), reports the longest keyword on the path that
+// is followed by a non-word char or the end, and goes on at the first word start after idx ("WholeWordLongest
+// as a chain").  Generation 1 ran that chain over EVERY haystack position (k_fwd_v<4> + k_sel_*: 34.6 ms per 10^9 chars
+// although only one position in six is a walk start).  k_wwl_starts finds the walk starts with k_ww_scan's bitmaps, walks
+// from each, and writes them COMPACTED and in order:
+//     wpos[i] = haystack position of walk start i
+//     v[i]    = reported length | (number of walk starts the chain moves on by) << 8     (1 + starts inside (wpos[i], idx])
+// so the selection kernels resolve the chain over n / 6 candidates in index space (SelArgs::wpos maps back).
+struct WwlArgs {
+    const uint16_t *hay;
+    int64_t n;
+    int64_t origin;         // first position of tile 0: <= 0 and hay + origin is 16-byte aligned
+    int64_t n_tiles;        // tiles cover [origin, n)
+    int32_t *wpos;          // [cap]
+    uint16_t *v;            // [cap]
+    int64_t cap;
+    unsigned long long *total_out;   // number of walk starts
+    unsigned int *tile_counter;
+    unsigned long long *status;
+};
+
+__global__ void __launch_bounds__(kWwThreads) k_wwl_starts(const DevAutomaton A, const DevWw W, const WwlArgs P) {
+    extern __shared__ __align__(16) uint16_t s_ww_dyn[];
+    uint16_t *s_c = s_ww_dyn;  // classes of [t0, t0 + kWwTile + 16 * n_halo)
+    __shared__ uint16_t s_tab[256];
+    __shared__ uint32_t s_wc[kWwTile / 32 + 18];  // word-char bits of the window
+    __shared__ uint32_t s_prev;
+    __shared__ uint16_t s_q[kWwQueue + 1];
+    __shared__ uint16_t s_v[kWwQueue + 1];
+    __shared__ uint32_t s_tmp[kWarps + 1];
+    __shared__ long long s_tile;
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_halo = (W.max_len + 1 + 15) / 16;  // <= 16
+    for (int i = tid; i < 256; i += kWwThreads) s_tab[i] = __ldg(&W.wcls[i]);
+    if (tid < 10) s_wc[kWwTile / 32 + 8 + tid] = 0u;
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_tile = (long long)atomicAdd(P.tile_counter, 1u);
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= P.n_tiles) break;
+        const int64_t t0 = P.origin + tile * kWwTile;
+        // ---- A: classes and word-char bits of the tile and its halo (k_ww_scan's phase A)
+        {
+            uint32_t bits = ww_classify16(W, P.hay, P.n, t0 + tid * 16, s_tab, s_c + tid * 16);
+            uint32_t other = __shfl_down_sync(0xFFFFFFFFu, bits, 1);
+            if (!(lane & 1)) s_wc[tid >> 1] = (bits & 0xFFFFu) | (other << 16);
+            bits = 0;
+            if (tid < n_halo) bits = ww_classify16(W, P.hay, P.n, t0 + kWwTile + tid * 16, s_tab, s_c + kWwTile + tid * 16);
+            if (warp == 0) {
+                other = __shfl_down_sync(0xFFFFFFFFu, bits, 1);
+                if (!(lane & 1) && lane < 16) s_wc[kWwTile / 32 + (lane >> 1)] = (bits & 0xFFFFu) | (other << 16);
+            }
+            if (tid == kWwThreads - 1) {
+                const int64_t p = t0 - 1;
+                uint32_t w = 0;
+                if (p >= 0 && p < P.n) {
+                    const uint32_t ch = __ldg(&P.hay[p]);
+                    w = ch < 256u ? (uint32_t)s_tab[ch] : (uint32_t)__ldg(&W.wcls[ch]);
+                }
+                s_prev = w >> 15;
+            }
+        }
+        __syncthreads();
+        // ---- B: walk starts of the thread's 16 positions (word starts, and the first char of the input), in order
+        uint32_t starts;
+        {
+            const uint32_t word = s_wc[tid >> 1];
+            const uint32_t mine = (tid & 1) ? word >> 16 : word & 0xFFFFu;
+            const uint32_t prev = (tid & 1) ? (word >> 15) & 1u : (tid ? s_wc[(tid >> 1) - 1] >> 31 : s_prev);
+            starts = mine & ~((mine << 1) | prev) & 0xFFFFu;
+            const int64_t p0 = t0 + tid * 16;
+            if (p0 <= 0 && p0 + 16 > 0) starts |= 1u << (int)(-p0);                       // position 0 always starts a walk
+            if (p0 < 0) starts &= -p0 >= 16 ? 0u : (0xFFFFu << (int)(-p0));
+            if (p0 + 16 > P.n) starts &= P.n <= p0 ? 0u : (0xFFFFu >> (int)(p0 + 16 - P.n));
+        }
+        uint32_t nq;
+        uint32_t qoff = block_exclusive_sum(__popc(starts), s_tmp, nq);
+        while (starts) {
+            const int j = __ffs(starts) - 1;
+            starts &= starts - 1u;
+            s_q[qoff++] = (uint16_t)(tid * 16 + j);
+        }
+        __syncthreads();
+        // ---- C: one walk per thread
+        const int win = kWwTile + 16 * n_halo;  // positions of the window
+        for (uint32_t q = tid; q < nq; q += kWwThreads) {
+            const int p = s_q[q];
+            uint32_t node = 0, info = 0, len = 0;
+            int i = p;
+            while (t0 + i < P.n) {
+                const uint32_t c = i < win ? (uint32_t)s_c[i] : (uint32_t)__ldg(&A.cls[__ldg(&P.hay[t0 + i])]);
+                if ((A.has_other && c == 0u) || !trie_step(A, node, c, info)) break;
+                ++i;
+                if (info & kTerm) {
+                    const bool word_next = t0 + i < P.n && (i < win ? ((s_wc[i >> 5] >> (i & 31)) & 1u) != 0u
+                                                                     : (__ldg(&W.wcls[__ldg(&P.hay[t0 + i])]) >> 15) != 0u);
+                    if (!word_next) len = (uint32_t)(i - p);
+                }
+                if (!(info & kKids)) break;
+            }
+            // walk starts inside (p, i]: word-start bits of those positions, 32 at a time (i - p <= max_len: inside the window)
+            uint32_t skipped = 0;
+            for (int at = p + 1; at <= i; at += 32) {
+                const uint32_t x = ww_bits32(s_wc, (uint32_t)at), xp = ww_bits32(s_wc, (uint32_t)(at - 1));
+                uint32_t st = x & ~xp;
+                const int left = i - at + 1;  // positions at .. i
+                if (left < 32) st &= (1u << left) - 1u;
+                skipped += (uint32_t)__popc(st);
+            }
+            s_v[q] = (uint16_t)(len | (1u + skipped) << 8);
+        }
+        __syncthreads();
+        // ---- D: the tile's walk starts go out in order
+        if (warp == 0) {
+            const unsigned long long excl = lookback_exclusive(P.status, tile, nq);
+            if (lane == 0) {
+                s_base = excl;
+                if (tile == P.n_tiles - 1) *P.total_out = excl + nq;
+            }
+        }
+        __syncthreads();
+        const unsigned long long base = s_base;
+        for (uint32_t q = tid; q < nq; q += kWwThreads) {
+            if (base + q < (unsigned long long)P.cap) {
+                P.wpos[base + q] = (int32_t)(t0 + s_q[q]);
+                P.v[base + q] = s_v[q];
+            }
+        }
+    }
+}
+
 }  // namespace acgpu

@@ -303,6 +303,7 @@ struct SelArgs {
     int64_t *entry2;     // [n_groups] absolute entry position of each group, -1 = skipped
     int32_t *entry1;     // [n_tiles] entry offset inside each tile, -1 = skipped
     int64_t entry0;      // chain position at the start (0 for a fresh haystack)
+    const int32_t *wpos; // WholeWordLongest over COMPACTED walk starts (k_wwl_starts): chain position i stands for haystack position wpos[i]; nullptr: the chain runs over haystack positions
     long long *carry_out;  // [0] first chain position >= n (left untouched when the chain never crosses n)
     // emission
     const uint16_t *hay;
@@ -575,7 +576,7 @@ __global__ void __launch_bounds__(kThreads) k_sel_emit(const DevAutomaton A, con
         for (int k = 0; k < kSelPer; k++) {
             if (!mk[k]) continue;
             const int p = p0 + k;
-            const int64_t st = tile_start + s_st[p];
+            const int64_t st = P.wpos ? (int64_t)__ldg(&P.wpos[tile_start + s_st[p]]) : tile_start + s_st[p];
             const int64_t en = (P.mode == kModeWholeWord) ? st + s_v[p]
                                : (P.mode == kModeWholeWordLongest ? st + (s_v[s_st[p]] & 0xFFu) : tile_start + s_nxt[p]);
             if (idx < (unsigned long long)P.cap) {
