@@ -545,11 +545,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
             bool closed = true;
             for (uint32_t c = 0; c < 65536 && closed; c++) closed = wc[c] == wc[lower[c]];
             if (!closed) {
-                if (family != 3)
-                    throw std::domain_error(
-                        "case-insensitive WholeWordLongest matcher with a word-character table that is not closed under "
-                        "Character.toLowerCase is not implemented on the GPU path (reference quirk Q7)");
-                // WholeWord: the reference's loop is followed literally (kernel_wwlit.cuh); it needs both views of the table
+                // the reference's loop is followed literally (kernel_wwlit.cuh); it needs both views of the table
                 a.ww_literal = true;
                 a.wordbits_fold.assign(2048, 0);
                 for (uint32_t c = 0; c < 65536; c++) {
@@ -667,8 +663,8 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
     // WholeWordLongest with a dictionary whose (trimmed) keywords hold no non-word char: a walk can never leave its word
     // (there is no transition on a non-word char) and a keyword followed by a non-word char is the whole word, so the
     // family coincides with WholeWord and takes its hash path.
-    if ((family == 3 && !a.ww_literal) || (family == 4 && a.ww_plain)) build_ww(a, wc, node_parent, node_cls);
-    if (family == 4 && !a.ww_plain && a.has_other && a.n_classes < 32768 && a.max_len <= kWwMaxLen - 1) {
+    if (!a.ww_literal && (family == 3 || (family == 4 && a.ww_plain))) build_ww(a, wc, node_parent, node_cls);
+    if (family == 4 && !a.ww_plain && !a.ww_literal && a.has_other && a.n_classes < 32768 && a.max_len <= kWwMaxLen - 1) {
         a.wwl_wcls.resize(65536);
         for (uint32_t c = 0; c < 65536; c++) a.wwl_wcls[c] = static_cast<uint16_t>(a.cls[c] | (wc[c] ? 0x8000u : 0u));
     }

@@ -105,6 +105,10 @@ struct Matcher {
     bool use_ww = false;
     DevWw ww{};
     void *d_ww_blob = nullptr;
+    // >= 0: the reference's loop is followed literally, one thread per synchronisation point (kernel_wwlit.cuh::k_segments):
+    // 0 = WholeWord with quirk Q7, 1 / 2 = Longest / Shortest with keywords the selection kernels cannot hold (> 2 047 chars),
+    // 4 = WholeWordLongest with keywords > 254 chars or quirk Q7
+    int literal_family = -1;
 };
 
 Matcher *as_matcher(uint64_t h) {
@@ -935,12 +939,19 @@ int enqueue_ww_literal(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos
     P.val_out = d_val;
     P.cap = cap;
     const int grid = static_cast<int>(std::min<int64_t>(n_rows, static_cast<int64_t>(m->sm_count) * 8));
+    auto launch = [&](auto write) {
+        constexpr bool kWrite = decltype(write)::value;
+        const bool is_map = m->dev.is_map != 0;
+        switch (m->literal_family) {
+        case 0: is_map ? k_segments<0, kWrite, true><<<grid, kMaskRow, 0, st>>>(m->dev, P) : k_segments<0, kWrite, false><<<grid, kMaskRow, 0, st>>>(m->dev, P); break;
+        case 1: is_map ? k_segments<1, kWrite, true><<<grid, kMaskRow, 0, st>>>(m->dev, P) : k_segments<1, kWrite, false><<<grid, kMaskRow, 0, st>>>(m->dev, P); break;
+        case 2: is_map ? k_segments<2, kWrite, true><<<grid, kMaskRow, 0, st>>>(m->dev, P) : k_segments<2, kWrite, false><<<grid, kMaskRow, 0, st>>>(m->dev, P); break;
+        default: is_map ? k_segments<4, kWrite, true><<<grid, kMaskRow, 0, st>>>(m->dev, P) : k_segments<4, kWrite, false><<<grid, kMaskRow, 0, st>>>(m->dev, P); break;
+        }
+    };
     if (rc == ACGPU_OK) {
-        if (m->dev.is_map)
-            k_ww_literal<false, true><<<grid, kMaskRow, 0, st>>>(m->dev, P);
-        else
-            k_ww_literal<false, false><<<grid, kMaskRow, 0, st>>>(m->dev, P);
-        launch_ok("k_ww_literal (count)");
+        launch(std::false_type{});
+        launch_ok("k_segments (count)");
     }
     if (rc == ACGPU_OK) {
         ScanArgs SA{};
@@ -953,11 +964,8 @@ int enqueue_ww_literal(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos
         launch_ok("k_row_scan");
     }
     if (rc == ACGPU_OK && cap > 0) {
-        if (m->dev.is_map)
-            k_ww_literal<true, true><<<grid, kMaskRow, 0, st>>>(m->dev, P);
-        else
-            k_ww_literal<true, false><<<grid, kMaskRow, 0, st>>>(m->dev, P);
-        launch_ok("k_ww_literal (write)");
+        launch(std::true_type{});
+        launch_ok("k_segments (write)");
     }
     cudaFreeAsync(ws, st);
     return rc;
@@ -1152,8 +1160,8 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
         CU_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
         return ACGPU_OK;
     }
-    if (m->host.ww_literal) {
-        if (opt.ctx != 0 || chain_n != n) return fail(ACGPU_EINVAL, "literal WholeWord matchers scan whole haystacks");
+    if (m->literal_family >= 0) {
+        if (opt.ctx != 0 || chain_n != n) return fail(ACGPU_EINVAL, "literal matchers scan whole haystacks");
         return enqueue_ww_literal(m, d_hay, n, d_pos, d_val, cap, d_total, st, opt);
     }
     const bool chain = A.family != ACGPU_WHOLEWORD && !(A.family == ACGPU_WHOLEWORDLONGEST && m->use_ww);
@@ -1716,14 +1724,14 @@ namespace {
 
 // device half of a constructor: m->host is flattened, bring the tables to `device`
 int finish_create(Matcher *m, int family, int device, uint64_t *handle) {
-    if ((family == ACGPU_LONGEST || family == ACGPU_SHORTEST) && m->host.max_len + 1 > kSelMaxLen) {
-        delete m;
-        return fail(ACGPU_EUNSUPPORTED, "Longest/Shortest selection kernels support keywords up to 2047 chars");
-    }
-    if (family == ACGPU_WHOLEWORDLONGEST && m->host.max_len > 254) {
-        delete m;
-        return fail(ACGPU_EUNSUPPORTED, "WholeWordLongest keywords longer than 254 chars are not supported");
-    }
+    // keywords the selection kernels cannot hold (one exit entry per possible keyword length in shared memory; 16-bit walk
+    // records for WholeWordLongest) and quirk Q7: the literal loops of kernel_wwlit.cuh
+    if (m->host.ww_literal)
+        m->literal_family = family == ACGPU_WHOLEWORD ? 0 : 4;
+    else if ((family == ACGPU_LONGEST || family == ACGPU_SHORTEST) && m->host.max_len + 1 > kSelMaxLen)
+        m->literal_family = family == ACGPU_LONGEST ? 1 : 2;
+    else if (family == ACGPU_WHOLEWORDLONGEST && m->host.max_len > 254)
+        m->literal_family = 4;
     if (m->host.max_len > 65535) {
         delete m;
         return fail(ACGPU_EUNSUPPORTED, "keywords longer than 65535 chars are not supported");
@@ -1970,9 +1978,10 @@ int acgpu_char_classes(uint64_t handle, uint16_t *out65536, int32_t *has_other) 
 int acgpu_launches_per_match(uint64_t handle) {
     Matcher *m = as_matcher(handle);
     if (!m) return fail(ACGPU_EINVAL, "bad handle");
+    if (m->literal_family >= 0) return 3;  // count, scan, write
     switch (m->host.family) {
     case ACGPU_AHOCORASICK: return m->use_tier ? 3 : (m->use_wide ? (m->wide_tile ? 4 : 3) : 1);  // wide, generation 2: tile, tail, scan, emit
-    case ACGPU_WHOLEWORD: return m->host.ww_literal ? 3 : (m->use_ww ? 1 : 2);
+    case ACGPU_WHOLEWORD: return m->use_ww ? 1 : 2;
     default: return m->use_tier && m->host.is_map ? 7 : 6;  // one-shot tier path: mask, map, group, top, tiles, emit (+ values)  // one-shot matches; the streaming path always takes the 6-launch route
     }
 }
@@ -2640,7 +2649,7 @@ int acgpu_stream_begin(uint64_t handle, uint64_t *stream_handle) {
     StreamCtx *s = new (std::nothrow) StreamCtx();
     if (!s) return fail(ACGPU_ENOMEM, "out of memory");
     s->m = m;
-    if (m->host.ww_literal) {
+    if (m->literal_family >= 0) {
         s->literal = true;
         *stream_handle = static_cast<uint64_t>(reinterpret_cast<uintptr_t>(s));
         return ACGPU_OK;

@@ -1,4 +1,4 @@
-// k_ww_literal: WholeWordMatchSet / Map for the one input class where "maximal runs of word chars" is not the reference's
+// k_segments<0> (the former k_ww_literal): WholeWordMatchSet / Map for the one input class where "maximal runs of word chars" is not the reference's
 // behaviour - a case-insensitive matcher whose word-character table is not closed under Character.toLowerCase (quirk Q7).
 //
 // The reference's loop (WholeWordMatchSet.java:47-132; Map :155-240, Readable :55-153 + scroll :325-339):
@@ -40,9 +40,10 @@ __device__ __forceinline__ bool bit_of(const uint32_t *bits, uint32_t c) { retur
 struct WwLitView {
     const DevAutomaton &A;
     const WwLitArgs &P;
-    __device__ __forceinline__ bool word_fold(int64_t i) const { return bit_of(A.wordbits_fold, __ldg(&P.hay[i])); }
+    // wordbits_fold is only there when the two views differ
+    __device__ __forceinline__ bool word_fold(int64_t i) const { return bit_of(A.wordbits_fold ? A.wordbits_fold : A.wordbits, __ldg(&P.hay[i])); }
     __device__ __forceinline__ bool word_scroll(int64_t i) const {
-        return bit_of(P.scroll_folded ? A.wordbits_fold : A.wordbits, __ldg(&P.hay[i]));
+        return bit_of(P.scroll_folded && A.wordbits_fold ? A.wordbits_fold : A.wordbits, __ldg(&P.hay[i]));
     }
     __device__ __forceinline__ uint32_t cls(int64_t i) const { return __ldg(&A.cls[__ldg(&P.hay[i])]); }
     // a walk starts at t in every execution of the loop
@@ -98,16 +99,155 @@ __device__ __forceinline__ uint32_t wwlit_segment(const WwLitView &V, int64_t s,
     return count;
 }
 
+// ---------------------------------------------------------------- literal loops for keywords the selection kernels cannot hold
+//
+// The generation-1 selection kernels keep one exit entry per possible keyword length in shared memory (Longest / Shortest:
+// keywords up to 2 047 chars) and pack a walk into 16 bits (WholeWordLongest: up to 254 chars).  Longer keywords - legal
+// for the reference, absurd in practice - take the same segment scheme as above: a char that occurs in no keyword sends
+// every one of these automata back to its root (LongestMatchSet.java:227 flushes the queue there, a Shortest walk ends, a
+// WholeWordLongest walk fails), so the position after it starts an independent chain; one thread per such position follows
+// the chain (SURVEY A.2 / A.3 / DESIGN "WholeWordLongest as a chain") with its own trie walks, to the next such position.
+
+// longest (kFirst = false) or first = shortest (kFirst = true) keyword that starts at s: its length, 0 if none
+template <bool kFirst>
+__device__ __forceinline__ int64_t seg_walk(const DevAutomaton &A, const WwLitArgs &P, int64_t s, uint32_t &node_out) {
+    uint32_t node = 0, info = 0;
+    int64_t best = 0;
+    for (int64_t i = s; i < P.n;) {
+        const uint32_t c = __ldg(&A.cls[__ldg(&P.hay[i])]);
+        if ((A.has_other && c == 0u) || !trie_step(A, node, c, info)) break;
+        ++i;
+        if (info & kTerm) {
+            best = i - s;
+            node_out = node;
+            if (kFirst) break;
+        }
+        if (!(info & kKids)) break;
+    }
+    return best;
+}
+
+struct SegReport {
+    const DevAutomaton &A;
+    const WwLitArgs &P;
+    unsigned long long first;
+    uint32_t count;
+    template <bool kWrite, bool kIsMap>
+    __device__ __forceinline__ void put(int64_t from, int64_t to, uint32_t node) {
+        if (kWrite) {
+            const unsigned long long at = first + count;
+            if (at < (unsigned long long)P.cap) {
+                P.pos_out[at] = make_int2((int32_t)from + P.pos_base, (int32_t)to + P.pos_base);
+                if (kIsMap) P.val_out[at] = __ldg(&A.node_value[node]);
+            }
+        }
+        ++count;
+    }
+};
+
+// kFamily: 0 = the literal WholeWord loop above, ACGPU-style 1 Longest, 2 Shortest, 4 WholeWordLongest
+template <int kFamily>
+__device__ __forceinline__ bool seg_start(const WwLitView &V, int64_t t) {
+    if (kFamily == 0) return V.sync_start(t);
+    if (t == 0) return true;
+    if (!V.A.has_other || V.cls(t - 1) != 0u) return false;
+    if (kFamily == 4) return !V.word_scroll(t - 1) && !V.word_fold(t - 1) && V.word_scroll(t);
+    return true;
+}
+
+template <int kFamily, bool kWrite, bool kIsMap>
+__device__ __forceinline__ uint32_t seg_run(const WwLitView &V, int64_t t, unsigned long long first) {
+    if (kFamily == 0) return wwlit_segment<kWrite, kIsMap>(V, t, first);
+    const DevAutomaton &A = V.A;
+    const WwLitArgs &P = V.P;
+    SegReport R{A, P, first, 0u};
+    if (kFamily == 1) {
+        // Longest (A.2): from chain position p the first start with a keyword wins with its longest keyword; the chain goes on behind it
+        int64_t s = t;
+        while (s < P.n) {
+            if (A.has_other && V.cls(s) == 0u) return R.count;  // the next segment starts behind this char
+            uint32_t node = 0;
+            const int64_t L = seg_walk<false>(A, P, s, node);
+            if (L) {
+                R.put<kWrite, kIsMap>(s, s + L, node);
+                s += L;
+            } else {
+                ++s;
+            }
+        }
+        return R.count;
+    }
+    if (kFamily == 2) {
+        // Shortest (A.3): among the starts >= p the keyword that ENDS first wins (leftmost start on ties); the chain goes on at its end
+        int64_t p = t;
+        while (p < P.n) {
+            int64_t best_end = P.n + 1, best_start = 0;
+            uint32_t best_node = 0;
+            for (int64_t s = p; s < best_end && s < P.n; ++s) {
+                if (A.has_other && V.cls(s) == 0u) {
+                    if (best_end > P.n) return R.count;  // nothing pending: the next segment starts behind this char
+                    break;
+                }
+                uint32_t node = 0;
+                const int64_t L = seg_walk<true>(A, P, s, node);
+                if (L && s + L < best_end) {
+                    best_end = s + L;
+                    best_start = s;
+                    best_node = node;
+                }
+            }
+            if (best_end > P.n) return R.count;
+            R.put<kWrite, kIsMap>(best_start, best_end, best_node);
+            p = best_end;
+        }
+        return R.count;
+    }
+    // WholeWordLongest (WholeWordLongestMatchSet.java:47-182): walk from a walk start until there is no transition (idx);
+    // report the longest keyword on the path that is followed by a non-word char or the end; scroll to the next word start.
+    // "Followed by a non-word char" is decided on the LOWER-CASED char (the node's own match: :62-66 tests the folded char
+    // at idx; a fail match: :224-240 tests the trie key, which is folded), the scrolls test the raw char in the String
+    // overloads and the folded one in the Readable overload (Map :401-414) - the two views differ only for case-insensitive
+    // matchers whose word-char table is not closed under toLowerCase (quirk Q7).
+    auto word = [&](int64_t i) { return V.word_scroll(i); };
+    int64_t idx = t;
+    while (idx < P.n) {
+        const int64_t s = idx;
+        uint32_t node = 0, info = 0, rep_node = 0;
+        int64_t len = 0;
+        while (idx < P.n) {
+            const uint32_t c = V.cls(idx);
+            if ((A.has_other && c == 0u) || !trie_step(A, node, c, info)) break;
+            ++idx;
+            if ((info & kTerm) && (idx == P.n || !V.word_fold(idx))) {
+                len = idx - s;
+                rep_node = node;
+            }
+            if (!(info & kKids)) break;
+        }
+        if (len) R.put<kWrite, kIsMap>(s, s + len, rep_node);
+        if (idx >= P.n) break;
+        // idx: the first position without a transition (a leaf has none for any char)
+        if (V.word_fold(idx)) {
+            while (++idx < P.n && word(idx)) {
+            }
+        }
+        while (++idx < P.n && !word(idx)) {
+        }
+        if (idx < P.n && seg_start<4>(V, idx)) return R.count;
+    }
+    return R.count;
+}
+
 // kWrite = false: row_count[row] = records of the segments starting in the row.  kWrite = true: the records.
-template <bool kWrite, bool kIsMap>
-__global__ void __launch_bounds__(kMaskRow) k_ww_literal(const DevAutomaton A, const WwLitArgs P) {
+template <int kFamily, bool kWrite, bool kIsMap>
+__global__ void __launch_bounds__(kMaskRow) k_segments(const DevAutomaton A, const WwLitArgs P) {
     __shared__ uint32_t s_warp[kMaskRow / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const WwLitView V{A, P};
     for (int64_t row = blockIdx.x; row < P.n_rows; row += gridDim.x) {
         const int64_t t = row * kMaskRow + tid;
-        const bool start = t < P.n && V.sync_start(t);
-        const uint32_t cnt = start ? wwlit_segment<false, kIsMap>(V, t, 0ull) : 0u;
+        const bool start = t < P.n && seg_start<kFamily>(V, t);
+        const uint32_t cnt = start ? seg_run<kFamily, false, kIsMap>(V, t, 0ull) : 0u;
         uint32_t inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -128,7 +268,7 @@ __global__ void __launch_bounds__(kMaskRow) k_ww_literal(const DevAutomaton A, c
             if (tid == 0) P.row_count[row] = total;
         } else if (cnt) {
             const unsigned long long first = __ldg(P.block_excl + (row >> 12)) + __ldg(P.row_excl + row) + before + (inc - cnt);
-            wwlit_segment<true, kIsMap>(V, t, first);
+            seg_run<kFamily, true, kIsMap>(V, t, first);
         }
     }
     static_assert(kScanRows == 4096, "row >> 12 is the scan block of a row");

@@ -196,6 +196,71 @@ def test_wholeword_case_insensitive_tables_not_closed_under_lowercase(seed):
         assert [v[0] for v in c.calls] == [int(r["value"]) for r in om.match(hay, readable=True)], (closed, len(hay))
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_wholewordlongest_case_insensitive_tables_not_closed_under_lowercase(seed):
+    """Quirk Q7 for the fifth family (WholeWordLongestMatchSet.java:47-182, Map :183-310, Readable :54-181 with the scroll
+    of :401-414): "followed by a non-word char" is decided on the lower-cased char, the scrolls on the raw char (String)
+    or the lower-cased one (Readable).  k_segments<4> follows the loop literally."""
+    rng = random.Random(8800 + seed)
+    letters = "abcdeABCDE"
+    if seed % 2 == 0:
+        chars = [c for c in letters + "-_1" if rng.random() < 0.6] or ["A"]
+        args, table = (chars,), ora.word_chars(1, chars, [])
+    else:
+        chars = [c for c in letters if rng.random() < 0.4] or ["a"]
+        toggles = [False] * len(chars)
+        args, table = (chars, toggles), ora.word_chars(2, chars, toggles)
+    alphabet = letters + "-_1 "
+    kws = sorted({"".join(rng.choice(alphabet) for _ in range(rng.randint(1, 7))).strip() for _ in range(60)} - {""})
+    values = list(range(len(kws)))
+    om = ora.Matcher("wholewordlongest", kws, n_values=len(kws), case_sensitive=False, word_chars_table=table)
+    gs = ac.WholeWordLongestMatchSet(kws, False, *args)
+    gm = ac.WholeWordLongestMatchMap(kws, values, False, *args)
+    hays = ["", "a", "A b", "".join(rng.choice(letters) for _ in range(3000))]
+    for n, sep in ((50, " "), (700, " .,;"), (5000, " "), (70_001, " -_,")):
+        hays.append("".join(rng.choice(sep) if rng.random() < 0.25 else rng.choice(letters + "1") for _ in range(n)))
+    for hay in hays:
+        want = oracle_stream(om, hay)
+        assert gpu_set_stream(gs, hay) == [(s, e) for s, e, _ in want], len(hay)
+        assert gpu_map_stream(gm, hay) == want, len(hay)
+        c = Collect()
+        gm.match(io.StringIO(hay), c)
+        assert [v[0] for v in c.calls] == [int(r["value"]) for r in om.match(hay, readable=True)], len(hay)
+
+
+@pytest.mark.parametrize("family,long_len", [("longest", 2048), ("longest", 5000), ("shortest", 2048), ("shortest", 3001),
+                                             ("wholewordlongest", 255), ("wholewordlongest", 4000)])
+def test_keywords_longer_than_the_selection_kernels_hold(family, long_len):
+    """The reference takes keywords of any length (LongestMatchSet.java:20-190 has no limit).  Dictionaries whose longest
+    keyword exceeds what the selection kernels keep in shared memory (2 046 chars; 254 for WholeWordLongest) run the
+    reference's loop one thread per synchronisation point (k_segments): same ordered stream as the oracle, String and
+    Readable overloads, early stop."""
+    rng = random.Random(long_len)
+    sigma = "abc"
+    longs = ["".join(rng.choice(sigma) for _ in range(long_len)), "ab" * (long_len // 2 - 3)]
+    if family == "wholewordlongest":
+        longs.append(("abc " * long_len)[:long_len - 1].strip())
+    kws = sorted({_rand_word(rng, sigma, 1, 6) for _ in range(40)} | set(longs))
+    values = list(range(len(kws)))
+    om = ora.Matcher(family, kws, n_values=len(kws))
+    gs, gm = SETS[family](kws, True), MAPS[family](kws, values, True)
+    from ahocorasick_b200 import _lib
+    assert _lib.lib().acgpu_launches_per_match(gm.handle) == 3   # count, scan, write of k_segments
+    body = "".join(rng.choice(sigma + "  .") for _ in range(40_000))
+    hays = ["", longs[0], longs[0][:-1], longs[1] + "ab", body + " " + longs[0] + " " + body[:500] + longs[1] + "." + longs[-1] + " x",
+            "".join(rng.choice(sigma) for _ in range(20_000)) + longs[0] * 2]   # the last one: no synchronisation point
+    for hay in hays:
+        want = oracle_stream(om, hay)
+        assert gpu_set_stream(gs, hay) == [(s, e) for s, e, _ in want], len(hay)
+        assert gpu_map_stream(gm, hay) == want, len(hay)
+        c = Collect()
+        gm.match(io.StringIO(hay), c)
+        assert [v[0] for v in c.calls] == [int(r["value"]) for r in om.match(hay, readable=True)], len(hay)
+    want = oracle_stream(om, hays[4])
+    assert len(want) > 100
+    assert gpu_map_stream(gm, hays[4], stop_after=7) == oracle_stream(om, hays[4], stop_after=7)
+
+
 @pytest.mark.parametrize("gen1", [False, True])
 @pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4])
 def test_baseline_configs_scaled(cfg, gen1, monkeypatch):
