@@ -13,7 +13,7 @@ EXTRA = os.environ.get("ACGPU_NVCC_EXTRA", "").split()
 LIB = os.environ.get("ACGPU_LIB_OUT") or os.path.join(HERE, "libacgpu.so")
 SOURCES = ["engine.cu", "builder.cpp"]
 TIER_KS = range(1, 9)  # tier_inst.cu is compiled once per K (-DTIER_K=k), in parallel
-HEADERS = ["kernels.cuh", "kernel_tier.cuh", "kernel_mask.cuh", "kernel_pair.cuh", "kernel_emit.cuh", "kernel_fuse.cuh", "kernel_wide.cuh", "kernel_sel2.cuh", "kernel_ww.cuh", "kernel_wwlit.cuh", "tier_launch.hpp", "tier_inst.cu", "device_tables.cuh", "builder.hpp", "trie_insert.hpp",
+HEADERS = ["kernels.cuh", "kernel_tier.cuh", "kernel_mask.cuh", "kernel_pair.cuh", "kernel_emit.cuh", "kernel_fuse.cuh", "kernel_wide.cuh", "kernel_sel2.cuh", "kernel_ww.cuh", "kernel_ww3.cuh", "kernel_wwlit.cuh", "tier_launch.hpp", "tier_inst.cu", "device_tables.cuh", "builder.hpp", "trie_insert.hpp",
            "java_char_tables.h", os.path.join("..", "..", "include", "acgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall"]

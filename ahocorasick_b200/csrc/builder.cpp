@@ -475,25 +475,51 @@ void build_ww(HostAutomaton &a, const std::vector<uint8_t> &wc, const std::vecto
     if (nb > 0x7FFFFFFFull) return;
     w.n_buckets = static_cast<uint32_t>(nb);
     w.buckets.assign(nb * 8, 0xFFFFFFFFu);
+    {
+        const char *gen = std::getenv("ACGPU_WW_GEN");  // ACGPU_WW_GEN=2: the generation-2 kernel and its hash (A/B runs)
+        w.poly = !(gen && gen[0] == '2');
+    }
+    if (w.poly && n_keys > 0 && n_keys <= 400000) {
+        uint64_t bits = 4096;
+        while (bits < n_keys * 8 && bits < 512 * 1024) bits <<= 1;
+        w.bloom_bits = static_cast<uint32_t>(bits);
+        w.bloom.assign(bits / 32, 0u);
+    }
     std::vector<uint16_t> tmp;
     for (int64_t id = 1; id < a.n_nodes; id++) {
         if (!(a.node_info[id] & kInfoTerminal)) continue;
         tmp.clear();
         for (uint32_t cur = static_cast<uint32_t>(id); cur != 0; cur = node_parent[cur]) tmp.push_back(node_cls[cur]);
         std::reverse(tmp.begin(), tmp.end());
-        WwHash h;
-        for (size_t i = 0; i < tmp.size(); i += 2)
-            h.add_pair(static_cast<uint32_t>(tmp[i]) | (i + 1 < tmp.size() ? static_cast<uint32_t>(tmp[i + 1]) << 16 : 0u));
-        h.finish(static_cast<uint32_t>(tmp.size()));
+        uint32_t tag, spread;
+        if (w.poly) {
+            uint32_t poly = 0;
+            for (uint16_t c : tmp) poly = poly * kWwPolyB + ww_poly_digit(c);
+            tag = ww_poly_key(poly, static_cast<uint32_t>(tmp.size()));
+            spread = ww_poly_spread(tag);
+            if (w.bloom_bits) {
+                int lb = 0;
+                while ((1u << lb) < w.bloom_bits) lb++;
+                const uint32_t bit = tag >> (32 - lb);
+                w.bloom[bit >> 5] |= 1u << (bit & 31);
+            }
+        } else {
+            WwHash h;
+            for (size_t i = 0; i < tmp.size(); i += 2)
+                h.add_pair(static_cast<uint32_t>(tmp[i]) | (i + 1 < tmp.size() ? static_cast<uint32_t>(tmp[i + 1]) << 16 : 0u));
+            h.finish(static_cast<uint32_t>(tmp.size()));
+            tag = h.h1;
+            spread = h.spread();
+        }
         if (w.pool.size() + tmp.size() > 0xFFFFFFF0ull) return;
         const uint32_t off = static_cast<uint32_t>(w.pool.size());
         w.pool.insert(w.pool.end(), tmp.begin(), tmp.end());
-        uint32_t bk = static_cast<uint32_t>((static_cast<uint64_t>(h.spread()) * nb) >> 32);
+        uint32_t bk = static_cast<uint32_t>((static_cast<uint64_t>(spread) * nb) >> 32);
         while (true) {
             uint32_t *e = &w.buckets[static_cast<size_t>(bk) * 8];
             const int k = e[2] == 0xFFFFFFFFu ? 0 : (e[6] == 0xFFFFFFFFu ? 1 : -1);
             if (k >= 0) {
-                e[4 * k] = h.h1;
+                e[4 * k] = tag;
                 e[4 * k + 1] = static_cast<uint32_t>(tmp.size());
                 e[4 * k + 2] = off;
                 e[4 * k + 3] = a.node_value[id];
@@ -706,7 +732,7 @@ uint64_t automaton_fingerprint(const HostAutomaton &a) {
     if (a.wide_ok) { num(a.wide_ok); vec(a.wide_pair); vec(a.wide_chain); vec(a.wide_pair16); vec(a.wide_vals); num(a.wide_n_vbuckets); }
     if (a.ww_literal) { num(a.ww_literal); vec(a.wordbits_fold); }
     vec(a.wwl_wcls);
-    num(a.ww.ok); vec(a.ww.wcls); vec(a.ww.buckets); num(a.ww.n_buckets); vec(a.ww.pool);
+    num(a.ww.ok); vec(a.ww.wcls); vec(a.ww.buckets); num(a.ww.n_buckets); vec(a.ww.pool); num(a.ww.poly); vec(a.ww.bloom);
     return h;
 }
 

@@ -122,7 +122,33 @@ struct WwTables {
     std::vector<uint32_t> buckets;
     uint32_t n_buckets = 0;
     std::vector<uint16_t> pool;
+    // generation 3 (kernel_ww3.cuh): the table is keyed by ww_poly_key, and a one-hash Bloom filter over the keys (a power of
+    // two of bits, at most 64 KB, 0 = none: it lives in shared memory and only pays for dictionaries it can separate)
+    bool poly = false;
+    std::vector<uint32_t> bloom;
+    uint32_t bloom_bits = 0;
 };
+
+// Generation-3 hash of a word (kernel_ww3.cuh): a polynomial in B over x = (class + 1) | 1 << 31 of its chars, mod 2^32 -
+//     poly(c_0 .. c_{L-1}) = sum x_j * B^(L-1-j)
+// so that with running prefix values G over the haystack (G[i] = G[i-1] * B + x[i], x = 0 for non-word chars) the hash of
+// the run [s, t) is G[t-1] - G[s-1] * B^(t-s): no per-word loop on the device.  ww_poly_key mixes the length in; the
+// Bloom filter takes the key's HIGH bits (the best mixed ones), the bucket another multiplicative mix.
+constexpr uint32_t kWwPolyB = 0x9E3779B1u;
+inline constexpr uint32_t ww_poly_digit(uint32_t cls) { return (cls + 1u) | 0x80000000u; }
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t ww_poly_key(uint32_t poly, uint32_t len) {
+    uint32_t k = (poly ^ (len * 0x27D4EB2Fu)) * 0x85EBCA6Bu;
+    k ^= k >> 15;
+    k *= 0xC2B2AE35u;
+    return k;
+}
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t ww_poly_spread(uint32_t key) { return (key ^ (key >> 16)) * 0x2C1B3C6Du; }
 
 // hash of a class string, shared by the builder and k_ww_scan: FNV-1a over PAIRS of classes (c[2i] | c[2i+1] << 16, a
 // lone last class with a zero upper half), murmur-style finish

@@ -22,6 +22,7 @@
 #include "kernel_mask.cuh"
 #include "kernel_emit.cuh"
 #include "kernel_fuse.cuh"
+#include "kernel_ww3.cuh"
 #include "kernel_sel2.cuh"
 #include "kernel_ww.cuh"
 #include "kernel_wide.cuh"
@@ -103,6 +104,7 @@ struct Matcher {
     uint16_t *d_wwl_wcls = nullptr;
     // WholeWord hash tables (kernel_ww.cuh)
     bool use_ww = false;
+    bool use_ww3 = false;     // generation 3 (kernel_ww3.cuh: hits, row scan, emit) instead of k_ww_scan
     DevWw ww{};
     void *d_ww_blob = nullptr;
     // >= 0: the reference's loop is followed literally, one thread per synchronisation point (kernel_wwlit.cuh::k_segments):
@@ -354,6 +356,7 @@ int upload_ww(Matcher *m) {
     const size_t o_wcls = reserve(65536 * 2);
     const size_t o_bk = reserve(t.buckets.size() * 4);
     const size_t o_pool = reserve(t.pool.size() * 2);
+    const size_t o_bloom = reserve(t.bloom.size() * 4);
     CU_TRY(cudaMalloc(&m->d_ww_blob, off));
     m->table_bytes += static_cast<int64_t>(off);
     char *b = static_cast<char *>(m->d_ww_blob);
@@ -365,6 +368,20 @@ int upload_ww(Matcher *m) {
     m->ww.pool = reinterpret_cast<const uint16_t *>(b + o_pool);
     m->ww.n_buckets = t.n_buckets;
     m->ww.max_len = m->host.max_len;
+    m->ww.bloom = nullptr;
+    m->ww.bloom_bits = 0;
+    m->use_ww3 = t.poly;
+    if (t.poly) {
+        if (!t.bloom.empty()) {
+            CU_TRY(cudaMemcpy(b + o_bloom, t.bloom.data(), t.bloom.size() * 4, cudaMemcpyHostToDevice));
+            m->ww.bloom = reinterpret_cast<const uint32_t *>(b + o_bloom);
+            m->ww.bloom_bits = t.bloom_bits;
+        }
+        CU_TRY(cudaFuncSetAttribute(k_ww3_hits<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ww3_smem_bytes(512 * 1024)));
+        CU_TRY(cudaFuncSetAttribute(k_ww3_hits<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ww3_smem_bytes(512 * 1024)));
+        CU_TRY(cudaFuncSetAttribute(k_ww3_hits<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ww3_smem_bytes(0)));
+        CU_TRY(cudaFuncSetAttribute(k_ww3_hits<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ww3_smem_bytes(0)));
+    }
     m->use_ww = true;
     return ACGPU_OK;
 }
@@ -907,6 +924,82 @@ int enqueue_wide(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from
     return rc;
 }
 
+// WholeWord, generation 3 (kernel_ww3.cuh): hit bits + row counts by atomics on zeroed scratch, row scan, records
+int enqueue_ww3(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t dom_lo, int64_t dom_hi, int64_t origin, int2 *d_pos, uint32_t *d_val,
+                int64_t cap, unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
+    const int64_t last = std::min<int64_t>(n, dom_hi + m->ww.max_len);   // the last position a reported run can end at (exclusive end)
+    const int64_t n_rows = (last - origin) / kW3Row + 1;
+    const int64_t n_blocks = (n_rows + kScanRows - 1) / kScanRows;
+    Scratch S;
+    const size_t o_ctr = S.reserve(256);
+    const size_t o_cnt = S.reserve(static_cast<size_t>(n_rows) * 4);
+    const size_t o_bits = S.reserve(static_cast<size_t>(n_rows) * 32);
+    const size_t zeroed = S.off;
+    const size_t o_blk = S.reserve(static_cast<size_t>(n_blocks) * 8);
+    void *ws = nullptr;
+    CU_TRY(cudaMallocAsync(&ws, S.off, st));
+    char *w = static_cast<char *>(ws);
+    int rc = ACGPU_OK;
+    auto launch_ok = [&](const char *what) {
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && rc == ACGPU_OK) rc = fail(ACGPU_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    };
+    if (cudaMemsetAsync(w, 0, zeroed, st) != cudaSuccess) rc = fail(ACGPU_ECUDA, "memset failed");
+    if (rc == ACGPU_OK) {
+        Ww3Args P{};
+        P.hay = d_hay;
+        P.n = n;
+        P.dom_lo = dom_lo;
+        P.dom_hi = dom_hi;
+        P.origin = origin;
+        P.n_rows = n_rows;
+        P.hitbits = reinterpret_cast<uint32_t *>(w + o_bits);
+        P.row_count = reinterpret_cast<uint32_t *>(w + o_cnt);
+        P.ticket = reinterpret_cast<unsigned int *>(w + o_ctr);
+        const int64_t n_chunks = (n_rows + kW3ChunkRows - 1) / kW3ChunkRows;
+        const int grid = static_cast<int>(std::min<int64_t>((n_chunks + kW3Warps - 1) / kW3Warps, m->sm_count));
+        const bool shortk = m->ww.max_len < 32;
+        const size_t smem = ww3_smem_bytes(m->ww.bloom_bits);
+        if (m->ww.bloom_bits)
+            shortk ? k_ww3_hits<true, true><<<grid, kW3Warps * 32, smem, st>>>(m->ww, P) : k_ww3_hits<true, false><<<grid, kW3Warps * 32, smem, st>>>(m->ww, P);
+        else
+            shortk ? k_ww3_hits<false, true><<<grid, kW3Warps * 32, smem, st>>>(m->ww, P) : k_ww3_hits<false, false><<<grid, kW3Warps * 32, smem, st>>>(m->ww, P);
+        launch_ok("k_ww3_hits");
+    }
+    if (rc == ACGPU_OK) {
+        ScanArgs SA{};
+        SA.row_count = reinterpret_cast<uint32_t *>(w + o_cnt);
+        SA.block_excl = reinterpret_cast<unsigned long long *>(w + o_blk);
+        SA.done = reinterpret_cast<unsigned int *>(w + o_ctr + 64);
+        SA.total_out = d_total;
+        SA.n_rows = n_rows;
+        k_row_scan<<<static_cast<unsigned>(n_blocks), 1024, 0, st>>>(SA);
+        launch_ok("k_row_scan");
+    }
+    if (rc == ACGPU_OK && cap > 0) {
+        Ww3EmitArgs E{};
+        E.hay = d_hay;
+        E.n = n;
+        E.origin = origin;
+        E.n_rows = n_rows;
+        E.hitbits = reinterpret_cast<const uint32_t *>(w + o_bits);
+        E.row_excl = reinterpret_cast<const uint32_t *>(w + o_cnt);
+        E.block_excl = reinterpret_cast<const unsigned long long *>(w + o_blk);
+        E.pos_base = opt.pos_base;
+        E.pos_out = d_pos;
+        E.val_out = d_val;
+        E.cap = cap;
+        const int grid = static_cast<int>(std::min<int64_t>((n_rows + 255) / 256, static_cast<int64_t>(m->sm_count) * 8));
+        if (m->dev.is_map)
+            k_ww3_emit<true><<<grid, 256, 0, st>>>(m->ww, E);
+        else
+            k_ww3_emit<false><<<grid, 256, 0, st>>>(m->ww, E);
+        launch_ok("k_ww3_emit");
+    }
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
 // WholeWord, case-insensitive with a word-character table that is not closed under toLowerCase (quirk Q7): the reference's
 // loop, literally, one thread per synchronisation point (kernel_wwlit.cuh): count, scan, write
 int enqueue_ww_literal(Matcher *m, const uint16_t *d_hay, int64_t n, int2 *d_pos, uint32_t *d_val, int64_t cap, unsigned long long *d_total,
@@ -1175,6 +1268,7 @@ int enqueue_match(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
             CU_TRY(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
             return ACGPU_OK;
         }
+        if (m->use_ww3) return enqueue_ww3(m, d_hay, n, dom_lo, dom_hi, origin, d_pos, d_val, cap, d_total, st, opt);
         const size_t bytes = 256 + static_cast<size_t>(n_tiles) * 8;
         void *ws = nullptr;
         CU_TRY(cudaMallocAsync(&ws, bytes, st));
@@ -1981,7 +2075,7 @@ int acgpu_launches_per_match(uint64_t handle) {
     if (m->literal_family >= 0) return 3;  // count, scan, write
     switch (m->host.family) {
     case ACGPU_AHOCORASICK: return m->use_tier ? 3 : (m->use_wide ? (m->wide_tile ? 4 : 3) : 1);  // wide, generation 2: tile, tail, scan, emit
-    case ACGPU_WHOLEWORD: return m->use_ww ? 1 : 2;
+    case ACGPU_WHOLEWORD: return m->use_ww ? (m->use_ww3 ? 3 : 1) : 2;
     default: return m->use_tier && m->host.is_map ? 7 : 6;  // one-shot tier path: mask, map, group, top, tiles, emit (+ values)  // one-shot matches; the streaming path always takes the 6-launch route
     }
 }

@@ -28,6 +28,8 @@ struct DevWw {
     const uint16_t *pool;
     uint32_t n_buckets;
     int32_t max_len;
+    const uint32_t *bloom;    // generation 3 (kernel_ww3.cuh): one-hash Bloom filter over the keys, bloom_bits = 0: none
+    uint32_t bloom_bits;
 };
 
 struct WwArgs {
