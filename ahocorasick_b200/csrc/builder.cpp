@@ -471,17 +471,20 @@ void build_ww(HostAutomaton &a, const std::vector<uint8_t> &wc, const std::vecto
     for (uint32_t c = 0; c < 65536; c++) w.wcls[c] = static_cast<uint16_t>(a.cls[c] | (wc[c] ? 0x8000u : 0u));
     uint64_t n_keys = 0;
     for (int64_t id = 1; id < a.n_nodes; id++) n_keys += a.node_info[id] & kInfoTerminal;
-    const uint64_t nb = std::max<uint64_t>(4, n_keys * 2);  // two entries per bucket: load factor 0.25 (most probes are misses)
-    if (nb > 0x7FFFFFFFull) return;
-    w.n_buckets = static_cast<uint32_t>(nb);
-    w.buckets.assign(nb * 8, 0xFFFFFFFFu);
     {
         const char *gen = std::getenv("ACGPU_WW_GEN");  // ACGPU_WW_GEN=2: the generation-2 kernel and its hash (A/B runs)
         w.poly = !(gen && gen[0] == '2');
     }
+    // two entries per bucket: load factor 0.25 (most probes are misses); generation 3 probes 32 keys in lockstep, so one
+    // long probe path stalls a whole batch: 0.125
+    const uint64_t nb = std::max<uint64_t>(4, n_keys * (w.poly ? 4 : 2));
+    if (nb > 0x7FFFFFFFull) return;
+    w.n_buckets = static_cast<uint32_t>(nb);
+    w.buckets.assign(nb * 8, 0xFFFFFFFFu);
     if (w.poly && n_keys > 0 && n_keys <= 400000) {
         uint64_t bits = 4096;
-        while (bits < n_keys * 8 && bits < 512 * 1024) bits <<= 1;
+        // 64 KB at most; 32 KB when keywords of 32 chars or more need the two-row ring (kernel_ww3.cuh: the CTA stays under the 164 KB carve-out)
+        while (bits < n_keys * 8 && bits < (a.max_len < 32 ? 512 : 256) * 1024) bits <<= 1;
         w.bloom_bits = static_cast<uint32_t>(bits);
         w.bloom.assign(bits / 32, 0u);
     }

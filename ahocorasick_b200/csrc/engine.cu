@@ -377,10 +377,10 @@ int upload_ww(Matcher *m) {
             m->ww.bloom = reinterpret_cast<const uint32_t *>(b + o_bloom);
             m->ww.bloom_bits = t.bloom_bits;
         }
-        CU_TRY(cudaFuncSetAttribute(k_ww3_hits<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ww3_smem_bytes(512 * 1024)));
-        CU_TRY(cudaFuncSetAttribute(k_ww3_hits<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ww3_smem_bytes(512 * 1024)));
-        CU_TRY(cudaFuncSetAttribute(k_ww3_hits<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ww3_smem_bytes(0)));
-        CU_TRY(cudaFuncSetAttribute(k_ww3_hits<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ww3_smem_bytes(0)));
+        CU_TRY(cudaFuncSetAttribute(k_ww3_hits<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ww3_smem_bytes(512 * 1024, true)));
+        CU_TRY(cudaFuncSetAttribute(k_ww3_hits<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ww3_smem_bytes(512 * 1024, false)));
+        CU_TRY(cudaFuncSetAttribute(k_ww3_hits<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ww3_smem_bytes(0, true)));
+        CU_TRY(cudaFuncSetAttribute(k_ww3_hits<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ww3_smem_bytes(0, false)));
     }
     m->use_ww = true;
     return ACGPU_OK;
@@ -959,7 +959,7 @@ int enqueue_ww3(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t dom_lo, in
         const int64_t n_chunks = (n_rows + kW3ChunkRows - 1) / kW3ChunkRows;
         const int grid = static_cast<int>(std::min<int64_t>((n_chunks + kW3Warps - 1) / kW3Warps, m->sm_count));
         const bool shortk = m->ww.max_len < 32;
-        const size_t smem = ww3_smem_bytes(m->ww.bloom_bits);
+        const size_t smem = ww3_smem_bytes(m->ww.bloom_bits, shortk);
         if (m->ww.bloom_bits)
             shortk ? k_ww3_hits<true, true><<<grid, kW3Warps * 32, smem, st>>>(m->ww, P) : k_ww3_hits<true, false><<<grid, kW3Warps * 32, smem, st>>>(m->ww, P);
         else

@@ -28,7 +28,13 @@ namespace acgpu {
 constexpr int kW3Warps = 32;                 // one CTA per SM
 constexpr int kW3Row = kMaskRow;             // 256 positions: k_row_scan's rows
 constexpr int kW3ChunkRows = 32;
-constexpr int kW3WarpWords = 512 + 16 + 64 + 128 + 128;   // G ring, word-bit ring, end queue (128 x u16), probe and verify queues (64 x 8 bytes each)
+// shared memory per warp, in words.  kShort (keywords < 32 chars: a run and the char before it are at most 33 positions back):
+// G of the row + the previous row's last 64, word-char bits likewise, no index wraps.  Otherwise a two-row ring.  Then the end
+// queue (128 x u16) and the probe and verify queues (64 x 8 bytes each).  (With 64 KB of Bloom filter the kShort layout keeps
+// the CTA under the 164 KB carve-out; 182 KB - the two-row ring for every dictionary - left 28 KB of L1 and cost 5 %.)
+__host__ __device__ constexpr int w3_g_words(bool shortk) { return shortk ? 64 + 256 : 64 + 512; }
+__host__ __device__ constexpr int w3_wb_words(bool shortk) { return shortk ? 12 : 20; }
+__host__ __device__ constexpr int w3_warp_words(bool shortk) { return w3_g_words(shortk) + w3_wb_words(shortk) + 64 + 128 + 128; }
 static_assert(kW3Row == 256 && kWwMaxLen <= 255, "a run and the char before it fit the two-row ring; lengths fit 8 bits");
 
 __host__ __device__ constexpr uint32_t w3_pow(uint32_t b, int e) {
@@ -36,8 +42,8 @@ __host__ __device__ constexpr uint32_t w3_pow(uint32_t b, int e) {
     for (int i = 0; i < e; i++) r *= b;
     return r;
 }
-__host__ __device__ constexpr size_t ww3_smem_bytes(uint32_t bloom_bits) {
-    return (size_t)(256 + 256 + bloom_bits / 32 + kW3Warps * kW3WarpWords) * 4;
+__host__ __device__ constexpr size_t ww3_smem_bytes(uint32_t bloom_bits, bool shortk) {
+    return (size_t)(256 + 256 + bloom_bits / 32 + kW3Warps * w3_warp_words(shortk)) * 4;
 }
 
 struct Ww3Args {
@@ -141,12 +147,12 @@ __global__ void __launch_bounds__(kW3Warps * 32, 1) k_ww3_hits(const DevWw W, co
     uint32_t *s_pow = s_w3 + 256;                           // [256] B^len
     uint32_t *s_bloom = s_w3 + 512;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t *s_mine = s_bloom + (W.bloom_bits >> 5) + warp * kW3WarpWords;
-    uint32_t *s_G = s_mine;                                  // [2][256] running polynomial of the last two rows
-    uint32_t *s_wb = s_mine + 512;                           // [2][8] their word-char bits
-    uint16_t *s_q = reinterpret_cast<uint16_t *>(s_mine + 528);   // [128] run ends of the row, row-relative
-    W3Queue probe_q{reinterpret_cast<uint2 *>(s_mine + 592), 0u};    // [64] {key, (start - chunk context base) << 8 | length}
-    W3Queue verify_q{reinterpret_cast<uint2 *>(s_mine + 720), 0u};   // [64] the same entries after a tag match
+    uint32_t *s_mine = s_bloom + (W.bloom_bits >> 5) + warp * w3_warp_words(kShort);
+    uint32_t *s_G = s_mine;                                  // running polynomial: [64 + 256] (kShort) or a ring of two rows at [64, 64 + 512)
+    uint32_t *s_wb = s_mine + w3_g_words(kShort);            // word-char bits of the same positions
+    uint16_t *s_q = reinterpret_cast<uint16_t *>(s_wb + w3_wb_words(kShort));   // [128] run ends of the row, row-relative
+    W3Queue probe_q{reinterpret_cast<uint2 *>(s_wb + w3_wb_words(kShort) + 64), 0u};    // [64] {key, (start - chunk context base) << 8 | length}
+    W3Queue verify_q{reinterpret_cast<uint2 *>(s_wb + w3_wb_words(kShort) + 192), 0u};  // [64] the same entries after a tag match
     constexpr uint32_t B = kWwPolyB;
 
     if (tid < 256) {
@@ -268,23 +274,38 @@ __global__ void __launch_bounds__(kW3Warps * 32, 1) k_ww3_hits(const DevWw W, co
                 for (int j = 0; j < 8; j++) g[j] += carry * w3_pow(B, j + 1);
                 carry_row = __shfl_sync(0xFFFFFFFFu, g[7], 31);
             }
-            const uint32_t slot256 = (uint32_t)(ri & 1) * 256u;
+            // kShort: the row at s_G[64 ..), bit 64 + i of s_wb; otherwise ring index i (= position mod 512) at s_G[64 + i]
+            const uint32_t slot256 = kShort ? 0u : (uint32_t)(ri & 1) * 256u;
             {
-                uint4 *dst = reinterpret_cast<uint4 *>(s_G + slot256 + lane * 8);
+                uint4 *dst = reinterpret_cast<uint4 *>(s_G + 64 + slot256 + lane * 8);
                 dst[0] = make_uint4(g[0], g[1], g[2], g[3]);
                 dst[1] = make_uint4(g[4], g[5], g[6], g[7]);
-                reinterpret_cast<uint8_t *>(s_wb)[(slot256 >> 3) + lane] = (uint8_t)wb;
+                reinterpret_cast<uint8_t *>(s_wb)[8 + (slot256 >> 3) + lane] = (uint8_t)wb;
             }
             uint32_t before = __shfl_up_sync(0xFFFFFFFFu, wb >> 7, 1);
             if (lane == 0) before = prev_bit;
             prev_bit = __shfl_sync(0xFFFFFFFFu, wb >> 7, 31);
+            auto keep_tail = [&]() {   // kShort: the next row finds this row's last 64 positions below its own
+                if (kShort) {
+                    __syncwarp();
+                    if (lane >= 24) {
+                        const uint4 a = *reinterpret_cast<const uint4 *>(s_G + 64 + lane * 8), b = *reinterpret_cast<const uint4 *>(s_G + 68 + lane * 8);
+                        *reinterpret_cast<uint4 *>(s_G + (lane - 24) * 8) = a;
+                        *reinterpret_cast<uint4 *>(s_G + (lane - 24) * 8 + 4) = b;
+                        reinterpret_cast<uint8_t *>(s_wb)[lane - 24] = (uint8_t)wb;
+                    }
+                }
+                __syncwarp();   // the next row overwrites the row (the other half of the ring) and the end queue
+            };
             if (ri == 0) {   // the context row reports nothing
-                __syncwarp();
+                keep_tail();
                 continue;
             }
-            uint32_t ends = ~wb & ((wb << 1) | before) & 0xFFu;   // a non-word char after a word char: a run ends here (exclusive)
+            // run ends (a non-word char after a word char; exclusive end), chunk-relative, compacted in order
+            const uint32_t row_rel = (uint32_t)ri * kW3Row;
+            uint32_t ends = ~wb & ((wb << 1) | before) & 0xFFu;
             const uint32_t inc = warp_inclusive_sum((uint32_t)__popc(ends));
-            const uint32_t nq = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
             uint32_t off = inc - (uint32_t)__popc(ends);
             while (ends) {
                 const int j = __ffs(ends) - 1;
@@ -292,26 +313,33 @@ __global__ void __launch_bounds__(kW3Warps * 32, 1) k_ww3_hits(const DevWw W, co
                 s_q[off++] = (uint16_t)(lane * 8 + j);
             }
             __syncwarp();
-            const uint32_t row_rel = (uint32_t)ri * kW3Row;
-            for (uint32_t q0 = 0; q0 < nq; q0 += 32) {
+            // (Carrying the last partial batch over to the next row - an end may wait one row if its run lies in this row - was
+            // measured: 15 % fewer candidate rounds, but the bookkeeping cost more instructions than the rounds saved.)
+            const uint32_t now = total;
+            for (uint32_t q0 = 0; q0 < now; q0 += 32) {
                 bool pass = false;
                 uint32_t key = 0, packed = 0;
-                if (q0 + lane < nq) {
-                    const uint32_t tq = s_q[q0 + lane], rt = slot256 + tq;   // ring index of the run's end
+                if (q0 + lane < now) {
+                    const uint32_t tq = s_q[q0 + lane], t = row_rel + tq, rt = slot256 + tq;   // chunk-relative end of the run, its (ring) index
                     // word-char bits of the 32 positions before the end, most recent highest: the run's length
-                    uint32_t b0 = (rt - 32u) & 511u;
-                    uint32_t len = (uint32_t)__clz((int)~__funnelshift_r(s_wb[b0 >> 5], s_wb[((b0 >> 5) + 1u) & 15u], b0 & 31u));
-                    if (!kShort) {
+                    uint32_t len;
+                    if (kShort) {
+                        const uint32_t b0 = rt + 32u;
+                        len = (uint32_t)__clz((int)~__funnelshift_r(s_wb[b0 >> 5], s_wb[(b0 >> 5) + 1u], b0 & 31u));
+                    } else {
+                        uint32_t b0 = (rt - 32u) & 511u;
+                        len = (uint32_t)__clz((int)~__funnelshift_r(s_wb[2u + (b0 >> 5)], s_wb[2u + (((b0 >> 5) + 1u) & 15u)], b0 & 31u));
                         uint32_t run = len;
                         while (run == 32u && len <= max_len) {
                             b0 = (b0 - 32u) & 511u;
-                            run = (uint32_t)__clz((int)~__funnelshift_r(s_wb[b0 >> 5], s_wb[((b0 >> 5) + 1u) & 15u], b0 & 31u));
+                            run = (uint32_t)__clz((int)~__funnelshift_r(s_wb[2u + (b0 >> 5)], s_wb[2u + (((b0 >> 5) + 1u) & 15u)], b0 & 31u));
                             len += run;
                         }
                     }
-                    const int32_t s = (int32_t)(row_rel + tq - len);
+                    const int32_t s = (int32_t)(t - len);
                     if (len <= max_len && s >= dom_lo && s < dom_hi) {
-                        const uint32_t poly = s_G[(rt - 1u) & 511u] - s_G[(rt - len - 1u) & 511u] * s_pow[len];
+                        const uint32_t poly = kShort ? s_G[63u + rt] - s_G[63u + rt - len] * s_pow[len]
+                                                     : s_G[64u + ((rt - 1u) & 511u)] - s_G[64u + ((rt - len - 1u) & 511u)] * s_pow[len];
                         key = ww_poly_key(poly, len);
                         pass = !kBloom || ((s_bloom[key >> (bloom_shift + 5u)] >> ((key >> bloom_shift) & 31u)) & 1u);
                         packed = (uint32_t)s << 8 | len;
@@ -323,7 +351,7 @@ __global__ void __launch_bounds__(kW3Warps * 32, 1) k_ww3_hits(const DevWw W, co
                     probe_q.pop32(lane);
                 }
             }
-            __syncwarp();   // the next row overwrites the other half of the ring and the end queue
+            keep_tail();
         }
         probe(probe_q.n);
         probe_q.n = 0;
