@@ -104,7 +104,7 @@ __device__ __forceinline__ void classify8x4(const DevAutomaton &A, const uint16_
             const uint32_t ch[8] = {v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16,
                                     v.z & 0xFFFFu, v.z >> 16, v.w & 0xFFFFu, v.w >> 16};
 #pragma unroll
-            for (int j = 0; j < 8; j++) c4[j] = ch[j] < 256u ? (uint32_t)s_cls4[ch[j]] : (uint32_t)__ldg(&A.cls[ch[j]]) * (uint32_t)SCALE;
+            for (int j = 0; j < 8; j++) c4[j] = (uint32_t)__ldg(&A.cls[ch[j]]) * (uint32_t)SCALE;  // no test per char: the Latin-1 part of the table stays in L1 (a select between the two tables cost 17 instructions per char: 15 % of k_tier_emit<1> on configs[1])
         }
     } else {
 #pragma unroll

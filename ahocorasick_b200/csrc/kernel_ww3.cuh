@@ -27,7 +27,16 @@ namespace acgpu {
 
 constexpr int kW3Warps = 32;                 // one CTA per SM
 constexpr int kW3Row = kMaskRow;             // 256 positions: k_row_scan's rows
-constexpr int kW3ChunkRows = 32;
+#ifndef ACGPU_W3_CHUNK
+#define ACGPU_W3_CHUNK 64     // rows per ticket (32: +1 %: one context row per chunk)
+#endif
+#ifndef ACGPU_W3_SWZ
+#define ACGPU_W3_SWZ 0      // experiment, lost 2 %: spread the class table over the banks (upper / lower case and digits share banks in ASCII order)
+#endif
+#ifndef ACGPU_W3_STS
+#define ACGPU_W3_STS 1      // conflict-free order of the two 128-bit stores of G (+2.3 %)
+#endif
+constexpr int kW3ChunkRows = ACGPU_W3_CHUNK;
 // shared memory per warp, in words.  kShort (keywords < 32 chars: a run and the char before it are at most 33 positions back):
 // G of the row + the previous row's last 64, word-char bits likewise, no index wraps.  Otherwise a two-row ring.  Then the end
 // queue (128 x u16) and the probe and verify queues (64 x 8 bytes each).  (With 64 KB of Bloom filter the kShort layout keeps
@@ -75,8 +84,10 @@ struct Ww3EmitArgs {
 // x of a wcls entry (class | word-char flag << 15): a word char gives (class + 1) | 1 << 31, any other char 0 - the top bit is
 // the word-char bit (one funnel shift per char collects the bits) and the whole word is the polynomial's digit
 __device__ __forceinline__ uint32_t w3_enc(uint32_t x) { return (x >> 15) ? ((x & 0x7FFFu) + 1u) | 0x80000000u : 0u; }
+// slot of a Latin-1 code unit in the shared-memory table
+__device__ __forceinline__ uint32_t w3_slot(uint32_t ch) { return ACGPU_W3_SWZ ? ch ^ (ch >> 5) : ch; }
 __device__ __forceinline__ uint32_t w3_v(const DevWw &W, const uint32_t *s_tab, uint32_t ch) {
-    return ch < 256u ? s_tab[ch] : w3_enc(__ldg(&W.wcls[ch]));
+    return ch < 256u ? s_tab[w3_slot(ch)] : w3_enc(__ldg(&W.wcls[ch]));
 }
 __device__ __forceinline__ uint32_t w3_bucket(const DevWw &W, uint32_t key) { return __umulhi(ww_poly_spread(key), W.n_buckets); }
 
@@ -156,7 +167,7 @@ __global__ void __launch_bounds__(kW3Warps * 32, 1) k_ww3_hits(const DevWw W, co
     constexpr uint32_t B = kWwPolyB;
 
     if (tid < 256) {
-        s_tab[tid] = w3_enc(__ldg(&W.wcls[tid]));
+        s_tab[w3_slot(tid)] = w3_enc(__ldg(&W.wcls[tid]));
         uint32_t p = 1, b = B;
         for (int e = tid; e; e >>= 1, b *= b)
             if (e & 1) p *= b;
@@ -234,10 +245,10 @@ __global__ void __launch_bounds__(kW3Warps * 32, 1) k_ww3_hits(const DevWw W, co
             uint32_t v[8];
             if (inside) {
                 if (((cur.x | cur.y | cur.z | cur.w) & 0xFF00FF00u) == 0u) {
-                    v[0] = s_tab[cur.x & 0xFFu]; v[1] = s_tab[cur.x >> 16];
-                    v[2] = s_tab[cur.y & 0xFFu]; v[3] = s_tab[cur.y >> 16];
-                    v[4] = s_tab[cur.z & 0xFFu]; v[5] = s_tab[cur.z >> 16];
-                    v[6] = s_tab[cur.w & 0xFFu]; v[7] = s_tab[cur.w >> 16];
+                    v[0] = s_tab[w3_slot(cur.x & 0xFFu)]; v[1] = s_tab[w3_slot(cur.x >> 16)];
+                    v[2] = s_tab[w3_slot(cur.y & 0xFFu)]; v[3] = s_tab[w3_slot(cur.y >> 16)];
+                    v[4] = s_tab[w3_slot(cur.z & 0xFFu)]; v[5] = s_tab[w3_slot(cur.z >> 16)];
+                    v[6] = s_tab[w3_slot(cur.w & 0xFFu)]; v[7] = s_tab[w3_slot(cur.w >> 16)];
                 } else {
                     const uint32_t ch[8] = {cur.x & 0xFFFFu, cur.x >> 16, cur.y & 0xFFFFu, cur.y >> 16,
                                             cur.z & 0xFFFFu, cur.z >> 16, cur.w & 0xFFFFu, cur.w >> 16};
@@ -278,8 +289,17 @@ __global__ void __launch_bounds__(kW3Warps * 32, 1) k_ww3_hits(const DevWw W, co
             const uint32_t slot256 = kShort ? 0u : (uint32_t)(ri & 1) * 256u;
             {
                 uint4 *dst = reinterpret_cast<uint4 *>(s_G + 64 + slot256 + lane * 8);
-                dst[0] = make_uint4(g[0], g[1], g[2], g[3]);
-                dst[1] = make_uint4(g[4], g[5], g[6], g[7]);
+                if (ACGPU_W3_STS) {
+                    // a quarter warp's 8 stores of 16 bytes at a stride of 32 bytes hit every bank twice; lanes 4-7 of each
+                    // quarter store their other half first
+                    const bool hi_first = (lane & 4) != 0;
+                    const uint4 lo = make_uint4(g[0], g[1], g[2], g[3]), hi = make_uint4(g[4], g[5], g[6], g[7]);
+                    dst[hi_first ? 1 : 0] = hi_first ? hi : lo;
+                    dst[hi_first ? 0 : 1] = hi_first ? lo : hi;
+                } else {
+                    dst[0] = make_uint4(g[0], g[1], g[2], g[3]);
+                    dst[1] = make_uint4(g[4], g[5], g[6], g[7]);
+                }
                 reinterpret_cast<uint8_t *>(s_wb)[8 + (slot256 >> 3) + lane] = (uint8_t)wb;
             }
             uint32_t before = __shfl_up_sync(0xFFFFFFFFu, wb >> 7, 1);
@@ -370,7 +390,7 @@ __global__ void __launch_bounds__(256) k_ww3_emit(const DevWw W, const Ww3EmitAr
     __shared__ uint32_t s_bits[8][32 * 8 + 4];
     __shared__ uint32_t s_inc[8][32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    s_tab[tid] = w3_enc(__ldg(&W.wcls[tid]));
+    s_tab[w3_slot(tid)] = w3_enc(__ldg(&W.wcls[tid]));
     __syncthreads();
     const int64_t n_groups = (E.n_rows + 31) / 32;
     for (int64_t group = (int64_t)blockIdx.x * 8 + warp; group < n_groups; group += (int64_t)gridDim.x * 8) {
