@@ -2348,6 +2348,11 @@ struct StreamCtx {
     int64_t ctx = 0;      // leading context chars of the active window
     int64_t base = 0;     // absolute stream offset of window[0]
     int64_t chain = 0;    // absolute chain position (selection families)
+    // Longest / Shortest on the start-mask path (stream_process_chain): the window starts at the chain domain, the chain enters
+    // it at window position `entry` (< 16: an exit offset of the previous block's map)
+    bool chain_blocks = false;
+    int32_t entry = 0;
+    unsigned long long *d_map = nullptr;   // [16] composed map of the block (exit offset | matches << 8)
     int64_t *d_carry = nullptr;
     unsigned long long *d_total = nullptr;
     double density = 0.0;  // records per finalised char seen so far (max over feeds): sizes the next feed's record buffer
@@ -2393,6 +2398,7 @@ void stream_free(StreamCtx *s) {
     if (s->pend.d_pos) cudaFree(s->pend.d_pos);
     if (s->pend.d_val) cudaFree(s->pend.d_val);
     if (s->d_carry) cudaFree(s->d_carry);
+    if (s->d_map) cudaFree(s->d_map);
     if (s->d_total) cudaFree(s->d_total);
     if (s->h_total) cudaFreeHost(s->h_total);
     if (s->ev_up) cudaEventDestroy(s->ev_up);
@@ -2455,8 +2461,116 @@ int stream_append(StreamCtx *s, const uint16_t *chars, int64_t n) {
     return ACGPU_OK;
 }
 
+// Longest / Shortest feeds on the start-mask path (kernel_sel2.cuh): every feed is a CHAIN SHARD (acgpu_chain_shard_*:
+// the same kernels the multi-GPU shards use).  The window starts at the chain domain; a feed finalises whole tiles of it
+// (8 192 positions, with 2 * max_len + 2 chars of look-ahead behind them), its composed map tells the number of records and
+// the offset at which the chain enters the next block before a single record is written, the unfinalised tail moves to the
+// front of the other window.  The window is cut to a multiple of 256 chars so that its index space starts at a tile boundary
+// (every entry offset has a map row); the last block (end of the Readable) takes whatever is left.
+int stream_process_chain(StreamCtx *s, bool final, acgpu_result *out) {
+    Matcher *m = s->m;
+    fill_empty(out);
+    const int64_t avail = s->len;
+    if (avail == 0) return ACGPU_OK;
+    const int64_t D = 2 * static_cast<int64_t>(m->host.max_len) + 2;
+    int64_t n = avail, n_domain = avail;
+    if (!final) {
+        n = avail & ~static_cast<int64_t>(kMaskRow - 1);
+        n_domain = n > D ? (n - D) / kS2Tile * kS2Tile : 0;
+        if (n_domain <= 0) return ACGPU_OK;   // not a whole tile yet: wait for the next feed
+    }
+    const uint16_t *win = s->d_win[s->cur];
+    RunOpts opt;
+    opt.pos_base = static_cast<int32_t>(static_cast<uint32_t>(s->base));
+    Sel2Run R;
+    int rc = sel2_setup(m, win, n, final ? -1 : n_domain / kS2Tile, s->st, opt, R);
+    if (rc != ACGPU_OK) return rc;
+    rc = sel2_masks(R);
+    if (rc == ACGPU_OK) rc = sel2_maps(R);
+    unsigned long long total = 0;
+    int32_t exit_off = 0;
+    uint32_t entry0 = static_cast<uint32_t>(s->entry);
+    int64_t cap = 0;
+    cudaError_t e = cudaSuccess;
+    if (rc == ACGPU_OK && !final) {
+        // R.moff == 0 (n is a multiple of 256 and the window is 256-byte aligned): the map has a row for every entry offset
+        unsigned long long row = 0;
+        rc = sel2_shard_map(R, s->d_map, s->d_total);
+        if (rc == ACGPU_OK) e = cudaMemcpyAsync(&row, s->d_map + s->entry, 8, cudaMemcpyDeviceToHost, s->st);
+        if (rc == ACGPU_OK && e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+        s->dma_pending = false;
+        total = row >> 8;
+        exit_off = static_cast<int32_t>(row & 0xFFu);
+        cap = static_cast<int64_t>(total);
+    } else if (rc == ACGPU_OK) {
+        const int64_t idx = R.moff + s->entry;  // index-space position the chain enters at
+        if (idx < kS2Ent) {
+            entry0 = static_cast<uint32_t>(idx);
+        } else {
+            entry0 = 0;
+            k_sel2_zero_prefix<<<1, 256, 0, s->st>>>(R.P.masks, R.moff, idx);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) rc = sel2_maps(R, 1);
+        }
+        cap = n;   // non-overlapping matches: at most one per char
+    }
+    int2 *d_pos = nullptr;
+    uint32_t *d_val = nullptr;
+    if (rc == ACGPU_OK && e == cudaSuccess && cap > 0) {
+        e = cudaMallocAsync(reinterpret_cast<void **>(&d_pos), static_cast<size_t>(cap) * 8, s->st);
+        if (e == cudaSuccess && m->host.is_map) e = cudaMallocAsync(reinterpret_cast<void **>(&d_val), static_cast<size_t>(cap) * 4, s->st);
+        if (e == cudaSuccess) rc = sel2_records(R, entry0, d_pos, d_val, cap, s->d_total);
+        if (rc == ACGPU_OK && e == cudaSuccess && final) {
+            e = cudaMemcpyAsync(&total, s->d_total, 8, cudaMemcpyDeviceToHost, s->st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+            s->dma_pending = false;
+        }
+    }
+    if (rc == ACGPU_OK && e == cudaSuccess && total > 0) {
+        PinnedBlock blk;
+        const bool want_pos = !(s->values_only && m->host.is_map);
+        const size_t pos_bytes = want_pos ? align_up(static_cast<size_t>(total) * 8, 16) : 0;
+        if (!pin_take(pos_bytes + (m->host.is_map ? static_cast<size_t>(total) * 4 : 0), &blk)) {
+            rc = fail(ACGPU_ENOMEM, "out of pinned host memory for the match records");
+        } else {
+            int32_t *h_pos = want_pos ? static_cast<int32_t *>(blk.p) : nullptr;
+            uint32_t *h_val = m->host.is_map ? reinterpret_cast<uint32_t *>(static_cast<char *>(blk.p) + pos_bytes) : nullptr;
+            if (want_pos) e = cudaMemcpyAsync(h_pos, d_pos, static_cast<size_t>(total) * 8, cudaMemcpyDeviceToHost, s->st);
+            if (e == cudaSuccess && h_val) e = cudaMemcpyAsync(h_val, d_val, static_cast<size_t>(total) * 4, cudaMemcpyDeviceToHost, s->st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+            if (e != cudaSuccess) {
+                pin_release(blk.p);
+            } else {
+                out->n = static_cast<int64_t>(total);
+                out->pos = h_pos;
+                out->val = h_val;
+            }
+        }
+    }
+    if (d_pos) cudaFreeAsync(d_pos, s->st);
+    if (d_val) cudaFreeAsync(d_val, s->st);
+    sel2_free(R);
+    if (e != cudaSuccess && rc == ACGPU_OK) rc = fail(ACGPU_ECUDA, std::string("stream block: ") + cudaGetErrorString(e));
+    if (rc != ACGPU_OK) return rc;
+    // slide: the unfinalised tail moves to the front of the other window (256-byte aligned: the next block's index space)
+    const int64_t keep = avail - n_domain;
+    const int other = s->cur ^ 1;
+    rc = stream_reserve(s, other, std::max<int64_t>(keep, 1));
+    if (rc != ACGPU_OK) return rc;
+    if (keep > 0)
+        CU_TRY(cudaMemcpyAsync(s->d_win[other], s->d_win[s->cur] + n_domain, static_cast<size_t>(keep) * 2, cudaMemcpyDeviceToDevice, s->st));
+    s->cur = other;
+    s->base += n_domain;
+    s->len = keep;
+    s->ctx = 0;
+    s->entry = exit_off;
+    s->chain = s->base + exit_off;
+    return ACGPU_OK;
+}
+
 // scan what can be finalised, copy the records out, slide the window
 int stream_process(StreamCtx *s, bool final, acgpu_result *out) {
+    if (s->chain_blocks) return stream_process_chain(s, final, out);
     Matcher *m = s->m;
     const int family = m->host.family;
     const int64_t L = m->host.max_len;
@@ -2755,6 +2869,11 @@ int acgpu_stream_begin(uint64_t handle, uint64_t *stream_handle) {
     }
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s->d_carry), 16);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s->d_total), 8);
+    {
+        const char *gen = getenv("ACGPU_STREAM_CHAIN_GEN");  // ACGPU_STREAM_CHAIN_GEN=1: the generation-1 kernels per feed (A/B runs)
+        s->chain_blocks = (m->host.family == ACGPU_LONGEST || m->host.family == ACGPU_SHORTEST) && m->use_tier && !(gen && gen[0] == '1');
+        if (s->chain_blocks && e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s->d_map), kS2Ent * 8);
+    }
     {
         const int fam = m->host.family;
         const char *sync = getenv("ACGPU_STREAM_SYNC");

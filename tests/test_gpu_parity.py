@@ -330,6 +330,42 @@ def test_readable_streaming_blocks(family, block):
         assert [x[0] for x in c.calls] == w
 
 
+@pytest.mark.parametrize("family", ["longest", "shortest"])
+@pytest.mark.parametrize("block", [1000, 8192, 50_000, 1 << 18])
+def test_readable_streaming_chain_blocks(family, block, monkeypatch):
+    """Longest / Shortest match(Readable) on the start-mask path: every feed is a chain shard (whole 8 192-position tiles with
+    look-ahead, entry offset carried by the composed map).  The value stream - with ShortestMatchMap's fill-boundary duplicates
+    (Q4) - and the (start, end, value) records equal the oracle's for feeds smaller than, equal to and larger than a tile, on
+    text with and without separators, and equal what the generation-1 kernels deliver."""
+    from ahocorasick_b200.streaming import DeviceStream, match_readable
+    rng = random.Random(block + len(family))
+    kws = sorted({_rand_word(rng, "abcde", 1, 12) for _ in range(3000)})
+    values = list(range(len(kws)))
+    om = ora.Matcher(family, kws, n_values=len(kws))
+    gm, gs = MAPS[family](kws, values, True), SETS[family](kws, True)
+    for n, alphabet in ((0, "abcde "), (5, "abcde"), (70_000, "abcde  "), (300_001, "abcde")):
+        hay = "".join(rng.choice(alphabet) for _ in range(n))
+        want = [int(r["value"]) for r in om.match(hay, readable=True)]
+        got = []
+        match_readable(gm, io.StringIO(hay), lambda v: got.append(v) or True, block_chars=block)
+        assert got == want, (n, len(got), len(want))
+        # the records themselves, block by block
+        arr = np.frombuffer(hay.encode("utf-16-le"), dtype=np.uint16)
+        st = DeviceStream(gs)
+        recs = []
+        for at in range(0, arr.size, block):
+            r = st.feed(arr[at:at + block])
+            recs += list(zip(r.start.tolist(), r.end.tolist()))
+        r = st.end()
+        recs += list(zip(r.start.tolist(), r.end.tolist()))
+        assert recs == [(a, b) for a, b, _ in oracle_stream(om, hay, cap=max(1 << 16, n + 1))], n
+    if len(want) > 600:
+        for stop in (1, 7, 500):
+            got = []
+            match_readable(gm, io.StringIO(hay), lambda v: got.append(v) or len(got) < stop, block_chars=block)
+            assert got == [int(r["value"]) for r in om.match(hay, readable=True, stop_after=stop)]
+
+
 def test_readable_config3_wholeword_map():
     """configs[3]: WholeWordMatchMap with the toggle word-char constructor, streamed via Readable."""
     c = W.config(3, scale=0.02)

@@ -42,12 +42,16 @@ def run(lib, m, host, ne, sizes):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--chars", type=int, default=200_000_000)
+    ap.add_argument("--configs", default="3,1,2")
     a = ap.parse_args()
+    only = {int(x) for x in a.configs.split(",")}
     torch.cuda.set_device(0)
     lib = _lib.lib()
     for idx, name, make in ((3, "WholeWordMatchMap", lambda c, k, v: ac.WholeWordMatchMap(k, v, True, *c["word_chars"])),
                             (1, "AhoCorasickMap(ci)", lambda c, k, v: ac.AhoCorasickMap(k, v, False)),
                             (2, "LongestMatchMap", lambda c, k, v: ac.LongestMatchMap(k, v, True))):
+        if idx not in only:
+            continue
         cfg = W.config(idx)
         kws = cfg["keywords"]
         m = make(cfg, kws, list(range(len(kws))))
