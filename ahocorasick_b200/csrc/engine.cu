@@ -2353,6 +2353,16 @@ struct StreamCtx {
     bool chain_blocks = false;
     int32_t entry = 0;
     unsigned long long *d_map = nullptr;   // [16] composed map of the block (exit offset | matches << 8)
+    // pipelined chain-shard feeds: the block whose masks and maps are enqueued (entry-independent work) while the caller prepares
+    // the next feed; its records are cut when the next feed (or end) arrives
+    bool chain_pipe = false;
+    struct ChainPending {
+        bool live = false;
+        Sel2Run R;
+        int64_t n_domain = 0;
+    } cpend;
+    unsigned long long *h_map = nullptr;   // pinned [16]: the pending block's map
+    cudaEvent_t ev_begin = nullptr;
     int64_t *d_carry = nullptr;
     unsigned long long *d_total = nullptr;
     double density = 0.0;  // records per finalised char seen so far (max over feeds): sizes the next feed's record buffer
@@ -2398,7 +2408,10 @@ void stream_free(StreamCtx *s) {
     if (s->pend.d_pos) cudaFree(s->pend.d_pos);
     if (s->pend.d_val) cudaFree(s->pend.d_val);
     if (s->d_carry) cudaFree(s->d_carry);
+    if (s->cpend.live) sel2_free(s->cpend.R);
     if (s->d_map) cudaFree(s->d_map);
+    if (s->h_map) cudaFreeHost(s->h_map);
+    if (s->ev_begin) cudaEventDestroy(s->ev_begin);
     if (s->d_total) cudaFree(s->d_total);
     if (s->h_total) cudaFreeHost(s->h_total);
     if (s->ev_up) cudaEventDestroy(s->ev_up);
@@ -2436,7 +2449,7 @@ int stream_reserve(StreamCtx *s, int which, int64_t chars) {
 int stream_append(StreamCtx *s, const uint16_t *chars, int64_t n) {
     int rc = stream_reserve(s, s->cur, s->len + n);
     if (rc != ACGPU_OK) return rc;
-    cudaStream_t up = s->pipelined ? s->st_up : s->st;
+    cudaStream_t up = (s->pipelined || s->chain_pipe) ? s->st_up : s->st;
     cudaPointerAttributes attr{};
     if (cudaPointerGetAttributes(&attr, chars) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
         CU_TRY(cudaMemcpyAsync(s->d_win[s->cur] + s->len, chars, static_cast<size_t>(n) * 2, cudaMemcpyHostToDevice, up));
@@ -2812,6 +2825,91 @@ int stream_enqueue(StreamCtx *s, bool final) {
     return ACGPU_OK;
 }
 
+// ---- pipelined chain-shard feeds: begin(block k) = masks, maps and the composed map, enqueued without a host wait;
+//      finish(block k) = records for the entry offset block k-1 handed over, cut when feed k+1 arrives - so the upload of block
+//      k+1 (st_up) runs next to the record kernels and the download (st_dn) of block k.
+
+// the records of the pending block: kernels on st, download on st_dn; the caller waits for ev_dn (stream_chain_wait)
+int stream_chain_finish(StreamCtx *s, Collected &c) {
+    StreamCtx::ChainPending &b = s->cpend;
+    if (!b.live) return ACGPU_OK;
+    b.live = false;
+    Matcher *m = s->m;
+    int rc = ACGPU_OK;
+    cudaError_t e = cudaEventSynchronize(s->ev_begin);   // the map is in pinned memory
+    const unsigned long long row = s->h_map[s->entry];
+    const int64_t total = static_cast<int64_t>(row >> 8);
+    const int32_t exit_off = static_cast<int32_t>(row & 0xFFu);
+    if (e == cudaSuccess && total > 0) {
+        e = cudaMallocAsync(reinterpret_cast<void **>(&c.d_pos), static_cast<size_t>(total) * 8, s->st);
+        if (e == cudaSuccess && m->host.is_map) e = cudaMallocAsync(reinterpret_cast<void **>(&c.d_val), static_cast<size_t>(total) * 4, s->st);
+        if (e == cudaSuccess) rc = sel2_records(b.R, static_cast<uint32_t>(s->entry), c.d_pos, c.d_val, total, s->d_total);
+        if (e == cudaSuccess) e = cudaEventRecord(s->ev_scan, s->st);
+        const bool want_pos = !(s->values_only && m->host.is_map);
+        const size_t pos_bytes = want_pos ? align_up(static_cast<size_t>(total) * 8, 16) : 0;
+        if (rc == ACGPU_OK && e == cudaSuccess && !pin_take(pos_bytes + (m->host.is_map ? static_cast<size_t>(total) * 4 : 0), &c.blk))
+            rc = fail(ACGPU_ENOMEM, "out of pinned host memory for the match records");
+        if (rc == ACGPU_OK && e == cudaSuccess) {
+            c.h_pos = want_pos ? static_cast<int32_t *>(c.blk.p) : nullptr;
+            c.h_val = m->host.is_map ? reinterpret_cast<uint32_t *>(static_cast<char *>(c.blk.p) + pos_bytes) : nullptr;
+            e = cudaStreamWaitEvent(s->st_dn, s->ev_scan, 0);
+            if (e == cudaSuccess && c.h_pos) e = cudaMemcpyAsync(c.h_pos, c.d_pos, static_cast<size_t>(total) * 8, cudaMemcpyDeviceToHost, s->st_dn);
+            if (e == cudaSuccess && c.h_val) e = cudaMemcpyAsync(c.h_val, c.d_val, static_cast<size_t>(total) * 4, cudaMemcpyDeviceToHost, s->st_dn);
+        }
+    }
+    sel2_free(b.R);
+    if (e == cudaSuccess) e = cudaEventRecord(s->ev_dn, s->st_dn);
+    c.total = total;
+    c.live = true;
+    s->entry = exit_off;
+    s->chain = s->base + exit_off;   // s->base already stands at the end of the block's domain
+    if (e != cudaSuccess && rc == ACGPU_OK) rc = fail(ACGPU_ECUDA, std::string("stream block: ") + cudaGetErrorString(e));
+    return rc;
+}
+
+// masks, maps and the composed map of what the window can finalise (no host wait); slide the window
+int stream_chain_begin(StreamCtx *s) {
+    Matcher *m = s->m;
+    CU_TRY(cudaEventRecord(s->ev_up, s->st_up));
+    CU_TRY(cudaStreamWaitEvent(s->st, s->ev_up, 0));   // the block has landed before anything on st touches the window
+    const int64_t avail = s->len;
+    const int64_t D = 2 * static_cast<int64_t>(m->host.max_len) + 2;
+    const int64_t n = avail & ~static_cast<int64_t>(kMaskRow - 1);
+    const int64_t n_domain = n > D ? (n - D) / kS2Tile * kS2Tile : 0;
+    if (n_domain <= 0) return ACGPU_OK;   // not a whole tile yet
+    StreamCtx::ChainPending &b = s->cpend;
+    RunOpts opt;
+    opt.pos_base = static_cast<int32_t>(static_cast<uint32_t>(s->base));
+    b.R = Sel2Run();
+    int rc = sel2_setup(m, s->d_win[s->cur], n, n_domain / kS2Tile, s->st, opt, b.R);
+    if (rc != ACGPU_OK) return rc;
+    rc = sel2_masks(b.R);
+    if (rc == ACGPU_OK) rc = sel2_maps(b.R);
+    if (rc == ACGPU_OK) rc = sel2_shard_map(b.R, s->d_map, s->d_total);
+    cudaError_t e = cudaSuccess;
+    if (rc == ACGPU_OK) e = cudaMemcpyAsync(s->h_map, s->d_map, kS2Ent * 8, cudaMemcpyDeviceToHost, s->st);
+    if (rc == ACGPU_OK && e == cudaSuccess) e = cudaEventRecord(s->ev_begin, s->st);
+    if (rc != ACGPU_OK || e != cudaSuccess) {
+        sel2_free(b.R);
+        return rc != ACGPU_OK ? rc : fail(ACGPU_ECUDA, std::string("stream block: ") + cudaGetErrorString(e));
+    }
+    b.n_domain = n_domain;
+    b.live = true;
+    // slide: the unfinalised tail moves to the front of the other window; the scanned window stays intact until the block's
+    // records are cut (the next feed), and is written again only by the feed after that
+    const int64_t keep = avail - n_domain;
+    const int other = s->cur ^ 1;
+    rc = stream_reserve(s, other, std::max<int64_t>(keep, 1));
+    if (rc != ACGPU_OK) return rc;
+    if (keep > 0)
+        CU_TRY(cudaMemcpyAsync(s->d_win[other], s->d_win[s->cur] + n_domain, static_cast<size_t>(keep) * 2, cudaMemcpyDeviceToDevice, s->st));
+    s->cur = other;
+    s->base += n_domain;
+    s->len = keep;
+    s->ctx = 0;
+    return ACGPU_OK;
+}
+
 // two results -> one (end(): the pending block, then the final flush)
 int merge_results(acgpu_result *a, acgpu_result *b, bool is_map, acgpu_result *out) {
     if (a->n == 0) {
@@ -2873,6 +2971,12 @@ int acgpu_stream_begin(uint64_t handle, uint64_t *stream_handle) {
         const char *gen = getenv("ACGPU_STREAM_CHAIN_GEN");  // ACGPU_STREAM_CHAIN_GEN=1: the generation-1 kernels per feed (A/B runs)
         s->chain_blocks = (m->host.family == ACGPU_LONGEST || m->host.family == ACGPU_SHORTEST) && m->use_tier && !(gen && gen[0] == '1');
         if (s->chain_blocks && e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&s->d_map), kS2Ent * 8);
+        const char *sync = getenv("ACGPU_STREAM_SYNC");
+        s->chain_pipe = s->chain_blocks && !(sync && sync[0] == '1');
+        if (s->chain_pipe) {
+            if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&s->h_map), kS2Ent * 8, cudaHostAllocDefault);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_begin, cudaEventDisableTiming);
+        }
     }
     {
         const int fam = m->host.family;
@@ -2880,7 +2984,7 @@ int acgpu_stream_begin(uint64_t handle, uint64_t *stream_handle) {
         s->pipelined = (fam == ACGPU_AHOCORASICK || fam == ACGPU_WHOLEWORD || (fam == ACGPU_WHOLEWORDLONGEST && m->use_ww)) &&
                        !(sync && sync[0] == '1');
     }
-    if (s->pipelined) {
+    if (s->pipelined || s->chain_pipe) {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st_up, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st_dn, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_dn, cudaEventDisableTiming);
@@ -2920,6 +3024,20 @@ int acgpu_stream_feed(uint64_t stream_handle, const uint16_t *chars, int32_t n, 
         return ACGPU_OK;
     }
     int rc = stream_append(s, chars, n);
+    if (s->chain_pipe) {
+        // upload of this block (st_up) || record kernels and download of the previous block (st, st_dn); then this block's
+        // masks and maps are enqueued and the call returns without waiting for them
+        Collected col;
+        if (rc == ACGPU_OK) rc = stream_chain_finish(s, col);
+        if (rc == ACGPU_OK) rc = stream_chain_begin(s);
+        rc = stream_collect_end(s, col, rc, out);
+        if (s->dma_pending || rc != ACGPU_OK) {
+            s->dma_pending = false;
+            const cudaError_t e = cudaStreamSynchronize(s->st_up);  // the caller's buffer is free again
+            if (e != cudaSuccess && rc == ACGPU_OK) rc = fail(ACGPU_ECUDA, std::string("stream upload: ") + cudaGetErrorString(e));
+        }
+        return rc;
+    }
     if (s->pipelined) {
         // upload of this block (st_up) || download of the previous block's records (st); then this block's scan is
         // enqueued and the call returns without waiting for it
@@ -2959,6 +3077,23 @@ int acgpu_stream_end(uint64_t stream_handle, acgpu_result *out) {
                 rc = hc.init();
                 if (rc == ACGPU_OK) rc = hc.run_whole(s->collected.data(), static_cast<int64_t>(s->collected.size()));
                 rc = hc.finish(rc, out);
+            }
+        } else if (s->chain_pipe) {
+            acgpu_result a, b;
+            fill_empty(&b);
+            Collected col;
+            rc = stream_chain_finish(s, col);
+            rc = stream_collect_end(s, col, rc, &a);
+            if (rc == ACGPU_OK) {
+                // whatever is left (less than a tile + look-ahead, or everything of a short Readable), synchronously
+                cudaEventRecord(s->ev_up, s->st_up);
+                cudaStreamWaitEvent(s->st, s->ev_up, 0);
+                rc = stream_process_chain(s, true, &b);
+            }
+            if (rc == ACGPU_OK) rc = merge_results(&a, &b, s->m->host.is_map, out);
+            if (rc != ACGPU_OK) {
+                acgpu_free_result(&a);
+                acgpu_free_result(&b);
             }
         } else if (s->pipelined) {
             acgpu_result a, b;

@@ -231,6 +231,10 @@ int acgpu_launches_per_match(uint64_t handle);
  * are final so far, in order; positions are offsets in the whole stream.  end() flushes the rest.
  * AhoCorasick / WholeWord streams are PIPELINED: the block of feed k goes up while the records of block k-1 come down,
  * and feed k returns the records of block k-1 (one block later than they could be known; no feed waits for its own scan).
+ * Longest / Shortest streams on the start-mask path scan every feed as a chain shard (whole 8 192-position tiles; the rest of
+ * the block waits for the next feed).  Matchers that follow the reference loop literally (quirk Q7 tables; keywords beyond what
+ * the selection kernels hold: Longest / Shortest > 2 047 chars, WholeWordLongest > 254) collect the feeds and deliver every
+ * record with end() - a segment of that loop can be as long as the input.
  */
 int acgpu_stream_begin(uint64_t handle, uint64_t *stream_handle);
 /* ReadableMatchListener.match(T value) sees VALUES only (ReadableMatchListener.java:7): with values_only on, the feeds of a
