@@ -812,11 +812,120 @@ int enqueue_fused(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_fro
     return rc;
 }
 
+// Tunables of the slab run (k_tier_duo, kernel_fuse.cuh).  ACGPU_DUO=1 turns it on.
+struct DuoTuning {
+    bool on = false;
+    int slabs = 4;
+    int emit_warps = 8;
+    int64_t min_rows = 8 * kScanRows;
+};
+const DuoTuning &duo_tuning() {
+    static const DuoTuning t = [] {
+        DuoTuning v;
+        if (const char *e = getenv("ACGPU_DUO")) v.on = e[0] == '1';
+        if (const char *e = getenv("ACGPU_DUO_SLABS")) v.slabs = std::min(64, std::max(2, atoi(e)));
+        if (const char *e = getenv("ACGPU_DUO_EMIT_WARPS")) v.emit_warps = std::min(kMaskWarps, std::max(1, atoi(e)));
+        if (const char *e = getenv("ACGPU_DUO_MIN_ROWS")) v.min_rows = std::max<int64_t>(2 * kScanRows, atoll(e));
+        return v;
+    }();
+    return t;
+}
+
+cudaError_t launch_duo(Matcher *m, const MaskArgs &P, const DuoArgs &D, int grid, size_t smem, cudaStream_t st) {
+    const int low = mask_low_variant(m->tier, false);
+    const bool is_map = m->dev.is_map != 0;
+    switch (m->tier.K) {
+    case 1: return duo_launch_1(low, is_map, m->dev, m->tier, P, D, grid, smem, st);
+    case 2: return duo_launch_2(low, is_map, m->dev, m->tier, P, D, grid, smem, st);
+    case 3: return duo_launch_3(low, is_map, m->dev, m->tier, P, D, grid, smem, st);
+    case 4: return duo_launch_4(low, is_map, m->dev, m->tier, P, D, grid, smem, st);
+    case 5: return duo_launch_5(low, is_map, m->dev, m->tier, P, D, grid, smem, st);
+    case 6: return duo_launch_6(low, is_map, m->dev, m->tier, P, D, grid, smem, st);
+    case 7: return duo_launch_7(low, is_map, m->dev, m->tier, P, D, grid, smem, st);
+    default: return duo_launch_8(low, is_map, m->dev, m->tier, P, D, grid, smem, st);
+    }
+}
+
+// Slab run: launch i = k_tier_duo(masks of slab i || records of slab i - 1), k_row_scan(slab i, running total); the last
+// slab's records by k_tier_emit.  Slabs are multiples of kScanRows rows, so every slab has its own scan blocks.
+int enqueue_duo(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from, int64_t emit_to, int64_t origin, int2 *d_pos,
+                uint32_t *d_val, int64_t cap, unsigned long long *d_total, cudaStream_t st, const RunOpts &opt, size_t smem) {
+    const DuoTuning &tune = duo_tuning();
+    const MaskWs L = mask_ws_layout(emit_to, origin);
+    const int64_t slab_rows = (((L.n_rows + tune.slabs - 1) / tune.slabs) + kScanRows - 1) / kScanRows * kScanRows;
+    const int n_slabs = static_cast<int>((L.n_rows + slab_rows - 1) / slab_rows);
+    const size_t ctr_bytes = static_cast<size_t>(n_slabs) * 64;   // per slab: mask ticket, emit ticket, scan "done", total (u64 at +16)
+    void *ws = nullptr;
+    CU_TRY(cudaMallocAsync(&ws, L.bytes + ctr_bytes, st));
+    char *w = static_cast<char *>(ws);
+    char *ctr = w + L.bytes;
+    int rc = ACGPU_OK;
+    if (cudaMemsetAsync(ctr, 0, ctr_bytes, st) != cudaSuccess) rc = fail(ACGPU_ECUDA, "memset failed");
+    uint32_t *masks = reinterpret_cast<uint32_t *>(w + L.o_mask);
+    uint32_t *row_count = reinterpret_cast<uint32_t *>(w + L.o_cnt);
+    unsigned long long *block_excl = reinterpret_cast<unsigned long long *>(w + L.o_blk);
+    auto emit_args = [&](int slab) {
+        EmitArgs E{};
+        const int64_t row_lo = static_cast<int64_t>(slab) * slab_rows;
+        E.hay = d_hay;
+        E.n = n;
+        E.masks = masks + row_lo * (kMaskRow / 2);
+        E.row_excl = row_count + row_lo;
+        E.block_excl = block_excl + row_lo / kScanRows;
+        E.n_rows = std::min(slab_rows, L.n_rows - row_lo);
+        E.origin = origin + row_lo * kMaskRow;
+        E.pos_base = opt.pos_base;
+        E.pos_out = d_pos;
+        E.val_out = d_val;
+        E.cap = cap;
+        return E;
+    };
+    for (int i = 0; i < n_slabs && rc == ACGPU_OK; i++) {
+        const int64_t row_lo = static_cast<int64_t>(i) * slab_rows;
+        const int64_t rows = std::min(slab_rows, L.n_rows - row_lo);
+        MaskArgs P{};
+        P.hay = d_hay;
+        P.n = n;
+        P.emit_from = emit_from;
+        P.emit_to = emit_to;
+        P.origin = origin + row_lo * kMaskRow;
+        P.masks = masks + row_lo * (kMaskRow / 2);
+        P.row_count = row_count + row_lo;
+        P.ticket = reinterpret_cast<unsigned int *>(ctr + i * 64);
+        P.n_rows = rows;
+        DuoArgs D{};
+        if (i > 0) D.E = emit_args(i - 1);
+        D.emit_ticket = reinterpret_cast<unsigned int *>(ctr + (i > 0 ? i - 1 : 0) * 64 + 4);
+        D.emit_warps = tune.emit_warps;
+        const cudaError_t e = launch_duo(m, P, D, m->sm_count, smem, st);
+        if (e != cudaSuccess) rc = fail(ACGPU_ECUDA, std::string("k_tier_duo: ") + cudaGetErrorString(e));
+        if (rc != ACGPU_OK) break;
+        ScanArgs SA{};
+        SA.row_count = P.row_count;
+        SA.block_excl = block_excl + row_lo / kScanRows;
+        SA.done = reinterpret_cast<unsigned int *>(ctr + i * 64 + 8);
+        SA.total_out = reinterpret_cast<unsigned long long *>(ctr + i * 64 + 16);
+        SA.n_rows = rows;
+        SA.base_in = i > 0 ? reinterpret_cast<const unsigned long long *>(ctr + (i - 1) * 64 + 16) : nullptr;
+        k_row_scan<<<static_cast<unsigned>((rows + kScanRows - 1) / kScanRows), 1024, 0, st>>>(SA);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(ACGPU_ECUDA, "k_row_scan failed");
+    }
+    if (rc == ACGPU_OK) rc = launch_emit(m, emit_args(n_slabs - 1), st);
+    if (rc == ACGPU_OK && cudaMemcpyAsync(d_total, ctr + (n_slabs - 1) * 64 + 16, 8, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        rc = fail(ACGPU_ECUDA, "total copy failed");
+    cudaFreeAsync(ws, st);
+    return rc;
+}
+
 int enqueue_mask(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit_from, int64_t emit_to, int64_t origin, int2 *d_pos,
                  uint32_t *d_val, int64_t cap, unsigned long long *d_total, cudaStream_t st, const RunOpts &opt) {
     const MaskWs whole = mask_ws_layout(emit_to, origin);
     if (m->fuse_smem && cap > 0 && whole.n_rows >= fuse_tuning().min_rows)
         return enqueue_fused(m, d_hay, n, emit_from, emit_to, origin, d_pos, d_val, cap, d_total, st, opt);
+    if (duo_tuning().on && !m->mask_pair && cap > 0 && whole.n_rows >= duo_tuning().min_rows) {
+        const size_t smem = duo_smem_bytes(m->host.tier.row_words.size(), m->dev.is_map != 0, duo_tuning().emit_warps);
+        if (smem <= 227 * 1024) return enqueue_duo(m, d_hay, n, emit_from, emit_to, origin, d_pos, d_val, cap, d_total, st, opt, smem);
+    }
     const MaskWs &L = whole;
     void *ws = nullptr;
     CU_TRY(cudaMallocAsync(&ws, L.bytes, st));

@@ -71,8 +71,9 @@ static __global__ void __launch_bounds__(1024, 1) k_row_scan(const ScanArgs S) {
             const unsigned long long y = __shfl_up_sync(0xFFFFFFFFu, wi, o);
             if (lane >= o) wi += y;
         }
-        s_warp[lane] = wi - w;
-        if (lane == 31) *S.total_out = wi;
+        const unsigned long long before = S.base_in ? *S.base_in : 0ull;
+        s_warp[lane] = before + wi - w;
+        if (lane == 31) *S.total_out = before + wi;
     }
     __syncthreads();
     unsigned long long run = s_warp[warp] + sinc - sum;

@@ -220,4 +220,96 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_fused(const DevAutomat
     tier_mask_body<K, LOW, false>(A, T, P, S, s_mem);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_tier_duo<K, LOW, isMap> (generation 6): the masks of one SLAB of the haystack and the records of the slab BEFORE it in
+// the same launch.
+//
+// k_tier_mask is bound by the L1 miss path (gathers, DRAM at 22 %), k_tier_emit by DRAM (94 % of the copy rate): run one
+// after the other each leaves the other's unit idle.  Running them as two kernels on two streams does not overlap them (the
+// persistent mask CTAs fill the register file), generation 5 interleaved them per ticket inside one kernel and lost to its own
+// ordering machinery and to 214 KB of shared memory.  Here the haystack is cut into a few slabs (multiples of 4 096 rows) and
+// launch i makes the masks of slab i while `emit_warps` warps of every CTA expand slab i - 1, whose masks and row offsets
+// (k_row_scan with the running total of the slabs before it) are final since the launches before: no ordering inside the
+// kernel, masks through HBM as in generation 3.  The emit warps take tickets of 8 rows until slab i - 1 is done, then mask
+// tickets like everyone else; only they have staging windows (8 x 0.9 KB: the CTA stays on the 196 KB carve-out).  The last
+// slab is expanded by k_tier_emit.
+constexpr int kDuoEmitRows = 8;
+
+struct DuoArgs {
+    EmitArgs E;                 // the slab to expand (n_rows = 0: none)
+    unsigned int *emit_ticket;
+    int emit_warps;             // warps 0 .. emit_warps - 1 of every CTA expand first
+};
+
+template <bool kIsMap>
+struct DuoSched {
+    static constexpr bool kFused = false;
+    const DevAutomaton &A;
+    const DevTier &T;
+    const DuoArgs &D;
+    unsigned int *mask_ticket;
+    EmitWarp W;
+    bool emit_pending;
+
+    __device__ __forceinline__ int rows() const { return kMaskChunkRows; }
+    __device__ __forceinline__ int64_t mask_row0(uint32_t, int64_t row0) const { return row0; }
+    __device__ __forceinline__ void finish(uint32_t, uint32_t, int) {}
+
+    __device__ __noinline__ void expand_all(int lane) {
+        const EmitArgs &E = D.E;
+        const int n_rows = (int)E.n_rows;
+        while (true) {
+            uint32_t t = 0;
+            if (lane == 0) t = atomicAdd(D.emit_ticket, 1u);
+            t = __shfl_sync(0xFFFFFFFFu, t, 0);
+            const int row0 = (int)t * kDuoEmitRows;
+            if (row0 >= n_rows) break;
+            const int n_r = min(kDuoEmitRows, n_rows - row0);
+            const uint4 *mp = reinterpret_cast<const uint4 *>(E.masks) + ((size_t)row0 * 32 + lane);
+            const unsigned long long block_base = __ldg(E.block_excl + (row0 >> 12));   // kDuoEmitRows divides 4 096: one scan block per ticket
+            uint4 mm_n = __ldcs(mp);
+            uint32_t off_n = __ldg(E.row_excl + row0);
+            for (int r = 0; r < n_r; ++r) {
+                const uint4 mm = mm_n;
+                const unsigned long long base = block_base + off_n;
+                if (r + 1 < n_r) {
+                    mm_n = __ldcs(mp + (size_t)(r + 1) * 32);
+                    off_n = __ldg(E.row_excl + row0 + r + 1);
+                }
+                emit_row<kIsMap>(A, T, E, W, row0 + r, mm, base);
+            }
+        }
+    }
+
+    __device__ __forceinline__ uint32_t next(int lane) {
+        if (emit_pending) {
+            expand_all(lane);
+            emit_pending = false;
+        }
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(mask_ticket, 1u);
+        return __shfl_sync(0xFFFFFFFFu, chunk, 0);
+    }
+};
+
+__host__ __device__ constexpr size_t duo_smem_bytes(size_t n_row_words, bool is_map, int emit_warps) {
+    return mask_smem_bytes(n_row_words) + (size_t)emit_warps * (is_map ? kEmitWarpBytesMap : kEmitWarpBytesSet);
+}
+
+template <int K, int LOW, bool kIsMap>
+__global__ void __launch_bounds__(kMaskThreads, 1) k_tier_duo(const DevAutomaton A, const DevTier T, const MaskArgs P, const DuoArgs D) {
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool emitter = warp < D.emit_warps;
+    unsigned char *s_emit = reinterpret_cast<unsigned char *>(s_mem) + mask_smem_bytes(T.n_row_words) +
+                            (size_t)(emitter ? warp : 0) * (kIsMap ? kEmitWarpBytesMap : kEmitWarpBytesSet);
+    int2 *s_stage = reinterpret_cast<int2 *>(s_emit);
+    uint32_t *s_val = reinterpret_cast<uint32_t *>(s_emit + kEmitWarpBytesSet);
+    uint2 *s_pack = reinterpret_cast<uint2 *>(s_emit + kEmitWarpBytesSet + 4 * ((kEmitWin + 3) & ~3));
+    DuoSched<kIsMap> S{A, T, D, P.ticket, make_emit_warp(T, D.E, s_stage, s_val, s_pack, reinterpret_cast<const uint8_t *>(s_mem), lane),
+                       emitter && D.E.n_rows > 0};
+    tier_mask_body<K, LOW, false>(A, T, P, S, s_mem);
+    static_assert(kScanRows % kDuoEmitRows == 0, "an emit ticket lies inside one scan block");
+}
+
 }  // namespace acgpu

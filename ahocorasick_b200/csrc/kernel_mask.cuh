@@ -60,6 +60,7 @@ struct ScanArgs {
     unsigned int *done;               // blocks finished
     unsigned long long *total_out;
     int64_t n_rows;
+    const unsigned long long *base_in;   // records before row 0 (slab runs: the total of the slabs before this one); nullptr: 0
 };
 
 struct EmitArgs {

@@ -68,6 +68,22 @@ cudaError_t launch_fuse_variant(const DevAutomaton &A, const DevTier &T, const M
     return cudaGetLastError();
 }
 
+template <int LOW, bool MAP>
+cudaError_t launch_duo_variant(const DevAutomaton &A, const DevTier &T, const MaskArgs &P, const DuoArgs &D, int grid, size_t smem, cudaStream_t st) {
+    static size_t attr_smem[64] = {0};
+    auto kern = k_tier_duo<TIER_K, LOW, MAP>;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || attr_smem[dev] < smem) {
+        e = cudaFuncSetAttribute(reinterpret_cast<const void *>(kern), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_smem[dev] = smem;
+    }
+    kern<<<grid, kMaskThreads, smem, st>>>(A, T, P, D);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 #define ACGPU_CAT2(a, b) a##b
@@ -95,6 +111,17 @@ cudaError_t ACGPU_CAT(fuse_launch_, TIER_K)(int low, bool is_map, const DevAutom
     ACGPU_FUSE_CASE(0, false) ACGPU_FUSE_CASE(1, false) ACGPU_FUSE_CASE(2, false)
     ACGPU_FUSE_CASE(0, true) ACGPU_FUSE_CASE(1, true) ACGPU_FUSE_CASE(2, true)
 #undef ACGPU_FUSE_CASE
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t ACGPU_CAT(duo_launch_, TIER_K)(int low, bool is_map, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, const DuoArgs &D, int grid,
+                                           size_t smem, cudaStream_t st) {
+    if (TIER_K == 1 || low < 0 || low > 2) low = 2;
+#define ACGPU_DUO_CASE(L, M) \
+    if (low == L && is_map == M) return launch_duo_variant<L, M>(A, T, P, D, grid, smem, st);
+    ACGPU_DUO_CASE(0, false) ACGPU_DUO_CASE(1, false) ACGPU_DUO_CASE(2, false)
+    ACGPU_DUO_CASE(0, true) ACGPU_DUO_CASE(1, true) ACGPU_DUO_CASE(2, true)
+#undef ACGPU_DUO_CASE
     return cudaErrorInvalidValue;
 }
 

@@ -10,6 +10,7 @@ namespace acgpu {
 struct DevTier;
 struct MaskArgs;
 struct FuseArgs;
+struct DuoArgs;
 
 // Tables that every probe gathers from (child masks + deep table): the launches ask L2 to keep them resident while the
 // haystack, mask and record streams pass through (cudaLaunchAttributeAccessPolicyWindow; bytes == 0: no window).
@@ -24,9 +25,11 @@ struct L2Window {
 // pair: k_tier_pair (kernel_pair.cuh, pair rows) instead of k_tier_mask.
 // k_tier_mask<K, LOW> (kernel_mask.cuh): persistent, one CTA per SM; no inter-CTA waiting, plain launch.
 // fuse_launch_k: k_tier_fused<K, LOW, isMap> (kernel_fuse.cuh) - masks and records in one persistent launch.
+// duo_launch_k: k_tier_duo<K, LOW, isMap> (kernel_fuse.cuh) - the masks of one slab and the records of the slab before it.
 #define ACGPU_DECLARE_MASK(k) \
     cudaError_t mask_launch_##k(int low, bool mir, bool pair, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, int grid, size_t smem, const L2Window &W, cudaStream_t st); \
-    cudaError_t fuse_launch_##k(int low, bool is_map, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, const FuseArgs &F, int grid, size_t smem, cudaStream_t st);
+    cudaError_t fuse_launch_##k(int low, bool is_map, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, const FuseArgs &F, int grid, size_t smem, cudaStream_t st); \
+    cudaError_t duo_launch_##k(int low, bool is_map, const DevAutomaton &A, const DevTier &T, const MaskArgs &P, const DuoArgs &D, int grid, size_t smem, cudaStream_t st);
 ACGPU_DECLARE_MASK(1)
 ACGPU_DECLARE_MASK(2)
 ACGPU_DECLARE_MASK(3)
