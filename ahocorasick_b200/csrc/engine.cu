@@ -59,6 +59,8 @@ struct CallCtx {
     cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_dn[2] = {nullptr, nullptr};
     unsigned long long *d_total = nullptr;  // [2] device
     unsigned long long *h_total = nullptr;  // [2] pinned
+    unsigned long long *d_map = nullptr;    // [2][16] device: composed maps of two chain shards in flight (run_chain), made on first use
+    unsigned long long *h_map = nullptr;    // [2][16] pinned
     void destroy() {
         for (int i = 0; i < 2; i++) {
             if (ev_up[i]) cudaEventDestroy(ev_up[i]);
@@ -67,6 +69,8 @@ struct CallCtx {
         }
         if (d_total) cudaFree(d_total);
         if (h_total) cudaFreeHost(h_total);
+        if (d_map) cudaFree(d_map);
+        if (h_map) cudaFreeHost(h_map);
         if (s_up) cudaStreamDestroy(s_up);
         if (s_k) cudaStreamDestroy(s_k);
         if (s_dn) cudaStreamDestroy(s_dn);
@@ -1823,6 +1827,118 @@ struct HostCall {
         return rc;
     }
 
+    // Longest / Shortest on the start-mask path, long haystacks: the haystack goes up chunk by chunk and every chunk is a CHAIN
+    // SHARD (acgpu_chain_shard_*: the kernels of the multi-GPU shards and of the Readable feeds).  begin(k) - masks, maps, the
+    // composed map - is entry-independent and runs as soon as chunk k and its look-ahead have landed; the map gives the record
+    // count and the offset at which the chain enters chunk k + 1, so the records of chunk k are cut and come down while chunk
+    // k + 2 goes up: H2D, kernels and D2H overlap as in run_chunked.  The last chunk takes what is left.
+    int run_chain(const uint16_t *hay, int64_t n) {
+        constexpr int64_t C = kChunk;   // a multiple of kS2Tile
+        static_assert(kChunk % kS2Tile == 0, "inner shards own whole tiles");
+        int64_t n_chunks = 1;
+        while (n_chunks * C + kMaskRow < n) n_chunks++;   // every chunk but the last has kMaskRow chars of look-ahead behind it
+        if (!cx->d_map) {
+            CU_TRY(cudaMalloc(reinterpret_cast<void **>(&cx->d_map), 2 * kS2Ent * 8));
+            CU_TRY(cudaHostAlloc(reinterpret_cast<void **>(&cx->h_map), 2 * kS2Ent * 8, cudaHostAllocDefault));
+        }
+        const int64_t last_lo = (n_chunks - 1) * C;
+        const int64_t chunk_cap = std::max<int64_t>(C, n - last_lo) + 64;   // non-overlapping matches: at most one per char
+        CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_hay), static_cast<size_t>(n) * 2, s_k));
+        for (int i = 0; i < (n_chunks > 1 ? 2 : 1); i++) {
+            CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_pos[i]), static_cast<size_t>(chunk_cap) * 8, s_k));
+            if (is_map) CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_val[i]), static_cast<size_t>(chunk_cap) * 4, s_k));
+        }
+        CU_TRY(cudaEventRecord(ev_dn[0], s_k));  // the upload stream may touch d_hay once it exists
+        CU_TRY(cudaStreamWaitEvent(s_up, ev_dn[0], 0));
+        Sel2Run R[2];
+        int64_t up_to = 0;   // chars uploaded (enqueued) so far
+        auto upload_to = [&](int64_t hi) -> int {
+            hi = std::min<int64_t>(n, hi);
+            while (up_to < hi) {
+                const int64_t c = std::min<int64_t>(C, hi - up_to);
+                CU_TRY(cudaMemcpyAsync(d_hay + up_to, hay + up_to, static_cast<size_t>(c) * 2, cudaMemcpyHostToDevice, s_up));
+                up_to += c;
+            }
+            return ACGPU_OK;
+        };
+        auto begin = [&](int64_t k) -> int {
+            const int bf = static_cast<int>(k & 1);
+            const bool last = k + 1 == n_chunks;
+            const int64_t lo = k * C, n_win = last ? n - lo : C + kMaskRow;
+            int rc = upload_to(lo + n_win);
+            if (rc != ACGPU_OK) return rc;
+            CU_TRY(cudaEventRecord(ev_up[bf], s_up));
+            CU_TRY(cudaStreamWaitEvent(s_k, ev_up[bf], 0));
+            RunOpts opt;
+            opt.pos_base = static_cast<int32_t>(lo);
+            R[bf] = Sel2Run();
+            rc = sel2_setup(m, d_hay + lo, n_win, last ? -1 : C / kS2Tile, s_k, opt, R[bf]);
+            if (rc == ACGPU_OK) rc = sel2_masks(R[bf]);
+            if (rc == ACGPU_OK) rc = sel2_maps(R[bf]);
+            if (rc == ACGPU_OK && !last) {
+                rc = sel2_shard_map(R[bf], cx->d_map + bf * kS2Ent, d_total + bf);
+                if (rc == ACGPU_OK) CU_TRY(cudaMemcpyAsync(cx->h_map + bf * kS2Ent, cx->d_map + bf * kS2Ent, kS2Ent * 8, cudaMemcpyDeviceToHost, s_k));
+            }
+            if (rc == ACGPU_OK) CU_TRY(cudaEventRecord(ev_k[bf], s_k));
+            return rc;
+        };
+        int rc = begin(0);
+        int32_t entry = 0;
+        for (int64_t k = 0; k < n_chunks && rc == ACGPU_OK; k++) {
+            const int bf = static_cast<int>(k & 1);
+            const bool last = k + 1 == n_chunks;
+            if (!last) rc = begin(k + 1);
+            if (rc != ACGPU_OK) break;
+            if (k >= 2) CU_TRY(cudaStreamWaitEvent(s_k, ev_dn[bf], 0));   // the records of chunk k - 2 have left the buffer
+            int64_t got = 0;
+            uint32_t entry0 = static_cast<uint32_t>(entry);
+            if (!last) {
+                CU_TRY(cudaEventSynchronize(ev_k[bf]));   // the chunk's map is in pinned memory
+                const unsigned long long row = cx->h_map[bf * kS2Ent + entry];
+                got = static_cast<int64_t>(row >> 8);
+                entry = static_cast<int32_t>(row & 0xFFu);
+                if (got > 0) rc = sel2_records(R[bf], entry0, d_pos[bf], d_val[bf], chunk_cap, d_total + bf);
+            } else {
+                const int64_t idx = R[bf].moff + entry;   // index-space position the chain enters at
+                if (idx < kS2Ent) {
+                    entry0 = static_cast<uint32_t>(idx);
+                } else {
+                    entry0 = 0;
+                    k_sel2_zero_prefix<<<1, 256, 0, s_k>>>(R[bf].P.masks, R[bf].moff, idx);
+                    CU_TRY(cudaGetLastError());
+                    rc = sel2_maps(R[bf], 1);
+                }
+                if (rc == ACGPU_OK) rc = sel2_records(R[bf], entry0, d_pos[bf], d_val[bf], chunk_cap, d_total + bf);
+                if (rc == ACGPU_OK) {
+                    CU_TRY(cudaMemcpyAsync(h_total + bf, d_total + bf, 8, cudaMemcpyDeviceToHost, s_k));
+                    CU_TRY(cudaStreamSynchronize(s_k));
+                    got = static_cast<int64_t>(h_total[bf]);
+                }
+            }
+            sel2_free(R[bf]);
+            if (rc != ACGPU_OK) break;
+            CU_TRY(cudaEventRecord(ev_k[bf], s_k));
+            if (count + got > cap) {
+                const int64_t done_chars = std::min<int64_t>(n, (k + 1) * C);
+                const double density = static_cast<double>(count + got) / static_cast<double>(done_chars);
+                const int64_t est = static_cast<int64_t>(density * 1.15 * static_cast<double>(n)) + (1 << 16);
+                rc = reserve(std::max<int64_t>(count + got, last ? count + got : est));
+                if (rc != ACGPU_OK) break;
+            }
+            CU_TRY(cudaStreamWaitEvent(s_dn, ev_k[bf], 0));
+            rc = download(d_pos[bf], d_val[bf], got);
+            if (rc != ACGPU_OK) break;
+            CU_TRY(cudaEventRecord(ev_dn[bf], s_dn));
+        }
+        if (rc != ACGPU_OK) {
+            sel2_free(R[0]);
+            sel2_free(R[1]);
+            return rc;
+        }
+        CU_TRY(cudaStreamSynchronize(s_dn));
+        return ACGPU_OK;
+    }
+
     int run_whole(const uint16_t *hay, int64_t n) {
         CU_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_hay), static_cast<size_t>(n) * 2, s_k));
         CU_TRY(cudaMemcpyAsync(d_hay, hay, static_cast<size_t>(n) * 2, cudaMemcpyHostToDevice, s_k));
@@ -2349,8 +2465,13 @@ int acgpu_match_utf16(uint64_t handle, const uint16_t *haystack, int32_t n, acgp
     if (n == 0) return ACGPU_OK;
     HostCall hc(m);
     rc = hc.init();
-    if (rc == ACGPU_OK)
-        rc = m->host.family == ACGPU_AHOCORASICK ? hc.run_chunked(haystack, n) : hc.run_whole(haystack, n);
+    {
+        static const char *chain_env = getenv("ACGPU_HOST_CHAIN");   // ACGPU_HOST_CHAIN=0: upload, scan, download in turn (A/B runs)
+        const bool chain = (m->host.family == ACGPU_LONGEST || m->host.family == ACGPU_SHORTEST) && m->use_tier && m->literal_family < 0 &&
+                           n >= 2 * HostCall::kChunk && !(chain_env && chain_env[0] == '0');
+        if (rc == ACGPU_OK)
+            rc = m->host.family == ACGPU_AHOCORASICK ? hc.run_chunked(haystack, n) : (chain ? hc.run_chain(haystack, n) : hc.run_whole(haystack, n));
+    }
     return hc.finish(rc, out);
 }
 

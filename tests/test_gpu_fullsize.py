@@ -68,6 +68,29 @@ def test_config2_full_dictionary_16mb_slice(family, is_map):
     assert len(want) > 500_000
 
 
+@pytest.mark.parametrize("family,is_map,text", [("longest", True, "config2"), ("shortest", False, "config2"), ("longest", False, "dense"),
+                                                ("shortest", True, "dense")])
+def test_config2_host_call_pipelines_chain_shards(family, is_map, text):
+    """acgpu_match_utf16 on a Longest / Shortest haystack of several 2^23-char chunks: the host call cuts the haystack into
+    chain shards (upload of chunk k + 2 next to the record download of chunk k; HostCall::run_chain) and must return the
+    stream of the oracle's single loop - also on text without any synchronisation point ("dense": every chunk hands a chain
+    position inside a keyword over to the next one)."""
+    c = W.config(2, scale=0.05)
+    kws = c["keywords"]
+    n = (1 << 24) + (1 << 23) + 12_345          # three chunks, the last one not a multiple of anything
+    if text == "config2":
+        hay = _slice(c["spec"], n)
+    else:
+        rng = np.random.default_rng(77)
+        hay = (rng.integers(0, 3, n) + ord("a")).astype(np.uint16)
+        kws = sorted({"".join(chr(ord("a") + int(x)) for x in rng.integers(0, 3, int(rng.integers(1, 12)))) for _ in range(400)})
+    want = ora.Matcher(family, kws, n_values=len(kws) if is_map else -1).match(hay, cap=n)
+    cls = getattr(ac, ("Longest" if family == "longest" else "Shortest") + "Match" + ("Map" if is_map else "Set"))
+    m = cls(kws, list(range(len(kws))), True) if is_map else cls(kws, True)
+    _same(m.match_records(hay), want, values=is_map, note=(family, is_map, text))
+    assert len(want) > 1_000_000
+
+
 def test_config3_full_dictionary_16mb_slice_string_and_readable():
     """configs[3]: WholeWordMatchSet(kw, true, {'_','='}, {false,true}) with ALL 50 000 keywords via String, and the Map
     via Readable (WholeWordMatchSet.java:47-132, WholeWordMatchMap.java:55-153)."""
