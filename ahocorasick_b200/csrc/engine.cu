@@ -421,6 +421,17 @@ struct RunOpts {
     bool folded_scroll = false;  // literal WholeWord matchers (quirk Q7): the Readable overloads scroll on the lower-cased char
 };
 
+// rows per ticket of the mask kernels: 32 for long haystacks; short ones take smaller tickets so that every warp of the grid
+// (sm_count x 32) gets work - 8 M chars are 977 tickets of 32 rows: 31 of 148 SMs busy.  ACGPU_CHUNK_ROWS forces a value.
+int mask_chunk_rows(const Matcher *m, int64_t n_rows) {
+    static const char *env = getenv("ACGPU_CHUNK_ROWS");
+    if (env && atoi(env) > 0) return std::min(kMaskChunkRows, atoi(env));
+    const int64_t warps = static_cast<int64_t>(m->sm_count) * kMaskWarps;
+    int rows = kMaskChunkRows;
+    while (rows > 2 && (n_rows + rows - 1) / rows < 2 * warps) rows >>= 1;
+    return rows;
+}
+
 int launch_mask(Matcher *m, const MaskArgs &P, int grid, cudaStream_t st, bool mir = false) {
     const int low = mask_low_variant(m->tier, m->mask_pair);
     cudaError_t e;
@@ -522,7 +533,8 @@ void sel2_free(Sel2Run &R) {
 
 int sel2_masks(Sel2Run &R) {
     CU_TRY(cudaMemsetAsync(static_cast<char *>(R.ws) + R.o_ctr, 0, 256, R.st));
-    const int64_t n_chunks = (R.n_rows + kMaskChunkRows - 1) / kMaskChunkRows;
+    R.P.chunk_rows = mask_chunk_rows(R.m, R.n_rows);
+    const int64_t n_chunks = (R.n_rows + R.P.chunk_rows - 1) / R.P.chunk_rows;
     const int grid = static_cast<int>(std::min<int64_t>((n_chunks + kMaskWarps - 1) / kMaskWarps, R.m->sm_count));
     return launch_mask(R.m, R.P, grid, R.st, true);
 }
@@ -678,7 +690,8 @@ int enqueue_mask_scan(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t emit
     P.row_count = reinterpret_cast<uint32_t *>(w + L.o_cnt);
     P.ticket = reinterpret_cast<unsigned int *>(w + L.o_ctr);
     P.n_rows = L.n_rows;
-    const int64_t n_chunks = (L.n_rows + kMaskChunkRows - 1) / kMaskChunkRows;
+    P.chunk_rows = mask_chunk_rows(m, L.n_rows);
+    const int64_t n_chunks = (L.n_rows + P.chunk_rows - 1) / P.chunk_rows;
     const int grid = static_cast<int>(std::min<int64_t>((n_chunks + kMaskWarps - 1) / kMaskWarps, m->sm_count));
     int rc = launch_mask(m, P, grid, st);
     if (rc != ACGPU_OK) return rc;

@@ -52,6 +52,7 @@ struct MaskArgs {
     uint32_t *row_count;    // [n_rows]
     unsigned int *ticket;
     int64_t n_rows;
+    int32_t chunk_rows;     // rows per ticket, 1 .. kMaskChunkRows (0 = kMaskChunkRows): short haystacks take small tickets so that every warp of the grid gets one
 };
 
 struct ScanArgs {
@@ -176,12 +177,13 @@ __device__ __noinline__ uint32_t deep_resolve(const uint4 *buckets, unsigned lon
 struct PlainSched {
     static constexpr bool kFused = false;
     unsigned int *ticket;
+    int chunk_rows;
     __device__ __forceinline__ uint32_t next(int lane) {
         uint32_t chunk = 0;
         if (lane == 0) chunk = atomicAdd(ticket, 1u);
         return __shfl_sync(0xFFFFFFFFu, chunk, 0);
     }
-    __device__ __forceinline__ int rows() const { return kMaskChunkRows; }
+    __device__ __forceinline__ int rows() const { return chunk_rows; }
     __device__ __forceinline__ int64_t mask_row0(uint32_t, int64_t row0) const { return row0; }
     __device__ __forceinline__ void finish(uint32_t, uint32_t, int) {}
 };
@@ -426,7 +428,7 @@ __device__ __forceinline__ void tier_mask_body(const DevAutomaton &A, const DevT
 template <int K, int LOW, bool MIR>
 __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_mask(const DevAutomaton A, const DevTier T, const MaskArgs P) {
     extern __shared__ __align__(16) uint32_t s_mem[];
-    PlainSched S{P.ticket};
+    PlainSched S{P.ticket, P.chunk_rows > 0 ? P.chunk_rows : kMaskChunkRows};
     tier_mask_body<K, LOW, MIR>(A, T, P, S, s_mem);
 }
 

@@ -56,13 +56,14 @@ __global__ void __launch_bounds__(kMaskThreads, 1) k_tier_pair(const DevAutomato
             deep_resolve<K>(T.buckets, T.hash_seed, T.n_buckets, T.b, T.inv_b, s_qctx[first + lane], s_qpos[first + lane], A.max_len,
                             P.masks, P.row_count);
     };
+    const int t_rows = P.chunk_rows > 0 ? P.chunk_rows : kMaskChunkRows;
     while (true) {
         uint32_t chunk = 0;
         if (lane == 0) chunk = atomicAdd(P.ticket, 1u);
         chunk = __shfl_sync(0xFFFFFFFFu, chunk, 0);
-        const int64_t row0 = (int64_t)chunk * kMaskChunkRows;
+        const int64_t row0 = (int64_t)chunk * t_rows;
         if (row0 >= P.n_rows) break;
-        const int n_cr = (int)min((int64_t)kMaskChunkRows, P.n_rows - row0);
+        const int n_cr = (int)min((int64_t)t_rows, P.n_rows - row0);
         const int64_t c_lo = P.origin + row0 * kMaskRow, c_hi = c_lo + (int64_t)n_cr * kMaskRow;
         const bool chunk_in = c_lo - 16 >= 0 && c_hi <= P.n;
         const bool chunk_full = c_lo >= P.emit_from && c_hi <= P.emit_to;
