@@ -1082,7 +1082,9 @@ int enqueue_ww3(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t dom_lo, in
         P.hitbits = reinterpret_cast<uint32_t *>(w + o_bits);
         P.row_count = reinterpret_cast<uint32_t *>(w + o_cnt);
         P.ticket = reinterpret_cast<unsigned int *>(w + o_ctr);
-        const int64_t n_chunks = (n_rows + kW3ChunkRows - 1) / kW3ChunkRows;
+        P.chunk_rows = kW3ChunkRows;
+        while (P.chunk_rows > 4 && (n_rows + P.chunk_rows - 1) / P.chunk_rows < 2 * static_cast<int64_t>(m->sm_count) * kW3Warps) P.chunk_rows >>= 1;
+        const int64_t n_chunks = (n_rows + P.chunk_rows - 1) / P.chunk_rows;
         const int grid = static_cast<int>(std::min<int64_t>((n_chunks + kW3Warps - 1) / kW3Warps, m->sm_count));
         const bool shortk = m->ww.max_len < 32;
         const size_t smem = ww3_smem_bytes(m->ww.bloom_bits, shortk);

@@ -65,6 +65,7 @@ struct Ww3Args {
     uint32_t *hitbits;      // [n_rows * 8], zeroed: bit t - origin = a keyword run ends at t (exclusive)
     uint32_t *row_count;    // [n_rows], zeroed
     unsigned int *ticket;
+    int32_t chunk_rows;     // rows per ticket, 1 .. kW3ChunkRows: short windows take small tickets so that every warp gets one
 };
 
 struct Ww3EmitArgs {
@@ -191,9 +192,9 @@ __global__ void __launch_bounds__(kW3Warps * 32, 1) k_ww3_hits(const DevWw W, co
         uint32_t ticket = 0;
         if (lane == 0) ticket = atomicAdd(P.ticket, 1u);
         ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
-        const int64_t row0 = (int64_t)ticket * kW3ChunkRows;
+        const int64_t row0 = (int64_t)ticket * P.chunk_rows;
         if (row0 >= P.n_rows) break;
-        const int n_chunk_rows = (int)(min(row0 + kW3ChunkRows, P.n_rows) - row0) + 1;   // with the context row
+        const int n_chunk_rows = (int)(min(row0 + P.chunk_rows, P.n_rows) - row0) + 1;   // with the context row
         const int64_t ctx_base = P.origin + (row0 - 1) * kW3Row;   // the chunk's context row: the 256 positions before it
         // positions are chunk-relative (0 = ctx_base) from here on
         const int32_t dom_lo = (int32_t)max((int64_t)-1, min(P.dom_lo - ctx_base, (int64_t)1 << 20));
