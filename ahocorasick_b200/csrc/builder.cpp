@@ -664,11 +664,17 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
     const std::vector<uint16_t> &node_cls = trie.cls;
 
     // ---- device tables: direct root table + hashed deeper edges, inserted in child-id order (canonical layout)
+    // info word of an edge = the child's flags | its child signature << 2 (bit c % 30: some child has class c; trie_step_sig)
+    std::vector<uint32_t> info32(static_cast<size_t>(a.n_nodes), 0u);
+    for (int64_t id = 1; id < a.n_nodes; id++) {
+        info32[id] |= a.node_info[id];
+        info32[node_parent[id]] |= 1u << (2u + node_cls[id] % 30u);
+    }
     a.root.assign(static_cast<size_t>(a.n_classes), RootEdge{kNone, 0});
     uint64_t deep_edges = 0;
     for (int64_t id = 1; id < a.n_nodes; id++) {
         if (node_parent[id] == 0) {
-            a.root[node_cls[id]] = RootEdge{static_cast<uint32_t>(id), a.node_info[id]};
+            a.root[node_cls[id]] = RootEdge{static_cast<uint32_t>(id), info32[id]};
         } else {
             ++deep_edges;
         }
@@ -683,7 +689,7 @@ HostAutomaton build_automaton(int family, const uint16_t *chars, const int64_t *
         if (parent == 0) continue;
         uint32_t i = edge_hash(parent, node_cls[id]) & a.edge_mask;
         while (a.edges[i].parent != kNone) i = (i + 1) & a.edge_mask;
-        a.edges[i] = Edge{parent, node_cls[id], static_cast<uint32_t>(id), a.node_info[id]};
+        a.edges[i] = Edge{parent, node_cls[id], static_cast<uint32_t>(id), info32[id]};
     }
     timer.lap("edge table");
     if (family != 4) build_tiers(a, node_parent, node_cls);

@@ -71,6 +71,14 @@ __device__ __forceinline__ bool trie_step(const DevAutomaton &A, uint32_t &node,
     }
 }
 
+// The same step for walks that carry `info` along (it holds the current node's info word on entry; 0 at the root): bits 2 .. 31
+// of an info word say which classes (mod 30) have a child, so a step that cannot succeed costs no probe of the edge table -
+// an unsuccessful open-addressing look-up walks ~2.5 slots, and in running text most walks END with one.
+__device__ __forceinline__ bool trie_step_sig(const DevAutomaton &A, uint32_t &node, uint32_t c, uint32_t &info) {
+    if (node != 0u && !((info >> (2u + c % 30u)) & 1u)) return false;
+    return trie_step(A, node, c, info);
+}
+
 __device__ __forceinline__ bool is_word_char(const DevAutomaton &A, uint32_t raw) {
     return (__ldg(&A.wordbits[raw >> 5]) >> (raw & 31)) & 1u;
 }

@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kWwThreads) k_wwl_starts(const DevAutomaton A,
             int i = p;
             while (t0 + i < P.n) {
                 const uint32_t c = i < win ? (uint32_t)s_c[i] : (uint32_t)__ldg(&A.cls[__ldg(&P.hay[t0 + i])]);
-                if ((A.has_other && c == 0u) || !trie_step(A, node, c, info)) break;
+                if ((A.has_other && c == 0u) || !trie_step_sig(A, node, c, info)) break;
                 ++i;
                 if (info & kTerm) {
                     const bool word_next = t0 + i < P.n && (i < win ? ((s_wc[i >> 5] >> (i & 31)) & 1u) != 0u

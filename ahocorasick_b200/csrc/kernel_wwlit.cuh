@@ -115,7 +115,7 @@ __device__ __forceinline__ int64_t seg_walk(const DevAutomaton &A, const WwLitAr
     int64_t best = 0;
     for (int64_t i = s; i < P.n;) {
         const uint32_t c = __ldg(&A.cls[__ldg(&P.hay[i])]);
-        if ((A.has_other && c == 0u) || !trie_step(A, node, c, info)) break;
+        if ((A.has_other && c == 0u) || !trie_step_sig(A, node, c, info)) break;
         ++i;
         if (info & kTerm) {
             best = i - s;
@@ -216,7 +216,7 @@ __device__ __forceinline__ uint32_t seg_run(const WwLitView &V, int64_t t, unsig
         int64_t len = 0;
         while (idx < P.n) {
             const uint32_t c = V.cls(idx);
-            if ((A.has_other && c == 0u) || !trie_step(A, node, c, info)) break;
+            if ((A.has_other && c == 0u) || !trie_step_sig(A, node, c, info)) break;
             ++idx;
             if ((info & kTerm) && (idx == P.n || !V.word_fold(idx))) {
                 len = idx - s;

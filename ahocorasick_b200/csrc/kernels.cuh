@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kThreads) k_ac_scan(const DevAutomaton A, cons
                 for (int64_t i = q; i >= lim; --i) {
                     uint32_t c = cls_at(i);
                     if (A.has_other && c == 0) break;
-                    if (!trie_step(A, node, c, info)) break;
+                    if (!trie_step_sig(A, node, c, info)) break;
                     c_hits += info & kTerm;
                     if (!(info & kKids)) break;
                 }
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kThreads) k_ac_scan(const DevAutomaton A, cons
             for (int64_t i = q; i >= lim; --i) {
                 uint32_t c = cls_at(i);
                 if (A.has_other && c == 0) break;
-                if (!trie_step(A, node, c, info)) break;
+                if (!trie_step_sig(A, node, c, info)) break;
                 if (info & kTerm) {
                     unsigned long long idx = last - k;
                     if (idx < (unsigned long long)P.cap) {
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kThreads) k_fwd_v(const DevAutomaton A, const 
                             break;
                         }
                         uint32_t c = cls_at(i);
-                        if ((A.has_other && c == 0) || !trie_step(A, node, c, info)) break;
+                        if ((A.has_other && c == 0) || !trie_step_sig(A, node, c, info)) break;
                         ++i;
                     }
                 }
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kThreads) k_fwd_v(const DevAutomaton A, const 
                     int64_t i = s;
                     while (i < P.n) {
                         const uint32_t c = cls_at(i);
-                        if ((A.has_other && c == 0) || !trie_step(A, node, c, info)) break;
+                        if ((A.has_other && c == 0) || !trie_step_sig(A, node, c, info)) break;
                         ++i;
                         if ((info & kTerm) && (i == P.n || !is_word_char(A, __ldg(&P.hay[i])))) len = (uint32_t)(i - s);
                         if (!(info & kKids)) break;
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(kThreads) k_fwd_v(const DevAutomaton A, const 
                 for (int64_t i = s; i < lim;) {
                     uint32_t c = cls_at(i);
                     if (A.has_other && c == 0) break;
-                    if (!trie_step(A, node, c, info)) break;
+                    if (!trie_step_sig(A, node, c, info)) break;
                     ++i;
                     if (info & kTerm) {
                         best = (uint32_t)(i - s);
