@@ -3008,8 +3008,11 @@ int stream_collect_end(StreamCtx *s, Collected &c, int rc, acgpu_result *out) {
     c.live = false;
     const cudaError_t e = cudaEventSynchronize(s->ev_dn);
     if (e != cudaSuccess && rc == ACGPU_OK) rc = fail(ACGPU_ECUDA, std::string("stream download: ") + cudaGetErrorString(e));
-    if (c.d_pos) cudaFreeAsync(c.d_pos, s->st_dn);
-    if (c.d_val) cudaFreeAsync(c.d_val, s->st_dn);
+    // the download has finished (host wait above): free on the stream the NEXT block allocates on, so that the pool hands the same
+    // memory out again (a free on st_dn is only reusable on st when the allocator happens to see it completed - feeds then
+    // grew the pool by a record buffer each, at random)
+    if (c.d_pos) cudaFreeAsync(c.d_pos, s->st);
+    if (c.d_val) cudaFreeAsync(c.d_val, s->st);
     if (rc == ACGPU_OK && c.total > 0) {
         out->n = c.total;
         out->pos = c.h_pos;
