@@ -1058,9 +1058,11 @@ int enqueue_ww3(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t dom_lo, in
     const int64_t n_blocks = (n_rows + kScanRows - 1) / kScanRows;
     Scratch S;
     const size_t o_ctr = S.reserve(256);
-    const size_t o_cnt = S.reserve(static_cast<size_t>(n_rows) * 4);
     const size_t o_bits = S.reserve(static_cast<size_t>(n_rows) * 32);
+    const size_t o_start = S.reserve(static_cast<size_t>(n_rows) * 32);
     const size_t zeroed = S.off;
+    const size_t o_cnt = S.reserve(static_cast<size_t>(n_rows) * 4);
+    const size_t o_val = S.reserve(m->dev.is_map && cap > 0 ? static_cast<size_t>(n_rows) * (kW3Row / 2) * 4 : 0);   // written at hits only
     const size_t o_blk = S.reserve(static_cast<size_t>(n_blocks) * 8);
     void *ws = nullptr;
     CU_TRY(cudaMallocAsync(&ws, S.off, st));
@@ -1080,7 +1082,8 @@ int enqueue_ww3(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t dom_lo, in
         P.origin = origin;
         P.n_rows = n_rows;
         P.hitbits = reinterpret_cast<uint32_t *>(w + o_bits);
-        P.row_count = reinterpret_cast<uint32_t *>(w + o_cnt);
+        P.startbits = reinterpret_cast<uint32_t *>(w + o_start);
+        P.val_scratch = (m->dev.is_map && cap > 0) ? reinterpret_cast<uint32_t *>(w + o_val) : nullptr;
         P.ticket = reinterpret_cast<unsigned int *>(w + o_ctr);
         P.chunk_rows = kW3ChunkRows;
         while (P.chunk_rows > 4 && (n_rows + P.chunk_rows - 1) / P.chunk_rows < 2 * static_cast<int64_t>(m->sm_count) * kW3Warps) P.chunk_rows >>= 1;
@@ -1093,6 +1096,11 @@ int enqueue_ww3(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t dom_lo, in
         else
             shortk ? k_ww3_hits<false, true><<<grid, kW3Warps * 32, smem, st>>>(m->ww, P) : k_ww3_hits<false, false><<<grid, kW3Warps * 32, smem, st>>>(m->ww, P);
         launch_ok("k_ww3_hits");
+    }
+    if (rc == ACGPU_OK) {
+        const int cgrid = static_cast<int>(std::min<int64_t>((n_rows + 255) / 256, static_cast<int64_t>(m->sm_count) * 8));
+        k_ww3_count<<<cgrid, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(w + o_bits), reinterpret_cast<uint32_t *>(w + o_cnt), n_rows);
+        launch_ok("k_ww3_count");
     }
     if (rc == ACGPU_OK) {
         ScanArgs SA{};
@@ -1111,6 +1119,8 @@ int enqueue_ww3(Matcher *m, const uint16_t *d_hay, int64_t n, int64_t dom_lo, in
         E.origin = origin;
         E.n_rows = n_rows;
         E.hitbits = reinterpret_cast<const uint32_t *>(w + o_bits);
+        E.startbits = reinterpret_cast<const uint32_t *>(w + o_start);
+        E.val_scratch = m->dev.is_map ? reinterpret_cast<const uint32_t *>(w + o_val) : nullptr;
         E.row_excl = reinterpret_cast<const uint32_t *>(w + o_cnt);
         E.block_excl = reinterpret_cast<const unsigned long long *>(w + o_blk);
         E.pos_base = opt.pos_base;
@@ -2315,7 +2325,7 @@ int acgpu_launches_per_match(uint64_t handle) {
     if (m->literal_family >= 0) return 3;  // count, scan, write
     switch (m->host.family) {
     case ACGPU_AHOCORASICK: return m->use_tier ? 3 : (m->use_wide ? (m->wide_tile ? 4 : 3) : 1);  // wide, generation 2: tile, tail, scan, emit
-    case ACGPU_WHOLEWORD: return m->use_ww ? (m->use_ww3 ? 3 : 1) : 2;
+    case ACGPU_WHOLEWORD: return m->use_ww ? (m->use_ww3 ? 4 : 1) : 2;  // generation 3: hits, count, scan, emit
     default: return m->use_tier && m->host.is_map ? 7 : 6;  // one-shot tier path: mask, map, group, top, tiles, emit (+ values)  // one-shot matches; the streaming path always takes the 6-launch route
     }
 }

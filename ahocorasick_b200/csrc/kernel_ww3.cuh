@@ -14,10 +14,14 @@
 // memory (50 k keywords: 12 % pass) and queues the survivors; the queue is probed against the keyword table 32 at a time
 // (one gathered 32-byte bucket; the stored class string is compared exactly on a tag match).
 //
-//   k_ww3_hits   hit bitmap (1 bit per position: a keyword run ends before it) + records per row, by atomics on zeroed scratch
+//   k_ww3_hits   two bitmaps on zeroed scratch (1 bit per position each): a keyword run STARTS here / ENDS before here; Maps
+//                also leave the run's value at slot end / 2 of a scratch array (run ends are at least 2 positions apart)
+//   k_ww3_count  records per row = set bits of the row's end bitmap
 //   k_row_scan   row counts -> offsets (kernel_emit.cuh)
-//   k_ww3_emit   hit bits -> (start, end[, value]) records in position order; the start is found by scanning back over the
-//                word chars, a Map's value by hashing the run once more (per RECORD, not per word)
+//   k_ww3_emit   end bits -> (start, end[, value]) records in position order; the start is the last start bit before the end
+// (The first version counted rows with one atomicAdd per hit, probed the table a second time to verify, and let the emit
+// kernel scan back over the word's chars and hash it again for a Map's value: on text where EVERY word is a keyword that
+// was 10.4 / 15.9 ms per 10^9 chars against generation 2's 6.3 / 6.7 - tools/bench_ww_dense.py.)
 #pragma once
 #include "builder.hpp"
 #include "kernel_emit.cuh"
@@ -63,7 +67,8 @@ struct Ww3Args {
     int64_t origin;         // first position of row 0: <= dom_lo and hay + origin is 16-byte aligned
     int64_t n_rows;         // rows cover [origin, min(n, dom_hi + max_len)] - a run that ends with the window is reported at n
     uint32_t *hitbits;      // [n_rows * 8], zeroed: bit t - origin = a keyword run ends at t (exclusive)
-    uint32_t *row_count;    // [n_rows], zeroed
+    uint32_t *startbits;    // [n_rows * 8], zeroed: bit s - origin = a keyword run starts at s
+    uint32_t *val_scratch;  // Maps: [n_rows * 128] value of the run that ends at t, at slot (t - origin) / 2
     unsigned int *ticket;
     int32_t chunk_rows;     // rows per ticket, 1 .. kW3ChunkRows: short windows take small tickets so that every warp gets one
 };
@@ -74,6 +79,8 @@ struct Ww3EmitArgs {
     int64_t origin;
     int64_t n_rows;
     const uint32_t *hitbits;
+    const uint32_t *startbits;
+    const uint32_t *val_scratch;
     const uint32_t *row_excl;
     const unsigned long long *block_excl;
     int32_t pos_base;
@@ -92,17 +99,37 @@ __device__ __forceinline__ uint32_t w3_v(const DevWw &W, const uint32_t *s_tab, 
 }
 __device__ __forceinline__ uint32_t w3_bucket(const DevWw &W, uint32_t key) { return __umulhi(ww_poly_spread(key), W.n_buckets); }
 
-// Is there an entry with this key and length on the key's probe path?  (No string comparison: the survivors are verified
-// 32 at a time by ww3_lookup.)
-__device__ __forceinline__ bool ww3_tag_probe(const DevWw &W, uint32_t key, uint32_t len) {
+// The slot (bucket * 2 + entry) of an entry with this key and length on the key's probe path, 0xFFFFFFFF if there is none.
+// (No string comparison: the survivors are verified 32 at a time.)
+__device__ __forceinline__ uint32_t ww3_tag_probe(const DevWw &W, uint32_t key, uint32_t len) {
     uint32_t bk = w3_bucket(W, key);
     for (uint32_t tries = 0; tries < W.n_buckets; tries++) {
         const uint4 e0 = __ldg(W.buckets + (size_t)bk * 2), e1 = __ldg(W.buckets + (size_t)bk * 2 + 1);
-        if ((e0.x == key && e0.y == len && e0.z != 0xFFFFFFFFu) || (e1.x == key && e1.y == len && e1.z != 0xFFFFFFFFu)) return true;
-        if (e0.z == 0xFFFFFFFFu || e1.z == 0xFFFFFFFFu) return false;  // a free slot on the probe path: not in the table
+        if (e0.x == key && e0.y == len && e0.z != 0xFFFFFFFFu) return bk * 2u;
+        if (e1.x == key && e1.y == len && e1.z != 0xFFFFFFFFu) return bk * 2u + 1u;
+        if (e0.z == 0xFFFFFFFFu || e1.z == 0xFFFFFFFFu) return 0xFFFFFFFFu;  // a free slot on the probe path: not in the table
         bk = bk + 1u == W.n_buckets ? 0u : bk + 1u;
     }
-    return false;
+    return 0xFFFFFFFFu;
+}
+
+// exact comparison of the run hay[s, s + len) with the class string of a table entry, four chars per step (their eight loads
+// are independent: on text full of keywords the one-char-per-step loop was a chain of L2 round trips)
+__device__ __forceinline__ bool ww3_same(const DevWw &W, const uint16_t *hay, const uint32_t *s_tab, uint32_t pool_off, uint32_t len, int64_t s) {
+    const uint16_t *kw = W.pool + pool_off, *h = hay + s;
+    bool same = true;
+    for (uint32_t i = 0; i < len && same; i += 4) {
+        uint32_t k[4], c[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool on = i + j < len;
+            k[j] = on ? (uint32_t)__ldg(kw + i + j) : 0u;
+            c[j] = on ? (uint32_t)__ldg(h + i + j) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) same = same && (i + j >= len || (k[j] + 1u | 0x80000000u) == w3_v(W, s_tab, c[j]));
+    }
+    return same;
 }
 
 // Is the run hay[s, s + len) with key `key` a keyword?  One bucket per step of the probe path; exact comparison of the
@@ -116,10 +143,7 @@ __device__ __forceinline__ bool ww3_lookup(const DevWw &W, const uint16_t *hay, 
         for (int k = 0; k < 2; k++) {
             const uint4 e = k ? e1 : e0;
             if (e.x != key || e.y != len || e.z == 0xFFFFFFFFu) continue;
-            const uint16_t *kw = W.pool + e.z;
-            bool same = true;
-            for (uint32_t i = 0; i < len && same; i++) same = ((uint32_t)__ldg(kw + i) + 1u | 0x80000000u) == w3_v(W, s_tab, __ldg(&hay[s + i]));
-            if (same) {
+            if (ww3_same(W, hay, s_tab, e.z, len, s)) {
                 val = e.w;
                 return true;
             }
@@ -202,27 +226,31 @@ __global__ void __launch_bounds__(kW3Warps * 32, 1) k_ww3_hits(const DevWw W, co
         const bool whole = ctx_base >= 0 && ctx_base + (int64_t)n_chunk_rows * kW3Row <= P.n;   // every load of the chunk lies inside the window
         uint32_t carry_row = 0, prev_bit = 0;
 
-        auto verify = [&](uint32_t count) {   // the first `count` entries of the verify queue, one per lane
+        auto verify = [&](uint32_t count) {   // the first `count` entries of the verify queue {packed, table slot}, one per lane
             if ((uint32_t)lane < count) {
-                const uint2 e = verify_q.q[lane];
-                const uint32_t len = e.y & 0xFFu;
-                uint32_t val;
-                if (ww3_lookup(W, P.hay, s_tab, e.x, len, ctx_base + (int64_t)(e.y >> 8), val)) {
-                    const int64_t rel = (row0 - 1) * kW3Row + (int64_t)((e.y >> 8) + len);   // end of the run, relative to the origin
-                    atomicOr(&P.hitbits[rel >> 5], 1u << (uint32_t)(rel & 31));
-                    atomicAdd(&P.row_count[rel >> 8], 1u);
+                const uint2 q = verify_q.q[lane];
+                const uint32_t len = q.x & 0xFFu;
+                const int64_t s = ctx_base + (int64_t)(q.x >> 8);
+                const uint4 e = __ldg(W.buckets + q.y);   // {key, length, pool offset, value}
+                uint32_t val = e.w;
+                // a tag match that is another string (a 32-bit collision) sends the search down the rest of the probe path
+                if (ww3_same(W, P.hay, s_tab, e.z, len, s) || ww3_lookup(W, P.hay, s_tab, e.x, len, s, val)) {
+                    const int64_t rs = (row0 - 1) * kW3Row + (int64_t)(q.x >> 8), rt = rs + len;   // relative to the origin
+                    atomicOr(&P.startbits[rs >> 5], 1u << (uint32_t)(rs & 31));
+                    atomicOr(&P.hitbits[rt >> 5], 1u << (uint32_t)(rt & 31));
+                    if (P.val_scratch) P.val_scratch[rt >> 1] = val;
                 }
             }
             __syncwarp();
         };
-        auto probe = [&](uint32_t count) {   // the first `count` entries of the probe queue
+        auto probe = [&](uint32_t count) {   // the first `count` entries of the probe queue {key, packed}
             uint2 e = make_uint2(0u, 0u);
-            bool tag = false;
+            uint32_t slot = 0xFFFFFFFFu;
             if ((uint32_t)lane < count) {
                 e = probe_q.q[lane];
-                tag = ww3_tag_probe(W, e.x, e.y & 0xFFu);
+                slot = ww3_tag_probe(W, e.x, e.y & 0xFFu);
             }
-            verify_q.push(tag, e, lt_mask);
+            verify_q.push(slot != 0xFFFFFFFFu, make_uint2(e.y, slot), lt_mask);
             if (verify_q.n >= 32u) {
                 verify(32u);
                 verify_q.pop32(lane);
@@ -381,18 +409,23 @@ __global__ void __launch_bounds__(kW3Warps * 32, 1) k_ww3_hits(const DevWw W, co
     }
 }
 
+// records of a row = set bits of its end bitmap
+__global__ void __launch_bounds__(256) k_ww3_count(const uint32_t *hitbits, uint32_t *row_count, int64_t n_rows) {
+    for (int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x; row < n_rows; row += (int64_t)gridDim.x * 256) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(hitbits + row * 8)), b = __ldg(reinterpret_cast<const uint4 *>(hitbits + row * 8) + 1);
+        row_count[row] = (uint32_t)(__popc(a.x) + __popc(a.y) + __popc(a.z) + __popc(a.w) + __popc(b.x) + __popc(b.y) + __popc(b.z) + __popc(b.w));
+    }
+}
+
 // hit bits -> records.  A warp takes 32 rows at a time (a lane loads one row's 256 hit bits), the rows' hits are numbered
 // by a warp scan, and every lane resolves one hit per step - 32 independent scans back to the word start in flight (one row
 // per warp and one hit per lane-step left the kernel waiting on a single chain of dependent loads: 1.0 ms per 10^9 chars
 // for 2 hits per 1 000 chars).
 template <bool kIsMap>
 __global__ void __launch_bounds__(256) k_ww3_emit(const DevWw W, const Ww3EmitArgs E) {
-    __shared__ uint32_t s_tab[256];
     __shared__ uint32_t s_bits[8][32 * 8 + 4];
     __shared__ uint32_t s_inc[8][32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    s_tab[w3_slot(tid)] = w3_enc(__ldg(&W.wcls[tid]));
-    __syncthreads();
     const int64_t n_groups = (E.n_rows + 31) / 32;
     for (int64_t group = (int64_t)blockIdx.x * 8 + warp; group < n_groups; group += (int64_t)gridDim.x * 8) {
         const int64_t row = group * 32 + lane;
@@ -429,17 +462,15 @@ __global__ void __launch_bounds__(256) k_ww3_emit(const DevWw W, const Ww3EmitAr
             const uint32_t bit = __fns(word, 0u, (int)k + 1);
             const int64_t hit_row = group * 32 + r;
             const int64_t t = E.origin + hit_row * kW3Row + j * 32 + bit;
-            int64_t s = t;
-            while (s > 0 && w3_v(W, s_tab, __ldg(&E.hay[s - 1])) != 0u) --s;   // the run is a keyword: at most max_len steps
+            // the run's start: the last start bit before the end (a keyword run is at most 255 chars: nine words back at most)
+            int64_t rel = t - E.origin - 1, w_at = rel >> 5;
+            uint32_t sw = __ldg(&E.startbits[w_at]) & (0xFFFFFFFFu >> (31u - (uint32_t)(rel & 31)));
+            while (sw == 0u && w_at > 0) sw = __ldg(&E.startbits[--w_at]);
+            const int64_t s = E.origin + w_at * 32 + (31 - __clz((int)sw));
             const unsigned long long idx = __ldg(E.block_excl + (hit_row >> 12)) + __ldg(E.row_excl + hit_row) + (h - (r ? s_inc[warp][r - 1] : 0u));
             if (idx < (unsigned long long)E.cap) {
                 E.pos_out[idx] = make_int2((int32_t)s + E.pos_base, (int32_t)t + E.pos_base);
-                if (kIsMap) {
-                    uint32_t poly = 0, val = kNoneD;
-                    for (int64_t i = s; i < t; i++) poly = poly * kWwPolyB + w3_v(W, s_tab, __ldg(&E.hay[i]));
-                    ww3_lookup(W, E.hay, s_tab, ww_poly_key(poly, (uint32_t)(t - s)), (uint32_t)(t - s), s, val);
-                    E.val_out[idx] = val;
-                }
+                if (kIsMap) E.val_out[idx] = __ldg(&E.val_scratch[(t - E.origin) >> 1]);
             }
         }
         __syncwarp();
